@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""Headline benchmark: agent-trial updates/s of the fitness grid sweep (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--alg positive|td0|negative]
+
+One *step* = one pass of the hot path over one batch: the softmax log-likelihood + value-update sweep of
+this rank's shard of the parameter grid over the session stream, the per-shard arg-min epilogue and the
+all-gather of the per-shard best fits.  Workload at N=1 (``config.workload``): BASELINE.json configs[1]
+-- the 64 x 64 x 32 (alpha, beta, gamma) grid = 131 072 parameter sets over one synthetic 5 000-step
+session on the 9x9 test maze with the 8-action set, max-backup learner (PositiveConditioning, i.e.
+Q-learning on deterministic after-states).  Weak scaling: every rank owns a 131 072-set shard (the gamma
+axis grows with N), no data-path collective besides the 16-byte-per-rank gather.
+
+Printed JSON (rank 0, one line): the base contract keys + ``roofline`` (FP64-issue bound; the peak is a
+DFMA probe kernel timed live because MEASURED_PEAKS.json has no FP64 figure) + ``cpu_baseline`` (the C
+oracle port on the box's host cores, bounded sample) + ``e2e`` (host buffers, H2D/D2H inside the timed
+region) + ``clocks``.  ``--impl reference`` times the CPU port alone, same metric/config.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+T_STEPS = 5000
+GRID = (64, 64, 32)
+CANON_EXP, CANON_LOG = 20, 30  # canonical FP64-instruction accounting of exp / log
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+def make_workload(n_shards):
+    """Synthetic session 0 + the (alpha, beta, gamma) grid; the gamma axis has 32 * n_shards points so that
+    every shard is a full 64 x 64 x 32 block (weak scaling)."""
+    from oracle import np_oracle as O  # seeded session recipe only (inputs, not the measured path)
+    from navigation_model_b200.sweep import parameter_grid
+    omz = O.OracleMaze(O.M9_LAYOUT, O.M9_SIZE_TILE)
+    traj, rew = O.synthetic_session(omz, 0, T_STEPS)
+    alpha_ax = np.linspace(0.01, 1.0, GRID[0])
+    beta_ax = np.logspace(-1.0, 1.5, GRID[1])
+    gamma_ax = np.linspace(0.5, 0.99, GRID[2] * n_shards)
+    # gamma slowest so that a contiguous shard of the flat index is a (gamma-slab x alpha x beta) block
+    g, a, b = parameter_grid(gamma_ax, alpha_ax, beta_ax)
+    return omz, traj, rew, a, b, g
+
+
+def algorithmic_fp64(records, n_online, alg):
+    """Canonical FP64 instructions one parameter set executes over a stream:
+    log-prob 4K + K*exp + log on observed steps, update 5 (+K-1 compares for max/min backups)."""
+    k = records["ncand"].astype(np.int64)
+    obs = (records["obs"] != 0xFF)
+    obs[n_online:] = False
+    ll = np.where(obs, 4 * k + CANON_EXP * k + CANON_LOG, 0)
+    upd = 5 + (np.maximum(k - 1, 0) if alg != "td0" else 0)
+    return int(ll.sum() + np.sum(upd))
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.1):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if mask & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def cpu_port_rate(records_tr, alg_code, a, b, g, seconds, threads=0):
+    """Time the C oracle port on a bounded sample of the same workload.  Returns (updates/s, sample, cores)."""
+    from oracle import c_oracle as CO
+    n = len(records_tr["s"])
+    P = 512
+    t0 = time.perf_counter()
+    CO.fit(alg_code, records_tr, a[:P], g[:P], 60, beta=b[:P], want_v=False, threads=threads)
+    dt = max(time.perf_counter() - t0, 1e-6)
+    P = int(min(len(a), max(P, P * seconds / dt)))
+    P = max(512, (P // 512) * 512)
+    idx = np.linspace(0, len(a) - 1, P).astype(np.int64)  # spread over the whole grid
+    t0 = time.perf_counter()
+    CO.fit(alg_code, records_tr, a[idx], g[idx], 60, beta=b[idx], want_v=False, threads=threads)
+    dt = time.perf_counter() - t0
+    cores = CO.max_threads() if threads <= 0 else threads
+    return P * n / dt, f"{P} of {len(a)} parameter sets (evenly spaced over the grid) x {n} steps, {dt:.1f} s", cores
+
+
+def run_reference(args):
+    """--impl reference: the CPU port of the path (oracle/nm_oracle.c, OpenMP over parameter sets) on the
+    box's host cores; each step is a bounded sample of the workload."""
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    from oracle import np_oracle as O
+    from oracle import c_oracle as CO
+    alg_code = {"td0": 0, "positive": 1, "negative": 2}[args.alg]
+    omz, traj, rew, a, b, g = make_workload(1)
+    tr = O.extract_transitions(omz, traj, rew, O.OracleMouse(traj[0], 0.0, O.A8_UNITS * O.M9_SIZE_TILE))
+    n = len(tr["s"])
+    P_s = 4096
+    idx = np.linspace(0, len(a) - 1, P_s).astype(np.int64)
+    for _ in range(args.warmup):
+        CO.fit(alg_code, tr, a[idx], g[idx], 60, beta=b[idx], want_v=False)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        CO.fit(alg_code, tr, a[idx], g[idx], 60, beta=b[idx], want_v=False)
+    dt = time.perf_counter() - t0
+    value = P_s * n * args.steps / dt
+    cores = CO.max_threads()
+    line = {"impl": "reference", "metric": "agent-trial updates/s (fitness grid sweep)", "value": value,
+            "unit": "updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, 1, P_s),
+            "cpu_baseline": {"value": value, "unit": "updates/s", "cores": cores, "kind": "port",
+                             "sample": f"{P_s} of {len(a)} parameter sets (evenly spaced) x {n} steps per step"},
+            "e2e": {"value": value, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(args, n_gpus, p_per_rank):
+    return {"workload": "BASELINE configs[1]: Q-learning (max-backup PositiveConditioning) fitness grid sweep "
+                        "64x64x32 (alpha,beta,gamma) over one synthetic 5000-step session, 9x9 maze, 8 actions"
+                        if args.alg == "positive" else f"configs[1] grid sweep with {args.alg}",
+            "algorithm": args.alg, "parameter_sets_per_gpu": int(p_per_rank), "sessions": 1, "steps_per_session": T_STEPS,
+            "sharding": f"parameter grid, {n_gpus} contiguous shard(s); all-gather of 16 B/rank best fits",
+            "l2": "flushed between timed steps (256 MiB memset, untimed)"}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from navigation_model_b200 import _native
+    from navigation_model_b200.simulation.maze import Maze
+    from navigation_model_b200.sweep import ConditioningSweep, reduce_best, shard_bounds
+    from oracle import np_oracle as O
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    _native.require_device()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    omz, traj, rew, a_all, b_all, g_all = make_workload(world)
+    lo, hi = shard_bounds(len(a_all), rank, world)
+    a, b, g = a_all[lo:hi], b_all[lo:hi], g_all[lo:hi]
+    P = hi - lo
+    maze = Maze(O.M9_LAYOUT, O.M9_SUBAREAS, size_tile=O.M9_SIZE_TILE)
+    sw = ConditioningSweep(maze, args.alg, possible_actions=O.A8_UNITS * O.M9_SIZE_TILE, device=local)
+    sw.add_session(traj, rew)
+    records = sw._records[0]
+    n_upd = sw.updates_per_parameter_set
+    h2d_stream_bytes = sw.upload()
+
+    # resident device inputs / outputs
+    a_t, b_t, g_t = (torch.from_numpy(x).to(dev) for x in (a, b, g))
+    ll_t = torch.empty((1, P), dtype=torch.float64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        sw.log_likelihood_device(a_t, b_t, g_t, ll_out=ll_t)
+        best = sw.argmin_device(ll_t)
+        return reduce_best_device(best, lo, world, dist)
+
+    def reduce_best_device(best, offset, world, dist):
+        if world > 1:
+            gathered = torch.empty(world * 2, dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(gathered, best)
+            return gathered
+        return best
+
+    # ---- value: inputs resident in HBM, per-step CUDA events on the launching stream ---------------------
+    for _ in range(args.warmup):
+        flush.zero_()
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
+           torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()
+        ev[i][0].record(stream)
+        sw.log_likelihood_device(a_t, b_t, g_t, ll_out=ll_t)
+        ev[i][1].record(stream)  # end of the dominant kernel
+        best = sw.argmin_device(ll_t)
+        reduce_best_device(best, lo, world, dist)
+        ev[i][2].record(stream)
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    step_ms = np.array([e[0].elapsed_time(e[2]) for e in ev])
+    kern_ms = np.array([e[0].elapsed_time(e[1]) for e in ev])
+    total_ms = torch.tensor([step_ms.sum()], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_s = float(total_ms.item()) * 1e-3
+    units = float(world) * P * n_upd * args.steps
+    value = units / total_s
+
+    # ---- e2e: host buffers, H2D / D2H inside the timed region, through the public API ---------------------
+    pin = [torch.from_numpy(x).pin_memory() for x in (a, b, g)]
+    ll_host = torch.empty((1, P), dtype=torch.float64).pin_memory()
+    best_host = torch.empty(2 * world, dtype=torch.float64).pin_memory()
+
+    def step_e2e():
+        nbytes = sw.upload()  # session stream: pinned host -> HBM (nm_streams_upload)
+        for dst, src in zip((a_t, b_t, g_t), pin):
+            dst.copy_(src, non_blocking=True)
+        sw.log_likelihood_device(a_t, b_t, g_t, ll_out=ll_t)
+        best = sw.argmin_device(ll_t)
+        out = reduce_best_device(best, lo, world, dist)
+        ll_host.copy_(ll_t, non_blocking=True)
+        best_host[: out.numel()].copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return nbytes
+
+    for _ in range(max(1, args.warmup)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        h2d_stream_bytes = step_e2e()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = units / float(e2e_s.item())
+    h2d = int(h2d_stream_bytes + 3 * P * 8)
+    d2h = int(P * 8 + 16 * world)
+
+    if rank == 0:
+        # ---- roofline: FP64 issue; peak measured live with the DFMA probe (burst, kernel timed alone) -------
+        sink = torch.zeros(1, dtype=torch.float64, device=dev)
+        lib = _native.lib()
+        import ctypes as C
+        n_instr = C.c_int64(0)
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        probe_ms = []
+        for it in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            _native.check(lib.nm_fp64_peak_probe(sms * 4, 512, 20000, _native.tensor_ptr(sink), C.byref(n_instr),
+                                                 _native.cuda_stream_ptr()))
+            e1.record(stream)
+            torch.cuda.synchronize()
+            if it:
+                probe_ms.append(e0.elapsed_time(e1))
+        peak_ginstr = n_instr.value / (min(probe_ms) * 1e-3) / 1e9
+        alg_instr = algorithmic_fp64(records, sw._online[0], args.alg) * P
+        achieved = alg_instr / (kern_ms.mean() * 1e-3) / 1e9
+        roofline = {"bound": "fp64_issue", "achieved": achieved, "peak": peak_ginstr, "unit": "GInstr/s",
+                    "frac": achieved / peak_ginstr, "traffic": None,
+                    "kernel": "nm_fit_kernel<positive,loglik>" if args.alg == "positive" else f"nm_fit_kernel<{args.alg}>",
+                    "kernel_ms": float(kern_ms.mean()),
+                    "peak_source": "nm_fp64_peak_probe (8 independent DFMA chains/thread) timed live, burst",
+                    "alg_fp64_instr_per_update": alg_instr / (P * n_upd),
+                    "hbm_gbs_achieved": (n_upd * 32 + P * 32) / (kern_ms.mean() * 1e-3) / 1e9}
+        # ---- cpu_baseline: the C oracle port on this box's host cores ---------------------------------------
+        tr = O.extract_transitions(omz, traj, rew, O.OracleMouse(traj[0], 0.0, O.A8_UNITS * O.M9_SIZE_TILE))
+        alg_code = {"td0": 0, "positive": 1, "negative": 2}[args.alg]
+        cpu_val, cpu_sample, cores = cpu_port_rate(tr, alg_code, a, b, g, seconds=args.cpu_seconds)
+        line = {"metric": "agent-trial updates/s (fitness grid sweep)", "value": value, "unit": "updates/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(args, world, P),
+                "roofline": roofline,
+                "cpu_baseline": {"value": cpu_val, "unit": "updates/s", "cores": cores, "kind": "port",
+                                 "sample": cpu_sample},
+                "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": 3 * args.steps, "clocks": clocks, "wall_s": wall,
+                "target_updates_per_s_8gpu": 1e10}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--alg", default="positive", choices=["positive", "td0", "negative"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,185 @@
+/*
+ * navmodel_b200.h -- C-ABI of the B200-native hot path of elimas9/navigation_model.
+ *
+ * One shared library (navigation_model_b200/libnavmodel_b200.so, built by __graft_entry__.build()
+ * with nvcc for sm_100a) exports exactly the entry points below.  Plain pointers and sizes only: no
+ * torch / pybind11 / Eigen types.  The Python host layer binds them with ctypes
+ * (navigation_model_b200/_native.py); INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns int: 0 (or a non-negative count/flag) on success, < 0 on error
+ *     (NM_ERR_*); the message is available from nm_last_error() (thread-local).
+ *   - pointers prefixed d_ are DEVICE pointers owned by the caller (torch tensors used as buffers);
+ *     h_ are HOST pointers.  The library never frees caller memory.  Handles (nm_maze, nm_streams,
+ *     nm_mouse) own what they allocate and are released with nm_*_free.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Calls are
+ *     asynchronous with respect to the host unless stated; re-entrant per (device, stream).
+ *   - there is NO CPU fallback: compute entry points fail with NM_ERR_CUDA when no device is usable.
+ *
+ * Reference interfaces replaced (paths relative to the reference repo root):
+ *   nm_mouse_*        src/_navigation_model/bindings.cpp:11-62, mouse.cpp:5-92, mouse.hpp:12-45
+ *                     (the reference's only native component; consumed at simulation/mouse.py:7-12)
+ *   nm_maze_*         simulation/maze.py:107-122 (dense tables of the list-of-lists layout), :380-395,
+ *                     :488-501
+ *   nm_stream_build   simulation/rl.py:85-102 (ConditioningExperiment.run transition extraction),
+ *                     :177-182,189 (PositiveConditioning candidate next states), :419-424 (replays)
+ *   nm_vtable_sweep   simulation/rl.py:72-117 ConditioningExperiment.run + RLAlgorithm.update
+ *                     (:176-194, :219-237, :256-262) + ShuffledReplays.offline_replays (:419-424),
+ *                     batched over a parameter grid
+ *   nm_loglik_sweep   the same recurrence + softmax log-probability of the observed choice built
+ *                     from simulation/exploration_model.py:84-93 (extension: the reference has no
+ *                     likelihood; see DESIGN.md "parity unpinned")
+ *   nm_argmin_nll     new (grid-sweep epilogue; per-shard best fit fed to the NCCL all-gather)
+ *   nm_simulate       simulation/experiment.py:23-51 StandardExperiment.run, with
+ *                     exploration_model.py:68-109, behavioural_components.py:315-544, maze.py:563-627,
+ *                     mouse.cpp:64-87 and analysis/metrics.py:192-248,425-442,697-731 fused
+ */
+#ifndef NAVMODEL_B200_H
+#define NAVMODEL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NM_ABI_VERSION 1
+
+/* error codes */
+#define NM_OK 0
+#define NM_ERR_INVALID (-1)  /* bad argument (shape, range, NULL)        -> Python ValueError   */
+#define NM_ERR_RUNTIME (-2)  /* reference-style RuntimeError condition   -> Python RuntimeError */
+#define NM_ERR_CUDA (-3)     /* CUDA runtime / launch failure, no device -> Python RuntimeError */
+#define NM_ERR_NOMEM (-4)    /* host or device allocation failed         -> Python MemoryError  */
+
+/* value-learning algorithms (simulation/rl.py:154-262) */
+#define NM_ALG_TD0 0      /* rpe = r + g*V[s1] - V[s]                  rl.py:257-259 */
+#define NM_ALG_POSITIVE 1 /* rpe = r + g*max_k V[cand_k] - V[s]        rl.py:184-187 */
+#define NM_ALG_NEGATIVE 2 /* rpe = r + g*min_k V[cand_k] - V[s]        rl.py:227-230 */
+
+#define NM_MAX_CAND 8    /* max candidate next states per step (= max number of relative actions) */
+#define NM_OBS_NONE 0xFF /* nm_step_rec.obs when the arrival tile is not among the candidates */
+
+int nm_version(void);
+const char *nm_last_error(void);
+/* number of usable CUDA devices (0 when there is none); never fails */
+int nm_device_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Mouse: pose + action endpoints (host object; replaces the pybind11 module `_navigation_model`)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct nm_mouse nm_mouse;
+
+/* actions: row-major [n_actions, n_cols]; n_cols must be 2 when n_actions > 0 (mouse.cpp:5-9 raises
+ * ValueError otherwise -> NULL is returned and nm_last_error() is set). */
+nm_mouse *nm_mouse_create(const double *init_pos, double init_ori, const double *actions, int n_actions,
+                          int n_cols, int save_history);
+void nm_mouse_free(nm_mouse *m);
+/* out[6] = {pos.x, pos.y, ori, init_pos.x, init_pos.y, init_ori} */
+int nm_mouse_state(const nm_mouse *m, double *out6);
+int nm_mouse_num_actions(const nm_mouse *m);
+/* out: row-major [n_actions, 2]; R(ori) * a_i + pos  (mouse.cpp:64-73) */
+int nm_mouse_endpoints(const nm_mouse *m, double *out);
+/* returns 1 if the mouse moved, 0 if new_pos isApprox(pos)  (mouse.cpp:75-87) */
+int nm_mouse_move_to(nm_mouse *m, double x, double y);
+int nm_mouse_enable_history(nm_mouse *m, int enable);
+int nm_mouse_reset_history(nm_mouse *m);
+/* init_pos / init_ori may be NULL (= keep)  (mouse.cpp:43-53) */
+int nm_mouse_reset(nm_mouse *m, const double *init_pos, const double *init_ori);
+int64_t nm_mouse_history_len(const nm_mouse *m);
+/* pos_out: [len, 2], ori_out: [len] */
+int nm_mouse_history(const nm_mouse *m, double *pos_out, double *ori_out);
+
+/* ------------------------------------------------------------------------------------------------
+ * Maze: dense tile tables resident on the device
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct nm_maze nm_maze;
+
+/* h_tiles: u8[X*Y], x-major (index = x*Y + y, x = text row; maze.py:126-143, 266-276); a tile is
+ * visitable iff its code != 0 (VOID; maze.py:56-57, 99-100).  h_subareas: u8[X*Y] or NULL.
+ * device < 0 builds a host-only handle (usable by nm_stream_build and the nm_maze_* queries). */
+nm_maze *nm_maze_upload(const uint8_t *h_tiles, const uint8_t *h_subareas, int X, int Y, double size_tile,
+                        int device, void *stream);
+void nm_maze_free(nm_maze *mz);
+/* number of visitable tiles = number of compact states */
+int nm_maze_num_states(const nm_maze *mz);
+/* int(x // size_tile), int(y // size_tile) with Python float floor-division (maze.py:393-394) */
+int nm_maze_cont2disc(const nm_maze *mz, double x, double y, int *dx, int *dy);
+/* ray / AABB segment test (maze.py:563-611): 1 possible, 0 not */
+int nm_maze_movement_possible_cont(const nm_maze *mz, double x1, double y1, double x2, double y2);
+/* closest visitable tile (maze.py:469-484) */
+int nm_maze_closest_visitable_cont(const nm_maze *mz, double x, double y, int *dx, int *dy);
+
+/* ------------------------------------------------------------------------------------------------
+ * Step streams: the parameter-independent part of a conditioning session
+ * ---------------------------------------------------------------------------------------------- */
+/* One transition (rl.py:12-24 `Transition`, flattened).  32 bytes, 16-byte aligned.  State ids are
+ * COMPACT ids of visitable tiles in x-major order (0 .. num_states-1). */
+typedef struct nm_step_rec {
+  double r;                    /* reward[i]                                      rl.py:95       */
+  uint16_t s;                  /* start state                                    rl.py:87,102   */
+  uint16_t s1;                 /* arrival state                                  rl.py:94       */
+  uint8_t ncand;               /* K = len(next_states), 0..NM_MAX_CAND           rl.py:182      */
+  uint8_t obs;                 /* first k with cand[k] == s1, else NM_OBS_NONE   (extension)    */
+  uint16_t reserved;
+  uint16_t cand[NM_MAX_CAND];  /* next_states in action order (unused slots = 0) rl.py:177-182  */
+} nm_step_rec;
+
+/* Build the T-1 online records of one session on the HOST (native C++, no GPU needed).
+ *   trajectory [T,2], reward [T] (reward[0] unused, rl.py:95).
+ *   mouse: the algorithm's own Mouse (rl.py:173); it is driven exactly like the reference drives it
+ *   (move_to(start), endpoints, move_to(arrival) per transition, rl.py:178-189 -- history included) and
+ *   is left at the final pose.  NULL skips the endpoint geometry (TD0 without likelihood): ncand = 0,
+ *   obs = NM_OBS_NONE.
+ * Returns the number of records written (T-1), or < 0.  A step with zero candidates is an error when
+ * a mouse is given (the reference raises from np.max([]), rl.py:184). */
+int64_t nm_stream_build(const nm_maze *mz, const double *trajectory, const double *reward, int64_t T,
+                        nm_mouse *mouse, nm_step_rec *out);
+
+typedef struct nm_streams nm_streams;
+
+/* Upload S concatenated session streams.  Session j owns records [h_offsets[j], h_offsets[j+1]);
+ * its first h_online[j] records are the observed (online) transitions, the remaining ones are the
+ * shuffled-replay passes in execution order (rl.py:419-424) and update V only.
+ * Copies are enqueued on `stream` from the (ideally pinned) host buffers, which must stay valid until
+ * the stream has been synchronised. */
+nm_streams *nm_streams_upload(const nm_step_rec *h_records, const int64_t *h_offsets, const int64_t *h_online,
+                              int S, int num_states, int device, void *stream);
+void nm_streams_free(nm_streams *st);
+
+/* ------------------------------------------------------------------------------------------------
+ * Parameter-grid sweeps (one thread = one parameter set; V-table resident in shared memory)
+ * ---------------------------------------------------------------------------------------------- */
+/* V-table learning over P parameter sets x S sessions (each session starts from v_init).
+ *   d_alpha, d_gamma: [P]
+ *   d_v_init: NULL (zeros, rl.py:66) | [X*Y] shared (v_init_per_unit = 0) | [P, X*Y] (= 1)  rl.py:63-64
+ *   d_v_out:  [S, P, X*Y] dense tables (non-visitable tiles keep their v_init value)
+ */
+int nm_vtable_sweep(int alg, const nm_maze *mz, const nm_streams *st, const double *d_alpha,
+                    const double *d_gamma, int64_t P, const double *d_v_init, int v_init_per_unit,
+                    double *d_v_out, void *stream);
+
+/* Same recurrence + log-likelihood of the observed choices under the softmax policy
+ * p_k = softmax_k(beta * V[cand_k]) (exploration_model.py:84-93), evaluated BEFORE the update of the
+ * step, accumulated in FP64 in step order over the online records whose obs != NM_OBS_NONE.
+ *   d_ll_out: [S, P];  d_v_out: [S, P, X*Y] or NULL.
+ */
+int nm_loglik_sweep(int alg, const nm_maze *mz, const nm_streams *st, const double *d_alpha,
+                    const double *d_beta, const double *d_gamma, int64_t P, const double *d_v_init,
+                    int v_init_per_unit, double *d_ll_out, double *d_v_out, void *stream);
+
+/* Per-shard best fit: nll[p] = -(sum_s ll[s, p]) (sessions added in index order), then the minimum and
+ * the LOWEST index attaining it (numpy argmin).  NaN entries are skipped; if all are NaN idx = -1.
+ *   d_nll_out: [P] or NULL;  d_best_out: {double best_nll; int64 best_idx} (16 bytes, device).
+ */
+int nm_argmin_nll(const double *d_ll, int S, int64_t P, double *d_nll_out, void *d_best_out, void *stream);
+
+/* FP64 issue-rate micro-benchmark used for the roofline denominator: every thread runs `iters`
+ * iterations of 8 independent DFMA chains; returns the instruction count via *h_fp64_instr.
+ * Launches on `stream`; the caller times it with CUDA events. */
+int nm_fp64_peak_probe(int blocks, int threads, int iters, double *d_sink, int64_t *h_fp64_instr, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NAVMODEL_B200_H */

@@ -1,0 +1,137 @@
+"""ctypes binding of ``libnavmodel_b200.so`` (the C-ABI declared in ``include/navmodel_b200.h``).
+
+There is no CPU fallback: if the library is missing, :func:`lib` raises; compute entry points raise
+``RuntimeError`` when no CUDA device is usable.  Error codes are translated to the exception types the
+reference raises for the same condition (``ValueError`` / ``RuntimeError``).
+"""
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+from . import _build
+
+NM_MAX_CAND = 8
+NM_OBS_NONE = 0xFF
+ALG_TD0, ALG_POSITIVE, ALG_NEGATIVE = 0, 1, 2
+
+#: numpy view of ``nm_step_rec`` (32 bytes)
+STEP_REC_DTYPE = np.dtype([("r", "<f8"), ("s", "<u2"), ("s1", "<u2"), ("ncand", "u1"), ("obs", "u1"),
+                           ("reserved", "<u2"), ("cand", "<u2", (NM_MAX_CAND,))], align=False)
+assert STEP_REC_DTYPE.itemsize == 32
+
+_p = C.c_void_p
+_dp = C.POINTER(C.c_double)
+_i64 = C.c_int64
+
+#: name -> (restype, argtypes); every symbol declared in include/navmodel_b200.h
+SIGNATURES = {
+    "nm_version": (C.c_int, []),
+    "nm_last_error": (C.c_char_p, []),
+    "nm_device_count": (C.c_int, []),
+    "nm_mouse_create": (_p, [_p, C.c_double, _p, C.c_int, C.c_int, C.c_int]),
+    "nm_mouse_free": (None, [_p]),
+    "nm_mouse_state": (C.c_int, [_p, _p]),
+    "nm_mouse_num_actions": (C.c_int, [_p]),
+    "nm_mouse_endpoints": (C.c_int, [_p, _p]),
+    "nm_mouse_move_to": (C.c_int, [_p, C.c_double, C.c_double]),
+    "nm_mouse_enable_history": (C.c_int, [_p, C.c_int]),
+    "nm_mouse_reset_history": (C.c_int, [_p]),
+    "nm_mouse_reset": (C.c_int, [_p, _p, _p]),
+    "nm_mouse_history_len": (_i64, [_p]),
+    "nm_mouse_history": (C.c_int, [_p, _p, _p]),
+    "nm_maze_upload": (_p, [_p, _p, C.c_int, C.c_int, C.c_double, C.c_int, _p]),
+    "nm_maze_free": (None, [_p]),
+    "nm_maze_num_states": (C.c_int, [_p]),
+    "nm_maze_cont2disc": (C.c_int, [_p, C.c_double, C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "nm_maze_movement_possible_cont": (C.c_int, [_p, C.c_double, C.c_double, C.c_double, C.c_double]),
+    "nm_maze_closest_visitable_cont": (C.c_int, [_p, C.c_double, C.c_double, C.POINTER(C.c_int),
+                                                 C.POINTER(C.c_int)]),
+    "nm_stream_build": (_i64, [_p, _p, _p, _i64, _p, _p]),
+    "nm_streams_upload": (_p, [_p, _p, _p, C.c_int, C.c_int, C.c_int, _p]),
+    "nm_streams_free": (None, [_p]),
+    "nm_vtable_sweep": (C.c_int, [C.c_int, _p, _p, _p, _p, _i64, _p, C.c_int, _p, _p]),
+    "nm_loglik_sweep": (C.c_int, [C.c_int, _p, _p, _p, _p, _p, _i64, _p, C.c_int, _p, _p, _p]),
+    "nm_argmin_nll": (C.c_int, [_p, C.c_int, _i64, _p, _p, _p]),
+    "nm_fp64_peak_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, _p, C.POINTER(_i64), _p]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+def library_path():
+    return _build.LIB_PATH
+
+
+def lib():
+    """Load (once) and return the ctypes library.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            path = library_path()
+            if not os.path.exists(path):
+                raise RuntimeError(
+                    f"{path} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                    "(navigation_model_b200 has no CPU fallback)")
+            handle = C.CDLL(path)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(handle, name)  # AttributeError if the .so lacks a declared symbol
+                fn.restype = res
+                fn.argtypes = args
+            _lib = handle
+    return _lib
+
+
+def last_error():
+    msg = lib().nm_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+_EXC = {-1: ValueError, -2: RuntimeError, -3: RuntimeError, -4: MemoryError}
+
+
+def check(rc):
+    """Raise the exception matching a negative return code; pass non-negative values through."""
+    if rc is None or rc >= 0:
+        return rc
+    raise _EXC.get(int(rc), RuntimeError)(last_error())
+
+
+def check_handle(h):
+    if not h:
+        msg = last_error()
+        raise (ValueError if "must have shape" in msg or "bad argument" in msg or "need " in msg else RuntimeError)(msg)
+    return h
+
+
+def device_count():
+    return int(lib().nm_device_count())
+
+
+def require_device():
+    if device_count() <= 0:
+        raise RuntimeError("navigation_model_b200: no usable CUDA device (there is no CPU fallback)")
+
+
+def np_ptr(a):
+    """Raw pointer of a C-contiguous numpy array (the array must outlive the call)."""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def cuda_stream_ptr(stream=None):
+    """``cudaStream_t`` (as int) of a torch stream, or of torch's current stream."""
+    import torch
+    if stream is None:
+        stream = torch.cuda.current_stream()
+    return C.c_void_p(stream.cuda_stream)
+
+
+def tensor_ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())

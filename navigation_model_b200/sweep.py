@@ -1,0 +1,490 @@
+"""Batched (parameter-grid) value learning and log-likelihood fitting on the GPU.
+
+This is the host layer above the C-ABI for the fitness hot path:
+
+* :func:`build_session_records` -- flatten one session into the parameter-independent step stream
+  (native ``nm_stream_build``; restates ``ConditioningExperiment.run`` ``rl.py:85-102`` and the
+  candidate computation of ``PositiveConditioning`` ``rl.py:177-182``);
+* :class:`DeviceMaze`, :class:`DeviceStreams` -- handles of the tables resident in HBM;
+* :class:`ConditioningSweep` -- the grid version of ``ConditioningExperiment``: V-tables and per-session
+  log-likelihoods for ``P`` parameter sets x ``S`` sessions in one kernel launch, per-shard arg-min and
+  the (tiny) cross-GPU gather of the best fits (``torch.distributed``; NCCL over NVLink on the GPU box).
+
+PyTorch is used only for device buffers, streams and the process group.  There is no CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native
+from .simulation.maze import Maze
+from .simulation.mouse import Mouse
+
+ALGORITHMS = {"td0": _native.ALG_TD0, "positive": _native.ALG_POSITIVE, "negative": _native.ALG_NEGATIVE,
+              "qlearning": _native.ALG_POSITIVE}  # max-backup on deterministic after-states == Q-learning
+
+
+def algorithm_code(alg):
+    """Accept a name, an ``NM_ALG_*`` code, or a reference-style algorithm class / instance."""
+    if isinstance(alg, str):
+        return ALGORITHMS[alg.lower()]
+    if isinstance(alg, (int, np.integer)):
+        if int(alg) not in (0, 1, 2):
+            raise ValueError(f"unknown algorithm code {alg}")
+        return int(alg)
+    kind = getattr(alg, "device_kind", None)
+    if kind is None:
+        raise ValueError(f"{alg!r} has no device implementation")
+    return kind
+
+
+# ----------------------------------------------------------------------------------- host handles
+class HostMaze:
+    """Host-only ``nm_maze`` handle (geometry queries + stream building; no GPU needed)."""
+
+    def __init__(self, maze, device=-1, stream=None):
+        if not isinstance(maze, Maze):
+            raise TypeError("expected a navigation_model_b200 Maze")
+        self.maze = maze
+        tabs = maze.flat_tables()
+        self.tables = tabs
+        self.n_tiles = maze.size_x * maze.size_y
+        self._lib = _native.lib()
+        tiles = np.ascontiguousarray(tabs["tiles"])
+        sub = None if tabs["subareas"] is None else np.ascontiguousarray(tabs["subareas"])
+        self.device = device
+        self._h = _native.check_handle(self._lib.nm_maze_upload(
+            _native.np_ptr(tiles), _native.np_ptr(sub), maze.size_x, maze.size_y, float(maze.size_tile), int(device),
+            stream))
+        self.num_states = int(self._lib.nm_maze_num_states(self._h))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def close(self):
+        h, self._h = self._h, None
+        if h:
+            self._lib.nm_maze_free(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_host_maze_cache = {}
+
+
+def host_maze(maze):
+    key = id(maze)
+    hm = _host_maze_cache.get(key)
+    if hm is None or hm.maze is not maze:
+        hm = HostMaze(maze)
+        _host_maze_cache[key] = hm
+    return hm
+
+
+class DeviceMaze(HostMaze):
+    """``nm_maze`` handle with the dense tables uploaded to HBM on ``device``."""
+
+    def __init__(self, maze, device=None):
+        import torch
+        _native.require_device()
+        if device is None:
+            device = torch.cuda.current_device()
+        self.torch_device = torch.device("cuda", int(device))
+        with torch.cuda.device(self.torch_device):
+            super().__init__(maze, device=int(device), stream=_native.cuda_stream_ptr())
+
+
+def build_session_records(maze, trajectory, reward, mouse=None, orientations=None, make_transitions=False):
+    """Flatten one session into ``nm_step_rec`` records (numpy structured array, ``T-1`` entries).
+
+    :param mouse: the algorithm's own :class:`Mouse` (``PositiveConditioning(..., mouse, maze)``); it is
+        driven through the session exactly as the reference drives it.  ``None``: no candidates (TD0
+        value learning only -- a likelihood needs candidates).
+    :param make_transitions: also return reference-style ``Transition`` objects for the replay buffer
+    """
+    from .simulation.rl import Transition
+    lib = _native.lib()
+    hm = host_maze(maze)
+    traj = np.ascontiguousarray(np.asarray(trajectory, dtype=np.float64).reshape(-1, 2))
+    rew = np.ascontiguousarray(np.asarray(reward, dtype=np.float64).reshape(-1))
+    if len(traj) != len(rew):
+        raise RuntimeError("trajectory and reward must have the same length")
+    T = len(traj)
+    recs = np.zeros(max(T - 1, 0), dtype=_native.STEP_REC_DTYPE)
+    if T >= 1:
+        mh = None if mouse is None else mouse._h
+        n = _native.check(lib.nm_stream_build(hm.handle, _native.np_ptr(traj), _native.np_ptr(rew), T, mh,
+                                              _native.np_ptr(recs) if T > 1 else None))
+        assert n == T - 1
+    if not make_transitions:
+        return recs
+    tos = hm.tables["tile_of_state"]
+    Y = maze.size_y
+    cells = [(int(t) // Y, int(t) % Y) for t in tos]
+    trans = []
+    for i, rec in enumerate(recs):
+        t = Transition(cs=traj[i], ori=None if orientations is None else orientations[i], s=cells[rec["s"]],
+                       cs1=traj[i + 1], ori1=None if orientations is None else orientations[i + 1],
+                       s1=cells[rec["s1"]], r=rew[i + 1])
+        if mouse is not None:
+            t.extra["next_states"] = [cells[c] for c in rec["cand"][:rec["ncand"]]]
+        t.extra["_rec"] = rec
+        trans.append(t)
+    return recs, trans
+
+
+def record_from_transition(maze, t):
+    """``nm_step_rec`` of a reference-style ``Transition`` (uses ``extra['next_states']`` if present)."""
+    rec = t.extra.get("_rec")
+    if rec is not None:
+        return rec
+    sot = host_maze(maze).tables["state_of_tile"]
+    Y = maze.size_y
+    out = np.zeros((), dtype=_native.STEP_REC_DTYPE)
+    out["r"] = t.r
+    out["s"] = sot[t.s[0] * Y + t.s[1]]
+    out["s1"] = sot[t.s1[0] * Y + t.s1[1]]
+    out["obs"] = _native.NM_OBS_NONE
+    ns = t.extra.get("next_states", [])
+    if len(ns) > _native.NM_MAX_CAND:
+        raise ValueError(f"at most {_native.NM_MAX_CAND} candidate next states are supported")
+    out["ncand"] = len(ns)
+    for k, c in enumerate(ns):
+        out["cand"][k] = sot[c[0] * Y + c[1]]
+        if out["obs"] == _native.NM_OBS_NONE and out["cand"][k] == out["s1"]:
+            out["obs"] = k
+    return out
+
+
+def replay_records(records, n_times, seed=None, rng=None):
+    """Records of ``n_times`` shuffled replay passes over ``records`` in execution order
+    (``ShuffledReplays.offline_replays``, ``rl.py:419-424``: cumulative in-place ``Generator.shuffle``)."""
+    if rng is None:
+        rng = np.random.default_rng(seed)
+    idx = np.arange(len(records))
+    out = []
+    for _ in range(int(n_times)):
+        rng.shuffle(idx)
+        out.append(records[idx])
+    if not out:
+        return records[:0]
+    return np.concatenate(out)
+
+
+class DeviceStreams:
+    """``S`` session streams resident in HBM (``nm_streams`` handle)."""
+
+    def __init__(self, dmaze, sessions, online=None, pinned=True, staging=None):
+        """
+        :param sessions: list of record arrays (online records followed by replay records)
+        :param online: per session, the number of leading online records (default: all)
+        :param staging: pinned uint8 tensor already holding the concatenated records (re-upload path)
+        """
+        import torch
+        self.dmaze = dmaze
+        self._lib = _native.lib()
+        if len(sessions) == 0:
+            raise ValueError("need at least one session")
+        lens = np.array([len(s) for s in sessions], dtype=np.int64)
+        self.offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        self.online = lens.copy() if online is None else np.asarray(online, dtype=np.int64).copy()
+        self.S = len(sessions)
+        self.total = int(self.offsets[-1])
+        if staging is None:
+            sessions = [np.ascontiguousarray(s, dtype=_native.STEP_REC_DTYPE) for s in sessions]
+            flat = np.concatenate(sessions) if self.total else np.zeros(0, dtype=_native.STEP_REC_DTYPE)
+            staging = torch.from_numpy(flat.view(np.uint8).reshape(-1).copy())
+            if pinned and self.total:
+                staging = staging.pin_memory()
+        # pinned staging buffer: kept alive by this object; the copy is enqueued and synchronised below
+        self._host = staging
+        with torch.cuda.device(dmaze.torch_device):
+            self._h = _native.check_handle(self._lib.nm_streams_upload(
+                C.c_void_p(self._host.data_ptr()), _native.np_ptr(self.offsets), _native.np_ptr(self.online), self.S,
+                dmaze.num_states, dmaze.device, _native.cuda_stream_ptr()))
+            torch.cuda.current_stream().synchronize()
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def host_bytes(self):
+        return int(self._host.numel())
+
+    def close(self):
+        h, self._h = self._h, None
+        if h:
+            self._lib.nm_streams_free(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _as_param(x, P=None):
+    a = np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1))
+    if P is not None and a.size == 1 and P != 1:
+        a = np.full(P, a[0])
+    return a
+
+
+def parameter_grid(*axes):
+    """Cartesian product of 1-D axes -> tuple of flat ``float64[P]`` arrays (first axis slowest)."""
+    mesh = np.meshgrid(*[np.asarray(a, dtype=np.float64) for a in axes], indexing="ij")
+    return tuple(np.ascontiguousarray(m.reshape(-1)) for m in mesh)
+
+
+def shard_bounds(P, rank, world):
+    """Contiguous block ``[lo, hi)`` of the flat parameter index owned by ``rank``."""
+    base, rem = divmod(int(P), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class ConditioningSweep:
+    """Grid version of ``ConditioningExperiment``: many parameter sets x many sessions on one GPU.
+
+    >>> sw = ConditioningSweep(maze, "positive", possible_actions=A8)
+    >>> sw.add_session(trajectory, reward)            # any number of sessions
+    >>> ll = sw.log_likelihood(alpha, beta, gamma)    # float64[S, P]
+    """
+
+    def __init__(self, maze, algorithm="td0", possible_actions=None, mouse_init=None, replay_n_times=0,
+                 replay_seed=None, device=None):
+        self.maze = maze
+        self.alg = algorithm_code(algorithm)
+        self.possible_actions = None if possible_actions is None else np.asarray(possible_actions, dtype=np.float64)
+        self.mouse_init = mouse_init  # (x, y, ori) or None -> first trajectory point, orientation 0
+        self.replay_n_times = int(replay_n_times)
+        self.replay_seed = replay_seed
+        self._device = device
+        self._records = []
+        self._online = []
+        self._dmaze = None
+        self._dstreams = None
+        self._staging = None  # pinned host copy of the concatenated records
+
+    # -- sessions -------------------------------------------------------------------------------
+    def add_session(self, trajectory, reward, session=None):
+        """Append one session (or a reference-style ``Session`` via ``session=``)."""
+        if session is not None:
+            trajectory, reward = session.trajectory, session.reward
+        traj = np.asarray(trajectory, dtype=np.float64).reshape(-1, 2)
+        mouse = None
+        if self.possible_actions is not None:
+            init = self.mouse_init if self.mouse_init is not None else (traj[0, 0], traj[0, 1], 0.0)
+            mouse = Mouse((init[0], init[1]), init[2], self.possible_actions, save_history=False)
+        elif self.alg != _native.ALG_TD0:
+            raise ValueError("PositiveConditioning / NegativeConditioning need possible_actions")
+        recs = build_session_records(self.maze, traj, reward, mouse=mouse)
+        n_on = len(recs)
+        if self.replay_n_times > 0:
+            seed = self.replay_seed
+            recs = np.concatenate([recs, replay_records(recs, self.replay_n_times, seed=seed)])
+        self.add_records(recs, n_on)
+
+    def add_records(self, records, n_online=None):
+        self._records.append(np.ascontiguousarray(records, dtype=_native.STEP_REC_DTYPE))
+        self._online.append(len(records) if n_online is None else int(n_online))
+        self._dstreams = None
+        self._staging = None
+
+    @property
+    def n_sessions(self):
+        return len(self._records)
+
+    @property
+    def updates_per_parameter_set(self):
+        """Number of value updates one parameter set performs over all sessions (online + replays)."""
+        return int(sum(len(r) for r in self._records))
+
+    # -- device state ----------------------------------------------------------------------------
+    def _ensure_device(self):
+        import torch
+        _native.require_device()
+        if self._dmaze is None:
+            self._dmaze = DeviceMaze(self.maze, self._device)
+        if self._dstreams is None:
+            if not self._records:
+                raise RuntimeError("no session added")
+            self._dstreams = DeviceStreams(self._dmaze, self._records, self._online, staging=self._staging)
+            self._staging = self._dstreams._host
+        return torch
+
+    def upload(self):
+        """(Re-)upload the session streams from the pinned staging buffer; returns the bytes copied
+        host->device."""
+        old, self._dstreams = self._dstreams, None
+        if old is not None:
+            old.close()
+        self._ensure_device()
+        return self._dstreams.host_bytes
+
+    @property
+    def torch_device(self):
+        self._ensure_device()
+        return self._dmaze.torch_device
+
+    def _v_init_tensor(self, torch, v_init, P):
+        if v_init is None:
+            return None, 0
+        v = np.asarray(v_init, dtype=np.float64)
+        X, Y = self.maze.shape
+        if v.shape == (X, Y):
+            return torch.from_numpy(np.ascontiguousarray(v).reshape(-1)).to(self.torch_device), 0
+        if v.shape == (P, X, Y):
+            return torch.from_numpy(np.ascontiguousarray(v).reshape(P, -1)).to(self.torch_device), 1
+        raise ValueError(f"v_init must have shape {(X, Y)} or {(P, X, Y)}")
+
+    # -- device-resident API (tensors in, tensors out; nothing synchronises) ---------------------------
+    def v_tables_device(self, alpha_t, gamma_t, v_init_t=None, v_init_per_unit=0, out=None):
+        torch = self._ensure_device()
+        P = int(alpha_t.numel())
+        n_tiles = self._dmaze.n_tiles
+        if out is None:
+            out = torch.empty((self.n_sessions, P, n_tiles), dtype=torch.float64, device=self.torch_device)
+        with torch.cuda.device(self.torch_device):
+            _native.check(self._dmaze._lib.nm_vtable_sweep(
+                self.alg, self._dmaze.handle, self._dstreams.handle, _native.tensor_ptr(alpha_t),
+                _native.tensor_ptr(gamma_t), P, _native.tensor_ptr(v_init_t), int(v_init_per_unit),
+                _native.tensor_ptr(out), _native.cuda_stream_ptr()))
+        return out
+
+    def log_likelihood_device(self, alpha_t, beta_t, gamma_t, v_init_t=None, v_init_per_unit=0, ll_out=None,
+                              v_out=None):
+        torch = self._ensure_device()
+        P = int(alpha_t.numel())
+        if ll_out is None:
+            ll_out = torch.empty((self.n_sessions, P), dtype=torch.float64, device=self.torch_device)
+        with torch.cuda.device(self.torch_device):
+            _native.check(self._dmaze._lib.nm_loglik_sweep(
+                self.alg, self._dmaze.handle, self._dstreams.handle, _native.tensor_ptr(alpha_t),
+                _native.tensor_ptr(beta_t), _native.tensor_ptr(gamma_t), P, _native.tensor_ptr(v_init_t),
+                int(v_init_per_unit), _native.tensor_ptr(ll_out), _native.tensor_ptr(v_out), _native.cuda_stream_ptr()))
+        return ll_out
+
+    def argmin_device(self, ll_t, nll_out=None):
+        """Per-shard best fit of ``ll_t`` ``[S, P]`` -> device tensor ``[2]`` int64-punned ``(nll, idx)``."""
+        torch = self._ensure_device()
+        S, P = int(ll_t.shape[0]), int(ll_t.shape[1])
+        best = torch.empty(2, dtype=torch.float64, device=self.torch_device)
+        with torch.cuda.device(self.torch_device):
+            _native.check(self._dmaze._lib.nm_argmin_nll(_native.tensor_ptr(ll_t), S, P, _native.tensor_ptr(nll_out),
+                                                         _native.tensor_ptr(best), _native.cuda_stream_ptr()))
+        return best
+
+    # -- numpy API ---------------------------------------------------------------------------------
+    def _to_dev(self, torch, a):
+        t = torch.from_numpy(a)
+        return t.to(self.torch_device, non_blocking=False)
+
+    def v_tables(self, alpha, gamma, v_init=None):
+        """V-tables after every session: ``float64[S, P, X, Y]`` (each session starts from ``v_init``)."""
+        torch = self._ensure_device()
+        alpha = _as_param(alpha)
+        gamma = _as_param(gamma, alpha.size)
+        alpha = _as_param(alpha, gamma.size)
+        P = alpha.size
+        if gamma.size != P:
+            raise ValueError("alpha and gamma must have the same length")
+        vi, per = self._v_init_tensor(torch, v_init, P)
+        out = self.v_tables_device(self._to_dev(torch, alpha), self._to_dev(torch, gamma), vi, per)
+        X, Y = self.maze.shape
+        return out.cpu().numpy().reshape(self.n_sessions, P, X, Y)
+
+    def log_likelihood(self, alpha, beta, gamma, v_init=None, return_v=False):
+        """Per-session log-likelihood of the observed choices: ``float64[S, P]``."""
+        torch = self._ensure_device()
+        alpha, beta, gamma = _as_param(alpha), _as_param(beta), _as_param(gamma)
+        P = max(alpha.size, beta.size, gamma.size)
+        alpha, beta, gamma = _as_param(alpha, P), _as_param(beta, P), _as_param(gamma, P)
+        if not (alpha.size == beta.size == gamma.size == P):
+            raise ValueError("alpha, beta and gamma must have the same length")
+        if any(r["ncand"].min(initial=1) == 0 for r in self._records if len(r)):
+            raise ValueError("the log-likelihood needs candidate next states: pass possible_actions")
+        vi, per = self._v_init_tensor(torch, v_init, P)
+        v_out = None
+        if return_v:
+            v_out = torch.empty((self.n_sessions, P, self._dmaze.n_tiles), dtype=torch.float64,
+                                device=self.torch_device)
+        ll = self.log_likelihood_device(self._to_dev(torch, alpha), self._to_dev(torch, beta),
+                                        self._to_dev(torch, gamma), vi, per, v_out=v_out)
+        ll = ll.cpu().numpy()
+        if return_v:
+            X, Y = self.maze.shape
+            return ll, v_out.cpu().numpy().reshape(self.n_sessions, P, X, Y)
+        return ll
+
+    def best_fit(self, alpha, beta, gamma, v_init=None, group=None):
+        """Grid search: minimise the negative log-likelihood summed over sessions.
+
+        With an initialised ``torch.distributed`` process group the flat parameter index is sharded in
+        contiguous blocks over the ranks (every rank holds all sessions) and the per-shard best fits
+        ``(nll, global index)`` -- 16 bytes per rank -- are all-gathered; every rank returns the global
+        arg-min (lowest index on ties, like ``numpy.argmin``).
+
+        :return: ``(best_nll, best_index)``
+        """
+        torch = self._ensure_device()
+        import torch.distributed as dist
+        alpha, beta, gamma = _as_param(alpha), _as_param(beta), _as_param(gamma)
+        P = alpha.size
+        rank, world = 0, 1
+        if dist.is_available() and dist.is_initialized():
+            rank, world = dist.get_rank(group), dist.get_world_size(group)
+        lo, hi = shard_bounds(P, rank, world)
+        if hi > lo:
+            vi, per = self._v_init_tensor(torch, None if v_init is None else
+                                          (v_init if np.asarray(v_init).ndim == 2 else np.asarray(v_init)[lo:hi]),
+                                          hi - lo)
+            ll = self.log_likelihood_device(self._to_dev(torch, alpha[lo:hi]), self._to_dev(torch, beta[lo:hi]),
+                                            self._to_dev(torch, gamma[lo:hi]), vi, per)
+            best = self.argmin_device(ll)
+        else:
+            best = torch.tensor([float("nan"), 0.0], dtype=torch.float64, device=self.torch_device)
+            best[1:].view(torch.int64).fill_(-1)
+        return reduce_best(best, lo, group=group)
+
+
+def reduce_best(best, offset, group=None):
+    """All-gather per-shard ``(nll, local idx)`` pairs and pick the global arg-min.
+
+    ``best``: tensor ``float64[2]`` whose second element holds an int64 bit pattern (the kernel's
+    ``{double, int64}`` output).  Works on CUDA tensors (NCCL) and CPU tensors (gloo)."""
+    import torch
+    import torch.distributed as dist
+    best = best.clone()
+    idx_view = best[1:].view(torch.int64)
+    idx_view += torch.where(idx_view >= 0, torch.tensor(int(offset), dtype=torch.int64, device=best.device),
+                            torch.tensor(0, dtype=torch.int64, device=best.device))
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        world = dist.get_world_size(group)
+        gathered = torch.empty(world * 2, dtype=torch.float64, device=best.device)
+        dist.all_gather_into_tensor(gathered, best, group=group)
+        pairs = gathered.view(world, 2).cpu()
+    else:
+        pairs = best.view(1, 2).cpu()
+    vals = pairs[:, 0].numpy()
+    idxs = pairs[:, 1:].contiguous().view(torch.int64).numpy().reshape(-1)
+    best_v, best_i = float("nan"), -1
+    for v, i in zip(vals, idxs):
+        if i < 0 or np.isnan(v):
+            continue
+        if best_i < 0 or v < best_v or (v == best_v and i < best_i):
+            best_v, best_i = float(v), int(i)
+    return best_v, best_i
+
+
+def vtable_single(maze, alg, records, n_online, alpha, gamma, v_init):
+    """One parameter set, one stream -> dense ``float64[X, Y]`` table (used by ``ConditioningExperiment``)."""
+    sw = ConditioningSweep(maze, alg)
+    sw.add_records(records, n_online)
+    return sw.v_tables([alpha], [gamma], v_init=v_init)[0, 0]

@@ -1,0 +1,292 @@
+"""CPU oracle (numpy / plain Python) of the hot path -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
+legs may import this module, and only as the checker.  The product (``navigation_model_b200``) never
+imports anything from ``oracle/``.
+
+It restates the reference's algorithm for the path, function by function, citing the reference
+``file:line`` each one follows (paths relative to ``/root/reference/src/navigation_model`` unless they
+start with ``src/``).  It is deliberately independent of the product code: it has its own maze
+geometry, mouse pose arithmetic and stream extraction.
+
+Pinning:
+
+* V-tables of ``TD0`` / ``PositiveConditioning`` / ``NegativeConditioning`` with and without
+  ``ShuffledReplays``, the extracted transitions, softmax step probabilities / choices of
+  ``BehaviouralModel.decision_making``, ``StandardExperiment.run`` trajectories under replayed draws
+  and the occupancy metrics are PINNED: ``tests/golden/make_golden.py`` runs the *unmodified* reference
+  (imported from ``/root/reference`` through ``oracle/refharness.py``) and commits its outputs as
+  fixtures; ``tests/test_oracle_golden.py`` checks this oracle against them bit for bit.
+* The **log-likelihood** is an extension with no reference implementation: **parity unpinned**.  It is
+  composed from pinned primitives -- the value recurrences above and the softmax of
+  ``simulation/exploration_model.py:84-93`` -- evaluated in log space.
+"""
+import math
+
+import numpy as np
+
+ALG_TD0, ALG_POSITIVE, ALG_NEGATIVE = 0, 1, 2
+OBS_NONE = 255
+
+
+# ------------------------------------------------------------------------------------------ maze
+class OracleMaze:
+    """Tile grid + geometry (simulation/maze.py:107-627), dense numpy layout.
+
+    ``tiles[x, y]``: 0 = VOID, 1 = WALL, 2 = CORNER, 3 = CENTRE, 4 = DECISION_POINT
+    (maze.py:28-32, 66-71); x = text row, y = column (maze.py:126-143).
+    """
+
+    CODES = {"W": 1, "C": 2, "M": 3, "D": 4}
+
+    def __init__(self, layout, size_tile, grid_tiles=False):
+        rows = layout.split("\n")
+        if rows and rows[-1] == "":
+            rows.pop()
+        codes = dict(self.CODES)
+        if not grid_tiles:
+            codes.pop("D")  # StandardTiles maps unknown chars (incl. 'D') to VOID, maze.py:35-42
+        self.tiles = np.array([[codes.get(c, 0) for c in r] for r in rows], dtype=np.uint8)
+        self.X, self.Y = self.tiles.shape
+        self.st = size_tile
+        self.vis = self.tiles != 0
+        self.vis_cells = [(int(x), int(y)) for x, y in np.argwhere(self.vis)]  # x-major
+        self.state_of = {c: i for i, c in enumerate(self.vis_cells)}
+        self.centres = np.array([self.centre(c) for c in self.vis_cells])
+
+    @classmethod
+    def from_file(cls, path, size_tile, grid_tiles=False):
+        with open(path) as fh:
+            text = fh.read()
+        return cls(text.split("SUB")[0], size_tile, grid_tiles)  # maze.py:183-190
+
+    def centre(self, c):  # maze.py:262-263
+        return self.st * (c[0] + 1) - self.st / 2, self.st * (c[1] + 1) - self.st / 2
+
+    def cont2disc(self, x, y):  # maze.py:393-394  (Python float floor-division)
+        return int(x // self.st), int(y // self.st)
+
+    def visitable(self, c):  # maze.py:499-501
+        x, y = c
+        if x < 0 or x >= self.X or y < 0 or y >= self.Y:
+            return False
+        return bool(self.vis[x, y])
+
+    def closest_visitable(self, x, y):  # maze.py:469-484 (KD-tree nearest centre -> exhaustive search)
+        c = self.cont2disc(x, y)
+        if self.visitable(c):
+            return c
+        d = (self.centres[:, 0] - x) ** 2 + (self.centres[:, 1] - y) ** 2
+        cx, cy = self.centres[int(np.argmin(d))]
+        return self.cont2disc(cx, cy)
+
+    def move_possible(self, x1, y1, x2, y2):  # maze.py:563-611
+        st = self.st
+        if not self.visitable(self.cont2disc(x1, y1)) or not self.visitable(self.cont2disc(x2, y2)):
+            return False
+        if x1 != x2:
+            if x1 > x2:
+                x1, x2 = x2, x1
+                y1, y2 = y2, y1
+            m = (y2 - y1) / (x2 - x1)
+            for dx in range(int(x1 // st), int(x2 // st)):
+                x = (dx + 1) * st
+                y = m * (x - x1) + y1
+                if not self.visitable(self.cont2disc(x - st, y)):
+                    return False
+                if not self.visitable(self.cont2disc(x, y)):
+                    return False
+        if y1 != y2:
+            if y1 > y2:
+                x1, x2 = x2, x1
+                y1, y2 = y2, y1
+            m = (x2 - x1) / (y2 - y1)
+            for dy in range(int(y1 // st), int(y2 // st)):
+                y = (dy + 1) * st
+                x = m * (y - y1) + x1
+                if not self.visitable(self.cont2disc(x, y - st)):
+                    return False
+                if not self.visitable(self.cont2disc(x, y)):
+                    return False
+        return True
+
+
+# ----------------------------------------------------------------------------------------- mouse
+class OracleMouse:
+    """Pose arithmetic of the C++ Mouse (src/_navigation_model/mouse.cpp:64-87)."""
+
+    def __init__(self, pos, ori, actions):
+        self.x, self.y = float(pos[0]), float(pos[1])
+        self.ori = float(ori)
+        self.actions = np.asarray(actions, dtype=np.float64).reshape(-1, 2)
+
+    def endpoints(self):  # mouse.cpp:64-73
+        c, s = math.cos(self.ori), math.sin(self.ori)
+        return [((c * ax + (-s) * ay) + self.x, (s * ax + c * ay) + self.y) for ax, ay in self.actions]
+
+    def move_to(self, x, y):  # mouse.cpp:75-81; Eigen isApprox, precision 1e-12
+        dx, dy = x - self.x, y - self.y
+        if (dx * dx + dy * dy) <= (1e-12 * 1e-12) * min(x * x + y * y, self.x * self.x + self.y * self.y):
+            return False
+        self.ori = math.atan2(y - self.y, x - self.x)
+        self.x, self.y = x, y
+        return True
+
+
+# -------------------------------------------------------------------------- stream extraction
+def extract_transitions(maze, trajectory, reward, mouse=None):
+    """The parameter-independent part of ``ConditioningExperiment.run`` (simulation/rl.py:85-102) and of
+    ``PositiveConditioning.update`` (rl.py:177-182, 189).
+
+    :return: dict of plain arrays: ``s, s1`` (compact state ids, x-major over visitable tiles), ``r``,
+             ``ncand``, ``cand[T-1, 8]``, ``obs`` (first k with cand[k] == s1, else 255)
+    """
+    T = len(trajectory)
+    if T != len(reward):
+        raise RuntimeError("trajectory and reward must have the same length")  # rl.py:82-83
+    n = T - 1
+    out = {"s": np.zeros(n, np.int32), "s1": np.zeros(n, np.int32), "r": np.zeros(n, np.float64),
+           "ncand": np.zeros(n, np.int32), "cand": np.zeros((n, 8), np.int32),
+           "obs": np.full(n, OBS_NONE, np.int32)}
+    s = maze.closest_visitable(trajectory[0][0], trajectory[0][1])  # rl.py:87
+    for i in range(1, T):
+        cs, cs1 = trajectory[i - 1], trajectory[i]
+        s1 = maze.closest_visitable(cs1[0], cs1[1])  # rl.py:94
+        out["s"][i - 1] = maze.state_of[s]
+        out["s1"][i - 1] = maze.state_of[s1]
+        out["r"][i - 1] = reward[i]  # rl.py:95
+        if mouse is not None:
+            mouse.move_to(cs[0], cs[1])  # rl.py:178
+            cells = [maze.cont2disc(ex, ey) for ex, ey in mouse.endpoints()]  # rl.py:179-180
+            nxt = [c for c in cells if maze.visitable(c)]  # rl.py:181-182
+            if len(nxt) == 0:
+                raise ValueError("zero-size array to reduction operation maximum which has no identity")
+            if len(nxt) > 8:
+                raise ValueError("oracle supports at most 8 candidates")
+            out["ncand"][i - 1] = len(nxt)
+            for k, c in enumerate(nxt):
+                out["cand"][i - 1, k] = maze.state_of[c]
+                if out["obs"][i - 1] == OBS_NONE and c == s1:
+                    out["obs"][i - 1] = k
+            mouse.move_to(cs1[0], cs1[1])  # rl.py:189
+        s = s1
+    return out
+
+
+def replay_orders(n, n_times, seed):
+    """Index orders of ``ShuffledReplays.offline_replays`` (rl.py:419-424): ``n_times`` cumulative in-place
+    ``Generator.shuffle`` calls; shuffling ``arange(n)`` draws the same permutation as shuffling the
+    buffer list."""
+    rng = np.random.default_rng(seed)
+    idx = np.arange(n)
+    orders = []
+    for _ in range(n_times):
+        rng.shuffle(idx)
+        orders.append(idx.copy())
+    return orders
+
+
+# ------------------------------------------------------------------------- value recurrences
+def np_sum(values):
+    """``numpy.sum`` of a contiguous float64 vector of length <= 8, spelled out: sequential from 0.0 for
+    n < 8, the 8-accumulator pairwise tree for n == 8."""
+    n = len(values)
+    if n < 8:
+        acc = 0.0
+        for v in values:
+            acc = acc + v
+        return acc
+    assert n == 8
+    e = values
+    return ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]))
+
+
+def step_update(alg, V, s, s1, r, cand, alpha, gamma):
+    """One value update on the compact table ``V`` (python floats, left-to-right like the reference)."""
+    if alg == ALG_TD0:  # rl.py:257-259
+        rpe = r + gamma * V[s1] - V[s]
+    elif alg == ALG_POSITIVE:  # rl.py:184-186
+        rpe = r + gamma * max(V[c] for c in cand) - V[s]
+    else:  # rl.py:227-229
+        rpe = r + gamma * min(V[c] for c in cand) - V[s]
+    V[s] += alpha * rpe
+
+
+def step_logp(V, cand, obs, beta):
+    """Log-probability of the observed candidate under ``softmax(beta * V[cand])``
+    (simulation/exploration_model.py:84-93, in log space).  EXTENSION -- parity unpinned."""
+    val = [beta * V[c] for c in cand]  # :87
+    m = max(val)  # :92
+    val = [v - m for v in val]
+    e = [math.exp(v) for v in val]  # :93
+    return val[obs] - math.log(np_sum(e))
+
+
+def run_session(alg, tr, alpha, gamma, n_states, beta=None, v0=None, orders=()):
+    """Online pass (+ replay passes) of one parameter set over one session.
+
+    :param tr: output of :func:`extract_transitions`
+    :param beta: None -> value learning only; else accumulate the log-likelihood over online steps
+    :param orders: replay index orders (see :func:`replay_orders`)
+    :return: ``(V[n_states], ll)``
+    """
+    V = [0.0] * n_states if v0 is None else [float(v) for v in v0]
+    ll = 0.0
+    n = len(tr["s"])
+    s_, s1_, r_, k_, c_, o_ = (tr["s"].tolist(), tr["s1"].tolist(), tr["r"].tolist(), tr["ncand"].tolist(),
+                               tr["cand"].tolist(), tr["obs"].tolist())
+    for i in range(n):
+        cand = c_[i][:k_[i]]
+        if beta is not None and o_[i] != OBS_NONE:
+            ll = ll + step_logp(V, cand, o_[i], beta)
+        step_update(alg, V, s_[i], s1_[i], r_[i], cand, alpha, gamma)
+    for order in orders:
+        for i in order.tolist():
+            step_update(alg, V, s_[i], s1_[i], r_[i], c_[i][:k_[i]], alpha, gamma)
+    return np.array(V), ll
+
+
+def dense_table(maze, V, v0_dense=None):
+    """Scatter a compact table to ``[X, Y]`` (untouched tiles keep their initial value / 0)."""
+    out = np.zeros((maze.X, maze.Y)) if v0_dense is None else np.array(v0_dense, dtype=np.float64)
+    for i, (x, y) in enumerate(maze.vis_cells):
+        out[x, y] = V[i]
+    return out
+
+
+# --------------------------------------------------------------------------- synthetic sessions
+def synthetic_session(maze, session_id, T=5000, start=(1, 1), goal=(7, 4), jitter=0.04):
+    """The seeded benchmark session of SURVEY section 8c / BASELINE.md section 4.
+
+    9-neighbourhood (stay included, ``dx`` slowest) random walk over visitable tiles: for every step draw
+    the next tile with ``rng.integers`` first, then the jitter ``rng.uniform(-j, j, 2)`` of the current
+    point; reward 1.0 when the jittered point lies on ``goal``.  Known answer for ``session_id=0``,
+    T=5000, ``TD0(0.1, 0.9)`` on the 9x9 test maze: ``V.max() = 0.5949675648481678``,
+    ``V[7,4] = 0.48326347528794783``, 108 rewarded steps, 60 distinct tiles.
+    """
+    rng = np.random.default_rng(session_id)
+    tile = tuple(start)
+    traj = np.zeros((T, 2))
+    rew = np.zeros(T)
+    steps = [(dx, dy) for dx in (-1, 0, 1) for dy in (-1, 0, 1)]
+    for t in range(T):
+        nbrs = [(tile[0] + dx, tile[1] + dy) for dx, dy in steps if maze.visitable((tile[0] + dx, tile[1] + dy))]
+        nxt = nbrs[rng.integers(len(nbrs))]
+        cx, cy = maze.centre(tile)
+        jx, jy = rng.uniform(-jitter, jitter, 2)
+        traj[t] = (cx + jx, cy + jy)
+        rew[t] = 1.0 if maze.cont2disc(traj[t, 0], traj[t, 1]) == tuple(goal) else 0.0
+        tile = nxt
+    return traj, rew
+
+
+#: 8 relative actions of SURVEY section 8 ("A8"), in units of size_tile
+A8_UNITS = np.array([(0, 0), (1, 0), (2, 0), (1, 1), (1, -1), (0, 1), (0, -1), (-1, 0)], dtype=np.float64)
+
+#: the 9x9 test maze of the reference (test/data/maze_layout.txt), restated so that GPU-box runs need no
+#: access to /root/reference
+M9_LAYOUT = "\n".join(["CWWWWWWWC", "WMMMMMMMW", "CWWWWWWWW", "VVVVVVVWW", "VVVVVVVWW", "VVVVVVVWW",
+                       "CWWWWWWWW", "WMMMMMMMW", "CWWWWWWWC"])
+M9_SUBAREAS = "\n".join(["111222333", "111222333", "111222333", "000000044", "000000044", "000000044",
+                         "777666555", "777666555", "777666555"])
+M9_SIZE_TILE = 0.111

@@ -1,0 +1,235 @@
+"""Parity of the CUDA fitness sweep (through the C-ABI) with the oracle and the reference's golden
+vectors.  V-tables: bit-exact.  Log-likelihoods: 1e-9 relative (BASELINE.json north_star tolerance; the
+device `exp`/`log` differ from glibc's by <= 1 ulp)."""
+import numpy as np
+import pytest
+
+from oracle import c_oracle as CO
+from oracle import np_oracle as O
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+LL_RTOL = 1e-9
+ALGS = {"td0": O.ALG_TD0, "positive": O.ALG_POSITIVE, "negative": O.ALG_NEGATIVE}
+
+
+def _sweep(alg, sessions, actions=True, replay_n_times=0, replay_seed=None, maze=None):
+    from navigation_model_b200.sweep import ConditioningSweep
+    maze = maze or H.product_m9()
+    sw = ConditioningSweep(maze, alg, possible_actions=H.a8(maze.size_tile) if actions else None,
+                           replay_n_times=replay_n_times, replay_seed=replay_seed)
+    for traj, rew in sessions:
+        sw.add_session(traj, rew)
+    return sw
+
+
+@pytest.mark.parametrize("alg", ["td0", "positive", "negative"])
+@pytest.mark.parametrize("n_times", [0, 2])
+def test_vtables_bit_exact_vs_oracle(cuda, alg, n_times):
+    omz = H.oracle_m9()
+    traj, rew = O.synthetic_session(omz, 1, 900)
+    if alg == "negative":
+        rew = -rew
+    tr = H.oracle_transitions(omz, traj, rew, H.a8())
+    rng = np.random.default_rng(42)
+    P = 257  # not a multiple of the block size
+    a, _, gm = H.grid_params(rng, P)
+    want, _ = CO.fit(ALGS[alg], tr, a, gm, 60, orders=O.replay_orders(len(tr["s"]), n_times, 5))
+    sw = _sweep(alg, [(traj, rew)], replay_n_times=n_times, replay_seed=5)
+    got = sw.v_tables(a, gm)  # [1, P, 9, 9]
+    assert got.shape == (1, P, 9, 9)
+    for p in range(P):
+        assert np.array_equal(got[0, p], O.dense_table(omz, want[p])), (alg, n_times, p)
+
+
+@pytest.mark.parametrize("alg", ["td0", "positive", "negative"])
+def test_loglik_vs_oracle(cuda, alg):
+    omz = H.oracle_m9()
+    sessions = [O.synthetic_session(omz, sid, T) for sid, T in ((0, 1500), (1, 333), (2, 64), (3, 65))]  # ragged
+    if alg == "negative":
+        sessions = [(t, -r) for t, r in sessions]
+    rng = np.random.default_rng(7)
+    P = 300
+    a, b, gm = H.grid_params(rng, P)
+    sw = _sweep(alg, sessions)
+    ll, V = sw.log_likelihood(a, b, gm, return_v=True)
+    assert ll.shape == (4, P)
+    for j, (traj, rew) in enumerate(sessions):
+        tr = H.oracle_transitions(omz, traj, rew, H.a8())
+        Vw, llw = CO.fit(ALGS[alg], tr, a, gm, 60, beta=b)
+        np.testing.assert_allclose(ll[j], llw, rtol=LL_RTOL, atol=0)
+        for p in range(0, P, 17):
+            assert np.array_equal(V[j, p], O.dense_table(omz, Vw[p]))
+
+
+def test_golden_vectors_through_reference_api(cuda, golden_fit):
+    """ConditioningExperiment / RLAlgorithm / ShuffledReplays classes of this repo (device path) against
+    the V-tables the reference produced for the same calls."""
+    from navigation_model_b200.simulation.maze import Maze
+    from navigation_model_b200.simulation.mouse import Mouse
+    from navigation_model_b200.simulation.rl import (ConditioningExperiment, NegativeConditioning,
+                                                     PositiveConditioning, ShuffledReplays, TD0)
+    g = golden_fit
+    maze = H.product_m9()
+    traj, rew = g["m9_traj"], g["m9_rew"]
+
+    def run(alg_name, a, gm, r, n_times, seed, v_init=None, extra=False, mz=maze, tj=traj, acts=g["A8"]):
+        mouse = Mouse(tj[0], 0.0, acts)
+        alg = {"td0": lambda: TD0(a, gm), "positive": lambda: PositiveConditioning(a, gm, mouse, mz),
+               "negative": lambda: NegativeConditioning(a, gm, mouse, mz)}[alg_name]()
+        rep = ShuffledReplays(n_times=n_times, seed=seed)
+        exp = ConditioningExperiment(mz, alg, rep, v_table=None if v_init is None else v_init.copy())
+        assert exp._device_eligible()
+        exp.run(list(tj), [0.0] * len(tj), list(r), do_replays=n_times > 0)
+        if extra:
+            exp.do_replays()
+        return exp.v_table, rep, mouse
+
+    for alg in ("td0", "positive", "negative"):
+        r = -rew if alg == "negative" else rew
+        for n_times in (0, 3):
+            for p, (a, gm) in enumerate(g["params"]):
+                V, rep, mouse = run(alg, a, gm, r, n_times, 11)
+                assert np.array_equal(V, g[f"m9_{alg}_rep{n_times}_V"][p]), (alg, n_times, p)
+                assert len(rep._buffer) == len(traj) - 1
+    # the algorithm's mouse ends where the reference's does
+    _, _, mouse = run("positive", 0.1, 0.9, rew, 0, None)
+    assert np.array_equal([*mouse.position, mouse.orientation], g["m9_mouse_final"])
+    # continued learning + a second do_replays()
+    assert np.array_equal(run("td0", 0.2, 0.8, rew, 2, 4, v_init=g["m9_v0"])[0], g["m9_td0_v0_V"])
+    assert np.array_equal(run("positive", 0.2, 0.8, rew, 2, 4, v_init=g["m9_v0"], extra=True)[0],
+                          g["m9_positive_v0_V"])
+    # 7x7 maze with an interior void; points outside the maze
+    m7 = Maze(str(g["m7_layout"]), "", size_tile=0.2)
+    a7 = O.A8_UNITS * 0.2
+    for p, (a, gm) in enumerate(g["params"]):
+        assert np.array_equal(run("td0", a, gm, g["m7_rew"], 2, 21, mz=m7, tj=g["m7_traj"], acts=a7)[0],
+                              g["m7_td0_rep2_V"][p])
+        for alg in ("positive", "negative"):
+            r = -g["m7b_rew"] if alg == "negative" else g["m7b_rew"]
+            assert np.array_equal(run(alg, a, gm, r, 2, 21, mz=m7, tj=g["m7b_traj"], acts=a7)[0],
+                                  g[f"m7b_{alg}_rep2_V"][p])
+
+
+def test_benchmark_session_kat(cuda, golden_fit):
+    omz = H.oracle_m9()
+    traj, rew = O.synthetic_session(omz, 0, 5000)
+    sw = _sweep("td0", [(traj, rew)])
+    V = sw.v_tables([0.1], [0.9])[0, 0]
+    assert np.array_equal(V, golden_fit["kat_td0_V"])
+    assert V.max() == 0.5949675648481678 and V[7, 4] == 0.48326347528794783
+
+
+def test_v_init_shared_and_per_unit(cuda):
+    omz = H.oracle_m9()
+    traj, rew = O.synthetic_session(omz, 4, 400)
+    tr = H.oracle_transitions(omz, traj, rew, H.a8())
+    rng = np.random.default_rng(3)
+    P = 70
+    a, b, gm = H.grid_params(rng, P)
+    sw = _sweep("positive", [(traj, rew)])
+    v0 = rng.random((9, 9))
+    got = sw.v_tables(a, gm, v_init=v0)[0]
+    want, _ = CO.fit(O.ALG_POSITIVE, tr, a, gm, 60, v0=H.compact(omz, v0))
+    for p in range(P):
+        assert np.array_equal(got[p], O.dense_table(omz, want[p], v0))
+    v0p = rng.random((P, 9, 9))
+    got = sw.v_tables(a, gm, v_init=v0p)[0]
+    for p in range(0, P, 7):
+        w, _ = CO.fit(O.ALG_POSITIVE, tr, a[p:p + 1], gm[p:p + 1], 60, v0=H.compact(omz, v0p[p]))
+        assert np.array_equal(got[p], O.dense_table(omz, w[0], v0p[p]))
+
+
+def test_empty_and_single_step_sessions(cuda):
+    omz = H.oracle_m9()
+    t1, r1 = O.synthetic_session(omz, 5, 1)   # no transition at all
+    t2, r2 = O.synthetic_session(omz, 5, 2)   # exactly one transition
+    sw = _sweep("td0", [(t1, r1), (t2, r2)])
+    V = sw.v_tables([0.5, 0.25], [0.9, 0.8])
+    assert not V[0].any()
+    ll = sw.log_likelihood([0.5, 0.25], [1.0, 2.0], [0.9, 0.8])
+    assert np.array_equal(ll[0], [0.0, 0.0])
+    tr = H.oracle_transitions(omz, t2, r2, H.a8())
+    _, llw = CO.fit(O.ALG_TD0, tr, [0.5, 0.25], [0.9, 0.8], 60, beta=[1.0, 2.0])
+    np.testing.assert_allclose(ll[1], llw, rtol=LL_RTOL)
+
+
+def test_full_grid_properties(cuda):
+    """BASELINE.json configs[1] at full size (64 x 64 x 32 = 131 072 parameter sets, T = 5 000) through
+    size-independent properties + spot checks against the oracle."""
+    from navigation_model_b200.sweep import parameter_grid
+    omz = H.oracle_m9()
+    traj, rew = O.synthetic_session(omz, 0, 5000)
+    tr = H.oracle_transitions(omz, traj, rew, H.a8())
+    alpha, beta, gamma = parameter_grid(np.linspace(0.01, 1, 64), np.logspace(-1, 1.5, 64), np.linspace(0.5, 0.99, 32))
+    P = alpha.size
+    assert P == 131072
+    sw = _sweep("positive", [(traj, rew)])
+    ll = sw.log_likelihood(alpha, beta, gamma)[0]
+    assert np.isfinite(ll).all() and (ll < 0).all()
+    # (1) spot check against the oracle
+    idx = np.random.default_rng(1).choice(P, 96, replace=False)
+    _, llw = CO.fit(O.ALG_POSITIVE, tr, alpha[idx], gamma[idx], 60, beta=beta[idx], want_v=False)
+    np.testing.assert_allclose(ll[idx], llw, rtol=LL_RTOL)
+    # (2) determinism / independence of the block decomposition: a permuted grid gives permuted results
+    perm = np.random.default_rng(2).permutation(P)
+    ll_perm = sw.log_likelihood(alpha[perm], beta[perm], gamma[perm])[0]
+    assert np.array_equal(ll_perm, ll[perm])
+    # (3) closed form: alpha = 0 keeps V = 0, so every observed choice has probability 1/K
+    obs = tr["obs"] != O.OBS_NONE
+    closed = 0.0
+    for k in tr["ncand"][obs]:
+        closed = closed + (0.0 - np.log(float(k)))
+    ll0 = sw.log_likelihood(np.zeros(4), beta[:4], gamma[:4])[0]
+    np.testing.assert_allclose(ll0, closed, rtol=1e-12)
+    # (4) the arg-min epilogue agrees with numpy
+    from navigation_model_b200.sweep import reduce_best
+    import torch
+    ll_t = torch.from_numpy(ll.reshape(1, P)).to(sw.torch_device)
+    best_v, best_i = reduce_best(sw.argmin_device(ll_t), 0)
+    assert best_i == int(np.argmin(-ll)) and best_v == float((-ll).min())
+
+
+def test_td0_linearity_in_reward(cuda):
+    """TD0 is linear in the reward: scaling rewards by a power of two scales V exactly."""
+    omz = H.oracle_m9()
+    traj, rew = O.synthetic_session(omz, 6, 2000)
+    rng = np.random.default_rng(9)
+    a, _, gm = H.grid_params(rng, 1024)
+    V1 = _sweep("td0", [(traj, rew)], actions=False).v_tables(a, gm)
+    V4 = _sweep("td0", [(traj, 4.0 * rew)], actions=False).v_tables(a, gm)
+    assert np.array_equal(4.0 * V1, V4)
+
+
+def test_best_fit_single_rank(cuda):
+    omz = H.oracle_m9()
+    sessions = [O.synthetic_session(omz, sid, 500) for sid in (0, 1, 2)]
+    rng = np.random.default_rng(11)
+    a, b, gm = H.grid_params(rng, 777)
+    sw = _sweep("td0", sessions)
+    ll = sw.log_likelihood(a, b, gm)
+    nll = -(ll[0] + ll[1] + ll[2])
+    v, i = sw.best_fit(a, b, gm)
+    assert i == int(np.argmin(nll)) and v == float(nll[i])
+
+
+def test_errors(cuda):
+    from navigation_model_b200.sweep import ConditioningSweep
+    maze = H.product_m9()
+    omz = H.oracle_m9()
+    traj, rew = O.synthetic_session(omz, 0, 50)
+    with pytest.raises(RuntimeError):  # rl.py:82-83
+        ConditioningSweep(maze, "td0").add_session(traj, rew[:-1])
+    with pytest.raises(ValueError):
+        ConditioningSweep(maze, "positive").add_session(traj, rew)  # needs possible_actions
+    sw = ConditioningSweep(maze, "td0")
+    sw.add_session(traj, rew)
+    with pytest.raises(ValueError):  # likelihood without candidates
+        sw.log_likelihood([0.1], [1.0], [0.9])
+    # a mouse stranded outside the maze has no candidate: np.max([]) raises ValueError in the reference
+    far = traj.copy()
+    far[10] = (5.0, 5.0)
+    with pytest.raises(ValueError):
+        ConditioningSweep(maze, "positive", possible_actions=H.a8()).add_session(far, rew)

@@ -1,0 +1,141 @@
+"""Host-side logic that needs no GPU: native stream builder vs the oracle's extraction, replay orders,
+grid sharding + the world_size-2 gather of per-shard best fits over gloo, loud failure without CUDA."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import np_oracle as O
+
+import helpers as H
+from conftest import has_cuda
+
+
+def _records(maze, traj, rew, actions):
+    from navigation_model_b200.simulation.mouse import Mouse
+    from navigation_model_b200.sweep import build_session_records
+    mouse = None if actions is None else Mouse(traj[0], 0.0, actions, save_history=False)
+    return build_session_records(maze, traj, rew, mouse=mouse)
+
+
+@pytest.mark.parametrize("sid,T", [(0, 5000), (7, 300), (9, 2)])
+def test_native_stream_builder_matches_oracle(sid, T):
+    omz, maze = H.oracle_m9(), H.product_m9()
+    traj, rew = O.synthetic_session(omz, sid, T)
+    tr = H.oracle_transitions(omz, traj, rew, H.a8())
+    recs = _records(maze, traj, rew, H.a8())
+    assert len(recs) == T - 1
+    assert np.array_equal(recs["s"], tr["s"]) and np.array_equal(recs["s1"], tr["s1"])
+    assert np.array_equal(recs["r"], tr["r"]) and np.array_equal(recs["ncand"], tr["ncand"])
+    assert np.array_equal(recs["obs"], tr["obs"])
+    for i in range(len(recs)):
+        k = recs["ncand"][i]
+        assert np.array_equal(recs["cand"][i, :k], tr["cand"][i, :k])
+    # without a mouse: no candidates
+    plain = _records(maze, traj, rew, None)
+    assert not plain["ncand"].any() and (plain["obs"] == 0xFF).all()
+    assert np.array_equal(plain["s"], tr["s"])
+
+
+def test_stream_builder_golden_transitions(golden_fit):
+    """...and against the transitions the reference itself extracted."""
+    g = golden_fit
+    maze = H.product_m9()
+    recs = _records(maze, g["m9_traj"], g["m9_rew"], g["A8"])
+    tos = maze.flat_tables()["tile_of_state"]
+    cells = np.stack([tos // 9, tos % 9], axis=1)
+    assert np.array_equal(cells[recs["s"]], g["m9_tr_s"]) and np.array_equal(cells[recs["s1"]], g["m9_tr_s1"])
+    assert np.array_equal(recs["r"], g["m9_tr_r"]) and np.array_equal(recs["ncand"], g["m9_tr_ncand"])
+    for i in range(len(recs)):
+        k = recs["ncand"][i]
+        assert np.array_equal(cells[recs["cand"][i, :k]], g["m9_tr_cand"][i, :k])
+
+
+def test_replay_records_follow_generator_shuffle():
+    from navigation_model_b200.sweep import replay_records
+    omz, maze = H.oracle_m9(), H.product_m9()
+    traj, rew = O.synthetic_session(omz, 1, 200)
+    recs = _records(maze, traj, rew, H.a8())
+    rep = replay_records(recs, 3, seed=5)
+    orders = O.replay_orders(len(recs), 3, 5)
+    assert np.array_equal(rep, recs[np.concatenate(orders)])
+    # same permutation as shuffling a list of objects in place (what the reference does, rl.py:420)
+    objs = list(range(len(recs)))
+    rng = np.random.default_rng(5)
+    rng.shuffle(objs)
+    assert objs == orders[0].tolist()
+
+
+def test_shard_bounds_cover_grid():
+    from navigation_model_b200.sweep import shard_bounds
+    for P in (1, 7, 8, 131072, 2097152 + 3):
+        for world in (1, 2, 4, 8):
+            spans = [shard_bounds(P, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == P
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _gloo_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import torch
+    import torch.distributed as dist
+    from navigation_model_b200.sweep import reduce_best, shard_bounds
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    nll = np.random.default_rng(123).random(1001)
+    nll[[17, 600]] = nll.min() - 1.0  # a tie across the two shards: the lowest index must win
+    lo, hi = shard_bounds(len(nll), rank, world)
+    local = nll[lo:hi]
+    best = torch.empty(2, dtype=torch.float64)
+    best[0] = float(local.min())
+    best[1:].view(torch.int64)[0] = int(np.argmin(local))
+    v, i = reduce_best(best, lo)
+    q.put((rank, v, i))
+    dist.destroy_process_group()
+
+
+def test_best_fit_gather_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    nll = np.random.default_rng(123).random(1001)
+    nll[[17, 600]] = nll.min() - 1.0
+    for _, v, i in res:
+        assert i == 17 and v == nll[17]
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly, not fall back."""
+    if has_cuda():
+        pytest.skip("CUDA device present")
+    from navigation_model_b200.sweep import ConditioningSweep
+    omz, maze = H.oracle_m9(), H.product_m9()
+    traj, rew = O.synthetic_session(omz, 0, 50)
+    sw = ConditioningSweep(maze, "td0")
+    sw.add_session(traj, rew)
+    with pytest.raises(RuntimeError, match="no usable CUDA device"):
+        sw.v_tables([0.1], [0.9])
+    from navigation_model_b200.simulation.rl import ConditioningExperiment, ShuffledReplays, TD0
+    exp = ConditioningExperiment(maze, TD0(0.1, 0.9), ShuffledReplays(0))
+    with pytest.raises(RuntimeError, match="no usable CUDA device"):
+        exp.run(list(traj), [0.0] * len(traj), list(rew))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "navigation_model_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("no oracle", ""), f"{f} mentions the oracle"
