@@ -71,7 +71,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -90,7 +90,7 @@ class ClockSampler(threading.Thread):
                  nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
                  nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
                  nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
@@ -99,10 +99,10 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(nm)
             except Exception:
                 pass
-            self._stop.wait(self.period)
+            self._halt.wait(self.period)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=2)
         med = float(np.median(self.samples)) if self.samples else None
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
