@@ -89,6 +89,9 @@ int nm_mouse_reset(nm_mouse *m, const double *init_pos, const double *init_ori);
 int64_t nm_mouse_history_len(const nm_mouse *m);
 /* pos_out: [len, 2], ori_out: [len] */
 int nm_mouse_history(const nm_mouse *m, double *pos_out, double *ori_out);
+/* Adopt a trajectory computed elsewhere (the simulation kernel): the n poses are appended to the history
+ * (when enabled) exactly as n move_to calls would have, and the last one becomes the current pose. */
+int nm_mouse_adopt_trajectory(nm_mouse *m, const double *pos, const double *ori, int64_t n);
 
 /* ------------------------------------------------------------------------------------------------
  * Maze: dense tile tables resident on the device
@@ -173,6 +176,70 @@ int nm_loglik_sweep(int alg, const nm_maze *mz, const nm_streams *st, const doub
  *   d_nll_out: [P] or NULL;  d_best_out: {double best_nll; int64 best_idx} (16 bytes, device).
  */
 int nm_argmin_nll(const double *d_ll, int S, int64_t P, double *d_nll_out, void *d_best_out, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Forward simulation of many mice (one thread = one mouse)
+ * ---------------------------------------------------------------------------------------------- */
+/* behavioural components, in the order the BehaviouralModel sums them (exploration_model.py:84-86) */
+#define NM_COMP_ANXIETY 1      /* behavioural_components.py:315-376 (StandardTiles and GridTiles variants) */
+#define NM_COMP_BCOST 2        /* :379-416  BiomechanicalCostComponent                                  */
+#define NM_COMP_EXPERIENCE 3   /* :419-482  ExperienceComponent                                         */
+#define NM_COMP_BPERSISTENCE 4 /* :485-516  BiomechPersistenceComponent                                 */
+#define NM_COMP_VTABLE 5       /* :519-544  ValueTableComponent                                         */
+#define NM_MAX_COMPONENTS 8
+
+/* All d_ arrays are device pointers; [N] = one entry per mouse.  Unused components: NULL. */
+typedef struct nm_sim_args {
+  int64_t n_mice;
+  int32_t n_steps;                         /* iterations of StandardExperiment.run (experiment.py:33)      */
+  int32_t n_actions;                       /* A <= NM_MAX_CAND                                             */
+  const double *h_actions;                 /* HOST [A,2] relative displacements of the Mouse               */
+  const uint8_t *h_zero_action;            /* HOST [A] 1 where the component's discrete action is (0,0)    */
+  int32_t n_components;                    /* <= NM_MAX_COMPONENTS                                         */
+  int32_t component_kind[NM_MAX_COMPONENTS];   /* NM_COMP_*, in model order                                */
+  int32_t component_active[NM_MAX_COMPONENTS]; /* Component.active (behavioural_components.py:237,283-285) */
+  const double *d_beta;                    /* [N]   BehaviouralModel beta (exploration_model.py:50)        */
+  const double *d_init_pose;               /* [N,3] Mouse(init_pos, init_ori)                              */
+  const double *d_init_prev;               /* [N,2] init_pos_discrete as doubles (exploration_model.py:47) */
+  const double *d_anxiety;                 /* [N,5] W_anx, p1, p2, p3, p4 (p4: GridTiles decision points)  */
+  const double *d_bcost_weight;            /* [N]   W_bcost                                                */
+  const double *d_bcost_table;             /* [N,A] vonmises(k).pdf(angle) * gamma-mask, host-precomputed
+                                              (behavioural_components.py:395-406)                          */
+  const double *d_experience;              /* [N,6] W_exp, xi, kappa_home, kappa_explo, theta_explo,
+                                              theta_home                                                   */
+  const double *d_bpersistence;            /* [N,4] W_bper, bp, Wm, Wnm                                    */
+  const double *d_vtable_weight;           /* [N]   W_values                                               */
+  const double *d_vtable;                  /* normalised table(s) (behavioural_components.py:530-535):
+                                              [X*Y] shared or [N,X*Y]                                      */
+  int32_t vtable_per_mouse;
+  int32_t reserved0;
+  const double *d_draws;                   /* [T,N] replayed uniforms of Generator.choice, or NULL         */
+  const uint64_t *d_pcg_state;             /* [N,4] PCG64 {state_hi, state_lo, inc_hi, inc_lo} or NULL     */
+  double visit_percentage;                 /* it_perc_visited_maze(percentage), metrics.py:698             */
+  /* outputs (NULL = not wanted) */
+  double *d_final_pose;                    /* [N,3]                                                        */
+  uint64_t *d_pcg_state_out;               /* [N,4] generator state after the run                          */
+  double *d_hist_pos;                      /* [T+1,N,2] mouse.history_position (time-major)                */
+  double *d_hist_ori;                      /* [T+1,N]   mouse.history_orientation                          */
+  uint8_t *d_hist_choice;                  /* [T,N]     index (into the A actions) of the chosen endpoint  */
+  uint32_t *d_occupancy;                   /* [N,X*Y]   occupancy_map over the T+1 history positions       */
+  int32_t *d_it_visit;                     /* [N]       it_perc_visited_maze                               */
+  int32_t *d_count_moving;                 /* [N]       motion_analysis count_moving                       */
+  int32_t *d_tile_counts;                  /* [N,8]     tile_analysis counts by tile code                  */
+  int32_t *d_status;                       /* [N]       0 ok; t+1 if step t had no reachable endpoint
+                                              (the reference raises from np.max([]))                        */
+  unsigned long long *d_occupancy_total;   /* [X*Y]     sum of the occupancy maps over all mice (atomics)  */
+  double *d_model_state;                   /* [N,5]     BehaviouralModel._prev_pos (x, y), _moving (0/1),
+                                              ExperienceComponent._familiarity, _ment_state (0 EXPLO/1 HOME) */
+} nm_sim_args;
+
+/* StandardExperiment.run(n_steps) for n_mice independent mice on the maze's device. */
+int nm_simulate(const nm_maze *mz, const nm_sim_args *args, void *stream);
+
+/* Vectorised Maze.is_movement_possible_cont on the device: d_segments [n,4] = (x1,y1,x2,y2),
+ * d_out u8[n] (1 possible).  maze.py:563-611 */
+int nm_maze_movements_possible_device(const nm_maze *mz, const double *d_segments, int64_t n, uint8_t *d_out,
+                                      void *stream);
 
 /* FP64 issue-rate micro-benchmark used for the roofline denominator: every thread runs `iters`
  * iterations of 8 independent DFMA chains; returns the instruction count via *h_fp64_instr.

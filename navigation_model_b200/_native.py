@@ -41,6 +41,7 @@ SIGNATURES = {
     "nm_mouse_reset": (C.c_int, [_p, _p, _p]),
     "nm_mouse_history_len": (_i64, [_p]),
     "nm_mouse_history": (C.c_int, [_p, _p, _p]),
+    "nm_mouse_adopt_trajectory": (C.c_int, [_p, _p, _p, _i64]),
     "nm_maze_upload": (_p, [_p, _p, C.c_int, C.c_int, C.c_double, C.c_int, _p]),
     "nm_maze_free": (None, [_p]),
     "nm_maze_num_states": (C.c_int, [_p]),
@@ -55,7 +56,34 @@ SIGNATURES = {
     "nm_loglik_sweep": (C.c_int, [C.c_int, _p, _p, _p, _p, _p, _i64, _p, C.c_int, _p, _p, _p]),
     "nm_argmin_nll": (C.c_int, [_p, C.c_int, _i64, _p, _p, _p]),
     "nm_fp64_peak_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, _p, C.POINTER(_i64), _p]),
+    "nm_simulate": (C.c_int, [_p, _p, _p]),
+    "nm_maze_movements_possible_device": (C.c_int, [_p, _p, _i64, _p, _p]),
 }
+
+NM_MAX_COMPONENTS = 8
+COMP_ANXIETY, COMP_BCOST, COMP_EXPERIENCE, COMP_BPERSISTENCE, COMP_VTABLE = 1, 2, 3, 4, 5
+
+
+class SimArgs(C.Structure):
+    """ctypes mirror of ``nm_sim_args`` (include/navmodel_b200.h)."""
+    _fields_ = [
+        ("n_mice", C.c_int64), ("n_steps", C.c_int32), ("n_actions", C.c_int32),
+        ("h_actions", C.c_void_p), ("h_zero_action", C.c_void_p),
+        ("n_components", C.c_int32),
+        ("component_kind", C.c_int32 * NM_MAX_COMPONENTS), ("component_active", C.c_int32 * NM_MAX_COMPONENTS),
+        ("d_beta", C.c_void_p), ("d_init_pose", C.c_void_p), ("d_init_prev", C.c_void_p),
+        ("d_anxiety", C.c_void_p), ("d_bcost_weight", C.c_void_p), ("d_bcost_table", C.c_void_p),
+        ("d_experience", C.c_void_p), ("d_bpersistence", C.c_void_p),
+        ("d_vtable_weight", C.c_void_p), ("d_vtable", C.c_void_p),
+        ("vtable_per_mouse", C.c_int32), ("reserved0", C.c_int32),
+        ("d_draws", C.c_void_p), ("d_pcg_state", C.c_void_p),
+        ("visit_percentage", C.c_double),
+        ("d_final_pose", C.c_void_p), ("d_pcg_state_out", C.c_void_p),
+        ("d_hist_pos", C.c_void_p), ("d_hist_ori", C.c_void_p), ("d_hist_choice", C.c_void_p),
+        ("d_occupancy", C.c_void_p), ("d_it_visit", C.c_void_p), ("d_count_moving", C.c_void_p),
+        ("d_tile_counts", C.c_void_p), ("d_status", C.c_void_p), ("d_occupancy_total", C.c_void_p),
+        ("d_model_state", C.c_void_p),
+    ]
 
 _lock = threading.Lock()
 _lib = None

@@ -1,0 +1,305 @@
+"""Batched forward simulation: many mice (parameter sets x seeds) in one kernel launch.
+
+Host layer above ``nm_simulate`` (``csrc/nm_sim.cu``): the grid version of the reference's
+``StandardExperiment(BehaviouralModel(components, ...), maze, Mouse(...)).run(iterations)``
+(``simulation/experiment.py:23-51``).  The model is described once (ordered component classes, the action
+set, the maze); every free parameter of ``BehaviouralModel.parameters`` (``beta`` + the components'
+descriptors, ``exploration_model.py:55-66``) becomes an array with one entry per mouse.
+
+Randomness: either ``seeds`` (each mouse draws from ``numpy.random.default_rng(seed)``'s PCG64 stream,
+generated on the device from the host-computed state) or ``draws[N, T]`` (replayed uniforms -- what the
+parity tests use).  PyTorch is used for device buffers only.  No CPU fallback.
+"""
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _native
+from .simulation import behavioural_components as bc
+from .sweep import DeviceMaze
+
+_KINDS = {_native.COMP_ANXIETY: "anxiety", _native.COMP_BCOST: "bcost", _native.COMP_EXPERIENCE: "experience",
+          _native.COMP_BPERSISTENCE: "bpersistence", _native.COMP_VTABLE: "vtable"}
+
+
+def pcg64_state_words(seeds):
+    """``uint64[N, 4]`` = (state_hi, state_lo, inc_hi, inc_lo) of ``numpy.random.default_rng(seed)`` for every
+    seed (or of already-constructed ``Generator`` objects)."""
+    out = np.empty((len(seeds), 4), dtype=np.uint64)
+    mask = (1 << 64) - 1
+    for i, s in enumerate(seeds):
+        gen = s if isinstance(s, np.random.Generator) else np.random.default_rng(None if s is None else int(s))
+        bg = gen.bit_generator
+        if type(bg).__name__ != "PCG64":
+            raise ValueError("only PCG64 generators can be continued on the device")
+        st = bg.state["state"]
+        out[i] = (st["state"] >> 64, st["state"] & mask, st["inc"] >> 64, st["inc"] & mask)
+    return out
+
+
+def set_pcg64_state(gen, words):
+    """Write a ``(state_hi, state_lo, inc_hi, inc_lo)`` quadruple back into a numpy ``Generator``."""
+    st = gen.bit_generator.state
+    st["state"] = {"state": (int(words[0]) << 64) | int(words[1]), "inc": (int(words[2]) << 64) | int(words[3])}
+    st["has_uint32"], st["uinteger"] = 0, 0
+    gen.bit_generator.state = st
+
+
+@dataclass
+class SimResult:
+    """Outputs of :meth:`BatchedExperiment.run` (numpy arrays; ``None`` when not requested)."""
+    final_pose: np.ndarray            # [N, 3]
+    status: np.ndarray                # [N] 0 ok, t+1 when step t had no reachable endpoint
+    it_visit: np.ndarray              # [N] it_perc_visited_maze(percentage)
+    count_moving: np.ndarray          # [N] motion_analysis
+    tile_counts: np.ndarray           # [N, 8] tile_analysis counts by tile code
+    occupancy: np.ndarray = None      # [N, X, Y] occupancy_map
+    occupancy_total: np.ndarray = None  # [X, Y] summed over mice
+    history_position: np.ndarray = None     # [N, T+1, 2]
+    history_orientation: np.ndarray = None  # [N, T+1]
+    choices: np.ndarray = None        # [N, T] chosen action index
+    pcg_state: np.ndarray = None      # [N, 4] generator state after the run
+    model_state: np.ndarray = None    # [N, 5] prev_pos.x, prev_pos.y, moving, familiarity, ment_state
+
+    def tile_analysis(self, maze, n_positions):
+        """``(perc, ratio, count)`` dicts keyed by tile type with one array entry per mouse
+        (``analysis/metrics.py:219-248``)."""
+        totals = maze.description()
+        count = {t: self.tile_counts[:, int(t)] for t in maze.MazeTile}
+        perc = {t: count[t] * 100 / n_positions for t in count}
+        ratio = {t: (count[t] / totals[t] if totals[t] > 0 else np.zeros(len(self.tile_counts))) for t in count}
+        return perc, ratio, count
+
+
+class BatchedExperiment:
+    """``N`` independent mice with the same model structure and per-mouse parameters.
+
+    >>> exp = BatchedExperiment(maze, actions, discrete_actions,
+    ...                         [AnxietyComponent, BiomechanicalCostComponent, ExperienceComponent,
+    ...                          BiomechPersistenceComponent, ValueTableComponent], v_table=V)
+    >>> res = exp.run(params, n_steps=10_000, init_pos=p0, init_ori=0.0, init_disc=(1, 1), seeds=range(N))
+    """
+
+    def __init__(self, maze, possible_actions, discrete_actions, components, v_table=None, active=None,
+                 device=None, v_table_normalised=False):
+        """
+        :param possible_actions: ``[A, 2]`` relative displacements of the Mouse (continuous units)
+        :param discrete_actions: ``[A, 2]`` the action list the biomechanical components are built from
+        :param components: ordered component classes (or instances, whose ``active`` flag is honoured)
+        :param v_table: raw value table(s) for ``ValueTableComponent``: ``[X, Y]`` shared or ``[N, X, Y]``
+        """
+        self.maze = maze
+        self.actions = np.ascontiguousarray(np.asarray(possible_actions, dtype=np.float64).reshape(-1, 2))
+        self.discrete_actions = np.asarray(discrete_actions)
+        if len(self.actions) != len(self.discrete_actions):
+            raise ValueError("possible_actions and discrete_actions must have the same length")
+        if not 1 <= len(self.actions) <= _native.NM_MAX_CAND:
+            raise ValueError(f"between 1 and {_native.NM_MAX_CAND} actions are supported")
+        self.zero_action = np.ascontiguousarray(np.all(self.discrete_actions == (0, 0), axis=1).astype(np.uint8))
+        self.kinds, self.active, self.classes = [], [], []
+        for i, c in enumerate(components):
+            cls = c if isinstance(c, type) else type(c)
+            kind = getattr(cls, "device_kind", None)
+            if kind is None:
+                raise ValueError(f"{cls.__name__} has no device implementation (host plugin components run through "
+                                 "StandardExperiment)")
+            self.kinds.append(kind)
+            self.classes.append(cls)
+            self.active.append(bool(active[i]) if active is not None else (True if isinstance(c, type) else c.active))
+        if len(self.kinds) > _native.NM_MAX_COMPONENTS:
+            raise ValueError("too many components")
+        if len(set(self.kinds)) != len(self.kinds):
+            raise ValueError("each component kind may appear once")
+        self.v_table = None if v_table is None else np.asarray(v_table, dtype=np.float64)
+        if _native.COMP_VTABLE in self.kinds and self.v_table is None:
+            raise ValueError("ValueTableComponent needs v_table")
+        self._device = device
+        self._dmaze = None
+        # True: v_table already holds ValueTableComponent._v_table (normalised once at construction)
+        self._normalise = (lambda t: np.asarray(t, dtype=np.float64)) if v_table_normalised else bc.normalise_v_table
+
+    @property
+    def parameter_names(self):
+        """Names of the per-mouse parameters, in ``BehaviouralModel.parameters`` order."""
+        names = ["beta"]
+        for cls in self.classes:
+            names += [d.name for d in cls.get_descriptors()]
+        return names
+
+    def parameter_bounds(self):
+        """``{name: (min, max, default)}`` from the component descriptors (the sweep's search space)."""
+        out = {"beta": (0.0, np.inf, None)}
+        for cls in self.classes:
+            for d in cls.get_descriptors():
+                out[d.name] = (d.minv, d.maxv, d.default)
+        return out
+
+    def _validate(self, params, N):
+        cols = {}
+        for name in self.parameter_names:
+            if name not in params:
+                raise RuntimeError(f"Value for {name} has not been specified")
+            a = np.asarray(params[name], dtype=np.float64).reshape(-1)
+            if a.size == 1 and N != 1:
+                a = np.full(N, a[0])
+            if a.size != N:
+                raise ValueError(f"parameter {name}: expected {N} values, got {a.size}")
+            cols[name] = a
+        for name, (lo, hi, _) in self.parameter_bounds().items():
+            if name == "beta":
+                continue
+            bad = ~((cols[name] >= lo) & (cols[name] <= hi))
+            if bad.any():
+                i = int(np.flatnonzero(bad)[0])
+                raise RuntimeError(f"Wrong value set for property '{name}' ({cols[name][i]}), must be in range "
+                                   f"[{lo}; {hi}]")
+        return cols
+
+    def run(self, params, n_steps, init_pos, init_ori=0.0, init_disc=None, seeds=None, draws=None,
+            visit_percentage=80, history=False, occupancy=False, occupancy_total=False, generators=None):
+        """Simulate ``n_steps`` iterations for every mouse.
+
+        :param params: ``{name: array[N] or scalar}`` for every name in :attr:`parameter_names`
+        :param init_pos: ``[2]`` or ``[N, 2]``; ``init_ori``: scalar or ``[N]``
+        :param init_disc: ``init_pos_discrete`` handed to ``BehaviouralModel`` (default: tile of ``init_pos``)
+        :param seeds: ``[N]`` seeds of ``default_rng`` -- or ``draws[N, n_steps]`` replayed uniforms
+        :param history: also return the full position / orientation / choice histories
+        """
+        import torch
+        _native.require_device()
+        if (seeds is None) == (draws is None) and generators is None:
+            raise ValueError("give exactly one of seeds and draws")
+        if draws is not None:
+            draws = np.asarray(draws, dtype=np.float64)
+            N = draws.shape[0]
+            if draws.shape != (N, n_steps):
+                raise ValueError("draws must have shape [N, n_steps]")
+        elif generators is not None:
+            N = len(generators)
+        else:
+            seeds = list(seeds)
+            N = len(seeds)
+        cols = self._validate(params, N)
+        if self._dmaze is None:
+            self._dmaze = DeviceMaze(self.maze, self._device)
+        dev = self._dmaze.torch_device
+        X, Y = self.maze.shape
+        nT = X * Y
+        T = int(n_steps)
+
+        pose = np.empty((N, 3))
+        pose[:, :2] = np.asarray(init_pos, dtype=np.float64).reshape(-1, 2)
+        pose[:, 2] = np.asarray(init_ori, dtype=np.float64).reshape(-1)
+        if init_disc is None:
+            prev = self.maze.cont2disc_array(pose[:, :2]).astype(np.float64)
+        else:
+            prev = np.empty((N, 2))
+            prev[:] = np.asarray(init_disc, dtype=np.float64).reshape(-1, 2)
+
+        keep = []  # device tensors must outlive the launch
+
+        def dev_f64(a):
+            t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+            keep.append(t)
+            return t
+
+        def out(shape, dtype, zero=False):
+            t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=dev)
+            keep.append(t)
+            return t
+
+        args = _native.SimArgs()
+        args.n_mice, args.n_steps, args.n_actions = N, T, len(self.actions)
+        args.h_actions = self.actions.ctypes.data
+        args.h_zero_action = self.zero_action.ctypes.data
+        args.n_components = len(self.kinds)
+        for i, (k, act) in enumerate(zip(self.kinds, self.active)):
+            args.component_kind[i] = k
+            args.component_active[i] = int(act)
+        args.d_beta = dev_f64(cols["beta"]).data_ptr()
+        args.d_init_pose = dev_f64(pose).data_ptr()
+        args.d_init_prev = dev_f64(prev).data_ptr()
+        if _native.COMP_ANXIETY in self.kinds:
+            p4 = cols["p4"] if "p4" in cols else np.zeros(N)
+            args.d_anxiety = dev_f64(np.stack([cols["W_anx"], cols["p1"], cols["p2"], cols["p3"], p4], 1)).data_ptr()
+        if _native.COMP_BCOST in self.kinds:
+            args.d_bcost_weight = dev_f64(cols["W_bcost"]).data_ptr()
+            args.d_bcost_table = dev_f64(bc.bcost_tables(self.discrete_actions, cols["k"], cols["gamma"])).data_ptr()
+        if _native.COMP_EXPERIENCE in self.kinds:
+            args.d_experience = dev_f64(np.stack([cols[n] for n in ("W_exp", "xi", "kappa_home", "kappa_explo",
+                                                                    "theta_explo", "theta_home")], 1)).data_ptr()
+        if _native.COMP_BPERSISTENCE in self.kinds:
+            args.d_bpersistence = dev_f64(np.stack([cols[n] for n in ("W_bper", "bp", "Wm", "Wnm")], 1)).data_ptr()
+        if _native.COMP_VTABLE in self.kinds:
+            args.d_vtable_weight = dev_f64(cols["W_values"]).data_ptr()
+            v = self.v_table
+            if v.shape == (X, Y):
+                args.d_vtable = dev_f64(self._normalise(v).reshape(-1)).data_ptr()
+                args.vtable_per_mouse = 0
+            elif v.shape == (N, X, Y):
+                args.d_vtable = dev_f64(np.stack([self._normalise(t) for t in v]).reshape(N, -1)).data_ptr()
+                args.vtable_per_mouse = 1
+            else:
+                raise ValueError(f"v_table must have shape {(X, Y)} or {(N, X, Y)}")
+        if draws is not None:
+            args.d_draws = dev_f64(draws.T).data_ptr()  # time-major [T, N]: coalesced per step
+        else:
+            words = pcg64_state_words(generators if generators is not None else seeds)
+            t = torch.from_numpy(words.view(np.int64)).to(dev)
+            keep.append(t)
+            args.d_pcg_state = t.data_ptr()
+        args.visit_percentage = float(visit_percentage)
+
+        o_pose = out((N, 3), torch.float64)
+        o_pcg = out((N, 4), torch.int64)
+        o_it = out((N,), torch.int32)
+        o_mov = out((N,), torch.int32)
+        o_tc = out((N, 8), torch.int32)
+        o_st = out((N,), torch.int32)
+        o_ms = out((N, 5), torch.float64)
+        args.d_final_pose, args.d_pcg_state_out = o_pose.data_ptr(), o_pcg.data_ptr()
+        args.d_it_visit, args.d_count_moving = o_it.data_ptr(), o_mov.data_ptr()
+        args.d_tile_counts, args.d_status, args.d_model_state = o_tc.data_ptr(), o_st.data_ptr(), o_ms.data_ptr()
+        o_hp = o_ho = o_hc = o_occ = o_tot = None
+        if history:
+            o_hp, o_ho = out((T + 1, N, 2), torch.float64, zero=True), out((T + 1, N), torch.float64, zero=True)
+            o_hc = out((T, N), torch.uint8, zero=True)
+            args.d_hist_pos, args.d_hist_ori, args.d_hist_choice = o_hp.data_ptr(), o_ho.data_ptr(), o_hc.data_ptr()
+        if occupancy:
+            o_occ = out((N, nT), torch.int32)
+            args.d_occupancy = o_occ.data_ptr()
+        if occupancy_total:
+            o_tot = out((nT,), torch.int64, zero=True)
+            args.d_occupancy_total = o_tot.data_ptr()
+
+        with torch.cuda.device(dev):
+            _native.check(self._dmaze._lib.nm_simulate(self._dmaze.handle, C.byref(args), _native.cuda_stream_ptr()))
+            torch.cuda.current_stream().synchronize()
+
+        res = SimResult(final_pose=o_pose.cpu().numpy(), status=o_st.cpu().numpy(), it_visit=o_it.cpu().numpy(),
+                        count_moving=o_mov.cpu().numpy(), tile_counts=o_tc.cpu().numpy(),
+                        pcg_state=o_pcg.cpu().numpy().view(np.uint64), model_state=o_ms.cpu().numpy())
+        if history:
+            res.history_position = np.ascontiguousarray(o_hp.cpu().numpy().transpose(1, 0, 2))
+            res.history_orientation = np.ascontiguousarray(o_ho.cpu().numpy().T)
+            res.choices = np.ascontiguousarray(o_hc.cpu().numpy().T)
+        if occupancy:
+            res.occupancy = o_occ.cpu().numpy().reshape(N, X, Y)
+        if occupancy_total:
+            res.occupancy_total = o_tot.cpu().numpy().reshape(X, Y)
+        return res
+
+
+def movements_possible(maze, segments, device=None):
+    """Vectorised ``Maze.is_movement_possible_cont`` on the GPU: ``segments[n, 4] = (x1, y1, x2, y2)``."""
+    import torch
+    _native.require_device()
+    dm = DeviceMaze(maze, device)
+    seg = torch.from_numpy(np.ascontiguousarray(segments, dtype=np.float64).reshape(-1, 4)).to(dm.torch_device)
+    res = torch.empty(seg.shape[0], dtype=torch.uint8, device=dm.torch_device)
+    with torch.cuda.device(dm.torch_device):
+        _native.check(dm._lib.nm_maze_movements_possible_device(dm.handle, _native.tensor_ptr(seg), seg.shape[0],
+                                                                _native.tensor_ptr(res), _native.cuda_stream_ptr()))
+    return res.cpu().numpy().astype(bool)
+

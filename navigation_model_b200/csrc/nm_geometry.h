@@ -48,8 +48,17 @@ NM_HD bool nm_tile_visitable(const NmMazeView &m, int x, int y) {
 }
 
 // int() of a float floor-quotient; clamp so that huge / non-finite values stay "outside the maze".
+//
+// Python's `x // w` equals the mathematical floor of the EXACT quotient (divmod is fmod-based).  On
+// the device that integer is obtained without fmod: q0 = floor(fl(x / w)) can only be n or n + 1, and
+// the residual x - q0 * w, evaluated exactly-rounded by one FMA, is negative iff q0 = n + 1.
 NM_HD int nm_tile_index(double x, double st) {
+#ifdef __CUDA_ARCH__
+  double q = floor(__ddiv_rn(x, st));
+  if (fma(-q, st, x) < 0.0) q -= 1.0;
+#else
   double q = py_floordiv(x, st);
+#endif
   if (!(q > -1.0e9)) return -1000000000;
   if (!(q < 1.0e9)) return 1000000000;
   return (int)q;

@@ -131,3 +131,18 @@ extern "C" int nm_mouse_history(const nm_mouse *m, double *pos_out, double *ori_
   if (ori_out) for (size_t i = 0; i < n; ++i) ori_out[i] = m->hist_ori[i];
   return NM_OK;
 }
+
+extern "C" int nm_mouse_adopt_trajectory(nm_mouse *m, const double *pos, const double *ori, int64_t n) {
+  NM_CHECK_ARG(m && n >= 0 && (n == 0 || (pos && ori)), "nm_mouse_adopt_trajectory: bad argument");
+  for (int64_t i = 0; i < n; ++i) {
+    m->pos[0] = pos[2 * i];
+    m->pos[1] = pos[2 * i + 1];
+    m->ori = ori[i];
+    if (m->save_history) {
+      m->hist_pos.push_back(m->pos[0]);
+      m->hist_pos.push_back(m->pos[1]);
+      m->hist_ori.push_back(m->ori);
+    }
+  }
+  return NM_OK;
+}

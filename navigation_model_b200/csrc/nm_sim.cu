@@ -1,0 +1,418 @@
+// Forward simulation of many independent mice: StandardExperiment.run on the device.
+//
+// Mapping (DESIGN.md "simulation kernel"):
+//   * one THREAD owns one mouse: pose, softmax policy state, experience map and generator live in
+//     registers / shared memory for the whole run; nothing is written to HBM per step unless a
+//     history is requested;
+//   * the visit-count map is kept in shared memory as count[tile][thread] (u32): one map serves both the
+//     ExperienceComponent (visits so far, behavioural_components.py:456-479) and the fused occupancy
+//     metric (analysis/metrics.py:204-216);
+//   * the maze tile table is staged once per CTA into shared memory; the ray / AABB walk reads it there;
+//   * random draws are either replayed (`draws[T, N]`, coalesced) or generated on the device with a
+//     numpy-identical PCG64 (XSL-RR 128/64) from host-computed (state, inc).
+//
+// Reference loop restated here, operation for operation (no FMA contraction, -fmad=false):
+//   StandardExperiment.run                     simulation/experiment.py:33-51
+//   Mouse.get_endpoints / move_to              src/_navigation_model/mouse.cpp:64-87
+//   Maze.are_movements_possible_cont           simulation/maze.py:563-627
+//   BehaviouralModel.decision_making           simulation/exploration_model.py:68-109
+//   components                                 simulation/behavioural_components.py:315-544
+//   Generator.choice(a, p=p)                   numpy: cdf = cumsum(p); cdf /= cdf[-1]; searchsorted(u, 'right')
+//   fused metrics                              analysis/metrics.py:192-248, 425-442, 697-731
+#include <cuda_runtime.h>
+
+#include "nm_common.h"
+#include "nm_pose.h"
+
+namespace {
+
+constexpr int kA = NM_MAX_CAND;
+constexpr int kSimThreads = 128;
+
+struct SimDev {
+  nm_sim_args a;  // device-visible copy (host pointers inside are not dereferenced on the device)
+  const uint8_t *tiles;
+  int X, Y, n_visitable;
+  double st;
+  double act[kA][2];
+  uint8_t zero_act[kA];
+};
+
+__device__ __forceinline__ uint64_t rotr64(uint64_t v, unsigned r) { return (v >> r) | (v << ((64 - r) & 63)); }
+
+// numpy PCG64: 128-bit LCG step, then XSL-RR output of the NEW state; random() = (u64 >> 11) * 2^-53
+struct Pcg64 {
+  unsigned __int128 state, inc;
+  __device__ __forceinline__ double next_double() {
+    const unsigned __int128 mult = ((unsigned __int128)0x2360ED051FC65DA4ULL << 64) | 0x4385DF649FCCF645ULL;
+    state = state * mult + inc;
+    const uint64_t hi = (uint64_t)(state >> 64), lo = (uint64_t)state;
+    const uint64_t out = rotr64(hi ^ lo, (unsigned)(hi >> 58));
+    return (double)(out >> 11) * (1.0 / 9007199254740992.0);
+  }
+};
+
+__global__ void __launch_bounds__(kSimThreads) nm_sim_kernel(const SimDev d) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nT = d.X * d.Y;
+  uint32_t *count = reinterpret_cast<uint32_t *>(smem_raw);                 // [nT][blockDim.x]
+  uint8_t *tiles = smem_raw + (size_t)nT * blockDim.x * sizeof(uint32_t);   // [nT]
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < nT; i += nt) tiles[i] = d.tiles[i];
+  for (int i = 0; i < nT; ++i) count[i * nt + tid] = 0u;
+  __syncthreads();
+
+  const nm_sim_args &a = d.a;
+  const int64_t n = (int64_t)blockIdx.x * nt + tid;
+  const int64_t N = a.n_mice;
+  const bool live = n < N;
+  NmMazeView mv;
+  mv.tiles = tiles;
+  mv.X = d.X;
+  mv.Y = d.Y;
+  mv.st = d.st;
+  const int A = a.n_actions;
+  const int T = a.n_steps;
+  uint32_t *cnt = count + tid;
+
+  int status = 0;
+  if (live) {
+    // ---- per-mouse state -------------------------------------------------------------------------
+    double px = a.d_init_pose[3 * n], py = a.d_init_pose[3 * n + 1], ori = a.d_init_pose[3 * n + 2];
+    double prevx = a.d_init_prev[2 * n], prevy = a.d_init_prev[2 * n + 1];
+    bool moving = false;  // BehaviouralModel._moving (True when the last choice was to STAY)
+    const double beta = a.d_beta[n];
+    double anx_w = 0, anx_tab[5] = {-1.0, 0, 0, 0, 0};
+    if (a.d_anxiety) {
+      const double *q = a.d_anxiety + 5 * n;
+      anx_w = q[0];
+      anx_tab[2] = q[1];                 // CORNER: p1                    behavioural_components.py:364
+      anx_tab[1] = q[2] * q[1];          // WALL:   p2 * p1
+      anx_tab[3] = q[3] * q[2] * q[1];   // CENTRE: p3 * p2 * p1
+      anx_tab[4] = q[4];                 // DECISION_POINT: p4            :332-333
+    }
+    double bc_w = 0, bc_tab[kA];
+#pragma unroll
+    for (int i = 0; i < kA; ++i) bc_tab[i] = 0.0;
+    if (a.d_bcost_table) {
+      bc_w = a.d_bcost_weight[n];
+#pragma unroll
+      for (int i = 0; i < kA; ++i)
+        if (i < A) bc_tab[i] = a.d_bcost_table[n * A + i];
+    }
+    double ex_w = 0, xi = 0, k_home = 0, k_explo = 0, th_explo = 0, th_home = 0, fam = 0.0;
+    bool home = false;  // ExperienceComponent.State.EXPLO at start (:440)
+    if (a.d_experience) {
+      const double *q = a.d_experience + 6 * n;
+      ex_w = q[0]; xi = q[1]; k_home = q[2]; k_explo = q[3]; th_explo = q[4]; th_home = q[5];
+    }
+    double bp_w = 0, bp = 0, bp_wm = 0, bp_wnm = 0;
+    if (a.d_bpersistence) {
+      const double *q = a.d_bpersistence + 4 * n;
+      bp_w = q[0]; bp = q[1]; bp_wm = q[2] * q[1]; bp_wnm = q[3] * q[1];  // Wm*bp, Wnm*bp  (:502-506)
+    }
+    double vt_w = 0;
+    const double *vt = nullptr;
+    if (a.d_vtable) {
+      vt_w = a.d_vtable_weight[n];
+      vt = a.vtable_per_mouse ? a.d_vtable + n * nT : a.d_vtable;
+    }
+    Pcg64 rng;
+    rng.state = 0;
+    rng.inc = 0;
+    if (a.d_pcg_state) {
+      const uint64_t *q = a.d_pcg_state + 4 * n;
+      rng.state = ((unsigned __int128)q[0] << 64) | q[1];
+      rng.inc = ((unsigned __int128)q[2] << 64) | q[3];
+    }
+
+    // ---- fused metrics over the history positions (history[0] = initial position, mouse.cpp:58-61) ----
+    int n_visited = 0, it_visit = T + 1, count_moving = 0;
+    int tile_counts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int cur_tx = nm_tile_index(px, d.st), cur_ty = nm_tile_index(py, d.st);
+    auto record_position = [&](int t_idx, int tx, int ty, bool inside) {
+      // occupancy_map / tile_analysis / it_perc_visited_maze on history entry t_idx
+      if (!inside) return;
+      const int tile = tx * d.Y + ty;
+      const uint32_t c = cnt[tile * nt];
+      cnt[tile * nt] = c + 1u;
+      tile_counts[tiles[tile] & 7] += 1;
+      if (c == 0u) {
+        n_visited += 1;
+        // perc = n_visited * 100 / number_visitable_tiles >= percentage      metrics.py:711-721
+        if (it_visit == T + 1 && (double)(n_visited * 100) / (double)d.n_visitable >= a.visit_percentage)
+          it_visit = t_idx;
+      }
+    };
+    bool cur_inside = cur_tx >= 0 && cur_tx < d.X && cur_ty >= 0 && cur_ty < d.Y;
+    // NOTE: the ExperienceComponent increments count[x, y] of the CURRENT tile at every decision
+    // (:456) -- that is exactly "occupancy over history[0..t]", so history entry t is recorded at the
+    // top of step t and the final entry after the loop.
+    if (a.d_hist_pos) {
+      a.d_hist_pos[2 * n] = px;
+      a.d_hist_pos[2 * n + 1] = py;
+    }
+    if (a.d_hist_ori) a.d_hist_ori[n] = ori;
+
+    for (int t = 0; t < T; ++t) {
+      record_position(t, cur_tx, cur_ty, cur_inside);
+      // -- endpoints + reachability                                          experiment.py:36-38
+      const double c = cos(ori), s = sin(ori);
+      double ex[kA], ey[kA];
+      unsigned vis = 0u;
+#pragma unroll
+      for (int i = 0; i < kA; ++i) {
+        ex[i] = 0.0;
+        ey[i] = 0.0;
+        if (i < A) {
+          nm_pose_endpoint(c, s, px, py, d.act[i][0], d.act[i][1], &ex[i], &ey[i]);
+          if (nm_move_possible(mv, px, py, ex[i], ey[i])) vis |= 1u << i;
+        }
+      }
+      const int K = __popc(vis);
+      if (K == 0) {  // np.max([]) raises in the reference (exploration_model.py:92)
+        status = t + 1;
+        break;
+      }
+      // -- component updates                                                 exploration_model.py:79-81
+      if (a.d_experience) {  // :456-466 (count of the current tile was just incremented above)
+        const double nvis = cur_inside ? (double)cnt[(cur_tx * d.Y + cur_ty) * nt] : 0.0;
+        fam = (1.0 - xi) * fam + xi * nvis;
+        if (home && fam >= th_explo) home = false;
+        else if (!home && fam < th_home) home = true;
+      }
+      // -- val_fin = beta * sum_c weighted_values_c                           :84-87
+      // (candidates stay in action order: the reference's list is the action list filtered by
+      //  reachability, so "k-th candidate" == "k-th reachable action" and nothing needs compacting)
+      double val[kA];
+      double vmax = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < kA; ++i) {
+        val[i] = 0.0;
+        if (vis & (1u << i)) {
+          const int tx = nm_tile_index(ex[i], d.st), ty = nm_tile_index(ey[i], d.st);
+          const int tile = tx * d.Y + ty;
+          double acc = 0.0;
+          for (int ci = 0; ci < a.n_components; ++ci) {
+            if (!a.component_active[ci]) continue;  // inactive: contributes integer 0 (:283-285)
+            double v;
+            switch (a.component_kind[ci]) {
+              case NM_COMP_ANXIETY:
+                v = anx_tab[tiles[tile] > 4 ? 0 : tiles[tile]] * anx_w;
+                break;
+              case NM_COMP_BCOST:  // cached[is_visitable] if moving else zeros   :410-413
+                v = (moving ? bc_tab[i] : 0.0) * bc_w;
+                break;
+              case NM_COMP_EXPERIENCE: {  // :473-479
+                const double cn = (double)cnt[tile * nt];
+                v = home ? (1.0 - exp(-k_home * cn)) : exp(-k_explo * cn);
+                v = v * ex_w;
+                break;
+              }
+              case NM_COMP_BPERSISTENCE:  // :508-513
+                v = (moving ? (d.zero_act[i] ? bp_wm : bp) : (d.zero_act[i] ? bp : bp_wnm)) * bp_w;
+                break;
+              case NM_COMP_VTABLE:  // :537-541
+                v = vt[tile] * vt_w;
+                break;
+              default:
+                v = 0.0;
+            }
+            acc = acc + v;
+          }
+          acc = beta * acc;
+          val[i] = acc;
+          vmax = fmax(vmax, acc);
+        }
+      }
+      // -- softmax + numpy Generator.choice                                   :92-98
+      double e[kA];
+#pragma unroll
+      for (int i = 0; i < kA; ++i) e[i] = (vis & (1u << i)) ? exp(val[i] - vmax) : 0.0;
+      double sum;
+      if (K == kA) {
+        sum = ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));  // numpy pairwise, n == 8
+      } else {
+        sum = 0.0;  // n < 8: sequential from 0.0 over the candidates
+#pragma unroll
+        for (int i = 0; i < kA; ++i)
+          if (vis & (1u << i)) sum = sum + e[i];
+      }
+      double cdf[kA];
+      double run = 0.0;
+      bool first = true;
+      int last_vis = 0;
+#pragma unroll
+      for (int i = 0; i < kA; ++i) {
+        if (vis & (1u << i)) {
+          const double p = e[i] / sum;
+          run = first ? p : run + p;  // cumsum
+          first = false;
+          last_vis = i;
+        }
+        cdf[i] = run;
+      }
+      const double last = run;
+      const double u = a.d_draws ? a.d_draws[(int64_t)t * N + n] : rng.next_double();
+      // searchsorted(cdf / cdf[-1], u, side='right'): the first candidate whose normalised cdf exceeds u
+      int act_idx = -1;
+#pragma unroll
+      for (int i = 0; i < kA; ++i)
+        if (act_idx < 0 && (vis & (1u << i)) && !(cdf[i] / last <= u)) act_idx = i;
+      if (act_idx < 0) act_idx = last_vis;  // cannot happen for u < 1 and finite probabilities
+      double nx = 0.0, ny = 0.0;
+#pragma unroll
+      for (int i = 0; i < kA; ++i)
+        if (i == act_idx) {
+          nx = ex[i];
+          ny = ey[i];
+        }
+      // -- moving flag                                                        :101-107
+      moving = (prevx == nx) && (prevy == ny);
+      prevx = nx;
+      prevy = ny;
+      // -- Mouse.move_to                                                      mouse.cpp:75-87
+      if (!nm_pos_is_approx(nx, ny, px, py)) {
+        ori = atan2(ny - py, nx - px);
+        px = nx;
+        py = ny;
+      }
+      const int ntx = nm_tile_index(px, d.st), nty = nm_tile_index(py, d.st);
+      if (ntx != cur_tx || nty != cur_ty) count_moving += 1;  // motion_analysis, metrics.py:437-440
+      cur_tx = ntx;
+      cur_ty = nty;
+      cur_inside = cur_tx >= 0 && cur_tx < d.X && cur_ty >= 0 && cur_ty < d.Y;
+      if (a.d_hist_pos) {
+        a.d_hist_pos[((int64_t)(t + 1) * N + n) * 2] = px;
+        a.d_hist_pos[((int64_t)(t + 1) * N + n) * 2 + 1] = py;
+      }
+      if (a.d_hist_ori) a.d_hist_ori[(int64_t)(t + 1) * N + n] = ori;
+      if (a.d_hist_choice) a.d_hist_choice[(int64_t)t * N + n] = (uint8_t)act_idx;
+    }
+    if (status == 0) record_position(T, cur_tx, cur_ty, cur_inside);
+
+    if (a.d_final_pose) {
+      a.d_final_pose[3 * n] = px;
+      a.d_final_pose[3 * n + 1] = py;
+      a.d_final_pose[3 * n + 2] = ori;
+    }
+    if (a.d_pcg_state_out) {
+      uint64_t *q = a.d_pcg_state_out + 4 * n;
+      q[0] = (uint64_t)(rng.state >> 64); q[1] = (uint64_t)rng.state;
+      q[2] = (uint64_t)(rng.inc >> 64);   q[3] = (uint64_t)rng.inc;
+    }
+    if (a.d_it_visit) a.d_it_visit[n] = it_visit;
+    if (a.d_count_moving) a.d_count_moving[n] = count_moving;
+    if (a.d_tile_counts) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a.d_tile_counts[8 * n + i] = tile_counts[i];
+    }
+    if (a.d_status) a.d_status[n] = status;
+    if (a.d_model_state) {
+      double *q = a.d_model_state + 5 * n;
+      q[0] = prevx; q[1] = prevy; q[2] = moving ? 1.0 : 0.0; q[3] = fam; q[4] = home ? 1.0 : 0.0;
+    }
+  }
+
+  // ---- occupancy maps: coalesced write through a transposed read of count[tile][thread] -------------
+  if (a.d_occupancy || a.d_occupancy_total) {
+    __syncthreads();
+    const int64_t n0 = (int64_t)blockIdx.x * nt;
+    const int64_t np = (N - n0 < nt) ? (N - n0) : nt;
+    if (a.d_occupancy) {
+      uint32_t *dst = a.d_occupancy + n0 * nT;
+      for (int64_t i = tid; i < np * nT; i += nt) {
+        const int u = (int)(i / nT), tile = (int)(i - (int64_t)u * nT);
+        dst[i] = count[tile * nt + u];
+      }
+    }
+    if (a.d_occupancy_total) {
+      for (int tile = tid; tile < nT; tile += nt) {
+        unsigned long long acc = 0ull;
+        for (int u = 0; u < (int)np; ++u) acc += count[tile * nt + u];
+        if (acc) atomicAdd(a.d_occupancy_total + tile, acc);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) nm_segments_kernel(const uint8_t *__restrict__ g_tiles, int X, int Y, double st,
+                                                          const double *__restrict__ seg, int64_t n,
+                                                          uint8_t *__restrict__ out) {
+  extern __shared__ unsigned char sm_tiles[];
+  for (int i = threadIdx.x; i < X * Y; i += blockDim.x) sm_tiles[i] = g_tiles[i];
+  __syncthreads();
+  NmMazeView mv;
+  mv.tiles = sm_tiles;
+  mv.X = X;
+  mv.Y = Y;
+  mv.st = st;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = nm_move_possible(mv, seg[4 * i], seg[4 * i + 1], seg[4 * i + 2], seg[4 * i + 3]) ? 1 : 0;
+}
+
+}  // namespace
+
+extern "C" int nm_simulate(const nm_maze *mz, const nm_sim_args *args, void *stream) {
+  NM_CHECK_ARG(mz && args, "nm_simulate: NULL argument");
+  NM_CHECK_ARG(mz->device >= 0, "nm_simulate: the maze has not been uploaded to a CUDA device");
+  const nm_sim_args &a = *args;
+  NM_CHECK_ARG(a.n_mice >= 0 && a.n_steps >= 0, "nm_simulate: negative size");
+  NM_CHECK_ARG(a.n_actions >= 1 && a.n_actions <= NM_MAX_CAND && a.h_actions,
+               "nm_simulate: need 1..%d relative actions", NM_MAX_CAND);
+  NM_CHECK_ARG(a.n_components >= 0 && a.n_components <= NM_MAX_COMPONENTS, "nm_simulate: too many components");
+  NM_CHECK_ARG(a.d_beta && a.d_init_pose && a.d_init_prev, "nm_simulate: NULL beta / init_pose / init_prev");
+  NM_CHECK_ARG((a.d_draws != nullptr) != (a.d_pcg_state != nullptr),
+               "nm_simulate: give exactly one of d_draws (replayed uniforms) and d_pcg_state");
+  for (int i = 0; i < a.n_components; ++i) {
+    const int k = a.component_kind[i];
+    const bool ok = (k == NM_COMP_ANXIETY && a.d_anxiety) || (k == NM_COMP_BCOST && a.d_bcost_table && a.d_bcost_weight) ||
+                    (k == NM_COMP_EXPERIENCE && a.d_experience) || (k == NM_COMP_BPERSISTENCE && a.d_bpersistence) ||
+                    (k == NM_COMP_VTABLE && a.d_vtable && a.d_vtable_weight);
+    NM_CHECK_ARG(ok, "nm_simulate: component %d (kind %d) has no parameter array", i, k);
+    if ((k == NM_COMP_BCOST || k == NM_COMP_BPERSISTENCE))
+      NM_CHECK_ARG(a.h_zero_action, "nm_simulate: h_zero_action is required by the biomechanical components");
+  }
+  if (a.n_mice == 0) return NM_OK;
+  if (cudaSetDevice(mz->device) != cudaSuccess) return nm_fail(NM_ERR_CUDA, "cudaSetDevice(%d) failed", mz->device);
+  SimDev d;
+  d.a = a;
+  d.tiles = mz->d_tiles;
+  d.X = mz->X;
+  d.Y = mz->Y;
+  d.n_visitable = mz->num_states;
+  d.st = mz->size_tile;
+  for (int i = 0; i < kA; ++i) {
+    d.act[i][0] = i < a.n_actions ? a.h_actions[2 * i] : 0.0;
+    d.act[i][1] = i < a.n_actions ? a.h_actions[2 * i + 1] : 0.0;
+    d.zero_act[i] = (i < a.n_actions && a.h_zero_action) ? a.h_zero_action[i] : 0;
+  }
+  const int nT = mz->X * mz->Y;
+  int threads = kSimThreads;
+  while (threads > 32 && (size_t)nT * threads * 4 + nT > 200 * 1024) threads /= 2;
+  const size_t smem = (size_t)nT * threads * sizeof(uint32_t) + (size_t)nT;
+  NM_CHECK_ARG(smem <= 227 * 1024, "nm_simulate: maze of %d tiles does not fit the shared-memory visit map", nT);
+  cudaError_t e = cudaFuncSetAttribute(nm_sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  const int64_t blocks = (a.n_mice + threads - 1) / threads;
+  NM_CHECK_ARG(blocks <= 2147483647LL, "nm_simulate: too many mice for one launch");
+  nm_sim_kernel<<<(unsigned)blocks, threads, smem, (cudaStream_t)stream>>>(d);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_sim_kernel launch: %s", cudaGetErrorString(e));
+  return NM_OK;
+}
+
+extern "C" int nm_maze_movements_possible_device(const nm_maze *mz, const double *d_segments, int64_t n,
+                                                 uint8_t *d_out, void *stream) {
+  NM_CHECK_ARG(mz && mz->device >= 0, "nm_maze_movements_possible_device: maze not on a device");
+  NM_CHECK_ARG(n >= 0 && (n == 0 || (d_segments && d_out)), "nm_maze_movements_possible_device: NULL argument");
+  if (n == 0) return NM_OK;
+  if (cudaSetDevice(mz->device) != cudaSuccess) return nm_fail(NM_ERR_CUDA, "cudaSetDevice(%d) failed", mz->device);
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  nm_segments_kernel<<<blocks, 256, (size_t)mz->X * mz->Y, (cudaStream_t)stream>>>(mz->d_tiles, mz->X, mz->Y,
+                                                                                  mz->size_tile, d_segments, n, d_out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_segments_kernel launch: %s", cudaGetErrorString(e));
+  return NM_OK;
+}

@@ -31,6 +31,12 @@ class Mouse:
         self._h = _native.check_handle(lib.nm_mouse_create(_native.np_ptr(pos), float(init_ori), _native.np_ptr(acts),
                                                            acts.shape[0], acts.shape[1], int(bool(save_history))))
         self._n_actions = acts.shape[0]
+        self._actions = acts.copy()
+
+    @property
+    def possible_actions(self):
+        """The ``[A, 2]`` relative actions the mouse was built with (copy)."""
+        return self._actions.copy()
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None

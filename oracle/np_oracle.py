@@ -290,3 +290,147 @@ M9_LAYOUT = "\n".join(["CWWWWWWWC", "WMMMMMMMW", "CWWWWWWWW", "VVVVVVVWW", "VVVV
 M9_SUBAREAS = "\n".join(["111222333", "111222333", "111222333", "000000044", "000000044", "000000044",
                          "777666555", "777666555", "777666555"])
 M9_SIZE_TILE = 0.111
+
+
+# ==================================================================================== simulation
+# Restatement of StandardExperiment.run (simulation/experiment.py:23-51) with BehaviouralModel
+# (simulation/exploration_model.py:68-109), the five behavioural components
+# (simulation/behavioural_components.py:348-544) and the C++ Mouse.  Pinned by
+# tests/golden/sim_golden.npz (histories, probabilities and metrics produced by the reference).
+COMP_ANXIETY, COMP_BCOST, COMP_EXPERIENCE, COMP_BPERSISTENCE, COMP_VTABLE = 1, 2, 3, 4, 5
+
+
+def bcost_table(discrete_actions, k, gamma):
+    """BiomechanicalCostComponent.__init__ cached values (behavioural_components.py:393-406)."""
+    from scipy.stats import vonmises
+    acts = np.array(discrete_actions)
+    angles = np.arctan2(acts[:, 1], acts[:, 0])
+    cached = vonmises(k).pdf(angles)
+    cached[np.all(acts == (0, 0), axis=1)] = 0.0
+    dist = np.linalg.norm(acts, ord=np.inf, axis=1)
+    gammas = np.ones(len(acts)) * gamma
+    gammas[dist < 2] = 1
+    return cached * gammas
+
+
+def normalise_vtable(v_table):
+    """ValueTableComponent.__init__ (behavioural_components.py:530-535)."""
+    v_table = np.asarray(v_table, dtype=np.float64)
+    max_v, min_v = np.max(v_table), np.min(v_table)
+    if max_v == min_v == 0:
+        return np.zeros(v_table.shape)
+    return (v_table - min_v) / (max_v - min_v) - 1
+
+
+def simulate(maze, actions, discrete_actions, init_pos, init_ori, init_disc, beta, components, draws,
+             record_probs=False):
+    """One mouse, ``len(draws)`` steps, with replayed uniform draws.
+
+    :param components: ordered list of ``(kind, params)``: ANXIETY ``dict(W_anx,p1,p2,p3[,p4])``, BCOST
+        ``dict(W_bcost, table)`` (see :func:`bcost_table`), EXPERIENCE ``dict(W_exp, xi, kappa_home,
+        kappa_explo, theta_explo, theta_home)``, BPERSISTENCE ``dict(W_bper, bp, Wm, Wnm)``, VTABLE
+        ``dict(W_values, table)`` (normalised, see :func:`normalise_vtable`)
+    :return: dict(hist_pos [T+1,2], hist_ori [T+1], choice [T] action indices, probs, status)
+    """
+    mouse = OracleMouse(init_pos, init_ori, actions)
+    zero_act = np.all(np.array(discrete_actions) == (0, 0), axis=1)
+    T = len(draws)
+    hist_pos = [(mouse.x, mouse.y)]
+    hist_ori = [mouse.ori]
+    choice = []
+    probs = []
+    prev = np.array(init_disc, dtype=np.float64)  # exploration_model.py:47
+    moving = False  # :48
+    exp_map = np.zeros((maze.X, maze.Y))  # behavioural_components.py:445
+    fam, home = 0.0, False  # :440, 447
+    status = 0
+    for t in range(T):
+        ends = mouse.endpoints()  # experiment.py:36
+        vis = [maze.move_possible(mouse.x, mouse.y, ex, ey) for ex, ey in ends]  # :37
+        idxs = [i for i, v in enumerate(vis) if v]
+        if not idxs:
+            status = t + 1  # np.max([]) raises in the reference
+            break
+        cand = [ends[i] for i in idxs]  # :38
+        cells = [maze.cont2disc(ex, ey) for ex, ey in cand]  # :39
+        x, y = maze.cont2disc(mouse.x, mouse.y)  # :41
+        val_fin = np.zeros(len(cand))  # exploration_model.py:84
+        for kind, p in components:
+            if kind == COMP_ANXIETY:  # behavioural_components.py:364-374
+                w = {2: p["p1"], 1: p["p2"] * p["p1"], 3: p["p3"] * p["p2"] * p["p1"], 0: -1.0, 4: p.get("p4", 0.0)}
+                v = np.array([w[int(maze.tiles[c])] for c in cells])
+                val_fin = val_fin + v * p["W_anx"]
+            elif kind == COMP_BCOST:  # :408-413
+                v = p["table"][vis] if moving else np.zeros(np.sum(vis))
+                val_fin = val_fin + v * p["W_bcost"]
+            elif kind == COMP_EXPERIENCE:  # :449-479
+                exp_map[x, y] += 1
+                fam = (1 - p["xi"]) * fam + p["xi"] * exp_map[x, y]
+                if home and fam >= p["theta_explo"]:
+                    home = False
+                elif (not home) and fam < p["theta_home"]:
+                    home = True
+                v = np.zeros(len(cells))
+                for i, c in enumerate(cells):
+                    if not home:
+                        v[i] = np.exp(-p["kappa_explo"] * exp_map[c[0], c[1]])
+                    else:
+                        v[i] = 1.0 - np.exp(-p["kappa_home"] * exp_map[c[0], c[1]])
+                val_fin = val_fin + v * p["W_exp"]
+            elif kind == COMP_BPERSISTENCE:  # :502-513
+                mov = np.array([p["bp"]] * len(zero_act))
+                mov[zero_act] = p["Wm"] * p["bp"]
+                nmov = np.array([p["Wnm"] * p["bp"]] * len(zero_act))
+                nmov[zero_act] = p["bp"]
+                v = mov[vis] if moving else nmov[vis]
+                val_fin = val_fin + v * p["W_bper"]
+            elif kind == COMP_VTABLE:  # :537-541
+                v = np.array([p["table"][c[0], c[1]] for c in cells])
+                val_fin = val_fin + v * p["W_values"]
+        val_fin = beta * val_fin  # exploration_model.py:87
+        val_fin = val_fin - np.max(val_fin)  # :92
+        p_soft = np.exp(val_fin) / np.sum(np.exp(val_fin))  # :93
+        cdf = p_soft.cumsum()  # Generator.choice(a, p=p)
+        cdf /= cdf[-1]
+        k = int(cdf.searchsorted(draws[t], side="right"))
+        new = cand[k]
+        moving = bool(np.all(prev == np.array(new)))  # :101
+        prev = np.array(new)
+        mouse.move_to(new[0], new[1])  # experiment.py:51
+        hist_pos.append((mouse.x, mouse.y))
+        hist_ori.append(mouse.ori)
+        choice.append(idxs[k])
+        if record_probs:
+            probs.append(p_soft)
+    return {"hist_pos": np.array(hist_pos), "hist_ori": np.array(hist_ori), "choice": np.array(choice),
+            "probs": probs, "status": status}
+
+
+def metrics_of_history(maze, hist_pos, percentage=80):
+    """discretize_positions / occupancy_map / it_perc_visited_maze / motion_analysis / tile_analysis counts
+    (analysis/metrics.py:192-248, 425-442, 697-731) of one history."""
+    disc = [maze.cont2disc(px, py) for px, py in hist_pos]  # :201
+    occ = np.zeros((maze.X, maze.Y))
+    for c in disc:  # :213-215
+        occ[c[0], c[1]] += 1
+    nvis = len(maze.vis_cells)
+    seen, n_seen, it = [], 0, len(disc)  # :707-721
+    for idx, c in enumerate(disc):
+        if c not in seen:
+            n_seen += 1
+            seen.append(c)
+            if (n_seen * 100) / nvis >= percentage:
+                it = idx
+                break
+    count_moving = sum(1 for i in range(1, len(disc)) if disc[i] != disc[i - 1])  # :437-440
+    tile_counts = np.zeros(8, dtype=np.int64)
+    for c in disc:  # :236-239
+        tile_counts[int(maze.tiles[c])] += 1
+    return {"disc": disc, "occupancy": occ, "it_visit": it, "count_moving": count_moving, "tile_counts": tile_counts}
+
+
+def pcg64_state_words(seed):
+    """``(state_hi, state_lo, inc_hi, inc_lo)`` of ``np.random.default_rng(seed)`` (PCG64)."""
+    st = np.random.default_rng(seed).bit_generator.state["state"]
+    m = (1 << 64) - 1
+    return np.array([st["state"] >> 64, st["state"] & m, st["inc"] >> 64, st["inc"] & m], dtype=np.uint64)

@@ -1,0 +1,246 @@
+"""Parity of the CUDA forward simulation (through the C-ABI) with the reference's golden histories and
+with the oracle, under replayed uniform draws.
+
+Bar (BASELINE.json north_star / SURVEY section 7 "hard parts"): the DISCRETE trajectory -- chosen action
+at every step, tile sequence, occupancy / exploration metrics -- is bit-exact; continuous poses agree to
+1e-12 absolute (device cos/sin/atan2/exp differ from glibc / numpy by <= 1-2 ulp)."""
+import numpy as np
+import pytest
+
+from oracle import np_oracle as O
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+POSE_ATOL = 1e-12
+NAMES5 = ("anx", "bcost", "exp", "bper", "vtable")
+
+
+def _classes():
+    from navigation_model_b200.simulation import behavioural_components as bc
+    return [bc.AnxietyComponent, bc.BiomechanicalCostComponent, bc.ExperienceComponent,
+            bc.BiomechPersistenceComponent, bc.ValueTableComponent]
+
+
+def _oracle_components(P, m, units, V):
+    return [(O.COMP_ANXIETY, {k: P[k][m] for k in ("W_anx", "p1", "p2", "p3")}),
+            (O.COMP_BCOST, {"W_bcost": P["W_bcost"][m], "table": O.bcost_table(units, P["k"][m], P["gamma"][m])}),
+            (O.COMP_EXPERIENCE, {k: P[k][m] for k in ("W_exp", "xi", "kappa_home", "kappa_explo", "theta_explo",
+                                                      "theta_home")}),
+            (O.COMP_BPERSISTENCE, {k: P[k][m] for k in ("W_bper", "bp", "Wm", "Wnm")}),
+            (O.COMP_VTABLE, {"W_values": P["W_values"][m], "table": O.normalise_vtable(V)})]
+
+
+def _random_params(rng, N):
+    u = rng.uniform
+    return {"beta": u(0.3, 6, N), "W_anx": u(0, 10, N), "p1": u(0, 1, N), "p2": u(0, 1, N), "p3": u(0, 1, N),
+            "W_bcost": u(0, 10, N), "k": u(0.05, 4, N), "gamma": u(0.2, 2, N), "W_exp": u(0, 10, N),
+            "xi": u(0.006, 0.6, N), "kappa_home": u(0.01, 5, N), "kappa_explo": u(0.01, 5, N),
+            "theta_explo": u(80, 120, N), "theta_home": u(30, 70, N), "W_bper": u(0, 10, N), "bp": u(0, 1, N),
+            "Wm": u(0, 2, N), "Wnm": u(0, 2, N), "W_values": u(0, 10, N)}
+
+
+def test_golden_histories(cuda, golden_sim):
+    """The reference's own StandardExperiment.run histories (6 mice x 600 steps, 5 components)."""
+    from navigation_model_b200.batched_sim import BatchedExperiment
+    g = golden_sim
+    maze = H.product_m9()
+    names = [str(s) for s in g["param_names"]]
+    P = {n: g["params"][:, i] for i, n in enumerate(names)}
+    T = int(g["T"])
+    exp = BatchedExperiment(maze, g["actions"], g["actions_units"], _classes(), v_table=g["v_table"])
+    for pct, key in ((80, "it_visit_80"), (50, "it_visit_50")):
+        res = exp.run(P, T, g["init_pose"][:, :2], g["init_pose"][:, 2], init_disc=g["init_disc"], draws=g["draws"],
+                      visit_percentage=pct, history=True, occupancy=True, occupancy_total=True)
+        assert not res.status.any()
+        omz = H.oracle_m9()
+        for m in range(len(g["seeds"])):
+            want_disc = [omz.cont2disc(x, y) for x, y in g["hist_pos"][m]]
+            got_disc = [omz.cont2disc(x, y) for x, y in res.history_position[m]]
+            assert got_disc == want_disc, f"mouse {m}: tile sequence differs"
+            np.testing.assert_allclose(res.history_position[m], g["hist_pos"][m], rtol=0, atol=POSE_ATOL)
+            np.testing.assert_allclose(res.history_orientation[m], g["hist_ori"][m], rtol=0, atol=1e-9)
+        assert np.array_equal(res.occupancy, g["occupancy"].astype(np.int64))
+        assert np.array_equal(res.it_visit, g[key])
+        assert np.array_equal(res.count_moving, g["count_moving"])
+        assert np.array_equal(res.tile_counts[:, :4], g["tile_counts"])
+        assert np.array_equal(res.occupancy_total, g["occupancy"].sum(0).astype(np.int64))
+        np.testing.assert_allclose(res.final_pose[:, :2], g["hist_pos"][:, -1], rtol=0, atol=POSE_ATOL)
+
+
+def test_device_pcg64_equals_replayed_draws(cuda, golden_sim):
+    """Seeds (numpy-identical PCG64 on the device) and replayed draws give the same run."""
+    from navigation_model_b200.batched_sim import BatchedExperiment
+    g = golden_sim
+    maze = H.product_m9()
+    names = [str(s) for s in g["param_names"]]
+    P = {n: g["params"][:, i] for i, n in enumerate(names)}
+    T = int(g["T"])
+    exp = BatchedExperiment(maze, g["actions"], g["actions_units"], _classes(), v_table=g["v_table"])
+    kw = dict(init_pos=g["init_pose"][:, :2], init_ori=g["init_pose"][:, 2], init_disc=g["init_disc"], history=True)
+    a = exp.run(P, T, draws=g["draws"], **kw)
+    b = exp.run(P, T, seeds=g["seeds"], **kw)
+    assert np.array_equal(a.choices, b.choices)
+    assert np.array_equal(a.history_position, b.history_position)
+    # the generator ends where numpy's ends after T random() calls
+    for m, seed in enumerate(g["seeds"]):
+        gen = np.random.default_rng(int(seed))
+        gen.random(T)
+        assert np.array_equal(b.pcg_state[m], O.pcg64_state_words(gen) if False else _words(gen))
+
+
+def _words(gen):
+    st = gen.bit_generator.state["state"]
+    m = (1 << 64) - 1
+    return np.array([st["state"] >> 64, st["state"] & m, st["inc"] >> 64, st["inc"] & m], dtype=np.uint64)
+
+
+def test_standard_experiment_api_matches_reference(cuda, golden_sim):
+    """StandardExperiment / BehaviouralModel / components / Mouse of this repo, driven like the reference
+    (seeded model, device path), leave the same history and the same object state."""
+    from navigation_model_b200.simulation import behavioural_components as bc
+    from navigation_model_b200.simulation.experiment import StandardExperiment
+    from navigation_model_b200.simulation.exploration_model import BehaviouralModel
+    from navigation_model_b200.simulation.mouse import Mouse
+    g = golden_sim
+    maze = H.product_m9()
+    names = [str(s) for s in g["param_names"]]
+    units = [tuple(int(v) for v in a) for a in g["actions_units"]]
+    T = int(g["T"])
+    for m in (0, 3):
+        p = dict(zip(names, g["params"][m]))
+        comps = [bc.AnxietyComponent(W_anx=p["W_anx"], p1=p["p1"], p2=p["p2"], p3=p["p3"]),
+                 bc.BiomechanicalCostComponent(units, W_bcost=p["W_bcost"], k=p["k"], gamma=p["gamma"]),
+                 bc.ExperienceComponent(maze.shape, W_exp=p["W_exp"], xi=p["xi"], kappa_home=p["kappa_home"],
+                                        kappa_explo=p["kappa_explo"], theta_explo=p["theta_explo"],
+                                        theta_home=p["theta_home"]),
+                 bc.BiomechPersistenceComponent(units, W_bper=p["W_bper"], bp=p["bp"], Wm=p["Wm"], Wnm=p["Wnm"]),
+                 bc.ValueTableComponent(g["v_table"], W_values=p["W_values"])]
+        model = BehaviouralModel(comps, tuple(int(v) for v in g["init_disc"][m]), beta=p["beta"], seed=int(g["seeds"][m]))
+        mouse = Mouse(g["init_pose"][m][:2], g["init_pose"][m][2], g["actions"])
+        exp = StandardExperiment(model, maze, mouse)
+        assert exp._device_eligible()
+        exp.run(T)
+        hp, ho = mouse.history
+        assert len(hp) == T + 1
+        np.testing.assert_allclose(np.array(hp), g["hist_pos"][m], rtol=0, atol=POSE_ATOL)
+        np.testing.assert_allclose(mouse.position, g["hist_pos"][m][-1], rtol=0, atol=POSE_ATOL)
+        # experience map = occupancy of history[0..T-1]
+        omz = H.oracle_m9()
+        occ = g["occupancy"][m].copy()
+        lx, ly = omz.cont2disc(*g["hist_pos"][m][-1])
+        occ[lx, ly] -= 1
+        assert np.array_equal(comps[2]._maze_map_exp, occ)
+        # the model's generator advanced by exactly T draws
+        twin = np.random.default_rng(int(g["seeds"][m]))
+        twin.random(T)
+        assert model._rng.random() == twin.random()
+
+
+def test_random_batch_vs_oracle(cuda):
+    """64 mice, random parameters inside the descriptor bounds, jittered starts, 300 steps."""
+    from navigation_model_b200.batched_sim import BatchedExperiment
+    rng = np.random.default_rng(99)
+    maze, omz = H.product_m9(), H.oracle_m9()
+    N, T = 64, 300
+    acts = H.a8()
+    V = rng.random((9, 9)) * 2 - 0.5
+    P = _random_params(rng, N)
+    starts = [(1, 1), (7, 4), (1, 6), (2, 8), (6, 8), (8, 0)]
+    cells = np.array([starts[i % len(starts)] for i in range(N)])
+    pos0 = np.array([maze.get_tile_centre(c) for c in cells]) + rng.uniform(-0.04, 0.04, (N, 2))
+    ori0 = rng.uniform(-np.pi, np.pi, N)
+    draws = rng.random((N, T))
+    exp = BatchedExperiment(maze, acts, O.A8_UNITS, _classes(), v_table=V)
+    res = exp.run(P, T, pos0, ori0, init_disc=cells, draws=draws, history=True, occupancy=True)
+    mismatched = 0
+    for m in range(N):
+        ref = O.simulate(omz, acts, O.A8_UNITS, pos0[m], ori0[m], cells[m], P["beta"][m],
+                         _oracle_components(P, m, O.A8_UNITS, V), draws[m])
+        assert ref["status"] == 0 and res.status[m] == 0
+        if not np.array_equal(ref["choice"], res.choices[m]):
+            mismatched += 1
+            continue
+        np.testing.assert_allclose(res.history_position[m], ref["hist_pos"], rtol=0, atol=POSE_ATOL)
+        met = O.metrics_of_history(omz, ref["hist_pos"])
+        assert np.array_equal(met["occupancy"], res.occupancy[m])
+        assert met["it_visit"] == res.it_visit[m] and met["count_moving"] == res.count_moving[m]
+        assert np.array_equal(met["tile_counts"], res.tile_counts[m])
+    assert mismatched == 0, f"{mismatched} of {N} discrete trajectories diverged"
+
+
+def test_component_subsets_order_and_inactive(cuda):
+    """Any ordered subset of components; an inactive component contributes nothing."""
+    from navigation_model_b200.batched_sim import BatchedExperiment
+    from navigation_model_b200.simulation import behavioural_components as bc
+    rng = np.random.default_rng(5)
+    maze, omz = H.product_m9(), H.oracle_m9()
+    N, T = 8, 120
+    acts = H.a8()
+    V = rng.random((9, 9))
+    P = _random_params(rng, N)
+    pos0 = np.array(maze.get_tile_centre(7, 4)) + rng.uniform(-0.03, 0.03, (N, 2))
+    draws = rng.random((N, T))
+    cls = _classes()
+    for order, active in (([4, 2, 0], None), ([1, 3], None), ([0, 1, 2, 3, 4], [True, False, True, False, True])):
+        comps = [cls[i] for i in order]
+        exp = BatchedExperiment(maze, acts, O.A8_UNITS, comps, v_table=V, active=active)
+        res = exp.run(P, T, pos0, 0.3, init_disc=(7, 4), draws=draws, history=True)
+        for m in range(N):
+            oc = _oracle_components(P, m, O.A8_UNITS, V)
+            sel = [oc[i] for k, i in enumerate(order) if active is None or active[k]]
+            ref = O.simulate(omz, acts, O.A8_UNITS, pos0[m], 0.3, (7, 4), P["beta"][m], sel, draws[m])
+            assert np.array_equal(ref["choice"], res.choices[m]), (order, m)
+
+
+def test_device_ray_check_matches_oracle(cuda):
+    """Maze.is_movement_possible_cont on the device (FMA-residual floor division) vs the oracle's Python
+    float floor division, including segments whose crossings land exactly on tile corners."""
+    from navigation_model_b200.batched_sim import movements_possible
+    maze, omz = H.product_m9(), H.oracle_m9()
+    rng = np.random.default_rng(17)
+    st = O.M9_SIZE_TILE
+    segs = [rng.uniform(-0.1, 1.1, (4000, 4))]
+    # centre-to-centre moves (diagonals cross grid corners exactly)
+    cells = np.array(omz.vis_cells)
+    a = cells[rng.integers(len(cells), size=3000)]
+    d = rng.integers(-2, 3, size=(3000, 2))
+    ca = np.array([omz.centre(c) for c in a])
+    cb = np.array([omz.centre(c) for c in a + d])
+    segs.append(np.concatenate([ca, cb], axis=1))
+    # end points exactly on tile boundaries
+    k = rng.integers(0, 10, size=(2000, 4)).astype(np.float64)
+    segs.append(k * st)
+    segs = np.concatenate(segs)
+    got = movements_possible(maze, segs)
+    want = np.array([omz.move_possible(*s) for s in segs])
+    assert np.array_equal(got, want)
+    assert want.any() and not want.all()
+
+
+def test_stranded_mouse_reports_status(cuda):
+    """No reachable endpoint: the reference raises from np.max([]); the kernel reports the failing step."""
+    from navigation_model_b200.batched_sim import BatchedExperiment
+    from navigation_model_b200.simulation import behavioural_components as bc
+    maze = H.product_m9()
+    exp = BatchedExperiment(maze, H.a8(), O.A8_UNITS, [bc.AnxietyComponent])
+    P = {"beta": [1.0, 1.0], "W_anx": [1.0, 1.0], "p1": [1.0, 1.0], "p2": [0.5, 0.5], "p3": [0.5, 0.5]}
+    pos0 = np.array([maze.get_tile_centre(1, 1), maze.get_tile_centre(4, 3)])  # (4,3) is VOID
+    res = exp.run(P, 10, pos0, 0.0, draws=np.full((2, 10), 0.5))
+    assert res.status[0] == 0 and res.status[1] == 1
+
+
+def test_parameter_validation(cuda):
+    from navigation_model_b200.batched_sim import BatchedExperiment
+    from navigation_model_b200.simulation import behavioural_components as bc
+    maze = H.product_m9()
+    exp = BatchedExperiment(maze, H.a8(), O.A8_UNITS, [bc.ExperienceComponent])
+    good = {"beta": 1.0, "W_exp": 1.0, "xi": 0.01, "kappa_home": 1.0, "kappa_explo": 1.0, "theta_explo": 100.0,
+            "theta_home": 50.0}
+    with pytest.raises(RuntimeError, match="Wrong value set for property 'xi'"):
+        exp.run(dict(good, xi=0.9), 5, maze.get_tile_centre(1, 1), draws=np.full((1, 5), 0.5))
+    missing = dict(good)
+    del missing["kappa_home"]
+    with pytest.raises(RuntimeError, match="kappa_home has not been specified"):
+        exp.run(missing, 5, maze.get_tile_centre(1, 1), draws=np.full((1, 5), 0.5))
