@@ -150,7 +150,7 @@ class SessionList:
     def _concat(parts):
         out = []
         for p in parts:
-            out += p
+            out.extend(p)  # also accepts ndarray trajectories (the reference's `list += ndarray` raises)
         return out
 
     @property
