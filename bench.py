@@ -67,7 +67,7 @@ def algorithmic_fp64(records, n_online, alg):
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons through NVML while the timed region runs."""
 
-    def __init__(self, index, period=0.1):
+    def __init__(self, index, period=0.02):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -329,7 +329,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--alg", default="positive", choices=["positive", "td0", "negative"])

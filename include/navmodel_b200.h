@@ -148,6 +148,9 @@ typedef struct nm_streams nm_streams;
  * the stream has been synchronised. */
 nm_streams *nm_streams_upload(const nm_step_rec *h_records, const int64_t *h_offsets, const int64_t *h_online,
                               int S, int num_states, int device, void *stream);
+/* Re-upload the records of streams with the same layout (same offsets / online counts) into the existing
+ * device allocation: one H2D copy enqueued on `stream`, no allocation. */
+int nm_streams_update(nm_streams *st, const nm_step_rec *h_records, void *stream);
 void nm_streams_free(nm_streams *st);
 
 /* ------------------------------------------------------------------------------------------------

@@ -51,6 +51,7 @@ SIGNATURES = {
                                                  C.POINTER(C.c_int)]),
     "nm_stream_build": (_i64, [_p, _p, _p, _i64, _p, _p]),
     "nm_streams_upload": (_p, [_p, _p, _p, C.c_int, C.c_int, C.c_int, _p]),
+    "nm_streams_update": (C.c_int, [_p, _p, _p]),
     "nm_streams_free": (None, [_p]),
     "nm_vtable_sweep": (C.c_int, [C.c_int, _p, _p, _p, _p, _i64, _p, C.c_int, _p, _p]),
     "nm_loglik_sweep": (C.c_int, [C.c_int, _p, _p, _p, _p, _p, _i64, _p, C.c_int, _p, _p, _p]),

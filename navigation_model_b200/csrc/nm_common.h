@@ -54,6 +54,7 @@ struct nm_streams {
   int num_states = 0;
   int device = -1;
   int64_t total = 0;
+  int min_ncand = NM_MAX_CAND;   // smallest candidate count over all records (0: value-only TD0 streams)
   std::vector<int64_t> offsets;  // [S+1]
   std::vector<int64_t> online;   // [S]
   nm_step_rec *d_records = nullptr;

@@ -224,19 +224,30 @@ __global__ void __launch_bounds__(512, 1) nm_fit_kernel(const FitArgs a) {
   }
 }
 
+#include "nm_fit_v2.cuh"
+
 // ---- launch -----------------------------------------------------------------------------------
 struct LaunchPlan {
-  int nt;
+  int nt;       // parameter sets (V columns) per CTA
+  int threads;  // launched threads per CTA (generation 2 adds one producer warp)
+  int gen;
   size_t smem;
 };
+
+int fit_generation() {
+  const char *env = getenv("NM_FIT_GEN");
+  return (env && atoi(env) == 1) ? 1 : 2;
+}
 
 int plan_launch(int num_states, int64_t P, int S, int device, LaunchPlan *plan) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  const int fixed = kBarBytes + kStageBytes;
+  const int gen = fit_generation();
+  plan->gen = gen;
+  const int fixed = gen == 2 ? k2FixedBytes : kBarBytes + kStageBytes;
   int max_nt = (int)(((int64_t)kMaxSmem - fixed) / ((int64_t)num_states * 8));
   max_nt = (max_nt / 32) * 32;
-  if (max_nt > 512) max_nt = 512;
+  if (max_nt > (gen == 2 ? 480 : 512)) max_nt = gen == 2 ? 480 : 512;
   if (max_nt < 32)
     return nm_fail(NM_ERR_INVALID, "maze with %d visitable tiles does not fit the shared-memory V layout", num_states);
   const char *env = getenv("NM_FIT_NT");
@@ -244,6 +255,7 @@ int plan_launch(int num_states, int64_t P, int S, int device, LaunchPlan *plan) 
     int v = atoi(env);
     if (v >= 32 && v <= max_nt && v % 32 == 0) {
       plan->nt = v;
+      plan->threads = v + (gen == 2 ? 32 : 0);
       plan->smem = (size_t)fixed + (size_t)num_states * 8 * v;
       return NM_OK;
     }
@@ -271,17 +283,18 @@ int plan_launch(int num_states, int64_t P, int S, int device, LaunchPlan *plan) 
     }
   }
   plan->nt = best_nt;
+  plan->threads = best_nt + (gen == 2 ? 32 : 0);
   plan->smem = (size_t)fixed + (size_t)num_states * 8 * best_nt;
   return NM_OK;
 }
 
 template <int ALG, bool LL>
 int launch_fit(const FitArgs &a, int S, const LaunchPlan &plan, cudaStream_t cs) {
-  cudaError_t e = cudaFuncSetAttribute(nm_fit_kernel<ALG, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)plan.smem);
+  auto kernel = plan.gen == 2 ? nm_fit2_kernel<ALG, LL> : nm_fit_kernel<ALG, LL>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
   if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   const dim3 grid((unsigned)((a.P + plan.nt - 1) / plan.nt), (unsigned)S, 1);
-  nm_fit_kernel<ALG, LL><<<grid, plan.nt, plan.smem, cs>>>(a);
+  kernel<<<grid, plan.threads, plan.smem, cs>>>(a);
   e = cudaGetLastError();
   if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_fit_kernel launch: %s", cudaGetErrorString(e));
   return NM_OK;
@@ -299,6 +312,9 @@ int fit_sweep(int alg, bool with_ll, const nm_maze *mz, const nm_streams *st, co
   NM_CHECK_ARG(!with_ll || P == 0 || (d_beta && d_ll_out), "loglik sweep: NULL beta / ll_out");
   NM_CHECK_ARG(with_ll || d_v_out, "vtable sweep: NULL v_out");
   NM_CHECK_ARG(st->S <= 65535, "sweep: at most 65535 sessions per call");
+  NM_CHECK_ARG(st->total == 0 || st->min_ncand > 0 || (alg == NM_ALG_TD0 && !with_ll),
+               "sweep: the streams hold steps without candidate next states; the look-ahead learners and the "
+               "log-likelihood need them (np.max([]) raises in the reference)");
   if (P == 0) return NM_OK;
   if (cudaSetDevice(mz->device) != cudaSuccess) return nm_fail(NM_ERR_CUDA, "cudaSetDevice(%d) failed", mz->device);
   LaunchPlan plan;

@@ -156,8 +156,10 @@ extern "C" nm_streams *nm_streams_upload(const nm_step_rec *h_records, const int
     nm_fail(NM_ERR_INVALID, "nm_streams_upload: NULL records");
     return nullptr;
   }
+  int min_ncand = NM_MAX_CAND;
   for (int64_t i = 0; i < total; ++i) {
     const nm_step_rec &r = h_records[i];
+    if (r.ncand < min_ncand) min_ncand = r.ncand;
     bool ok = r.s < num_states && r.s1 < num_states && r.ncand <= NM_MAX_CAND &&
               (r.obs == NM_OBS_NONE || r.obs < r.ncand);
     for (int k = 0; ok && k < r.ncand; ++k) ok = r.cand[k] < num_states;
@@ -176,6 +178,7 @@ extern "C" nm_streams *nm_streams_upload(const nm_step_rec *h_records, const int
   st->num_states = num_states;
   st->device = device;
   st->total = total;
+  st->min_ncand = min_ncand;
   st->offsets.assign(h_offsets, h_offsets + S + 1);
   st->online.assign(h_online, h_online + S);
   {
@@ -204,6 +207,28 @@ fail:
   if (st->d_block) cudaFree(st->d_block);
   delete st;
   return nullptr;
+}
+
+extern "C" int nm_streams_update(nm_streams *st, const nm_step_rec *h_records, void *stream) {
+  NM_CHECK_ARG(st && (st->total == 0 || h_records), "nm_streams_update: NULL argument");
+  int min_ncand = NM_MAX_CAND;
+  for (int64_t i = 0; i < st->total; ++i) {
+    const nm_step_rec &r = h_records[i];
+    if (r.ncand < min_ncand) min_ncand = r.ncand;
+    bool ok = r.s < st->num_states && r.s1 < st->num_states && r.ncand <= NM_MAX_CAND &&
+              (r.obs == NM_OBS_NONE || r.obs < r.ncand);
+    for (int k = 0; ok && k < r.ncand; ++k) ok = r.cand[k] < st->num_states;
+    if (!ok)
+      return nm_fail(NM_ERR_INVALID, "nm_streams_update: record %lld has an out-of-range state / candidate",
+                     (long long)i);
+  }
+  st->min_ncand = min_ncand;
+  if (st->total == 0) return NM_OK;
+  if (cudaSetDevice(st->device) != cudaSuccess) return nm_fail(NM_ERR_CUDA, "cudaSetDevice(%d) failed", st->device);
+  cudaError_t e = cudaMemcpyAsync(st->d_records, h_records, sizeof(nm_step_rec) * (size_t)st->total,
+                                  cudaMemcpyHostToDevice, (cudaStream_t)stream);
+  if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_streams_update: %s", cudaGetErrorString(e));
+  return NM_OK;
 }
 
 extern "C" void nm_streams_free(nm_streams *st) {

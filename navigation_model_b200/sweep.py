@@ -217,6 +217,14 @@ class DeviceStreams:
     def host_bytes(self):
         return int(self._host.numel())
 
+    def reupload(self):
+        """Copy the pinned staging buffer to the device again (``nm_streams_update``; asynchronous on
+        torch's current stream)."""
+        import torch
+        with torch.cuda.device(self.dmaze.torch_device):
+            _native.check(self._lib.nm_streams_update(self._h, C.c_void_p(self._host.data_ptr()),
+                                                      _native.cuda_stream_ptr()))
+
     def close(self):
         h, self._h = self._h, None
         if h:
@@ -322,9 +330,9 @@ class ConditioningSweep:
     def upload(self):
         """(Re-)upload the session streams from the pinned staging buffer; returns the bytes copied
         host->device."""
-        old, self._dstreams = self._dstreams, None
-        if old is not None:
-            old.close()
+        if self._dstreams is not None:  # same layout: one async H2D copy into the existing allocation
+            self._dstreams.reupload()
+            return self._dstreams.host_bytes
         self._ensure_device()
         return self._dstreams.host_bytes
 
