@@ -109,9 +109,18 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+def host_threads():
+    """All the host threads this process may use (torchrun pins OMP_NUM_THREADS=1; the CPU legs override it)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_port_rate(records_tr, alg_code, a, b, g, seconds, threads=0):
     """Time the C oracle port on a bounded sample of the same workload.  Returns (updates/s, sample, cores)."""
     from oracle import c_oracle as CO
+    threads = threads if threads > 0 else host_threads()
     n = len(records_tr["s"])
     P = 512
     t0 = time.perf_counter()
@@ -123,7 +132,7 @@ def cpu_port_rate(records_tr, alg_code, a, b, g, seconds, threads=0):
     t0 = time.perf_counter()
     CO.fit(alg_code, records_tr, a[idx], g[idx], 60, beta=b[idx], want_v=False, threads=threads)
     dt = time.perf_counter() - t0
-    cores = CO.max_threads() if threads <= 0 else threads
+    cores = threads
     return P * n / dt, f"{P} of {len(a)} parameter sets (evenly spaced over the grid) x {n} steps, {dt:.1f} s", cores
 
 
@@ -141,14 +150,14 @@ def run_reference(args):
     n = len(tr["s"])
     P_s = 4096
     idx = np.linspace(0, len(a) - 1, P_s).astype(np.int64)
+    cores = host_threads()
     for _ in range(args.warmup):
-        CO.fit(alg_code, tr, a[idx], g[idx], 60, beta=b[idx], want_v=False)
+        CO.fit(alg_code, tr, a[idx], g[idx], 60, beta=b[idx], want_v=False, threads=cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        CO.fit(alg_code, tr, a[idx], g[idx], 60, beta=b[idx], want_v=False)
+        CO.fit(alg_code, tr, a[idx], g[idx], 60, beta=b[idx], want_v=False, threads=cores)
     dt = time.perf_counter() - t0
     value = P_s * n * args.steps / dt
-    cores = CO.max_threads()
     line = {"impl": "reference", "metric": "agent-trial updates/s (fitness grid sweep)", "value": value,
             "unit": "updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -269,8 +278,11 @@ def run_b200(args):
         step_e2e()
     barrier()
     t0 = time.perf_counter()
+    e2e_step_ms = []
     for _ in range(args.steps):
+        ts = time.perf_counter()
         h2d_stream_bytes = step_e2e()
+        e2e_step_ms.append(1e3 * (time.perf_counter() - ts))
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
@@ -317,7 +329,10 @@ def run_b200(args):
                 "roofline": roofline,
                 "cpu_baseline": {"value": cpu_val, "unit": "updates/s", "cores": cores, "kind": "port",
                                  "sample": cpu_sample},
-                "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "step_ms_min_median_max": [float(np.min(e2e_step_ms)), float(np.median(e2e_step_ms)),
+                                                   float(np.max(e2e_step_ms))],
+                        "slowest_step_index": int(np.argmax(e2e_step_ms))},
                 "gpu_launches": 3 * args.steps, "clocks": clocks, "wall_s": wall,
                 "target_updates_per_s_8gpu": 1e10}
         print(json.dumps(line))

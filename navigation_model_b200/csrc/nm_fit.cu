@@ -18,6 +18,10 @@
 #include <cuda_runtime.h>
 #include <stdlib.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "nm_common.h"
 
 namespace {
@@ -449,13 +453,29 @@ extern "C" int nm_argmin_nll(const double *d_ll, int S, int64_t P, double *d_nll
   cudaStream_t cs = (cudaStream_t)stream;
   int blocks = (int)((P + 255) / 256);
   if (blocks > 1024) blocks = 1024;
+  // 16 KB of partials: one persistent scratch buffer per (device, stream), allocated on first use and
+  // kept for the life of the process -- no allocator traffic on the hot path (stream-ordered pools hand
+  // memory back to the OS at synchronisation points, which showed up as 20-500 ms stalls in bench e2e)
+  int device = 0;
+  cudaGetDevice(&device);
   Best *partial = nullptr;
-  cudaError_t e = cudaMallocAsync((void **)&partial, sizeof(Best) * blocks, cs);
-  if (e != cudaSuccess) return nm_fail(NM_ERR_NOMEM, "nm_argmin_nll: cudaMallocAsync: %s", cudaGetErrorString(e));
+  {
+    static std::mutex mu;
+    static std::map<std::pair<int, void *>, Best *> scratch;
+    std::lock_guard<std::mutex> lock(mu);
+    auto key = std::make_pair(device, stream);
+    auto it = scratch.find(key);
+    if (it == scratch.end()) {
+      Best *buf = nullptr;
+      cudaError_t ea = cudaMalloc((void **)&buf, sizeof(Best) * 1024);
+      if (ea != cudaSuccess) return nm_fail(NM_ERR_NOMEM, "nm_argmin_nll: cudaMalloc: %s", cudaGetErrorString(ea));
+      it = scratch.emplace(key, buf).first;
+    }
+    partial = it->second;
+  }
   nm_nll_partial_kernel<<<blocks, 256, 0, cs>>>(d_ll, S, P, d_nll_out, partial);
   nm_nll_final_kernel<<<1, 256, 0, cs>>>(partial, blocks, (Best *)d_best_out);
-  e = cudaGetLastError();
-  cudaFreeAsync(partial, cs);
+  cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_argmin_nll launch: %s", cudaGetErrorString(e));
   return NM_OK;
 }
