@@ -1,17 +1,7 @@
-// Parameter-grid sweeps of the conditioning recurrence (V-table learning + softmax log-likelihood).
+// Parameter-grid sweeps of the conditioning recurrence (V-table learning + softmax log-likelihood):
+// launch planning and the C-ABI entry points.  The device code lives in nm_fit_kernels.cuh.
 //
-// Mapping (DESIGN.md "fit kernel"):
-//   * one THREAD owns one parameter set (alpha, beta, gamma); its V-table lives in shared memory as
-//     V[state][thread] (column per thread): every thread of the CTA walks the SAME observed stream, so
-//     at each step all lanes touch the same state row -> conflict-free LDS/STS, no divergence;
-//   * the step stream (32-byte records, nm_step_rec) is staged global->shared by the TMA engine
-//     (cp.async.bulk + mbarrier complete_tx, SASS UBLKCP) in a 4-deep ring of 64-record chunks issued
-//     by one elected thread; consumers read records with broadcast LDS.128;
-//   * grid = (ceil(P / threads), S): CTA (b, j) runs parameter block b on session j;
-//   * all arithmetic FP64; the V recurrence uses explicit _rn intrinsics (no FMA contraction) so that
-//     V-tables are bit-identical to the reference's numpy scalars (rl.py:184-187, 227-230, 257-259).
-//
-// Reference semantics restated here:
+// Reference semantics restated on the device:
 //   TD0 / PositiveConditioning / NegativeConditioning .update      simulation/rl.py:176-194,219-237,256-262
 //   ConditioningExperiment.run loop + ShuffledReplays passes        simulation/rl.py:88-102, 419-424
 //   softmax of BehaviouralModel.decision_making                    simulation/exploration_model.py:84-93
@@ -26,13 +16,7 @@
 
 namespace {
 
-constexpr int kChunk = 64;   // records per staging chunk
-constexpr int kStages = 4;   // ring depth
-constexpr int kRecBytes = (int)sizeof(nm_step_rec);
-constexpr int kBarBytes = 128;
-constexpr int kStageBytes = kStages * kChunk * kRecBytes;
 constexpr int kMaxSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
-
 static_assert(sizeof(nm_step_rec) == 32, "nm_step_rec must be 32 bytes");
 
 struct FitArgs {
@@ -58,6 +42,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   asm volatile(
       "{\n"
@@ -78,230 +65,94 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
                : "memory");
 }
 
-// ---- one step of the recurrence ---------------------------------------------------------------
-// w0 = {r.lo, r.hi, s | s1 << 16, ncand | obs << 8}, w1 = cand[0..7] as 4 x (u16, u16)
-template <int ALG, bool LL>
-__device__ __forceinline__ void fit_step(const uint4 w0, const uint4 w1, double *__restrict__ Vcol, const int nt,
-                                         const double alpha, const double beta, const double gamma, double &ll) {
-  const double r = __hiloint2double((int)w0.y, (int)w0.x);
-  const int s = (int)(w0.z & 0xffffu);
-  const int s1 = (int)(w0.z >> 16);
-  const int K = (int)(w0.w & 0xffu);
-  const int obs = (int)((w0.w >> 8) & 0xffu);
+#include "nm_fit_kernels.cuh"
 
-  double v[NM_MAX_CAND];
-  if (LL || ALG != NM_ALG_TD0) {
-    const uint32_t cw[4] = {w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-    for (int k = 0; k < NM_MAX_CAND; ++k) {
-      const int c = (int)((k & 1) ? (cw[k >> 1] >> 16) : (cw[k >> 1] & 0xffffu));
-      v[k] = (k < K) ? Vcol[c * nt] : 0.0;
-    }
-  }
-
-  if (LL) {
-    if (obs != NM_OBS_NONE) {  // warp-uniform
-      // val = beta * V[cand]; val -= max(val); p = exp(val) / sum(exp(val))   exploration_model.py:87-93
-      double z[NM_MAX_CAND];
-      double m = -INFINITY;
-      double zobs = 0.0;
-#pragma unroll
-      for (int k = 0; k < NM_MAX_CAND; ++k) {
-        z[k] = __dmul_rn(beta, v[k]);
-        if (k < K) m = fmax(m, z[k]);
-        if (k == obs) zobs = z[k];
-      }
-      double e[NM_MAX_CAND];
-#pragma unroll
-      for (int k = 0; k < NM_MAX_CAND; ++k) e[k] = (k < K) ? exp(__dsub_rn(z[k], m)) : 0.0;
-      double sum;
-      if (K == NM_MAX_CAND) {  // numpy pairwise sum for n == 8
-        sum = __dadd_rn(__dadd_rn(__dadd_rn(e[0], e[1]), __dadd_rn(e[2], e[3])),
-                        __dadd_rn(__dadd_rn(e[4], e[5]), __dadd_rn(e[6], e[7])));
-      } else {  // n < 8: sequential from 0.0
-        sum = 0.0;
-#pragma unroll
-        for (int k = 0; k < NM_MAX_CAND - 1; ++k)
-          if (k < K) sum = __dadd_rn(sum, e[k]);
-      }
-      ll = __dadd_rn(ll, __dsub_rn(__dsub_rn(zobs, m), log(sum)));
-    }
-  }
-
-  // value update
-  double boot;
-  if (ALG == NM_ALG_TD0) {
-    boot = Vcol[s1 * nt];
-  } else {
-    boot = v[0];
-#pragma unroll
-    for (int k = 1; k < NM_MAX_CAND; ++k)
-      if (k < K) boot = (ALG == NM_ALG_POSITIVE) ? fmax(boot, v[k]) : fmin(boot, v[k]);
-  }
-  const double vs = Vcol[s * nt];
-  // rpe = r + gamma * boot - V[s];  V[s] += alpha * rpe       (left-to-right, no contraction)
-  const double rpe = __dsub_rn(__dadd_rn(r, __dmul_rn(gamma, boot)), vs);
-  Vcol[s * nt] = __dadd_rn(vs, __dmul_rn(alpha, rpe));
-}
-
-template <int ALG, bool LL>
-__global__ void __launch_bounds__(512, 1) nm_fit_kernel(const FitArgs a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
-  uint4 *stage = reinterpret_cast<uint4 *>(smem_raw + kBarBytes);
-  double *V = reinterpret_cast<double *>(smem_raw + kBarBytes + kStageBytes);
-
-  const int tid = threadIdx.x, nt = blockDim.x;
-  const int sess = blockIdx.y;
-  const int64_t p = (int64_t)blockIdx.x * nt + tid;
-  const bool live = p < a.P;
-  const int64_t rec0 = a.offsets[sess];
-  const int64_t n = a.offsets[sess + 1] - rec0;
-  const int64_t n_on = a.online[sess];
-  const int nchunks = (int)((n + kChunk - 1) / kChunk);
-  const nm_step_rec *src = a.records + rec0;
-
-  auto issue = [&](int c) {  // elected thread: arm the barrier, launch the bulk copy of chunk c
-    const int stg = c % kStages;
-    const int64_t first = (int64_t)c * kChunk;
-    const uint32_t bytes = (uint32_t)((n - first < kChunk ? n - first : kChunk) * kRecBytes);
-    mbar_expect_tx(&full[stg], bytes);
-    tma_bulk_g2s(stage + stg * (kChunk * 2), src + first, bytes, &full[stg]);
-  };
-
-  if (tid == 0) {
-    for (int i = 0; i < kStages; ++i) mbar_init(&full[i], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (tid == 0)
-    for (int c = 0; c < kStages && c < nchunks; ++c) issue(c);
-
-  const double alpha = live ? a.alpha[p] : 0.0;
-  const double beta = (LL && live) ? a.beta[p] : 0.0;
-  const double gamma = live ? a.gamma[p] : 0.0;
-  double *Vcol = V + tid;
-  const int NV = a.num_states;
-  if (a.v_init == nullptr) {
-    for (int s = 0; s < NV; ++s) Vcol[s * nt] = 0.0;
-  } else if (!a.v_init_per_unit) {
-    for (int s = 0; s < NV; ++s) Vcol[s * nt] = a.v_init[a.tile_of_state[s]];
-  } else {
-    for (int s = 0; s < NV; ++s) Vcol[s * nt] = live ? a.v_init[p * a.n_tiles + a.tile_of_state[s]] : 0.0;
-  }
-
-  double ll = 0.0;
-  for (int c = 0; c < nchunks; ++c) {
-    const int stg = c % kStages;
-    mbar_wait(&full[stg], (uint32_t)((c / kStages) & 1));
-    const uint4 *recs = stage + stg * (kChunk * 2);
-    const int64_t first = (int64_t)c * kChunk;
-    const int cnt = (int)(n - first < kChunk ? n - first : kChunk);
-    int cnt_on = (int)(n_on - first);
-    cnt_on = cnt_on < 0 ? 0 : (cnt_on > cnt ? cnt : cnt_on);
-    int i = 0;
-    if (LL) {
-      for (; i < cnt_on; ++i) fit_step<ALG, true>(recs[2 * i], recs[2 * i + 1], Vcol, nt, alpha, beta, gamma, ll);
-    }
-    for (; i < cnt; ++i) fit_step<ALG, false>(recs[2 * i], recs[2 * i + 1], Vcol, nt, alpha, beta, gamma, ll);
-    __syncthreads();  // every warp is done with this stage -> it can be refilled
-    if (tid == 0 && c + kStages < nchunks) issue(c + kStages);
-  }
-
-  if (LL && live && a.ll_out) a.ll_out[(int64_t)sess * a.P + p] = ll;
-
-  if (a.v_out) {  // dense [S, P, X*Y] tables, written coalesced through a transposed read of V
-    __syncthreads();
-    const int64_t p0 = (int64_t)blockIdx.x * nt;
-    const int64_t np = (a.P - p0 < nt) ? (a.P - p0) : nt;
-    const int nT = a.n_tiles;
-    double *dst = a.v_out + ((int64_t)sess * a.P + p0) * nT;
-    for (int64_t i = tid; i < np * nT; i += nt) {
-      const int u = (int)(i / nT), tile = (int)(i - (int64_t)u * nT);
-      const int st = a.state_of_tile[tile];
-      double val;
-      if (st >= 0) val = V[st * nt + u];
-      else if (a.v_init == nullptr) val = 0.0;
-      else val = a.v_init_per_unit ? a.v_init[(p0 + u) * nT + tile] : a.v_init[tile];
-      dst[i] = val;
-    }
-  }
-}
-
-#include "nm_fit_v2.cuh"
-
-// ---- launch -----------------------------------------------------------------------------------
+// ---- launch planning ---------------------------------------------------------------------------------
 struct LaunchPlan {
-  int nt;       // parameter sets (V columns) per CTA
-  int threads;  // launched threads per CTA (generation 2 adds one producer warp)
-  int gen;
-  size_t smem;
+  int nc;       // parameter sets (V columns) per CTA
+  size_t smem;  // dynamic shared memory per CTA
 };
 
-int fit_generation() {
-  const char *env = getenv("NM_FIT_GEN");
-  return (env && atoi(env) == 1) ? 1 : 2;
-}
-
-int plan_launch(int num_states, int64_t P, int S, int device, LaunchPlan *plan) {
+// Pick the number of parameter sets per CTA: fill the SMs with as few, as even waves as possible.
+// bytes_per_unit = shared memory one parameter set needs (V: 8 B/state; V + W: 16 B/state).
+int plan_launch(int bytes_per_unit, int64_t P, int S, int device, const char *env_name, LaunchPlan *plan) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  const int gen = fit_generation();
-  plan->gen = gen;
-  const int fixed = gen == 2 ? k2FixedBytes : kBarBytes + kStageBytes;
-  int max_nt = (int)(((int64_t)kMaxSmem - fixed) / ((int64_t)num_states * 8));
-  max_nt = (max_nt / 32) * 32;
-  if (max_nt > (gen == 2 ? 480 : 512)) max_nt = gen == 2 ? 480 : 512;
-  if (max_nt < 32)
-    return nm_fail(NM_ERR_INVALID, "maze with %d visitable tiles does not fit the shared-memory V layout", num_states);
-  const char *env = getenv("NM_FIT_NT");
+  int max_nc = (int)(((int64_t)kMaxSmem - kFixedBytes) / bytes_per_unit);
+  max_nc = (max_nc / 32) * 32;
+  if (max_nc > 480) max_nc = 480;  // + the producer warp = 512 threads
+  if (max_nc < 32) return nm_fail(NM_ERR_INVALID, "the maze does not fit the shared-memory value-table layout");
+  int chosen = 0;
+  const char *env = getenv(env_name);
   if (env) {
-    int v = atoi(env);
-    if (v >= 32 && v <= max_nt && v % 32 == 0) {
-      plan->nt = v;
-      plan->threads = v + (gen == 2 ? 32 : 0);
-      plan->smem = (size_t)fixed + (size_t)num_states * 8 * v;
-      return NM_OK;
+    const int v = atoi(env);
+    if (v >= 32 && v <= max_nc && v % 32 == 0) chosen = v;
+  }
+  if (!chosen) {
+    const double sat = 224.0;  // resident consumer threads per SM below which latency is not hidden
+    double best = 1e300;
+    for (int nc = max_nc; nc >= 32; nc -= 32) {  // descending: ties go to the fuller CTA
+      const size_t smem = (size_t)kFixedBytes + (size_t)bytes_per_unit * nc;
+      int r = (int)(kMaxSmem / (smem + 1024));  // 1 KB per-CTA reservation
+      if (r < 1) r = 1;
+      if (r > 2048 / (nc + 32)) r = 2048 / (nc + 32);
+      if (r > 32) r = 32;
+      const int64_t ctas = (int64_t)S * ((P + nc - 1) / nc);
+      const int64_t slots = (int64_t)sms * r;
+      const int64_t waves = (ctas + slots - 1) / slots;
+      int64_t r_eff = (ctas + sms - 1) / sms;
+      if (r_eff > r) r_eff = r;
+      double load = (double)(r_eff * nc);
+      if (load < sat) load = sat;
+      const double cost = (double)waves * load;
+      if (cost < best * 0.999) {
+        best = cost;
+        chosen = nc;
+      }
     }
   }
-  const double sat = 256.0;  // resident threads per SM below which the FP64 pipe is latency-starved
-  double best = 1e300;
-  int best_nt = 32;
-  for (int nt = 32; nt <= max_nt; nt += 32) {
-    const size_t smem = (size_t)fixed + (size_t)num_states * 8 * nt;
-    int r = (int)(kMaxSmem / (smem + 1024));  // 1 KB per-CTA reservation
-    if (r < 1) r = 1;
-    if (r > 2048 / nt) r = 2048 / nt;
-    if (r > 32) r = 32;
-    const int64_t ctas = (int64_t)S * ((P + nt - 1) / nt);
-    const int64_t slots = (int64_t)sms * r;
-    const int64_t waves = (ctas + slots - 1) / slots;
-    int64_t r_eff = (ctas + sms - 1) / sms;
-    if (r_eff > r) r_eff = r;
-    double load = (double)(r_eff * nt);
-    if (load < sat) load = sat;
-    const double cost = (double)waves * load;
-    if (cost < best * 0.999) {
-      best = cost;
-      best_nt = nt;
-    }
-  }
-  plan->nt = best_nt;
-  plan->threads = best_nt + (gen == 2 ? 32 : 0);
-  plan->smem = (size_t)fixed + (size_t)num_states * 8 * best_nt;
+  plan->nc = chosen;
+  plan->smem = (size_t)kFixedBytes + (size_t)bytes_per_unit * chosen;
   return NM_OK;
 }
 
-template <int ALG, bool LL>
-int launch_fit(const FitArgs &a, int S, const LaunchPlan &plan, cudaStream_t cs) {
-  auto kernel = plan.gen == 2 ? nm_fit2_kernel<ALG, LL> : nm_fit_kernel<ALG, LL>;
+template <typename Kernel>
+int launch(Kernel kernel, const FitArgs &a, int S, const LaunchPlan &plan, cudaStream_t cs, const char *what) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
-  if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-  const dim3 grid((unsigned)((a.P + plan.nt - 1) / plan.nt), (unsigned)S, 1);
-  kernel<<<grid, plan.threads, plan.smem, cs>>>(a);
+  if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "cudaFuncSetAttribute(%s): %s", what, cudaGetErrorString(e));
+  const dim3 grid((unsigned)((a.P + plan.nc - 1) / plan.nc), (unsigned)S, 1);
+  kernel<<<grid, plan.nc + 32, plan.smem, cs>>>(a);
   e = cudaGetLastError();
-  if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_fit_kernel launch: %s", cudaGetErrorString(e));
+  if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "%s launch: %s", what, cudaGetErrorString(e));
   return NM_OK;
+}
+
+// The memoised-exponential body is OPT-IN (NM_FIT_MEMO=1).  Measured on B200 (profiles/r01_fit_memo.md): its
+// 16 B/state tables halve the parameter sets resident per SM (224 vs 448), which leaves it latency-bound
+// (6.1 ms vs 6.7 ms for the exact body on configs[1]), and on grids where |beta * V| exceeds the guard for
+// part of the grid (beta ~ 30, gamma ~ 0.99) the exact redo pass costs one more serial wave (3.3 ms).
+bool memo_enabled() {
+  const char *env = getenv("NM_FIT_MEMO");
+  return env && atoi(env) == 1;
+}
+
+template <int ALG>
+int sweep_alg(bool with_ll, FitArgs a, int S, int device, cudaStream_t cs) {
+  LaunchPlan exact;
+  int rc = plan_launch(a.num_states * 8, a.P, S, device, "NM_FIT_NC", &exact);
+  if (rc != NM_OK) return rc;
+  if (!with_ll) return launch(nm_fit_exact_kernel<ALG, false, false>, a, S, exact, cs, "nm_fit_exact_kernel");
+  LaunchPlan memo;
+  if (memo_enabled() && plan_launch(a.num_states * 16, a.P, S, device, "NM_FIT_MEMO_NC", &memo) == NM_OK) {
+    rc = launch(nm_fit_memo_kernel<ALG>, a, S, memo, cs, "nm_fit_memo_kernel");
+    if (rc != NM_OK) return rc;
+    // safety net: parameter sets that left the |beta * V| <= 700 guard wrote NaN; recompute them with
+    // the exact body (CTAs without such a parameter set exit immediately)
+    FitArgs redo = a;
+    redo.v_out = nullptr;
+    return launch(nm_fit_exact_kernel<ALG, true, true>, redo, S, exact, cs, "nm_fit_exact_kernel(redo)");
+  }
+  return launch(nm_fit_exact_kernel<ALG, true, false>, a, S, exact, cs, "nm_fit_exact_kernel");
 }
 
 int fit_sweep(int alg, bool with_ll, const nm_maze *mz, const nm_streams *st, const double *d_alpha,
@@ -321,10 +172,6 @@ int fit_sweep(int alg, bool with_ll, const nm_maze *mz, const nm_streams *st, co
                "log-likelihood need them (np.max([]) raises in the reference)");
   if (P == 0) return NM_OK;
   if (cudaSetDevice(mz->device) != cudaSuccess) return nm_fail(NM_ERR_CUDA, "cudaSetDevice(%d) failed", mz->device);
-  LaunchPlan plan;
-  int rc = plan_launch(mz->num_states, P, st->S, mz->device, &plan);
-  if (rc != NM_OK) return rc;
-  NM_CHECK_ARG((P + plan.nt - 1) / plan.nt <= 2147483647LL, "sweep: too many parameter sets");
   FitArgs a;
   a.records = st->d_records;
   a.offsets = st->d_offsets;
@@ -342,16 +189,11 @@ int fit_sweep(int alg, bool with_ll, const nm_maze *mz, const nm_streams *st, co
   a.ll_out = d_ll_out;
   a.v_out = d_v_out;
   cudaStream_t cs = (cudaStream_t)stream;
-#define NM_DISPATCH(A)                                             \
-  case A:                                                          \
-    return with_ll ? launch_fit<A, true>(a, st->S, plan, cs) : launch_fit<A, false>(a, st->S, plan, cs);
   switch (alg) {
-    NM_DISPATCH(NM_ALG_TD0)
-    NM_DISPATCH(NM_ALG_POSITIVE)
-    NM_DISPATCH(NM_ALG_NEGATIVE)
+    case NM_ALG_TD0: return sweep_alg<NM_ALG_TD0>(with_ll, a, st->S, mz->device, cs);
+    case NM_ALG_POSITIVE: return sweep_alg<NM_ALG_POSITIVE>(with_ll, a, st->S, mz->device, cs);
+    default: return sweep_alg<NM_ALG_NEGATIVE>(with_ll, a, st->S, mz->device, cs);
   }
-#undef NM_DISPATCH
-  return nm_fail(NM_ERR_INVALID, "unreachable");
 }
 
 // ---- argmin epilogue ---------------------------------------------------------------------------
@@ -366,24 +208,8 @@ __device__ __forceinline__ bool better(double v, long long i, double bv, long lo
   return v < bv || (v == bv && i < bi);
 }
 
-__global__ void __launch_bounds__(256) nm_nll_partial_kernel(const double *__restrict__ ll, int S, int64_t P,
-                                                             double *__restrict__ nll_out,
-                                                             Best *__restrict__ partial) {
-  double bv = 0.0;
-  long long bi = -1;
-  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
-    double acc = 0.0;
-    for (int s = 0; s < S; ++s) acc = __dadd_rn(acc, ll[(int64_t)s * P + p]);
-    const double nll = -acc;
-    if (nll_out) nll_out[p] = nll;
-    if (nll == nll && better(nll, p, bv, bi)) {
-      bv = nll;
-      bi = p;
-    }
-  }
-  __shared__ Best red[256];
-  red[threadIdx.x].val = bv;
-  red[threadIdx.x].idx = bi;
+__device__ __forceinline__ void block_reduce_best(Best *red, Best mine) {
+  red[threadIdx.x] = mine;
   __syncthreads();
   for (int off = 128; off > 0; off >>= 1) {
     if (threadIdx.x < off) {
@@ -392,6 +218,26 @@ __global__ void __launch_bounds__(256) nm_nll_partial_kernel(const double *__res
     }
     __syncthreads();
   }
+}
+
+__global__ void __launch_bounds__(256) nm_nll_partial_kernel(const double *__restrict__ ll, int S, int64_t P,
+                                                             double *__restrict__ nll_out,
+                                                             Best *__restrict__ partial) {
+  Best b;
+  b.val = 0.0;
+  b.idx = -1;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    for (int s = 0; s < S; ++s) acc = __dadd_rn(acc, ll[(int64_t)s * P + p]);  // sessions in index order
+    const double nll = -acc;
+    if (nll_out) nll_out[p] = nll;
+    if (nll == nll && better(nll, p, b.val, b.idx)) {
+      b.val = nll;
+      b.idx = p;
+    }
+  }
+  __shared__ Best red[256];
+  block_reduce_best(red, b);
   if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
 }
 
@@ -403,15 +249,7 @@ __global__ void __launch_bounds__(256) nm_nll_final_kernel(const Best *__restric
   b.idx = -1;
   for (int i = threadIdx.x; i < n; i += 256)
     if (better(partial[i].val, partial[i].idx, b.val, b.idx)) b = partial[i];
-  red[threadIdx.x] = b;
-  __syncthreads();
-  for (int off = 128; off > 0; off >>= 1) {
-    if (threadIdx.x < off) {
-      const Best o = red[threadIdx.x + off];
-      if (better(o.val, o.idx, red[threadIdx.x].val, red[threadIdx.x].idx)) red[threadIdx.x] = o;
-    }
-    __syncthreads();
-  }
+  block_reduce_best(red, b);
   if (threadIdx.x == 0) {
     if (red[0].idx < 0) red[0].val = __longlong_as_double(0x7ff8000000000000LL);
     *out = red[0];
@@ -453,9 +291,9 @@ extern "C" int nm_argmin_nll(const double *d_ll, int S, int64_t P, double *d_nll
   cudaStream_t cs = (cudaStream_t)stream;
   int blocks = (int)((P + 255) / 256);
   if (blocks > 1024) blocks = 1024;
-  // 16 KB of partials: one persistent scratch buffer per (device, stream), allocated on first use and
-  // kept for the life of the process -- no allocator traffic on the hot path (stream-ordered pools hand
-  // memory back to the OS at synchronisation points, which showed up as 20-500 ms stalls in bench e2e)
+  // 16 KB of partials: one persistent scratch buffer per (device, stream), allocated on first use and kept
+  // for the life of the process -- no allocator traffic on the hot path (stream-ordered pools hand memory
+  // back to the OS at synchronisation points, which showed up as 20-500 ms stalls in bench.py's e2e loop)
   int device = 0;
   cudaGetDevice(&device);
   Best *partial = nullptr;
@@ -463,11 +301,11 @@ extern "C" int nm_argmin_nll(const double *d_ll, int S, int64_t P, double *d_nll
     static std::mutex mu;
     static std::map<std::pair<int, void *>, Best *> scratch;
     std::lock_guard<std::mutex> lock(mu);
-    auto key = std::make_pair(device, stream);
+    const auto key = std::make_pair(device, stream);
     auto it = scratch.find(key);
     if (it == scratch.end()) {
       Best *buf = nullptr;
-      cudaError_t ea = cudaMalloc((void **)&buf, sizeof(Best) * 1024);
+      const cudaError_t ea = cudaMalloc((void **)&buf, sizeof(Best) * 1024);
       if (ea != cudaSuccess) return nm_fail(NM_ERR_NOMEM, "nm_argmin_nll: cudaMalloc: %s", cudaGetErrorString(ea));
       it = scratch.emplace(key, buf).first;
     }
@@ -475,7 +313,7 @@ extern "C" int nm_argmin_nll(const double *d_ll, int S, int64_t P, double *d_nll
   }
   nm_nll_partial_kernel<<<blocks, 256, 0, cs>>>(d_ll, S, P, d_nll_out, partial);
   nm_nll_final_kernel<<<1, 256, 0, cs>>>(partial, blocks, (Best *)d_best_out);
-  cudaError_t e = cudaGetLastError();
+  const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_argmin_nll launch: %s", cudaGetErrorString(e));
   return NM_OK;
 }
@@ -484,7 +322,7 @@ extern "C" int nm_fp64_peak_probe(int blocks, int threads, int iters, double *d_
                                   void *stream) {
   NM_CHECK_ARG(blocks > 0 && threads > 0 && threads <= 1024 && iters > 0 && d_sink, "nm_fp64_peak_probe: bad argument");
   nm_fp64_probe_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, d_sink);
-  cudaError_t e = cudaGetLastError();
+  const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_fp64_probe launch: %s", cudaGetErrorString(e));
   if (h_fp64_instr) *h_fp64_instr = (int64_t)blocks * threads * (int64_t)iters * 8;
   return NM_OK;

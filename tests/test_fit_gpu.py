@@ -233,3 +233,38 @@ def test_errors(cuda):
     far[10] = (5.0, 5.0)
     with pytest.raises(ValueError):
         ConditioningSweep(maze, "positive", possible_actions=H.a8()).add_session(far, rew)
+
+
+@pytest.mark.parametrize("alg", ["td0", "positive", "negative"])
+def test_memo_and_exact_bodies_agree_and_guard_falls_back(cuda, alg, monkeypatch):
+    """The memoised-exponential kernel (default) and the exact-formula kernel (NM_FIT_MEMO=0) both match
+    the oracle; parameter sets whose |beta * V| leaves the guard (huge beta, v_init far from 0) are
+    recomputed by the exact kernel and still match."""
+    omz = H.oracle_m9()
+    traj, rew = O.synthetic_session(omz, 8, 1200)
+    if alg == "negative":
+        rew = -rew
+    tr = H.oracle_transitions(omz, traj, rew, H.a8())
+    rng = np.random.default_rng(21)
+    P = 480
+    a, b, gm = H.grid_params(rng, P)
+    b[::7] = rng.uniform(2e3, 5e4, len(b[::7]))      # |beta * V| >> 700 -> guard -> exact redo
+    b[3::11] = rng.uniform(1e-6, 1e-3, len(b[3::11]))  # nearly uniform policy
+    a[5::13] = 1.0
+    gm[2::17] = 0.999
+    _, want = CO.fit(ALGS[alg], tr, a, gm, 60, beta=b, want_v=False)
+    assert np.isfinite(want).all()
+    sw = _sweep(alg, [(traj, rew)])
+    monkeypatch.setenv("NM_FIT_MEMO", "1")
+    ll_memo, V_memo = sw.log_likelihood(a, b, gm, return_v=True)
+    monkeypatch.setenv("NM_FIT_MEMO", "0")
+    ll_exact, V_exact = sw.log_likelihood(a, b, gm, return_v=True)
+    np.testing.assert_allclose(ll_memo[0], want, rtol=LL_RTOL, atol=0)
+    np.testing.assert_allclose(ll_exact[0], want, rtol=LL_RTOL, atol=0)
+    assert np.array_equal(V_memo, V_exact)  # the V recurrence is the same operations in both
+    # a starting table far from zero: every parameter set with beta * V0 > 700 is flagged at t = 0
+    v0 = np.full((9, 9), 40.0)
+    monkeypatch.setenv("NM_FIT_MEMO", "1")
+    ll0 = sw.log_likelihood(a, b, gm, v_init=v0)[0]
+    _, want0 = CO.fit(ALGS[alg], tr, a, gm, 60, beta=b, v0=H.compact(omz, v0), want_v=False)
+    np.testing.assert_allclose(ll0, want0, rtol=LL_RTOL, atol=0)
