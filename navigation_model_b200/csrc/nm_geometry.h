@@ -22,7 +22,8 @@
 struct NmMazeView {
   const uint8_t *tiles;  // [X*Y], x-major; 0 = VOID
   int X, Y;
-  double st;  // size_tile
+  double st;   // size_tile
+  double inv;  // fl(1 / size_tile): only the device fast path uses it
 };
 
 // Python `x // w` for floats, w > 0 or w < 0 (w != 0).
@@ -52,11 +53,16 @@ NM_HD bool nm_tile_visitable(const NmMazeView &m, int x, int y) {
 // Python's `x // w` equals the mathematical floor of the EXACT quotient (divmod is fmod-based).  On
 // the device that integer is obtained without fmod: q0 = floor(fl(x / w)) can only be n or n + 1, and
 // the residual x - q0 * w, evaluated exactly-rounded by one FMA, is negative iff q0 = n + 1.
-NM_HD int nm_tile_index(double x, double st) {
+NM_HD int nm_tile_index_inv(double x, double st, double inv) {
 #ifdef __CUDA_ARCH__
-  double q = floor(__ddiv_rn(x, st));
-  if (fma(-q, st, x) < 0.0) q -= 1.0;
+  // q0 = floor(fl(x * fl(1/st))) is within one of the exact floor n; the FMA residual x - q0*st (exact up to
+  // a rounding that preserves its order relative to 0 and st) tells which: < 0 -> n = q0 - 1, >= st -> q0 + 1.
+  double q = floor(x * inv);
+  const double res = fma(-q, st, x);
+  if (res < 0.0) q -= 1.0;
+  else if (res >= st) q += 1.0;
 #else
+  (void)inv;
   double q = py_floordiv(x, st);
 #endif
   if (!(q > -1.0e9)) return -1000000000;
@@ -64,8 +70,10 @@ NM_HD int nm_tile_index(double x, double st) {
   return (int)q;
 }
 
+NM_HD int nm_tile_index(double x, double st) { return nm_tile_index_inv(x, st, 1.0 / st); }
+
 NM_HD bool nm_free_at(const NmMazeView &m, double x, double y) {
-  return nm_tile_visitable(m, nm_tile_index(x, m.st), nm_tile_index(y, m.st));
+  return nm_tile_visitable(m, nm_tile_index_inv(x, m.st, m.inv), nm_tile_index_inv(y, m.st, m.inv));
 }
 
 NM_HD bool nm_move_possible(const NmMazeView &m, double x1, double y1, double x2, double y2) {
@@ -77,7 +85,7 @@ NM_HD bool nm_move_possible(const NmMazeView &m, double x1, double y1, double x2
       t = y1; y1 = y2; y2 = t;
     }
     const double slope = (y2 - y1) / (x2 - x1);
-    const int lo = nm_tile_index(x1, st), hi = nm_tile_index(x2, st);
+    const int lo = nm_tile_index_inv(x1, st, m.inv), hi = nm_tile_index_inv(x2, st, m.inv);
     for (int i = lo; i < hi; ++i) {
       const double gx = (double)(i + 1) * st;
       const double gy = slope * (gx - x1) + y1;
@@ -91,7 +99,7 @@ NM_HD bool nm_move_possible(const NmMazeView &m, double x1, double y1, double x2
       t = y1; y1 = y2; y2 = t;
     }
     const double slope = (x2 - x1) / (y2 - y1);
-    const int lo = nm_tile_index(y1, st), hi = nm_tile_index(y2, st);
+    const int lo = nm_tile_index_inv(y1, st, m.inv), hi = nm_tile_index_inv(y2, st, m.inv);
     for (int j = lo; j < hi; ++j) {
       const double gy = (double)(j + 1) * st;
       const double gx = slope * (gy - y1) + x1;

@@ -110,6 +110,7 @@ static inline NmMazeView host_view(const nm_maze *mz) {
   v.X = mz->X;
   v.Y = mz->Y;
   v.st = mz->size_tile;
+  v.inv = 1.0 / mz->size_tile;
   return v;
 }
 

@@ -52,7 +52,7 @@ struct Pcg64 {
   }
 };
 
-__global__ void __launch_bounds__(kSimThreads) nm_sim_kernel(const SimDev d) {
+__global__ void __launch_bounds__(kSimThreads, 3) nm_sim_kernel(const SimDev d) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nT = d.X * d.Y;
   uint32_t *count = reinterpret_cast<uint32_t *>(smem_raw);                 // [nT][blockDim.x]
@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(kSimThreads) nm_sim_kernel(const SimDev d) {
   mv.X = d.X;
   mv.Y = d.Y;
   mv.st = d.st;
+  mv.inv = 1.0 / d.st;
   const int A = a.n_actions;
   const int T = a.n_steps;
   uint32_t *cnt = count + tid;
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(kSimThreads) nm_sim_kernel(const SimDev d) {
     // ---- fused metrics over the history positions (history[0] = initial position, mouse.cpp:58-61) ----
     int n_visited = 0, it_visit = T + 1, count_moving = 0;
     int tile_counts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int cur_tx = nm_tile_index(px, d.st), cur_ty = nm_tile_index(py, d.st);
+    int cur_tx = nm_tile_index_inv(px, d.st, mv.inv), cur_ty = nm_tile_index_inv(py, d.st, mv.inv);
     auto record_position = [&](int t_idx, int tx, int ty, bool inside) {
       // occupancy_map / tile_analysis / it_perc_visited_maze on history entry t_idx
       if (!inside) return;
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(kSimThreads) nm_sim_kernel(const SimDev d) {
       for (int i = 0; i < kA; ++i) {
         val[i] = 0.0;
         if (vis & (1u << i)) {
-          const int tx = nm_tile_index(ex[i], d.st), ty = nm_tile_index(ey[i], d.st);
+          const int tx = nm_tile_index_inv(ex[i], d.st, mv.inv), ty = nm_tile_index_inv(ey[i], d.st, mv.inv);
           const int tile = tx * d.Y + ty;
           double acc = 0.0;
           for (int ci = 0; ci < a.n_components; ++ci) {
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(kSimThreads) nm_sim_kernel(const SimDev d) {
         px = nx;
         py = ny;
       }
-      const int ntx = nm_tile_index(px, d.st), nty = nm_tile_index(py, d.st);
+      const int ntx = nm_tile_index_inv(px, d.st, mv.inv), nty = nm_tile_index_inv(py, d.st, mv.inv);
       if (ntx != cur_tx || nty != cur_ty) count_moving += 1;  // motion_analysis, metrics.py:437-440
       cur_tx = ntx;
       cur_ty = nty;
@@ -347,6 +348,7 @@ __global__ void __launch_bounds__(256) nm_segments_kernel(const uint8_t *__restr
   mv.X = X;
   mv.Y = Y;
   mv.st = st;
+  mv.inv = 1.0 / st;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     out[i] = nm_move_possible(mv, seg[4 * i], seg[4 * i + 1], seg[4 * i + 2], seg[4 * i + 3]) ? 1 : 0;
 }

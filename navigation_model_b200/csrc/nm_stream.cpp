@@ -27,6 +27,7 @@ extern "C" int64_t nm_stream_build(const nm_maze *mz, const double *trajectory, 
   mv.X = mz->X;
   mv.Y = mz->Y;
   mv.st = mz->size_tile;
+  mv.inv = 1.0 / mz->size_tile;
 
   const double *actions = with_candidates ? mouse->actions.data() : nullptr;
 
