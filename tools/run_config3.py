@@ -1,0 +1,118 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[2]: grid sweep over 128^3 (alpha, beta, gamma) parameter sets x 100 synthetic sessions of
+5 000 steps, parameter grid sharded across the ranks, arg-min all-gather.
+
+    torchrun --nproc-per-node N tools/run_config3.py [--grid 128] [--sessions 100] [--steps 5000] [--check 8]
+
+Every rank sweeps its contiguous block of the flat parameter index over ALL sessions in one launch
+(grid = (blocks, sessions)), reduces the per-session log-likelihoods to nll[p] on the device, finds its best fit
+and all-gathers the 16-byte (nll, index) pairs.  Rank 0 spot-checks `--check` parameter sets against the C oracle
+and prints one JSON line with the whole-job throughput (max over ranks of the device time)."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--grid", type=int, default=128)
+    ap.add_argument("--sessions", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=5000)
+    ap.add_argument("--alg", default="positive")
+    ap.add_argument("--check", type=int, default=8)
+    ap.add_argument("--chunk", type=int, default=1 << 18, help="parameter sets per launch (bounds ll[S, P] memory)")
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    from navigation_model_b200.simulation.maze import Maze
+    from navigation_model_b200.sweep import ConditioningSweep, parameter_grid, reduce_best, shard_bounds
+    from oracle import np_oracle as O
+
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    G = args.grid
+    g_ax, a_ax, b_ax = np.linspace(0.5, 0.99, G), np.linspace(0.01, 1.0, G), np.logspace(-1.0, 1.5, G)
+    g, a, b = parameter_grid(g_ax, a_ax, b_ax)
+    P = a.size
+    lo, hi = shard_bounds(P, rank, world)
+    omz = O.OracleMaze(O.M9_LAYOUT, O.M9_SIZE_TILE)
+    maze = Maze(O.M9_LAYOUT, O.M9_SUBAREAS, size_tile=O.M9_SIZE_TILE)
+    acts = O.A8_UNITS * O.M9_SIZE_TILE
+    t0 = time.perf_counter()
+    sessions = [O.synthetic_session(omz, sid, args.steps) for sid in range(args.sessions)]
+    sw = ConditioningSweep(maze, args.alg, possible_actions=acts, device=local)
+    for traj, rew in sessions:
+        sw.add_session(traj, rew)
+    prep_s = time.perf_counter() - t0
+    h2d = sw.upload()
+    a_t, b_t, g_t = (torch.from_numpy(x[lo:hi]).to(dev) for x in (a, b, g))
+    n_loc = hi - lo
+    nll = torch.empty(n_loc, dtype=torch.float64, device=dev)
+    S = sw.n_sessions
+    ll_buf = torch.empty((S, min(args.chunk, n_loc)), dtype=torch.float64, device=dev)
+    best_chunks = []
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for c0 in range(0, n_loc, args.chunk):
+        c1 = min(n_loc, c0 + args.chunk)
+        ll = ll_buf[:, : c1 - c0] if c1 - c0 == ll_buf.shape[1] else torch.empty((S, c1 - c0), dtype=torch.float64, device=dev)
+        sw.log_likelihood_device(a_t[c0:c1], b_t[c0:c1], g_t[c0:c1], ll_out=ll)
+        best = sw.argmin_device(ll, nll_out=nll[c0:c1])
+        best_chunks.append((best, lo + c0))
+    e1.record()
+    torch.cuda.synchronize()
+    dev_s = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=dev)
+    # per-rank best over its chunks, then the cross-rank gather
+    cand = [reduce_best(bst, off) if world == 1 else None for bst, off in best_chunks]
+    loc_v, loc_i = float("inf"), -1
+    for bst, off in best_chunks:
+        v = float(bst[0].item())
+        i = int(bst[1:].view(torch.int64).item())
+        if i >= 0 and (v < loc_v or (v == loc_v and off + i < loc_i)):
+            loc_v, loc_i = v, off + i
+    mine = torch.empty(2, dtype=torch.float64, device=dev)
+    mine[0] = loc_v
+    mine[1:].view(torch.int64)[0] = loc_i
+    best_v, best_i = reduce_best(mine, 0)
+    if world > 1:
+        dist.all_reduce(dev_s, op=dist.ReduceOp.MAX)
+    updates = float(P) * sw.updates_per_parameter_set
+    if rank == 0:
+        chk = np.random.default_rng(0).choice(n_loc, args.check, replace=False) if args.check else []
+        max_rel = 0.0
+        nll_host = nll.cpu().numpy()
+        for j in chk:
+            want = 0.0
+            for traj, rew in sessions:
+                tr = O.extract_transitions(omz, traj, rew, O.OracleMouse(traj[0], 0.0, acts))
+                from oracle import c_oracle as CO
+                _, llw = CO.fit({"td0": 0, "positive": 1, "negative": 2}[args.alg], tr, a[lo + j:lo + j + 1],
+                                g[lo + j:lo + j + 1], 60, beta=b[lo + j:lo + j + 1], want_v=False)
+                want = want + llw[0]
+            max_rel = max(max_rel, abs(-want - nll_host[j]) / abs(want))
+        print(json.dumps({"config": f"{G}^3 parameter sets x {S} sessions x {args.steps} steps, {args.alg}",
+                          "n_gpus": world, "updates": updates, "device_seconds_max_over_ranks": float(dev_s.item()),
+                          "updates_per_s": updates / float(dev_s.item()), "best_nll": best_v, "best_index": best_i,
+                          "best_params": {"gamma": float(g[best_i]), "alpha": float(a[best_i]), "beta": float(b[best_i])},
+                          "oracle_spot_check": {"n": int(len(chk)), "max_rel_err": max_rel},
+                          "stream_h2d_bytes": h2d, "host_stream_prep_s": prep_s}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
