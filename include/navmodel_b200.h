@@ -215,7 +215,9 @@ typedef struct nm_sim_args {
   const double *d_vtable;                  /* normalised table(s) (behavioural_components.py:530-535):
                                               [X*Y] shared or [N,X*Y]                                      */
   int32_t vtable_per_mouse;
-  int32_t reserved0;
+  int32_t model_kind;                      /* 0 BehaviouralModel (softmax over components);
+                                              1 RandomModel (uniform rng.choice, exploration_model.py:131-144;
+                                              components ignored)                                          */
   const double *d_draws;                   /* [T,N] replayed uniforms of Generator.choice, or NULL         */
   const uint64_t *d_pcg_state;             /* [N,4] PCG64 {state_hi, state_lo, inc_hi, inc_lo} or NULL     */
   double visit_percentage;                 /* it_perc_visited_maze(percentage), metrics.py:698             */
@@ -234,6 +236,8 @@ typedef struct nm_sim_args {
   unsigned long long *d_occupancy_total;   /* [X*Y]     sum of the occupancy maps over all mice (atomics)  */
   double *d_model_state;                   /* [N,5]     BehaviouralModel._prev_pos (x, y), _moving (0/1),
                                               ExperienceComponent._familiarity, _ment_state (0 EXPLO/1 HOME) */
+  const uint32_t *d_pcg_u32;               /* [N,2] numpy's buffered 32-bit half {has_uint32, uinteger} or NULL */
+  uint32_t *d_pcg_u32_out;                 /* [N,2] ... after the run                                       */
 } nm_sim_args;
 
 /* StandardExperiment.run(n_steps) for n_mice independent mice on the maze's device. */

@@ -76,14 +76,14 @@ class SimArgs(C.Structure):
         ("d_anxiety", C.c_void_p), ("d_bcost_weight", C.c_void_p), ("d_bcost_table", C.c_void_p),
         ("d_experience", C.c_void_p), ("d_bpersistence", C.c_void_p),
         ("d_vtable_weight", C.c_void_p), ("d_vtable", C.c_void_p),
-        ("vtable_per_mouse", C.c_int32), ("reserved0", C.c_int32),
+        ("vtable_per_mouse", C.c_int32), ("model_kind", C.c_int32),
         ("d_draws", C.c_void_p), ("d_pcg_state", C.c_void_p),
         ("visit_percentage", C.c_double),
         ("d_final_pose", C.c_void_p), ("d_pcg_state_out", C.c_void_p),
         ("d_hist_pos", C.c_void_p), ("d_hist_ori", C.c_void_p), ("d_hist_choice", C.c_void_p),
         ("d_occupancy", C.c_void_p), ("d_it_visit", C.c_void_p), ("d_count_moving", C.c_void_p),
         ("d_tile_counts", C.c_void_p), ("d_status", C.c_void_p), ("d_occupancy_total", C.c_void_p),
-        ("d_model_state", C.c_void_p),
+        ("d_model_state", C.c_void_p), ("d_pcg_u32", C.c_void_p), ("d_pcg_u32_out", C.c_void_p),
     ]
 
 _lock = threading.Lock()

@@ -38,11 +38,23 @@ def pcg64_state_words(seeds):
     return out
 
 
-def set_pcg64_state(gen, words):
-    """Write a ``(state_hi, state_lo, inc_hi, inc_lo)`` quadruple back into a numpy ``Generator``."""
+def pcg64_buffered_u32(seeds):
+    """``uint32[N, 2]`` = numpy's buffered half of a 64-bit output ``(has_uint32, uinteger)`` per generator
+    (all zeros for fresh ``default_rng(seed)`` generators)."""
+    out = np.zeros((len(seeds), 2), dtype=np.uint32)
+    for i, s in enumerate(seeds):
+        if isinstance(s, np.random.Generator):
+            st = s.bit_generator.state
+            out[i] = (st["has_uint32"], st["uinteger"])
+    return out
+
+
+def set_pcg64_state(gen, words, buffered=(0, 0)):
+    """Write a ``(state_hi, state_lo, inc_hi, inc_lo)`` quadruple (and the buffered 32-bit half) back into a
+    numpy ``Generator``."""
     st = gen.bit_generator.state
     st["state"] = {"state": (int(words[0]) << 64) | int(words[1]), "inc": (int(words[2]) << 64) | int(words[3])}
-    st["has_uint32"], st["uinteger"] = 0, 0
+    st["has_uint32"], st["uinteger"] = int(buffered[0]), int(buffered[1])
     gen.bit_generator.state = st
 
 
@@ -61,6 +73,7 @@ class SimResult:
     choices: np.ndarray = None        # [N, T] chosen action index
     pcg_state: np.ndarray = None      # [N, 4] generator state after the run
     model_state: np.ndarray = None    # [N, 5] prev_pos.x, prev_pos.y, moving, familiarity, ment_state
+    pcg_buffered: np.ndarray = None   # [N, 2] numpy's buffered 32-bit half (has_uint32, uinteger)
 
     def tile_analysis(self, maze, n_positions):
         """``(perc, ratio, count)`` dicts keyed by tile type with one array entry per mouse
@@ -82,13 +95,20 @@ class BatchedExperiment:
     """
 
     def __init__(self, maze, possible_actions, discrete_actions, components, v_table=None, active=None,
-                 device=None, v_table_normalised=False):
+                 device=None, v_table_normalised=False, model="behavioural"):
         """
+        :param model: ``"behavioural"`` (softmax over the components, ``BehaviouralModel``) or ``"random"``
+            (uniform ``rng.choice`` among the reachable endpoints, ``RandomModel``; ``components`` must be empty)
         :param possible_actions: ``[A, 2]`` relative displacements of the Mouse (continuous units)
         :param discrete_actions: ``[A, 2]`` the action list the biomechanical components are built from
         :param components: ordered component classes (or instances, whose ``active`` flag is honoured)
         :param v_table: raw value table(s) for ``ValueTableComponent``: ``[X, Y]`` shared or ``[N, X, Y]``
         """
+        if model not in ("behavioural", "random"):
+            raise ValueError("model must be 'behavioural' or 'random'")
+        self.model_kind = 0 if model == "behavioural" else 1
+        if self.model_kind == 1 and len(components):
+            raise ValueError("the random model has no components")
         self.maze = maze
         self.actions = np.ascontiguousarray(np.asarray(possible_actions, dtype=np.float64).reshape(-1, 2))
         self.discrete_actions = np.asarray(discrete_actions)
@@ -122,6 +142,8 @@ class BatchedExperiment:
     @property
     def parameter_names(self):
         """Names of the per-mouse parameters, in ``BehaviouralModel.parameters`` order."""
+        if self.model_kind == 1:
+            return []  # RandomModel.parameters == {}
         names = ["beta"]
         for cls in self.classes:
             names += [d.name for d in cls.get_descriptors()]
@@ -217,7 +239,8 @@ class BatchedExperiment:
         for i, (k, act) in enumerate(zip(self.kinds, self.active)):
             args.component_kind[i] = k
             args.component_active[i] = int(act)
-        args.d_beta = dev_f64(cols["beta"]).data_ptr()
+        args.model_kind = self.model_kind
+        args.d_beta = dev_f64(cols["beta"] if self.model_kind == 0 else np.zeros(N)).data_ptr()
         args.d_init_pose = dev_f64(pose).data_ptr()
         args.d_init_prev = dev_f64(prev).data_ptr()
         if _native.COMP_ANXIETY in self.kinds:
@@ -245,20 +268,26 @@ class BatchedExperiment:
         if draws is not None:
             args.d_draws = dev_f64(draws.T).data_ptr()  # time-major [T, N]: coalesced per step
         else:
-            words = pcg64_state_words(generators if generators is not None else seeds)
+            gens = generators if generators is not None else seeds
+            words = pcg64_state_words(gens)
             t = torch.from_numpy(words.view(np.int64)).to(dev)
             keep.append(t)
             args.d_pcg_state = t.data_ptr()
+            t32 = torch.from_numpy(pcg64_buffered_u32(gens).view(np.int32)).to(dev)
+            keep.append(t32)
+            args.d_pcg_u32 = t32.data_ptr()
         args.visit_percentage = float(visit_percentage)
 
         o_pose = out((N, 3), torch.float64)
         o_pcg = out((N, 4), torch.int64)
+        o_p32 = out((N, 2), torch.int32, zero=True)
         o_it = out((N,), torch.int32)
         o_mov = out((N,), torch.int32)
         o_tc = out((N, 8), torch.int32)
         o_st = out((N,), torch.int32)
         o_ms = out((N, 5), torch.float64)
         args.d_final_pose, args.d_pcg_state_out = o_pose.data_ptr(), o_pcg.data_ptr()
+        args.d_pcg_u32_out = o_p32.data_ptr()
         args.d_it_visit, args.d_count_moving = o_it.data_ptr(), o_mov.data_ptr()
         args.d_tile_counts, args.d_status, args.d_model_state = o_tc.data_ptr(), o_st.data_ptr(), o_ms.data_ptr()
         o_hp = o_ho = o_hc = o_occ = o_tot = None
@@ -279,7 +308,8 @@ class BatchedExperiment:
 
         res = SimResult(final_pose=o_pose.cpu().numpy(), status=o_st.cpu().numpy(), it_visit=o_it.cpu().numpy(),
                         count_moving=o_mov.cpu().numpy(), tile_counts=o_tc.cpu().numpy(),
-                        pcg_state=o_pcg.cpu().numpy().view(np.uint64), model_state=o_ms.cpu().numpy())
+                        pcg_state=o_pcg.cpu().numpy().view(np.uint64), model_state=o_ms.cpu().numpy(),
+                        pcg_buffered=o_p32.cpu().numpy().view(np.uint32))
         if history:
             res.history_position = np.ascontiguousarray(o_hp.cpu().numpy().transpose(1, 0, 2))
             res.history_orientation = np.ascontiguousarray(o_ho.cpu().numpy().T)

@@ -43,12 +43,40 @@ __device__ __forceinline__ uint64_t rotr64(uint64_t v, unsigned r) { return (v >
 // numpy PCG64: 128-bit LCG step, then XSL-RR output of the NEW state; random() = (u64 >> 11) * 2^-53
 struct Pcg64 {
   unsigned __int128 state, inc;
-  __device__ __forceinline__ double next_double() {
+  uint32_t has32, buf32;  // numpy's buffered second half of a 64-bit output (bitgen_t has_uint32 / uinteger)
+  __device__ __forceinline__ uint64_t next64() {
     const unsigned __int128 mult = ((unsigned __int128)0x2360ED051FC65DA4ULL << 64) | 0x4385DF649FCCF645ULL;
     state = state * mult + inc;
     const uint64_t hi = (uint64_t)(state >> 64), lo = (uint64_t)state;
-    const uint64_t out = rotr64(hi ^ lo, (unsigned)(hi >> 58));
-    return (double)(out >> 11) * (1.0 / 9007199254740992.0);
+    return rotr64(hi ^ lo, (unsigned)(hi >> 58));
+  }
+  __device__ __forceinline__ double next_double() {
+    return (double)(next64() >> 11) * (1.0 / 9007199254740992.0);
+  }
+  __device__ __forceinline__ uint32_t next32() {  // low half first, the high half is buffered
+    if (has32) {
+      has32 = 0u;
+      return buf32;
+    }
+    const uint64_t v = next64();
+    has32 = 1u;
+    buf32 = (uint32_t)(v >> 32);
+    return (uint32_t)v;
+  }
+  // Generator.integers(0, n) for n <= 2^32: buffered 32-bit Lemire rejection; n == 1 consumes nothing.
+  // (Generator.choice(a) without p is a[integers(0, len(a))].)
+  __device__ __forceinline__ uint32_t bounded(uint32_t n) {
+    if (n <= 1u) return 0u;
+    uint64_t m = (uint64_t)next32() * n;
+    uint32_t left = (uint32_t)m;
+    if (left < n) {
+      const uint32_t thr = (0xffffffffu - (n - 1u)) % n;
+      while (left < thr) {
+        m = (uint64_t)next32() * n;
+        left = (uint32_t)m;
+      }
+    }
+    return (uint32_t)(m >> 32);
   }
 };
 
@@ -121,10 +149,16 @@ __global__ void __launch_bounds__(kSimThreads, 3) nm_sim_kernel(const SimDev d) 
     Pcg64 rng;
     rng.state = 0;
     rng.inc = 0;
+    rng.has32 = 0u;
+    rng.buf32 = 0u;
     if (a.d_pcg_state) {
       const uint64_t *q = a.d_pcg_state + 4 * n;
       rng.state = ((unsigned __int128)q[0] << 64) | q[1];
       rng.inc = ((unsigned __int128)q[2] << 64) | q[3];
+      if (a.d_pcg_u32) {
+        rng.has32 = a.d_pcg_u32[2 * n];
+        rng.buf32 = a.d_pcg_u32[2 * n + 1];
+      }
     }
 
     // ---- fused metrics over the history positions (history[0] = initial position, mouse.cpp:58-61) ----
@@ -175,6 +209,8 @@ __global__ void __launch_bounds__(kSimThreads, 3) nm_sim_kernel(const SimDev d) 
         status = t + 1;
         break;
       }
+      int act_idx = -1;
+      if (a.model_kind == 0) {  // ---------------- BehaviouralModel -----------------------------------------
       // -- component updates                                                 exploration_model.py:79-81
       if (a.d_experience) {  // :456-466 (count of the current tile was just incremented above)
         const double nvis = cur_inside ? (double)cnt[(cur_tx * d.Y + cur_ty) * nt] : 0.0;
@@ -256,11 +292,27 @@ __global__ void __launch_bounds__(kSimThreads, 3) nm_sim_kernel(const SimDev d) 
       const double last = run;
       const double u = a.d_draws ? a.d_draws[(int64_t)t * N + n] : rng.next_double();
       // searchsorted(cdf / cdf[-1], u, side='right'): the first candidate whose normalised cdf exceeds u
-      int act_idx = -1;
 #pragma unroll
       for (int i = 0; i < kA; ++i)
         if (act_idx < 0 && (vis & (1u << i)) && !(cdf[i] / last <= u)) act_idx = i;
       if (act_idx < 0) act_idx = last_vis;  // cannot happen for u < 1 and finite probabilities
+      } else {  // ---------------- RandomModel: rng.choice(next_positions_cont)   exploration_model.py:141 ----
+        uint32_t pick;
+        if (a.d_draws) {  // replayed uniforms: floor(u * K) (convenience mode, not numpy's draw)
+          const double u = a.d_draws[(int64_t)t * N + n];
+          pick = (uint32_t)(u * (double)K);
+          if (pick >= (uint32_t)K) pick = (uint32_t)K - 1u;
+        } else {
+          pick = rng.bounded((uint32_t)K);
+        }
+        uint32_t seen = 0u;
+#pragma unroll
+        for (int i = 0; i < kA; ++i)
+          if (vis & (1u << i)) {
+            if (seen == pick) act_idx = i;
+            ++seen;
+          }
+      }
       double nx = 0.0, ny = 0.0;
 #pragma unroll
       for (int i = 0; i < kA; ++i)
@@ -301,6 +353,10 @@ __global__ void __launch_bounds__(kSimThreads, 3) nm_sim_kernel(const SimDev d) 
       uint64_t *q = a.d_pcg_state_out + 4 * n;
       q[0] = (uint64_t)(rng.state >> 64); q[1] = (uint64_t)rng.state;
       q[2] = (uint64_t)(rng.inc >> 64);   q[3] = (uint64_t)rng.inc;
+    }
+    if (a.d_pcg_u32_out) {
+      a.d_pcg_u32_out[2 * n] = rng.has32;
+      a.d_pcg_u32_out[2 * n + 1] = rng.buf32;
     }
     if (a.d_it_visit) a.d_it_visit[n] = it_visit;
     if (a.d_count_moving) a.d_count_moving[n] = count_moving;

@@ -13,7 +13,7 @@ import numpy as np
 
 from .. import _native
 from . import behavioural_components as bc
-from .exploration_model import BehaviouralModel
+from .exploration_model import BehaviouralModel, RandomModel
 from .maze import Maze
 from .mouse import Mouse
 
@@ -32,7 +32,12 @@ class StandardExperiment:
 
     def _device_eligible(self):
         model = self._exp_model
-        if type(model) is not BehaviouralModel or type(self._maze) is not Maze or type(self._mouse) is not Mouse:
+        if type(self._maze) is not Maze or type(self._mouse) is not Mouse:
+            return False
+        if type(model) is RandomModel:
+            return (1 <= len(self._mouse.possible_actions) <= _native.NM_MAX_CAND
+                    and type(model._rng.bit_generator).__name__ == "PCG64")
+        if type(model) is not BehaviouralModel:
             return False
         comps = model._components
         if any(type(c) not in _BUILTIN for c in comps):
@@ -77,9 +82,29 @@ class StandardExperiment:
             mouse.move_to(new_position)
 
     # -- device path ----------------------------------------------------------------------------------------
+    def _run_device_random(self, iterations):
+        """RandomModel: uniform ``rng.choice`` among the reachable endpoints (``exploration_model.py:131-144``),
+        continued on the device from the model's generator (incl. numpy's buffered 32-bit half)."""
+        from ..batched_sim import BatchedExperiment, set_pcg64_state
+        model, mouse, maze = self._exp_model, self._mouse, self._maze
+        actions = mouse.possible_actions
+        exp = BatchedExperiment(maze, actions, np.ones((len(actions), 2)), [], model="random")
+        res = exp.run({}, iterations, mouse.position, mouse.orientation, generators=[model._rng], history=True)
+        if res.status[0] != 0:  # rng.choice of an empty array
+            raise ValueError("a must be non-empty")
+        if iterations <= 0:
+            return
+        hp, ho = res.history_position[0], res.history_orientation[0]
+        _native.check(_native.lib().nm_mouse_adopt_trajectory(
+            mouse._h, _native.np_ptr(np.ascontiguousarray(hp[1:])), _native.np_ptr(np.ascontiguousarray(ho[1:])),
+            iterations))
+        set_pcg64_state(model._rng, res.pcg_state[0], res.pcg_buffered[0])
+
     def _run_device(self, iterations):
         from ..batched_sim import BatchedExperiment, set_pcg64_state
         model, mouse, maze = self._exp_model, self._mouse, self._maze
+        if type(model) is RandomModel:
+            return self._run_device_random(iterations)
         comps = model._components
         actions = mouse.possible_actions
         disc_actions, v_norm = None, None
@@ -106,7 +131,7 @@ class StandardExperiment:
         lib = _native.lib()
         _native.check(lib.nm_mouse_adopt_trajectory(mouse._h, _native.np_ptr(np.ascontiguousarray(hp[1:])),
                                                     _native.np_ptr(np.ascontiguousarray(ho[1:])), iterations))
-        set_pcg64_state(model._rng, res.pcg_state[0])
+        set_pcg64_state(model._rng, res.pcg_state[0], res.pcg_buffered[0])
         ms = res.model_state[0]
         model._prev_pos = np.array([ms[0], ms[1]])
         model._moving = np.bool_(ms[2] != 0.0)

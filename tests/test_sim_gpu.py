@@ -246,3 +246,40 @@ def test_parameter_validation(cuda):
     del missing["kappa_home"]
     with pytest.raises(RuntimeError, match="kappa_home has not been specified"):
         exp.run(missing, 5, maze.get_tile_centre(1, 1), draws=np.full((1, 5), 0.5))
+
+
+def test_random_model_matches_numpy_choice(cuda):
+    """RandomModel on the device: Generator.choice(a) == a[integers(0, K)] with numpy's buffered 32-bit Lemire
+    draws, reproduced from the PCG64 state; checked against the host per-step loop driven by numpy itself."""
+    from navigation_model_b200.batched_sim import BatchedExperiment
+    from navigation_model_b200.simulation.experiment import StandardExperiment
+    from navigation_model_b200.simulation.exploration_model import RandomModel
+    from navigation_model_b200.simulation.mouse import Mouse
+    maze = H.product_m9()
+    acts = H.a8()
+    T = 400
+    for seed, start, ori in ((11, (1, 1), 0.0), (12, (7, 4), 2.1), (13, (2, 8), -1.3)):
+        pos = np.array(maze.get_tile_centre(start)) + np.array([0.013, -0.021])
+        # host plugin loop (numpy's own rng.choice)
+        m_host = Mouse(pos, ori, acts)
+        model_h = RandomModel(seed=seed)
+        exp_h = StandardExperiment(model_h, maze, m_host)
+        exp_h._run_host.__func__  # the generic loop
+        m_host.enable_history(True)
+        exp_h._run_host(T)
+        # device path through the same class
+        m_dev = Mouse(pos, ori, acts)
+        model_d = RandomModel(seed=seed)
+        exp_d = StandardExperiment(model_d, maze, m_dev)
+        assert exp_d._device_eligible()
+        exp_d.run(T)
+        hp_h, hp_d = np.array(m_host.history_position), np.array(m_dev.history_position)
+        omz = H.oracle_m9()
+        assert [omz.cont2disc(*p) for p in hp_h] == [omz.cont2disc(*p) for p in hp_d]
+        np.testing.assert_allclose(hp_d, hp_h, rtol=0, atol=POSE_ATOL)
+        # both generators end in the same state (including the buffered 32-bit half)
+        assert model_h._rng.bit_generator.state == model_d._rng.bit_generator.state
+    # batched: many seeds at once, metrics fused
+    exp = BatchedExperiment(maze, acts, O.A8_UNITS, [], model="random")
+    res = exp.run({}, 200, maze.get_tile_centre(1, 1), 0.0, seeds=list(range(64)), occupancy=True)
+    assert not res.status.any() and (res.occupancy.sum(axis=(1, 2)) == 201).all()
