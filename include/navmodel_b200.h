@@ -248,6 +248,20 @@ int nm_simulate(const nm_maze *mz, const nm_sim_args *args, void *stream);
 int nm_maze_movements_possible_device(const nm_maze *mz, const double *d_segments, int64_t n, uint8_t *d_out,
                                       void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Model-based agent (EXTENSION, parity unpinned: the reference has no model-based agent)
+ * ---------------------------------------------------------------------------------------------- */
+/* One warp = one parameter set.  Learned reward model Rhat[s1] += alpha * (r - Rhat[s1]), n_sweeps synchronous
+ * value-iteration sweeps V'[u] = max_a (Rhat[next(u,a)] + gamma * V[next(u,a)]) after every observed step, and
+ * the softmax log-likelihood (exploration_model.py:84-93) of the observed tile step under
+ * Q(s,a) = Rhat[next(s,a)] + gamma * V[next(s,a)], evaluated before the step's updates.
+ *   d_next: int16[num_states, n_actions] compact successor states, -1 where the centre-to-centre movement is
+ *           not possible (Maze.is_movement_possible, maze.py:512-527); the streams only need s, s1, r.
+ *   d_v_init: [X*Y] shared or NULL;  d_ll_out: [S, P];  d_v_out, d_r_out: [S, P, X*Y] or NULL. */
+int nm_modelbased_sweep(const nm_maze *mz, const nm_streams *st, const int16_t *d_next, int n_actions, int n_sweeps,
+                        const double *d_alpha, const double *d_beta, const double *d_gamma, int64_t P,
+                        const double *d_v_init, double *d_ll_out, double *d_v_out, double *d_r_out, void *stream);
+
 /* FP64 issue-rate micro-benchmark used for the roofline denominator: every thread runs `iters`
  * iterations of 8 independent DFMA chains; returns the instruction count via *h_fp64_instr.
  * Launches on `stream`; the caller times it with CUDA events. */

@@ -1,0 +1,185 @@
+// Model-based agent: learned reward model + value-iteration planning + softmax likelihood, swept over a
+// parameter grid.  EXTENSION (the reference has no model-based agent) specified in DESIGN.md
+// section 2 and composed from reference primitives: the maze geometry as the transition model
+// (Maze.is_movement_possible, simulation/maze.py:512-527), the `x += alpha * (target - x)` update form
+// (simulation/rl.py:185-187) and the softmax of simulation/exploration_model.py:84-93.
+//
+// Mapping: one WARP owns one parameter set (alpha, beta, gamma).  Its tables V, V' and Rhat ([S] doubles each) live in
+// shared memory; the transition table next[S, A] (int16) is staged once per CTA and shared by its warps.
+//   * likelihood of a step: lanes 0..A-1 evaluate Q(s, a) = Rhat[next] + gamma * V[next]; max / gather by warp
+//     shuffles; log-probability in FP64 with the same operation order as the oracle;
+//   * planning: the value-iteration sweep is split over the 32 lanes (states u = lane, lane + 32, ...), synchronous
+//     (Jacobi) update into V', pointers swapped after a __syncwarp.
+// The V / Rhat recurrences use _rn intrinsics (no FMA contraction): tables are bit-identical to the numpy oracle.
+#include <cuda_runtime.h>
+
+#include "nm_common.h"
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+struct MbArgs {
+  const nm_step_rec *records;
+  const int64_t *offsets, *online;
+  const int16_t *next;  // [S * A]
+  int S, A, n_sweeps;
+  const double *alpha, *beta, *gamma;
+  int64_t P;
+  const double *v_init;  // [n_tiles] shared or NULL
+  int n_tiles;
+  const int32_t *tile_of_state, *state_of_tile;
+  double *ll_out, *v_out, *r_out;
+};
+
+__device__ __forceinline__ double dmax2(double a, double b) { return (b > a) ? b : a; }
+
+__global__ void __launch_bounds__(512) nm_mb_kernel(const MbArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int S = a.S, A = a.A;
+  const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int16_t *next_sm = reinterpret_cast<int16_t *>(smem_raw);
+  const size_t next_bytes = ((size_t)S * A * sizeof(int16_t) + 15) & ~(size_t)15;
+  double *tabs = reinterpret_cast<double *>(smem_raw + next_bytes) + (size_t)warp * 3 * S;
+  double *V = tabs, *Vn = tabs + S, *R = tabs + 2 * S;
+  for (int i = threadIdx.x; i < S * A; i += blockDim.x) next_sm[i] = a.next[i];
+
+  const int sess = blockIdx.y;
+  const int64_t p = (int64_t)blockIdx.x * warps + warp;
+  const bool live = p < a.P;
+  const double alpha = live ? a.alpha[p] : 0.0, beta = live ? a.beta[p] : 0.0, gamma = live ? a.gamma[p] : 0.0;
+  for (int u = lane; u < S; u += 32) {
+    V[u] = a.v_init ? a.v_init[a.tile_of_state[u]] : 0.0;
+    R[u] = 0.0;
+  }
+  __syncthreads();
+
+  const int64_t rec0 = a.offsets[sess];
+  const int64_t n = a.offsets[sess + 1] - rec0, n_on = a.online[sess];
+  const uint4 *recs = reinterpret_cast<const uint4 *>(a.records + rec0);
+  double ll = 0.0;
+  for (int64_t i = 0; i < n; ++i) {
+    const uint4 w0 = __ldg(recs + 2 * i);  // warp-uniform address: one broadcast transaction
+    const double r = __hiloint2double((int)w0.y, (int)w0.x);
+    const int s = (int)(w0.z & 0xffffu), s1 = (int)(w0.z >> 16);
+    // ---- action values of the current state -------------------------------------------------------------
+    const int na = (lane < A) ? (int)next_sm[s * A + lane] : -1;
+    const bool ok = na >= 0;
+    const double q = ok ? __dadd_rn(R[na], __dmul_rn(gamma, V[na])) : 0.0;
+    const unsigned avail = __ballot_sync(kFull, ok);
+    const unsigned hit = __ballot_sync(kFull, ok && na == s1);
+    if (i < n_on && hit) {  // observed action = first a with next(s, a) == s1 (warp-uniform branch)
+      const int a_obs = __ffs(hit) - 1;
+      const double z = __dmul_rn(beta, q);  // exploration_model.py:87
+      double m = ok ? z : -INFINITY;
+#pragma unroll
+      for (int off = 4; off > 0; off >>= 1) m = dmax2(m, __shfl_xor_sync(kFull, m, off));  // lanes 0..7 hold the max
+      m = __shfl_sync(kFull, m, 0);
+      const double zc = __dsub_rn(z, m);  // :92
+      const double e = ok ? exp(zc) : 0.0;
+      const int K = __popc(avail);
+      double sum;
+      if (K == NM_MAX_CAND) {  // numpy pairwise sum, n == 8: lanes 0..7 are all available
+        double t = __dadd_rn(e, __shfl_xor_sync(kFull, e, 1));   // (e0+e1), (e2+e3), ...
+        t = __dadd_rn(t, __shfl_xor_sync(kFull, t, 2));          // ((e0+e1)+(e2+e3)), ...
+        sum = __dadd_rn(__shfl_sync(kFull, t, 0), __shfl_sync(kFull, t, 4));
+      } else {  // n < 8: sequential from 0.0 over the available actions in order
+        sum = 0.0;
+        for (int k = 0; k < A; ++k) {
+          const double ek = __shfl_sync(kFull, e, k);
+          if ((avail >> k) & 1u) sum = __dadd_rn(sum, ek);
+        }
+      }
+      const double zobs = __shfl_sync(kFull, zc, a_obs);
+      ll = __dadd_rn(ll, __dsub_rn(zobs, log(sum)));
+    }
+    // ---- world model: Rhat[s1] += alpha * (r - Rhat[s1]) ---------------------------------------------------
+    if (lane == 0) {
+      const double rs = R[s1];
+      R[s1] = __dadd_rn(rs, __dmul_rn(alpha, __dsub_rn(r, rs)));
+    }
+    __syncwarp();
+    // ---- planning: n_sweeps synchronous value-iteration sweeps --------------------------------------------
+    for (int sw = 0; sw < a.n_sweeps; ++sw) {
+      for (int u = lane; u < S; u += 32) {
+        double best = 0.0;
+        bool any = false;
+        for (int k = 0; k < A; ++k) {
+          const int nu = (int)next_sm[u * A + k];
+          if (nu >= 0) {
+            const double qv = __dadd_rn(R[nu], __dmul_rn(gamma, V[nu]));
+            best = any ? dmax2(best, qv) : qv;
+            any = true;
+          }
+        }
+        Vn[u] = any ? best : V[u];
+      }
+      __syncwarp();
+      double *t = V;
+      V = Vn;
+      Vn = t;
+    }
+  }
+  if (live && lane == 0 && a.ll_out) a.ll_out[(int64_t)sess * a.P + p] = ll;
+  if (live && (a.v_out || a.r_out)) {
+    const int nT = a.n_tiles;
+    for (int tile = lane; tile < nT; tile += 32) {
+      const int st = a.state_of_tile[tile];
+      const int64_t o = ((int64_t)sess * a.P + p) * nT + tile;
+      if (a.v_out) a.v_out[o] = st >= 0 ? V[st] : (a.v_init ? a.v_init[tile] : 0.0);
+      if (a.r_out) a.r_out[o] = st >= 0 ? R[st] : 0.0;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int nm_modelbased_sweep(const nm_maze *mz, const nm_streams *st, const int16_t *d_next, int n_actions,
+                                   int n_sweeps, const double *d_alpha, const double *d_beta, const double *d_gamma,
+                                   int64_t P, const double *d_v_init, double *d_ll_out, double *d_v_out,
+                                   double *d_r_out, void *stream) {
+  NM_CHECK_ARG(mz && st && d_next, "nm_modelbased_sweep: NULL maze / streams / transition table");
+  NM_CHECK_ARG(mz->device >= 0 && mz->device == st->device, "nm_modelbased_sweep: maze and streams must live on the "
+               "same CUDA device");
+  NM_CHECK_ARG(st->num_states == mz->num_states, "nm_modelbased_sweep: streams were built for another maze");
+  NM_CHECK_ARG(n_actions >= 1 && n_actions <= NM_MAX_CAND, "nm_modelbased_sweep: need 1..%d actions", NM_MAX_CAND);
+  NM_CHECK_ARG(n_sweeps >= 0 && n_sweeps <= 1024, "nm_modelbased_sweep: n_sweeps out of range");
+  NM_CHECK_ARG(P >= 0 && (P == 0 || (d_alpha && d_beta && d_gamma && d_ll_out)), "nm_modelbased_sweep: NULL array");
+  NM_CHECK_ARG(st->S <= 65535, "nm_modelbased_sweep: at most 65535 sessions per call");
+  if (P == 0) return NM_OK;
+  if (cudaSetDevice(mz->device) != cudaSuccess) return nm_fail(NM_ERR_CUDA, "cudaSetDevice(%d) failed", mz->device);
+  const int S = mz->num_states;
+  const size_t next_bytes = ((size_t)S * n_actions * sizeof(int16_t) + 15) & ~(size_t)15;
+  const size_t per_warp = (size_t)3 * S * sizeof(double);
+  int warps = (int)((200 * 1024 - next_bytes) / per_warp);
+  if (warps > 8) warps = 8;  // several CTAs per SM rather than one very wide CTA
+  NM_CHECK_ARG(warps >= 1, "nm_modelbased_sweep: a maze with %d states does not fit in shared memory", S);
+  const size_t smem = next_bytes + per_warp * warps;
+  cudaError_t e = cudaFuncSetAttribute(nm_mb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  MbArgs a;
+  a.records = st->d_records;
+  a.offsets = st->d_offsets;
+  a.online = st->d_online;
+  a.next = d_next;
+  a.S = S;
+  a.A = n_actions;
+  a.n_sweeps = n_sweeps;
+  a.alpha = d_alpha;
+  a.beta = d_beta;
+  a.gamma = d_gamma;
+  a.P = P;
+  a.v_init = d_v_init;
+  a.n_tiles = mz->X * mz->Y;
+  a.tile_of_state = mz->d_tile_of_state;
+  a.state_of_tile = mz->d_state_of_tile;
+  a.ll_out = d_ll_out;
+  a.v_out = d_v_out;
+  a.r_out = d_r_out;
+  const int64_t blocks = (P + warps - 1) / warps;
+  NM_CHECK_ARG(blocks <= 2147483647LL, "nm_modelbased_sweep: too many parameter sets for one launch");
+  nm_mb_kernel<<<dim3((unsigned)blocks, (unsigned)st->S, 1), warps * 32, smem, (cudaStream_t)stream>>>(a);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_mb_kernel launch: %s", cudaGetErrorString(e));
+  return NM_OK;
+}

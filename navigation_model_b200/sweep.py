@@ -496,3 +496,70 @@ def vtable_single(maze, alg, records, n_online, alpha, gamma, v_init):
     sw = ConditioningSweep(maze, alg)
     sw.add_records(records, n_online)
     return sw.v_tables([alpha], [gamma], v_init=v_init)[0, 0]
+
+
+class ModelBasedSweep:
+    """Grid sweep of the model-based agent (EXTENSION -- the reference has no model-based agent; semantics in
+    DESIGN.md section 2): learned reward model + ``n_sweeps`` value-iteration sweeps per observed step on the maze's
+    transition table, softmax likelihood of the observed tile steps.  One warp per parameter set.
+
+    >>> mb = ModelBasedSweep(maze, [(dx, dy) for dx in (-1, 0, 1) for dy in (-1, 0, 1) if (dx, dy) != (0, 0)])
+    >>> mb.add_session(trajectory, reward)
+    >>> ll = mb.log_likelihood(alpha, beta, gamma)      # float64[S, P]
+    """
+
+    def __init__(self, maze, discrete_actions, n_sweeps=1, device=None):
+        self.maze = maze
+        self.discrete_actions = np.asarray(discrete_actions, dtype=np.int64).reshape(-1, 2)
+        if not 1 <= len(self.discrete_actions) <= _native.NM_MAX_CAND:
+            raise ValueError(f"between 1 and {_native.NM_MAX_CAND} discrete actions are supported")
+        self.n_sweeps = int(n_sweeps)
+        self.next_table = np.ascontiguousarray(maze.transition_table(self.discrete_actions), dtype=np.int16)
+        self._base = ConditioningSweep(maze, "td0", device=device)  # session streams: s, s1, r only
+
+    def add_session(self, trajectory, reward):
+        self._base.add_session(trajectory, reward)
+
+    @property
+    def n_sessions(self):
+        return self._base.n_sessions
+
+    @property
+    def updates_per_parameter_set(self):
+        return self._base.updates_per_parameter_set
+
+    def log_likelihood(self, alpha, beta, gamma, v_init=None, return_tables=False):
+        """``float64[S, P]`` log-likelihoods (and, optionally, the final ``V`` and ``Rhat`` tables ``[S, P, X, Y]``)."""
+        b = self._base
+        torch = b._ensure_device()
+        alpha, beta, gamma = _as_param(alpha), _as_param(beta), _as_param(gamma)
+        P = max(alpha.size, beta.size, gamma.size)
+        alpha, beta, gamma = _as_param(alpha, P), _as_param(beta, P), _as_param(gamma, P)
+        if not (alpha.size == beta.size == gamma.size == P):
+            raise ValueError("alpha, beta and gamma must have the same length")
+        dev = b.torch_device
+        X, Y = self.maze.shape
+        nxt = torch.from_numpy(self.next_table).to(dev)
+        vi = None
+        if v_init is not None:
+            v = np.asarray(v_init, dtype=np.float64)
+            if v.shape != (X, Y):
+                raise ValueError(f"v_init must have shape {(X, Y)}")
+            vi = torch.from_numpy(np.ascontiguousarray(v).reshape(-1)).to(dev)
+        S = b.n_sessions
+        ll = torch.empty((S, P), dtype=torch.float64, device=dev)
+        v_out = r_out = None
+        if return_tables:
+            v_out = torch.empty((S, P, X * Y), dtype=torch.float64, device=dev)
+            r_out = torch.empty((S, P, X * Y), dtype=torch.float64, device=dev)
+        at, bt, gt = (b._to_dev(torch, x) for x in (alpha, beta, gamma))
+        with torch.cuda.device(dev):
+            _native.check(b._dmaze._lib.nm_modelbased_sweep(
+                b._dmaze.handle, b._dstreams.handle, _native.tensor_ptr(nxt), self.next_table.shape[1], self.n_sweeps,
+                _native.tensor_ptr(at), _native.tensor_ptr(bt), _native.tensor_ptr(gt), P, _native.tensor_ptr(vi),
+                _native.tensor_ptr(ll), _native.tensor_ptr(v_out), _native.tensor_ptr(r_out),
+                _native.cuda_stream_ptr()))
+            torch.cuda.current_stream().synchronize()
+        if return_tables:
+            return (ll.cpu().numpy(), v_out.cpu().numpy().reshape(S, P, X, Y), r_out.cpu().numpy().reshape(S, P, X, Y))
+        return ll.cpu().numpy()

@@ -434,3 +434,56 @@ def pcg64_state_words(seed):
     st = np.random.default_rng(seed).bit_generator.state["state"]
     m = (1 << 64) - 1
     return np.array([st["state"] >> 64, st["state"] & m, st["inc"] >> 64, st["inc"] & m], dtype=np.uint64)
+
+
+# ============================================================================ model-based agent
+# EXTENSION with no reference implementation: parity unpinned.  Composed from the
+# reference's primitives: the maze geometry as the transition model (Maze.is_movement_possible,
+# simulation/maze.py:512-527 -- what PositiveConditioning's look-ahead uses, rl.py:177-187), the
+# `x += alpha * (target - x)` update form (rl.py:185-187) and the softmax of exploration_model.py:84-93.
+def transition_table(maze, discrete_actions):
+    """``next[S, A]``: compact state reached from state ``s`` by tile displacement ``a`` when the centre-to-
+    centre movement is possible (maze.py:512-527), else -1."""
+    acts = np.asarray(discrete_actions, dtype=np.int64).reshape(-1, 2)
+    out = np.full((len(maze.vis_cells), len(acts)), -1, dtype=np.int64)
+    for s, (x, y) in enumerate(maze.vis_cells):
+        cx, cy = maze.centre((x, y))
+        for a, (dx, dy) in enumerate(acts):
+            c = (x + int(dx), y + int(dy))
+            if maze.visitable(c) and maze.move_possible(cx, cy, *maze.centre(c)):
+                out[s, a] = maze.state_of[c]
+    return out
+
+
+def run_model_based(tr, nxt, alpha, beta, gamma, n_sweeps=1, v0=None):
+    """Learned reward model + synchronous value-iteration planning + softmax likelihood.
+
+    Per online step (s -> s1, reward r):
+      Q_a   = Rhat[next(s,a)] + gamma * V[next(s,a)]        for the available actions a, in action order
+      logp  = softmax(beta * Q)[a_obs]  (log space; a_obs = first a with next(s,a) == s1, step skipped if none)
+      Rhat[s1] += alpha * (r - Rhat[s1])
+      n_sweeps x:  V'[u] = max_a (Rhat[next(u,a)] + gamma * V[next(u,a)])  for every state u;  V <- V'
+    :return: (V[S], Rhat[S], ll)
+    """
+    S, A = nxt.shape
+    V = np.zeros(S) if v0 is None else np.array(v0, dtype=np.float64)
+    R = np.zeros(S)
+    ll = 0.0
+    avail = nxt >= 0
+    safe = np.where(avail, nxt, 0)
+    for s, s1, r in zip(tr["s"].tolist(), tr["s1"].tolist(), tr["r"].tolist()):
+        acts = [a for a in range(A) if nxt[s, a] >= 0]
+        if acts:
+            q = [R[nxt[s, a]] + gamma * V[nxt[s, a]] for a in acts]
+            obs = next((i for i, a in enumerate(acts) if nxt[s, a] == s1), None)
+            if obs is not None:
+                val = [beta * v for v in q]
+                m = max(val)
+                val = [v - m for v in val]
+                ll = ll + (val[obs] - math.log(np_sum([math.exp(v) for v in val])))
+        R[s1] += alpha * (r - R[s1])
+        for _ in range(n_sweeps):
+            q_all = np.where(avail, R[safe] + gamma * V[safe], -np.inf)
+            best = q_all.max(axis=1)
+            V = np.where(avail.any(axis=1), best, V)
+    return V, R, ll
