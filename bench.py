@@ -208,7 +208,7 @@ def run_b200(args):
     import torch.distributed as dist
     from navigation_model_b200 import _native
     from navigation_model_b200.simulation.maze import Maze
-    from navigation_model_b200.sweep import ConditioningSweep, reduce_best, shard_bounds
+    from navigation_model_b200.sweep import ConditioningSweep, shard_bounds
     from oracle import np_oracle as O
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)

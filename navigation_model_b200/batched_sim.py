@@ -19,10 +19,6 @@ from . import _native
 from .simulation import behavioural_components as bc
 from .sweep import DeviceMaze
 
-_KINDS = {_native.COMP_ANXIETY: "anxiety", _native.COMP_BCOST: "bcost", _native.COMP_EXPERIENCE: "experience",
-          _native.COMP_BPERSISTENCE: "bpersistence", _native.COMP_VTABLE: "vtable"}
-
-
 def pcg64_state_words(seeds):
     """``uint64[N, 4]`` = (state_hi, state_lo, inc_hi, inc_lo) of ``numpy.random.default_rng(seed)`` for every
     seed (or of already-constructed ``Generator`` objects)."""

@@ -14,7 +14,6 @@ import helpers as H
 pytestmark = pytest.mark.gpu
 
 POSE_ATOL = 1e-12
-NAMES5 = ("anx", "bcost", "exp", "bper", "vtable")
 
 
 def _classes():
@@ -89,7 +88,7 @@ def test_device_pcg64_equals_replayed_draws(cuda, golden_sim):
     for m, seed in enumerate(g["seeds"]):
         gen = np.random.default_rng(int(seed))
         gen.random(T)
-        assert np.array_equal(b.pcg_state[m], O.pcg64_state_words(gen) if False else _words(gen))
+        assert np.array_equal(b.pcg_state[m], _words(gen))
 
 
 def _words(gen):
@@ -264,7 +263,6 @@ def test_random_model_matches_numpy_choice(cuda):
         m_host = Mouse(pos, ori, acts)
         model_h = RandomModel(seed=seed)
         exp_h = StandardExperiment(model_h, maze, m_host)
-        exp_h._run_host.__func__  # the generic loop
         m_host.enable_history(True)
         exp_h._run_host(T)
         # device path through the same class

@@ -7,7 +7,6 @@
 Prints one JSON line: agent-steps/s on the GPU (CUDA events around the launch, inputs resident) and of
 the numpy oracle on one host core for a small sample."""
 import argparse
-import ctypes as C
 import json
 import os
 import sys
@@ -52,8 +51,7 @@ def main():
                                                      bc.ValueTableComponent], v_table=V, device=0)
     pos0 = np.array(maze.get_tile_centre(1, 1)) + rng.uniform(-0.03, 0.03, (N, 2))
     ori0 = rng.uniform(-3, 3, N)
-    # host-computed PCG64 states: seed the first 4096 mice through numpy, derive the rest by offsetting the
-    # stream increment (any odd increment is a valid independent PCG64 stream)
+    # host-computed PCG64 states of default_rng(0..1023), reused cyclically (throughput only)
     gens = [np.random.default_rng(i) for i in range(min(N, 1024))]
     times = []
     res = None
