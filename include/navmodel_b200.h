@@ -262,6 +262,15 @@ int nm_modelbased_sweep(const nm_maze *mz, const nm_streams *st, const int16_t *
                         const double *d_alpha, const double *d_beta, const double *d_gamma, int64_t P,
                         const double *d_v_init, double *d_ll_out, double *d_v_out, double *d_r_out, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Batched distances between per-mouse metric results and data metrics (analysis/statistics.py:10-103)
+ * ---------------------------------------------------------------------------------------------- */
+#define NM_DIST_NORMALIZED 0 /* normalized_distance  statistics.py:67-92  */
+#define NM_DIST_MANHATTAN 1  /* manhattan_distance   statistics.py:95-103 */
+#define NM_DIST_JS 2         /* js_distance on the count vectors, statistics.py:10-54 */
+/* d_x: [N, L] one result vector per mouse; d_ref: [L] the data metric; d_out: [N]. */
+int nm_distance_rows(int kind, const double *d_x, const double *d_ref, int64_t N, int L, double *d_out, void *stream);
+
 /* FP64 issue-rate micro-benchmark used for the roofline denominator: every thread runs `iters`
  * iterations of 8 independent DFMA chains; returns the instruction count via *h_fp64_instr.
  * Launches on `stream`; the caller times it with CUDA events. */

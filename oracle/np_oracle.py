@@ -487,3 +487,34 @@ def run_model_based(tr, nxt, alpha, beta, gamma, n_sweeps=1, v0=None):
             best = q_all.max(axis=1)
             V = np.where(avail.any(axis=1), best, V)
     return V, R, ll
+
+
+# ================================================================================= distances
+# Restatement of analysis/statistics.py (pinned by the reference's test/test_statistics.py and test_fitness.py).
+def normalized_distance(h1, h2):  # statistics.py:67-92
+    h1, h2 = np.asarray(h1, dtype=np.float64), np.asarray(h2, dtype=np.float64)
+    c1, c2 = np.sum(h1), np.sum(h2)
+    if c1 == 0 and c2 != 0:
+        nd = np.linalg.norm(h2 / c2)
+    elif c2 == 0 and c1 != 0:
+        nd = np.linalg.norm(h1 / c1)
+    elif c2 == 0 and c1 == 0:
+        nd = 0
+    else:
+        nd = np.linalg.norm(h1 / c1 - h2 / c2)
+    return 1 if nd > 1 else nd
+
+
+def manhattan_distance(x1, x2):  # statistics.py:95-103
+    return np.linalg.norm(np.array(x1, dtype=np.float64) - np.array(x2, dtype=np.float64), ord=1)
+
+
+def js_distance(c1, c2):  # statistics.py:10-54 on the count vectors h[0]
+    from scipy.special import rel_entr
+    p, q = np.asarray(c1, dtype=np.float64), np.asarray(c2, dtype=np.float64)
+    p = 0 if np.sum(p) == 0 else p / np.sum(p)
+    q = 0 if np.sum(q) == 0 else q / np.sum(q)
+    m = (p + q) / 2.0
+    js = np.sum(rel_entr(p, m)) + np.sum(rel_entr(q, m))
+    d = np.sqrt(js / 2.0)
+    return 1 if math.isinf(d) else d
