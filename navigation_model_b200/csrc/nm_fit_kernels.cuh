@@ -83,8 +83,8 @@ __device__ __forceinline__ void producer_loop(const Rings &rg, const nm_step_rec
   uint32_t carry_s = kNone;  // state of the last record of the previous chunk (MEMO hazard detection)
   for (int c = 0; c < nchunks; ++c) {
     const int rslot = c % kRawStages, dslot = c % kDecStages;
-    if (c >= kDecStages) mbar_wait(&rg.empty_dec[dslot], (uint32_t)(((c / kDecStages) - 1) & 1));
-    mbar_wait(&rg.full_raw[rslot], (uint32_t)((c / kRawStages) & 1));
+    if (c >= kDecStages) mbar_wait_relaxed(&rg.empty_dec[dslot], (uint32_t)(((c / kDecStages) - 1) & 1));
+    mbar_wait_relaxed(&rg.full_raw[rslot], (uint32_t)((c / kRawStages) & 1));
     const int64_t first = (int64_t)c * kChunk;
     const int cnt = (int)(n - first < kChunk ? n - first : kChunk);
     const int src_lane = lane < cnt ? lane : cnt - 1;
@@ -170,6 +170,30 @@ __device__ __forceinline__ double exp_core(double x) {
 // < 1e-307).
 __device__ __forceinline__ double exp_nonpos(double x) { return (x < -708.0) ? 0.0 : exp_core(x); }
 
+// The same polynomial with its 16 constants pinned in registers (loaded once per thread through an opaque move,
+// so the compiler cannot turn them back into per-use constant loads: LDCU was 11 % of the issued instructions).
+struct ExpRegs {
+  double c[16];
+  __device__ __forceinline__ void load() {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) asm volatile("mov.f64 %0, %1;" : "=d"(c[i]) : "d"(c_exp[i]));
+  }
+  __device__ __forceinline__ double exp_nonpos(double x) const {
+    const double t = fma(x, c[12], c[13]);
+    const int k = __double2loint(t);
+    const double n = __dsub_rn(t, c[13]);
+    double r = fma(n, c[14], x);
+    r = fma(n, c[15], r);
+    double p = fma(c[0], r, c[1]);
+#pragma unroll
+    for (int i = 2; i < 12; ++i) p = fma(p, r, c[i]);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const double v = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+    return (x < -708.0) ? 0.0 : v;
+  }
+};
+
 __device__ __forceinline__ double dmax(double a, double b) { return (b > a) ? b : a; }  // first of equals, like np.max
 __device__ __forceinline__ double dmin(double a, double b) { return (b < a) ? b : a; }
 
@@ -207,6 +231,7 @@ __device__ __forceinline__ double lds_f64(const char *base, uint32_t off) {
 // =================================== EXACT body ===========================================================
 struct ExactAcc {
   double acc_obs, prod;
+  ExpRegs er;
 };
 
 template <int ALG, bool LL, int K>
@@ -237,7 +262,7 @@ __device__ __forceinline__ void exact_step_k(const uint4 q0, const uint4 q1, con
     }
     double e[NM_MAX_CAND];
 #pragma unroll
-    for (int k = 0; k < K; ++k) e[k] = exp_nonpos(__dsub_rn(z[k], m));  // :92-93
+    for (int k = 0; k < K; ++k) e[k] = acc.er.exp_nonpos(__dsub_rn(z[k], m));  // :92-93
     const double sum = np_sum_fixed<K>(e);
     const double zobs = __dmul_rn(beta, lds_f64(vb, q0.w));
     acc.acc_obs = __dadd_rn(acc.acc_obs, __dsub_rn(zobs, m));
@@ -334,6 +359,7 @@ __global__ void __launch_bounds__(512, 1) nm_fit_exact_kernel(const FitArgs a) {
     ExactAcc acc;
     acc.acc_obs = 0.0;
     acc.prod = 1.0;
+    acc.er.load();
     const int lane = tid & 31;
     for (int c = 0; c < nchunks; ++c) {
       const int dslot = c % kDecStages;
