@@ -189,8 +189,9 @@ struct ExpRegs {
     for (int i = 2; i < 12; ++i) p = fma(p, r, c[i]);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
-    const double v = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
-    return (x < -708.0) ? 0.0 : v;
+    // x << 0: clamp the binary exponent instead of selecting 0 -- the result (<= 2^-1021) is as good as 0 next to
+    // a softmax denominator >= 1, and one integer max replaces a DSETP + two FSEL per exponential
+    return __hiloint2double(__double2hiint(p) + (max(k, -1021) << 20), __double2loint(p));
   }
 };
 
