@@ -34,7 +34,8 @@ constexpr int kDecStages = 4;   // decoded ring
 constexpr int kRawBytes = kRawStages * kChunk * 32;
 constexpr int kDecBytes = kDecStages * kChunk * 64;
 constexpr int kBarBytes = 128;  // full_raw[2], full_dec[4], empty_dec[4]
-constexpr int kFixedBytes = kBarBytes + kRawBytes + kDecBytes;
+constexpr int kTabBytes = 128;  // 2^(j/16), j = 0..15: one shared-memory row, conflict-free for any lane pattern
+constexpr int kFixedBytes = kBarBytes + kRawBytes + kDecBytes + kTabBytes;
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 
 // decoded record, 64 bytes = 4 x uint4 (offsets = byte offsets of table rows = state * row_bytes):
@@ -170,28 +171,50 @@ __device__ __forceinline__ double exp_core(double x) {
 // < 1e-307).
 __device__ __forceinline__ double exp_nonpos(double x) { return (x < -708.0) ? 0.0 : exp_core(x); }
 
-// The same polynomial with its 16 constants pinned in registers (loaded once per thread through an opaque move,
-// so the compiler cannot turn them back into per-use constant loads: LDCU was 11 % of the issued instructions).
+// exp(x), x <= 0, for the hot loop: table-driven.  x = (16 e + j) * ln2/16 + r with |r| <= ln2/32, so
+// exp(x) = 2^e * 2^(j/16) * exp(r): a degree-7 polynomial (truncation 1.2e-18) instead of degree 13, one
+// conflict-free LDS for 2^(j/16) and one DMUL -- 12 FP64 instructions instead of 17, and a 6-deep instead of a
+// 13-deep dependent chain.  The 10 constants are pinned in registers (loaded once per thread through an opaque
+// move: as immediates / constant-bank operands they cost an LDCU or two UMOVs per use -- 11 % of the issued
+// instructions before).  Very negative x: the binary exponent is clamped instead of selecting 0 -- the result
+// (<= 2^-1021) is as good as 0 next to a softmax denominator >= 1.  Valid for -1e8 < x <= 0.
+__constant__ double c_exp2tab[16] = {1.00000000000000000e+00, 1.04427378242741375e+00, 1.09050773266525769e+00,
+                                     1.13878863475669156e+00, 1.18920711500272103e+00, 1.24185781207348400e+00,
+                                     1.29683955465100964e+00, 1.35425554693689265e+00, 1.41421356237309515e+00,
+                                     1.47682614593949935e+00, 1.54221082540794074e+00, 1.61049033194925428e+00,
+                                     1.68179283050742900e+00, 1.75625216037329945e+00, 1.83400808640934243e+00,
+                                     1.91520656139714740e+00};
+__constant__ double c_exptab_k[10] = {2.30831206542234141921e+01,           // 16 * log2(e)
+                                      6755399441055744.0,                  // 1.5 * 2^52
+                                      -6.93147180369123816490e-01 / 16.0,  // -ln2/16 (high part, exact scaling)
+                                      -1.90821492927058770002e-10 / 16.0,  // -ln2/16 (low part)
+                                      1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5};
+
 struct ExpRegs {
-  double c[16];
-  __device__ __forceinline__ void load() {
+  double c[10];
+  uint32_t tab;  // shared-window address of the 2^(j/16) table
+  __device__ __forceinline__ void load(const unsigned char *smem_base) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) asm volatile("mov.f64 %0, %1;" : "=d"(c[i]) : "d"(c_exp[i]));
+    for (int i = 0; i < 10; ++i) asm volatile("mov.f64 %0, %1;" : "=d"(c[i]) : "d"(c_exptab_k[i]));
+    tab = smem_u32(smem_base + kBarBytes + kRawBytes + kDecBytes);
   }
   __device__ __forceinline__ double exp_nonpos(double x) const {
-    const double t = fma(x, c[12], c[13]);
-    const int k = __double2loint(t);
-    const double n = __dsub_rn(t, c[13]);
-    double r = fma(n, c[14], x);
-    r = fma(n, c[15], r);
-    double p = fma(c[0], r, c[1]);
-#pragma unroll
-    for (int i = 2; i < 12; ++i) p = fma(p, r, c[i]);
+    const double t = fma(x, c[0], c[1]);
+    const int k = __double2loint(t);  // round(16 x / ln2)
+    const double n = __dsub_rn(t, c[1]);
+    double r = fma(n, c[2], x);
+    r = fma(n, c[3], r);
+    double s;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(s) : "r"(tab + ((uint32_t)(k & 15) << 3)));
+    double p = fma(c[4], r, c[5]);
+    p = fma(p, r, c[6]);
+    p = fma(p, r, c[7]);
+    p = fma(p, r, c[8]);
+    p = fma(p, r, c[9]);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
-    // x << 0: clamp the binary exponent instead of selecting 0 -- the result (<= 2^-1021) is as good as 0 next to
-    // a softmax denominator >= 1, and one integer max replaces a DSETP + two FSEL per exponential
-    return __hiloint2double(__double2hiint(p) + (max(k, -1021) << 20), __double2loint(p));
+    p = __dmul_rn(p, s);
+    return __hiloint2double(__double2hiint(p) + (max(k >> 4, -1021) << 20), __double2loint(p));
   }
 };
 
@@ -331,6 +354,7 @@ __global__ void __launch_bounds__(512, 1) nm_fit_exact_kernel(const FitArgs a) {
   const Rings rg = carve_rings(smem_raw);
   double *V = reinterpret_cast<double *>(smem_raw + kFixedBytes);
   const int tid = threadIdx.x;
+  if (tid < 16) reinterpret_cast<double *>(smem_raw + kBarBytes + kRawBytes + kDecBytes)[tid] = c_exp2tab[tid];
   const int nc = blockDim.x - 32;
   const int sess = blockIdx.y;
   const int64_t p = (int64_t)blockIdx.x * nc + tid;
@@ -360,7 +384,7 @@ __global__ void __launch_bounds__(512, 1) nm_fit_exact_kernel(const FitArgs a) {
     ExactAcc acc;
     acc.acc_obs = 0.0;
     acc.prod = 1.0;
-    acc.er.load();
+    acc.er.load(smem_raw);
     const int lane = tid & 31;
     for (int c = 0; c < nchunks; ++c) {
       const int dslot = c % kDecStages;
