@@ -128,7 +128,7 @@ def measured_hbm_peak():
 def ncu_dram_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of the fit kernel, per launch, from the committed
     `ncu --set full` capture of the same command (profiles/); None if the summary is missing."""
-    path = os.path.join(ROOT, "profiles", "r01_v2_fit_kernel_ncu.txt")
+    path = os.path.join(ROOT, "profiles", "r01_v3_fit_kernel_ncu.txt")
     try:
         total = 0.0
         for line in open(path):
