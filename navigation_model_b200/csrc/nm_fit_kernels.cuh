@@ -171,52 +171,7 @@ __device__ __forceinline__ double exp_core(double x) {
 // < 1e-307).
 __device__ __forceinline__ double exp_nonpos(double x) { return (x < -708.0) ? 0.0 : exp_core(x); }
 
-// exp(x), x <= 0, for the hot loop: table-driven.  x = (16 e + j) * ln2/16 + r with |r| <= ln2/32, so
-// exp(x) = 2^e * 2^(j/16) * exp(r): a degree-7 polynomial (truncation 1.2e-18) instead of degree 13, one
-// conflict-free LDS for 2^(j/16) and one DMUL -- 12 FP64 instructions instead of 17, and a 6-deep instead of a
-// 13-deep dependent chain.  The 10 constants are pinned in registers (loaded once per thread through an opaque
-// move: as immediates / constant-bank operands they cost an LDCU or two UMOVs per use -- 11 % of the issued
-// instructions before).  Very negative x: the binary exponent is clamped instead of selecting 0 -- the result
-// (<= 2^-1021) is as good as 0 next to a softmax denominator >= 1.  Valid for -1e8 < x <= 0.
-__constant__ double c_exp2tab[16] = {1.00000000000000000e+00, 1.04427378242741375e+00, 1.09050773266525769e+00,
-                                     1.13878863475669156e+00, 1.18920711500272103e+00, 1.24185781207348400e+00,
-                                     1.29683955465100964e+00, 1.35425554693689265e+00, 1.41421356237309515e+00,
-                                     1.47682614593949935e+00, 1.54221082540794074e+00, 1.61049033194925428e+00,
-                                     1.68179283050742900e+00, 1.75625216037329945e+00, 1.83400808640934243e+00,
-                                     1.91520656139714740e+00};
-__constant__ double c_exptab_k[10] = {2.30831206542234141921e+01,           // 16 * log2(e)
-                                      6755399441055744.0,                  // 1.5 * 2^52
-                                      -6.93147180369123816490e-01 / 16.0,  // -ln2/16 (high part, exact scaling)
-                                      -1.90821492927058770002e-10 / 16.0,  // -ln2/16 (low part)
-                                      1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5};
-
-struct ExpRegs {
-  double c[10];
-  uint32_t tab;  // shared-window address of the 2^(j/16) table
-  __device__ __forceinline__ void load(const unsigned char *smem_base) {
-#pragma unroll
-    for (int i = 0; i < 10; ++i) asm volatile("mov.f64 %0, %1;" : "=d"(c[i]) : "d"(c_exptab_k[i]));
-    tab = smem_u32(smem_base + kBarBytes + kRawBytes + kDecBytes);
-  }
-  __device__ __forceinline__ double exp_nonpos(double x) const {
-    const double t = fma(x, c[0], c[1]);
-    const int k = __double2loint(t);  // round(16 x / ln2)
-    const double n = __dsub_rn(t, c[1]);
-    double r = fma(n, c[2], x);
-    r = fma(n, c[3], r);
-    double s;
-    asm("ld.shared.f64 %0, [%1];" : "=d"(s) : "r"(tab + ((uint32_t)(k & 15) << 3)));
-    double p = fma(c[4], r, c[5]);
-    p = fma(p, r, c[6]);
-    p = fma(p, r, c[7]);
-    p = fma(p, r, c[8]);
-    p = fma(p, r, c[9]);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
-    p = __dmul_rn(p, s);
-    return __hiloint2double(__double2hiint(p) + (max(k >> 4, -1021) << 20), __double2loint(p));
-  }
-};
+#include "nm_exp.cuh"
 
 __device__ __forceinline__ double dmax(double a, double b) { return (b > a) ? b : a; }  // first of equals, like np.max
 __device__ __forceinline__ double dmin(double a, double b) { return (b < a) ? b : a; }
@@ -384,7 +339,7 @@ __global__ void __launch_bounds__(512, 1) nm_fit_exact_kernel(const FitArgs a) {
     ExactAcc acc;
     acc.acc_obs = 0.0;
     acc.prod = 1.0;
-    acc.er.load(smem_raw);
+    acc.er.load(smem_u32(smem_raw + kBarBytes + kRawBytes + kDecBytes));
     const int lane = tid & 31;
     for (int c = 0; c < nchunks; ++c) {
       const int dslot = c % kDecStages;

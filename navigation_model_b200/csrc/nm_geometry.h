@@ -76,9 +76,11 @@ NM_HD bool nm_free_at(const NmMazeView &m, double x, double y) {
   return nm_tile_visitable(m, nm_tile_index_inv(x, m.st, m.inv), nm_tile_index_inv(y, m.st, m.inv));
 }
 
-NM_HD bool nm_move_possible(const NmMazeView &m, double x1, double y1, double x2, double y2) {
+// `start_ok`: visitability of the tile under (x1, y1), computed by the caller (the simulation checks eight
+// endpoints from the same start point).
+NM_HD bool nm_move_possible_from(const NmMazeView &m, bool start_ok, double x1, double y1, double x2, double y2) {
   const double st = m.st;
-  if (!nm_free_at(m, x1, y1) || !nm_free_at(m, x2, y2)) return false;
+  if (!start_ok || !nm_free_at(m, x2, y2)) return false;
   if (x1 != x2) {
     if (x1 > x2) {
       double t = x1; x1 = x2; x2 = t;
@@ -108,6 +110,10 @@ NM_HD bool nm_move_possible(const NmMazeView &m, double x1, double y1, double x2
     }
   }
   return true;
+}
+
+NM_HD bool nm_move_possible(const NmMazeView &m, double x1, double y1, double x2, double y2) {
+  return nm_move_possible_from(m, nm_free_at(m, x1, y1), x1, y1, x2, y2);
 }
 
 // centre of tile i along one axis: st*(i+1) - st/2   (maze.py:262-263)

@@ -26,6 +26,9 @@
 
 namespace {
 
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+#include "nm_exp.cuh"
+
 constexpr int kA = NM_MAX_CAND;
 constexpr int kSimThreads = 128;
 
@@ -84,8 +87,10 @@ __global__ void __launch_bounds__(kSimThreads, 3) nm_sim_kernel(const SimDev d) 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nT = d.X * d.Y;
   uint32_t *count = reinterpret_cast<uint32_t *>(smem_raw);                 // [nT][blockDim.x]
-  uint8_t *tiles = smem_raw + (size_t)nT * blockDim.x * sizeof(uint32_t);   // [nT]
+  double *exp_tab = reinterpret_cast<double *>(smem_raw + (size_t)nT * blockDim.x * sizeof(uint32_t));  // [16]
+  uint8_t *tiles = reinterpret_cast<uint8_t *>(exp_tab + 16);                                            // [nT]
   const int tid = threadIdx.x, nt = blockDim.x;
+  if (tid < 16) exp_tab[tid] = c_exp2tab[tid];
   for (int i = tid; i < nT; i += nt) tiles[i] = d.tiles[i];
   for (int i = 0; i < nT; ++i) count[i * nt + tid] = 0u;
   __syncthreads();
@@ -105,6 +110,8 @@ __global__ void __launch_bounds__(kSimThreads, 3) nm_sim_kernel(const SimDev d) 
   uint32_t *cnt = count + tid;
 
   int status = 0;
+  ExpRegs er;
+  er.load(smem_u32(exp_tab));
   if (live) {
     // ---- per-mouse state -------------------------------------------------------------------------
     double px = a.d_init_pose[3 * n], py = a.d_init_pose[3 * n + 1], ori = a.d_init_pose[3 * n + 2];
@@ -195,13 +202,14 @@ __global__ void __launch_bounds__(kSimThreads, 3) nm_sim_kernel(const SimDev d) 
       const double c = cos(ori), s = sin(ori);
       double ex[kA], ey[kA];
       unsigned vis = 0u;
+      const bool start_ok = cur_inside && tiles[cur_tx * d.Y + cur_ty] != 0;  // tile under the mouse (maze.py:578)
 #pragma unroll
       for (int i = 0; i < kA; ++i) {
         ex[i] = 0.0;
         ey[i] = 0.0;
         if (i < A) {
           nm_pose_endpoint(c, s, px, py, d.act[i][0], d.act[i][1], &ex[i], &ey[i]);
-          if (nm_move_possible(mv, px, py, ex[i], ey[i])) vis |= 1u << i;
+          if (nm_move_possible_from(mv, start_ok, px, py, ex[i], ey[i])) vis |= 1u << i;
         }
       }
       const int K = __popc(vis);
@@ -242,7 +250,7 @@ __global__ void __launch_bounds__(kSimThreads, 3) nm_sim_kernel(const SimDev d) 
                 break;
               case NM_COMP_EXPERIENCE: {  // :473-479
                 const double cn = (double)cnt[tile * nt];
-                v = home ? (1.0 - exp(-k_home * cn)) : exp(-k_explo * cn);
+                v = home ? (1.0 - er.exp_nonpos(-k_home * cn)) : er.exp_nonpos(-k_explo * cn);
                 v = v * ex_w;
                 break;
               }
@@ -265,7 +273,7 @@ __global__ void __launch_bounds__(kSimThreads, 3) nm_sim_kernel(const SimDev d) 
       // -- softmax + numpy Generator.choice                                   :92-98
       double e[kA];
 #pragma unroll
-      for (int i = 0; i < kA; ++i) e[i] = (vis & (1u << i)) ? exp(val[i] - vmax) : 0.0;
+      for (int i = 0; i < kA; ++i) e[i] = (vis & (1u << i)) ? er.exp_nonpos(val[i] - vmax) : 0.0;
       double sum;
       if (K == kA) {
         sum = ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));  // numpy pairwise, n == 8
@@ -275,26 +283,30 @@ __global__ void __launch_bounds__(kSimThreads, 3) nm_sim_kernel(const SimDev d) 
         for (int i = 0; i < kA; ++i)
           if (vis & (1u << i)) sum = sum + e[i];
       }
+      // p = e / sum, cdf = cumsum(p), choice = first k with cdf_k / cdf_last > u.  The 2 K divisions are replaced by
+      // one reciprocal and K + 1 multiplications (p = e * (1/sum); cdf_k > u * cdf_last): like the device exp, this
+      // moves p by <= 1 ulp against numpy, which can only change a choice when u falls within ~1e-16 of a cdf step.
       double cdf[kA];
       double run = 0.0;
       bool first = true;
       int last_vis = 0;
+      const double inv_sum = 1.0 / sum;
 #pragma unroll
       for (int i = 0; i < kA; ++i) {
         if (vis & (1u << i)) {
-          const double p = e[i] / sum;
+          const double p = e[i] * inv_sum;
           run = first ? p : run + p;  // cumsum
           first = false;
           last_vis = i;
         }
         cdf[i] = run;
       }
-      const double last = run;
       const double u = a.d_draws ? a.d_draws[(int64_t)t * N + n] : rng.next_double();
+      const double thr = u * run;  // u * cdf[-1]
       // searchsorted(cdf / cdf[-1], u, side='right'): the first candidate whose normalised cdf exceeds u
 #pragma unroll
       for (int i = 0; i < kA; ++i)
-        if (act_idx < 0 && (vis & (1u << i)) && !(cdf[i] / last <= u)) act_idx = i;
+        if (act_idx < 0 && (vis & (1u << i)) && !(cdf[i] <= thr)) act_idx = i;
       if (act_idx < 0) act_idx = last_vis;  // cannot happen for u < 1 and finite probabilities
       } else {  // ---------------- RandomModel: rng.choice(next_positions_cont)   exploration_model.py:141 ----
         uint32_t pick;
@@ -448,7 +460,7 @@ extern "C" int nm_simulate(const nm_maze *mz, const nm_sim_args *args, void *str
   const int nT = mz->X * mz->Y;
   int threads = kSimThreads;
   while (threads > 32 && (size_t)nT * threads * 4 + nT > 200 * 1024) threads /= 2;
-  const size_t smem = (size_t)nT * threads * sizeof(uint32_t) + (size_t)nT;
+  const size_t smem = (size_t)nT * threads * sizeof(uint32_t) + 128 + (size_t)nT;  // visit map | 2^(j/16) table | tiles
   NM_CHECK_ARG(smem <= 227 * 1024, "nm_simulate: maze of %d tiles does not fit the shared-memory visit map", nT);
   cudaError_t e = cudaFuncSetAttribute(nm_sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
