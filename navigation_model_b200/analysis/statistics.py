@@ -65,24 +65,27 @@ class ResultsDistance:
         self._distances = []
 
     def __call__(self, results):
-        d = self._distance_function([results[k] for k in self._keys], self._x2)
-        self._distances.append(d)
-        return d
+        picked = [results[k] for k in self._keys]
+        self._distances.append(self._distance_function(picked, self._x2))
+        return self._distances[-1]
 
     def reset(self):
         self._distances = []
 
-    def median(self):
-        return np.median(self._distances)
-
-    def mean(self):
-        return np.mean(self._distances)
-
-    def std(self):
-        return np.std(self._distances)
-
-    def percentile(self):
-        return np.percentile(self._distances, 25), np.percentile(self._distances, 75)
-
     def data(self):
         return self._distances
+
+    def _summary(self, fn, *args):
+        return fn(self._distances, *args)
+
+    def median(self):
+        return self._summary(np.median)
+
+    def mean(self):
+        return self._summary(np.mean)
+
+    def std(self):
+        return self._summary(np.std)
+
+    def percentile(self):
+        return self._summary(np.percentile, 25), self._summary(np.percentile, 75)

@@ -10,6 +10,7 @@ reference's tests drive); the batched simulation does not call them -- it flatte
 per-mouse parameter arrays (:meth:`Component.device_kind`, :func:`bcost_tables`, :func:`normalise_v_table`)
 and evaluates them inside the CUDA kernel (``csrc/nm_sim.cu``).
 """
+from dataclasses import dataclass
 from enum import IntEnum
 
 import numpy as np
@@ -19,31 +20,31 @@ from .maze import GridTiles, StandardTiles
 
 
 # ------------------------------------------------------------------------------ parameter system
+@dataclass(frozen=True)
 class ParameterDescriptor:
-    """Name, bounds and default of a parameter -- no value (``:10-69``)."""
-
-    def __init__(self, name, minv, maxv, default):
-        self._name, self._minv, self._maxv, self._default = name, minv, maxv, default
-
-    name = property(lambda self: self._name)
-    minv = property(lambda self: self._minv)
-    maxv = property(lambda self: self._maxv)
-    default = property(lambda self: self._default)
+    """Name, bounds and default of a parameter -- no value, so it can live on the class (``:10-69``)."""
+    name: str
+    minv: float
+    maxv: float
+    default: float
 
     def __str__(self):
         return f"[{self.name}; range: ({self.minv}; {self.maxv}); default: {self.default}]"
 
 
 class Parameter:
-    """A descriptor plus the current, range-checked value (``:72-139``)."""
+    """A descriptor bound to a current, range-checked value; created per component instance (``:72-139``)."""
+
+    __slots__ = ("_descriptor", "_val")
 
     def __init__(self, descriptor, **kwargs):
         self._descriptor = descriptor
-        self.val = kwargs.get(self.name, descriptor.default)
+        self.val = kwargs.get(descriptor.name, descriptor.default)
 
-    name = property(lambda self: self._descriptor.name)
-    minv = property(lambda self: self._descriptor.minv)
-    maxv = property(lambda self: self._descriptor.maxv)
+    def __getattr__(self, item):  # name / minv / maxv are those of the descriptor
+        if item in ("name", "minv", "maxv"):
+            return getattr(self._descriptor, item)
+        raise AttributeError(item)
 
     @property
     def val(self):
@@ -51,9 +52,10 @@ class Parameter:
 
     @val.setter
     def val(self, value):
-        if not self.minv <= value <= self.maxv:
+        lo, hi = self._descriptor.minv, self._descriptor.maxv
+        if not lo <= value <= hi:
             raise RuntimeError(
-                f"Wrong value set for property '{self.name}' ({value}), must be in range [{self.minv}; {self.maxv}]")
+                f"Wrong value set for property '{self._descriptor.name}' ({value}), must be in range [{lo}; {hi}]")
         self._val = value
 
     def __str__(self):
@@ -163,10 +165,10 @@ def _anxiety_table(c, w, m, d=None, v=-1.0):
 
 
 @weight("W_anx")
-@parameter("p1", doc="absolute weight of the corner tile")
-@parameter("p2", minv=0., maxv=1., doc="relative weight of the wall tile")
-@parameter("p3", minv=0., maxv=1., doc="relative weight of the central area and decision-point tiles")
-@parameter("p4", doc="weight of the decision-point tiles")
+@parameter("p1", doc="value of a CORNER tile")
+@parameter("p2", doc="WALL value as a fraction of the CORNER value", minv=0.0, maxv=1.0)
+@parameter("p3", doc="CENTRE value as a fraction of the WALL value", minv=0.0, maxv=1.0)
+@parameter("p4", doc="value of a DECISION_POINT tile")
 class AnxietyComponent_Grid(Component):
     """Values the type of the tile under each candidate (grid mazes with decision points, ``:315-346``)."""
 
@@ -182,9 +184,9 @@ class AnxietyComponent_Grid(Component):
 
 
 @weight("W_anx")
-@parameter("p1", doc="absolute weight of the corner tile")
-@parameter("p2", minv=0., maxv=1., doc="relative weight of the wall tile")
-@parameter("p3", minv=0., maxv=1., doc="relative weight of the central area tile")
+@parameter("p1", doc="value of a CORNER tile")
+@parameter("p2", doc="WALL value as a fraction of the CORNER value", minv=0.0, maxv=1.0)
+@parameter("p3", doc="CENTRE value as a fraction of the WALL value", minv=0.0, maxv=1.0)
 class AnxietyComponent(Component):
     """Values the type of the tile under each candidate (``:348-376``)."""
 
@@ -217,8 +219,8 @@ def bcost_tables(discrete_actions, k, gamma):
 
 
 @weight("W_bcost")
-@parameter("k", doc="")
-@parameter("gamma", doc="")
+@parameter("k", doc="concentration of the von Mises heading preference")
+@parameter("gamma", doc="factor applied to actions two or more tiles long")
 class BiomechanicalCostComponent(Component):
     """Values the direction of the movement; contributes only on the step after a stay (``:379-416``)."""
 
@@ -235,11 +237,11 @@ class BiomechanicalCostComponent(Component):
 
 
 @weight("W_exp")
-@parameter("xi", minv=0.006, maxv=0.6, default=0.006, doc="")
-@parameter("kappa_home", minv=0.01, maxv=5.0, default=0.01, doc="")
-@parameter("kappa_explo", minv=0.01, maxv=5.0, default=0.01, doc="")
-@parameter("theta_explo", minv=80., maxv=120., default=80., doc="")
-@parameter("theta_home", minv=30., maxv=70., default=30.0, doc="")
+@parameter("xi", doc="familiarity averaging rate", default=0.006, minv=0.006, maxv=0.6)
+@parameter("kappa_home", doc="visit-count decay in the HOME state", default=0.01, minv=0.01, maxv=5.0)
+@parameter("kappa_explo", doc="visit-count decay in the EXPLO state", default=0.01, minv=0.01, maxv=5.0)
+@parameter("theta_explo", doc="familiarity above which HOME switches to EXPLO", default=80.0, minv=80.0, maxv=120.0)
+@parameter("theta_home", doc="familiarity below which EXPLO switches to HOME", default=30.0, minv=30.0, maxv=70.0)
 class ExperienceComponent(Component):
     """Visit counts, a familiarity average and a HOME / EXPLO hysteresis (``:419-482``)."""
 
@@ -272,9 +274,9 @@ class ExperienceComponent(Component):
 
 
 @weight("W_bper")
-@parameter("bp", doc="")
-@parameter("Wm", doc="")
-@parameter("Wnm", doc="")
+@parameter("bp", doc="base persistence value")
+@parameter("Wm", doc="factor of the null action after a stay")
+@parameter("Wnm", doc="factor of the moving actions after a move")
 class BiomechPersistenceComponent(Component):
     """Tendency to keep moving / keep still (``:485-516``)."""
 
