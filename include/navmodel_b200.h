@@ -238,6 +238,11 @@ typedef struct nm_sim_args {
                                               ExperienceComponent._familiarity, _ment_state (0 EXPLO/1 HOME) */
   const uint32_t *d_pcg_u32;               /* [N,2] numpy's buffered 32-bit half {has_uint32, uinteger} or NULL */
   uint32_t *d_pcg_u32_out;                 /* [N,2] ... after the run                                       */
+  uint64_t device_seed;                    /* use_device_seed != 0: every mouse seeds its own PCG64 stream ON THE
+                                              DEVICE from (device_seed, mouse index) (splitmix64 -> pcg64_srandom);
+                                              fast path for millions of mice, NOT numpy's default_rng seeding   */
+  int32_t use_device_seed;
+  int32_t reserved1;
 } nm_sim_args;
 
 /* StandardExperiment.run(n_steps) for n_mice independent mice on the maze's device. */

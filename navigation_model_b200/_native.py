@@ -87,6 +87,7 @@ class SimArgs(C.Structure):
         ("d_occupancy", C.c_void_p), ("d_it_visit", C.c_void_p), ("d_count_moving", C.c_void_p),
         ("d_tile_counts", C.c_void_p), ("d_status", C.c_void_p), ("d_occupancy_total", C.c_void_p),
         ("d_model_state", C.c_void_p), ("d_pcg_u32", C.c_void_p), ("d_pcg_u32_out", C.c_void_p),
+        ("device_seed", C.c_uint64), ("use_device_seed", C.c_int32), ("reserved1", C.c_int32),
     ]
 
 _lock = threading.Lock()

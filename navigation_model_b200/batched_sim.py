@@ -132,6 +132,7 @@ class BatchedExperiment:
             raise ValueError("ValueTableComponent needs v_table")
         self._device = device
         self._dmaze = None
+        self.last_kernel_ms = None
         # True: v_table already holds ValueTableComponent._v_table (normalised once at construction)
         self._normalise = (lambda t: np.asarray(t, dtype=np.float64)) if v_table_normalised else bc.normalise_v_table
 
@@ -175,20 +176,29 @@ class BatchedExperiment:
         return cols
 
     def run(self, params, n_steps, init_pos, init_ori=0.0, init_disc=None, seeds=None, draws=None,
-            visit_percentage=80, history=False, occupancy=False, occupancy_total=False, generators=None):
+            visit_percentage=80, history=False, occupancy=False, occupancy_total=False, generators=None,
+            device_seed=None, n_mice=None):
         """Simulate ``n_steps`` iterations for every mouse.
 
         :param params: ``{name: array[N] or scalar}`` for every name in :attr:`parameter_names`
         :param init_pos: ``[2]`` or ``[N, 2]``; ``init_ori``: scalar or ``[N]``
         :param init_disc: ``init_pos_discrete`` handed to ``BehaviouralModel`` (default: tile of ``init_pos``)
-        :param seeds: ``[N]`` seeds of ``default_rng`` -- or ``draws[N, n_steps]`` replayed uniforms
+        :param seeds: ``[N]`` seeds of ``default_rng`` -- or ``draws[N, n_steps]`` replayed uniforms -- or
+            ``device_seed`` (with ``n_mice``): every mouse seeds its own PCG64 stream on the device from
+            ``(device_seed, mouse index)``; the fast path for millions of mice (not numpy's seeding)
         :param history: also return the full position / orientation / choice histories
         """
         import torch
         _native.require_device()
-        if (seeds is None) == (draws is None) and generators is None:
-            raise ValueError("give exactly one of seeds and draws")
-        if draws is not None:
+        if device_seed is not None:
+            if seeds is not None or draws is not None or generators is not None or n_mice is None:
+                raise ValueError("device_seed needs n_mice and excludes seeds / draws / generators")
+            N = int(n_mice)
+        elif (seeds is None) == (draws is None) and generators is None:
+            raise ValueError("give exactly one of seeds, draws and device_seed")
+        if device_seed is not None:
+            pass
+        elif draws is not None:
             draws = np.asarray(draws, dtype=np.float64)
             N = draws.shape[0]
             if draws.shape != (N, n_steps):
@@ -261,7 +271,10 @@ class BatchedExperiment:
                 args.vtable_per_mouse = 1
             else:
                 raise ValueError(f"v_table must have shape {(X, Y)} or {(N, X, Y)}")
-        if draws is not None:
+        if device_seed is not None:
+            args.device_seed = int(device_seed) & ((1 << 64) - 1)
+            args.use_device_seed = 1
+        elif draws is not None:
             args.d_draws = dev_f64(draws.T).data_ptr()  # time-major [T, N]: coalesced per step
         else:
             gens = generators if generators is not None else seeds
@@ -299,8 +312,12 @@ class BatchedExperiment:
             args.d_occupancy_total = o_tot.data_ptr()
 
         with torch.cuda.device(dev):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
             _native.check(self._dmaze._lib.nm_simulate(self._dmaze.handle, C.byref(args), _native.cuda_stream_ptr()))
+            e1.record()
             torch.cuda.current_stream().synchronize()
+            self.last_kernel_ms = e0.elapsed_time(e1)  # device time of nm_sim_kernel (CUDA events)
 
         res = SimResult(final_pose=o_pose.cpu().numpy(), status=o_st.cpu().numpy(), it_visit=o_it.cpu().numpy(),
                         count_moving=o_mov.cpu().numpy(), tile_counts=o_tc.cpu().numpy(),

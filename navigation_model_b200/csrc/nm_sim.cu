@@ -166,6 +166,25 @@ __global__ void __launch_bounds__(kSimThreads, 3) nm_sim_kernel(const SimDev d) 
         rng.has32 = a.d_pcg_u32[2 * n];
         rng.buf32 = a.d_pcg_u32[2 * n + 1];
       }
+    } else if (a.use_device_seed) {
+      // pcg64_srandom(initstate, initseq) with both 128-bit values drawn from splitmix64(device_seed, mouse index)
+      uint64_t z = a.device_seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(4 * n + 1);
+      uint64_t w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        z += 0x9E3779B97F4A7C15ULL;
+        uint64_t y = z;
+        y = (y ^ (y >> 30)) * 0xBF58476D1CE4E5B9ULL;
+        y = (y ^ (y >> 27)) * 0x94D049BB133111EBULL;
+        w[i] = y ^ (y >> 31);
+      }
+      const unsigned __int128 initstate = ((unsigned __int128)w[0] << 64) | w[1];
+      const unsigned __int128 initseq = ((unsigned __int128)w[2] << 64) | w[3];
+      rng.state = 0;
+      rng.inc = (initseq << 1) | 1u;
+      rng.next64();
+      rng.state += initstate;
+      rng.next64();
     }
 
     // ---- fused metrics over the history positions (history[0] = initial position, mouse.cpp:58-61) ----
@@ -432,8 +451,8 @@ extern "C" int nm_simulate(const nm_maze *mz, const nm_sim_args *args, void *str
                "nm_simulate: need 1..%d relative actions", NM_MAX_CAND);
   NM_CHECK_ARG(a.n_components >= 0 && a.n_components <= NM_MAX_COMPONENTS, "nm_simulate: too many components");
   NM_CHECK_ARG(a.d_beta && a.d_init_pose && a.d_init_prev, "nm_simulate: NULL beta / init_pose / init_prev");
-  NM_CHECK_ARG((a.d_draws != nullptr) != (a.d_pcg_state != nullptr),
-               "nm_simulate: give exactly one of d_draws (replayed uniforms) and d_pcg_state");
+  NM_CHECK_ARG((a.d_draws != nullptr) + (a.d_pcg_state != nullptr) + (a.use_device_seed != 0) == 1,
+               "nm_simulate: give exactly one of d_draws (replayed uniforms), d_pcg_state and use_device_seed");
   for (int i = 0; i < a.n_components; ++i) {
     const int k = a.component_kind[i];
     const bool ok = (k == NM_COMP_ANXIETY && a.d_anxiety) || (k == NM_COMP_BCOST && a.d_bcost_table && a.d_bcost_weight) ||

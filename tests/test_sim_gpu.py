@@ -281,3 +281,23 @@ def test_random_model_matches_numpy_choice(cuda):
     exp = BatchedExperiment(maze, acts, O.A8_UNITS, [], model="random")
     res = exp.run({}, 200, maze.get_tile_centre(1, 1), 0.0, seeds=list(range(64)), occupancy=True)
     assert not res.status.any() and (res.occupancy.sum(axis=(1, 2)) == 201).all()
+
+
+def test_device_seeded_streams(cuda):
+    """device_seed: per-mouse PCG64 streams seeded on the device -- deterministic, distinct across mice and seeds."""
+    from navigation_model_b200.batched_sim import BatchedExperiment
+    from navigation_model_b200.simulation import behavioural_components as bc
+    maze = H.product_m9()
+    exp = BatchedExperiment(maze, H.a8(), O.A8_UNITS, [bc.AnxietyComponent])
+    P = {"beta": 1.5, "W_anx": 2.0, "p1": 0.9, "p2": 0.5, "p3": 0.4}
+    kw = dict(init_pos=maze.get_tile_centre(1, 1), init_ori=0.0, init_disc=(1, 1), history=True, n_mice=512)
+    a = exp.run(P, 150, device_seed=7, **kw)
+    b = exp.run(P, 150, device_seed=7, **kw)
+    c = exp.run(P, 150, device_seed=8, **kw)
+    assert not a.status.any() and np.array_equal(a.choices, b.choices)
+    assert not np.array_equal(a.choices, c.choices)
+    assert len({tuple(r) for r in a.choices}) > 500          # the mice do not share a stream
+    freq = np.bincount(a.choices.ravel(), minlength=8) / a.choices.size
+    assert freq.max() < 0.6 and (freq > 0).sum() >= 6          # a softmax policy, not a stuck generator
+    with pytest.raises(ValueError):
+        exp.run(P, 10, device_seed=1, seeds=[1], **kw)
