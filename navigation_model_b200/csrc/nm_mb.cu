@@ -4,12 +4,17 @@
 // (Maze.is_movement_possible, simulation/maze.py:512-527), the `x += alpha * (target - x)` update form
 // (simulation/rl.py:185-187) and the softmax of simulation/exploration_model.py:84-93.
 //
-// Mapping: one WARP owns one parameter set (alpha, beta, gamma).  Its tables V, V' and Rhat ([S] doubles each) live in
-// shared memory; the transition table next[S, A] (int16) is staged once per CTA and shared by its warps.
+// Mapping: one WARP owns one parameter set (alpha, beta, gamma).  Its tables W, V and Rhat live in shared memory; the
+// transition table is staged once per CTA as rows of eight 16-bit byte offsets into W (one LDS.128 per state) and
+// shared by its warps.
 //   * likelihood of a step: lanes 0..A-1 evaluate Q(s, a) = Rhat[next] + gamma * V[next]; max / gather by warp
 //     shuffles; log-probability in FP64 with the same operation order as the oracle;
-//   * planning: the value-iteration sweep is split over the 32 lanes (states u = lane, lane + 32, ...), synchronous
-//     (Jacobi) update into V', pointers swapped after a __syncwarp.
+//   * planning: a value-iteration sweep is two passes split over the 32 lanes (states u = lane, lane + 32, ...):
+//     (1) W[u] = Rhat[u] + gamma * V[u] once per state -- Q(u, a) depends on (u, a) only through next(u, a), so the
+//     S*A action values of a sweep are S distinct numbers, computed with exactly the oracle's two roundings;
+//     (2) V[u] = max over the available actions, in action order, of W[next(u, a)].  Unavailable actions point at
+//     the sentinel slot W[-1] = -inf, which the running compare-select never picks, so the pass is branch-free; V can
+//     be overwritten in place because pass 2 reads only W (the sweep stays synchronous / Jacobi).
 // The V / Rhat recurrences use _rn intrinsics (no FMA contraction): tables are bit-identical to the numpy oracle.
 #include <cuda_runtime.h>
 
@@ -34,15 +39,45 @@ struct MbArgs {
 
 __device__ __forceinline__ double dmax2(double a, double b) { return (b > a) ? b : a; }
 
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+
+// max over the eight row entries, in action order, starting from the sentinel (-inf): identical to "first available
+// action initialises, the others compare-select" for every non-NaN table.
+__device__ __forceinline__ double row_max(uint32_t w_base, const uint4 row) {
+  const double q0 = lds_f64(w_base + (row.x & 0xffffu)), q1 = lds_f64(w_base + (row.x >> 16));
+  const double q2 = lds_f64(w_base + (row.y & 0xffffu)), q3 = lds_f64(w_base + (row.y >> 16));
+  const double q4 = lds_f64(w_base + (row.z & 0xffffu)), q5 = lds_f64(w_base + (row.z >> 16));
+  const double q6 = lds_f64(w_base + (row.w & 0xffffu)), q7 = lds_f64(w_base + (row.w >> 16));
+  double best = q0;
+  best = dmax2(best, q1);
+  best = dmax2(best, q2);
+  best = dmax2(best, q3);
+  best = dmax2(best, q4);
+  best = dmax2(best, q5);
+  best = dmax2(best, q6);
+  best = dmax2(best, q7);
+  return best;
+}
+
 __global__ void __launch_bounds__(512) nm_mb_kernel(const MbArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int S = a.S, A = a.A;
   const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int16_t *next_sm = reinterpret_cast<int16_t *>(smem_raw);
-  const size_t next_bytes = ((size_t)S * A * sizeof(int16_t) + 15) & ~(size_t)15;
-  double *tabs = reinterpret_cast<double *>(smem_raw + next_bytes) + (size_t)warp * 3 * S;
-  double *V = tabs, *Vn = tabs + S, *R = tabs + 2 * S;
-  for (int i = threadIdx.x; i < S * A; i += blockDim.x) next_sm[i] = a.next[i];
+  // rows[u] = eight u16 byte offsets into W: 8 * (next(u, a) + 1), or 0 (the sentinel slot) when unavailable
+  uint16_t *rows = reinterpret_cast<uint16_t *>(smem_raw);
+  const size_t rows_bytes = (size_t)S * 16;
+  const size_t tab_doubles = (size_t)3 * S + 2;  // W[-1..S-1] (+1 pad keeps V 16-byte aligned) | V[S] | R[S]
+  double *tabs = reinterpret_cast<double *>(smem_raw + rows_bytes) + (size_t)warp * tab_doubles;
+  double *W = tabs, *V = tabs + S + 2, *R = tabs + 2 * S + 2;
+  for (int i = threadIdx.x; i < S * 8; i += blockDim.x) {
+    const int u = i >> 3, k = i & 7;
+    const int nu = k < A ? (int)a.next[u * A + k] : -1;
+    rows[i] = (uint16_t)(nu >= 0 ? 8 * (nu + 1) : 0);
+  }
 
   const int sess = blockIdx.y;
   const int64_t p = (int64_t)blockIdx.x * warps + warp;
@@ -52,7 +87,10 @@ __global__ void __launch_bounds__(512) nm_mb_kernel(const MbArgs a) {
     V[u] = a.v_init ? a.v_init[a.tile_of_state[u]] : 0.0;
     R[u] = 0.0;
   }
+  if (lane == 0) W[0] = -INFINITY;
   __syncthreads();
+  const uint32_t w_base = (uint32_t)__cvta_generic_to_shared(W);
+  const uint4 *rows4 = reinterpret_cast<const uint4 *>(rows);
 
   const int64_t rec0 = a.offsets[sess];
   const int64_t n = a.offsets[sess + 1] - rec0, n_on = a.online[sess];
@@ -63,7 +101,7 @@ __global__ void __launch_bounds__(512) nm_mb_kernel(const MbArgs a) {
     const double r = __hiloint2double((int)w0.y, (int)w0.x);
     const int s = (int)(w0.z & 0xffffu), s1 = (int)(w0.z >> 16);
     // ---- action values of the current state -------------------------------------------------------------
-    const int na = (lane < A) ? (int)next_sm[s * A + lane] : -1;
+    const int na = (lane < A) ? ((int)rows[s * 8 + lane] >> 3) - 1 : -1;
     const bool ok = na >= 0;
     const double q = ok ? __dadd_rn(R[na], __dmul_rn(gamma, V[na])) : 0.0;
     const unsigned avail = __ballot_sync(kFull, ok);
@@ -101,23 +139,21 @@ __global__ void __launch_bounds__(512) nm_mb_kernel(const MbArgs a) {
     __syncwarp();
     // ---- planning: n_sweeps synchronous value-iteration sweeps --------------------------------------------
     for (int sw = 0; sw < a.n_sweeps; ++sw) {
-      for (int u = lane; u < S; u += 32) {
-        double best = 0.0;
-        bool any = false;
-        for (int k = 0; k < A; ++k) {
-          const int nu = (int)next_sm[u * A + k];
-          if (nu >= 0) {
-            const double qv = __dadd_rn(R[nu], __dmul_rn(gamma, V[nu]));
-            best = any ? dmax2(best, qv) : qv;
-            any = true;
-          }
-        }
-        Vn[u] = any ? best : V[u];
+      for (int u = lane; u < S; u += 32) W[u + 1] = __dadd_rn(R[u], __dmul_rn(gamma, V[u]));
+      __syncwarp();
+      int u = lane;
+      for (; u + 32 < S; u += 64) {  // two states per trip: sixteen independent loads in flight
+        const uint4 ra = rows4[u], rb = rows4[u + 32];
+        const double ba = row_max(w_base, ra), bb = row_max(w_base, rb);
+        if (ra.x | ra.y | ra.z | ra.w) V[u] = ba;  // no available action: V[u] stays
+        if (rb.x | rb.y | rb.z | rb.w) V[u + 32] = bb;
+      }
+      if (u < S) {
+        const uint4 ra = rows4[u];
+        const double ba = row_max(w_base, ra);
+        if (ra.x | ra.y | ra.z | ra.w) V[u] = ba;
       }
       __syncwarp();
-      double *t = V;
-      V = Vn;
-      Vn = t;
     }
   }
   if (live && lane == 0 && a.ll_out) a.ll_out[(int64_t)sess * a.P + p] = ll;
@@ -149,12 +185,25 @@ extern "C" int nm_modelbased_sweep(const nm_maze *mz, const nm_streams *st, cons
   if (P == 0) return NM_OK;
   if (cudaSetDevice(mz->device) != cudaSuccess) return nm_fail(NM_ERR_CUDA, "cudaSetDevice(%d) failed", mz->device);
   const int S = mz->num_states;
-  const size_t next_bytes = ((size_t)S * n_actions * sizeof(int16_t) + 15) & ~(size_t)15;
-  const size_t per_warp = (size_t)3 * S * sizeof(double);
-  int warps = (int)((200 * 1024 - next_bytes) / per_warp);
-  if (warps > 8) warps = 8;  // several CTAs per SM rather than one very wide CTA
+  NM_CHECK_ARG(S < 8190, "nm_modelbased_sweep: at most 8189 states (16-bit byte offsets into the value table)");
+  const size_t rows_bytes = (size_t)S * 16;
+  const size_t per_warp = ((size_t)3 * S + 2) * sizeof(double);
+  // CTAs per SM x warps per CTA: as many resident warps as 227 KB of shared memory (1 KB reserved per CTA) allow
+  int warps = 0, best_total = 0;
+  for (int ctas = 1; ctas <= 8; ++ctas) {
+    const long avail = (long)(227 * 1024) / ctas - 1024 - (long)rows_bytes;
+    if (avail < (long)per_warp) break;
+    int w = (int)(avail / (long)per_warp);
+    if (w > 16) w = 16;
+    int total = w * ctas;
+    if (total > 64) total = 64;
+    if (total >= best_total) {
+      best_total = total;
+      warps = w;
+    }
+  }
   NM_CHECK_ARG(warps >= 1, "nm_modelbased_sweep: a maze with %d states does not fit in shared memory", S);
-  const size_t smem = next_bytes + per_warp * warps;
+  const size_t smem = rows_bytes + per_warp * warps;
   cudaError_t e = cudaFuncSetAttribute(nm_mb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   MbArgs a;

@@ -23,6 +23,7 @@
 
 #include "nm_common.h"
 #include "nm_pose.h"
+#include "nm_simgeom.cuh"
 
 namespace {
 
@@ -88,10 +89,11 @@ __global__ void __launch_bounds__(kSimThreads, 3) nm_sim_kernel(const SimDev d) 
   const int nT = d.X * d.Y;
   uint32_t *count = reinterpret_cast<uint32_t *>(smem_raw);                 // [nT][blockDim.x]
   double *exp_tab = reinterpret_cast<double *>(smem_raw + (size_t)nT * blockDim.x * sizeof(uint32_t));  // [16]
-  uint8_t *tiles = reinterpret_cast<uint8_t *>(exp_tab + 16);                                            // [nT]
   const int tid = threadIdx.x, nt = blockDim.x;
   if (tid < 16) exp_tab[tid] = c_exp2tab[tid];
-  for (int i = tid; i < nT; i += nt) tiles[i] = d.tiles[i];
+  NmSimGeom geo;  // tile table, grid-line tables (nm_simgeom.cuh)
+  geo.build(reinterpret_cast<unsigned char *>(exp_tab + 16), d.tiles, d.X, d.Y, d.st);
+  const uint8_t *tiles = geo.tiles;
   for (int i = 0; i < nT; ++i) count[i * nt + tid] = 0u;
   __syncthreads();
 
@@ -99,12 +101,6 @@ __global__ void __launch_bounds__(kSimThreads, 3) nm_sim_kernel(const SimDev d) 
   const int64_t n = (int64_t)blockIdx.x * nt + tid;
   const int64_t N = a.n_mice;
   const bool live = n < N;
-  NmMazeView mv;
-  mv.tiles = tiles;
-  mv.X = d.X;
-  mv.Y = d.Y;
-  mv.st = d.st;
-  mv.inv = 1.0 / d.st;
   const int A = a.n_actions;
   const int T = a.n_steps;
   uint32_t *cnt = count + tid;
@@ -190,7 +186,7 @@ __global__ void __launch_bounds__(kSimThreads, 3) nm_sim_kernel(const SimDev d) 
     // ---- fused metrics over the history positions (history[0] = initial position, mouse.cpp:58-61) ----
     int n_visited = 0, it_visit = T + 1, count_moving = 0;
     int tile_counts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int cur_tx = nm_tile_index_inv(px, d.st, mv.inv), cur_ty = nm_tile_index_inv(py, d.st, mv.inv);
+    int cur_tx = geo.tile(px), cur_ty = geo.tile(py);
     auto record_position = [&](int t_idx, int tx, int ty, bool inside) {
       // occupancy_map / tile_analysis / it_perc_visited_maze on history entry t_idx
       if (!inside) return;
@@ -218,17 +214,18 @@ __global__ void __launch_bounds__(kSimThreads, 3) nm_sim_kernel(const SimDev d) 
     for (int t = 0; t < T; ++t) {
       record_position(t, cur_tx, cur_ty, cur_inside);
       // -- endpoints + reachability                                          experiment.py:36-38
-      const double c = cos(ori), s = sin(ori);
-      double ex[kA], ey[kA];
+      double c, s;
+      sincos(ori, &s, &c);
+      int etile[kA];
       unsigned vis = 0u;
       const bool start_ok = cur_inside && tiles[cur_tx * d.Y + cur_ty] != 0;  // tile under the mouse (maze.py:578)
 #pragma unroll
       for (int i = 0; i < kA; ++i) {
-        ex[i] = 0.0;
-        ey[i] = 0.0;
+        etile[i] = 0;
         if (i < A) {
-          nm_pose_endpoint(c, s, px, py, d.act[i][0], d.act[i][1], &ex[i], &ey[i]);
-          if (nm_move_possible_from(mv, start_ok, px, py, ex[i], ey[i])) vis |= 1u << i;
+          double ex, ey;
+          nm_pose_endpoint(c, s, px, py, d.act[i][0], d.act[i][1], &ex, &ey);
+          if (geo.move_ok(start_ok, cur_tx, cur_ty, px, py, ex, ey, &etile[i])) vis |= 1u << i;
         }
       }
       const int K = __popc(vis);
@@ -254,8 +251,7 @@ __global__ void __launch_bounds__(kSimThreads, 3) nm_sim_kernel(const SimDev d) 
       for (int i = 0; i < kA; ++i) {
         val[i] = 0.0;
         if (vis & (1u << i)) {
-          const int tx = nm_tile_index_inv(ex[i], d.st, mv.inv), ty = nm_tile_index_inv(ey[i], d.st, mv.inv);
-          const int tile = tx * d.Y + ty;
+          const int tile = etile[i];
           double acc = 0.0;
           for (int ci = 0; ci < a.n_components; ++ci) {
             if (!a.component_active[ci]) continue;  // inactive: contributes integer 0 (:283-285)
@@ -344,13 +340,8 @@ __global__ void __launch_bounds__(kSimThreads, 3) nm_sim_kernel(const SimDev d) 
             ++seen;
           }
       }
-      double nx = 0.0, ny = 0.0;
-#pragma unroll
-      for (int i = 0; i < kA; ++i)
-        if (i == act_idx) {
-          nx = ex[i];
-          ny = ey[i];
-        }
+      double nx, ny;  // the chosen endpoint, recomputed (same operations, same bits)
+      nm_pose_endpoint(c, s, px, py, d.act[act_idx][0], d.act[act_idx][1], &nx, &ny);
       // -- moving flag                                                        :101-107
       moving = (prevx == nx) && (prevy == ny);
       prevx = nx;
@@ -361,7 +352,7 @@ __global__ void __launch_bounds__(kSimThreads, 3) nm_sim_kernel(const SimDev d) 
         px = nx;
         py = ny;
       }
-      const int ntx = nm_tile_index_inv(px, d.st, mv.inv), nty = nm_tile_index_inv(py, d.st, mv.inv);
+      const int ntx = geo.tile(px), nty = geo.tile(py);
       if (ntx != cur_tx || nty != cur_ty) count_moving += 1;  // motion_analysis, metrics.py:437-440
       cur_tx = ntx;
       cur_ty = nty;
@@ -427,17 +418,19 @@ __global__ void __launch_bounds__(kSimThreads, 3) nm_sim_kernel(const SimDev d) 
 __global__ void __launch_bounds__(256) nm_segments_kernel(const uint8_t *__restrict__ g_tiles, int X, int Y, double st,
                                                           const double *__restrict__ seg, int64_t n,
                                                           uint8_t *__restrict__ out) {
-  extern __shared__ unsigned char sm_tiles[];
-  for (int i = threadIdx.x; i < X * Y; i += blockDim.x) sm_tiles[i] = g_tiles[i];
+  // the simulation kernel's geometry (tabulated grid lines, branch-free walk) on caller-supplied segments
+  extern __shared__ __align__(16) unsigned char sm_geo[];
+  NmSimGeom geo;
+  geo.build(sm_geo, g_tiles, X, Y, st);
   __syncthreads();
-  NmMazeView mv;
-  mv.tiles = sm_tiles;
-  mv.X = X;
-  mv.Y = Y;
-  mv.st = st;
-  mv.inv = 1.0 / st;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    out[i] = nm_move_possible(mv, seg[4 * i], seg[4 * i + 1], seg[4 * i + 2], seg[4 * i + 3]) ? 1 : 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double x1 = seg[4 * i], y1 = seg[4 * i + 1], x2 = seg[4 * i + 2], y2 = seg[4 * i + 3];
+    const int tx = geo.tile(x1), ty = geo.tile(y1);
+    const bool s_in = (unsigned)tx < (unsigned)X && (unsigned)ty < (unsigned)Y;
+    const bool start_ok = s_in && geo.tiles[s_in ? tx * Y + ty : 0] != 0;
+    int et;
+    out[i] = geo.move_ok(start_ok, tx, ty, x1, y1, x2, y2, &et) ? 1 : 0;
+  }
 }
 
 }  // namespace
@@ -478,8 +471,9 @@ extern "C" int nm_simulate(const nm_maze *mz, const nm_sim_args *args, void *str
   }
   const int nT = mz->X * mz->Y;
   int threads = kSimThreads;
-  while (threads > 32 && (size_t)nT * threads * 4 + nT > 200 * 1024) threads /= 2;
-  const size_t smem = (size_t)nT * threads * sizeof(uint32_t) + 128 + (size_t)nT;  // visit map | 2^(j/16) table | tiles
+  const size_t geo_bytes = NmSimGeom::smem_bytes(mz->X, mz->Y);
+  while (threads > 32 && (size_t)nT * threads * 4 + 128 + geo_bytes > 200 * 1024) threads /= 2;
+  const size_t smem = (size_t)nT * threads * sizeof(uint32_t) + 128 + geo_bytes;  // visit map | 2^(j/16) | geometry
   NM_CHECK_ARG(smem <= 227 * 1024, "nm_simulate: maze of %d tiles does not fit the shared-memory visit map", nT);
   cudaError_t e = cudaFuncSetAttribute(nm_sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -499,9 +493,13 @@ extern "C" int nm_maze_movements_possible_device(const nm_maze *mz, const double
   if (cudaSetDevice(mz->device) != cudaSuccess) return nm_fail(NM_ERR_CUDA, "cudaSetDevice(%d) failed", mz->device);
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  nm_segments_kernel<<<blocks, 256, (size_t)mz->X * mz->Y, (cudaStream_t)stream>>>(mz->d_tiles, mz->X, mz->Y,
-                                                                                  mz->size_tile, d_segments, n, d_out);
-  cudaError_t e = cudaGetLastError();
+  const size_t geo_bytes = NmSimGeom::smem_bytes(mz->X, mz->Y);
+  NM_CHECK_ARG(geo_bytes <= 200 * 1024, "nm_maze_movements_possible_device: maze too large for shared memory");
+  cudaError_t e = cudaFuncSetAttribute(nm_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo_bytes);
+  if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  nm_segments_kernel<<<blocks, 256, geo_bytes, (cudaStream_t)stream>>>(mz->d_tiles, mz->X, mz->Y, mz->size_tile,
+                                                                       d_segments, n, d_out);
+  e = cudaGetLastError();
   if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_segments_kernel launch: %s", cudaGetErrorString(e));
   return NM_OK;
 }

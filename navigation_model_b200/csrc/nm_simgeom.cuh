@@ -1,0 +1,138 @@
+// Device-only fast path of Maze.is_movement_possible_cont (simulation/maze.py:563-611) for the simulation kernel.
+//
+// Same decisions as nm_geometry.h::nm_move_possible (which restates the reference operation for operation), with the
+// parameter-independent parts of the ray / AABB walk tabulated once per CTA and the rest made branch-free, so that
+// the 32 mice of a warp stay converged:
+//
+//   * the walk visits the vertical lines x = fl((dx+1)*st), dx in [tile(x1), tile(x2)), and tests the two tiles
+//     cont2disc(x - st, y) and cont2disc(x, y) (maze.py:588-595).  Their x indices depend on dx only, so
+//         crossx[dx][ty] = visitable(tile(fl(x - st)), ty) && visitable(tile(x), ty)
+//     is a table of X*Y bytes built with the exact floor division of nm_geometry.h; `gl[dx]` holds x itself.
+//     Horizontal lines: crossy[dy][tx] likewise (maze.py:602-610);
+//   * what remains per crossing is y = m*(x - x1) + y1 (the reference's operations, no FMA) and ONE tile index;
+//   * m = (y2-y1)/(x2-x1) does not depend on the swap that orders the end points (maze.py:583-586, 598-601):
+//     IEEE subtraction and division are sign-symmetric, (-a)/(-b) == a/b bit for bit;
+//   * both end points are inside the maze whenever the walk runs, so dx in [0, X-2] and the tables never overflow;
+//     lanes whose move is already refused run the same instructions on index 0 and discard the result.
+//
+// tile index: Python's `x // st` is the floor of the exact quotient.  n = rint(x * fl(1/st)) (one FMA against the
+// 1.5*2^52 constant, low word = n) is floor or floor+1 for |x/st| < 2^31; the residual x - n*st, rounded once by an
+// FMA, keeps its sign, and is negative exactly when n = floor+1.  No FRND / F2I (quarter-rate XU ops) needed.
+#ifndef NM_SIMGEOM_CUH
+#define NM_SIMGEOM_CUH
+
+#include "nm_geometry.h"
+
+struct NmSimGeom {
+  const uint8_t *tiles;   // [X*Y] shared memory
+  const uint8_t *crossx;  // [X][Y]
+  const uint8_t *crossy;  // [Y][X]
+  const double *gl;       // [max(X,Y)]  fl((i+1)*st)
+  int X, Y;
+  double st, inv;
+
+  static __host__ __device__ size_t smem_bytes(int X, int Y) {
+    const int m = X > Y ? X : Y;
+    return (size_t)m * sizeof(double) + 3 * (((size_t)X * Y + 15) & ~(size_t)15);
+  }
+
+  // `base` 8-byte aligned, smem_bytes(X, Y) long; every thread of the CTA calls build(), then __syncthreads().
+  __device__ __forceinline__ void attach(unsigned char *base, int X_, int Y_, double st_) {
+    X = X_; Y = Y_; st = st_; inv = 1.0 / st_;
+    const int m = X > Y ? X : Y;
+    const size_t slab = ((size_t)X * Y + 15) & ~(size_t)15;
+    gl = reinterpret_cast<const double *>(base);
+    tiles = base + (size_t)m * sizeof(double);
+    crossx = tiles + slab;
+    crossy = crossx + slab;
+  }
+
+  static __device__ __noinline__ void fill(unsigned char *base, const uint8_t *g_tiles, int X, int Y, double st) {
+    const double inv = 1.0 / st;
+    const int nT = X * Y, m = X > Y ? X : Y;
+    const size_t slab = ((size_t)nT + 15) & ~(size_t)15;
+    double *gl_w = reinterpret_cast<double *>(base);
+    uint8_t *t_w = base + (size_t)m * sizeof(double), *cx_w = t_w + slab, *cy_w = cx_w + slab;
+    NmMazeView mv;
+    mv.tiles = g_tiles; mv.X = X; mv.Y = Y; mv.st = st; mv.inv = inv;
+#pragma unroll 1
+    for (int i = threadIdx.x; i < m; i += blockDim.x) gl_w[i] = (double)(i + 1) * st;
+#pragma unroll 1
+    for (int i = threadIdx.x; i < nT; i += blockDim.x) {
+      t_w[i] = g_tiles[i];
+      {  // crossx[dx][ty]
+        const int dx = i / Y, ty = i - dx * Y;
+        const double gx = (double)(dx + 1) * st;
+        const int ta = nm_tile_index_inv(gx - st, st, inv), tb = nm_tile_index_inv(gx, st, inv);
+        cx_w[i] = (nm_tile_visitable(mv, ta, ty) && nm_tile_visitable(mv, tb, ty)) ? 1 : 0;
+      }
+      {  // crossy[dy][tx]
+        const int dy = i / X, tx = i - dy * X;
+        const double gy = (double)(dy + 1) * st;
+        const int ta = nm_tile_index_inv(gy - st, st, inv), tb = nm_tile_index_inv(gy, st, inv);
+        cy_w[i] = (nm_tile_visitable(mv, tx, ta) && nm_tile_visitable(mv, tx, tb)) ? 1 : 0;
+      }
+    }
+  }
+
+  __device__ __forceinline__ void build(unsigned char *base, const uint8_t *g_tiles, int X_, int Y_, double st_) {
+    attach(base, X_, Y_, st_);
+    fill(base, g_tiles, X_, Y_, st_);
+  }
+
+  __device__ __forceinline__ int tile(double x) const {
+    const double kMagic = 6755399441055744.0;  // 1.5 * 2^52
+    const double t = fma(x, inv, kMagic);
+    const int n = __double2loint(t);
+    const double res = fma(-__dsub_rn(t, kMagic), st, x);
+    return res < 0.0 ? n - 1 : n;
+  }
+
+  // one pass of the walk: lines crossed between the start tile index s_t and the end tile index e_t along the axis
+  // whose coordinates are (pa, ea); (pb, eb) are the coordinates along the other axis.
+  __device__ __forceinline__ bool pass(bool ok, double pa, double pb, double ea, double eb, int s_t, int e_t,
+                                       const uint8_t *cross, int n_other) const {
+    const bool sw = pa > ea;                       // order the end points along this axis
+    const double a1 = sw ? ea : pa, b1 = sw ? eb : pb;
+    const int lo = sw ? e_t : s_t, hi = sw ? s_t : e_t;
+    const int n = ok ? hi - lo : 0;                // equal coordinates give equal tiles: the pass is skipped
+    const double den = __dsub_rn(ea, pa);
+    const double m = __ddiv_rn(__dsub_rn(eb, pb), den != 0.0 ? den : 1.0);
+    bool good = true;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {                  // the first two crossings, predicated
+      const bool on = n > c;
+      const int d = on ? lo + c : 0;
+      const double g = gl[d];
+      const double o = __dadd_rn(__dmul_rn(m, __dsub_rn(g, a1)), b1);
+      const int t = tile(o);
+      const bool in = (unsigned)t < (unsigned)n_other;
+      const uint8_t f = cross[d * n_other + (in ? t : 0)];
+      good = good && (!on || (in && f != 0));
+    }
+#pragma unroll 1
+    for (int c = 2; c < n; ++c) {                  // longer moves (actions of more than two tiles)
+      const int d = lo + c;
+      const double o = __dadd_rn(__dmul_rn(m, __dsub_rn(gl[d], a1)), b1);
+      const int t = tile(o);
+      good = good && (unsigned)t < (unsigned)n_other && cross[d * n_other + t] != 0;
+    }
+    return good;
+  }
+
+  // (px, py) in tile (stx, sty) whose visitability is `start_ok`; end point (ex, ey).  *etile = flat index of the end
+  // tile (0 when outside).
+  __device__ __forceinline__ bool move_ok(bool start_ok, int stx, int sty, double px, double py, double ex, double ey,
+                                          int *etile) const {
+    const int etx = tile(ex), ety = tile(ey);
+    const bool e_in = (unsigned)etx < (unsigned)X && (unsigned)ety < (unsigned)Y;
+    const int et = e_in ? etx * Y + ety : 0;
+    *etile = et;
+    const bool ok = start_ok && e_in && tiles[et] != 0;      // maze.py:578-579
+    const bool gx = pass(ok, px, py, ex, ey, stx, etx, crossx, Y);  // vertical lines   :581-595
+    const bool gy = pass(ok, py, px, ey, ex, sty, ety, crossy, X);  // horizontal lines :597-610
+    return ok && gx && gy;
+  }
+};
+
+#endif  // NM_SIMGEOM_CUH
