@@ -49,7 +49,8 @@ def build_native(force=False, verbose=False):
     """Compile every CUDA / C++ source of the package into ``libnavmodel_b200.so``."""
     if not force and not needs_rebuild():
         return LIB_PATH
-    cmd = [find_nvcc()] + NVCC_FLAGS + ["-x", "cu"] + sources() + ["-o", LIB_PATH + ".tmp"]
+    extra = os.environ.get("NM_NVCC_EXTRA", "").split()  # tuning experiments, e.g. -DNM_SIM_MIN_CTAS=4
+    cmd = [find_nvcc()] + NVCC_FLAGS + extra + ["-x", "cu"] + sources() + ["-o", LIB_PATH + ".tmp"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr
     with open(os.path.join(HERE, "build.log"), "w") as fh:

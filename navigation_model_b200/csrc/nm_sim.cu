@@ -32,6 +32,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 
 constexpr int kA = NM_MAX_CAND;
 constexpr int kSimThreads = 128;
+#ifndef NM_SIM_MIN_CTAS
+#define NM_SIM_MIN_CTAS 4  // resident CTAs per SM the register allocation is capped for
+#endif
 
 struct SimDev {
   nm_sim_args a;  // device-visible copy (host pointers inside are not dereferenced on the device)
@@ -84,16 +87,21 @@ struct Pcg64 {
   }
 };
 
-__global__ void __launch_bounds__(kSimThreads, 3) nm_sim_kernel(const SimDev d) {
+__global__ void __launch_bounds__(kSimThreads, NM_SIM_MIN_CTAS) nm_sim_kernel(const SimDev d) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nT = d.X * d.Y;
   uint32_t *count = reinterpret_cast<uint32_t *>(smem_raw);                 // [nT][blockDim.x]
   double *exp_tab = reinterpret_cast<double *>(smem_raw + (size_t)nT * blockDim.x * sizeof(uint32_t));  // [16]
   const int tid = threadIdx.x, nt = blockDim.x;
   if (tid < 16) exp_tab[tid] = c_exp2tab[tid];
+  double *anx_sm = exp_tab + 16;                       // [5][nt]  anxiety value * weight by tile code, per mouse
+  double *bcw_sm = anx_sm + 5 * (size_t)blockDim.x;    // [kA][nt] biomechanical cost * weight by action, per mouse
+  double *vt_sm = bcw_sm + kA * (size_t)blockDim.x;    // [nT]     the shared normalised value table
   NmSimGeom geo;  // tile table, grid-line tables (nm_simgeom.cuh)
-  geo.build(reinterpret_cast<unsigned char *>(exp_tab + 16), d.tiles, d.X, d.Y, d.st);
+  geo.build(reinterpret_cast<unsigned char *>(vt_sm + nT), d.tiles, d.X, d.Y, d.st);
   const uint8_t *tiles = geo.tiles;
+  if (d.a.d_vtable && !d.a.vtable_per_mouse)
+    for (int i = tid; i < nT; i += nt) vt_sm[i] = d.a.d_vtable[i];
   for (int i = 0; i < nT; ++i) count[i * nt + tid] = 0u;
   __syncthreads();
 
@@ -114,23 +122,24 @@ __global__ void __launch_bounds__(kSimThreads, 3) nm_sim_kernel(const SimDev d) 
     double prevx = a.d_init_prev[2 * n], prevy = a.d_init_prev[2 * n + 1];
     bool moving = false;  // BehaviouralModel._moving (True when the last choice was to STAY)
     const double beta = a.d_beta[n];
-    double anx_w = 0, anx_tab[5] = {-1.0, 0, 0, 0, 0};
+    // value * weight is the same product at every step (Component.weighted_values, behavioural_components.py:277-285):
+    // it is formed once here and looked up afterwards.
+    double *anx_t = anx_sm + tid, *bcw_t = bcw_sm + tid;
     if (a.d_anxiety) {
       const double *q = a.d_anxiety + 5 * n;
-      anx_w = q[0];
-      anx_tab[2] = q[1];                 // CORNER: p1                    behavioural_components.py:364
-      anx_tab[1] = q[2] * q[1];          // WALL:   p2 * p1
-      anx_tab[3] = q[3] * q[2] * q[1];   // CENTRE: p3 * p2 * p1
-      anx_tab[4] = q[4];                 // DECISION_POINT: p4            :332-333
+      const double w = q[0];
+      anx_t[0 * nt] = -1.0 * w;                  // VOID
+      anx_t[2 * nt] = q[1] * w;                  // CORNER: p1                    behavioural_components.py:364
+      anx_t[1 * nt] = (q[2] * q[1]) * w;         // WALL:   p2 * p1
+      anx_t[3 * nt] = (q[3] * q[2] * q[1]) * w;  // CENTRE: p3 * p2 * p1
+      anx_t[4 * nt] = q[4] * w;                  // DECISION_POINT: p4            :332-333
     }
-    double bc_w = 0, bc_tab[kA];
-#pragma unroll
-    for (int i = 0; i < kA; ++i) bc_tab[i] = 0.0;
+    double bc_zero = 0.0;  // 0.0 * W_bcost: the component's contribution when the mouse has just moved (:410-413)
     if (a.d_bcost_table) {
-      bc_w = a.d_bcost_weight[n];
+      const double w = a.d_bcost_weight[n];
+      bc_zero = 0.0 * w;
 #pragma unroll
-      for (int i = 0; i < kA; ++i)
-        if (i < A) bc_tab[i] = a.d_bcost_table[n * A + i];
+      for (int i = 0; i < kA; ++i) bcw_t[i * nt] = i < A ? a.d_bcost_table[n * A + i] * w : 0.0;
     }
     double ex_w = 0, xi = 0, k_home = 0, k_explo = 0, th_explo = 0, th_home = 0, fam = 0.0;
     bool home = false;  // ExperienceComponent.State.EXPLO at start (:440)
@@ -138,16 +147,18 @@ __global__ void __launch_bounds__(kSimThreads, 3) nm_sim_kernel(const SimDev d) 
       const double *q = a.d_experience + 6 * n;
       ex_w = q[0]; xi = q[1]; k_home = q[2]; k_explo = q[3]; th_explo = q[4]; th_home = q[5];
     }
-    double bp_w = 0, bp = 0, bp_wm = 0, bp_wnm = 0;
+    double bpw_plain = 0, bpw_m = 0, bpw_nm = 0;  // bp * W, (Wm*bp) * W, (Wnm*bp) * W   (:502-513)
     if (a.d_bpersistence) {
       const double *q = a.d_bpersistence + 4 * n;
-      bp_w = q[0]; bp = q[1]; bp_wm = q[2] * q[1]; bp_wnm = q[3] * q[1];  // Wm*bp, Wnm*bp  (:502-506)
+      bpw_plain = q[1] * q[0];
+      bpw_m = (q[2] * q[1]) * q[0];
+      bpw_nm = (q[3] * q[1]) * q[0];
     }
     double vt_w = 0;
     const double *vt = nullptr;
     if (a.d_vtable) {
       vt_w = a.d_vtable_weight[n];
-      vt = a.vtable_per_mouse ? a.d_vtable + n * nT : a.d_vtable;
+      vt = a.vtable_per_mouse ? a.d_vtable + n * nT : vt_sm;
     }
     Pcg64 rng;
     rng.state = 0;
@@ -185,7 +196,6 @@ __global__ void __launch_bounds__(kSimThreads, 3) nm_sim_kernel(const SimDev d) 
 
     // ---- fused metrics over the history positions (history[0] = initial position, mouse.cpp:58-61) ----
     int n_visited = 0, it_visit = T + 1, count_moving = 0;
-    int tile_counts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int cur_tx = geo.tile(px), cur_ty = geo.tile(py);
     auto record_position = [&](int t_idx, int tx, int ty, bool inside) {
       // occupancy_map / tile_analysis / it_perc_visited_maze on history entry t_idx
@@ -193,7 +203,6 @@ __global__ void __launch_bounds__(kSimThreads, 3) nm_sim_kernel(const SimDev d) 
       const int tile = tx * d.Y + ty;
       const uint32_t c = cnt[tile * nt];
       cnt[tile * nt] = c + 1u;
-      tile_counts[tiles[tile] & 7] += 1;
       if (c == 0u) {
         n_visited += 1;
         // perc = n_visited * 100 / number_visitable_tiles >= percentage      metrics.py:711-721
@@ -245,45 +254,62 @@ __global__ void __launch_bounds__(kSimThreads, 3) nm_sim_kernel(const SimDev d) 
       // -- val_fin = beta * sum_c weighted_values_c                           :84-87
       // (candidates stay in action order: the reference's list is the action list filtered by
       //  reachability, so "k-th candidate" == "k-th reachable action" and nothing needs compacting)
+      // Components outermost (one uniform dispatch per component and step), the eight endpoints innermost and
+      // unrolled; every endpoint is evaluated (an unreachable one reads the tile it would land on, or tile 0) and the
+      // reachable ones are selected afterwards, so the warp stays converged.  Per endpoint the sum still runs over the
+      // components in model order starting from 0.0 (:84-86).
       double val[kA];
+#pragma unroll
+      for (int i = 0; i < kA; ++i) val[i] = 0.0;
+#pragma unroll 1
+      for (int ci = 0; ci < a.n_components; ++ci) {
+        if (!a.component_active[ci]) continue;  // inactive: contributes integer 0 (:283-285)
+        switch (a.component_kind[ci]) {
+          case NM_COMP_ANXIETY:
+#pragma unroll
+            for (int i = 0; i < kA; ++i)
+              if (i < A) {
+                const int code = tiles[etile[i]];
+                val[i] = val[i] + anx_t[(code > 4 ? 0 : code) * nt];
+              }
+            break;
+          case NM_COMP_BCOST:  // cached[is_visitable] if moving else zeros   :410-413
+#pragma unroll
+            for (int i = 0; i < kA; ++i)
+              if (i < A) val[i] = val[i] + (moving ? bcw_t[i * nt] : bc_zero);
+            break;
+          case NM_COMP_EXPERIENCE: {  // :473-479
+            const double kk = home ? -k_home : -k_explo;
+#pragma unroll
+            for (int i = 0; i < kA; ++i)
+              if (i < A) {
+                // (double)count by the 2^52 trick: exact for a u32, and no I2F on the quarter-rate pipe
+                const double cn = __hiloint2double(0x43300000, (int)cnt[etile[i] * nt]) - 4503599627370496.0;
+                const double ee = er.exp_nonpos(kk * cn);
+                val[i] = val[i] + (home ? 1.0 - ee : ee) * ex_w;
+              }
+            break;
+          }
+          case NM_COMP_BPERSISTENCE:  // :508-513
+#pragma unroll
+            for (int i = 0; i < kA; ++i)
+              if (i < A)
+                val[i] = val[i] + (moving ? (d.zero_act[i] ? bpw_m : bpw_plain) : (d.zero_act[i] ? bpw_plain : bpw_nm));
+            break;
+          case NM_COMP_VTABLE:  // :537-541
+#pragma unroll
+            for (int i = 0; i < kA; ++i)
+              if (i < A) val[i] = val[i] + vt[etile[i]] * vt_w;
+            break;
+          default:
+            break;
+        }
+      }
       double vmax = -INFINITY;
 #pragma unroll
       for (int i = 0; i < kA; ++i) {
-        val[i] = 0.0;
-        if (vis & (1u << i)) {
-          const int tile = etile[i];
-          double acc = 0.0;
-          for (int ci = 0; ci < a.n_components; ++ci) {
-            if (!a.component_active[ci]) continue;  // inactive: contributes integer 0 (:283-285)
-            double v;
-            switch (a.component_kind[ci]) {
-              case NM_COMP_ANXIETY:
-                v = anx_tab[tiles[tile] > 4 ? 0 : tiles[tile]] * anx_w;
-                break;
-              case NM_COMP_BCOST:  // cached[is_visitable] if moving else zeros   :410-413
-                v = (moving ? bc_tab[i] : 0.0) * bc_w;
-                break;
-              case NM_COMP_EXPERIENCE: {  // :473-479
-                const double cn = (double)cnt[tile * nt];
-                v = home ? (1.0 - er.exp_nonpos(-k_home * cn)) : er.exp_nonpos(-k_explo * cn);
-                v = v * ex_w;
-                break;
-              }
-              case NM_COMP_BPERSISTENCE:  // :508-513
-                v = (moving ? (d.zero_act[i] ? bp_wm : bp) : (d.zero_act[i] ? bp : bp_wnm)) * bp_w;
-                break;
-              case NM_COMP_VTABLE:  // :537-541
-                v = vt[tile] * vt_w;
-                break;
-              default:
-                v = 0.0;
-            }
-            acc = acc + v;
-          }
-          acc = beta * acc;
-          val[i] = acc;
-          vmax = fmax(vmax, acc);
-        }
+        val[i] = beta * val[i];
+        if (vis & (1u << i)) vmax = fmax(vmax, val[i]);
       }
       // -- softmax + numpy Generator.choice                                   :92-98
       double e[kA];
@@ -382,9 +408,14 @@ __global__ void __launch_bounds__(kSimThreads, 3) nm_sim_kernel(const SimDev d) 
     }
     if (a.d_it_visit) a.d_it_visit[n] = it_visit;
     if (a.d_count_moving) a.d_count_moving[n] = count_moving;
-    if (a.d_tile_counts) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) a.d_tile_counts[8 * n + i] = tile_counts[i];
+    if (a.d_tile_counts) {  // tile_analysis counts = the visit map summed by tile code (metrics.py:219-248)
+#pragma unroll 1
+      for (int code = 0; code < 8; ++code) {
+        int acc = 0;
+        for (int tile = 0; tile < nT; ++tile)
+          if ((tiles[tile] & 7) == code) acc += (int)cnt[tile * nt];
+        a.d_tile_counts[8 * n + code] = acc;
+      }
     }
     if (a.d_status) a.d_status[n] = status;
     if (a.d_model_state) {
@@ -472,8 +503,13 @@ extern "C" int nm_simulate(const nm_maze *mz, const nm_sim_args *args, void *str
   const int nT = mz->X * mz->Y;
   int threads = kSimThreads;
   const size_t geo_bytes = NmSimGeom::smem_bytes(mz->X, mz->Y);
-  while (threads > 32 && (size_t)nT * threads * 4 + 128 + geo_bytes > 200 * 1024) threads /= 2;
-  const size_t smem = (size_t)nT * threads * sizeof(uint32_t) + 128 + geo_bytes;  // visit map | 2^(j/16) | geometry
+  // visit map | 2^(j/16) | per-mouse anxiety and biomechanical-cost tables | shared value table | geometry
+  auto smem_for = [&](int th) {
+    return (size_t)nT * th * sizeof(uint32_t) + 128 + (size_t)(5 + kA) * th * sizeof(double) + (size_t)nT * sizeof(double) +
+           geo_bytes;
+  };
+  while (threads > 32 && smem_for(threads) > 200 * 1024) threads /= 2;
+  const size_t smem = smem_for(threads);
   NM_CHECK_ARG(smem <= 227 * 1024, "nm_simulate: maze of %d tiles does not fit the shared-memory visit map", nT);
   cudaError_t e = cudaFuncSetAttribute(nm_sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
