@@ -87,16 +87,22 @@ struct Pcg64 {
   }
 };
 
-__global__ void __launch_bounds__(kSimThreads, NM_SIM_MIN_CTAS) nm_sim_kernel(const SimDev d) {
+// NT = threads per CTA (compile-time: every per-mouse table is indexed [row][thread], so row strides and the
+// fixed-size tables' offsets become immediates).
+template <int NT>
+__global__ void __launch_bounds__(NT, (NM_SIM_MIN_CTAS * kSimThreads) / NT) nm_sim_kernel(const SimDev d) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nT = d.X * d.Y;
-  uint32_t *count = reinterpret_cast<uint32_t *>(smem_raw);                 // [nT][blockDim.x]
-  double *exp_tab = reinterpret_cast<double *>(smem_raw + (size_t)nT * blockDim.x * sizeof(uint32_t));  // [16]
-  const int tid = threadIdx.x, nt = blockDim.x;
+  constexpr int nt = NT;
+  const int tid = threadIdx.x;
+  // 2^(j/16) | anxiety value*weight by tile code [5][nt] | biomechanical cost*weight by action [kA][nt] |
+  // visit map [nT][nt] u32 | shared normalised value table [nT] | geometry tables
+  double *exp_tab = reinterpret_cast<double *>(smem_raw);
+  double *anx_sm = exp_tab + 16;
+  double *bcw_sm = anx_sm + 5 * nt;
+  uint32_t *count = reinterpret_cast<uint32_t *>(bcw_sm + kA * nt);
+  double *vt_sm = reinterpret_cast<double *>(count + (size_t)nT * nt);
   if (tid < 16) exp_tab[tid] = c_exp2tab[tid];
-  double *anx_sm = exp_tab + 16;                       // [5][nt]  anxiety value * weight by tile code, per mouse
-  double *bcw_sm = anx_sm + 5 * (size_t)blockDim.x;    // [kA][nt] biomechanical cost * weight by action, per mouse
-  double *vt_sm = bcw_sm + kA * (size_t)blockDim.x;    // [nT]     the shared normalised value table
   NmSimGeom geo;  // tile table, grid-line tables (nm_simgeom.cuh)
   geo.build(reinterpret_cast<unsigned char *>(vt_sm + nT), d.tiles, d.X, d.Y, d.st);
   const uint8_t *tiles = geo.tiles;
@@ -232,9 +238,16 @@ __global__ void __launch_bounds__(kSimThreads, NM_SIM_MIN_CTAS) nm_sim_kernel(co
       for (int i = 0; i < kA; ++i) {
         etile[i] = 0;
         if (i < A) {
-          double ex, ey;
-          nm_pose_endpoint(c, s, px, py, d.act[i][0], d.act[i][1], &ex, &ey);
-          if (geo.move_ok(start_ok, cur_tx, cur_ty, px, py, ex, ey, &etile[i])) vis |= 1u << i;
+          if (d.act[i][0] == 0.0 && d.act[i][1] == 0.0) {
+            // null displacement (uniform over the CTA): the endpoint IS the position, R(ori)*0 + p == p bit for bit,
+            // and no grid line is crossed -- reachable iff the tile under the mouse is visitable
+            etile[i] = cur_inside ? cur_tx * d.Y + cur_ty : 0;
+            if (start_ok) vis |= 1u << i;
+          } else {
+            double ex, ey;
+            nm_pose_endpoint(c, s, px, py, d.act[i][0], d.act[i][1], &ex, &ey);
+            if (geo.move_ok(start_ok, cur_tx, cur_ty, px, py, ex, ey, &etile[i])) vis |= 1u << i;
+          }
         }
       }
       const int K = __popc(vis);
@@ -503,19 +516,20 @@ extern "C" int nm_simulate(const nm_maze *mz, const nm_sim_args *args, void *str
   const int nT = mz->X * mz->Y;
   int threads = kSimThreads;
   const size_t geo_bytes = NmSimGeom::smem_bytes(mz->X, mz->Y);
-  // visit map | 2^(j/16) | per-mouse anxiety and biomechanical-cost tables | shared value table | geometry
+  // 2^(j/16) | per-mouse anxiety and biomechanical-cost tables | visit map | shared value table | geometry
   auto smem_for = [&](int th) {
-    return (size_t)nT * th * sizeof(uint32_t) + 128 + (size_t)(5 + kA) * th * sizeof(double) + (size_t)nT * sizeof(double) +
+    return 128 + (size_t)(5 + kA) * th * sizeof(double) + (size_t)nT * th * sizeof(uint32_t) + (size_t)nT * sizeof(double) +
            geo_bytes;
   };
   while (threads > 32 && smem_for(threads) > 200 * 1024) threads /= 2;
   const size_t smem = smem_for(threads);
   NM_CHECK_ARG(smem <= 227 * 1024, "nm_simulate: maze of %d tiles does not fit the shared-memory visit map", nT);
-  cudaError_t e = cudaFuncSetAttribute(nm_sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   const int64_t blocks = (a.n_mice + threads - 1) / threads;
   NM_CHECK_ARG(blocks <= 2147483647LL, "nm_simulate: too many mice for one launch");
-  nm_sim_kernel<<<(unsigned)blocks, threads, smem, (cudaStream_t)stream>>>(d);
+  void (*kern)(const SimDev) = threads == 128 ? nm_sim_kernel<128> : threads == 64 ? nm_sim_kernel<64> : nm_sim_kernel<32>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  kern<<<(unsigned)blocks, threads, smem, (cudaStream_t)stream>>>(d);
   e = cudaGetLastError();
   if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_sim_kernel launch: %s", cudaGetErrorString(e));
   return NM_OK;

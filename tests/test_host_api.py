@@ -177,6 +177,13 @@ def test_component_known_answers():
     npt.assert_allclose(bcost.values, np.zeros(3))
     assert np.array_equal(bc.bcost_tables(acts, [0.5, 1.5], [2.0, 0.3])[0], bcost._cachedval)
     assert np.array_equal(bc.bcost_tables(O.A8_UNITS, 1.7, 0.4)[0], O.bcost_table(O.A8_UNITS, 1.7, 0.4))
+    # the vectorised table is scipy's vonmises.pdf bit for bit (the reference calls vonmises(k).pdf, :395-399)
+    ks = np.concatenate([np.random.default_rng(3).uniform(0, 60, 500), [0.0, 1e-12, 700.0]])
+    ang = np.arctan2(O.A8_UNITS[:, 1], O.A8_UNITS[:, 0])
+    want = vonmises.pdf(ang[None, :], ks[:, None])
+    want[:, 0] = 0.0            # the null action
+    want[:, 2] *= 0.25          # (2, 0) is two tiles long: times gamma
+    assert np.array_equal(bc.bcost_tables(O.A8_UNITS, ks, np.full(len(ks), 0.25)), want)
 
     exp = bc.ExperienceComponent((7, 7), W_exp=0.7, theta_home=30, theta_explo=80, kappa_home=5.0, kappa_explo=2.0,
                                  xi=0.006)
