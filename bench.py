@@ -203,6 +203,86 @@ def workload_config(args, n_gpus, p_per_rank):
             "l2": "flushed between timed steps (256 MiB memset, untimed)"}
 
 
+def other_paths(local, world, rank, dist, dev):
+    """The two other kernels of the hot path, measured the same way (per-rank shard of fixed size, device time as the
+    max over ranks): forward simulation (BASELINE configs[4] shape, scaled to 262 144 mice x 1 000 steps per GPU, all
+    five components, device-seeded PCG64 streams, fused metrics) and the model-based agent (configs[3] shape: 400-state
+    maze, 8 actions, 20 000 parameter sets x 1 000 steps per GPU, one value-iteration sweep per step).  Reported under
+    ``also_measured``; the headline metric stays the fitness grid sweep."""
+    import torch
+    from navigation_model_b200.batched_sim import BatchedExperiment
+    from navigation_model_b200.simulation import behavioural_components as bc
+    from navigation_model_b200.simulation.maze import Maze
+    from navigation_model_b200.sweep import ModelBasedSweep
+    from oracle import np_oracle as O  # maze layout / seeded session recipe only (inputs)
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    out = {}
+    # ---- forward simulation -----------------------------------------------------------------------------
+    maze = Maze(O.M9_LAYOUT, O.M9_SUBAREAS, size_tile=O.M9_SIZE_TILE)
+    rng = np.random.default_rng(1000 + rank)
+    N, T = 262144, 1000
+    u = rng.uniform
+    P = {"beta": u(0.5, 6, N), "W_anx": u(0, 10, N), "p1": u(0, 1, N), "p2": u(0, 1, N), "p3": u(0, 1, N),
+         "W_bcost": u(0, 10, N), "k": u(0.05, 4, N), "gamma": u(0.2, 2, N), "W_exp": u(0, 10, N),
+         "xi": u(0.006, 0.6, N), "kappa_home": u(0.01, 5, N), "kappa_explo": u(0.01, 5, N),
+         "theta_explo": u(80, 120, N), "theta_home": u(30, 70, N), "W_bper": u(0, 10, N), "bp": u(0, 1, N),
+         "Wm": u(0, 2, N), "Wnm": u(0, 2, N), "W_values": u(0, 10, N)}
+    exp = BatchedExperiment(maze, O.A8_UNITS * O.M9_SIZE_TILE, O.A8_UNITS,
+                            [bc.AnxietyComponent, bc.BiomechanicalCostComponent, bc.ExperienceComponent,
+                             bc.BiomechPersistenceComponent, bc.ValueTableComponent], v_table=rng.random((9, 9)),
+                            device=local)
+    pos0 = np.array(maze.get_tile_centre(1, 1)) + rng.uniform(-0.03, 0.03, (N, 2))
+    ori0 = rng.uniform(-3, 3, N)
+    k_ms, e2e_s = [], []
+    for rep in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = exp.run(P, T, pos0, ori0, init_disc=(1, 1), device_seed=77 + rep, n_mice=N, occupancy_total=True,
+                      shock_zone={"tile_lines": 5}, corridors=(1, 7), static_intervals=True, subareas=True,
+                      orientation_histogram={})
+        e2e_s.append(time.perf_counter() - t0)
+        k_ms.append(exp.last_kernel_ms)
+    k = max_over_ranks(min(k_ms[1:])) * 1e-3
+    e = max_over_ranks(min(e2e_s[1:]))
+    out["forward_simulation"] = {
+        "metric": "agent-steps/s", "value": world * N * T / k, "e2e_value": world * N * T / e, "kernel_ms": k * 1e3,
+        "workload": f"{N} mice x {T} steps per GPU, 9x9 maze, 8 actions, 5 components, device-seeded PCG64, fused "
+                    "occupancy / exploration / orientation / shock-zone metrics; e2e includes host parameter "
+                    "preparation, H2D and D2H of every per-mouse result",
+        "mice_ok": int((res.status == 0).sum())}
+    # ---- model-based agent ------------------------------------------------------------------------------
+    acts = [(dx, dy) for dx in (-1, 0, 1) for dy in (-1, 0, 1) if (dx, dy) != (0, 0)]
+    layout = "\n".join(["M" * 20] * 20)
+    maze20 = Maze(layout, "", size_tile=0.05)
+    traj, rew = O.synthetic_session(O.OracleMaze(layout, 0.05), 0, 1000, start=(3, 3), goal=(15, 12), jitter=0.02)
+    Pm = 20000
+    a, b, g = rng.uniform(0.01, 1, Pm), np.exp(rng.uniform(np.log(0.1), np.log(30), Pm)), rng.uniform(0.5, 0.99, Pm)
+    mb = ModelBasedSweep(maze20, acts, n_sweeps=1, device=local)
+    mb.add_session(traj, rew)
+    k_ms, e2e_s = [], []
+    for rep in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        mb.log_likelihood(a, b, g)
+        e2e_s.append(time.perf_counter() - t0)
+        k_ms.append(mb.last_kernel_ms)
+    k = max_over_ranks(min(k_ms[1:])) * 1e-3
+    e = max_over_ranks(min(e2e_s[1:]))
+    upd = world * Pm * mb.updates_per_parameter_set
+    out["model_based"] = {
+        "metric": "agent-trial updates/s", "value": upd / k, "e2e_value": upd / e, "kernel_ms": k * 1e3,
+        "state_action_backups_per_s": upd * 400 * 8 / k,
+        "workload": f"{Pm} parameter sets x {mb.updates_per_parameter_set} steps per GPU, 400-state maze, 8 actions, "
+                    "1 value-iteration sweep per step (extension: parity against this repo's numpy oracle only)"}
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -315,6 +395,7 @@ def run_b200(args):
     h2d = int(h2d_stream_bytes + 3 * P * 8)
     d2h = int(P * 8 + 16 * world)
 
+    extras = None if args.no_extras else other_paths(local, world, rank, dist, dev)
     if rank == 0:
         # ---- roofline: FP64 issue; peak measured live with the DFMA probe (burst, kernel timed alone) -------
         sink = torch.zeros(1, dtype=torch.float64, device=dev)
@@ -364,6 +445,9 @@ def run_b200(args):
                         "slowest_step_index": int(np.argmax(e2e_step_ms))},
                 "gpu_launches": 3 * args.steps, "clocks": clocks, "wall_s": wall,
                 "target_updates_per_s_8gpu": 1e10}
+        if extras is not None:
+            line["also_measured"] = extras
+            line["gpu_launches"] += 6
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -378,6 +462,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--alg", default="positive", choices=["positive", "td0", "negative"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-extras", action="store_true", help="skip the forward-simulation / model-based side measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

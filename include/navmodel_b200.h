@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define NM_ABI_VERSION 1
+#define NM_ABI_VERSION 2
 
 /* error codes */
 #define NM_OK 0
@@ -192,6 +192,13 @@ int nm_argmin_nll(const double *d_ll, int S, int64_t P, double *d_nll_out, void 
 #define NM_MAX_COMPONENTS 8
 
 /* All d_ arrays are device pointers; [N] = one entry per mouse.  Unused components: NULL. */
+#define NM_TILE_ZONE_IN 1u    /* tile belongs to the shock zone                                       */
+#define NM_TILE_ZONE_OUT 2u   /* standing here ends a visit of the shock zone                         */
+#define NM_TILE_CORRIDOR_A 4u /* arms(): subarea 1                                                    */
+#define NM_TILE_CORRIDOR_B 8u /* arms(): subarea 7                                                    */
+#define NM_MAX_SUBAREAS 16
+#define NM_MAX_ORI_BINS 16
+
 typedef struct nm_sim_args {
   int64_t n_mice;
   int32_t n_steps;                         /* iterations of StandardExperiment.run (experiment.py:33)      */
@@ -243,6 +250,26 @@ typedef struct nm_sim_args {
                                               fast path for millions of mice, NOT numpy's default_rng seeding   */
   int32_t use_device_seed;
   int32_t reserved1;
+  /* ---- more fused trajectory metrics (analysis/metrics.py; all optional, NULL / 0 = not wanted) ---- */
+  const uint8_t *d_tile_flags;             /* [X*Y] per tile: NM_TILE_ZONE_IN | NM_TILE_ZONE_OUT | NM_TILE_CORRIDOR_A |
+                                              NM_TILE_CORRIDOR_B (host-built from subareas / tile lines)       */
+  int32_t *d_zone_metrics;                 /* [N,4] latency_enter_shock_zone (metrics.py:488-516; n_steps if never),
+                                              positions inside the zone (occupancy_shock_zone :519-534),
+                                              shock_zone_entries (:537-586), corridor switches (arms :735-769) */
+  int32_t *d_static_intervals;             /* [N] not-moving runs of moving_bool_list (hist_time_moving :445-467
+                                              -> compute_static_intervals :621-635)                            */
+  int32_t *d_subarea_counts;               /* [N,NM_MAX_SUBAREAS] positions by subarea index (subareas :470-485);
+                                              the maze must have been uploaded with subareas                   */
+  int32_t n_ori_bins;                      /* > 0: histogram of the turns ori[t+1]-ori[t] over the steps that
+                                              change tile (hist_orientations :306-359), <= NM_MAX_ORI_BINS      */
+  int32_t ori_distance;                    /* hist_orientations(distance=True): turns in bin 2 that jump more
+                                              than 1.5 tiles go to the extra last entry                        */
+  uint32_t ori_tile_filter;                /* != 0: hist_orientations_filtered (:383-422), bit c = tile code c of
+                                              the step's START tile is accepted                                */
+  int32_t reserved2;
+  const double *h_ori_edges;               /* HOST [n_ori_bins+1] the edges numpy.histogram uses               */
+  double ori_min_lim, ori_max_lim;         /* turns outside are shifted by one full turn (:331-334)            */
+  int32_t *d_ori_hist;                     /* [N, n_ori_bins+1]; last entry = the distance=True extra count    */
 } nm_sim_args;
 
 /* StandardExperiment.run(n_steps) for n_mice independent mice on the maze's device. */

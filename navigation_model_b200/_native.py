@@ -64,6 +64,9 @@ SIGNATURES = {
 }
 
 NM_MAX_COMPONENTS = 8
+NM_MAX_SUBAREAS = 16
+NM_MAX_ORI_BINS = 16
+TILE_ZONE_IN, TILE_ZONE_OUT, TILE_CORRIDOR_A, TILE_CORRIDOR_B = 1, 2, 4, 8  # NM_TILE_* (navmodel_b200.h)
 COMP_ANXIETY, COMP_BCOST, COMP_EXPERIENCE, COMP_BPERSISTENCE, COMP_VTABLE = 1, 2, 3, 4, 5
 DIST_NORMALIZED, DIST_MANHATTAN, DIST_JS = 0, 1, 2
 
@@ -88,6 +91,12 @@ class SimArgs(C.Structure):
         ("d_tile_counts", C.c_void_p), ("d_status", C.c_void_p), ("d_occupancy_total", C.c_void_p),
         ("d_model_state", C.c_void_p), ("d_pcg_u32", C.c_void_p), ("d_pcg_u32_out", C.c_void_p),
         ("device_seed", C.c_uint64), ("use_device_seed", C.c_int32), ("reserved1", C.c_int32),
+        ("d_tile_flags", C.c_void_p), ("d_zone_metrics", C.c_void_p), ("d_static_intervals", C.c_void_p),
+        ("d_subarea_counts", C.c_void_p),
+        ("n_ori_bins", C.c_int32), ("ori_distance", C.c_int32), ("ori_tile_filter", C.c_uint32),
+        ("reserved2", C.c_int32),
+        ("h_ori_edges", C.c_void_p), ("ori_min_lim", C.c_double), ("ori_max_lim", C.c_double),
+        ("d_ori_hist", C.c_void_p),
     ]
 
 _lock = threading.Lock()

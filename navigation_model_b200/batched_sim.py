@@ -70,6 +70,60 @@ class SimResult:
     pcg_state: np.ndarray = None      # [N, 4] generator state after the run
     model_state: np.ndarray = None    # [N, 5] prev_pos.x, prev_pos.y, moving, familiarity, ment_state
     pcg_buffered: np.ndarray = None   # [N, 2] numpy's buffered 32-bit half (has_uint32, uinteger)
+    # fused trajectory metrics (analysis/metrics.py), each None unless requested in run()
+    zone_latency: np.ndarray = None         # [N] latency_enter_shock_zone
+    zone_occupancy: np.ndarray = None       # [N] positions inside the shock zone (occupancy_shock_zone)
+    zone_entries: np.ndarray = None         # [N] shock_zone_entries
+    corridor_switches: np.ndarray = None    # [N] arms
+    static_intervals: np.ndarray = None     # [N] compute_static_intervals(hist_time_moving(moving_bool_list))
+    subarea_counts: np.ndarray = None       # [N, 16] positions by subarea index
+    orientations_histogram: np.ndarray = None       # [N, n_bins (+1 with distance=True)] hist_orientations(_filtered)
+    orientations_histogram_bins: np.ndarray = None  # [n_bins + 1]
+    n_positions: int = 0                    # history length, n_steps + 1
+
+    def as_results(self, maze):
+        """The fused metrics under the product names of the reference's ``@metric`` functions (``analysis/metrics.py``),
+        one row per mouse: what ``BatchedMultiObjectiveFitness`` / ``MultiObjectiveFitness`` objectives key on."""
+        res = {"count_moving": self.count_moving, "it_2_visit_perc_maze": self.it_visit,
+               "moving_dynamics_histogram": self.mov_bouts(), "tiles_histogram": self.tiles_histogram(maze)}
+        if self.occupancy is not None:
+            res["occupancy"] = self.occupancy
+        if self.static_intervals is not None:
+            res["static_intervals"] = self.static_intervals
+        if self.subarea_counts is not None:
+            res["subareas_histogram"] = self.subareas_histogram(maze)
+        if self.zone_entries is not None:
+            res.update(latency_enter_shock_zone=self.zone_latency, occupancy_shock_zone=self.zone_occupancy,
+                       shock_zone_entries=self.zone_entries)
+        if self.corridor_switches is not None:
+            res["corridors_switches"] = self.corridor_switches
+        if self.orientations_histogram is not None:
+            res["orientations_histogram"] = self.orientations_histogram
+            if self.orientations_histogram.shape[1] >= 7:
+                res["rel_ori_signature_histogram"] = self.rel_ori_signature()
+        return res
+
+    def mov_bouts(self):
+        """``moving_dynamics_histogram`` of every mouse, ``[N, 2]`` = (steps in moving bouts, steps in not-moving bouts)
+        (``metrics.py:589-616``): the moved flags are True ``count_moving`` times out of ``n_steps + 1``."""
+        return np.stack([self.count_moving, self.n_positions - self.count_moving], axis=1)
+
+    def subareas_histogram(self, maze):
+        """``[N, max - min + 1]`` like ``metrics.subareas`` (``:470-485``)."""
+        ids = maze.subareas
+        return self.subarea_counts[:, min(ids):max(ids) + 1]
+
+    def tiles_histogram(self, maze):
+        """``[N, 3]`` visits per tile of type (CORNER, WALL, CENTRE) (``histogram_tiles``, ``:251-277``)."""
+        T, totals = maze.MazeTile, maze.description()
+        return np.stack([self.tile_counts[:, int(t)] / totals[t] if totals[t] > 0 else np.zeros(len(self.tile_counts))
+                         for t in (T.CORNER, T.WALL, T.CENTRE)], axis=1)
+
+    def rel_ori_signature(self):
+        """``[N, 3]`` contrasts of the eight-bin turn histogram (``relative_orientation_signatures``, ``:362-380``)."""
+        h = self.orientations_histogram
+        lateral = np.median(h[:, [0, 1, 3, 4]], axis=1)
+        return np.stack([h[:, 2] - lateral, h[:, 2] - h[:, 5], h[:, 6] - h[:, 5]], axis=1)
 
     def tile_analysis(self, maze, n_positions):
         """``(perc, ratio, count)`` dicts keyed by tile type with one array entry per mouse
@@ -177,7 +231,8 @@ class BatchedExperiment:
 
     def run(self, params, n_steps, init_pos, init_ori=0.0, init_disc=None, seeds=None, draws=None,
             visit_percentage=80, history=False, occupancy=False, occupancy_total=False, generators=None,
-            device_seed=None, n_mice=None):
+            device_seed=None, n_mice=None, shock_zone=None, corridors=None, static_intervals=False, subareas=False,
+            orientation_histogram=None):
         """Simulate ``n_steps`` iterations for every mouse.
 
         :param params: ``{name: array[N] or scalar}`` for every name in :attr:`parameter_names`
@@ -187,6 +242,14 @@ class BatchedExperiment:
             ``device_seed`` (with ``n_mice``): every mouse seeds its own PCG64 stream on the device from
             ``(device_seed, mouse index)``; the fast path for millions of mice (not numpy's seeding)
         :param history: also return the full position / orientation / choice histories
+        :param shock_zone: ``{"subareas": int or ints}`` or ``{"tile_lines": int}`` -- fuse ``latency_enter_shock_zone``,
+            ``occupancy_shock_zone`` and ``shock_zone_entries`` (``analysis/metrics.py:488-586``)
+        :param corridors: pair of subarea indices (the reference's ``arms`` uses ``(1, 7)``) -- fuse the switch count
+        :param static_intervals: fuse ``compute_static_intervals`` of the moved flags
+        :param subareas: fuse the per-subarea visit counts (``metrics.subareas``)
+        :param orientation_histogram: ``{}`` or a dict with any of ``n_bins``, ``max_lim``, ``possible_actions``,
+            ``distance``, ``tiles_filter`` (tile types: ``hist_orientations_filtered``) -- fuse ``hist_orientations``
+            of the mouse's own orientation history
         """
         import torch
         _native.require_device()
@@ -310,6 +373,43 @@ class BatchedExperiment:
         if occupancy_total:
             o_tot = out((nT,), torch.int64, zero=True)
             args.d_occupancy_total = o_tot.data_ptr()
+        o_zone = o_static = o_sub = o_oh = edges = None
+        if shock_zone is not None or corridors is not None:
+            flags = torch.from_numpy(tile_flags(self.maze, shock_zone, corridors)).to(dev)
+            keep.append(flags)
+            args.d_tile_flags = flags.data_ptr()
+            o_zone = out((N, 4), torch.int32)
+            args.d_zone_metrics = o_zone.data_ptr()
+        if static_intervals:
+            o_static = out((N,), torch.int32)
+            args.d_static_intervals = o_static.data_ptr()
+        if subareas:
+            if max(self.maze.subareas) >= _native.NM_MAX_SUBAREAS:
+                raise ValueError(f"subarea indices must be below {_native.NM_MAX_SUBAREAS}")
+            o_sub = out((N, _native.NM_MAX_SUBAREAS), torch.int32)
+            args.d_subarea_counts = o_sub.data_ptr()
+        if orientation_histogram is not None:
+            from .analysis import metrics as M
+            oh = dict(orientation_histogram)
+            filt = oh.pop("tiles_filter", None)
+            distance = bool(oh.pop("distance", False))
+            bins, lo, hi = M.orientation_bins("hist_orientations", oh.pop("n_bins", None), oh.pop("max_lim", None),
+                                              oh.pop("possible_actions", None))
+            if oh:
+                raise TypeError(f"unknown orientation_histogram options {sorted(oh)}")
+            edges = np.ascontiguousarray(M.orientation_bin_edges(bins, lo, hi), dtype=np.float64)
+            if len(edges) - 1 > _native.NM_MAX_ORI_BINS:
+                raise ValueError(f"at most {_native.NM_MAX_ORI_BINS} orientation bins")
+            if distance and len(edges) != 7:
+                raise ValueError("hist_orientations(distance=True) is defined for six-bin histograms")
+            args.n_ori_bins, args.ori_distance = len(edges) - 1, int(distance)
+            args.h_ori_edges, args.ori_min_lim, args.ori_max_lim = edges.ctypes.data, float(lo), float(hi)
+            if filt is not None:
+                args.ori_tile_filter = sum(1 << int(t) for t in filt)
+                if args.ori_tile_filter == 0:
+                    raise ValueError("tiles_filter must name at least one tile type")
+            o_oh = out((N, len(edges)), torch.int32)
+            args.d_ori_hist = o_oh.data_ptr()
 
         with torch.cuda.device(dev):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -331,7 +431,53 @@ class BatchedExperiment:
             res.occupancy = o_occ.cpu().numpy().reshape(N, X, Y)
         if occupancy_total:
             res.occupancy_total = o_tot.cpu().numpy().reshape(X, Y)
+        res.n_positions = T + 1
+        if o_zone is not None:
+            z = o_zone.cpu().numpy()
+            if shock_zone is not None:
+                res.zone_latency, res.zone_occupancy, res.zone_entries = z[:, 0].copy(), z[:, 1].copy(), z[:, 2].copy()
+            if corridors is not None:
+                res.corridor_switches = z[:, 3].copy()
+        if o_static is not None:
+            res.static_intervals = o_static.cpu().numpy()
+        if o_sub is not None:
+            res.subarea_counts = o_sub.cpu().numpy()
+        if o_oh is not None:
+            h = o_oh.cpu().numpy()
+            res.orientations_histogram = h if args.ori_distance else h[:, :-1].copy()
+            res.orientations_histogram_bins = edges
         return res
+
+
+def tile_flags(maze, shock_zone=None, corridors=None):
+    """``uint8[X*Y]`` of ``NM_TILE_*`` bits for the fused shock-zone / corridor metrics (x-major).
+
+    ``shock_zone``: ``{"subareas": int or sequence}`` -- inside = subarea in the set, leaving = any other tile -- or
+    ``{"tile_lines": n}`` -- inside = ``y <= n - 1 and x <= 2``, leaving = ``y > n - 1 or x >= 6``
+    (``analysis/metrics.py:488-586``).  ``corridors``: the two subarea indices ``arms`` counts passages between."""
+    X, Y = maze.shape
+    flags = np.zeros((X, Y), dtype=np.uint8)
+    xs, ys = np.meshgrid(np.arange(X), np.arange(Y), indexing="ij")
+    sub = None
+    if (shock_zone is not None and "subareas" in shock_zone) or corridors is not None:
+        sub = np.array([[maze.get_subarea(x, y) for y in range(Y)] for x in range(X)])
+    if shock_zone is not None:
+        if set(shock_zone) == {"subareas"}:
+            z = shock_zone["subareas"]
+            inside = np.isin(sub, [z] if isinstance(z, (int, np.integer)) else list(z))
+            leaving = ~inside
+        elif set(shock_zone) == {"tile_lines"}:
+            low = ys <= int(shock_zone["tile_lines"]) - 1
+            inside, leaving = low & (xs <= 2), ~low | (xs >= 6)
+        else:
+            raise ValueError("shock_zone must be {'subareas': ...} or {'tile_lines': n}")
+        flags |= np.where(inside, _native.TILE_ZONE_IN, 0).astype(np.uint8)
+        flags |= np.where(leaving, _native.TILE_ZONE_OUT, 0).astype(np.uint8)
+    if corridors is not None:
+        a, b = corridors
+        flags |= np.where(sub == a, _native.TILE_CORRIDOR_A, 0).astype(np.uint8)
+        flags |= np.where(sub == b, _native.TILE_CORRIDOR_B, 0).astype(np.uint8)
+    return np.ascontiguousarray(flags.reshape(-1))
 
 
 def movements_possible(maze, segments, device=None):

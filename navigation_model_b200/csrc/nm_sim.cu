@@ -43,6 +43,8 @@ struct SimDev {
   double st;
   double act[kA][2];
   uint8_t zero_act[kA];
+  const uint8_t *subareas;                 // [X*Y] or NULL
+  double ori_edges[NM_MAX_ORI_BINS + 1];   // numpy.histogram edges of the turn histogram
 };
 
 __device__ __forceinline__ uint64_t rotr64(uint64_t v, unsigned r) { return (v >> r) | (v << ((64 - r) & 63)); }
@@ -202,11 +204,36 @@ __global__ void __launch_bounds__(NT, (NM_SIM_MIN_CTAS * kSimThreads) / NT) nm_s
 
     // ---- fused metrics over the history positions (history[0] = initial position, mouse.cpp:58-61) ----
     int n_visited = 0, it_visit = T + 1, count_moving = 0;
+    // shock zone (latency_enter_shock_zone / shock_zone_entries, metrics.py:488-586), corridors (arms, :735-769),
+    // not-moving runs (hist_time_moving -> compute_static_intervals, :445-467, 621-635): moving_bool_list[0] is False,
+    // so the history opens with a not-moving run
+    int zone_latency = T, zone_entries = 0, corridor_switches = 0, corridor_side = 0, static_runs = 1;
+    bool in_zone = false, prev_moved = false;
+    int ohist[NM_MAX_ORI_BINS + 1];
+#pragma unroll
+    for (int i = 0; i <= NM_MAX_ORI_BINS; ++i) ohist[i] = 0;
     int cur_tx = geo.tile(px), cur_ty = geo.tile(py);
     auto record_position = [&](int t_idx, int tx, int ty, bool inside) {
       // occupancy_map / tile_analysis / it_perc_visited_maze on history entry t_idx
       if (!inside) return;
       const int tile = tx * d.Y + ty;
+      if (a.d_tile_flags) {
+        const unsigned f = a.d_tile_flags[tile];
+        if (f & NM_TILE_ZONE_IN) {
+          if (zone_latency == T && t_idx < T) zone_latency = t_idx;  // "never" and "at the last position" are both T
+          if (!in_zone) {
+            zone_entries += 1;
+            in_zone = true;
+          }
+        } else if ((f & NM_TILE_ZONE_OUT) && in_zone) {
+          in_zone = false;
+        }
+        const int side = (int)((f >> 2) & 3u);
+        if (side) {
+          if (corridor_side && corridor_side != side) corridor_switches += 1;
+          corridor_side = side;
+        }
+      }
       const uint32_t c = cnt[tile * nt];
       cnt[tile * nt] = c + 1u;
       if (c == 0u) {
@@ -386,13 +413,33 @@ __global__ void __launch_bounds__(NT, (NM_SIM_MIN_CTAS * kSimThreads) / NT) nm_s
       prevx = nx;
       prevy = ny;
       // -- Mouse.move_to                                                      mouse.cpp:75-87
+      const double ori_before = ori;
       if (!nm_pos_is_approx(nx, ny, px, py)) {
         ori = atan2(ny - py, nx - px);
         px = nx;
         py = ny;
       }
       const int ntx = geo.tile(px), nty = geo.tile(py);
-      if (ntx != cur_tx || nty != cur_ty) count_moving += 1;  // motion_analysis, metrics.py:437-440
+      const bool tile_changed = ntx != cur_tx || nty != cur_ty;
+      if (tile_changed) count_moving += 1;  // motion_analysis, metrics.py:437-440
+      if (prev_moved && !tile_changed) static_runs += 1;
+      prev_moved = tile_changed;
+      if (a.n_ori_bins > 0 && tile_changed &&
+          (a.ori_tile_filter == 0u || (cur_inside && ((a.ori_tile_filter >> tiles[cur_tx * d.Y + cur_ty]) & 1u)))) {
+        // hist_orientations (:329-356): the turn of this step, brought back by one full turn when it leaves
+        // [min_lim, max_lim]; numpy.histogram's bins (left-closed, the last one closed on both sides)
+        double rel = ori - ori_before;
+        if (rel > a.ori_max_lim) rel = rel - 6.283185307179586;
+        else if (rel < a.ori_min_lim) rel = rel - (-6.283185307179586);
+        const int nb = a.n_ori_bins;
+        if (rel >= d.ori_edges[0] && rel <= d.ori_edges[nb]) {
+          int b = 0;
+          for (int k = 1; k < nb; ++k) b += (rel >= d.ori_edges[k]) ? 1 : 0;
+          const int ddx = ntx - cur_tx, ddy = nty - cur_ty;
+          if (a.ori_distance && b == 2 && ddx * ddx + ddy * ddy > 2) b = nb;  // math.dist(...) > 1.5   (:339-343)
+          ohist[b] += 1;
+        }
+      }
       cur_tx = ntx;
       cur_ty = nty;
       cur_inside = cur_tx >= 0 && cur_tx < d.X && cur_ty >= 0 && cur_ty < d.Y;
@@ -431,6 +478,26 @@ __global__ void __launch_bounds__(NT, (NM_SIM_MIN_CTAS * kSimThreads) / NT) nm_s
       }
     }
     if (a.d_status) a.d_status[n] = status;
+    if (a.d_zone_metrics) {
+      int zone_occ = 0;  // positions inside the zone = the visit map summed over the zone's tiles
+      if (a.d_tile_flags)
+        for (int tile = 0; tile < nT; ++tile)
+          if (a.d_tile_flags[tile] & NM_TILE_ZONE_IN) zone_occ += (int)cnt[tile * nt];
+      int *q = a.d_zone_metrics + 4 * n;
+      q[0] = zone_latency; q[1] = zone_occ; q[2] = zone_entries; q[3] = corridor_switches;
+    }
+    if (a.d_static_intervals) a.d_static_intervals[n] = static_runs;
+    if (a.d_subarea_counts) {
+#pragma unroll 1
+      for (int sub = 0; sub < NM_MAX_SUBAREAS; ++sub) {
+        int acc = 0;
+        for (int tile = 0; tile < nT; ++tile)
+          if (d.subareas[tile] == sub) acc += (int)cnt[tile * nt];
+        a.d_subarea_counts[(int64_t)NM_MAX_SUBAREAS * n + sub] = acc;
+      }
+    }
+    if (a.d_ori_hist)
+      for (int b = 0; b <= a.n_ori_bins; ++b) a.d_ori_hist[(int64_t)(a.n_ori_bins + 1) * n + b] = ohist[b];
     if (a.d_model_state) {
       double *q = a.d_model_state + 5 * n;
       q[0] = prevx; q[1] = prevy; q[2] = moving ? 1.0 : 0.0; q[3] = fam; q[4] = home ? 1.0 : 0.0;
@@ -499,10 +566,21 @@ extern "C" int nm_simulate(const nm_maze *mz, const nm_sim_args *args, void *str
     if ((k == NM_COMP_BCOST || k == NM_COMP_BPERSISTENCE))
       NM_CHECK_ARG(a.h_zero_action, "nm_simulate: h_zero_action is required by the biomechanical components");
   }
+  NM_CHECK_ARG(a.n_ori_bins >= 0 && a.n_ori_bins <= NM_MAX_ORI_BINS, "nm_simulate: at most %d orientation bins",
+               NM_MAX_ORI_BINS);
+  NM_CHECK_ARG(a.n_ori_bins == 0 || (a.h_ori_edges && a.d_ori_hist), "nm_simulate: the orientation histogram needs "
+               "h_ori_edges and d_ori_hist");
+  NM_CHECK_ARG(!a.ori_distance || a.n_ori_bins == 6, "nm_simulate: hist_orientations(distance=True) is defined for "
+               "six-bin histograms");
+  NM_CHECK_ARG(!a.d_zone_metrics || a.d_tile_flags, "nm_simulate: d_zone_metrics needs d_tile_flags");
+  NM_CHECK_ARG(!a.d_subarea_counts || mz->d_subareas, "nm_simulate: d_subarea_counts needs a maze with subareas");
   if (a.n_mice == 0) return NM_OK;
   if (cudaSetDevice(mz->device) != cudaSuccess) return nm_fail(NM_ERR_CUDA, "cudaSetDevice(%d) failed", mz->device);
   SimDev d;
   d.a = a;
+  d.subareas = mz->d_subareas;
+  for (int i = 0; i <= NM_MAX_ORI_BINS; ++i) d.ori_edges[i] = (a.n_ori_bins > 0 && i <= a.n_ori_bins) ? a.h_ori_edges[i] : 0.0;
+  if (a.n_ori_bins == 0) d.a.d_ori_hist = nullptr;
   d.tiles = mz->d_tiles;
   d.X = mz->X;
   d.Y = mz->Y;

@@ -516,6 +516,7 @@ class ModelBasedSweep:
         self.n_sweeps = int(n_sweeps)
         self.next_table = np.ascontiguousarray(maze.transition_table(self.discrete_actions), dtype=np.int16)
         self._base = ConditioningSweep(maze, "td0", device=device)  # session streams: s, s1, r only
+        self.last_kernel_ms = None
 
     def add_session(self, trajectory, reward):
         self._base.add_session(trajectory, reward)
@@ -554,12 +555,16 @@ class ModelBasedSweep:
             r_out = torch.empty((S, P, X * Y), dtype=torch.float64, device=dev)
         at, bt, gt = (b._to_dev(torch, x) for x in (alpha, beta, gamma))
         with torch.cuda.device(dev):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
             _native.check(b._dmaze._lib.nm_modelbased_sweep(
                 b._dmaze.handle, b._dstreams.handle, _native.tensor_ptr(nxt), self.next_table.shape[1], self.n_sweeps,
                 _native.tensor_ptr(at), _native.tensor_ptr(bt), _native.tensor_ptr(gt), P, _native.tensor_ptr(vi),
                 _native.tensor_ptr(ll), _native.tensor_ptr(v_out), _native.tensor_ptr(r_out),
                 _native.cuda_stream_ptr()))
+            e1.record()
             torch.cuda.current_stream().synchronize()
+            self.last_kernel_ms = e0.elapsed_time(e1)  # device time of nm_mb_kernel (CUDA events)
         if return_tables:
             return (ll.cpu().numpy(), v_out.cpu().numpy().reshape(S, P, X, Y), r_out.cpu().numpy().reshape(S, P, X, Y))
         return ll.cpu().numpy()

@@ -26,7 +26,7 @@ def test_header_symbols_exported_and_bound():
 def test_version_error_and_no_silent_cpu_fallback():
     from navigation_model_b200 import _native
     lib = _native.lib()
-    assert lib.nm_version() == 1
+    assert lib.nm_version() == 2
     assert lib.nm_mouse_num_actions(None) < 0
     assert b"NULL" in lib.nm_last_error()
     assert _native.STEP_REC_DTYPE.itemsize == 32

@@ -63,3 +63,50 @@ def test_simulation_to_fitness_stays_on_device(cuda):
                                    rtol=1e-12)
         np.testing.assert_allclose(d["tiles"][n], O.js_distance(res.tile_counts[n], data["tile_counts"]), rtol=1e-10)
         assert d["moving"][n] == abs(res.count_moving[n] - 120.0)
+
+
+def test_reference_style_objectives_from_fused_metrics(cuda, golden_sim):
+    """The whole reference pipeline (experiment -> Analyzer metrics -> MultiObjectiveFitness) for a
+    batch: fused metrics under the reference's product names -> batched distances; every value equals the host
+    ``MultiObjectiveFitness`` applied to the host ``Analyzer`` results of the same mouse's history."""
+    from navigation_model_b200.analysis import metrics as M
+    from navigation_model_b200.analysis.statistics import js_distance, manhattan_distance, normalized_distance
+    from navigation_model_b200.batched_fitness import BatchedMultiObjectiveFitness
+    from navigation_model_b200.batched_sim import BatchedExperiment
+    from navigation_model_b200.optimization.fitness import MultiObjectiveFitness
+    from test_sim_gpu import _classes
+    g = golden_sim
+    maze = H.product_m9()
+    names = [str(s) for s in g["param_names"]]
+    P = {n: g["params"][:, i] for i, n in enumerate(names)}
+    T = int(g["T"])
+    exp = BatchedExperiment(maze, g["actions"], g["actions_units"], _classes(), v_table=g["v_table"])
+    r = exp.run(P, T, g["init_pose"][:, :2], g["init_pose"][:, 2], init_disc=g["init_disc"], draws=g["draws"],
+                history=True, occupancy=True, shock_zone={"tile_lines": 5}, corridors=(1, 7), static_intervals=True,
+                subareas=True, orientation_histogram={})
+    results = r.as_results(maze)
+    data = {"orientations_histogram": np.array([1, 10, 5, 9, 3, 8, 0, 120.0]),
+            "subareas_histogram": np.array([0, 150, 60, 20, 10, 40, 80, 241.0]),
+            "moving_dynamics_histogram": np.array([180.0, 421.0]), "static_intervals": 60.0,
+            "shock_zone_entries": 3.0, "tiles_histogram": np.array([9.0, 7.5, 6.0])}
+    spec = [("ori", "js", js_distance, "orientations_histogram"), ("sub", "normalized", normalized_distance,
+                                                                   "subareas_histogram"),
+            ("bouts", "normalized", normalized_distance, "moving_dynamics_histogram"),
+            ("static", "manhattan", manhattan_distance, "static_intervals"),
+            ("entries", "manhattan", manhattan_distance, "shock_zone_entries"),
+            ("tiles", "normalized", normalized_distance, "tiles_histogram")]
+    dev_fit = BatchedMultiObjectiveFitness(data)
+    host_fit = MultiObjectiveFitness(data)
+    for name, kind, fn, key in spec:
+        dev_fit.add_objective(name, kind, key)
+        host_fit.add_objective(name, fn, key)
+    d = dev_fit(results)
+    ana = M.Analyzer(M.discretize_positions, M.motion_analysis, M.hist_time_moving, M.mov_bouts,
+                     M.compute_static_intervals, M.hist_orientations, M.subareas, M.shock_zone_entries,
+                     M.histogram_tiles)
+    for m in range(len(g["seeds"])):
+        host_res = ana.analize(continuous_positions=r.history_position[m], maze=maze, tile_lines=5,
+                               absolute_orientations=list(r.history_orientation[m]))
+        want = host_fit(host_res)
+        for name, *_ in spec:
+            np.testing.assert_allclose(d[name][m], want[name], rtol=1e-10, atol=1e-12, err_msg=f"{name} mouse {m}")
