@@ -139,6 +139,15 @@ typedef struct nm_step_rec {
 int64_t nm_stream_build(const nm_maze *mz, const double *trajectory, const double *reward, int64_t T,
                         nm_mouse *mouse, nm_step_rec *out);
 
+/* Records of n INDEPENDENT transitions starts[i] -> arrivals[i] ([n,2] continuous points) between the given tiles
+ * ([n,2] int32 (x, y), both visitable): what RLAlgorithm.update is handed by ShuffledReplays' imaginary replays
+ * (simulation/rl.py:388-418), one fresh Transition per update.  The algorithm's mouse is driven per transition as in
+ * rl.py:178-189 (move_to(start), endpoints -> candidates, move_to(arrival)); NULL: no candidates (TD0).
+ * Returns n or < 0. */
+int64_t nm_stream_build_pairs(const nm_maze *mz, const double *starts, const double *arrivals,
+                              const int32_t *start_tiles, const int32_t *arrival_tiles, const double *reward, int64_t n,
+                              nm_mouse *mouse, nm_step_rec *out);
+
 typedef struct nm_streams nm_streams;
 
 /* Upload S concatenated session streams.  Session j owns records [h_offsets[j], h_offsets[j+1]);

@@ -50,6 +50,7 @@ SIGNATURES = {
     "nm_maze_closest_visitable_cont": (C.c_int, [_p, C.c_double, C.c_double, C.POINTER(C.c_int),
                                                  C.POINTER(C.c_int)]),
     "nm_stream_build": (_i64, [_p, _p, _p, _i64, _p, _p]),
+    "nm_stream_build_pairs": (_i64, [_p, _p, _p, _p, _p, _p, _i64, _p, _p]),
     "nm_streams_upload": (_p, [_p, _p, _p, C.c_int, C.c_int, C.c_int, _p]),
     "nm_streams_update": (C.c_int, [_p, _p, _p]),
     "nm_streams_free": (None, [_p]),

@@ -9,14 +9,16 @@ Same names, signatures and error behaviour as the reference (``rl.py:12-424``):
   the reference's tests drive one transition at a time, so it stays host Python;
 * :class:`ShuffledReplays` (``rl.py:291-424``) and :class:`ConditioningExperiment` (``rl.py:38-121``).
 
-``ConditioningExperiment.run`` / ``do_replays`` with the three built-in algorithms and (non-imaginary)
-``ShuffledReplays`` do **not** loop in Python: the trajectory is flattened to a step stream by the
-native builder (``nm_stream_build``) and the whole recurrence -- online pass and shuffled replay passes --
-runs in one launch of the sweep kernel (``nm_vtable_sweep`` with a single parameter set; many
-parameter sets: :mod:`navigation_model_b200.sweep`).  That path needs a CUDA device and fails loudly
-without one.  User-defined ``RLAlgorithm`` / ``ReplayStrategy`` subclasses and ``imaginary=True`` replays
-(unseeded stdlib ``random``, ``rl.py:388-418``) are host plugins by nature and go through the generic
-per-transition loop.
+``ConditioningExperiment.run`` / ``do_replays`` with the three built-in algorithms and ``ShuffledReplays``
+do **not** loop in Python: the trajectory is flattened to a step stream by the native builder
+(``nm_stream_build``) and the whole recurrence -- online pass and replay passes -- runs in one launch of
+the sweep kernel (``nm_vtable_sweep`` with a single parameter set; many parameter sets:
+:mod:`navigation_model_b200.sweep`).  Replay passes are parameter-independent step records too: shuffled
+passes are permutations of the online records; ``imaginary=True`` passes (``rl.py:388-418``) are transitions
+sampled from the maze with the stdlib ``random`` module exactly as the reference samples them (seed it with
+``random.seed`` for a replayable run), flattened by ``nm_stream_build_pairs``.  That path needs a CUDA device
+and fails loudly without one.  User-defined ``RLAlgorithm`` / ``ReplayStrategy`` subclasses are host plugins by
+nature and go through the generic per-transition loop.
 """
 import random
 import sys
@@ -198,35 +200,47 @@ class ShuffledReplays(ReplayStrategy):
             return set()
         return {u.transition.s1 for u in self._buffer if u.transition.r == wanted}
 
+    def imaginary_transitions(self, alg):
+        """The ``n_times * len(buffer)`` transitions of the imaginary replays, sampled exactly as ``rl.py:388-418``
+        samples them and in the same order: a start tile with ``random.choice`` over the visitable tiles, a heading
+        with ``random.uniform(-pi, pi)``, an arrival tile with ``random.choice`` among the tiles under the endpoints the
+        ray check accepts; reward +-1 when that tile was ever reached with a stimulation.  The draws come from the
+        stdlib ``random`` module like the reference's (seed it with ``random.seed`` for a replayable sequence); they do
+        not depend on the value table, so they can be drawn ahead of the updates."""
+        hot = self._rewarded_arrivals(alg)
+        sign = -1 if isinstance(alg, NegativeConditioning) else 1
+        coords = self._maze.get_visitable_coordinates()
+        acts = [np.asarray(a, dtype=np.float64) for a in self._possible_actions]
+        out = []
+        for _ in range(self._n_times * len(self._buffer)):
+            t = Transition()
+            t.s = random.choice(coords)
+            t.cs = self._maze.disc2cont(t.s)
+            t.ori = random.uniform(-np.pi, np.pi)
+            c, s = np.cos(t.ori), np.sin(t.ori)
+            rot = np.array([[c, -s], [s, c]])
+            ends = np.zeros((len(acts), 2))
+            for i, act in enumerate(acts):
+                ends[i] = t.cs + np.matmul(rot, act)
+            ok = self._maze.are_movements_possible_cont(t.cs, ends)
+            t.s1 = random.choice(self._maze.cont2disc_list(ends[ok]))
+            t.cs1 = self._maze.disc2cont(t.s1)
+            t.ori1 = np.arctan2(t.cs1[1] - t.cs[1], t.cs1[0] - t.cs[0])
+            t.r = sign if t.s1 in hot else 0
+            out.append(t)
+        return out
+
     def offline_replays(self, alg):
         """Host loop (plugin interface).  ``ConditioningExperiment`` bypasses it for the built-in
         algorithms and runs the passes on the device."""
         if self._imaginary:
-            hot = self._rewarded_arrivals(alg)
-            sign = -1 if isinstance(alg, NegativeConditioning) else 1
-        for _ in range(self._n_times):
-            if not self._imaginary:
-                self._rng.shuffle(self._buffer)
-                for u in self._buffer:
-                    alg.update(u.transition)
-                continue
-            # imaginary transitions sampled from the maze with the (unseeded) stdlib generator, rl.py:388-418
-            for _rep in range(len(self._buffer)):
-                t = Transition()
-                t.s = random.choice(self._maze.get_visitable_coordinates())
-                t.cs = self._maze.disc2cont(t.s)
-                t.ori = random.uniform(-np.pi, np.pi)
-                c, s = np.cos(t.ori), np.sin(t.ori)
-                rot = np.array([[c, -s], [s, c]])
-                ends = np.zeros((len(self._possible_actions), 2))
-                for i, act in enumerate(self._possible_actions):
-                    ends[i] = t.cs + np.matmul(rot, act)
-                ok = self._maze.are_movements_possible_cont(t.cs, ends)
-                t.s1 = random.choice(self._maze.cont2disc_list(ends[ok]))
-                t.cs1 = self._maze.disc2cont(t.s1)
-                t.ori1 = np.arctan2(t.cs1[1] - t.cs[1], t.cs1[0] - t.cs[0])
-                t.r = sign if t.s1 in hot else 0
+            for t in self.imaginary_transitions(alg):
                 alg.update(t)
+            return
+        for _ in range(self._n_times):
+            self._rng.shuffle(self._buffer)
+            for u in self._buffer:
+                alg.update(u.transition)
 
 
 # ------------------------------------------------------------------------------------ experiment
@@ -247,7 +261,9 @@ class ConditioningExperiment:
         alg, rs = self._alg, self._replay_strategy
         if type(alg) not in (TD0, PositiveConditioning, NegativeConditioning):
             return False
-        if type(rs) is not ShuffledReplays or rs._imaginary:
+        if type(rs) is not ShuffledReplays:
+            return False
+        if rs._imaginary and (rs._maze is not self._maze or rs._possible_actions is None):
             return False
         if type(self._maze) is not Maze:
             return False
@@ -313,6 +329,13 @@ class ConditioningExperiment:
     def _replay_records(self):
         from .. import sweep
         rs = self._replay_strategy
+        if rs._imaginary:
+            # sampled transitions are parameter-independent: draw them on the host (same stdlib draws as the
+            # reference), flatten them to records (the algorithm's mouse walks through them as in rl.py:178-189)
+            # and run the updates in the same launch
+            alg = self._alg
+            mouse = alg._mouse if alg.device_kind != _native.ALG_TD0 else None
+            return sweep.records_from_transitions(self._maze, rs.imaginary_transitions(alg), mouse=mouse)
         all_recs = np.zeros(len(rs._buffer), dtype=_native.STEP_REC_DTYPE)
         for i, u in enumerate(rs._buffer):
             all_recs[i] = sweep.record_from_transition(self._maze, u.transition)

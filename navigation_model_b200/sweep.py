@@ -161,6 +161,27 @@ def record_from_transition(maze, t):
     return out
 
 
+def records_from_transitions(maze, transitions, mouse=None):
+    """``nm_step_rec`` records of independent ``Transition`` objects (``cs``, ``cs1``, ``s``, ``s1``, ``r``) -- each one
+    a fresh transition as ``RLAlgorithm.update`` first sees it (no cached ``next_states``): with ``mouse`` (the
+    algorithm's own) the candidate next states are computed by driving it through every transition like
+    ``PositiveConditioning.update`` does (``rl.py:177-189``)."""
+    n = len(transitions)
+    recs = np.zeros(n, dtype=_native.STEP_REC_DTYPE)
+    if n == 0:
+        return recs
+    cs = np.ascontiguousarray(np.array([t.cs for t in transitions], dtype=np.float64).reshape(n, 2))
+    cs1 = np.ascontiguousarray(np.array([t.cs1 for t in transitions], dtype=np.float64).reshape(n, 2))
+    s = np.ascontiguousarray(np.array([t.s for t in transitions], dtype=np.int32).reshape(n, 2))
+    s1 = np.ascontiguousarray(np.array([t.s1 for t in transitions], dtype=np.int32).reshape(n, 2))
+    r = np.ascontiguousarray(np.array([t.r for t in transitions], dtype=np.float64))
+    got = _native.check(_native.lib().nm_stream_build_pairs(
+        host_maze(maze).handle, _native.np_ptr(cs), _native.np_ptr(cs1), _native.np_ptr(s), _native.np_ptr(s1),
+        _native.np_ptr(r), n, None if mouse is None else mouse._h, _native.np_ptr(recs)))
+    assert got == n
+    return recs
+
+
 def replay_records(records, n_times, seed=None, rng=None):
     """Records of ``n_times`` shuffled replay passes over ``records`` in execution order
     (``ShuffledReplays.offline_replays``, ``rl.py:419-424``: cumulative in-place ``Generator.shuffle``)."""

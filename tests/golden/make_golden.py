@@ -150,8 +150,63 @@ def make_fit():
     print("fit_golden.npz:", {k: np.shape(v) for k, v in out.items()})
 
 
+def make_imaginary():
+    """ShuffledReplays(imaginary=True) (rl.py:388-418): transitions sampled from the maze with the stdlib `random`
+    module, made replayable by seeding it right before the run.  Stores the V-tables and, for one run, the
+    transitions the strategy sampled (recorded by wrapping the algorithm's update -- the reference is not modified)."""
+    import random
+    out = {}
+    maze = Maze.from_file(M9_FILE, size_tile=SIZE_TILE)
+    T = 400
+    traj, rew = synthetic_session(maze, 6, T, goal=(1, 2))  # a goal next to the start: rewarded often
+    out["traj"], out["rew"] = traj, rew
+    params = [(0.1, 0.9), (0.6, 0.7)]
+    out["params"] = np.array(params)
+    out["random_seed"] = np.array(4242)
+    for alg_name in ("td0", "positive", "negative"):
+        r = -rew if alg_name == "negative" else rew
+        tabs = []
+        for (a, g) in params:
+            mouse = Mouse(traj[0], 0.0, A8)
+            alg = {"td0": lambda: TD0(a, g), "positive": lambda: PositiveConditioning(a, g, mouse, maze),
+                   "negative": lambda: NegativeConditioning(a, g, mouse, maze)}[alg_name]()
+            rep = ShuffledReplays(n_times=2, seed=1, imaginary=True, maze=maze, possible_actions=A8)
+            exp = ConditioningExperiment(maze, alg, rep)
+            random.seed(4242)
+            exp.run(list(traj), [0.0] * len(traj), list(r), do_replays=True)
+            exp.do_replays()  # a second round of imaginary replays continues the stdlib stream
+            tabs.append(np.array(exp.v_table))
+        out[f"{alg_name}_V"] = np.array(tabs)
+    # the sampled transitions of one run (positive, first parameter set, first do_replays only)
+    mouse = Mouse(traj[0], 0.0, A8)
+    alg = PositiveConditioning(0.1, 0.9, mouse, maze)
+    rep = ShuffledReplays(n_times=2, seed=1, imaginary=True, maze=maze, possible_actions=A8)
+    exp = ConditioningExperiment(maze, alg, rep)
+    random.seed(4242)
+    exp.run(list(traj), [0.0] * len(traj), list(rew), do_replays=False)
+    seen = []
+    plain_update = alg.update
+
+    def recording_update(t):
+        u = plain_update(t)
+        seen.append((t.s, t.s1, t.r, t.ori, [tuple(c) for c in t.extra["next_states"]]))
+        return u
+
+    alg.update = recording_update
+    exp.do_replays()
+    out["im_s"] = np.array([x[0] for x in seen])
+    out["im_s1"] = np.array([x[1] for x in seen])
+    out["im_r"] = np.array([x[2] for x in seen], dtype=np.float64)
+    out["im_ori"] = np.array([x[3] for x in seen])
+    out["im_ncand"] = np.array([len(x[4]) for x in seen])
+    np.savez_compressed(os.path.join(HERE, "imaginary_golden.npz"), **out)
+    print("imaginary_golden.npz:", {k: np.shape(v) for k, v in out.items()}, "rewarded:", int((out["im_r"] != 0).sum()))
+
+
 if __name__ == "__main__":
     stages = sys.argv[1:] or ["fit", "sim"]
+    if "imaginary" in stages:
+        make_imaginary()
     if "fit" in stages:
         make_fit()
     if "sim" in stages:
