@@ -163,6 +163,44 @@ int nm_streams_update(nm_streams *st, const nm_step_rec *h_records, void *stream
 void nm_streams_free(nm_streams *st);
 
 /* ------------------------------------------------------------------------------------------------
+ * Session ingestion on the device (many sessions at once)
+ * ---------------------------------------------------------------------------------------------- */
+/* Session.__init__(new_sampling_time=...) subsampling (analysis/data.py:39-74) of S raw recordings stored back to
+ * back: session j owns samples [d_offsets[j], d_offsets[j+1]) of d_time [n], d_traj [n,2] and (optional) d_reward [n].
+ * For every window of at least `sampling_time` seconds the first finite point and the first reward that is neither 0
+ * nor NaN (else 0.0) are kept; windows without a finite point are skipped; NaN timestamps are skipped.  Session j's
+ * d_counts[j] subsampled points are written from index d_offsets[j] of d_traj_out / d_reward_out (same layout as
+ * the input: no compaction).  All pointers are DEVICE pointers. */
+int nm_sessions_subsample_device(const double *d_time, const double *d_traj, const double *d_reward,
+                                 const int64_t *d_offsets, int S, double sampling_time, double *d_traj_out,
+                                 double *d_reward_out, int64_t *d_counts, void *stream);
+
+/* compute_orientations (analysis/metrics.py:653-694) of S sessions laid out like above (session j: d_counts[j] points
+ * from index d_offsets[j]).  d_ori_out [.] gets one heading per point at the same indices; d_first_moved [S] the index
+ * of the first step that moved, -1 when a session never moves (its headings are NaN; the reference raises IndexError).
+ * n_actions > 0 (with a device maze): a step only counts as a move when its end tile lies under one of the endpoints
+ * of the actions rotated by the previous heading (":668-671").  All d_ pointers are DEVICE pointers. */
+int nm_sessions_orientations_device(const nm_maze *mz, const double *d_traj, const int64_t *d_offsets,
+                                    const int64_t *d_counts, int S, const double *h_actions, int n_actions,
+                                    double *d_ori_out, int64_t *d_first_moved, void *stream);
+
+/* adjust_positions_to_maze (analysis/data.py:372-388) on n DEVICE points [n,2]: a point outside the visitable tiles
+ * moves to the centre of the nearest visitable tile; points with a NaN coordinate stay.  d_out may alias d_points. */
+int nm_positions_adjust_device(const nm_maze *mz, const double *d_points, int64_t n, double *d_out, void *stream);
+
+/* nm_stream_build for S sessions at once, on the device: session j's h_counts[j] >= 1 points start at index
+ * h_offsets[j] of d_traj [.,2] / d_reward [.] (e.g. the output of nm_sessions_subsample_device) and yield
+ * h_counts[j] - 1 online records.  n_actions = 0: no candidates (TD0 value learning); otherwise every session gets its
+ * own algorithm mouse, Mouse(trajectory[0], 0.0, actions) or h_mouse_init[j] = (x, y, ori).  The returned handle is
+ * resident on the maze's device and is used like one from nm_streams_upload.  Synchronises `stream`.  NULL on error
+ * (a step without visitable candidate is an error, rl.py:184). */
+nm_streams *nm_streams_build_device(const nm_maze *mz, const double *d_traj, const double *d_reward,
+                                    const int64_t *h_offsets, const int64_t *h_counts, int S, const double *h_actions,
+                                    int n_actions, const double *h_mouse_init, void *stream);
+/* Copy the records of a stream handle back to the host ([total] nm_step_rec); synchronises `stream`. */
+int nm_streams_download(const nm_streams *st, nm_step_rec *h_records, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Parameter-grid sweeps (one thread = one parameter set; V-table resident in shared memory)
  * ---------------------------------------------------------------------------------------------- */
 /* V-table learning over P parameter sets x S sessions (each session starts from v_init).

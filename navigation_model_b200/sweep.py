@@ -300,6 +300,7 @@ class ConditioningSweep:
         self._dmaze = None
         self._dstreams = None
         self._staging = None  # pinned host copy of the concatenated records
+        self._external = False  # True: the streams were built on the device (use_streams)
 
     # -- sessions -------------------------------------------------------------------------------
     def add_session(self, trajectory, reward, session=None):
@@ -323,17 +324,31 @@ class ConditioningSweep:
     def add_records(self, records, n_online=None):
         self._records.append(np.ascontiguousarray(records, dtype=_native.STEP_REC_DTYPE))
         self._online.append(len(records) if n_online is None else int(n_online))
+        if self._external:
+            raise RuntimeError("this sweep uses device-built streams; host sessions cannot be mixed in")
         self._dstreams = None
         self._staging = None
 
+    def use_streams(self, streams):
+        """Use step streams that already live on the device (``SessionBatch.streams``, built by
+        ``nm_streams_build_device``) instead of host-built records; replaces every session added so far."""
+        if streams.dmaze.maze is not self.maze:
+            raise ValueError("the streams were built for another maze")
+        if self.alg != _native.ALG_TD0 and not streams.has_candidates:
+            raise ValueError("PositiveConditioning / NegativeConditioning need possible_actions")
+        self._records, self._online, self._staging = [], [], None
+        self._dmaze = streams.dmaze
+        self._dstreams = streams
+        self._external = True
+
     @property
     def n_sessions(self):
-        return len(self._records)
+        return self._dstreams.S if self._external else len(self._records)
 
     @property
     def updates_per_parameter_set(self):
         """Number of value updates one parameter set performs over all sessions (online + replays)."""
-        return int(sum(len(r) for r in self._records))
+        return self._dstreams.total if self._external else int(sum(len(r) for r in self._records))
 
     # -- device state ----------------------------------------------------------------------------
     def _ensure_device(self):
@@ -437,7 +452,8 @@ class ConditioningSweep:
         alpha, beta, gamma = _as_param(alpha, P), _as_param(beta, P), _as_param(gamma, P)
         if not (alpha.size == beta.size == gamma.size == P):
             raise ValueError("alpha, beta and gamma must have the same length")
-        if any(r["ncand"].min(initial=1) == 0 for r in self._records if len(r)):
+        if (self._external and not self._dstreams.has_candidates) or \
+                any(r["ncand"].min(initial=1) == 0 for r in self._records if len(r)):
             raise ValueError("the log-likelihood needs candidate next states: pass possible_actions")
         vi, per = self._v_init_tensor(torch, v_init, P)
         v_out = None
