@@ -33,7 +33,13 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 constexpr int kA = NM_MAX_CAND;
 constexpr int kSimThreads = 128;
 #ifndef NM_SIM_MIN_CTAS
-#define NM_SIM_MIN_CTAS 4  // resident CTAs per SM the register allocation is capped for
+#define NM_SIM_MIN_CTAS 3  // resident CTAs per SM the register allocation is capped for (32-bit visit counters)
+#endif
+#ifndef NM_SIM_COOP_MAX_ROUNDS
+#define NM_SIM_COOP_MAX_ROUNDS 5  // more rounds of shared ray walks than this: every mouse walks its own endpoints
+#endif
+#ifndef NM_SIM_MIN_CTAS_U16
+#define NM_SIM_MIN_CTAS_U16 6  // same, for the variant with 16-bit visit counters
 #endif
 
 struct SimDev {
@@ -43,6 +49,10 @@ struct SimDev {
   double st;
   double act[kA][2];
   uint8_t zero_act[kA];
+  uint8_t null_act[kA];  // exactly (0, 0): the endpoint is the position itself
+  uint8_t walk_ord[kA];  // ordinal of action i among the actions that need a ray walk
+  uint32_t walk_list;    // 4 bits per entry: walk_list >> 4j & 7 = j-th action that needs a ray walk
+  int n_walk;            // number of those
   const uint8_t *subareas;                 // [X*Y] or NULL
   double ori_edges[NM_MAX_ORI_BINS + 1];   // numpy.histogram edges of the turn histogram
 };
@@ -91,8 +101,10 @@ struct Pcg64 {
 
 // NT = threads per CTA (compile-time: every per-mouse table is indexed [row][thread], so row strides and the
 // fixed-size tables' offsets become immediates).
-template <int NT>
-__global__ void __launch_bounds__(NT, (NM_SIM_MIN_CTAS * kSimThreads) / NT) nm_sim_kernel(const SimDev d) {
+// CntT = type of a visit counter: u16 when n_steps + 1 < 65536 (half the shared memory: one more resident CTA), else u32.
+template <int NT, typename CntT>
+__global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 : NM_SIM_MIN_CTAS) * kSimThreads) / NT)
+    nm_sim_kernel(const SimDev d) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nT = d.X * d.Y;
   constexpr int nt = NT;
@@ -100,31 +112,38 @@ __global__ void __launch_bounds__(NT, (NM_SIM_MIN_CTAS * kSimThreads) / NT) nm_s
   // 2^(j/16) | anxiety value*weight by tile code [5][nt] | biomechanical cost*weight by action [kA][nt] |
   // visit map [nT][nt] u32 | shared normalised value table [nT] | geometry tables
   double *exp_tab = reinterpret_cast<double *>(smem_raw);
-  double *anx_sm = exp_tab + 16;
+  double *act_sm = exp_tab + 16;                                        // [kA][2] relative actions
+  uint8_t *rank_sm = reinterpret_cast<uint8_t *>(act_sm + 2 * kA);      // [warps][32] rank -> lane of the dirty mice
+  uint16_t *res_sm = reinterpret_cast<uint16_t *>(rank_sm + nt);        // [thread][kA] walk results: tile | ok << 15
+  double *anx_sm = exp_tab + 16 + 2 * kA + (nt / 32) * 4 + 2 * nt;
   double *bcw_sm = anx_sm + 5 * nt;
-  uint32_t *count = reinterpret_cast<uint32_t *>(bcw_sm + kA * nt);
+  CntT *count = reinterpret_cast<CntT *>(bcw_sm + kA * nt);
   double *vt_sm = reinterpret_cast<double *>(count + (size_t)nT * nt);
   if (tid < 16) exp_tab[tid] = c_exp2tab[tid];
+  if (tid < 2 * kA) act_sm[tid] = d.act[tid >> 1][tid & 1];
   NmSimGeom geo;  // tile table, grid-line tables (nm_simgeom.cuh)
   geo.build(reinterpret_cast<unsigned char *>(vt_sm + nT), d.tiles, d.X, d.Y, d.st);
   const uint8_t *tiles = geo.tiles;
   if (d.a.d_vtable && !d.a.vtable_per_mouse)
     for (int i = tid; i < nT; i += nt) vt_sm[i] = d.a.d_vtable[i];
-  for (int i = 0; i < nT; ++i) count[i * nt + tid] = 0u;
+  for (int i = 0; i < nT; ++i) count[i * nt + tid] = (CntT)0;
   __syncthreads();
 
   const nm_sim_args &a = d.a;
-  const int64_t n = (int64_t)blockIdx.x * nt + tid;
   const int64_t N = a.n_mice;
-  const bool live = n < N;
+  const int64_t n_raw = (int64_t)blockIdx.x * nt + tid;
+  // The warp shares the ray walks of its mice (below), so all 32 lanes run the step loop together: the lanes past the
+  // last mouse (final CTA only) shadow mouse N - 1 and store nothing.
+  const bool live = n_raw < N;
+  const int64_t n = live ? n_raw : N - 1;
   const int A = a.n_actions;
   const int T = a.n_steps;
-  uint32_t *cnt = count + tid;
+  CntT *cnt = count + tid;
 
   int status = 0;
   ExpRegs er;
   er.load(smem_u32(exp_tab));
-  if (live) {
+  {
     // ---- per-mouse state -------------------------------------------------------------------------
     double px = a.d_init_pose[3 * n], py = a.d_init_pose[3 * n + 1], ori = a.d_init_pose[3 * n + 2];
     double prevx = a.d_init_prev[2 * n], prevy = a.d_init_prev[2 * n + 1];
@@ -235,7 +254,7 @@ __global__ void __launch_bounds__(NT, (NM_SIM_MIN_CTAS * kSimThreads) / NT) nm_s
         }
       }
       const uint32_t c = cnt[tile * nt];
-      cnt[tile * nt] = c + 1u;
+      cnt[tile * nt] = (CntT)(c + 1u);
       if (c == 0u) {
         n_visited += 1;
         // perc = n_visited * 100 / number_visitable_tiles >= percentage      metrics.py:711-721
@@ -247,40 +266,106 @@ __global__ void __launch_bounds__(NT, (NM_SIM_MIN_CTAS * kSimThreads) / NT) nm_s
     // NOTE: the ExperienceComponent increments count[x, y] of the CURRENT tile at every decision
     // (:456) -- that is exactly "occupancy over history[0..t]", so history entry t is recorded at the
     // top of step t and the final entry after the loop.
-    if (a.d_hist_pos) {
+    if (live && a.d_hist_pos) {
       a.d_hist_pos[2 * n] = px;
       a.d_hist_pos[2 * n + 1] = py;
     }
-    if (a.d_hist_ori) a.d_hist_ori[n] = ori;
+    if (live && a.d_hist_ori) a.d_hist_ori[n] = ori;
+
+    // Reachability of the A endpoints (experiment.py:36-38) depends on the pose only, and most mice keep their pose
+    // in a given step (the null action wins): every mouse caches its reachability mask `vis` and the tiles under its
+    // endpoints (16 bits each), and the walks of the mice whose pose did change ("dirty") are spread over all 32
+    // lanes of the warp -- item = (dirty mouse, action), 32 items per round, inputs and results travel by shuffles.
+    constexpr unsigned kFull = 0xffffffffu;
+    const int lane = tid & 31;
+    uint8_t *rank_w = rank_sm + (tid >> 5) * 32;
+    uint16_t *res_w = res_sm + (tid >> 5) * (32 * kA);  // the warp's mailbox: [lane][action]
+    const int n_walk = d.n_walk;
+    const unsigned div_walk = n_walk > 0 ? (65536u + (unsigned)n_walk - 1u) / (unsigned)n_walk : 0u;  // item / n_walk
+    bool active = true, dirty = true;
+    unsigned vis = 0u;
+    uint4 et = make_uint4(0u, 0u, 0u, 0u);  // eight 16-bit entries: tile under endpoint i | reachable << 15
+    double c = 1.0, s = 0.0;
+    auto et_get = [&](int i) -> int {  // i is a compile-time constant after unrolling
+      const uint32_t w = i < 2 ? et.x : i < 4 ? et.y : i < 6 ? et.z : et.w;
+      return (int)((i & 1) ? ((w >> 16) & 0x7fffu) : (w & 0x7fffu));
+    };
+#pragma unroll
+    for (int i = 0; i < kA; ++i) res_w[lane * kA + i] = 0;
 
     for (int t = 0; t < T; ++t) {
-      record_position(t, cur_tx, cur_ty, cur_inside);
-      // -- endpoints + reachability                                          experiment.py:36-38
-      double c, s;
-      sincos(ori, &s, &c);
-      int etile[kA];
-      unsigned vis = 0u;
-      const bool start_ok = cur_inside && tiles[cur_tx * d.Y + cur_ty] != 0;  // tile under the mouse (maze.py:578)
+      __syncwarp();
+      if (__ballot_sync(kFull, active) == 0u) break;
+      if (active) record_position(t, cur_tx, cur_ty, cur_inside);
+      const bool need = active && dirty;
+      const unsigned dmask = __ballot_sync(kFull, need);
+      if (dmask != 0u) {
+        const bool start_ok = cur_inside && tiles[cur_tx * d.Y + cur_ty] != 0;  // tile under the mouse (maze.py:578)
+        const int cur_tile = cur_inside ? cur_tx * d.Y + cur_ty : 0;
+        if (need) {
+          sincos(ori, &s, &c);
 #pragma unroll
-      for (int i = 0; i < kA; ++i) {
-        etile[i] = 0;
-        if (i < A) {
-          if (d.act[i][0] == 0.0 && d.act[i][1] == 0.0) {
-            // null displacement (uniform over the CTA): the endpoint IS the position, R(ori)*0 + p == p bit for bit,
-            // and no grid line is crossed -- reachable iff the tile under the mouse is visitable
-            etile[i] = cur_inside ? cur_tx * d.Y + cur_ty : 0;
-            if (start_ok) vis |= 1u << i;
-          } else {
+          for (int i = 0; i < kA; ++i)
+            if (i < A && d.null_act[i])
+              // null displacement: the endpoint IS the position, R(ori)*0 + p == p bit for bit, and no grid line is
+              // crossed -- reachable iff the tile under the mouse is visitable
+              res_w[lane * kA + i] = (uint16_t)(cur_tile | (start_ok ? 0x8000 : 0));
+        }
+        const int nd = __popc(dmask);
+        if (nd * n_walk > NM_SIM_COOP_MAX_ROUNDS * 32) {
+          // (almost) every mouse moved: each walks its own endpoints
+          if (need) {
+#pragma unroll 1
+            for (int j = 0; j < n_walk; ++j) {
+              const int i = (int)((d.walk_list >> (4 * j)) & 7u);
+              double ex, ey;
+              nm_pose_endpoint(c, s, px, py, act_sm[2 * i], act_sm[2 * i + 1], &ex, &ey);
+              int tile_e;
+              const bool ok = geo.move_ok(start_ok, cur_tx, cur_ty, px, py, ex, ey, &tile_e);
+              res_w[lane * kA + i] = (uint16_t)(tile_e | (ok ? 0x8000 : 0));
+            }
+          }
+        } else if (n_walk > 0) {
+          const int my_rank = __popc(dmask & ((1u << lane) - 1u));
+          if (need) rank_w[my_rank] = (uint8_t)lane;
+          __syncwarp();
+          const int info = (start_ok ? 1 : 0) | ((cur_inside ? cur_tx : 0) << 1) | ((cur_inside ? cur_ty : 0) << 16);
+          const int items = nd * n_walk;
+#pragma unroll 1
+          for (int base = 0; base < items; base += 32) {
+            const int it = base + lane;
+            const bool valid = it < items;
+            const int r = valid ? (int)(((unsigned)it * div_walk) >> 16) : 0;  // exact for it < 256
+            const int j = valid ? it - r * n_walk : 0;
+            const int i = (int)((d.walk_list >> (4 * j)) & 7u);
+            const int src = rank_w[r];
+            const double spx = __shfl_sync(kFull, px, src), spy = __shfl_sync(kFull, py, src);
+            const double sc = __shfl_sync(kFull, c, src), ss = __shfl_sync(kFull, s, src);
+            const int sinfo = __shfl_sync(kFull, info, src);
             double ex, ey;
-            nm_pose_endpoint(c, s, px, py, d.act[i][0], d.act[i][1], &ex, &ey);
-            if (geo.move_ok(start_ok, cur_tx, cur_ty, px, py, ex, ey, &etile[i])) vis |= 1u << i;
+            nm_pose_endpoint(sc, ss, spx, spy, act_sm[2 * i], act_sm[2 * i + 1], &ex, &ey);
+            int tile_e;
+            const bool ok = geo.move_ok((sinfo & 1) != 0, (sinfo >> 1) & 0x7fff, sinfo >> 16, spx, spy, ex, ey, &tile_e);
+            if (valid) res_w[src * kA + i] = (uint16_t)(tile_e | (ok ? 0x8000 : 0));  // into the owner's mailbox
           }
         }
+        __syncwarp();
+        if (need) {
+          et = *reinterpret_cast<const uint4 *>(res_w + lane * kA);
+          vis = ((et.x >> 15) & 1u) | ((et.x >> 30) & 2u) | ((et.y >> 13) & 4u) | ((et.y >> 28) & 8u) |
+                ((et.z >> 11) & 16u) | ((et.z >> 26) & 32u) | ((et.w >> 9) & 64u) | ((et.w >> 24) & 128u);
+        }
+        dirty = false;
       }
+      if (!active) continue;
+      int etile[kA];
+#pragma unroll
+      for (int i = 0; i < kA; ++i) etile[i] = et_get(i);
       const int K = __popc(vis);
       if (K == 0) {  // np.max([]) raises in the reference (exploration_model.py:92)
         status = t + 1;
-        break;
+        active = false;
+        continue;
       }
       int act_idx = -1;
       if (a.model_kind == 0) {  // ---------------- BehaviouralModel -----------------------------------------
@@ -418,6 +503,7 @@ __global__ void __launch_bounds__(NT, (NM_SIM_MIN_CTAS * kSimThreads) / NT) nm_s
         ori = atan2(ny - py, nx - px);
         px = nx;
         py = ny;
+        dirty = true;  // new pose: the cached reachability is stale
       }
       const int ntx = geo.tile(px), nty = geo.tile(py);
       const bool tile_changed = ntx != cur_tx || nty != cur_ty;
@@ -443,15 +529,16 @@ __global__ void __launch_bounds__(NT, (NM_SIM_MIN_CTAS * kSimThreads) / NT) nm_s
       cur_tx = ntx;
       cur_ty = nty;
       cur_inside = cur_tx >= 0 && cur_tx < d.X && cur_ty >= 0 && cur_ty < d.Y;
-      if (a.d_hist_pos) {
+      if (live && a.d_hist_pos) {
         a.d_hist_pos[((int64_t)(t + 1) * N + n) * 2] = px;
         a.d_hist_pos[((int64_t)(t + 1) * N + n) * 2 + 1] = py;
       }
-      if (a.d_hist_ori) a.d_hist_ori[(int64_t)(t + 1) * N + n] = ori;
-      if (a.d_hist_choice) a.d_hist_choice[(int64_t)t * N + n] = (uint8_t)act_idx;
+      if (live && a.d_hist_ori) a.d_hist_ori[(int64_t)(t + 1) * N + n] = ori;
+      if (live && a.d_hist_choice) a.d_hist_choice[(int64_t)t * N + n] = (uint8_t)act_idx;
     }
     if (status == 0) record_position(T, cur_tx, cur_ty, cur_inside);
 
+    if (live) {
     if (a.d_final_pose) {
       a.d_final_pose[3 * n] = px;
       a.d_final_pose[3 * n + 1] = py;
@@ -502,6 +589,7 @@ __global__ void __launch_bounds__(NT, (NM_SIM_MIN_CTAS * kSimThreads) / NT) nm_s
       double *q = a.d_model_state + 5 * n;
       q[0] = prevx; q[1] = prevy; q[2] = moving ? 1.0 : 0.0; q[3] = fam; q[4] = home ? 1.0 : 0.0;
     }
+    }  // live
   }
 
   // ---- occupancy maps: coalesced write through a transposed read of count[tile][thread] -------------
@@ -591,20 +679,37 @@ extern "C" int nm_simulate(const nm_maze *mz, const nm_sim_args *args, void *str
     d.act[i][1] = i < a.n_actions ? a.h_actions[2 * i + 1] : 0.0;
     d.zero_act[i] = (i < a.n_actions && a.h_zero_action) ? a.h_zero_action[i] : 0;
   }
+  d.n_walk = 0;
+  d.walk_list = 0u;
+  for (int i = 0; i < kA; ++i) {
+    d.null_act[i] = (i < a.n_actions && d.act[i][0] == 0.0 && d.act[i][1] == 0.0) ? 1 : 0;
+    d.walk_ord[i] = (uint8_t)d.n_walk;
+    if (i < a.n_actions && !d.null_act[i]) {
+      d.walk_list |= (uint32_t)i << (4 * d.n_walk);
+      d.n_walk += 1;
+    }
+  }
   const int nT = mz->X * mz->Y;
   int threads = kSimThreads;
   const size_t geo_bytes = NmSimGeom::smem_bytes(mz->X, mz->Y);
-  // 2^(j/16) | per-mouse anxiety and biomechanical-cost tables | visit map | shared value table | geometry
+  // 2^(j/16) | actions | rank -> lane scratch | per-mouse anxiety and biomechanical-cost tables | visit map | shared
+  // value table | geometry
+  const bool small_counts = a.n_steps < 65535;  // a tile is visited at most n_steps + 1 times
+  const size_t cnt_bytes = small_counts ? sizeof(uint16_t) : sizeof(uint32_t);
   auto smem_for = [&](int th) {
-    return 128 + (size_t)(5 + kA) * th * sizeof(double) + (size_t)nT * th * sizeof(uint32_t) + (size_t)nT * sizeof(double) +
-           geo_bytes;
+    return 128 + 16 * kA + (size_t)th * (1 + 2 * kA) + (size_t)(5 + kA) * th * sizeof(double) + (size_t)nT * th * cnt_bytes +
+           (size_t)nT * sizeof(double) + geo_bytes;
   };
   while (threads > 32 && smem_for(threads) > 200 * 1024) threads /= 2;
   const size_t smem = smem_for(threads);
   NM_CHECK_ARG(smem <= 227 * 1024, "nm_simulate: maze of %d tiles does not fit the shared-memory visit map", nT);
   const int64_t blocks = (a.n_mice + threads - 1) / threads;
   NM_CHECK_ARG(blocks <= 2147483647LL, "nm_simulate: too many mice for one launch");
-  void (*kern)(const SimDev) = threads == 128 ? nm_sim_kernel<128> : threads == 64 ? nm_sim_kernel<64> : nm_sim_kernel<32>;
+  void (*kern)(const SimDev);
+  if (small_counts)
+    kern = threads == 128 ? nm_sim_kernel<128, uint16_t> : threads == 64 ? nm_sim_kernel<64, uint16_t> : nm_sim_kernel<32, uint16_t>;
+  else
+    kern = threads == 128 ? nm_sim_kernel<128, uint32_t> : threads == 64 ? nm_sim_kernel<64, uint32_t> : nm_sim_kernel<32, uint32_t>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   kern<<<(unsigned)blocks, threads, smem, (cudaStream_t)stream>>>(d);
