@@ -205,7 +205,7 @@ def workload_config(args, n_gpus, p_per_rank):
 
 def other_paths(local, world, rank, dist, dev):
     """The two other kernels of the hot path, measured the same way (per-rank shard of fixed size, device time as the
-    max over ranks): forward simulation (BASELINE configs[4] shape, scaled to 262 144 mice x 1 000 steps per GPU, all
+    max over ranks): forward simulation (BASELINE configs[4] shape, scaled to 909 312 mice x 1 000 steps per GPU, all
     five components, device-seeded PCG64 streams, fused metrics) and the model-based agent (configs[3] shape: 400-state
     maze, 8 actions, 20 000 parameter sets x 1 000 steps per GPU, one value-iteration sweep per step).  Reported under
     ``also_measured``; the headline metric stays the fitness grid sweep."""
@@ -226,7 +226,7 @@ def other_paths(local, world, rank, dist, dev):
     # ---- forward simulation -----------------------------------------------------------------------------
     maze = Maze(O.M9_LAYOUT, O.M9_SUBAREAS, size_tile=O.M9_SIZE_TILE)
     rng = np.random.default_rng(1000 + rank)
-    N, T = 262144, 1000
+    N, T = 148 * 6 * 128 * 8, 1000  # eight full waves of the kernel's residency (6 CTAs of 128 mice per SM)
     u = rng.uniform
     P = {"beta": u(0.5, 6, N), "W_anx": u(0, 10, N), "p1": u(0, 1, N), "p2": u(0, 1, N), "p3": u(0, 1, N),
          "W_bcost": u(0, 10, N), "k": u(0.05, 4, N), "gamma": u(0.2, 2, N), "W_exp": u(0, 10, N),

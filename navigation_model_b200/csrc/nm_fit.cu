@@ -107,7 +107,10 @@ int plan_launch(int bytes_per_unit, int64_t P, int S, int device, const char *en
     if (v >= 32 && v <= max_nc && v % 32 == 0) chosen = v;
   }
   if (!chosen) {
-    const double sat = 224.0;  // resident consumer threads per SM below which latency is not hidden
+    // Cost of a candidate CTA size = waves x time of one wave.  Measured on B200 (tools/fit_nc_sweep.py,
+    // profiles/r01_fit_nc_sweep.md): the consumer warps of an SM are dealt round-robin to its four schedulers and a
+    // wave lasts as long as the busiest scheduler needs, T(w) ~ 0.96 + 0.36 w (ms per 5000 steps) for w consumer warps
+    // on it -- 12 warps (3 + 3 + 3 + 3) are as fast per parameter set as 14 (4 + 4 + 3 + 3), 13 are slower than both.
     double best = 1e300;
     for (int nc = max_nc; nc >= 32; nc -= 32) {  // descending: ties go to the fuller CTA
       const size_t smem = (size_t)kFixedBytes + (size_t)bytes_per_unit * nc;
@@ -120,9 +123,8 @@ int plan_launch(int bytes_per_unit, int64_t P, int S, int device, const char *en
       const int64_t waves = (ctas + slots - 1) / slots;
       int64_t r_eff = (ctas + sms - 1) / sms;
       if (r_eff > r) r_eff = r;
-      double load = (double)(r_eff * nc);
-      if (load < sat) load = sat;
-      const double cost = (double)waves * load;
+      const int64_t busiest = (r_eff * (nc / 32) + 3) / 4;  // consumer warps on the fullest scheduler
+      const double cost = (double)waves * (0.96 + 0.36 * (double)busiest);
       if (cost < best * 0.999) {
         best = cost;
         chosen = nc;

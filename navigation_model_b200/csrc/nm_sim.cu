@@ -21,6 +21,8 @@
 //   fused metrics                              analysis/metrics.py:192-248, 425-442, 697-731
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "nm_common.h"
 #include "nm_pose.h"
 #include "nm_simgeom.cuh"
@@ -694,7 +696,9 @@ extern "C" int nm_simulate(const nm_maze *mz, const nm_sim_args *args, void *str
   const size_t geo_bytes = NmSimGeom::smem_bytes(mz->X, mz->Y);
   // 2^(j/16) | actions | rank -> lane scratch | per-mouse anxiety and biomechanical-cost tables | visit map | shared
   // value table | geometry
-  const bool small_counts = a.n_steps < 65535;  // a tile is visited at most n_steps + 1 times
+  // a tile is visited at most n_steps + 1 times; NM_SIM_COUNTERS=32 forces the wide variant (tests)
+  const char *env_cnt = getenv("NM_SIM_COUNTERS");
+  const bool small_counts = a.n_steps < 65535 && !(env_cnt && env_cnt[0] == '3');
   const size_t cnt_bytes = small_counts ? sizeof(uint16_t) : sizeof(uint32_t);
   auto smem_for = [&](int th) {
     return 128 + 16 * kA + (size_t)th * (1 + 2 * kA) + (size_t)(5 + kA) * th * sizeof(double) + (size_t)nT * th * cnt_bytes +

@@ -40,9 +40,12 @@ def _random_params(rng, N):
             "Wm": u(0, 2, N), "Wnm": u(0, 2, N), "W_values": u(0, 10, N)}
 
 
-def test_golden_histories(cuda, golden_sim):
-    """The reference's own StandardExperiment.run histories (6 mice x 600 steps, 5 components)."""
+@pytest.mark.parametrize("counters", ["16", "32"])
+def test_golden_histories(cuda, golden_sim, counters, monkeypatch):
+    """The reference's own StandardExperiment.run histories (6 mice x 600 steps, 5 components), with both widths of
+    the kernel's visit counters (16 bits is what a run of fewer than 65 535 steps uses)."""
     from navigation_model_b200.batched_sim import BatchedExperiment
+    monkeypatch.setenv("NM_SIM_COUNTERS", counters)
     g = golden_sim
     maze = H.product_m9()
     names = [str(s) for s in g["param_names"]]

@@ -61,9 +61,15 @@ def main():
     S = sw.n_sessions
     ll_buf = torch.empty((S, min(args.chunk, n_loc)), dtype=torch.float64, device=dev)
     best_chunks = []
+    # untimed warm-up launch on a sliver of the shard (module load, function attributes, scratch allocation)
+    wn = min(n_loc, 896)
+    sw.argmin_device(sw.log_likelihood_device(a_t[:wn], b_t[:wn], g_t[:wn]))
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    from bench import ClockSampler  # NVML SM clock + throttle reasons while the sweep runs
+    sampler = ClockSampler(local)
+    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for c0 in range(0, n_loc, args.chunk):
@@ -74,6 +80,7 @@ def main():
         best_chunks.append((best, lo + c0))
     e1.record()
     torch.cuda.synchronize()
+    clocks = sampler.stop()
     dev_s = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=dev)
     # per-rank best over its chunks, then the cross-rank gather
     cand = [reduce_best(bst, off) if world == 1 else None for bst, off in best_chunks]
@@ -108,7 +115,7 @@ def main():
                           "updates_per_s": updates / float(dev_s.item()), "best_nll": best_v, "best_index": best_i,
                           "best_params": {"gamma": float(g[best_i]), "alpha": float(a[best_i]), "beta": float(b[best_i])},
                           "oracle_spot_check": {"n": int(len(chk)), "max_rel_err": max_rel},
-                          "stream_h2d_bytes": h2d, "host_stream_prep_s": prep_s}))
+                          "stream_h2d_bytes": h2d, "host_stream_prep_s": prep_s, "clocks_rank0": clocks}))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
