@@ -13,8 +13,12 @@
 //     (1) W[u] = Rhat[u] + gamma * V[u] once per state -- Q(u, a) depends on (u, a) only through next(u, a), so the
 //     S*A action values of a sweep are S distinct numbers, computed with exactly the oracle's two roundings;
 //     (2) V[u] = max over the available actions, in action order, of W[next(u, a)].  Unavailable actions point at
-//     the sentinel slot W[-1] = -inf, which the running compare-select never picks, so the pass is branch-free; V can
-//     be overwritten in place because pass 2 reads only W (the sweep stays synchronous / Jacobi).
+//     one of sixteen sentinel slots W[-16..-1] = -inf, which the running compare-select never picks, so the pass is
+//     branch-free; V can be overwritten in place because pass 2 reads only W (the sweep stays synchronous / Jacobi).
+//     Which sentinel: a 64-bit LDS is served per half-warp, conflict-free when its sixteen lanes touch sixteen
+//     different bank pairs (or the same address).  For every group of sixteen consecutive states and every action the
+//     prologue picks a sentinel whose bank pair none of the group's available actions uses, and all unavailable
+//     lanes of the group share it (a broadcast).  With a single sentinel 22 % of the wavefronts were conflicts.
 // The V / Rhat recurrences use _rn intrinsics (no FMA contraction): tables are bit-identical to the numpy oracle.
 #include <cuda_runtime.h>
 
@@ -23,6 +27,7 @@
 namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kSent = 16;  // sentinel slots in front of W (one per bank pair of a half-warp's 64-bit access)
 
 struct MbArgs {
   const nm_step_rec *records;
@@ -67,16 +72,27 @@ __global__ void __launch_bounds__(512) nm_mb_kernel(const MbArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int S = a.S, A = a.A;
   const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // rows[u] = eight u16 byte offsets into W: 8 * (next(u, a) + 1), or 0 (the sentinel slot) when unavailable
+  // rows[u] = eight u16 byte offsets into W: 8 * (next(u, a) + kSent), or 8 * t (sentinel slot t < kSent) when
+  // unavailable
   uint16_t *rows = reinterpret_cast<uint16_t *>(smem_raw);
   const size_t rows_bytes = (size_t)S * 16;
-  const size_t tab_doubles = (size_t)3 * S + 2;  // W[-1..S-1] (+1 pad keeps V 16-byte aligned) | V[S] | R[S]
+  const size_t tab_doubles = (size_t)3 * S + kSent;  // W[-kSent..S-1] | V[S] | R[S]
   double *tabs = reinterpret_cast<double *>(smem_raw + rows_bytes) + (size_t)warp * tab_doubles;
-  double *W = tabs, *V = tabs + S + 2, *R = tabs + 2 * S + 2;
-  for (int i = threadIdx.x; i < S * 8; i += blockDim.x) {
-    const int u = i >> 3, k = i & 7;
-    const int nu = k < A ? (int)a.next[u * A + k] : -1;
-    rows[i] = (uint16_t)(nu >= 0 ? 8 * (nu + 1) : 0);
+  double *W = tabs, *V = tabs + S + kSent, *R = tabs + 2 * S + kSent;
+  const int groups = (S + 15) >> 4;
+  for (int i = threadIdx.x; i < groups * 8; i += blockDim.x) {  // one (group of 16 states, action) per thread
+    const int u0 = (i >> 3) << 4, k = i & 7;
+    const int cnt = (S - u0 < 16) ? (S - u0) : 16;
+    unsigned used = 0u;
+    for (int j = 0; j < cnt; ++j) {
+      const int nu = k < A ? (int)a.next[(u0 + j) * A + k] : -1;
+      if (nu >= 0) used |= 1u << (nu & 15);  // bank pair of slot nu + kSent, relative to the table base
+    }
+    const int t = used == 0xffffu ? 0 : __ffs(~used) - 1;
+    for (int j = 0; j < cnt; ++j) {
+      const int nu = k < A ? (int)a.next[(u0 + j) * A + k] : -1;
+      rows[(u0 + j) * 8 + k] = (uint16_t)(8 * (nu >= 0 ? nu + kSent : t));
+    }
   }
 
   const int sess = blockIdx.y;
@@ -87,7 +103,7 @@ __global__ void __launch_bounds__(512) nm_mb_kernel(const MbArgs a) {
     V[u] = a.v_init ? a.v_init[a.tile_of_state[u]] : 0.0;
     R[u] = 0.0;
   }
-  if (lane == 0) W[0] = -INFINITY;
+  if (lane < kSent) W[lane] = -INFINITY;
   __syncthreads();
   const uint32_t w_base = (uint32_t)__cvta_generic_to_shared(W);
   const uint4 *rows4 = reinterpret_cast<const uint4 *>(rows);
@@ -101,7 +117,7 @@ __global__ void __launch_bounds__(512) nm_mb_kernel(const MbArgs a) {
     const double r = __hiloint2double((int)w0.y, (int)w0.x);
     const int s = (int)(w0.z & 0xffffu), s1 = (int)(w0.z >> 16);
     // ---- action values of the current state -------------------------------------------------------------
-    const int na = (lane < A) ? ((int)rows[s * 8 + lane] >> 3) - 1 : -1;
+    const int na = (lane < A) ? ((int)rows[s * 8 + lane] >> 3) - kSent : -1;
     const bool ok = na >= 0;
     const double q = ok ? __dadd_rn(R[na], __dmul_rn(gamma, V[na])) : 0.0;
     const unsigned avail = __ballot_sync(kFull, ok);
@@ -139,19 +155,19 @@ __global__ void __launch_bounds__(512) nm_mb_kernel(const MbArgs a) {
     __syncwarp();
     // ---- planning: n_sweeps synchronous value-iteration sweeps --------------------------------------------
     for (int sw = 0; sw < a.n_sweeps; ++sw) {
-      for (int u = lane; u < S; u += 32) W[u + 1] = __dadd_rn(R[u], __dmul_rn(gamma, V[u]));
+      for (int u = lane; u < S; u += 32) W[u + kSent] = __dadd_rn(R[u], __dmul_rn(gamma, V[u]));
       __syncwarp();
       int u = lane;
       for (; u + 32 < S; u += 64) {  // two states per trip: sixteen independent loads in flight
         const uint4 ra = rows4[u], rb = rows4[u + 32];
         const double ba = row_max(w_base, ra), bb = row_max(w_base, rb);
-        if (ra.x | ra.y | ra.z | ra.w) V[u] = ba;  // no available action: V[u] stays
-        if (rb.x | rb.y | rb.z | rb.w) V[u + 32] = bb;
+        if (ba != -INFINITY) V[u] = ba;  // no available action (every entry a sentinel): V[u] stays
+        if (bb != -INFINITY) V[u + 32] = bb;
       }
       if (u < S) {
         const uint4 ra = rows4[u];
         const double ba = row_max(w_base, ra);
-        if (ra.x | ra.y | ra.z | ra.w) V[u] = ba;
+        if (ba != -INFINITY) V[u] = ba;
       }
       __syncwarp();
     }
@@ -185,9 +201,10 @@ extern "C" int nm_modelbased_sweep(const nm_maze *mz, const nm_streams *st, cons
   if (P == 0) return NM_OK;
   if (cudaSetDevice(mz->device) != cudaSuccess) return nm_fail(NM_ERR_CUDA, "cudaSetDevice(%d) failed", mz->device);
   const int S = mz->num_states;
-  NM_CHECK_ARG(S < 8190, "nm_modelbased_sweep: at most 8189 states (16-bit byte offsets into the value table)");
+  NM_CHECK_ARG(S <= 8192 - kSent, "nm_modelbased_sweep: at most %d states (16-bit byte offsets into the value table)",
+               8192 - kSent);
   const size_t rows_bytes = (size_t)S * 16;
-  const size_t per_warp = ((size_t)3 * S + 2) * sizeof(double);
+  const size_t per_warp = ((size_t)3 * S + kSent) * sizeof(double);
   // CTAs per SM x warps per CTA: as many resident warps as 227 KB of shared memory (1 KB reserved per CTA) allow
   int warps = 0, best_total = 0;
   for (int ctas = 1; ctas <= 8; ++ctas) {
