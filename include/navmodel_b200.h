@@ -342,6 +342,21 @@ int nm_modelbased_sweep(const nm_maze *mz, const nm_streams *st, const int16_t *
                         const double *d_v_init, double *d_ll_out, double *d_v_out, double *d_r_out, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Tabular Q-learning agent with an explicit Q[s,a] table (EXTENSION, parity unpinned: the reference's learners keep
+ * state values only, simulation/rl.py:154-262)
+ * ---------------------------------------------------------------------------------------------- */
+/* Eight lanes = one parameter set, lane k = action k.  Per step (s -> s1, r) whose observed action
+ * a = first a with next[s,a] == s1 exists (other steps are skipped): the softmax log-likelihood
+ * (exploration_model.py:84-93) of a under beta * Q[s, available actions], evaluated before the update, then
+ * Q[s,a] += alpha * (r + gamma * max_{a' available at s1} Q[s1,a'] - Q[s,a])  (update form of rl.py:184-187;
+ * bootstrap 0 when s1 has no available action).  Replay records update Q only.
+ *   d_next: int16[num_states, n_actions] as for nm_modelbased_sweep; the streams only need s, s1, r.
+ *   d_q_init: [X*Y, n_actions] shared or NULL (zeros);  d_ll_out: [S, P];  d_q_out: [S, P, X*Y, n_actions] or NULL. */
+int nm_qtable_sweep(const nm_maze *mz, const nm_streams *st, const int16_t *d_next, int n_actions,
+                    const double *d_alpha, const double *d_beta, const double *d_gamma, int64_t P,
+                    const double *d_q_init, double *d_ll_out, double *d_q_out, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Batched distances between per-mouse metric results and data metrics (analysis/statistics.py:10-103)
  * ---------------------------------------------------------------------------------------------- */
 #define NM_DIST_NORMALIZED 0 /* normalized_distance  statistics.py:67-92  */

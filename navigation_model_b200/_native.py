@@ -64,6 +64,7 @@ SIGNATURES = {
     "nm_argmin_nll": (C.c_int, [_p, C.c_int, _i64, _p, _p, _p]),
     "nm_fp64_peak_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, _p, C.POINTER(_i64), _p]),
     "nm_modelbased_sweep": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, _p, _p, _p, _i64, _p, _p, _p, _p, _p]),
+    "nm_qtable_sweep": (C.c_int, [_p, _p, _p, C.c_int, _p, _p, _p, _i64, _p, _p, _p, _p]),
     "nm_distance_rows": (C.c_int, [C.c_int, _p, _p, _i64, C.c_int, _p, _p]),
     "nm_simulate": (C.c_int, [_p, _p, _p]),
     "nm_maze_movements_possible_device": (C.c_int, [_p, _p, _i64, _p, _p]),

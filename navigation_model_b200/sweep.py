@@ -535,24 +535,20 @@ def vtable_single(maze, alg, records, n_online, alpha, gamma, v_init):
     return sw.v_tables([alpha], [gamma], v_init=v_init)[0, 0]
 
 
-class ModelBasedSweep:
-    """Grid sweep of the model-based agent (EXTENSION -- the reference has no model-based agent; semantics in
-    DESIGN.md section 2): learned reward model + ``n_sweeps`` value-iteration sweeps per observed step on the maze's
-    transition table, softmax likelihood of the observed tile steps.  One warp per parameter set.
+class _TileActionSweep:
+    """Shared host side of the two tile-action agents (model-based, Q-table): actions are tile displacements, the
+    transition model ``next[s, a]`` is the maze's own geometry (``Maze.is_movement_possible``, ``maze.py:512-527``),
+    the session streams only carry ``(s, s1, r)``."""
 
-    >>> mb = ModelBasedSweep(maze, [(dx, dy) for dx in (-1, 0, 1) for dy in (-1, 0, 1) if (dx, dy) != (0, 0)])
-    >>> mb.add_session(trajectory, reward)
-    >>> ll = mb.log_likelihood(alpha, beta, gamma)      # float64[S, P]
-    """
-
-    def __init__(self, maze, discrete_actions, n_sweeps=1, device=None):
+    def __init__(self, maze, discrete_actions, device=None, replay_n_times=0, replay_seed=None):
         self.maze = maze
         self.discrete_actions = np.asarray(discrete_actions, dtype=np.int64).reshape(-1, 2)
         if not 1 <= len(self.discrete_actions) <= _native.NM_MAX_CAND:
             raise ValueError(f"between 1 and {_native.NM_MAX_CAND} discrete actions are supported")
-        self.n_sweeps = int(n_sweeps)
         self.next_table = np.ascontiguousarray(maze.transition_table(self.discrete_actions), dtype=np.int16)
-        self._base = ConditioningSweep(maze, "td0", device=device)  # session streams: s, s1, r only
+        # session streams: s, s1, r only
+        self._base = ConditioningSweep(maze, "td0", device=device, replay_n_times=replay_n_times,
+                                       replay_seed=replay_seed)
         self.last_kernel_ms = None
 
     def add_session(self, trajectory, reward):
@@ -566,18 +562,84 @@ class ModelBasedSweep:
     def updates_per_parameter_set(self):
         return self._base.updates_per_parameter_set
 
-    def log_likelihood(self, alpha, beta, gamma, v_init=None, return_tables=False):
-        """``float64[S, P]`` log-likelihoods (and, optionally, the final ``V`` and ``Rhat`` tables ``[S, P, X, Y]``)."""
-        b = self._base
-        torch = b._ensure_device()
+    @staticmethod
+    def _params(alpha, beta, gamma):
         alpha, beta, gamma = _as_param(alpha), _as_param(beta), _as_param(gamma)
         P = max(alpha.size, beta.size, gamma.size)
         alpha, beta, gamma = _as_param(alpha, P), _as_param(beta, P), _as_param(gamma, P)
         if not (alpha.size == beta.size == gamma.size == P):
             raise ValueError("alpha, beta and gamma must have the same length")
+        return alpha, beta, gamma, P
+
+    def _timed(self, torch, launch):
+        """Run ``launch()`` (one C-ABI call) between two CUDA events on the current stream."""
+        with torch.cuda.device(self._base.torch_device):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _native.check(launch())
+            e1.record()
+            torch.cuda.current_stream().synchronize()
+            self.last_kernel_ms = e0.elapsed_time(e1)
+
+    def log_likelihood_device(self, alpha_t, beta_t, gamma_t):
+        raise NotImplementedError
+
+    def best_fit(self, alpha, beta, gamma, group=None):
+        """Grid search like :meth:`ConditioningSweep.best_fit`: the flat parameter index is sharded over the ranks of
+        an initialised process group, 16 bytes per rank are all-gathered.  ``(best_nll, best_index)``."""
+        b = self._base
+        torch = b._ensure_device()
+        import torch.distributed as dist
+        alpha, beta, gamma, P = self._params(alpha, beta, gamma)
+        rank, world = 0, 1
+        if dist.is_available() and dist.is_initialized():
+            rank, world = dist.get_rank(group), dist.get_world_size(group)
+        lo, hi = shard_bounds(P, rank, world)
+        if hi > lo:
+            ll = self.log_likelihood_device(*(b._to_dev(torch, x[lo:hi]) for x in (alpha, beta, gamma)))
+            best = b.argmin_device(ll)
+        else:
+            best = torch.tensor([float("nan"), 0.0], dtype=torch.float64, device=b.torch_device)
+            best[1:].view(torch.int64).fill_(-1)
+        return reduce_best(best, lo, group=group)
+
+
+class ModelBasedSweep(_TileActionSweep):
+    """Grid sweep of the model-based agent (EXTENSION -- the reference has no model-based agent; semantics in
+    DESIGN.md section 2): learned reward model + ``n_sweeps`` value-iteration sweeps per observed step on the maze's
+    transition table, softmax likelihood of the observed tile steps.  One warp per parameter set.
+
+    >>> mb = ModelBasedSweep(maze, [(dx, dy) for dx in (-1, 0, 1) for dy in (-1, 0, 1) if (dx, dy) != (0, 0)])
+    >>> mb.add_session(trajectory, reward)
+    >>> ll = mb.log_likelihood(alpha, beta, gamma)      # float64[S, P]
+    """
+
+    def __init__(self, maze, discrete_actions, n_sweeps=1, device=None):
+        super().__init__(maze, discrete_actions, device=device)
+        self.n_sweeps = int(n_sweeps)
+
+    def log_likelihood_device(self, alpha_t, beta_t, gamma_t, v_init_t=None, ll_out=None, v_out=None, r_out=None):
+        b = self._base
+        torch = b._ensure_device()
+        dev = b.torch_device
+        P = int(alpha_t.numel())
+        nxt = torch.from_numpy(self.next_table).to(dev)
+        if ll_out is None:
+            ll_out = torch.empty((b.n_sessions, P), dtype=torch.float64, device=dev)
+        self._timed(torch, lambda: b._dmaze._lib.nm_modelbased_sweep(
+            b._dmaze.handle, b._dstreams.handle, _native.tensor_ptr(nxt), self.next_table.shape[1], self.n_sweeps,
+            _native.tensor_ptr(alpha_t), _native.tensor_ptr(beta_t), _native.tensor_ptr(gamma_t), P,
+            _native.tensor_ptr(v_init_t), _native.tensor_ptr(ll_out), _native.tensor_ptr(v_out),
+            _native.tensor_ptr(r_out), _native.cuda_stream_ptr()))  # last_kernel_ms: device time of nm_mb_kernel
+        return ll_out
+
+    def log_likelihood(self, alpha, beta, gamma, v_init=None, return_tables=False):
+        """``float64[S, P]`` log-likelihoods (and, optionally, the final ``V`` and ``Rhat`` tables ``[S, P, X, Y]``)."""
+        b = self._base
+        torch = b._ensure_device()
+        alpha, beta, gamma, P = self._params(alpha, beta, gamma)
         dev = b.torch_device
         X, Y = self.maze.shape
-        nxt = torch.from_numpy(self.next_table).to(dev)
         vi = None
         if v_init is not None:
             v = np.asarray(v_init, dtype=np.float64)
@@ -585,23 +647,63 @@ class ModelBasedSweep:
                 raise ValueError(f"v_init must have shape {(X, Y)}")
             vi = torch.from_numpy(np.ascontiguousarray(v).reshape(-1)).to(dev)
         S = b.n_sessions
-        ll = torch.empty((S, P), dtype=torch.float64, device=dev)
         v_out = r_out = None
         if return_tables:
             v_out = torch.empty((S, P, X * Y), dtype=torch.float64, device=dev)
             r_out = torch.empty((S, P, X * Y), dtype=torch.float64, device=dev)
         at, bt, gt = (b._to_dev(torch, x) for x in (alpha, beta, gamma))
-        with torch.cuda.device(dev):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            _native.check(b._dmaze._lib.nm_modelbased_sweep(
-                b._dmaze.handle, b._dstreams.handle, _native.tensor_ptr(nxt), self.next_table.shape[1], self.n_sweeps,
-                _native.tensor_ptr(at), _native.tensor_ptr(bt), _native.tensor_ptr(gt), P, _native.tensor_ptr(vi),
-                _native.tensor_ptr(ll), _native.tensor_ptr(v_out), _native.tensor_ptr(r_out),
-                _native.cuda_stream_ptr()))
-            e1.record()
-            torch.cuda.current_stream().synchronize()
-            self.last_kernel_ms = e0.elapsed_time(e1)  # device time of nm_mb_kernel (CUDA events)
+        ll = self.log_likelihood_device(at, bt, gt, vi, v_out=v_out, r_out=r_out)
         if return_tables:
             return (ll.cpu().numpy(), v_out.cpu().numpy().reshape(S, P, X, Y), r_out.cpu().numpy().reshape(S, P, X, Y))
+        return ll.cpu().numpy()
+
+
+class QLearningSweep(_TileActionSweep):
+    """Grid sweep of a tabular Q-learning agent with an explicit ``Q[s, a]`` table (EXTENSION -- the reference's
+    learners keep state values only, ``rl.py:154-262``; semantics in DESIGN.md section 2): softmax likelihood of the
+    observed tile steps under ``beta * Q[s, .]`` and the update ``Q[s,a] += alpha * (r + gamma * max_a' Q[s1,a'] -
+    Q[s,a])``.  Eight lanes per parameter set, the table in shared memory.  ``replay_n_times`` shuffled replay passes
+    (``ShuffledReplays``, ``rl.py:419-424``) update ``Q`` after the online pass.
+
+    >>> ql = QLearningSweep(maze, [(dx, dy) for dx in (-1, 0, 1) for dy in (-1, 0, 1) if (dx, dy) != (0, 0)])
+    >>> ql.add_session(trajectory, reward)
+    >>> ll = ql.log_likelihood(alpha, beta, gamma)      # float64[S, P]
+    """
+
+    def log_likelihood_device(self, alpha_t, beta_t, gamma_t, q_init_t=None, ll_out=None, q_out=None):
+        b = self._base
+        torch = b._ensure_device()
+        dev = b.torch_device
+        P = int(alpha_t.numel())
+        nxt = torch.from_numpy(self.next_table).to(dev)
+        if ll_out is None:
+            ll_out = torch.empty((b.n_sessions, P), dtype=torch.float64, device=dev)
+        self._timed(torch, lambda: b._dmaze._lib.nm_qtable_sweep(
+            b._dmaze.handle, b._dstreams.handle, _native.tensor_ptr(nxt), self.next_table.shape[1],
+            _native.tensor_ptr(alpha_t), _native.tensor_ptr(beta_t), _native.tensor_ptr(gamma_t), P,
+            _native.tensor_ptr(q_init_t), _native.tensor_ptr(ll_out), _native.tensor_ptr(q_out),
+            _native.cuda_stream_ptr()))  # last_kernel_ms: device time of nm_q_kernel
+        return ll_out
+
+    def log_likelihood(self, alpha, beta, gamma, q_init=None, return_tables=False):
+        """``float64[S, P]`` log-likelihoods (and, optionally, the final tables ``Q[S, P, X, Y, A]``; entries of
+        non-visitable tiles and unavailable actions keep their initial value)."""
+        b = self._base
+        torch = b._ensure_device()
+        alpha, beta, gamma, P = self._params(alpha, beta, gamma)
+        dev = b.torch_device
+        X, Y = self.maze.shape
+        A = self.next_table.shape[1]
+        qi = None
+        if q_init is not None:
+            q = np.asarray(q_init, dtype=np.float64)
+            if q.shape != (X, Y, A):
+                raise ValueError(f"q_init must have shape {(X, Y, A)}")
+            qi = torch.from_numpy(np.ascontiguousarray(q).reshape(-1)).to(dev)
+        S = b.n_sessions
+        q_out = torch.empty((S, P, X * Y * A), dtype=torch.float64, device=dev) if return_tables else None
+        at, bt, gt = (b._to_dev(torch, x) for x in (alpha, beta, gamma))
+        ll = self.log_likelihood_device(at, bt, gt, qi, q_out=q_out)
+        if return_tables:
+            return ll.cpu().numpy(), q_out.cpu().numpy().reshape(S, P, X, Y, A)
         return ll.cpu().numpy()

@@ -489,6 +489,49 @@ def run_model_based(tr, nxt, alpha, beta, gamma, n_sweeps=1, v0=None):
     return V, R, ll
 
 
+def run_q_learning(tr, nxt, alpha, beta, gamma, q0=None, orders=()):
+    """Tabular Q-learning on an explicit Q[s, a] table + softmax likelihood (EXTENSION; the
+    reference's learners keep state values only -- the update is PositiveConditioning's max-backup, rl.py:184-187,
+    moved to state-action values; the softmax is exploration_model.py:84-93).
+
+    Per step (s -> s1, reward r), a = first action with next(s, a) == s1 (steps without one are skipped):
+      logp    = softmax(beta * Q[s, available actions])[a]        (log space, Q before the update; online pass only)
+      Q[s, a] += alpha * (r + gamma * max_{a' available at s1} Q[s1, a'] - Q[s, a])     (bootstrap 0 if none)
+    :param orders: replay index orders (see :func:`replay_orders`): update-only passes after the online pass
+    :return: (Q[S, A], ll)
+    """
+    S, A = nxt.shape
+    Q = np.zeros((S, A)) if q0 is None else np.array(q0, dtype=np.float64).reshape(S, A)
+    ll = 0.0
+    steps = list(zip(tr["s"].tolist(), tr["s1"].tolist(), tr["r"].tolist()))
+    acts_of = [[a for a in range(A) if nxt[s, a] >= 0] for s in range(S)]
+
+    def one(step, online):
+        nonlocal ll
+        s, s1, r = step
+        acts = acts_of[s]
+        obs = next((j for j, a in enumerate(acts) if nxt[s, a] == s1), None)
+        if obs is None:
+            return
+        if online:
+            val = [beta * float(Q[s, a]) for a in acts]
+            m = max(val)
+            val = [v - m for v in val]
+            ll = ll + (val[obs] - math.log(np_sum([math.exp(v) for v in val])))
+        boot = max(float(Q[s1, a]) for a in acts_of[s1]) if acts_of[s1] else 0.0
+        a = acts[obs]
+        q = float(Q[s, a])
+        rpe = r + gamma * boot - q
+        Q[s, a] = q + alpha * rpe
+
+    for step in steps:
+        one(step, True)
+    for order in orders:
+        for i in order.tolist():
+            one(steps[i], False)
+    return Q, ll
+
+
 # ================================================================================= distances
 # Restatement of analysis/statistics.py (pinned by the reference's test/test_statistics.py and test_fitness.py).
 def normalized_distance(h1, h2):  # statistics.py:67-92
