@@ -204,16 +204,17 @@ def workload_config(args, n_gpus, p_per_rank):
 
 
 def other_paths(local, world, rank, dist, dev):
-    """The two other kernels of the hot path, measured the same way (per-rank shard of fixed size, device time as the
+    """The other kernels of the hot path, measured the same way (per-rank shard of fixed size, device time as the
     max over ranks): forward simulation (BASELINE configs[4] shape, scaled to 909 312 mice x 1 000 steps per GPU, all
     five components, device-seeded PCG64 streams, fused metrics) and the model-based agent (configs[3] shape: 400-state
-    maze, 8 actions, 20 000 parameter sets x 1 000 steps per GPU, one value-iteration sweep per step).  Reported under
+    maze, 8 actions, 20 000 parameter sets x 1 000 steps per GPU, one value-iteration sweep per step) and the Q-table agent
+    (the configs[1] grid and session).  Reported under
     ``also_measured``; the headline metric stays the fitness grid sweep."""
     import torch
     from navigation_model_b200.batched_sim import BatchedExperiment
     from navigation_model_b200.simulation import behavioural_components as bc
     from navigation_model_b200.simulation.maze import Maze
-    from navigation_model_b200.sweep import ModelBasedSweep
+    from navigation_model_b200.sweep import ModelBasedSweep, QLearningSweep, parameter_grid
     from oracle import np_oracle as O  # maze layout / seeded session recipe only (inputs)
 
     def max_over_ranks(x):
@@ -280,6 +281,26 @@ def other_paths(local, world, rank, dist, dev):
         "state_action_backups_per_s": upd * 400 * 8 / k,
         "workload": f"{Pm} parameter sets x {mb.updates_per_parameter_set} steps per GPU, 400-state maze, 8 actions, "
                     "1 value-iteration sweep per step (extension: parity against this repo's numpy oracle only)"}
+    # ---- Q-table agent ------------------------------------------------------------------------------------
+    traj9, rew9 = O.synthetic_session(O.OracleMaze(O.M9_LAYOUT, O.M9_SIZE_TILE), 0, T_STEPS)
+    aq, bq, gq = parameter_grid(np.linspace(0.01, 1, 64), np.logspace(-1, 1.5, 64), np.linspace(0.5, 0.99, 32))
+    ql = QLearningSweep(maze, acts, device=local)
+    ql.add_session(traj9, rew9)
+    k_ms, e2e_s = [], []
+    for rep in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ql.log_likelihood(aq, bq, gq)
+        e2e_s.append(time.perf_counter() - t0)
+        k_ms.append(ql.last_kernel_ms)
+    k = max_over_ranks(min(k_ms[1:])) * 1e-3
+    e = max_over_ranks(min(e2e_s[1:]))
+    upd = world * aq.size * ql.updates_per_parameter_set
+    out["q_table"] = {
+        "metric": "agent-trial updates/s", "value": upd / k, "e2e_value": upd / e, "kernel_ms": k * 1e3,
+        "workload": f"{aq.size} parameter sets (the configs[1] grid) x {ql.updates_per_parameter_set} steps per GPU, "
+                    "9x9 maze, 8 tile actions, explicit Q[s,a] table in shared memory (extension: parity against this "
+                    "repo's numpy oracle only)"}
     return out
 
 

@@ -43,12 +43,15 @@ struct QArgs {
 
 __device__ __forceinline__ double dmax2(double a, double b) { return (b > a) ? b : a; }
 
-// max over the eight lanes of an octet; every lane receives it
-__device__ __forceinline__ double octet_max(double v) {
-  v = dmax2(v, __shfl_xor_sync(kFull, v, 1));
-  v = dmax2(v, __shfl_xor_sync(kFull, v, 2));
-  v = dmax2(v, __shfl_xor_sync(kFull, v, 4));
-  return v;
+// max over the eight lanes of an octet, for two independent values at once (the two butterfly chains are interleaved
+// by hand: each level issues its four shuffles before the first compare); every lane receives both maxima
+__device__ __forceinline__ void octet_max2(double &a, double &b) {
+#pragma unroll
+  for (int off = 1; off < 8; off <<= 1) {
+    const double a2 = __shfl_xor_sync(kFull, a, off), b2 = __shfl_xor_sync(kFull, b, off);
+    a = dmax2(a, a2);
+    b = dmax2(b, b2);
+  }
 }
 
 __global__ void __launch_bounds__(512) nm_q_kernel(const QArgs a) {
@@ -79,45 +82,71 @@ __global__ void __launch_bounds__(512) nm_q_kernel(const QArgs a) {
   const int64_t n = a.offsets[sess + 1] - rec0, n_on = a.online[sess];
   const uint4 *recs = reinterpret_cast<const uint4 *>(a.records + rec0);
   double ll = 0.0, acc_obs = 0.0, prod = 1.0;
-  for (int64_t i = 0; i < n; ++i) {
-    const uint4 w0 = __ldg(recs + 2 * i);  // warp-uniform address: one broadcast transaction
-    const int s = (int)(w0.z & 0xffffu), s1 = (int)(w0.z >> 16);
-    const int nk = nxt8[s * 8 + k], n1 = nxt8[s1 * 8 + k];
-    const bool ok = nk >= 0, ok1 = n1 >= 0;
-    const unsigned avail = __ballot_sync(kFull, ok) & 0xffu;  // the four octets agree: octet 0's answer
-    const unsigned hit = __ballot_sync(kFull, ok && nk == s1) & 0xffu;
-    if (hit) {  // warp-uniform
-      const int a_obs = __ffs(hit) - 1;
-      const double r = __hiloint2double((int)w0.y, (int)w0.x);
-      const double q = Q[s * 8 + k], q1 = Q[s1 * 8 + k];
-      const unsigned avail1 = __ballot_sync(kFull, ok1) & 0xffu;
-      const double boot = avail1 ? octet_max(ok1 ? q1 : -INFINITY) : 0.0;
-      if (i < n_on) {
-        const double z = __dmul_rn(beta, q);  // exploration_model.py:87
-        const double m = octet_max(ok ? z : -INFINITY);
+  // Everything a step needs besides Q -- the record, the action sets of s and s1, the observed action -- does not
+  // depend on the parameters: it is fetched and decoded one (action sets) and two (record) steps ahead, so that the
+  // only latency left in a step is the Q-dependent chain.
+  struct Step {
+    int s, s1;
+    double r;
+    unsigned avail, hit, avail1;
+    bool ok, ok1;
+  };
+  auto fetch = [&](int64_t i) -> uint4 { return i < n ? __ldg(recs + 2 * i) : make_uint4(0u, 0u, 0u, 0u); };
+  auto decode = [&](const uint4 w0) -> Step {
+    Step d;
+    d.s = (int)(w0.z & 0xffffu);
+    d.s1 = (int)(w0.z >> 16);
+    d.r = __hiloint2double((int)w0.y, (int)w0.x);
+    const int nk = nxt8[d.s * 8 + k], n1 = nxt8[d.s1 * 8 + k];
+    d.ok = nk >= 0;
+    d.ok1 = n1 >= 0;
+    d.avail = __ballot_sync(kFull, d.ok) & 0xffu;  // the four octets agree: octet 0's answer
+    d.hit = __ballot_sync(kFull, d.ok && nk == d.s1) & 0xffu;
+    d.avail1 = __ballot_sync(kFull, d.ok1) & 0xffu;
+    return d;
+  };
+  uint4 w_next = fetch(1);
+  Step cur = decode(fetch(0));
+  const int n32 = (int)n, n_on32 = (int)(n_on < n ? n_on : n);  // n < 2^31 (checked on the host)
+  for (int i = 0; i < n32; ++i) {
+    const Step st = cur;
+    cur = decode(w_next);  // step i + 1 (an all-zero record past the end: state 0, harmless)
+    w_next = fetch(i + 2);
+    if (st.hit) {  // warp-uniform; a step without an observed action is skipped entirely
+      const int a_obs = __ffs(st.hit) - 1;
+      double *row = Q + st.s * 8 + k;
+      const double q = *row, q1 = Q[st.s1 * 8 + k];
+      const double z = __dmul_rn(beta, q);  // exploration_model.py:87
+      double boot = st.ok1 ? q1 : -INFINITY, m = st.ok ? z : -INFINITY;
+      octet_max2(boot, m);
+      if (!st.avail1) boot = 0.0;
+      if (i < n_on32) {
         const double zc = __dsub_rn(z, m);  // :92
-        const double e = ok ? er.exp_nonpos(dmax2(zc, -800.0)) : 0.0;  // :93
+        const double e = st.ok ? er.exp_nonpos(dmax2(zc, -800.0)) : 0.0;  // :93
+        // every lane gathers the octet's eight terms (sixteen independent shuffles), then adds them in numpy's order:
+        // pairwise for n == 8, else sequentially from 0.0 over the available actions -- an unavailable action's term
+        // is +0.0, and x + 0.0 == x bit for bit for the non-negative partial sums, so nothing needs to be skipped
+        double ev[8];
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) ev[kk] = __shfl_sync(kFull, e, kk, 8);
         double sum;
-        if (avail == 0xffu) {  // numpy pairwise sum, n == 8
-          double t = __dadd_rn(e, __shfl_xor_sync(kFull, e, 1));
-          t = __dadd_rn(t, __shfl_xor_sync(kFull, t, 2));
-          sum = __dadd_rn(__shfl_sync(kFull, t, 0, 8), __shfl_sync(kFull, t, 4, 8));
-        } else {  // n < 8: sequential from 0.0 over the available actions in order
+        if (st.avail == 0xffu) {
+          sum = __dadd_rn(__dadd_rn(__dadd_rn(ev[0], ev[1]), __dadd_rn(ev[2], ev[3])),
+                          __dadd_rn(__dadd_rn(ev[4], ev[5]), __dadd_rn(ev[6], ev[7])));
+        } else {
           sum = 0.0;
-          for (int kk = 0; kk < A; ++kk) {
-            const double ek = __shfl_sync(kFull, e, kk, 8);
-            if ((avail >> kk) & 1u) sum = __dadd_rn(sum, ek);
-          }
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) sum = __dadd_rn(sum, ev[kk]);
         }
         acc_obs = __dadd_rn(acc_obs, __shfl_sync(kFull, zc, a_obs, 8));
         prod = __dmul_rn(prod, sum);
       }
       if (k == a_obs) {
-        const double rpe = __dsub_rn(__dadd_rn(r, __dmul_rn(gamma, boot)), q);  // update form of rl.py:185
-        Q[s * 8 + k] = __dadd_rn(q, __dmul_rn(alpha, rpe));                      // rl.py:186-187
+        const double rpe = __dsub_rn(__dadd_rn(st.r, __dmul_rn(gamma, boot)), q);  // update form of rl.py:185
+        *row = __dadd_rn(q, __dmul_rn(alpha, rpe));                                 // rl.py:186-187
       }
     }
-    if ((i & 31) == 31 || i + 1 == n) {  // fold: at most 32 sums, each in [1, 8] -> prod <= 2^96
+    if ((i & 31) == 31 || i + 1 == n32) {  // fold: at most 32 sums, each in [1, 8] -> prod <= 2^96
       ll = __dadd_rn(ll, __dsub_rn(acc_obs, log(prod)));
       acc_obs = 0.0;
       prod = 1.0;
@@ -146,6 +175,8 @@ extern "C" int nm_qtable_sweep(const nm_maze *mz, const nm_streams *st, const in
   NM_CHECK_ARG(n_actions >= 1 && n_actions <= NM_MAX_CAND, "nm_qtable_sweep: need 1..%d actions", NM_MAX_CAND);
   NM_CHECK_ARG(P >= 0 && (P == 0 || (d_alpha && d_beta && d_gamma && d_ll_out)), "nm_qtable_sweep: NULL array");
   NM_CHECK_ARG(st->S <= 65535, "nm_qtable_sweep: at most 65535 sessions per call");
+  for (int i = 0; i < st->S; ++i)
+    NM_CHECK_ARG(st->offsets[i + 1] - st->offsets[i] < 2147483647LL, "nm_qtable_sweep: session %d is too long", i);
   if (P == 0) return NM_OK;
   if (cudaSetDevice(mz->device) != cudaSuccess) return nm_fail(NM_ERR_CUDA, "cudaSetDevice(%d) failed", mz->device);
   const int S = mz->num_states;
