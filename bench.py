@@ -169,7 +169,8 @@ def run_reference(args):
     from oracle import np_oracle as O
     from oracle import c_oracle as CO
     alg_code = {"td0": 0, "positive": 1, "negative": 2}[args.alg]
-    omz, traj, rew, a, b, g = make_workload(1)
+    world = max(1, int(args.gpus))
+    omz, traj, rew, a, b, g = make_workload(world)  # the whole job's grid: the sample is drawn from all of it
     tr = O.extract_transitions(omz, traj, rew, O.OracleMouse(traj[0], 0.0, O.A8_UNITS * O.M9_SIZE_TILE))
     n = len(tr["s"])
     P_s = 4096
@@ -186,7 +187,7 @@ def run_reference(args):
             "unit": "updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, 1, P_s),
+            "config": workload_config(args, world, len(a) // world),  # the product arm's config, word for word
             "cpu_baseline": {"value": value, "unit": "updates/s", "cores": cores, "kind": "port",
                              "sample": f"{P_s} of {len(a)} parameter sets (evenly spaced) x {n} steps per step"},
             "e2e": {"value": value, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
