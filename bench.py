@@ -125,20 +125,28 @@ def measured_hbm_peak():
         return 6650.0  # fallback stated in B200_PROFILING.md
 
 
-def ncu_dram_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the fit kernel, per launch, from the committed
-    `ncu --set full` capture of the same command (profiles/); None if the summary is missing."""
-    path = os.path.join(ROOT, "profiles", "r01_v3_fit_kernel_ncu.txt")
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "r01_v9_fit_kernel_ncu.txt")
+
+
+def ncu_counter(prefixes, scale_units=False):
+    """Sum of the counters whose line starts with one of `prefixes` in the committed `ncu --set full` summary of the
+    dominant kernel (same command, profiles/); None if the summary is missing."""
     try:
-        total = 0.0
-        for line in open(path):
-            if line.startswith("dram__bytes_read.sum [") or line.startswith("dram__bytes_write.sum ["):
+        total, seen = 0.0, False
+        for line in open(NCU_SUMMARY):
+            if any(line.startswith(p + " [") for p in prefixes):
                 unit = line.split("[")[1].split("]")[0]
                 val = float(line.split("=")[1])
-                total += val * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
-        return total or None
+                total += val * ({"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit] if scale_units else 1.0)
+                seen = True
+        return total if seen else None
     except Exception:
         return None
+
+
+def ncu_dram_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the fit kernel, per launch."""
+    return ncu_counter(["dram__bytes_read.sum", "dram__bytes_write.sum"], scale_units=True)
 
 
 def cpu_port_rate(records_tr, alg_code, a, b, g, seconds, threads=0):
@@ -374,6 +382,7 @@ def run_b200(args):
     barrier()
     wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
+    sweep_mode = sw.last_sweep_mode()  # which fit kernel the device picked (reads one word; after the timed region)
     step_ms = np.array([e[0].elapsed_time(e[2]) for e in ev])
     kern_ms = np.array([e[0].elapsed_time(e[1]) for e in ev])
     total_ms = torch.tensor([step_ms.sum()], dtype=torch.float64, device=dev)
@@ -441,8 +450,19 @@ def run_b200(args):
         alg_bytes = n_upd * 32 + P * 32  # stream once + (alpha, beta, gamma, ll) per parameter set
         roofline = {"bound": "fp64_issue", "achieved": achieved, "peak": peak_ginstr, "unit": "GInstr/s",
                     "frac": achieved / peak_ginstr, "traffic": ncu_dram_traffic(),
-                    "kernel": f"nm_fit_exact_kernel<{args.alg}, loglik>",
+                    "kernel": {2: f"nm_fit_group_kernel<{args.alg}, 2 parameter sets per lane>",
+                               1: f"nm_fit_group_kernel<{args.alg}, 1 parameter set per lane>"}.get(
+                                   sweep_mode, f"nm_fit_exact_kernel<{args.alg}, loglik>"),
                     "kernel_ms": float(kern_ms.mean()),
+                    "kernel_ms_covers": "the whole nm_loglik_sweep call: the dominant kernel + 5 launches of a few "
+                                        "microseconds (run detection, the two kernels that stand down)",
+                    "frac_note": "achieved counts the CANONICAL FP64 instructions of SURVEY 8d (exp = 20, log = 30); the "
+                                 "kernel executes fewer (table-driven exp = 12, one log per 32 steps), so the canonical "
+                                 "fraction can pass 1 -- the executed fraction is fp64_pipe_busy_ncu",
+                    "fp64_pipe_busy_ncu": (lambda v: None if v is None else v / 100.0)(
+                        ncu_counter(["sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"])),
+                    "issue_slots_busy_ncu": (lambda v: None if v is None else v / 100.0)(
+                        ncu_counter(["smsp__issue_active.avg.pct_of_peak_sustained_active"])),
                     "peak_source": "nm_fp64_peak_probe (8 independent DFMA chains/thread) timed live, burst; "
                                    "MEASURED_PEAKS.json has no FP64 figure",
                     "alg_fp64_instr_per_update": alg_instr / (P * n_upd),
@@ -465,11 +485,11 @@ def run_b200(args):
                         "step_ms_min_median_max": [float(np.min(e2e_step_ms)), float(np.median(e2e_step_ms)),
                                                    float(np.max(e2e_step_ms))],
                         "slowest_step_index": int(np.argmax(e2e_step_ms))},
-                "gpu_launches": 3 * args.steps, "clocks": clocks, "wall_s": wall,
+                "gpu_launches": (4 if os.environ.get("NM_FIT_GROUP") == "0" else 8) * args.steps, "clocks": clocks, "wall_s": wall,
                 "target_updates_per_s_8gpu": 1e10}
         if extras is not None:
             line["also_measured"] = extras
-            line["gpu_launches"] += 6
+            line["gpu_launches"] += 9
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -221,6 +221,13 @@ int nm_loglik_sweep(int alg, const nm_maze *mz, const nm_streams *st, const doub
                     const double *d_beta, const double *d_gamma, int64_t P, const double *d_v_init,
                     int v_init_per_unit, double *d_ll_out, double *d_v_out, void *stream);
 
+/* Which kernel the last nm_loglik_sweep on `stream` (current device) used: 0 = one value table per parameter set,
+ * 1 / 2 = one table per warp shared by aligned runs of 32 / 64 consecutive parameter sets with equal (alpha, gamma)
+ * -- the device checks the arrays itself, so a Cartesian grid whose beta axis varies fastest takes the shared path
+ * without any hint (results are bit-identical either way; NM_FIT_GROUP=0 forces 0).  Synchronises the stream:
+ * diagnostics and tests only. */
+int nm_loglik_sweep_mode(void *stream, int *mode_out);
+
 /* Per-shard best fit: nll[p] = -(sum_s ll[s, p]) (sessions added in index order), then the minimum and
  * the LOWEST index attaining it (numpy argmin).  NaN entries are skipped; if all are NaN idx = -1.
  *   d_nll_out: [P] or NULL;  d_best_out: {double best_nll; int64 best_idx} (16 bytes, device).

@@ -30,6 +30,7 @@ struct FitArgs {
   const double *v_init;
   int v_init_per_unit;
   double *ll_out, *v_out;
+  const int *mode;  // device word picked by nm_group_pick_kernel: 0 exact kernel, NB group kernel; NULL: always run
 };
 
 // ---- PTX helpers: mbarrier + 1-D TMA bulk copy ------------------------------------------------
@@ -84,6 +85,30 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 }
 
 #include "nm_fit_kernels.cuh"
+
+// ---- persistent scratch ------------------------------------------------------------------------------
+// One small buffer per (device, stream), allocated on first use and kept for the life of the process -- no allocator
+// traffic on the hot path (stream-ordered pools hand memory back to the OS at synchronisation points, which showed up
+// as 20-500 ms stalls in bench.py's e2e loop).  Layout: 1024 arg-min partials (16 KB) | 4 ints of sweep mode.
+constexpr size_t kScratchPartials = 1024 * 16;
+constexpr size_t kScratchBytes = kScratchPartials + 64;
+int stream_scratch(void *stream, unsigned char **out) {
+  int device = 0;
+  cudaGetDevice(&device);
+  static std::mutex mu;
+  static std::map<std::pair<int, void *>, unsigned char *> scratch;
+  std::lock_guard<std::mutex> lock(mu);
+  const auto key = std::make_pair(device, stream);
+  auto it = scratch.find(key);
+  if (it == scratch.end()) {
+    unsigned char *buf = nullptr;
+    const cudaError_t ea = cudaMalloc((void **)&buf, kScratchBytes);
+    if (ea != cudaSuccess) return nm_fail(NM_ERR_NOMEM, "scratch cudaMalloc: %s", cudaGetErrorString(ea));
+    it = scratch.emplace(key, buf).first;
+  }
+  *out = it->second;
+  return NM_OK;
+}
 
 // ---- launch planning ---------------------------------------------------------------------------------
 struct LaunchPlan {
@@ -156,11 +181,65 @@ bool memo_enabled() {
   return env && atoi(env) == 1;
 }
 
+// Consumer warps per CTA of a group kernel (one table column per warp: shared memory is no constraint; 126 registers
+// per thread allow 16 resident warps per SM, i.e. up to 15 consumer warps + the producer).  Cost model measured on B200
+// (tools/fit_group_sweep.py, profiles/r01_fit_group.md): warp i sits on scheduler i % 4, and a wave lasts
+// F + X * w for w consumer warps on the busiest scheduler, X = the FP64-pipe time of one warp and F = 1.84 X (two
+// parameter sets per lane) or 2.67 X (one) -- a staircase in the warps per CTA.  Pick the CTA size with the lowest
+// waves x wave-time product; ties go to the smaller CTA (more SMs covered, less contention: configs[1] runs as 147
+// CTAs of 14 consumer warps in 4.55 ms, as 137 CTAs of 15 in 4.62 ms).
+int group_warps(int64_t runs, int S, int device, int nb) {
+  const char *env = getenv("NM_FIT_GROUP_NW");
+  if (env && atoi(env) >= 1 && atoi(env) <= 15) return atoi(env);
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const double F = nb == 2 ? 1.84 : 2.67;
+  int best_nw = 1;
+  double best = 1e300;
+  for (int nw = 1; nw <= 15; ++nw) {
+    const int r = 16 / (nw + 1);  // co-resident CTAs per SM (registers)
+    const int64_t ctas = (int64_t)S * ((runs + nw - 1) / nw);
+    const int64_t waves = (ctas + (int64_t)sms * r - 1) / ((int64_t)sms * r);
+    int64_t r_eff = (ctas + sms - 1) / sms;
+    if (r_eff > r) r_eff = r;
+    const int64_t busiest = (r_eff * nw + 3) / 4;
+    // two producers and twice the barrier traffic: co-resident CTAs cost a little (configs[1]: 2 x 7 warps 4.83 ms)
+    const double cost = (double)waves * (F + (double)busiest) * (1.0 + 0.03 * (double)(r_eff - 1));
+    if (cost < best * 0.999) {
+      best = cost;
+      best_nw = nw;
+    }
+  }
+  return best_nw;
+}
+
+template <int ALG, int NB>
+int launch_group(const FitArgs &a, int S, int device, cudaStream_t cs) {
+  const int64_t runs = (a.P + 32 * NB - 1) / (32 * NB);
+  const int nw = group_warps(runs, S, device, NB);
+  const size_t smem = (size_t)kFixedBytes + (size_t)a.num_states * 8 * nw;
+  auto kernel = nm_fit_group_kernel<ALG, NB>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "cudaFuncSetAttribute(nm_fit_group_kernel): %s", cudaGetErrorString(e));
+  const dim3 grid((unsigned)((runs + nw - 1) / nw), (unsigned)S, 1);
+  kernel<<<grid, 32 * (nw + 1), smem, cs>>>(a);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_fit_group_kernel launch: %s", cudaGetErrorString(e));
+  return NM_OK;
+}
+
+// The group kernels are on unless NM_FIT_GROUP=0 (A/B runs, tests of the exact body on grids).
+bool group_enabled() {
+  const char *env = getenv("NM_FIT_GROUP");
+  return !(env && atoi(env) == 0);
+}
+
 template <int ALG>
 int sweep_alg(bool with_ll, FitArgs a, int S, int device, cudaStream_t cs) {
   LaunchPlan exact;
   int rc = plan_launch(a.num_states * 8, a.P, S, device, "NM_FIT_NC", &exact);
   if (rc != NM_OK) return rc;
+  a.mode = nullptr;
   if (!with_ll) return launch(nm_fit_exact_kernel<ALG, false, false>, a, S, exact, cs, "nm_fit_exact_kernel");
   LaunchPlan memo;
   if (memo_enabled() && plan_launch(a.num_states * 16, a.P, S, device, "NM_FIT_MEMO_NC", &memo) == NM_OK) {
@@ -171,6 +250,26 @@ int sweep_alg(bool with_ll, FitArgs a, int S, int device, cudaStream_t cs) {
     FitArgs redo = a;
     redo.v_out = nullptr;
     return launch(nm_fit_exact_kernel<ALG, true, true>, redo, S, exact, cs, "nm_fit_exact_kernel(redo)");
+  }
+  // Likelihood sweep.  Parameter sets that share (alpha, gamma) share their value table: the device decides whether
+  // every aligned run of 64 (else 32) consecutive sets does, and exactly one of the three kernels below does the work
+  // (the other two return at their first instruction) -- no host round trip, the call stays asynchronous.
+  const bool try_group = group_enabled() && !a.v_init_per_unit && a.num_states * 8 * 15 + kFixedBytes <= kMaxSmem;
+  unsigned char *scratch = nullptr;
+  rc = stream_scratch((void *)cs, &scratch);
+  if (rc != NM_OK) return rc;
+  int *mode = reinterpret_cast<int *>(scratch + kScratchPartials);
+  if (!try_group) {
+    nm_group_pick_kernel<<<1, 1, 0, cs>>>(mode, 0);  // nm_loglik_sweep_mode reports 0
+  } else {
+    nm_group_init_kernel<<<1, 1, 0, cs>>>(mode);
+    nm_group_detect_kernel<<<(unsigned)((a.P + 255) / 256), 256, 0, cs>>>(a.alpha, a.gamma, a.P, mode);
+    nm_group_pick_kernel<<<1, 1, 0, cs>>>(mode, 1);
+    a.mode = mode;
+    rc = launch_group<ALG, 2>(a, S, device, cs);
+    if (rc != NM_OK) return rc;
+    rc = launch_group<ALG, 1>(a, S, device, cs);
+    if (rc != NM_OK) return rc;
   }
   return launch(nm_fit_exact_kernel<ALG, true, false>, a, S, exact, cs, "nm_fit_exact_kernel");
 }
@@ -311,30 +410,26 @@ extern "C" int nm_argmin_nll(const double *d_ll, int S, int64_t P, double *d_nll
   cudaStream_t cs = (cudaStream_t)stream;
   int blocks = (int)((P + 255) / 256);
   if (blocks > 1024) blocks = 1024;
-  // 16 KB of partials: one persistent scratch buffer per (device, stream), allocated on first use and kept
-  // for the life of the process -- no allocator traffic on the hot path (stream-ordered pools hand memory
-  // back to the OS at synchronisation points, which showed up as 20-500 ms stalls in bench.py's e2e loop)
-  int device = 0;
-  cudaGetDevice(&device);
-  Best *partial = nullptr;
-  {
-    static std::mutex mu;
-    static std::map<std::pair<int, void *>, Best *> scratch;
-    std::lock_guard<std::mutex> lock(mu);
-    const auto key = std::make_pair(device, stream);
-    auto it = scratch.find(key);
-    if (it == scratch.end()) {
-      Best *buf = nullptr;
-      const cudaError_t ea = cudaMalloc((void **)&buf, sizeof(Best) * 1024);
-      if (ea != cudaSuccess) return nm_fail(NM_ERR_NOMEM, "nm_argmin_nll: cudaMalloc: %s", cudaGetErrorString(ea));
-      it = scratch.emplace(key, buf).first;
-    }
-    partial = it->second;
-  }
+  unsigned char *scratch = nullptr;
+  const int rc = stream_scratch(stream, &scratch);  // 16 KB of partials, persistent per (device, stream)
+  if (rc != NM_OK) return rc;
+  Best *partial = reinterpret_cast<Best *>(scratch);
   nm_nll_partial_kernel<<<blocks, 256, 0, cs>>>(d_ll, S, P, d_nll_out, partial);
   nm_nll_final_kernel<<<1, 256, 0, cs>>>(partial, blocks, (Best *)d_best_out);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_argmin_nll launch: %s", cudaGetErrorString(e));
+  return NM_OK;
+}
+
+extern "C" int nm_loglik_sweep_mode(void *stream, int *mode_out) {
+  NM_CHECK_ARG(mode_out, "nm_loglik_sweep_mode: NULL output");
+  unsigned char *scratch = nullptr;
+  const int rc = stream_scratch(stream, &scratch);
+  if (rc != NM_OK) return rc;
+  // synchronous by design (diagnostics / tests): waits for the stream, then reads the word the device picked
+  cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+  if (e == cudaSuccess) e = cudaMemcpy(mode_out, scratch + kScratchPartials, sizeof(int), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_loglik_sweep_mode: %s", cudaGetErrorString(e));
   return NM_OK;
 }
 

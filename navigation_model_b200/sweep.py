@@ -415,6 +415,17 @@ class ConditioningSweep:
                 int(v_init_per_unit), _native.tensor_ptr(ll_out), _native.tensor_ptr(v_out), _native.cuda_stream_ptr()))
         return ll_out
 
+    def last_sweep_mode(self):
+        """Kernel the last :meth:`log_likelihood_device` on the current stream used: 0 = a value table per parameter
+        set, 1 / 2 = a table per warp shared by aligned runs of 32 / 64 consecutive parameter sets with equal
+        ``(alpha, gamma)`` (order the grid with beta fastest, ``parameter_grid(gamma, alpha, beta)``, to get there).
+        Synchronises the stream."""
+        torch = self._ensure_device()
+        mode = C.c_int(-1)
+        with torch.cuda.device(self.torch_device):
+            _native.check(self._dmaze._lib.nm_loglik_sweep_mode(_native.cuda_stream_ptr(), C.byref(mode)))
+        return mode.value
+
     def argmin_device(self, ll_t, nll_out=None):
         """Per-shard best fit of ``ll_t`` ``[S, P]`` -> device tensor ``[2]`` int64-punned ``(nll, idx)``."""
         torch = self._ensure_device()

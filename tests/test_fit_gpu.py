@@ -192,6 +192,50 @@ def test_full_grid_properties(cuda):
     assert best_i == int(np.argmin(-ll)) and best_v == float((-ll).min())
 
 
+@pytest.mark.parametrize("alg", ["td0", "positive", "negative"])
+@pytest.mark.parametrize("n_beta", [64, 128, 32, 160])
+def test_group_kernels_match_exact_kernel_and_oracle(cuda, alg, n_beta, monkeypatch):
+    """Grids whose beta axis varies fastest: aligned runs of consecutive parameter sets share (alpha, gamma) and the
+    warp-shared-table kernels take over -- two sets per lane when every aligned run of 64 is uniform (n_beta = 64,
+    128), one set per lane when only the runs of 32 are (n_beta = 32, 160).  Their results must be bit-identical to
+    the exact kernel's (same operation sequence per parameter set) and agree with the oracle."""
+    omz = H.oracle_m9()
+    sessions = [O.synthetic_session(omz, sid, T) for sid, T in ((0, 700), (4, 97), (5, 1))]
+    if alg == "negative":
+        sessions = [(t, -r) for t, r in sessions]
+    rng = np.random.default_rng(n_beta)
+    pairs = 5
+    a = np.repeat(rng.uniform(0.01, 1, pairs), n_beta)
+    g = np.repeat(rng.uniform(0.5, 0.99, pairs), n_beta)
+    b = np.tile(np.logspace(-1, 1.5, n_beta), pairs)
+    P = a.size - 11  # the last run is incomplete
+    a, b, g = a[:P].copy(), b[:P].copy(), g[:P].copy()
+    b[3] = -b[3]  # mixed signs of beta inside a warp
+    v0 = rng.random((9, 9))
+    sw = _sweep(alg, sessions, replay_n_times=1, replay_seed=3)
+    ll, V = sw.log_likelihood(a, b, g, v_init=v0, return_v=True)
+    assert sw.last_sweep_mode() == (2 if n_beta % 64 == 0 else 1)  # the shared-table kernel really ran
+    monkeypatch.setenv("NM_FIT_GROUP", "0")
+    ll_x, V_x = sw.log_likelihood(a, b, g, v_init=v0, return_v=True)
+    assert sw.last_sweep_mode() == 0
+    monkeypatch.delenv("NM_FIT_GROUP")
+    assert np.array_equal(ll, ll_x) and np.array_equal(V, V_x)
+    for j, (traj, rew) in enumerate(sessions):
+        tr = H.oracle_transitions(omz, traj, rew, H.a8())
+        orders = O.replay_orders(len(tr["s"]), 1, 3)
+        Vw, llw = CO.fit(ALGS[alg], tr, a, g, 60, beta=b, v0=H.compact(omz, v0), orders=orders)
+        np.testing.assert_allclose(ll[j], llw, rtol=LL_RTOL, atol=1e-300)
+        for p in (0, 63, 64, P - 1):
+            assert np.array_equal(V[j, p], O.dense_table(omz, Vw[p], v0))
+    # runs that are uniform in alpha but not in gamma must NOT be grouped: perturb one gamma inside a run
+    g2 = g.copy()
+    g2[70] = 0.6123
+    ll2 = sw.log_likelihood(a, b, g2)
+    assert sw.last_sweep_mode() == 0
+    monkeypatch.setenv("NM_FIT_GROUP", "0")
+    assert np.array_equal(ll2, sw.log_likelihood(a, b, g2))
+
+
 def test_td0_linearity_in_reward(cuda):
     """TD0 is linear in the reward: scaling rewards by a power of two scales V exactly."""
     omz = H.oracle_m9()

@@ -1,0 +1,52 @@
+#!/usr/bin/env python
+"""Time of one wave of the warp-shared-table fit kernel (two parameter sets per lane) as a function of its consumer
+warps per CTA (NM_FIT_GROUP_NW): one CTA per SM, 148 * nw * 64 parameter sets.
+
+    python tools/fit_group_sweep.py            # prints nw, kernel ms, parameter sets / (SM ms)"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    from navigation_model_b200.simulation.maze import Maze
+    from navigation_model_b200.sweep import ConditioningSweep
+    from oracle import np_oracle as O
+    omz = O.OracleMaze(O.M9_LAYOUT, O.M9_SIZE_TILE)
+    maze = Maze(O.M9_LAYOUT, O.M9_SUBAREAS, size_tile=O.M9_SIZE_TILE)
+    acts = O.A8_UNITS * O.M9_SIZE_TILE
+    traj, rew = O.synthetic_session(omz, 0, 5000)
+    sw = ConditioningSweep(maze, "positive", possible_actions=acts, device=0)
+    sw.add_session(traj, rew)
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(0)
+    mult = int(os.environ.get("SWEEP_CTAS_PER_SM", "1"))  # co-resident CTAs per SM (small CTAs only)
+    for nw in [int(x) for x in (sys.argv[1:] or range(14, 0, -1))]:
+        os.environ["NM_FIT_GROUP_NW"] = str(nw)
+        runs = 148 * nw * mult
+        P = runs * 64
+        a = torch.from_numpy(np.repeat(rng.uniform(0.01, 1, runs), 64)).to(dev)
+        g = torch.from_numpy(np.repeat(rng.uniform(0.5, 0.99, runs), 64)).to(dev)
+        b = torch.from_numpy(rng.uniform(0.1, 30, P)).to(dev)
+        ll = torch.empty((1, P), dtype=torch.float64, device=dev)
+        best = 1e9
+        for rep in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            sw.log_likelihood_device(a, b, g, ll_out=ll)
+            e1.record()
+            torch.cuda.synchronize()
+            if rep:
+                best = min(best, e0.elapsed_time(e1))
+        print(json.dumps({"nw": nw, "kernel_ms": best, "ctas_per_sm": mult, "sets_per_sm_ms": mult * nw * 64 / best,
+                          "updates_per_s": P * 4999 / (best * 1e-3)}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
