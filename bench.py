@@ -200,7 +200,7 @@ def run_reference(args):
                              "sample": f"{P_s} of {len(a)} parameter sets (evenly spaced) x {n} steps per step"},
             "e2e": {"value": value, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args, n_gpus, p_per_rank):
@@ -368,8 +368,7 @@ def run_b200(args):
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
-           torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(4)) for _ in range(args.steps)]
     t_wall0 = time.perf_counter()
     for i in range(args.steps):
         flush.zero_()
@@ -377,6 +376,7 @@ def run_b200(args):
         sw.log_likelihood_device(a_t, b_t, g_t, ll_out=ll_t)
         ev[i][1].record(stream)  # end of the dominant kernel
         best = sw.argmin_device(ll_t)
+        ev[i][3].record(stream)  # before the cross-GPU exchange
         reduce_best_device(best, lo, world, dist)
         ev[i][2].record(stream)
     barrier()
@@ -385,6 +385,7 @@ def run_b200(args):
     sweep_mode = sw.last_sweep_mode()  # which fit kernel the device picked (reads one word; after the timed region)
     step_ms = np.array([e[0].elapsed_time(e[2]) for e in ev])
     kern_ms = np.array([e[0].elapsed_time(e[1]) for e in ev])
+    gather_ms = np.array([e[3].elapsed_time(e[2]) for e in ev])  # all-gather incl. the wait for the slowest rank
     total_ms = torch.tensor([step_ms.sum()], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
@@ -486,17 +487,37 @@ def run_b200(args):
                                                    float(np.max(e2e_step_ms))],
                         "slowest_step_index": int(np.argmax(e2e_step_ms))},
                 "gpu_launches": (4 if os.environ.get("NM_FIT_GROUP") == "0" else 8) * args.steps, "clocks": clocks, "wall_s": wall,
+                "exchange_ms_per_step_rank0": float(gather_ms.mean()) if world > 1 else 0.0,
                 "target_updates_per_s_8gpu": 1e10}
         if extras is not None:
             line["also_measured"] = extras
             line["gpu_launches"] += 9
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def own_stdout():
+    """The contract is ONE JSON line on stdout, but native libraries print there too (NCCL's version banner when the box
+    sets NCCL_DEBUG): keep a private copy of the real stdout for that line and point file descriptor 1 at stderr."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    own_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
