@@ -565,6 +565,10 @@ class _TileActionSweep:
     def add_session(self, trajectory, reward):
         self._base.add_session(trajectory, reward)
 
+    def use_streams(self, streams):
+        """Use step streams built on the device (``SessionBatch.streams``) instead of host-built records."""
+        self._base.use_streams(streams)
+
     @property
     def n_sessions(self):
         return self._base.n_sessions

@@ -114,6 +114,40 @@ def test_loglik_c_vs_numpy_oracle():
             assert abs(ll - llc[p]) <= 1e-12 * abs(ll)
 
 
+def test_tile_action_agent_oracles_closed_forms():
+    """The Q-table and model-based agents are extensions without a reference implementation: their numpy oracles are
+    at least held to closed forms.  alpha = 0 never moves the tables, so every observed step has probability 1 / K;
+    beta = 0 gives the same likelihood whatever was learned; and on the deterministic maze the Q-table learner's
+    max-backup equals PositiveConditioning's on after-states: Q(s, a) -> r + gamma * max Q(next(s, a), .)."""
+    mz = H.oracle_m9()
+    acts = [(dx, dy) for dx in (-1, 0, 1) for dy in (-1, 0, 1) if (dx, dy) != (0, 0)]
+    nxt = O.transition_table(mz, acts)
+    traj, rew = O.synthetic_session(mz, 3, 600)
+    tr = O.extract_transitions(mz, traj, rew, None)
+    closed = 0.0
+    for s, s1 in zip(tr["s"].tolist(), tr["s1"].tolist()):
+        avail = [a for a in range(len(acts)) if nxt[s, a] >= 0]
+        if any(nxt[s, a] == s1 for a in avail):
+            closed = closed + (0.0 - np.log(float(len(avail))))
+    Q, ll = O.run_q_learning(tr, nxt, 0.0, 3.0, 0.9)
+    assert not Q.any() and abs(ll - closed) <= 1e-12 * abs(closed)
+    Q, ll = O.run_q_learning(tr, nxt, 0.4, 0.0, 0.9)
+    assert Q.any() and abs(ll - closed) <= 1e-12 * abs(closed)
+    V, R, ll = O.run_model_based(tr, nxt, 0.0, 3.0, 0.9)
+    assert not V.any() and not R.any() and abs(ll - closed) <= 1e-12 * abs(closed)
+    # replays only ever update: the likelihood is that of the online pass
+    orders = O.replay_orders(len(tr["s"]), 2, 1)
+    Q2, ll2 = O.run_q_learning(tr, nxt, 0.3, 2.0, 0.8, orders=orders)
+    Q1, ll1 = O.run_q_learning(tr, nxt, 0.3, 2.0, 0.8)
+    assert ll1 == ll2 and not np.array_equal(Q1, Q2)
+    # fixed point of the backup with alpha = 1 on a two-step stream: Q(s, a) = r + gamma * max_a' Q(s1, a')
+    two = {k: v[:2] for k, v in tr.items()}
+    Q, _ = O.run_q_learning(two, nxt, 1.0, 1.0, 0.5, q0=np.ones_like(nxt, dtype=np.float64))
+    s, s1, r = int(two["s"][0]), int(two["s1"][0]), float(two["r"][0])
+    a = next(a for a in range(len(acts)) if nxt[s, a] == s1)
+    assert Q[s, a] == r + 0.5 * 1.0 or (s1 == s)  # the bootstrap row was still all ones
+
+
 def test_floor_division_boundaries():
     """Python float floor-division differs from floor(x / w) on tile multiples."""
     mz = H.oracle_m9()

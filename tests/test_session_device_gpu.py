@@ -172,6 +172,27 @@ def test_sweep_on_device_built_streams(cuda, alg):
         dev.add_session(*sessions[0])
 
 
+@pytest.mark.parametrize("agent", ["qtable", "modelbased"])
+def test_tile_action_agents_on_device_built_streams(cuda, agent):
+    """The two tile-action agents only need (s, s1, r): streams built on the device without actions serve them."""
+    from navigation_model_b200.batched_sessions import SessionBatch
+    from navigation_model_b200.sweep import ModelBasedSweep, QLearningSweep
+    maze = H.product_m9()
+    omz = H.oracle_m9()
+    moves = [(dx, dy) for dx in (-1, 0, 1) for dy in (-1, 0, 1) if (dx, dy) != (0, 0)]
+    sessions = [O.synthetic_session(omz, sid, 300 + 40 * sid) for sid in range(3)]
+    rng = np.random.default_rng(5)
+    a, b, g = H.grid_params(rng, 50)
+    make = (lambda: QLearningSweep(maze, moves)) if agent == "qtable" else (lambda: ModelBasedSweep(maze, moves, n_sweeps=2))
+    host, dev = make(), make()
+    for traj, rew in sessions:
+        host.add_session(traj, rew)
+    dev.use_streams(SessionBatch(None, [s[0] for s in sessions], [s[1] for s in sessions]).streams(maze, None))
+    assert dev.n_sessions == 3 and dev.updates_per_parameter_set == host.updates_per_parameter_set
+    assert np.array_equal(host.log_likelihood(a, b, g), dev.log_likelihood(a, b, g))
+    assert dev.best_fit(a, b, g) == host.best_fit(a, b, g)
+
+
 def test_no_candidate_is_an_error(cuda):
     """A step whose rotated endpoints all fall outside the maze: np.max([]) raises in the reference (rl.py:184)."""
     from navigation_model_b200.batched_sessions import SessionBatch
