@@ -125,7 +125,7 @@ def measured_hbm_peak():
         return 6650.0  # fallback stated in B200_PROFILING.md
 
 
-NCU_SUMMARY = os.path.join(ROOT, "profiles", "r01_v9_fit_kernel_ncu.txt")
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "r01_v10_fit_kernel_ncu.txt")
 
 
 def ncu_counter(prefixes, scale_units=False):
@@ -181,7 +181,7 @@ def run_reference(args):
     omz, traj, rew, a, b, g = make_workload(world)  # the whole job's grid: the sample is drawn from all of it
     tr = O.extract_transitions(omz, traj, rew, O.OracleMouse(traj[0], 0.0, O.A8_UNITS * O.M9_SIZE_TILE))
     n = len(tr["s"])
-    P_s = 4096
+    P_s = 16384  # ~0.25 s of 16 host threads per step
     idx = np.linspace(0, len(a) - 1, P_s).astype(np.int64)
     cores = host_threads()
     for _ in range(args.warmup):
@@ -451,12 +451,11 @@ def run_b200(args):
         alg_bytes = n_upd * 32 + P * 32  # stream once + (alpha, beta, gamma, ll) per parameter set
         roofline = {"bound": "fp64_issue", "achieved": achieved, "peak": peak_ginstr, "unit": "GInstr/s",
                     "frac": achieved / peak_ginstr, "traffic": ncu_dram_traffic(),
-                    "kernel": {2: f"nm_fit_group_kernel<{args.alg}, 2 parameter sets per lane>",
-                               1: f"nm_fit_group_kernel<{args.alg}, 1 parameter set per lane>"}.get(
-                                   sweep_mode, f"nm_fit_exact_kernel<{args.alg}, loglik>"),
+                    "kernel": (f"nm_fit_group_kernel<{args.alg}> (one value table per warp)" if sweep_mode == 1
+                               else f"nm_fit_exact_kernel<{args.alg}, loglik>"),
                     "kernel_ms": float(kern_ms.mean()),
-                    "kernel_ms_covers": "the whole nm_loglik_sweep call: the dominant kernel + 5 launches of a few "
-                                        "microseconds (run detection, the two kernels that stand down)",
+                    "kernel_ms_covers": "the whole nm_loglik_sweep call: the dominant kernel + 3 launches of a few "
+                                        "microseconds (run detection, the kernel that stands down)",
                     "frac_note": "achieved counts the CANONICAL FP64 instructions of SURVEY 8d (exp = 20, log = 30); the "
                                  "kernel executes fewer (table-driven exp = 12, one log per 32 steps), so the canonical "
                                  "fraction can pass 1 -- the executed fraction is fp64_pipe_busy_ncu",
@@ -486,7 +485,7 @@ def run_b200(args):
                         "step_ms_min_median_max": [float(np.min(e2e_step_ms)), float(np.median(e2e_step_ms)),
                                                    float(np.max(e2e_step_ms))],
                         "slowest_step_index": int(np.argmax(e2e_step_ms))},
-                "gpu_launches": (4 if os.environ.get("NM_FIT_GROUP") == "0" else 8) * args.steps, "clocks": clocks, "wall_s": wall,
+                "gpu_launches": (4 if os.environ.get("NM_FIT_GROUP") == "0" else 6) * args.steps, "clocks": clocks, "wall_s": wall,
                 "exchange_ms_per_step_rank0": float(gather_ms.mean()) if world > 1 else 0.0,
                 "target_updates_per_s_8gpu": 1e10}
         if extras is not None:

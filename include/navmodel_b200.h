@@ -222,10 +222,10 @@ int nm_loglik_sweep(int alg, const nm_maze *mz, const nm_streams *st, const doub
                     int v_init_per_unit, double *d_ll_out, double *d_v_out, void *stream);
 
 /* Which kernel the last nm_loglik_sweep on `stream` (current device) used: 0 = one value table per parameter set,
- * 1 / 2 = one table per warp shared by aligned runs of 32 / 64 consecutive parameter sets with equal (alpha, gamma)
- * -- the device checks the arrays itself, so a Cartesian grid whose beta axis varies fastest takes the shared path
- * without any hint (results are bit-identical either way; NM_FIT_GROUP=0 forces 0).  Synchronises the stream:
- * diagnostics and tests only. */
+ * 1 = one table per warp, shared by an aligned run of 32 consecutive parameter sets with equal (alpha, gamma) -- the
+ * device checks the arrays itself, so a Cartesian grid whose beta axis varies fastest (a multiple of 32 points) takes
+ * the shared path without any hint (results are bit-identical either way; NM_FIT_GROUP=0 forces 0).  Synchronises
+ * the stream: diagnostics and tests only. */
 int nm_loglik_sweep_mode(void *stream, int *mode_out);
 
 /* Per-shard best fit: nll[p] = -(sum_s ll[s, p]) (sessions added in index order), then the minimum and

@@ -30,7 +30,7 @@ struct FitArgs {
   const double *v_init;
   int v_init_per_unit;
   double *ll_out, *v_out;
-  const int *mode;  // device word picked by nm_group_pick_kernel: 0 exact kernel, NB group kernel; NULL: always run
+  const int *mode;  // device word set by nm_group_detect_kernel: 0 exact kernel, 1 group kernel; NULL: always run
 };
 
 // ---- PTX helpers: mbarrier + 1-D TMA bulk copy ------------------------------------------------
@@ -181,30 +181,29 @@ bool memo_enabled() {
   return env && atoi(env) == 1;
 }
 
-// Consumer warps per CTA of a group kernel (one table column per warp: shared memory is no constraint; 126 registers
-// per thread allow 16 resident warps per SM, i.e. up to 15 consumer warps + the producer).  Cost model measured on B200
-// (tools/fit_group_sweep.py, profiles/r01_fit_group.md): warp i sits on scheduler i % 4, and a wave lasts
-// F + X * w for w consumer warps on the busiest scheduler, X = the FP64-pipe time of one warp and F = 1.84 X (two
-// parameter sets per lane) or 2.67 X (one) -- a staircase in the warps per CTA.  Pick the CTA size with the lowest
-// waves x wave-time product; ties go to the smaller CTA (more SMs covered, less contention: configs[1] runs as 147
-// CTAs of 14 consumer warps in 4.55 ms, as 137 CTAs of 15 in 4.62 ms).
-int group_warps(int64_t runs, int S, int device, int nb) {
+// Consumer warps per CTA of the group kernel (one table column per warp: shared memory is no constraint; 64 registers
+// per thread allow 32 resident warps per SM, i.e. up to 29 consumer warps + the producer in one CTA of 960 threads).
+// Cost model measured on B200 (tools/fit_group_sweep.py, profiles/r01_fit_group.md): warp i sits on scheduler i % 4
+// and a wave lasts kWave[w] (relative) for w consumer warps on the busiest scheduler -- a staircase in the warps per
+// CTA.  Pick the CTA size with the lowest waves x wave-time product; ties go to the smaller CTA.
+int group_warps(int64_t runs, int S, int device) {
+  static const double kWave[9] = {0.0, 1.0, 1.12, 1.29, 1.45, 1.65, 1.91, 2.19, 2.50};
+  const int max_nw = 29;
   const char *env = getenv("NM_FIT_GROUP_NW");
-  if (env && atoi(env) >= 1 && atoi(env) <= 15) return atoi(env);
+  if (env && atoi(env) >= 1 && atoi(env) <= max_nw) return atoi(env);
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  const double F = nb == 2 ? 1.84 : 2.67;
   int best_nw = 1;
   double best = 1e300;
-  for (int nw = 1; nw <= 15; ++nw) {
-    const int r = 16 / (nw + 1);  // co-resident CTAs per SM (registers)
+  for (int nw = 1; nw <= max_nw; ++nw) {
+    const int r = 32 / (nw + 1);  // co-resident CTAs per SM (registers)
     const int64_t ctas = (int64_t)S * ((runs + nw - 1) / nw);
     const int64_t waves = (ctas + (int64_t)sms * r - 1) / ((int64_t)sms * r);
     int64_t r_eff = (ctas + sms - 1) / sms;
     if (r_eff > r) r_eff = r;
     const int64_t busiest = (r_eff * nw + 3) / 4;
-    // two producers and twice the barrier traffic: co-resident CTAs cost a little (configs[1]: 2 x 7 warps 4.83 ms)
-    const double cost = (double)waves * (F + (double)busiest) * (1.0 + 0.03 * (double)(r_eff - 1));
+    // several producers and rings per SM: co-resident CTAs cost a little
+    const double cost = (double)waves * kWave[busiest > 8 ? 8 : busiest] * (1.0 + 0.03 * (double)(r_eff - 1));
     if (cost < best * 0.999) {
       best = cost;
       best_nw = nw;
@@ -213,12 +212,12 @@ int group_warps(int64_t runs, int S, int device, int nb) {
   return best_nw;
 }
 
-template <int ALG, int NB>
+template <int ALG>
 int launch_group(const FitArgs &a, int S, int device, cudaStream_t cs) {
-  const int64_t runs = (a.P + 32 * NB - 1) / (32 * NB);
-  const int nw = group_warps(runs, S, device, NB);
+  const int64_t runs = (a.P + 31) / 32;
+  const int nw = group_warps(runs, S, device);
   const size_t smem = (size_t)kFixedBytes + (size_t)a.num_states * 8 * nw;
-  auto kernel = nm_fit_group_kernel<ALG, NB>;
+  auto kernel = nm_fit_group_kernel<ALG>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "cudaFuncSetAttribute(nm_fit_group_kernel): %s", cudaGetErrorString(e));
   const dim3 grid((unsigned)((runs + nw - 1) / nw), (unsigned)S, 1);
@@ -252,23 +251,20 @@ int sweep_alg(bool with_ll, FitArgs a, int S, int device, cudaStream_t cs) {
     return launch(nm_fit_exact_kernel<ALG, true, true>, redo, S, exact, cs, "nm_fit_exact_kernel(redo)");
   }
   // Likelihood sweep.  Parameter sets that share (alpha, gamma) share their value table: the device decides whether
-  // every aligned run of 64 (else 32) consecutive sets does, and exactly one of the three kernels below does the work
-  // (the other two return at their first instruction) -- no host round trip, the call stays asynchronous.
-  const bool try_group = group_enabled() && !a.v_init_per_unit && a.num_states * 8 * 15 + kFixedBytes <= kMaxSmem;
+  // every aligned run of 32 consecutive sets does, and exactly one of the two kernels below does the work (the other
+  // returns at its first instruction) -- no host round trip, the call stays asynchronous.
+  const bool try_group = group_enabled() && !a.v_init_per_unit && a.num_states * 8 * 29 + kFixedBytes <= kMaxSmem;
   unsigned char *scratch = nullptr;
   rc = stream_scratch((void *)cs, &scratch);
   if (rc != NM_OK) return rc;
   int *mode = reinterpret_cast<int *>(scratch + kScratchPartials);
   if (!try_group) {
-    nm_group_pick_kernel<<<1, 1, 0, cs>>>(mode, 0);  // nm_loglik_sweep_mode reports 0
+    nm_group_off_kernel<<<1, 1, 0, cs>>>(mode);  // nm_loglik_sweep_mode reports 0
   } else {
     nm_group_init_kernel<<<1, 1, 0, cs>>>(mode);
     nm_group_detect_kernel<<<(unsigned)((a.P + 255) / 256), 256, 0, cs>>>(a.alpha, a.gamma, a.P, mode);
-    nm_group_pick_kernel<<<1, 1, 0, cs>>>(mode, 1);
     a.mode = mode;
-    rc = launch_group<ALG, 2>(a, S, device, cs);
-    if (rc != NM_OK) return rc;
-    rc = launch_group<ALG, 1>(a, S, device, cs);
+    rc = launch_group<ALG>(a, S, device, cs);
     if (rc != NM_OK) return rc;
   }
   return launch(nm_fit_exact_kernel<ALG, true, false>, a, S, exact, cs, "nm_fit_exact_kernel");

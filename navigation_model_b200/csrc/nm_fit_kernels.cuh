@@ -369,88 +369,30 @@ __global__ void __launch_bounds__(512, 1) nm_fit_exact_kernel(const FitArgs a) {
 // =================================== GROUP body ============================================================
 // A value table depends on (alpha, gamma) only -- beta enters the likelihood, not the recurrence -- so on a Cartesian
 // grid whose beta axis varies fastest, runs of consecutive parameter sets own IDENTICAL tables.  When every aligned
-// run of 32 * NB parameter sets shares (alpha, gamma) (checked on the device by nm_group_detect_kernel), a WARP keeps
-// ONE table column for its 32 * NB sets: lane l evaluates the sets p0 + l, p0 + 32 + l, ... (NB of them).  Loads of V
-// become broadcasts, the table update is the same value in every lane (all lanes store it: same address, same
-// bits), shared memory stops limiting residency, and the NB softmax evaluations of a lane are independent chains
-// the scheduler overlaps.  Per parameter set the operation sequence is the exact body's: results are bit-identical.
-template <int NB>
-struct GroupAcc {
-  double acc_obs[NB], prod[NB];
-  ExpRegs er;
-};
-
-template <int ALG, int K, int NB>
-__device__ __forceinline__ void group_step_k(const uint4 q0, const uint4 q1, const uint4 q2, const uint4 q3, char *vb,
-                                             const double alpha, const double (&beta)[NB], const double gamma,
-                                             GroupAcc<NB> &acc) {
-  const double r = __hiloint2double((int)q0.y, (int)q0.x);
-  const uint32_t offs[NM_MAX_CAND] = {q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y};
-  double *ps = reinterpret_cast<double *>(vb + q0.z);
-  const double vs = *ps;
-  double v[NM_MAX_CAND];
-#pragma unroll
-  for (int k = 0; k < K; ++k) v[k] = lds_f64(vb, offs[k]);
-  double boot;
-  if constexpr (ALG == NM_ALG_TD0) boot = lds_f64(vb, q1.y);
-  else boot = extremum<ALG, K>(v);
-  if (q0.w != kNone) {  // observed step (warp-uniform)
-    const double vobs = lds_f64(vb, q0.w);
-#pragma unroll
-    for (int j = 0; j < NB; ++j) {
-      double z[NM_MAX_CAND];
-#pragma unroll
-      for (int k = 0; k < K; ++k) z[k] = __dmul_rn(beta[j], v[k]);  // exploration_model.py:87
-      double m;
-      if ((ALG == NM_ALG_POSITIVE && beta[j] >= 0.0) || (ALG == NM_ALG_NEGATIVE && beta[j] <= 0.0)) {
-        m = __dmul_rn(beta[j], boot);  // == max_k fl(beta * v_k): rounding is monotonic
-      } else {
-        m = extremum<NM_ALG_POSITIVE, K>(z);
-      }
-      double e[NM_MAX_CAND];
-#pragma unroll
-      for (int k = 0; k < K; ++k) e[k] = acc.er.exp_nonpos(__dsub_rn(z[k], m));  // :92-93
-      const double sum = np_sum_fixed<K>(e);
-      acc.acc_obs[j] = __dadd_rn(acc.acc_obs[j], __dsub_rn(__dmul_rn(beta[j], vobs), m));
-      acc.prod[j] = __dmul_rn(acc.prod[j], sum);
-    }
-  }
-  const double rpe = __dsub_rn(__dadd_rn(r, __dmul_rn(gamma, boot)), vs);  // rl.py:185, 228, 257
-  *ps = __dadd_rn(vs, __dmul_rn(alpha, rpe));                               // rl.py:186-187, 258-259
-}
-
-template <int ALG, int NB>
-__device__ __forceinline__ void group_step(const uint4 *__restrict__ rec, char *vb, const double alpha,
-                                           const double (&beta)[NB], const double gamma, GroupAcc<NB> &acc) {
-  const uint4 q0 = rec[0], q1 = rec[1], q2 = rec[2], q3 = rec[3];
-#define NM_CASE(KK) \
-  case KK: group_step_k<ALG, KK, NB>(q0, q1, q2, q3, vb, alpha, beta, gamma, acc); break;
-  switch (q1.x & 0xffu) {  // K, warp-uniform
-    NM_CASE(1) NM_CASE(2) NM_CASE(3) NM_CASE(4) NM_CASE(5) NM_CASE(6) NM_CASE(7) NM_CASE(8)
-    default: break;  // K == 0 is rejected on the host for likelihood sweeps
-  }
-#undef NM_CASE
-}
-
-// mode[0] = largest NB in {2, 1} such that every aligned run of 32 * NB parameter sets shares (alpha, gamma), else 0.
-// Launched after nm_group_init_kernel set mode[1] = mode[2] = 1 (mode[1]: runs of 64 uniform, mode[2]: runs of 32).
-__global__ void nm_group_init_kernel(int *mode) { mode[0] = -1; mode[1] = 1; mode[2] = 1; }
+// run of 32 parameter sets shares (alpha, gamma) (checked on the device by nm_group_detect_kernel), a WARP keeps ONE
+// table column for its 32 sets: loads of V become broadcasts, the table update is the same value in every lane (all
+// lanes store it: same address, same bits) and shared memory stops limiting residency -- the kernel is compiled for
+// 64 registers, so up to 29 consumer warps + the producer share an SM (the exact kernel: 14).  Per parameter set the
+// operation sequence is the exact body's: results are bit-identical.
+//
+// mode[0] = 1 if every aligned run of 32 parameter sets shares (alpha, gamma), else 0.
+__global__ void nm_group_init_kernel(int *mode) { mode[0] = 1; }
 __global__ void __launch_bounds__(256) nm_group_detect_kernel(const double *__restrict__ alpha,
                                                               const double *__restrict__ gamma, int64_t P, int *mode) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
-  const long long a = __double_as_longlong(alpha[p]), g = __double_as_longlong(gamma[p]);
-  const int64_t h64 = p & ~(int64_t)63, h32 = p & ~(int64_t)31;
-  if (a != __double_as_longlong(alpha[h64]) || g != __double_as_longlong(gamma[h64])) mode[1] = 0;
-  if (a != __double_as_longlong(alpha[h32]) || g != __double_as_longlong(gamma[h32])) mode[2] = 0;
+  const int64_t head = p & ~(int64_t)31;
+  if (__double_as_longlong(alpha[p]) != __double_as_longlong(alpha[head]) ||
+      __double_as_longlong(gamma[p]) != __double_as_longlong(gamma[head]))
+    mode[0] = 0;
 }
-__global__ void nm_group_pick_kernel(int *mode, int allow) { mode[0] = !allow ? 0 : mode[1] ? 2 : mode[2] ? 1 : 0; }
+__global__ void nm_group_off_kernel(int *mode) { mode[0] = 0; }
 
-// Runs only when *a.mode == NB (the exact kernel takes mode 0).  blockDim.x = 32 * (nw + 1): nw consumer warps, each
+// Runs only when *a.mode == 1 (the exact kernel takes mode 0).  blockDim.x = 32 * (nw + 1): nw consumer warps, each
 // with its own table column V[state][warp], and the producer warp.
-template <int ALG, int NB>
-__global__ void __launch_bounds__(512, 1) nm_fit_group_kernel(const FitArgs a) {
-  if (*a.mode != NB) return;
+template <int ALG>
+__global__ void __launch_bounds__(960, 1) nm_fit_group_kernel(const FitArgs a) {
+  if (*a.mode != 1) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const Rings rg = carve_rings(smem_raw);
   double *V = reinterpret_cast<double *>(smem_raw + kFixedBytes);
@@ -469,28 +411,20 @@ __global__ void __launch_bounds__(512, 1) nm_fit_group_kernel(const FitArgs a) {
   if (warp >= nw) {
     producer_loop<false>(rg, a.records + rec0, n, n_on, nchunks, (uint32_t)nw * 8u, lane);
   } else {
-    const int64_t p0 = ((int64_t)blockIdx.x * nw + warp) * (32 * NB);
+    const int64_t p0 = ((int64_t)blockIdx.x * nw + warp) * 32;
+    const int64_t p = p0 + lane;
     const bool alive = p0 < a.P;  // warp-uniform
     const double alpha = alive ? a.alpha[p0] : 0.0, gamma = alive ? a.gamma[p0] : 0.0;
-    double beta[NB];
-#pragma unroll
-    for (int j = 0; j < NB; ++j) {
-      const int64_t p = p0 + j * 32 + lane;
-      beta[j] = p < a.P ? a.beta[p] : 0.0;
-    }
+    const double beta = p < a.P ? a.beta[p] : 0.0;
     double *Vcol = V + warp;
     for (int s = lane; s < a.num_states; s += 32)
       Vcol[s * nw] = a.v_init ? a.v_init[a.tile_of_state[s]] : 0.0;  // rl.py:63-66 (shared initial table)
     __syncwarp();
     char *vb = reinterpret_cast<char *>(Vcol);
-    double ll[NB];
-    GroupAcc<NB> acc;
-#pragma unroll
-    for (int j = 0; j < NB; ++j) {
-      ll[j] = 0.0;
-      acc.acc_obs[j] = 0.0;
-      acc.prod[j] = 1.0;
-    }
+    double ll = 0.0;
+    ExactAcc acc;
+    acc.acc_obs = 0.0;
+    acc.prod = 1.0;
     acc.er.load(smem_u32(smem_raw + kBarBytes + kRawBytes + kDecBytes));
     for (int c = 0; c < nchunks; ++c) {
       const int dslot = c % kDecStages;
@@ -499,32 +433,25 @@ __global__ void __launch_bounds__(512, 1) nm_fit_group_kernel(const FitArgs a) {
       const int64_t first = (int64_t)c * kChunk;
       const int cnt = (int)(n - first < kChunk ? n - first : kChunk);
 #pragma unroll 1
-      for (int i = 0; i < cnt; ++i) group_step<ALG, NB>(recs + 4 * i, vb, alpha, beta, gamma, acc);
-#pragma unroll
-      for (int j = 0; j < NB; ++j) {  // fold the chunk exactly like the exact kernel
-        ll[j] = __dadd_rn(ll[j], __dsub_rn(acc.acc_obs[j], log(acc.prod[j])));
-        acc.acc_obs[j] = 0.0;
-        acc.prod[j] = 1.0;
-      }
+      for (int i = 0; i < cnt; ++i) exact_step<ALG, true>(recs + 4 * i, vb, alpha, beta, gamma, acc);
+      ll = __dadd_rn(ll, __dsub_rn(acc.acc_obs, log(acc.prod)));  // fold the chunk exactly like the exact kernel
+      acc.acc_obs = 0.0;
+      acc.prod = 1.0;
       __syncwarp();
       if (lane == 0) mbar_arrive(&rg.empty_dec[dslot]);
     }
-#pragma unroll
-    for (int j = 0; j < NB; ++j) {
-      const int64_t p = p0 + j * 32 + lane;
-      if (p < a.P && a.ll_out) a.ll_out[(int64_t)sess * a.P + p] = ll[j];
-    }
+    if (p < a.P && a.ll_out) a.ll_out[(int64_t)sess * a.P + p] = ll;
   }
   if (a.v_out) {  // every parameter set of a run receives the run's table
     __syncthreads();
-    const int64_t pc = (int64_t)blockIdx.x * nw * (32 * NB);
-    const int64_t np = (a.P - pc < (int64_t)nw * 32 * NB) ? (a.P - pc) : (int64_t)nw * 32 * NB;
+    const int64_t pc = (int64_t)blockIdx.x * nw * 32;
+    const int64_t np = (a.P - pc < (int64_t)nw * 32) ? (a.P - pc) : (int64_t)nw * 32;
     const int nT = a.n_tiles;
     double *dst = a.v_out + ((int64_t)sess * a.P + pc) * nT;
     for (int64_t i = tid; i < np * nT; i += blockDim.x) {
       const int u = (int)(i / nT), tile = (int)(i - (int64_t)u * nT);
       const int st = a.state_of_tile[tile];
-      dst[i] = st >= 0 ? V[st * nw + u / (32 * NB)] : (a.v_init ? a.v_init[tile] : 0.0);
+      dst[i] = st >= 0 ? V[st * nw + (u >> 5)] : (a.v_init ? a.v_init[tile] : 0.0);
     }
   }
 }

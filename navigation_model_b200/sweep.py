@@ -417,9 +417,9 @@ class ConditioningSweep:
 
     def last_sweep_mode(self):
         """Kernel the last :meth:`log_likelihood_device` on the current stream used: 0 = a value table per parameter
-        set, 1 / 2 = a table per warp shared by aligned runs of 32 / 64 consecutive parameter sets with equal
-        ``(alpha, gamma)`` (order the grid with beta fastest, ``parameter_grid(gamma, alpha, beta)``, to get there).
-        Synchronises the stream."""
+        set, 1 = a table per warp shared by an aligned run of 32 consecutive parameter sets with equal
+        ``(alpha, gamma)`` (order the grid with beta fastest, ``parameter_grid(gamma, alpha, beta)``, and give the beta
+        axis a multiple of 32 points to get there).  Synchronises the stream."""
         torch = self._ensure_device()
         mode = C.c_int(-1)
         with torch.cuda.device(self.torch_device):

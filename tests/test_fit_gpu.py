@@ -195,10 +195,9 @@ def test_full_grid_properties(cuda):
 @pytest.mark.parametrize("alg", ["td0", "positive", "negative"])
 @pytest.mark.parametrize("n_beta", [64, 128, 32, 160])
 def test_group_kernels_match_exact_kernel_and_oracle(cuda, alg, n_beta, monkeypatch):
-    """Grids whose beta axis varies fastest: aligned runs of consecutive parameter sets share (alpha, gamma) and the
-    warp-shared-table kernels take over -- two sets per lane when every aligned run of 64 is uniform (n_beta = 64,
-    128), one set per lane when only the runs of 32 are (n_beta = 32, 160).  Their results must be bit-identical to
-    the exact kernel's (same operation sequence per parameter set) and agree with the oracle."""
+    """Grids whose beta axis varies fastest: aligned runs of 32 consecutive parameter sets share (alpha, gamma) and
+    the warp-shared-table kernel takes over.  Its results must be bit-identical to the exact kernel's (same operation
+    sequence per parameter set) and agree with the oracle."""
     omz = H.oracle_m9()
     sessions = [O.synthetic_session(omz, sid, T) for sid, T in ((0, 700), (4, 97), (5, 1))]
     if alg == "negative":
@@ -214,7 +213,7 @@ def test_group_kernels_match_exact_kernel_and_oracle(cuda, alg, n_beta, monkeypa
     v0 = rng.random((9, 9))
     sw = _sweep(alg, sessions, replay_n_times=1, replay_seed=3)
     ll, V = sw.log_likelihood(a, b, g, v_init=v0, return_v=True)
-    assert sw.last_sweep_mode() == (2 if n_beta % 64 == 0 else 1)  # the shared-table kernel really ran
+    assert sw.last_sweep_mode() == 1  # the shared-table kernel really ran
     monkeypatch.setenv("NM_FIT_GROUP", "0")
     ll_x, V_x = sw.log_likelihood(a, b, g, v_init=v0, return_v=True)
     assert sw.last_sweep_mode() == 0

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Time of one wave of the warp-shared-table fit kernel (two parameter sets per lane) as a function of its consumer
-warps per CTA (NM_FIT_GROUP_NW): one CTA per SM, 148 * nw * 64 parameter sets.
+"""Time of one wave of the warp-shared-table fit kernel as a function of its consumer warps per CTA
+(NM_FIT_GROUP_NW): one CTA per SM, 148 * nw * 32 parameter sets.
 
     python tools/fit_group_sweep.py            # prints nw, kernel ms, parameter sets / (SM ms)"""
 import json
@@ -27,12 +27,12 @@ def main():
     dev = torch.device("cuda", 0)
     rng = np.random.default_rng(0)
     mult = int(os.environ.get("SWEEP_CTAS_PER_SM", "1"))  # co-resident CTAs per SM (small CTAs only)
-    for nw in [int(x) for x in (sys.argv[1:] or range(14, 0, -1))]:
+    for nw in [int(x) for x in (sys.argv[1:] or range(28, 0, -4))]:
         os.environ["NM_FIT_GROUP_NW"] = str(nw)
-        runs = 148 * nw * mult
-        P = runs * 64
-        a = torch.from_numpy(np.repeat(rng.uniform(0.01, 1, runs), 64)).to(dev)
-        g = torch.from_numpy(np.repeat(rng.uniform(0.5, 0.99, runs), 64)).to(dev)
+        runs = 148 * nw * mult  # uniform runs of 32 parameter sets, one per consumer warp
+        P = runs * 32
+        a = torch.from_numpy(np.repeat(rng.uniform(0.01, 1, runs), 32)).to(dev)
+        g = torch.from_numpy(np.repeat(rng.uniform(0.5, 0.99, runs), 32)).to(dev)
         b = torch.from_numpy(rng.uniform(0.1, 30, P)).to(dev)
         ll = torch.empty((1, P), dtype=torch.float64, device=dev)
         best = 1e9
@@ -44,7 +44,7 @@ def main():
             torch.cuda.synchronize()
             if rep:
                 best = min(best, e0.elapsed_time(e1))
-        print(json.dumps({"nw": nw, "kernel_ms": best, "ctas_per_sm": mult, "sets_per_sm_ms": mult * nw * 64 / best,
+        print(json.dumps({"nw": nw, "kernel_ms": best, "ctas_per_sm": mult, "sets_per_sm_ms": P / 148 / best,
                           "updates_per_s": P * 4999 / (best * 1e-3)}), flush=True)
 
 
