@@ -292,7 +292,7 @@ def other_paths(local, world, rank, dist, dev):
                     "1 value-iteration sweep per step (extension: parity against this repo's numpy oracle only)"}
     # ---- Q-table agent ------------------------------------------------------------------------------------
     traj9, rew9 = O.synthetic_session(O.OracleMaze(O.M9_LAYOUT, O.M9_SIZE_TILE), 0, T_STEPS)
-    aq, bq, gq = parameter_grid(np.linspace(0.01, 1, 64), np.logspace(-1, 1.5, 64), np.linspace(0.5, 0.99, 32))
+    gq, aq, bq = parameter_grid(np.linspace(0.5, 0.99, 32), np.linspace(0.01, 1, 64), np.logspace(-1, 1.5, 64))
     ql = QLearningSweep(maze, acts, device=local)
     ql.add_session(traj9, rew9)
     k_ms, e2e_s = [], []

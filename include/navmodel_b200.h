@@ -363,6 +363,12 @@ int nm_qtable_sweep(const nm_maze *mz, const nm_streams *st, const int16_t *d_ne
                     const double *d_alpha, const double *d_beta, const double *d_gamma, int64_t P,
                     const double *d_q_init, double *d_ll_out, double *d_q_out, void *stream);
 
+/* Which kernel the last nm_qtable_sweep on `stream` (current device) used: 0 = one table per parameter set (eight
+ * lanes each), 1 = one table per warp, shared by an aligned run of 32 consecutive parameter sets with equal
+ * (alpha, gamma) -- checked on the device, bit-identical results; NM_Q_GROUP=0 forces 0.  Synchronises the stream:
+ * diagnostics and tests only. */
+int nm_qtable_sweep_mode(void *stream, int *mode_out);
+
 /* ------------------------------------------------------------------------------------------------
  * Batched distances between per-mouse metric results and data metrics (analysis/statistics.py:10-103)
  * ---------------------------------------------------------------------------------------------- */

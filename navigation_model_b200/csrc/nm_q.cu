@@ -17,7 +17,21 @@
 //   * update: Q[s, a] += alpha * (r + gamma * max_{a' avail at s1} Q[s1, a'] - Q[s, a]), bootstrap 0 when s1 has no
 //     available action.  _rn intrinsics only (no FMA contraction): tables are bit-identical to the numpy oracle.
 // Replay records (past the session's online count) update the table without contributing to the likelihood.
+//
+// Second mapping (nm_qgroup_kernel), taken when every aligned run of 32 consecutive parameter sets shares (alpha,
+// gamma) -- a Cartesian grid with beta fastest; the device checks the arrays itself (nm_qgroup_detect_kernel): the
+// table depends on (alpha, gamma) only, so a WARP keeps ONE table Q[state * 8 + action][warp] for its 32 sets and
+// lane l evaluates the softmax of set p0 + l.  Table loads are broadcasts, every lane stores the same updated value.
+// A producer warp TMA-stages the raw records (cp.async.bulk + mbarrier), derives the action lists of s and s1 and
+// the observed action ONCE per CTA and hands 80-byte decoded records to the consumer warps through mbarriers.  Per
+// parameter set the operations are those of the octet kernel, in the same order: results are bit-identical.
 #include <cuda_runtime.h>
+
+#include <stdlib.h>
+
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "nm_common.h"
 
@@ -26,6 +40,8 @@ namespace {
 constexpr unsigned kFull = 0xffffffffu;
 
 #include "nm_exp.cuh"
+#include "nm_ring.cuh"
+#include "nm_step_math.cuh"
 
 struct QArgs {
   const nm_step_rec *records;
@@ -39,6 +55,7 @@ struct QArgs {
   int n_tiles;
   const int32_t *tile_of_state, *state_of_tile;
   double *ll_out, *q_out;
+  const int *mode;  // device word set by nm_qgroup_detect_kernel: 0 octet kernel, 1 group kernel; NULL: always run
 };
 
 __device__ __forceinline__ double dmax2(double a, double b) { return (b > a) ? b : a; }
@@ -55,6 +72,7 @@ __device__ __forceinline__ void octet_max2(double &a, double &b) {
 }
 
 __global__ void __launch_bounds__(512) nm_q_kernel(const QArgs a) {
+  if (a.mode && *a.mode != 0) return;  // the group kernel owns this sweep
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int S = a.S, A = a.A;
   const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -163,6 +181,259 @@ __global__ void __launch_bounds__(512) nm_q_kernel(const QArgs a) {
   }
 }
 
+// =================================== one table per warp =======================================================
+constexpr int kQChunk = 32;     // records per chunk = one per producer lane
+constexpr int kQRawStages = 2;  // raw (TMA landing) ring
+constexpr int kQDecStages = 4;  // decoded ring
+constexpr int kQDecWords = 5;   // uint4 per decoded record (80 bytes)
+constexpr int kQBarBytes = 128;
+constexpr int kQRawBytes = kQRawStages * kQChunk * 32;
+constexpr int kQDecBytes = kQDecStages * kQChunk * kQDecWords * 16;
+constexpr int kQTabBytes = 128;  // 2^(j/16)
+constexpr int kQFixedBytes = kQBarBytes + kQRawBytes + kQDecBytes + kQTabBytes;
+constexpr uint32_t kQOnline = 1u << 8, kQHit = 1u << 9, kQBoot = 1u << 10;
+
+// decoded record (byte offsets = table row * row_bytes; row = state * 8 + action; the row past the table holds -inf):
+//   q0 = {r.lo, r.hi, K1 | kQOnline | kQHit | kQBoot, offset of the updated entry (s, observed action)}
+//   q1, q2 = the K1 available actions of s, in action order (softmax candidates)
+//   q3, q4 = the eight actions of s1 (unavailable ones point at the -inf row)
+struct QRings {
+  uint64_t *full_raw, *full_dec, *empty_dec;
+  uint4 *raw, *dec;
+};
+
+// mode[0] = 1 if every aligned run of 32 parameter sets shares (alpha, gamma), else 0
+__global__ void nm_qgroup_init_kernel(int *mode, int value) { mode[0] = value; }
+__global__ void __launch_bounds__(256) nm_qgroup_detect_kernel(const double *__restrict__ alpha,
+                                                               const double *__restrict__ gamma, int64_t P, int *mode) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const int64_t head = p & ~(int64_t)31;
+  if (__double_as_longlong(alpha[p]) != __double_as_longlong(alpha[head]) ||
+      __double_as_longlong(gamma[p]) != __double_as_longlong(gamma[head]))
+    mode[0] = 0;
+}
+
+__device__ __forceinline__ void q_producer_loop(const QRings &rg, const nm_step_rec *src, int64_t n, int64_t n_on,
+                                                int nchunks, const int16_t *nxt8, uint32_t row_bytes, uint32_t sentinel,
+                                                int lane) {
+  auto issue = [&](int c) {
+    const int slot = c % kQRawStages;
+    const int64_t first = (int64_t)c * kQChunk;
+    const uint32_t bytes = (uint32_t)((n - first < kQChunk ? n - first : kQChunk) * 32);
+    mbar_expect_tx(&rg.full_raw[slot], bytes);
+    tma_bulk_g2s(rg.raw + slot * (kQChunk * 2), src + first, bytes, &rg.full_raw[slot]);
+  };
+  if (lane == 0)
+    for (int c = 0; c < kQRawStages && c < nchunks; ++c) issue(c);
+  for (int c = 0; c < nchunks; ++c) {
+    const int rslot = c % kQRawStages, dslot = c % kQDecStages;
+    if (c >= kQDecStages) mbar_wait_relaxed(&rg.empty_dec[dslot], (uint32_t)(((c / kQDecStages) - 1) & 1));
+    mbar_wait_relaxed(&rg.full_raw[rslot], (uint32_t)((c / kQRawStages) & 1));
+    const int64_t first = (int64_t)c * kQChunk;
+    const int cnt = (int)(n - first < kQChunk ? n - first : kQChunk);
+    const int src_lane = lane < cnt ? lane : cnt - 1;
+    const uint4 w0 = rg.raw[(rslot * kQChunk + src_lane) * 2];
+    const int s = (int)(w0.z & 0xffffu), s1 = (int)(w0.z >> 16);
+    const uint4 n_s = *reinterpret_cast<const uint4 *>(nxt8 + s * 8), n_s1 = *reinterpret_cast<const uint4 *>(nxt8 + s1 * 8);
+    const uint32_t ws[4] = {n_s.x, n_s.y, n_s.z, n_s.w}, ws1[4] = {n_s1.x, n_s1.y, n_s1.z, n_s1.w};
+    uint32_t o1[8], o2[8];
+    uint32_t K1 = 0, upd = 0, flags = (first + lane < n_on) ? kQOnline : 0u;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o1[k] = sentinel;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int nk = (int)(int16_t)((k & 1) ? (ws[k >> 1] >> 16) : (ws[k >> 1] & 0xffffu));
+      const int n1 = (int)(int16_t)((k & 1) ? (ws1[k >> 1] >> 16) : (ws1[k >> 1] & 0xffffu));
+      const uint32_t off = (uint32_t)(s * 8 + k) * row_bytes;
+      if (nk >= 0) {
+        if (nk == s1 && !(flags & kQHit)) {  // observed action = first a with next[s, a] == s1
+          flags |= kQHit;
+          upd = off;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if ((uint32_t)j == K1) o1[j] = off;
+        ++K1;
+      }
+      o2[k] = n1 >= 0 ? (uint32_t)(s1 * 8 + k) * row_bytes : sentinel;
+      if (n1 >= 0) flags |= kQBoot;
+    }
+    if (lane < cnt) {
+      uint4 *d = rg.dec + (dslot * kQChunk + lane) * kQDecWords;
+      d[0] = make_uint4(w0.x, w0.y, K1 | flags, upd);
+      d[1] = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+      d[2] = make_uint4(o1[4], o1[5], o1[6], o1[7]);
+      d[3] = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+      d[4] = make_uint4(o2[4], o2[5], o2[6], o2[7]);
+    }
+    mbar_arrive(&rg.full_dec[dslot]);  // every lane: releases its own stores (count = 32)
+    __syncwarp();                      // all lanes have read the raw slot before it is refilled
+    if (lane == 0 && c + kQRawStages < nchunks) issue(c + kQRawStages);
+  }
+}
+
+struct QAcc {
+  double acc_obs, prod;
+  ExpRegs er;
+};
+
+template <int K1>
+__device__ __forceinline__ void qgroup_step_k(const uint4 q0, const uint4 q1, const uint4 q2, const uint4 q3,
+                                              const uint4 q4, char *qb, const double alpha, const double beta,
+                                              const double gamma, QAcc &acc) {
+  const double r = __hiloint2double((int)q0.y, (int)q0.x);
+  double *pu = reinterpret_cast<double *>(qb + q0.w);
+  const double q = *pu;  // Q[s, observed action]
+  const uint32_t o2[8] = {q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, q4.z, q4.w};
+  double w[NM_MAX_CAND];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) w[k] = lds_f64(qb, o2[k]);
+  double boot = extremum<NM_ALG_POSITIVE, 8>(w);  // unavailable actions read -inf
+  if (!(q0.z & kQBoot)) boot = 0.0;
+  if (q0.z & kQOnline) {
+    const uint32_t o1[8] = {q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+    double v[NM_MAX_CAND], z[NM_MAX_CAND], e[NM_MAX_CAND];
+#pragma unroll
+    for (int k = 0; k < K1; ++k) v[k] = lds_f64(qb, o1[k]);
+#pragma unroll
+    for (int k = 0; k < K1; ++k) z[k] = __dmul_rn(beta, v[k]);  // exploration_model.py:87
+    // beta >= 0: max_k fl(beta * v_k) == fl(beta * max_k v_k), rounding is monotonic
+    const double m = (beta >= 0.0) ? __dmul_rn(beta, extremum<NM_ALG_POSITIVE, K1>(v)) : extremum<NM_ALG_POSITIVE, K1>(z);
+#pragma unroll
+    for (int k = 0; k < K1; ++k) e[k] = acc.er.exp_nonpos(dmax(__dsub_rn(z[k], m), -800.0));  // :92-93
+    acc.acc_obs = __dadd_rn(acc.acc_obs, __dsub_rn(__dmul_rn(beta, q), m));
+    acc.prod = __dmul_rn(acc.prod, np_sum_fixed<K1>(e));
+  }
+  const double rpe = __dsub_rn(__dadd_rn(r, __dmul_rn(gamma, boot)), q);  // update form of rl.py:185
+  *pu = __dadd_rn(q, __dmul_rn(alpha, rpe));                               // rl.py:186-187
+}
+
+__device__ __forceinline__ void qgroup_step(const uint4 *__restrict__ rec, char *qb, const double alpha, const double beta,
+                                            const double gamma, QAcc &acc) {
+  const uint4 q0 = rec[0];
+  if (!(q0.z & kQHit)) return;  // no observed action: the step is skipped entirely (warp-uniform)
+  const uint4 q1 = rec[1], q2 = rec[2], q3 = rec[3], q4 = rec[4];
+#define NM_CASE(KK) \
+  case KK: qgroup_step_k<KK>(q0, q1, q2, q3, q4, qb, alpha, beta, gamma, acc); break;
+  switch (q0.z & 0xffu) {  // K1, warp-uniform (>= 1 on a hit)
+    NM_CASE(1) NM_CASE(2) NM_CASE(3) NM_CASE(4) NM_CASE(5) NM_CASE(6) NM_CASE(7) NM_CASE(8)
+    default: break;
+  }
+#undef NM_CASE
+}
+
+// Runs only when *a.mode == 1.  blockDim.x = 32 * (nw + 1): nw consumer warps, each with its own table
+// Q[state * 8 + action][warp] (+ one row of -inf), and the producer warp.
+__global__ void __launch_bounds__(960, 1) nm_qgroup_kernel(const QArgs a) {
+  if (*a.mode != 1) return;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int S = a.S, A = a.A;
+  QRings rg;
+  rg.full_raw = reinterpret_cast<uint64_t *>(smem_raw);
+  rg.full_dec = rg.full_raw + kQRawStages;
+  rg.empty_dec = rg.full_dec + kQDecStages;
+  rg.raw = reinterpret_cast<uint4 *>(smem_raw + kQBarBytes);
+  rg.dec = reinterpret_cast<uint4 *>(smem_raw + kQBarBytes + kQRawBytes);
+  double *exptab = reinterpret_cast<double *>(smem_raw + kQBarBytes + kQRawBytes + kQDecBytes);
+  int16_t *nxt8 = reinterpret_cast<int16_t *>(smem_raw + kQFixedBytes);
+  const size_t nxt_bytes = ((size_t)S * 16 + 127) & ~(size_t)127;
+  double *Q = reinterpret_cast<double *>(smem_raw + kQFixedBytes + nxt_bytes);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nw = (blockDim.x >> 5) - 1;
+  if (tid < 16) exptab[tid] = c_exp2tab[tid];
+  for (int i = tid; i < S * 8; i += blockDim.x) {
+    const int u = i >> 3, kk = i & 7;
+    nxt8[i] = kk < A ? a.next[u * A + kk] : (int16_t)-1;
+  }
+  const int sess = blockIdx.y;
+  const int64_t rec0 = a.offsets[sess];
+  const int64_t n = a.offsets[sess + 1] - rec0, n_on = a.online[sess];
+  const int nchunks = (int)((n + kQChunk - 1) / kQChunk);
+  if (tid == 0) {
+    for (int i = 0; i < kQRawStages; ++i) mbar_init(&rg.full_raw[i], 1);
+    for (int i = 0; i < kQDecStages; ++i) {
+      mbar_init(&rg.full_dec[i], 32);
+      mbar_init(&rg.empty_dec[i], nw);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int rows = S * 8;
+  if (warp >= nw) {
+    q_producer_loop(rg, a.records + rec0, n, n_on, nchunks, nxt8, (uint32_t)nw * 8u, (uint32_t)rows * (uint32_t)nw * 8u,
+                    lane);
+  } else {
+    const int64_t p0 = ((int64_t)blockIdx.x * nw + warp) * 32;
+    const int64_t p = p0 + lane;
+    const bool alive = p0 < a.P;  // warp-uniform
+    const double alpha = alive ? a.alpha[p0] : 0.0, gamma = alive ? a.gamma[p0] : 0.0;
+    const double beta = p < a.P ? a.beta[p] : 0.0;
+    double *Qcol = Q + warp;
+    for (int e = lane; e < rows; e += 32) {
+      const int u = e >> 3, kk = e & 7;
+      Qcol[e * nw] = (a.q_init && kk < A) ? a.q_init[(int64_t)a.tile_of_state[u] * A + kk] : 0.0;
+    }
+    if (lane == 0) Qcol[rows * nw] = -INFINITY;
+    __syncwarp();
+    char *qb = reinterpret_cast<char *>(Qcol);
+    double ll = 0.0;
+    QAcc acc;
+    acc.acc_obs = 0.0;
+    acc.prod = 1.0;
+    acc.er.load(smem_u32(exptab));
+    for (int c = 0; c < nchunks; ++c) {
+      const int dslot = c % kQDecStages;
+      mbar_wait(&rg.full_dec[dslot], (uint32_t)((c / kQDecStages) & 1));
+      const uint4 *recs = rg.dec + dslot * (kQChunk * kQDecWords);
+      const int64_t first = (int64_t)c * kQChunk;
+      const int cnt = (int)(n - first < kQChunk ? n - first : kQChunk);
+#pragma unroll 1
+      for (int i = 0; i < cnt; ++i) qgroup_step(recs + kQDecWords * i, qb, alpha, beta, gamma, acc);
+      ll = __dadd_rn(ll, __dsub_rn(acc.acc_obs, log(acc.prod)));  // the octet kernel folds every 32 records too
+      acc.acc_obs = 0.0;
+      acc.prod = 1.0;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&rg.empty_dec[dslot]);
+    }
+    if (p < a.P && a.ll_out) a.ll_out[(int64_t)sess * a.P + p] = ll;
+  }
+  if (a.q_out) {  // every parameter set of a run receives the run's table
+    __syncthreads();
+    const int64_t pc = (int64_t)blockIdx.x * nw * 32;
+    const int64_t np = (a.P - pc < (int64_t)nw * 32) ? (a.P - pc) : (int64_t)nw * 32;
+    const int64_t per_set = (int64_t)a.n_tiles * A;
+    double *dst = a.q_out + ((int64_t)sess * a.P + pc) * per_set;
+    for (int64_t i = tid; i < np * per_set; i += blockDim.x) {
+      const int u = (int)(i / per_set);
+      const int rest = (int)(i - (int64_t)u * per_set);
+      const int tile = rest / A, kk = rest - tile * A;
+      const int st = a.state_of_tile[tile];
+      dst[i] = st >= 0 ? Q[(st * 8 + kk) * nw + (u >> 5)] : (a.q_init ? a.q_init[(int64_t)tile * A + kk] : 0.0);
+    }
+  }
+}
+
+// one int of sweep mode per (device, stream), allocated on first use and kept for the life of the process
+int q_mode_word(void *stream, int **out) {
+  int device = 0;
+  cudaGetDevice(&device);
+  static std::mutex mu;
+  static std::map<std::pair<int, void *>, int *> words;
+  std::lock_guard<std::mutex> lock(mu);
+  const auto key = std::make_pair(device, stream);
+  auto it = words.find(key);
+  if (it == words.end()) {
+    int *buf = nullptr;
+    const cudaError_t e = cudaMalloc((void **)&buf, 64);
+    if (e != cudaSuccess) return nm_fail(NM_ERR_NOMEM, "nm_qtable_sweep: cudaMalloc: %s", cudaGetErrorString(e));
+    it = words.emplace(key, buf).first;
+  }
+  *out = it->second;
+  return NM_OK;
+}
+
 }  // namespace
 
 extern "C" int nm_qtable_sweep(const nm_maze *mz, const nm_streams *st, const int16_t *d_next, int n_actions,
@@ -222,11 +493,67 @@ extern "C" int nm_qtable_sweep(const nm_maze *mz, const nm_streams *st, const in
   a.state_of_tile = mz->d_state_of_tile;
   a.ll_out = d_ll_out;
   a.q_out = d_q_out;
+  cudaStream_t cs = (cudaStream_t)stream;
+  // Parameter sets that share (alpha, gamma) share their table: the device decides whether every aligned run of 32
+  // consecutive sets does, and exactly one of the two kernels does the work (the other returns at its first
+  // instruction) -- no host round trip.  NM_Q_GROUP=0 keeps the octet kernel (A/B runs, tests).
+  int *mode = nullptr;
+  const int rc = q_mode_word(stream, &mode);
+  if (rc != NM_OK) return rc;
+  a.mode = mode;
+  const char *env = getenv("NM_Q_GROUP");
+  const size_t g_fixed = kQFixedBytes + (((size_t)S * 16 + 127) & ~(size_t)127);
+  const size_t g_per_warp = ((size_t)S * 8 + 1) * sizeof(double);  // one table + the -inf row
+  int g_max = (int)(((size_t)227 * 1024 - g_fixed) / g_per_warp);
+  if (g_max > 29) g_max = 29;
+  if ((env && atoi(env) == 0) || g_max < 1 || (size_t)(S * 8 + 1) * g_max * 8 > 0xffffffffull) {
+    nm_qgroup_init_kernel<<<1, 1, 0, cs>>>(mode, 0);
+  } else {
+    nm_qgroup_init_kernel<<<1, 1, 0, cs>>>(mode, 1);
+    nm_qgroup_detect_kernel<<<(unsigned)((P + 255) / 256), 256, 0, cs>>>(d_alpha, d_gamma, P, mode);
+    // consumer warps per CTA: spread few runs over the SMs, else the fullest CTA (same staircase as the value-table
+    // group kernel: only the busiest scheduler's warp count matters, ties go to the smaller CTA)
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, mz->device);
+    const int64_t runs = (P + 31) / 32;
+    static const double kWave[9] = {0.0, 1.0, 1.12, 1.29, 1.45, 1.65, 1.91, 2.19, 2.50};
+    int nw = 1;
+    double best = 1e300;
+    const char *env_nw = getenv("NM_Q_GROUP_NW");
+    for (int c = 1; c <= g_max; ++c) {
+      const int64_t ctas = (int64_t)st->S * ((runs + c - 1) / c);
+      const int64_t waves = (ctas + sms - 1) / sms;
+      const double cost = (double)waves * kWave[(c + 3) / 4 > 8 ? 8 : (c + 3) / 4];
+      if (cost < best * 0.999) {
+        best = cost;
+        nw = c;
+      }
+    }
+    if (env_nw && atoi(env_nw) >= 1 && atoi(env_nw) <= g_max) nw = atoi(env_nw);
+    const size_t g_smem = g_fixed + g_per_warp * nw;
+    e = cudaFuncSetAttribute(nm_qgroup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_smem);
+    if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "cudaFuncSetAttribute(nm_qgroup_kernel): %s", cudaGetErrorString(e));
+    nm_qgroup_kernel<<<dim3((unsigned)((runs + nw - 1) / nw), (unsigned)st->S, 1), 32 * (nw + 1), g_smem, cs>>>(a);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_qgroup_kernel launch: %s", cudaGetErrorString(e));
+  }
   const int64_t per_cta = (int64_t)warps * 4;
   const int64_t blocks = (P + per_cta - 1) / per_cta;
   NM_CHECK_ARG(blocks <= 2147483647LL, "nm_qtable_sweep: too many parameter sets for one launch");
-  nm_q_kernel<<<dim3((unsigned)blocks, (unsigned)st->S, 1), warps * 32, smem, (cudaStream_t)stream>>>(a);
+  nm_q_kernel<<<dim3((unsigned)blocks, (unsigned)st->S, 1), warps * 32, smem, cs>>>(a);
   e = cudaGetLastError();
   if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_q_kernel launch: %s", cudaGetErrorString(e));
+  return NM_OK;
+}
+
+extern "C" int nm_qtable_sweep_mode(void *stream, int *mode_out) {
+  NM_CHECK_ARG(mode_out, "nm_qtable_sweep_mode: NULL output");
+  int *mode = nullptr;
+  const int rc = q_mode_word(stream, &mode);
+  if (rc != NM_OK) return rc;
+  // synchronous by design (diagnostics / tests): waits for the stream, then reads the word the device set
+  cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+  if (e == cudaSuccess) e = cudaMemcpy(mode_out, mode, sizeof(int), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_qtable_sweep_mode: %s", cudaGetErrorString(e));
   return NM_OK;
 }

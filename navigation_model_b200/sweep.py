@@ -700,6 +700,17 @@ class QLearningSweep(_TileActionSweep):
             _native.cuda_stream_ptr()))  # last_kernel_ms: device time of nm_q_kernel
         return ll_out
 
+    def last_sweep_mode(self):
+        """Kernel the last sweep on the current stream used: 0 = a table per parameter set (eight lanes each), 1 = a
+        table per warp shared by an aligned run of 32 consecutive parameter sets with equal ``(alpha, gamma)`` (order
+        the grid with beta fastest, ``parameter_grid(gamma, alpha, beta)``).  Synchronises the stream."""
+        b = self._base
+        torch = b._ensure_device()
+        mode = C.c_int(-1)
+        with torch.cuda.device(b.torch_device):
+            _native.check(b._dmaze._lib.nm_qtable_sweep_mode(_native.cuda_stream_ptr(), C.byref(mode)))
+        return mode.value
+
     def log_likelihood(self, alpha, beta, gamma, q_init=None, return_tables=False):
         """``float64[S, P]`` log-likelihoods (and, optionally, the final tables ``Q[S, P, X, Y, A]``; entries of
         non-visitable tiles and unavailable actions keep their initial value)."""

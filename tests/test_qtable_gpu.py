@@ -90,3 +90,53 @@ def test_qtable_extreme_beta_empty_session_and_best_fit(cuda):
     assert idx == int(np.argmin(-want)) and abs(nll + want[idx]) <= 1e-9 * abs(want[idx])
     with pytest.raises(ValueError):
         ql.log_likelihood(a, b, g, q_init=np.zeros((3, 3, 8)))
+
+
+@pytest.mark.parametrize("maze_name,acts", [("m9", ACTS8), ("m9", ACTS5), ("m20", ACTS8)])
+def test_qtable_group_kernel_matches_octet_kernel_and_oracle(cuda, maze_name, acts, monkeypatch):
+    """A grid whose beta axis varies fastest: aligned runs of 32 parameter sets share (alpha, gamma), the table lives
+    once per warp (nm_qgroup_kernel).  Bit-identical to the octet kernel (same operations per parameter set), tables
+    bit-exact and likelihoods to 1e-9 against the oracle; incomplete last run, replays, initial table, beta < 0."""
+    from navigation_model_b200.simulation.maze import Maze
+    from navigation_model_b200.sweep import QLearningSweep
+    if maze_name == "m9":
+        omz, maze = H.oracle_m9(), H.product_m9()
+        sessions = [O.synthetic_session(omz, sid, T) for sid, T in ((0, 600), (3, 97), (5, 1))]
+    else:
+        layout = "\n".join(["M" * 20] * 20)
+        maze, omz = Maze(layout, "", size_tile=0.05), O.OracleMaze(layout, 0.05)
+        sessions = [O.synthetic_session(omz, 1, 300, start=(3, 3), goal=(15, 12), jitter=0.02)]
+    nxt = O.transition_table(omz, acts)
+    rng = np.random.default_rng(21)
+    pairs, n_beta = 4, 32
+    a = np.repeat(rng.uniform(0.01, 1, pairs), n_beta)
+    g = np.repeat(rng.uniform(0.5, 0.99, pairs), n_beta)
+    b = np.tile(np.logspace(-1, 1.5, n_beta), pairs)
+    P = a.size - 5
+    a, b, g = a[:P].copy(), b[:P].copy(), g[:P].copy()
+    b[7] = -b[7]
+    q0 = rng.normal(size=(omz.X, omz.Y, len(acts)))
+    ql = QLearningSweep(maze, acts, replay_n_times=1, replay_seed=9)
+    for traj, rew in sessions:
+        ql.add_session(traj, rew)
+    ll, Q = ql.log_likelihood(a, b, g, q_init=q0, return_tables=True)
+    assert ql.last_sweep_mode() == 1  # the warp-shared-table kernel really ran
+    monkeypatch.setenv("NM_Q_GROUP", "0")
+    ll_x, Q_x = ql.log_likelihood(a, b, g, q_init=q0, return_tables=True)
+    assert ql.last_sweep_mode() == 0
+    monkeypatch.delenv("NM_Q_GROUP")
+    assert np.array_equal(ll, ll_x) and np.array_equal(Q, Q_x)
+    q0c = np.array([q0[x, y] for x, y in omz.vis_cells])
+    for j, (traj, rew) in enumerate(sessions):
+        tr = O.extract_transitions(omz, traj, rew, None)
+        orders = O.replay_orders(len(tr["s"]), 1, 9)
+        for p in (0, 31, 32, P - 1):
+            Qw, llw = O.run_q_learning(tr, nxt, a[p], b[p], g[p], q0=q0c, orders=orders)
+            assert np.array_equal(Q[j, p], _dense_q(omz, Qw, fill=q0)), (j, p)
+            assert abs(ll[j, p] - llw) <= 1e-9 * abs(llw) + 1e-300, (j, p)
+    # a run that is not uniform keeps the octet kernel
+    g2 = g.copy()
+    g2[40] = 0.777
+    ql.log_likelihood(a, b, g2)
+    assert ql.last_sweep_mode() == 0
+

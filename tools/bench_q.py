@@ -38,7 +38,8 @@ def main():
         omz = O.OracleMaze(layout, 0.05)
         traj, rew = O.synthetic_session(omz, 0, args.steps, start=(3, 3), goal=(15, 12), jitter=0.02)
     na, nb, ng = args.grid
-    a, b, g = parameter_grid(np.linspace(0.01, 1, na), np.logspace(-1, 1.5, nb), np.linspace(0.5, 0.99, ng))
+    # beta fastest: runs of 32 consecutive parameter sets share (alpha, gamma) and with it their table
+    g, a, b = parameter_grid(np.linspace(0.5, 0.99, ng), np.linspace(0.01, 1, na), np.logspace(-1, 1.5, nb))
     P = a.size
     ql = QLearningSweep(maze, acts, device=0)
     ql.add_session(traj, rew)
@@ -61,7 +62,7 @@ def main():
     upd = P * (args.steps - 1)
     k_ms = min(kern[1:])
     print(json.dumps({"metric": "agent-trial updates/s (Q-table agent, %s maze, 8 actions)" % args.maze,
-                      "value": upd / (k_ms * 1e-3), "kernel_ms": k_ms, "params": P, "steps": args.steps,
+                      "value": upd / (k_ms * 1e-3), "kernel_ms": k_ms, "sweep_mode": ql.last_sweep_mode(), "params": P, "steps": args.steps,
                       "seconds_best_incl_h2d_d2h": min(wall[1:]), "oracle_max_rel_err": chk,
                       "cpu_numpy_oracle_1core_updates_per_s": cpu}))
 
