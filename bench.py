@@ -288,8 +288,27 @@ def other_paths(local, world, rank, dist, dev):
     out["model_based"] = {
         "metric": "agent-trial updates/s", "value": upd / k, "e2e_value": upd / e, "kernel_ms": k * 1e3,
         "state_action_backups_per_s": upd * 400 * 8 / k,
-        "workload": f"{Pm} parameter sets x {mb.updates_per_parameter_set} steps per GPU, 400-state maze, 8 actions, "
-                    "1 value-iteration sweep per step (extension: parity against this repo's numpy oracle only)"}
+        "workload": f"{Pm} ARBITRARY parameter sets x {mb.updates_per_parameter_set} steps per GPU, 400-state maze, 8 "
+                    "actions, 1 value-iteration sweep per step, a warp per parameter set (extension: parity against "
+                    "this repo's numpy oracle only)"}
+    # the same agent on a Cartesian grid with beta fastest: runs of 32 sets share (alpha, gamma), hence V, Rhat and the
+    # planning sweeps -- a warp per run
+    ag, gg, bg = parameter_grid(np.linspace(0.01, 1, 25), np.linspace(0.5, 0.99, 25), np.logspace(-1, 1.5, 32))
+    k_ms, e2e_s = [], []
+    for rep in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        mb.log_likelihood(ag, bg, gg)
+        e2e_s.append(time.perf_counter() - t0)
+        k_ms.append(mb.last_kernel_ms)
+    k = max_over_ranks(min(k_ms[1:])) * 1e-3
+    e = max_over_ranks(min(e2e_s[1:]))
+    upd = world * ag.size * mb.updates_per_parameter_set
+    out["model_based_grid"] = {
+        "metric": "agent-trial updates/s", "value": upd / k, "e2e_value": upd / e, "kernel_ms": k * 1e3,
+        "sweep_mode": mb.last_sweep_mode(),
+        "workload": f"{ag.size} parameter sets = 25 x 25 (alpha, gamma) x 32 beta, beta fastest, x "
+                    f"{mb.updates_per_parameter_set} steps per GPU, same maze: tables and sweeps once per run of 32 sets"}
     # ---- Q-table agent ------------------------------------------------------------------------------------
     traj9, rew9 = O.synthetic_session(O.OracleMaze(O.M9_LAYOUT, O.M9_SIZE_TILE), 0, T_STEPS)
     gq, aq, bq = parameter_grid(np.linspace(0.5, 0.99, 32), np.linspace(0.01, 1, 64), np.logspace(-1, 1.5, 64))
@@ -490,7 +509,7 @@ def run_b200(args):
                 "target_updates_per_s_8gpu": 1e10}
         if extras is not None:
             line["also_measured"] = extras
-            line["gpu_launches"] += 9
+            line["gpu_launches"] += 12
         emit(line)
     if world > 1:
         dist.barrier()

@@ -348,6 +348,12 @@ int nm_modelbased_sweep(const nm_maze *mz, const nm_streams *st, const int16_t *
                         const double *d_alpha, const double *d_beta, const double *d_gamma, int64_t P,
                         const double *d_v_init, double *d_ll_out, double *d_v_out, double *d_r_out, void *stream);
 
+/* Which mapping the last nm_modelbased_sweep on `stream` (current device) used: 0 = a warp per parameter set,
+ * 1 = a warp per aligned run of 32 consecutive parameter sets with equal (alpha, gamma) -- V, Rhat and the
+ * value-iteration sweeps are then computed once per run (checked on the device, bit-identical results;
+ * NM_MB_GROUP=0 forces 0).  Synchronises the stream: diagnostics and tests only. */
+int nm_modelbased_sweep_mode(void *stream, int *mode_out);
+
 /* ------------------------------------------------------------------------------------------------
  * Tabular Q-learning agent with an explicit Q[s,a] table (EXTENSION, parity unpinned: the reference's learners keep
  * state values only, simulation/rl.py:154-262)

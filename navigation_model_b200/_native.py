@@ -66,6 +66,7 @@ SIGNATURES = {
     "nm_fp64_peak_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, _p, C.POINTER(_i64), _p]),
     "nm_modelbased_sweep": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, _p, _p, _p, _i64, _p, _p, _p, _p, _p]),
     "nm_qtable_sweep": (C.c_int, [_p, _p, _p, C.c_int, _p, _p, _p, _i64, _p, _p, _p, _p]),
+    "nm_modelbased_sweep_mode": (C.c_int, [_p, C.POINTER(C.c_int)]),
     "nm_qtable_sweep_mode": (C.c_int, [_p, C.POINTER(C.c_int)]),
     "nm_distance_rows": (C.c_int, [C.c_int, _p, _p, _i64, C.c_int, _p, _p]),
     "nm_simulate": (C.c_int, [_p, _p, _p]),

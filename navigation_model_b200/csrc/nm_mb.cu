@@ -20,11 +20,26 @@
 //     prologue picks a sentinel whose bank pair none of the group's available actions uses, and all unavailable
 //     lanes of the group share it (a broadcast).  With a single sentinel 22 % of the wavefronts were conflicts.
 // The V / Rhat recurrences use _rn intrinsics (no FMA contraction): tables are bit-identical to the numpy oracle.
+//
+// GROUP variant (nm_mb_kernel<true>): V and Rhat depend on (alpha, gamma) only -- beta enters the likelihood, not the
+// model or the planning -- so when every aligned run of 32 consecutive parameter sets shares (alpha, gamma) (a grid
+// with beta fastest; checked on the device, nm_group.cuh) a warp owns a RUN: the tables, the reward-model update and
+// the value-iteration sweeps -- almost all of the work -- are done once for the 32 sets, and lane l evaluates the
+// likelihood of set p0 + l from action values every lane loads as broadcasts.  Same operations per parameter set in
+// the same order: results are bit-identical to the warp-per-set kernel.
 #include <cuda_runtime.h>
+
+#include <stdlib.h>
+
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "nm_common.h"
 
 namespace {
+
+#include "nm_group.cuh"
 
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kSent = 16;  // sentinel slots in front of W (one per bank pair of a half-warp's 64-bit access)
@@ -40,6 +55,7 @@ struct MbArgs {
   int n_tiles;
   const int32_t *tile_of_state, *state_of_tile;
   double *ll_out, *v_out, *r_out;
+  const int *mode;  // device word set by nm_runs_detect_kernel: 0 warp-per-set kernel, 1 warp-per-run kernel
 };
 
 __device__ __forceinline__ double dmax2(double a, double b) { return (b > a) ? b : a; }
@@ -68,7 +84,9 @@ __device__ __forceinline__ double row_max(uint32_t w_base, const uint4 row) {
   return best;
 }
 
+template <bool GROUP>
 __global__ void __launch_bounds__(512) nm_mb_kernel(const MbArgs a) {
+  if (*a.mode != (GROUP ? 1 : 0)) return;  // the other mapping owns this sweep
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int S = a.S, A = a.A;
   const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -96,9 +114,12 @@ __global__ void __launch_bounds__(512) nm_mb_kernel(const MbArgs a) {
   }
 
   const int sess = blockIdx.y;
-  const int64_t p = (int64_t)blockIdx.x * warps + warp;
+  // the warp's unit: one parameter set, or (GROUP) a run of 32 sets of which lane l evaluates set p + l
+  const int64_t p = ((int64_t)blockIdx.x * warps + warp) * (GROUP ? 32 : 1);
   const bool live = p < a.P;
-  const double alpha = live ? a.alpha[p] : 0.0, beta = live ? a.beta[p] : 0.0, gamma = live ? a.gamma[p] : 0.0;
+  const double alpha = live ? a.alpha[p] : 0.0, gamma = live ? a.gamma[p] : 0.0;
+  const int64_t pl = GROUP ? p + lane : p;
+  const double beta = pl < a.P ? a.beta[pl] : 0.0;
   for (int u = lane; u < S; u += 32) {
     V[u] = a.v_init ? a.v_init[a.tile_of_state[u]] : 0.0;
     R[u] = 0.0;
@@ -117,6 +138,7 @@ __global__ void __launch_bounds__(512) nm_mb_kernel(const MbArgs a) {
     const double r = __hiloint2double((int)w0.y, (int)w0.x);
     const int s = (int)(w0.z & 0xffffu), s1 = (int)(w0.z >> 16);
     // ---- action values of the current state -------------------------------------------------------------
+    if constexpr (!GROUP) {
     const int na = (lane < A) ? ((int)rows[s * 8 + lane] >> 3) - kSent : -1;
     const bool ok = na >= 0;
     const double q = ok ? __dadd_rn(R[na], __dmul_rn(gamma, V[na])) : 0.0;
@@ -147,6 +169,51 @@ __global__ void __launch_bounds__(512) nm_mb_kernel(const MbArgs a) {
       const double zobs = __shfl_sync(kFull, zc, a_obs);
       ll = __dadd_rn(ll, __dsub_rn(zobs, log(sum)));
     }
+    } else {
+    // every lane loads the (at most eight) action values as broadcasts and evaluates its own beta; the action set
+    // and the observed action are warp-uniform
+    const uint4 rw = rows4[s];
+    const uint32_t offs[8] = {rw.x & 0xffffu, rw.x >> 16, rw.y & 0xffffu, rw.y >> 16,
+                              rw.z & 0xffffu, rw.z >> 16, rw.w & 0xffffu, rw.w >> 16};
+    unsigned avail = 0u;
+    int a_obs = -1;
+    double q[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int na = (int)(offs[k] >> 3) - kSent;
+      q[k] = 0.0;
+      if (na >= 0) {
+        avail |= 1u << k;
+        if (a_obs < 0 && na == s1) a_obs = k;
+        q[k] = __dadd_rn(R[na], __dmul_rn(gamma, V[na]));
+      }
+    }
+    if (i < n_on && a_obs >= 0) {
+      double z[8], m = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        z[k] = __dmul_rn(beta, q[k]);  // exploration_model.py:87
+        if ((avail >> k) & 1u) m = dmax2(m, z[k]);
+      }
+      double e[8], zobs = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const double zc = __dsub_rn(z[k], m);  // :92
+        e[k] = ((avail >> k) & 1u) ? exp(zc) : 0.0;
+        if (k == a_obs) zobs = zc;
+      }
+      double sum;
+      if (avail == 0xffu) {  // numpy pairwise sum, n == 8
+        sum = __dadd_rn(__dadd_rn(__dadd_rn(e[0], e[1]), __dadd_rn(e[2], e[3])),
+                        __dadd_rn(__dadd_rn(e[4], e[5]), __dadd_rn(e[6], e[7])));
+      } else {  // n < 8: sequential from 0.0; an unavailable action's +0.0 leaves the partial sum unchanged
+        sum = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sum = __dadd_rn(sum, e[k]);
+      }
+      ll = __dadd_rn(ll, __dsub_rn(zobs, log(sum)));
+    }
+    }
     // ---- world model: Rhat[s1] += alpha * (r - Rhat[s1]) ---------------------------------------------------
     if (lane == 0) {
       const double rs = R[s1];
@@ -172,15 +239,17 @@ __global__ void __launch_bounds__(512) nm_mb_kernel(const MbArgs a) {
       __syncwarp();
     }
   }
-  if (live && lane == 0 && a.ll_out) a.ll_out[(int64_t)sess * a.P + p] = ll;
+  if (a.ll_out && (GROUP ? pl < a.P : (live && lane == 0))) a.ll_out[(int64_t)sess * a.P + pl] = ll;
   if (live && (a.v_out || a.r_out)) {
     const int nT = a.n_tiles;
-    for (int tile = lane; tile < nT; tile += 32) {
-      const int st = a.state_of_tile[tile];
-      const int64_t o = ((int64_t)sess * a.P + p) * nT + tile;
-      if (a.v_out) a.v_out[o] = st >= 0 ? V[st] : (a.v_init ? a.v_init[tile] : 0.0);
-      if (a.r_out) a.r_out[o] = st >= 0 ? R[st] : 0.0;
-    }
+    const int copies = GROUP ? (int)(a.P - p < 32 ? a.P - p : 32) : 1;  // every set of a run receives the run's tables
+    for (int c = 0; c < copies; ++c)
+      for (int tile = lane; tile < nT; tile += 32) {
+        const int st = a.state_of_tile[tile];
+        const int64_t o = ((int64_t)sess * a.P + p + c) * nT + tile;
+        if (a.v_out) a.v_out[o] = st >= 0 ? V[st] : (a.v_init ? a.v_init[tile] : 0.0);
+        if (a.r_out) a.r_out[o] = st >= 0 ? R[st] : 0.0;
+      }
   }
 }
 
@@ -221,7 +290,9 @@ extern "C" int nm_modelbased_sweep(const nm_maze *mz, const nm_streams *st, cons
   }
   NM_CHECK_ARG(warps >= 1, "nm_modelbased_sweep: a maze with %d states does not fit in shared memory", S);
   const size_t smem = rows_bytes + per_warp * warps;
-  cudaError_t e = cudaFuncSetAttribute(nm_mb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(nm_mb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(nm_mb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   MbArgs a;
   a.records = st->d_records;
@@ -242,10 +313,35 @@ extern "C" int nm_modelbased_sweep(const nm_maze *mz, const nm_streams *st, cons
   a.ll_out = d_ll_out;
   a.v_out = d_v_out;
   a.r_out = d_r_out;
+  // Parameter sets that share (alpha, gamma) share V and Rhat: the device decides whether every aligned run of 32
+  // consecutive sets does, and exactly one of the two launches does the work (NM_MB_GROUP=0: never group).
+  cudaStream_t cs = (cudaStream_t)stream;
+  int *mode = nullptr;
+  const int rc = runs_mode_word(stream, &mode);
+  if (rc != NM_OK) return rc;
+  a.mode = mode;
+  const char *env = getenv("NM_MB_GROUP");
+  const bool group = !(env && atoi(env) == 0);
+  runs_decide(group, d_alpha, d_gamma, P, mode, cs);
   const int64_t blocks = (P + warps - 1) / warps;
   NM_CHECK_ARG(blocks <= 2147483647LL, "nm_modelbased_sweep: too many parameter sets for one launch");
-  nm_mb_kernel<<<dim3((unsigned)blocks, (unsigned)st->S, 1), warps * 32, smem, (cudaStream_t)stream>>>(a);
+  if (group) {
+    // a run per warp: spread few runs over the SMs (the sweep is shared-memory bound: fewer warps per SM are faster)
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, mz->device);
+    const int64_t runs = (P + 31) / 32;
+    int64_t per_cta = (runs * st->S + sms - 1) / sms;
+    per_cta = (per_cta + st->S - 1) / st->S;
+    const int gw = (int)(per_cta < 1 ? 1 : per_cta > warps ? warps : per_cta);
+    nm_mb_kernel<true><<<dim3((unsigned)((runs + gw - 1) / gw), (unsigned)st->S, 1), gw * 32, rows_bytes + per_warp * gw,
+                         cs>>>(a);
+  }
+  nm_mb_kernel<false><<<dim3((unsigned)blocks, (unsigned)st->S, 1), warps * 32, smem, cs>>>(a);
   e = cudaGetLastError();
   if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_mb_kernel launch: %s", cudaGetErrorString(e));
   return NM_OK;
+}
+
+extern "C" int nm_modelbased_sweep_mode(void *stream, int *mode_out) {
+  return runs_mode_read(stream, mode_out, "nm_modelbased_sweep_mode");
 }

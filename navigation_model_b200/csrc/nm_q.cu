@@ -19,7 +19,7 @@
 // Replay records (past the session's online count) update the table without contributing to the likelihood.
 //
 // Second mapping (nm_qgroup_kernel), taken when every aligned run of 32 consecutive parameter sets shares (alpha,
-// gamma) -- a Cartesian grid with beta fastest; the device checks the arrays itself (nm_qgroup_detect_kernel): the
+// gamma) -- a Cartesian grid with beta fastest; the device checks the arrays itself (nm_runs_detect_kernel): the
 // table depends on (alpha, gamma) only, so a WARP keeps ONE table Q[state * 8 + action][warp] for its 32 sets and
 // lane l evaluates the softmax of set p0 + l.  Table loads are broadcasts, every lane stores the same updated value.
 // A producer warp TMA-stages the raw records (cp.async.bulk + mbarrier), derives the action lists of s and s1 and
@@ -40,6 +40,7 @@ namespace {
 constexpr unsigned kFull = 0xffffffffu;
 
 #include "nm_exp.cuh"
+#include "nm_group.cuh"
 #include "nm_ring.cuh"
 #include "nm_step_math.cuh"
 
@@ -55,7 +56,7 @@ struct QArgs {
   int n_tiles;
   const int32_t *tile_of_state, *state_of_tile;
   double *ll_out, *q_out;
-  const int *mode;  // device word set by nm_qgroup_detect_kernel: 0 octet kernel, 1 group kernel; NULL: always run
+  const int *mode;  // device word set by nm_runs_detect_kernel: 0 octet kernel, 1 group kernel; NULL: always run
 };
 
 __device__ __forceinline__ double dmax2(double a, double b) { return (b > a) ? b : a; }
@@ -201,18 +202,6 @@ struct QRings {
   uint64_t *full_raw, *full_dec, *empty_dec;
   uint4 *raw, *dec;
 };
-
-// mode[0] = 1 if every aligned run of 32 parameter sets shares (alpha, gamma), else 0
-__global__ void nm_qgroup_init_kernel(int *mode, int value) { mode[0] = value; }
-__global__ void __launch_bounds__(256) nm_qgroup_detect_kernel(const double *__restrict__ alpha,
-                                                               const double *__restrict__ gamma, int64_t P, int *mode) {
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P) return;
-  const int64_t head = p & ~(int64_t)31;
-  if (__double_as_longlong(alpha[p]) != __double_as_longlong(alpha[head]) ||
-      __double_as_longlong(gamma[p]) != __double_as_longlong(gamma[head]))
-    mode[0] = 0;
-}
 
 __device__ __forceinline__ void q_producer_loop(const QRings &rg, const nm_step_rec *src, int64_t n, int64_t n_on,
                                                 int nchunks, const int16_t *nxt8, uint32_t row_bytes, uint32_t sentinel,
@@ -415,25 +404,6 @@ __global__ void __launch_bounds__(960, 1) nm_qgroup_kernel(const QArgs a) {
   }
 }
 
-// one int of sweep mode per (device, stream), allocated on first use and kept for the life of the process
-int q_mode_word(void *stream, int **out) {
-  int device = 0;
-  cudaGetDevice(&device);
-  static std::mutex mu;
-  static std::map<std::pair<int, void *>, int *> words;
-  std::lock_guard<std::mutex> lock(mu);
-  const auto key = std::make_pair(device, stream);
-  auto it = words.find(key);
-  if (it == words.end()) {
-    int *buf = nullptr;
-    const cudaError_t e = cudaMalloc((void **)&buf, 64);
-    if (e != cudaSuccess) return nm_fail(NM_ERR_NOMEM, "nm_qtable_sweep: cudaMalloc: %s", cudaGetErrorString(e));
-    it = words.emplace(key, buf).first;
-  }
-  *out = it->second;
-  return NM_OK;
-}
-
 }  // namespace
 
 extern "C" int nm_qtable_sweep(const nm_maze *mz, const nm_streams *st, const int16_t *d_next, int n_actions,
@@ -498,7 +468,7 @@ extern "C" int nm_qtable_sweep(const nm_maze *mz, const nm_streams *st, const in
   // consecutive sets does, and exactly one of the two kernels does the work (the other returns at its first
   // instruction) -- no host round trip.  NM_Q_GROUP=0 keeps the octet kernel (A/B runs, tests).
   int *mode = nullptr;
-  const int rc = q_mode_word(stream, &mode);
+  const int rc = runs_mode_word(stream, &mode);
   if (rc != NM_OK) return rc;
   a.mode = mode;
   const char *env = getenv("NM_Q_GROUP");
@@ -506,11 +476,9 @@ extern "C" int nm_qtable_sweep(const nm_maze *mz, const nm_streams *st, const in
   const size_t g_per_warp = ((size_t)S * 8 + 1) * sizeof(double);  // one table + the -inf row
   int g_max = (int)(((size_t)227 * 1024 - g_fixed) / g_per_warp);
   if (g_max > 29) g_max = 29;
-  if ((env && atoi(env) == 0) || g_max < 1 || (size_t)(S * 8 + 1) * g_max * 8 > 0xffffffffull) {
-    nm_qgroup_init_kernel<<<1, 1, 0, cs>>>(mode, 0);
-  } else {
-    nm_qgroup_init_kernel<<<1, 1, 0, cs>>>(mode, 1);
-    nm_qgroup_detect_kernel<<<(unsigned)((P + 255) / 256), 256, 0, cs>>>(d_alpha, d_gamma, P, mode);
+  const bool group = !(env && atoi(env) == 0) && g_max >= 1 && (size_t)(S * 8 + 1) * g_max * 8 <= 0xffffffffull;
+  runs_decide(group, d_alpha, d_gamma, P, mode, cs);
+  if (group) {
     // consumer warps per CTA: spread few runs over the SMs, else the fullest CTA (same staircase as the value-table
     // group kernel: only the busiest scheduler's warp count matters, ties go to the smaller CTA)
     int sms = 148;
@@ -547,13 +515,5 @@ extern "C" int nm_qtable_sweep(const nm_maze *mz, const nm_streams *st, const in
 }
 
 extern "C" int nm_qtable_sweep_mode(void *stream, int *mode_out) {
-  NM_CHECK_ARG(mode_out, "nm_qtable_sweep_mode: NULL output");
-  int *mode = nullptr;
-  const int rc = q_mode_word(stream, &mode);
-  if (rc != NM_OK) return rc;
-  // synchronous by design (diagnostics / tests): waits for the stream, then reads the word the device set
-  cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
-  if (e == cudaSuccess) e = cudaMemcpy(mode_out, mode, sizeof(int), cudaMemcpyDeviceToHost);
-  if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_qtable_sweep_mode: %s", cudaGetErrorString(e));
-  return NM_OK;
+  return runs_mode_read(stream, mode_out, "nm_qtable_sweep_mode");
 }

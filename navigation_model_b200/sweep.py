@@ -599,6 +599,20 @@ class _TileActionSweep:
     def log_likelihood_device(self, alpha_t, beta_t, gamma_t):
         raise NotImplementedError
 
+    _mode_symbol = None  # C-ABI diagnostic of the subclass
+
+    def last_sweep_mode(self):
+        """Mapping the last sweep on the current stream used: 0 = tables per parameter set, 1 = tables per aligned run
+        of 32 consecutive parameter sets with equal ``(alpha, gamma)`` -- the tables do not depend on beta, so on a
+        grid with beta fastest (``parameter_grid(gamma, alpha, beta)``, a multiple of 32 beta points) they are kept and
+        updated once per run.  Decided on the device, bit-identical results.  Synchronises the stream."""
+        b = self._base
+        torch = b._ensure_device()
+        mode = C.c_int(-1)
+        with torch.cuda.device(b.torch_device):
+            _native.check(getattr(b._dmaze._lib, self._mode_symbol)(_native.cuda_stream_ptr(), C.byref(mode)))
+        return mode.value
+
     def best_fit(self, alpha, beta, gamma, group=None):
         """Grid search like :meth:`ConditioningSweep.best_fit`: the flat parameter index is sharded over the ranks of
         an initialised process group, 16 bytes per rank are all-gathered.  ``(best_nll, best_index)``."""
@@ -628,6 +642,8 @@ class ModelBasedSweep(_TileActionSweep):
     >>> mb.add_session(trajectory, reward)
     >>> ll = mb.log_likelihood(alpha, beta, gamma)      # float64[S, P]
     """
+
+    _mode_symbol = "nm_modelbased_sweep_mode"
 
     def __init__(self, maze, discrete_actions, n_sweeps=1, device=None):
         super().__init__(maze, discrete_actions, device=device)
@@ -685,6 +701,8 @@ class QLearningSweep(_TileActionSweep):
     >>> ll = ql.log_likelihood(alpha, beta, gamma)      # float64[S, P]
     """
 
+    _mode_symbol = "nm_qtable_sweep_mode"
+
     def log_likelihood_device(self, alpha_t, beta_t, gamma_t, q_init_t=None, ll_out=None, q_out=None):
         b = self._base
         torch = b._ensure_device()
@@ -699,17 +717,6 @@ class QLearningSweep(_TileActionSweep):
             _native.tensor_ptr(q_init_t), _native.tensor_ptr(ll_out), _native.tensor_ptr(q_out),
             _native.cuda_stream_ptr()))  # last_kernel_ms: device time of nm_q_kernel
         return ll_out
-
-    def last_sweep_mode(self):
-        """Kernel the last sweep on the current stream used: 0 = a table per parameter set (eight lanes each), 1 = a
-        table per warp shared by an aligned run of 32 consecutive parameter sets with equal ``(alpha, gamma)`` (order
-        the grid with beta fastest, ``parameter_grid(gamma, alpha, beta)``).  Synchronises the stream."""
-        b = self._base
-        torch = b._ensure_device()
-        mode = C.c_int(-1)
-        with torch.cuda.device(b.torch_device):
-            _native.check(b._dmaze._lib.nm_qtable_sweep_mode(_native.cuda_stream_ptr(), C.byref(mode)))
-        return mode.value
 
     def log_likelihood(self, alpha, beta, gamma, q_init=None, return_tables=False):
         """``float64[S, P]`` log-likelihoods (and, optionally, the final tables ``Q[S, P, X, Y, A]``; entries of

@@ -22,6 +22,8 @@ def main():
     ap.add_argument("--sweeps", type=int, default=1)
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--cpu-params", type=int, default=2)
+    ap.add_argument("--grid", type=int, nargs=3, default=None, metavar=("N_ALPHA", "N_GAMMA", "N_BETA"),
+                    help="a Cartesian grid with beta fastest instead of --params random parameter sets")
     args = ap.parse_args()
     import torch
     from navigation_model_b200.simulation.maze import Maze
@@ -35,6 +37,11 @@ def main():
     rng = np.random.default_rng(0)
     P = args.params
     a, b, g = rng.uniform(0.01, 1, P), np.exp(rng.uniform(np.log(0.1), np.log(30), P)), rng.uniform(0.5, 0.99, P)
+    if args.grid:
+        from navigation_model_b200.sweep import parameter_grid
+        na, ng, nb = args.grid
+        a, g, b = parameter_grid(np.linspace(0.01, 1, na), np.linspace(0.5, 0.99, ng), np.logspace(-1, 1.5, nb))
+        P = a.size
     mb = ModelBasedSweep(maze, acts, n_sweeps=args.sweeps, device=0)
     mb.add_session(traj, rew)
     times = []
@@ -54,7 +61,7 @@ def main():
     cpu = args.cpu_params * (args.steps - 1) / (time.perf_counter() - t0)
     upd = P * (args.steps - 1)
     print(json.dumps({"metric": "agent-trial updates/s (model-based agent, 400-state maze, 8 actions)",
-                      "value": upd / best, "params": P, "steps": args.steps, "n_sweeps": args.sweeps,
+                      "value": upd / best, "params": P, "steps": args.steps, "n_sweeps": args.sweeps, "sweep_mode": mb.last_sweep_mode(),
                       "seconds_best_incl_h2d_d2h": best, "all_reps_s": times,
                       "state_action_backups_per_s": upd * args.sweeps * 400 * 8 / best,
                       "oracle_max_rel_err": chk, "cpu_numpy_oracle_1core_updates_per_s": cpu}))
