@@ -509,7 +509,7 @@ def run_b200(args):
                 "target_updates_per_s_8gpu": 1e10}
         if extras is not None:
             line["also_measured"] = extras
-            line["gpu_launches"] += 12
+            line["gpu_launches_also_measured"] = 3 + 12 + 12 + 12  # simulation, model-based (two workloads), Q-table
         emit(line)
     if world > 1:
         dist.barrier()
