@@ -271,11 +271,22 @@ def parameter_grid(*axes):
     return tuple(np.ascontiguousarray(m.reshape(-1)) for m in mesh)
 
 
-def shard_bounds(P, rank, world):
-    """Contiguous block ``[lo, hi)`` of the flat parameter index owned by ``rank``."""
-    base, rem = divmod(int(P), int(world))
+def shard_bounds(P, rank, world, align=32):
+    """Contiguous block ``[lo, hi)`` of the flat parameter index owned by ``rank``.
+
+    Shards start on multiples of ``align`` = 32 parameter sets (when there are at least ``world`` such blocks), so that
+    the runs of 32 sets sharing ``(alpha, gamma)`` that the sweeps look for stay aligned inside every shard; sizes then
+    differ by less than two blocks."""
+    P, world = int(P), int(world)
+    blocks = -(-P // align)
+    if blocks < world:  # tiny grids: split single parameter sets
+        base, rem = divmod(P, world)
+        lo = rank * base + min(rank, rem)
+        return lo, lo + base + (1 if rank < rem else 0)
+    base, rem = divmod(blocks, world)
     lo = rank * base + min(rank, rem)
-    return lo, lo + base + (1 if rank < rem else 0)
+    hi = lo + base + (1 if rank < rem else 0)
+    return min(lo * align, P), min(hi * align, P)
 
 
 class ConditioningSweep:

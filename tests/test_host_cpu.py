@@ -69,13 +69,16 @@ def test_replay_records_follow_generator_shuffle():
 
 def test_shard_bounds_cover_grid():
     from navigation_model_b200.sweep import shard_bounds
-    for P in (1, 7, 8, 131072, 2097152 + 3):
+    for P in (1, 7, 8, 100, 255, 256, 131072, 100352, 2097152 + 3):
         for world in (1, 2, 4, 8):
             spans = [shard_bounds(P, r, world) for r in range(world)]
             assert spans[0][0] == 0 and spans[-1][1] == P
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
             sizes = [hi - lo for lo, hi in spans]
-            assert max(sizes) - min(sizes) <= 1
+            if -(-P // 32) >= world:  # shards start on multiples of 32 parameter sets, sizes within two blocks
+                assert all(lo % 32 == 0 for lo, _ in spans) and max(sizes) - min(sizes) < 64
+            else:
+                assert max(sizes) - min(sizes) <= 1
 
 
 def _gloo_worker(rank, world, port, q):
