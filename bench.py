@@ -41,16 +41,15 @@ def env_int(name, default):
 def make_workload(n_shards):
     """Synthetic session 0 + the (alpha, beta, gamma) grid; the gamma axis has 32 * n_shards points so that
     every shard is a full 64 x 64 x 32 block (weak scaling)."""
-    from oracle import np_oracle as O  # seeded session recipe only (inputs, not the measured path)
+    from navigation_model_b200 import workloads as W
     from navigation_model_b200.sweep import parameter_grid
-    omz = O.OracleMaze(O.M9_LAYOUT, O.M9_SIZE_TILE)
-    traj, rew = O.synthetic_session(omz, 0, T_STEPS)
+    traj, rew = W.synthetic_session(W.maze_m9(), 0, T_STEPS)
     alpha_ax = np.linspace(0.01, 1.0, GRID[0])
     beta_ax = np.logspace(-1.0, 1.5, GRID[1])
     gamma_ax = np.linspace(0.5, 0.99, GRID[2] * n_shards)
     # gamma slowest so that a contiguous shard of the flat index is a (gamma-slab x alpha x beta) block
     g, a, b = parameter_grid(gamma_ax, alpha_ax, beta_ax)
-    return omz, traj, rew, a, b, g
+    return traj, rew, a, b, g
 
 
 def algorithmic_fp64(records, n_online, alg):
@@ -149,6 +148,13 @@ def ncu_dram_traffic():
     return ncu_counter(["dram__bytes_read.sum", "dram__bytes_write.sum"], scale_units=True)
 
 
+def oracle_transitions(traj, rew):
+    """CPU legs only: the oracle's own extraction of the session's transitions (its maze, its mouse)."""
+    from oracle import np_oracle as O
+    omz = O.OracleMaze(O.M9_LAYOUT, O.M9_SIZE_TILE)
+    return O.extract_transitions(omz, traj, rew, O.OracleMouse(traj[0], 0.0, O.A8_UNITS * O.M9_SIZE_TILE))
+
+
 def cpu_port_rate(records_tr, alg_code, a, b, g, seconds, threads=0):
     """Time the C oracle port on a bounded sample of the same workload.  Returns (updates/s, sample, cores)."""
     from oracle import c_oracle as CO
@@ -174,12 +180,11 @@ def run_reference(args):
     rank = env_int("RANK", 0)
     if rank != 0:
         return
-    from oracle import np_oracle as O
     from oracle import c_oracle as CO
     alg_code = {"td0": 0, "positive": 1, "negative": 2}[args.alg]
     world = max(1, int(args.gpus))
-    omz, traj, rew, a, b, g = make_workload(world)  # the whole job's grid: the sample is drawn from all of it
-    tr = O.extract_transitions(omz, traj, rew, O.OracleMouse(traj[0], 0.0, O.A8_UNITS * O.M9_SIZE_TILE))
+    traj, rew, a, b, g = make_workload(world)  # the whole job's grid: the sample is drawn from all of it
+    tr = oracle_transitions(traj, rew)
     n = len(tr["s"])
     P_s = 16384  # ~0.25 s of 16 host threads per step
     idx = np.linspace(0, len(a) - 1, P_s).astype(np.int64)
@@ -222,9 +227,8 @@ def other_paths(local, world, rank, dist, dev):
     import torch
     from navigation_model_b200.batched_sim import BatchedExperiment
     from navigation_model_b200.simulation import behavioural_components as bc
-    from navigation_model_b200.simulation.maze import Maze
+    from navigation_model_b200 import workloads as W
     from navigation_model_b200.sweep import ModelBasedSweep, QLearningSweep, parameter_grid
-    from oracle import np_oracle as O  # maze layout / seeded session recipe only (inputs)
 
     def max_over_ranks(x):
         t = torch.tensor([x], dtype=torch.float64, device=dev)
@@ -234,7 +238,7 @@ def other_paths(local, world, rank, dist, dev):
 
     out = {}
     # ---- forward simulation -----------------------------------------------------------------------------
-    maze = Maze(O.M9_LAYOUT, O.M9_SUBAREAS, size_tile=O.M9_SIZE_TILE)
+    maze = W.maze_m9()
     rng = np.random.default_rng(1000 + rank)
     N, T = 148 * 6 * 128 * 8, 1000  # eight full waves of the kernel's residency (6 CTAs of 128 mice per SM)
     u = rng.uniform
@@ -243,7 +247,7 @@ def other_paths(local, world, rank, dist, dev):
          "xi": u(0.006, 0.6, N), "kappa_home": u(0.01, 5, N), "kappa_explo": u(0.01, 5, N),
          "theta_explo": u(80, 120, N), "theta_home": u(30, 70, N), "W_bper": u(0, 10, N), "bp": u(0, 1, N),
          "Wm": u(0, 2, N), "Wnm": u(0, 2, N), "W_values": u(0, 10, N)}
-    exp = BatchedExperiment(maze, O.A8_UNITS * O.M9_SIZE_TILE, O.A8_UNITS,
+    exp = BatchedExperiment(maze, W.a8(), W.A8_UNITS,
                             [bc.AnxietyComponent, bc.BiomechanicalCostComponent, bc.ExperienceComponent,
                              bc.BiomechPersistenceComponent, bc.ValueTableComponent], v_table=rng.random((9, 9)),
                             device=local)
@@ -267,10 +271,9 @@ def other_paths(local, world, rank, dist, dev):
                     "preparation, H2D and D2H of every per-mouse result",
         "mice_ok": int((res.status == 0).sum())}
     # ---- model-based agent ------------------------------------------------------------------------------
-    acts = [(dx, dy) for dx in (-1, 0, 1) for dy in (-1, 0, 1) if (dx, dy) != (0, 0)]
-    layout = "\n".join(["M" * 20] * 20)
-    maze20 = Maze(layout, "", size_tile=0.05)
-    traj, rew = O.synthetic_session(O.OracleMaze(layout, 0.05), 0, 1000, start=(3, 3), goal=(15, 12), jitter=0.02)
+    acts = W.MOVES8
+    maze20 = W.maze_m20()
+    traj, rew = W.synthetic_session(maze20, 0, 1000, start=(3, 3), goal=(15, 12), jitter=0.02)
     Pm = 20000
     a, b, g = rng.uniform(0.01, 1, Pm), np.exp(rng.uniform(np.log(0.1), np.log(30), Pm)), rng.uniform(0.5, 0.99, Pm)
     mb = ModelBasedSweep(maze20, acts, n_sweeps=1, device=local)
@@ -310,7 +313,7 @@ def other_paths(local, world, rank, dist, dev):
         "workload": f"{ag.size} parameter sets = 25 x 25 (alpha, gamma) x 32 beta, beta fastest, x "
                     f"{mb.updates_per_parameter_set} steps per GPU, same maze: tables and sweeps once per run of 32 sets"}
     # ---- Q-table agent ------------------------------------------------------------------------------------
-    traj9, rew9 = O.synthetic_session(O.OracleMaze(O.M9_LAYOUT, O.M9_SIZE_TILE), 0, T_STEPS)
+    traj9, rew9 = W.synthetic_session(maze, 0, T_STEPS)
     gq, aq, bq = parameter_grid(np.linspace(0.5, 0.99, 32), np.linspace(0.01, 1, 64), np.logspace(-1, 1.5, 64))
     ql = QLearningSweep(maze, acts, device=local)
     ql.add_session(traj9, rew9)
@@ -336,9 +339,8 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     from navigation_model_b200 import _native
-    from navigation_model_b200.simulation.maze import Maze
+    from navigation_model_b200 import workloads as W
     from navigation_model_b200.sweep import ConditioningSweep, shard_bounds
-    from oracle import np_oracle as O
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     _native.require_device()
@@ -346,12 +348,12 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    omz, traj, rew, a_all, b_all, g_all = make_workload(world)
+    traj, rew, a_all, b_all, g_all = make_workload(world)
     lo, hi = shard_bounds(len(a_all), rank, world)
     a, b, g = a_all[lo:hi], b_all[lo:hi], g_all[lo:hi]
     P = hi - lo
-    maze = Maze(O.M9_LAYOUT, O.M9_SUBAREAS, size_tile=O.M9_SIZE_TILE)
-    sw = ConditioningSweep(maze, args.alg, possible_actions=O.A8_UNITS * O.M9_SIZE_TILE, device=local)
+    maze = W.maze_m9()
+    sw = ConditioningSweep(maze, args.alg, possible_actions=W.a8(), device=local)
     sw.add_session(traj, rew)
     records = sw._records[0]
     n_upd = sw.updates_per_parameter_set
@@ -490,7 +492,7 @@ def run_b200(args):
                                    % (alg_bytes, alg_bytes / (kern_ms.mean() * 1e-3) / 1e9, measured_hbm_peak()),
                     "hbm_gbs_achieved": alg_bytes / (kern_ms.mean() * 1e-3) / 1e9}
         # ---- cpu_baseline: the C oracle port on this box's host cores ---------------------------------------
-        tr = O.extract_transitions(omz, traj, rew, O.OracleMouse(traj[0], 0.0, O.A8_UNITS * O.M9_SIZE_TILE))
+        tr = oracle_transitions(traj, rew)  # the one place the product arm touches oracle/: the cpu_baseline leg
         alg_code = {"td0": 0, "positive": 1, "negative": 2}[args.alg]
         cpu_val, cpu_sample, cores = cpu_port_rate(tr, alg_code, a, b, g, seconds=args.cpu_seconds)
         line = {"metric": "agent-trial updates/s (fitness grid sweep)", "value": value, "unit": "updates/s",

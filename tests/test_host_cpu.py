@@ -145,3 +145,36 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not bad.search(text), f"{f} depends on the oracle"
+
+
+def test_workload_recipes_match_the_oracle_restatement():
+    """bench.py and tools/ build their inputs from navigation_model_b200.workloads (product side); the oracle keeps its
+    own restatement of the same seeded recipe for the parity tests.  The two must give identical bits."""
+    from navigation_model_b200 import workloads as W
+    from oracle import np_oracle as O
+    assert W.M9_LAYOUT == O.M9_LAYOUT and W.M9_SUBAREAS == O.M9_SUBAREAS and W.M9_SIZE_TILE == O.M9_SIZE_TILE
+    assert np.array_equal(W.A8_UNITS, O.A8_UNITS)
+    m9, om9 = W.maze_m9(), O.OracleMaze(O.M9_LAYOUT, O.M9_SIZE_TILE)
+    for sid, T in ((0, 5000), (3, 257), (9, 1)):
+        got, want = W.synthetic_session(m9, sid, T), O.synthetic_session(om9, sid, T)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    m20, om20 = W.maze_m20(), O.OracleMaze("\n".join(["M" * 20] * 20), W.M20_SIZE_TILE)
+    got = W.synthetic_session(m20, 0, 1000, start=(3, 3), goal=(15, 12), jitter=0.02)
+    want = O.synthetic_session(om20, 0, 1000, start=(3, 3), goal=(15, 12), jitter=0.02)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    assert np.array_equal(m20.transition_table(W.MOVES8), O.transition_table(om20, W.MOVES8))
+
+
+def test_bench_product_arm_touches_the_oracle_only_in_its_cpu_legs():
+    """bench.py may execute oracle/ in exactly two places: the cpu_baseline leg and --impl reference."""
+    import ast
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tree = ast.parse(open(os.path.join(root, "bench.py")).read())
+    allowed = {"oracle_transitions", "cpu_port_rate", "run_reference"}
+    for fn in [n for n in tree.body if isinstance(n, ast.FunctionDef)]:
+        uses = any(isinstance(n, ast.ImportFrom) and (n.module or "").split(".")[0] == "oracle" for n in ast.walk(fn)) or \
+            any(isinstance(n, ast.Import) and any(a.name.split(".")[0] == "oracle" for a in n.names) for n in ast.walk(fn))
+        assert not uses or fn.name in allowed, f"bench.py:{fn.name} imports the oracle"
+    top = [n for n in tree.body if isinstance(n, (ast.Import, ast.ImportFrom))]
+    assert not any("oracle" in ast.dump(n) for n in top)
+

@@ -28,12 +28,13 @@ def main():
     import torch
     from navigation_model_b200.simulation.maze import Maze
     from navigation_model_b200.sweep import ModelBasedSweep
-    from oracle import np_oracle as O
+    from navigation_model_b200 import workloads as W
+    from oracle import np_oracle as O  # spot check of the result only
     acts = [(dx, dy) for dx in (-1, 0, 1) for dy in (-1, 0, 1) if (dx, dy) != (0, 0)]
     layout = "\n".join(["M" * 20] * 20)
     maze = Maze(layout, "", size_tile=0.05)
     omz = O.OracleMaze(layout, 0.05)
-    traj, rew = O.synthetic_session(omz, 0, args.steps, start=(3, 3), goal=(15, 12), jitter=0.02)
+    traj, rew = W.synthetic_session(maze, 0, args.steps, start=(3, 3), goal=(15, 12), jitter=0.02)
     rng = np.random.default_rng(0)
     P = args.params
     a, b, g = rng.uniform(0.01, 1, P), np.exp(rng.uniform(np.log(0.1), np.log(30), P)), rng.uniform(0.5, 0.99, P)

@@ -26,17 +26,18 @@ def main():
     import torch
     from navigation_model_b200.simulation.maze import Maze
     from navigation_model_b200.sweep import QLearningSweep, parameter_grid
-    from oracle import np_oracle as O
+    from navigation_model_b200 import workloads as W
+    from oracle import np_oracle as O  # spot check of the result only
     acts = [(dx, dy) for dx in (-1, 0, 1) for dy in (-1, 0, 1) if (dx, dy) != (0, 0)]
     if args.maze == "m9":
         maze = Maze(O.M9_LAYOUT, O.M9_SUBAREAS, size_tile=O.M9_SIZE_TILE)
         omz = O.OracleMaze(O.M9_LAYOUT, O.M9_SIZE_TILE)
-        traj, rew = O.synthetic_session(omz, 0, args.steps)
+        traj, rew = W.synthetic_session(maze, 0, args.steps)
     else:
         layout = "\n".join(["M" * 20] * 20)
         maze = Maze(layout, "", size_tile=0.05)
         omz = O.OracleMaze(layout, 0.05)
-        traj, rew = O.synthetic_session(omz, 0, args.steps, start=(3, 3), goal=(15, 12), jitter=0.02)
+        traj, rew = W.synthetic_session(maze, 0, args.steps, start=(3, 3), goal=(15, 12), jitter=0.02)
     na, nb, ng = args.grid
     # beta fastest: runs of 32 consecutive parameter sets share (alpha, gamma) and with it their table
     g, a, b = parameter_grid(np.linspace(0.5, 0.99, ng), np.linspace(0.01, 1, na), np.logspace(-1, 1.5, nb))

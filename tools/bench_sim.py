@@ -38,15 +38,16 @@ def main():
     from navigation_model_b200.batched_sim import BatchedExperiment
     from navigation_model_b200.simulation import behavioural_components as bc
     from navigation_model_b200.simulation.maze import Maze
-    from oracle import np_oracle as O
+    from navigation_model_b200 import workloads as W
+    from oracle import np_oracle as O  # the CPU sample at the end only
 
-    maze = Maze(O.M9_LAYOUT, O.M9_SUBAREAS, size_tile=O.M9_SIZE_TILE)
-    acts = O.A8_UNITS * O.M9_SIZE_TILE
+    maze = W.maze_m9()
+    acts = W.a8()
     rng = np.random.default_rng(0)
     N, T = args.mice, args.steps
     V = rng.random((9, 9))
     P = params(rng, N)
-    exp = BatchedExperiment(maze, acts, O.A8_UNITS, [bc.AnxietyComponent, bc.BiomechanicalCostComponent,
+    exp = BatchedExperiment(maze, acts, W.A8_UNITS, [bc.AnxietyComponent, bc.BiomechanicalCostComponent,
                                                      bc.ExperienceComponent, bc.BiomechPersistenceComponent,
                                                      bc.ValueTableComponent], v_table=V, device=0)
     pos0 = np.array(maze.get_tile_centre(1, 1)) + rng.uniform(-0.03, 0.03, (N, 2))

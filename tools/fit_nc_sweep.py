@@ -15,13 +15,11 @@ sys.path.insert(0, ROOT)
 
 def main():
     import torch
-    from navigation_model_b200.simulation.maze import Maze
     from navigation_model_b200.sweep import ConditioningSweep
-    from oracle import np_oracle as O
-    omz = O.OracleMaze(O.M9_LAYOUT, O.M9_SIZE_TILE)
-    maze = Maze(O.M9_LAYOUT, O.M9_SUBAREAS, size_tile=O.M9_SIZE_TILE)
-    acts = O.A8_UNITS * O.M9_SIZE_TILE
-    traj, rew = O.synthetic_session(omz, 0, 5000)
+    from navigation_model_b200 import workloads as W
+    maze = W.maze_m9()
+    acts = W.a8()
+    traj, rew = W.synthetic_session(maze, 0, 5000)
     sw = ConditioningSweep(maze, "positive", possible_actions=acts, device=0)
     sw.add_session(traj, rew)
     dev = torch.device("cuda", 0)

@@ -33,7 +33,8 @@ def main():
     import torch.distributed as dist
     from navigation_model_b200.simulation.maze import Maze
     from navigation_model_b200.sweep import ConditioningSweep, parameter_grid, reduce_best, shard_bounds
-    from oracle import np_oracle as O
+    from navigation_model_b200 import workloads as W
+    from oracle import np_oracle as O  # rank 0's spot check of the result only
 
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -46,10 +47,10 @@ def main():
     P = a.size
     lo, hi = shard_bounds(P, rank, world)
     omz = O.OracleMaze(O.M9_LAYOUT, O.M9_SIZE_TILE)
-    maze = Maze(O.M9_LAYOUT, O.M9_SUBAREAS, size_tile=O.M9_SIZE_TILE)
-    acts = O.A8_UNITS * O.M9_SIZE_TILE
+    maze = W.maze_m9()
+    acts = W.a8()
     t0 = time.perf_counter()
-    sessions = [O.synthetic_session(omz, sid, args.steps) for sid in range(args.sessions)]
+    sessions = [W.synthetic_session(maze, sid, args.steps) for sid in range(args.sessions)]
     sw = ConditioningSweep(maze, args.alg, possible_actions=acts, device=local)
     for traj, rew in sessions:
         sw.add_session(traj, rew)
