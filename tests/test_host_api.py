@@ -388,3 +388,26 @@ def test_multiobjective_fitness_known_answers():
     npt.assert_allclose(fit.percentiles_list()[0], (2.5, 3.5))
     fit.reset()
     assert fit.data()["obj1"] == []
+
+
+def test_multi_result_views_and_batched_leaves():
+    """MultiResult (results.py:4-101): nested addressing, statistics over the result axis, views that see later
+    appends, and the batched form whose leaves already carry the result axis."""
+    from navigation_model_b200.analysis.results import MultiResult
+    mr = MultiResult({"a": {"b": 0.0}, "h": np.zeros(4)}, {"a": {"b": 1.5}, "h": np.ones(4)})
+    view = mr["a"]["b"]
+    mr.append({"a": {"b": 2.0}, "h": np.full(4, 2.0)})
+    assert len(mr) == 3 and np.array_equal(view.data(), [0.0, 1.5, 2.0])  # the view follows the root
+    assert view.median() == 1.5 and np.isclose(view.mean(), np.mean([0.0, 1.5, 2.0]))
+    assert np.isclose(view.std(), np.std([0.0, 1.5, 2.0])) and view.percentile() == (0.75, 1.75)
+    assert np.array_equal(mr["h"].mean(), np.ones(4)) and mr["h"].data().shape == (3, 4)
+    with pytest.raises(KeyError):
+        mr["missing"]
+    with pytest.raises(TypeError):
+        view.append({"a": {"b": 1.0}})
+    batch = MultiResult.from_batch({"moving": np.array([3, 5, 10]), "hist": np.arange(12.0).reshape(3, 4)})
+    assert len(batch["moving"]) == 3 and batch["moving"].median() == 5
+    assert np.array_equal(batch["hist"].mean(), np.arange(12.0).reshape(3, 4).mean(axis=0))
+    mr.reset()
+    assert len(mr) == 0
+

@@ -8,7 +8,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_TESTS = "/root/reference/test"
-SUITES = ["test_rl.py", "test_mouse.py", "test_maze.py", "test_components.py", "test_exploration.py",
+SUITES = ["test_rl.py", "test_mouse.py", "test_maze.py", "test_components.py", "test_exploration.py", "test_results.py",
           "test_fitness.py", "test_statistics.py", "test_session.py", "test_metrics.py"]
 
 PLUGIN = """
@@ -27,4 +27,4 @@ def test_reference_suites_pass_against_this_package(tmp_path):
                           *SUITES], cwd=REF_TESTS, env=env, capture_output=True, text=True, timeout=600)
     tail = res.stdout[-1500:] + res.stderr[-500:]
     assert res.returncode == 0, tail
-    assert "68 passed" in res.stdout, tail
+    assert "73 passed" in res.stdout, tail
