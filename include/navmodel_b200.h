@@ -197,6 +197,14 @@ int nm_positions_adjust_device(const nm_maze *mz, const double *d_points, int64_
 nm_streams *nm_streams_build_device(const nm_maze *mz, const double *d_traj, const double *d_reward,
                                     const int64_t *h_offsets, const int64_t *h_counts, int S, const double *h_actions,
                                     int n_actions, const double *h_mouse_init, void *stream);
+
+/* New streams = the online records of every session of `src` (built on the device) followed by replay passes:
+ * h_order holds, session after session, h_counts[j] indices into session j's online records -- the order in which
+ * ShuffledReplays.offline_replays presents them again (n_times cumulative in-place Generator.shuffle passes,
+ * rl.py:419-424; the permutation is parameter-independent, so it is drawn once on the host).  The records are gathered
+ * on the device; `src` is left untouched.  NULL on error. */
+nm_streams *nm_streams_with_replays(const nm_streams *src, const int64_t *h_order, const int64_t *h_counts,
+                                    void *stream);
 /* Copy the records of a stream handle back to the host ([total] nm_step_rec); synchronises `stream`. */
 int nm_streams_download(const nm_streams *st, nm_step_rec *h_records, void *stream);
 

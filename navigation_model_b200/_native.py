@@ -56,6 +56,7 @@ SIGNATURES = {
     "nm_streams_free": (None, [_p]),
     "nm_sessions_subsample_device": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_double, _p, _p, _p, _p]),
     "nm_streams_build_device": (_p, [_p, _p, _p, _p, _p, C.c_int, _p, C.c_int, _p, _p]),
+    "nm_streams_with_replays": (_p, [_p, _p, _p, _p]),
     "nm_streams_download": (C.c_int, [_p, _p, _p]),
     "nm_sessions_orientations_device": (C.c_int, [_p, _p, _p, _p, C.c_int, _p, C.c_int, _p, _p, _p]),
     "nm_positions_adjust_device": (C.c_int, [_p, _p, _i64, _p, _p]),

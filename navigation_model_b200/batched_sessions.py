@@ -28,12 +28,13 @@ from .sweep import DeviceMaze
 class DeviceBuiltStreams:
     """``nm_streams`` handle whose records were built on the device (same duck type as ``DeviceStreams``)."""
 
-    def __init__(self, dmaze, handle, counts, has_candidates):
+    def __init__(self, dmaze, handle, counts, has_candidates, replays=None):
         self.dmaze = dmaze
         self._lib = _native.lib()
         self._h = handle
         self.online = np.maximum(np.asarray(counts, dtype=np.int64) - 1, 0)
-        self.offsets = np.concatenate([[0], np.cumsum(self.online)]).astype(np.int64)
+        extra = np.zeros_like(self.online) if replays is None else np.asarray(replays, dtype=np.int64)
+        self.offsets = np.concatenate([[0], np.cumsum(self.online + extra)]).astype(np.int64)
         self.S = len(self.online)
         self.total = int(self.offsets[-1])
         self.has_candidates = bool(has_candidates)
@@ -57,6 +58,23 @@ class DeviceBuiltStreams:
             with torch.cuda.device(self.dmaze.torch_device):
                 _native.check(self._lib.nm_streams_download(self._h, _native.np_ptr(recs), _native.cuda_stream_ptr()))
         return [recs[self.offsets[j]:self.offsets[j + 1]] for j in range(self.S)]
+
+    def with_replays(self, n_times, seed=None):
+        """New streams whose sessions carry ``n_times`` shuffled replay passes after their online records
+        (``ShuffledReplays.offline_replays``, ``rl.py:419-424``): the same cumulative ``Generator.shuffle`` orders the
+        host path draws (every session from ``default_rng(seed)``), gathered on the device
+        (``nm_streams_with_replays``).  This object stays valid."""
+        import torch
+        from .sweep import replay_order
+        if np.any(self.offsets[1:] - self.offsets[:-1] != self.online):
+            raise RuntimeError("these streams already carry replay passes")
+        orders = [replay_order(int(n), n_times, seed=seed) for n in self.online]
+        counts = np.ascontiguousarray([len(o) for o in orders], dtype=np.int64)
+        order = np.ascontiguousarray(np.concatenate(orders) if len(orders) else np.zeros(0), dtype=np.int64)
+        with torch.cuda.device(self.dmaze.torch_device):
+            h = _native.check_handle(self._lib.nm_streams_with_replays(
+                self._h, _native.np_ptr(order), _native.np_ptr(counts), _native.cuda_stream_ptr()))
+        return DeviceBuiltStreams(self.dmaze, h, self.online + 1, self.has_candidates, replays=counts)
 
     def close(self):
         h, self._h = self._h, None

@@ -259,6 +259,16 @@ __global__ void nm_adjust_kernel(const double *pts, int64_t n, const uint8_t *__
 
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// dst = online records of every session followed by its replay passes: dst[i] = src[map[i]]
+__global__ void __launch_bounds__(256) nm_gather_records_kernel(const uint4 *__restrict__ src, const int64_t *__restrict__ map,
+                                                                int64_t n, uint4 *__restrict__ dst) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = map[i];
+    dst[2 * i] = src[2 * j];
+    dst[2 * i + 1] = src[2 * j + 1];
+  }
+}
+
 }  // namespace
 
 extern "C" int nm_sessions_subsample_device(const double *d_time, const double *d_traj, const double *d_reward,
@@ -434,4 +444,84 @@ extern "C" int nm_streams_download(const nm_streams *st, nm_step_rec *h_records,
   if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
   if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_streams_download: %s", cudaGetErrorString(e));
   return NM_OK;
+}
+
+extern "C" nm_streams *nm_streams_with_replays(const nm_streams *src, const int64_t *h_order, const int64_t *h_counts,
+                                               void *stream) {
+  if (!src || src->device < 0 || !h_counts || src->S <= 0) {
+    nm_fail(NM_ERR_INVALID, "nm_streams_with_replays: bad argument (the streams must live on a CUDA device)");
+    return nullptr;
+  }
+  const int S = src->S;
+  nm_streams *st = new (std::nothrow) nm_streams();
+  if (!st) {
+    nm_fail(NM_ERR_NOMEM, "nm_streams_with_replays: out of memory");
+    return nullptr;
+  }
+  st->S = S;
+  st->num_states = src->num_states;
+  st->device = src->device;
+  st->min_ncand = src->min_ncand;
+  st->offsets.assign(S + 1, 0);
+  st->online.assign(S, 0);
+  std::vector<int64_t> map;  // global source index of every destination record
+  int64_t cursor = 0;
+  for (int j = 0; j < S; ++j) {
+    const int64_t n_on = src->online[j], base = src->offsets[j], extra = h_counts[j];
+    if (extra < 0 || (extra > 0 && !h_order)) {
+      nm_fail(NM_ERR_INVALID, "nm_streams_with_replays: bad replay count for session %d", j);
+      delete st;
+      return nullptr;
+    }
+    st->online[j] = n_on;
+    st->offsets[j + 1] = st->offsets[j] + n_on + extra;
+    for (int64_t i = 0; i < n_on; ++i) map.push_back(base + i);
+    for (int64_t i = 0; i < extra; ++i) {
+      const int64_t k = h_order[cursor + i];
+      if (k < 0 || k >= n_on) {
+        nm_fail(NM_ERR_INVALID, "nm_streams_with_replays: replay index %lld of session %d is out of range", (long long)k, j);
+        delete st;
+        return nullptr;
+      }
+      map.push_back(base + k);
+    }
+    cursor += extra;
+  }
+  const int64_t total = st->offsets[S];
+  st->total = total;
+  cudaStream_t cs = (cudaStream_t)stream;
+  char *base = nullptr;
+  int64_t *d_map = nullptr;
+  cudaError_t e = cudaSetDevice(src->device);
+  const size_t o_off = align256(sizeof(nm_step_rec) * (size_t)(total + 1)),
+               o_onl = o_off + align256(sizeof(int64_t) * (S + 1)), bytes = o_onl + align256(sizeof(int64_t) * S);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&base, bytes);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&d_map, sizeof(int64_t) * (size_t)(total + 1));
+  if (e == cudaSuccess) {
+    st->d_block = base;
+    st->d_records = (nm_step_rec *)base;
+    st->d_offsets = (int64_t *)(base + o_off);
+    st->d_online = (int64_t *)(base + o_onl);
+    e = cudaMemcpyAsync(st->d_offsets, st->offsets.data(), sizeof(int64_t) * (S + 1), cudaMemcpyHostToDevice, cs);
+  }
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(st->d_online, st->online.data(), sizeof(int64_t) * S, cudaMemcpyHostToDevice, cs);
+  if (e == cudaSuccess && total > 0) {
+    e = cudaMemcpyAsync(d_map, map.data(), sizeof(int64_t) * (size_t)total, cudaMemcpyHostToDevice, cs);
+    if (e == cudaSuccess) {
+      int blocks = (int)((total + 255) / 256);
+      if (blocks > 148 * 8) blocks = 148 * 8;
+      nm_gather_records_kernel<<<blocks, 256, 0, cs>>>((const uint4 *)src->d_records, d_map, total, (uint4 *)st->d_records);
+      e = cudaGetLastError();
+    }
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(cs);  // setup call; `map` and d_map die here
+  if (d_map) cudaFree(d_map);
+  if (e != cudaSuccess) {
+    nm_fail(NM_ERR_CUDA, "nm_streams_with_replays: %s", cudaGetErrorString(e));
+    if (base) cudaFree(base);
+    delete st;
+    return nullptr;
+  }
+  return st;
 }

@@ -182,19 +182,24 @@ def records_from_transitions(maze, transitions, mouse=None):
     return recs
 
 
-def replay_records(records, n_times, seed=None, rng=None):
-    """Records of ``n_times`` shuffled replay passes over ``records`` in execution order
+def replay_order(n, n_times, seed=None, rng=None):
+    """Indices, in execution order, of ``n_times`` shuffled replay passes over a buffer of ``n`` updates
     (``ShuffledReplays.offline_replays``, ``rl.py:419-424``: cumulative in-place ``Generator.shuffle``)."""
     if rng is None:
         rng = np.random.default_rng(seed)
-    idx = np.arange(len(records))
+    idx = np.arange(int(n))
     out = []
     for _ in range(int(n_times)):
         rng.shuffle(idx)
-        out.append(records[idx])
+        out.append(idx.copy())
     if not out:
-        return records[:0]
+        return np.zeros(0, dtype=np.int64)
     return np.concatenate(out)
+
+
+def replay_records(records, n_times, seed=None, rng=None):
+    """Records of ``n_times`` shuffled replay passes over ``records`` in execution order."""
+    return records[replay_order(len(records), n_times, seed=seed, rng=rng)]
 
 
 class DeviceStreams:
@@ -348,6 +353,8 @@ class ConditioningSweep:
         if self.alg != _native.ALG_TD0 and not streams.has_candidates:
             raise ValueError("PositiveConditioning / NegativeConditioning need possible_actions")
         self._records, self._online, self._staging = [], [], None
+        if self.replay_n_times > 0:  # the sweep's replay strategy applies to device-built sessions too
+            streams = streams.with_replays(self.replay_n_times, self.replay_seed)
         self._dmaze = streams.dmaze
         self._dstreams = streams
         self._external = True

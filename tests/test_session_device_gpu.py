@@ -193,6 +193,35 @@ def test_tile_action_agents_on_device_built_streams(cuda, agent):
     assert dev.best_fit(a, b, g) == host.best_fit(a, b, g)
 
 
+@pytest.mark.parametrize("alg", ["td0", "positive"])
+def test_replays_on_device_built_streams(cuda, alg):
+    """Shuffled replay passes (rl.py:419-424) appended to device-built streams by a device gather: same records, same
+    tables and likelihoods as host sessions with the same replay strategy."""
+    from navigation_model_b200.batched_sessions import SessionBatch
+    from navigation_model_b200.sweep import ConditioningSweep
+    maze = H.product_m9()
+    omz = H.oracle_m9()
+    sessions = [O.synthetic_session(omz, sid, 200 + 30 * sid) for sid in range(4)]
+    rng = np.random.default_rng(7)
+    a, b, g = H.grid_params(rng, 70)
+    host = ConditioningSweep(maze, alg, possible_actions=H.a8(), replay_n_times=2, replay_seed=11)
+    for traj, rew in sessions:
+        host.add_session(traj, rew)
+    plain = SessionBatch(None, [s[0] for s in sessions], [s[1] for s in sessions]).streams(maze, H.a8())
+    with_rep = plain.with_replays(2, seed=11)
+    for got, want, n_on in zip(with_rep.download(), host._records, host._online):
+        assert got.tobytes() == want.tobytes() and len(got) == 3 * n_on
+    assert plain.total * 3 == with_rep.total  # the source streams are untouched
+    dev = ConditioningSweep(maze, alg, possible_actions=H.a8(), replay_n_times=2, replay_seed=11)
+    dev.use_streams(plain)  # applies the sweep's replay strategy itself
+    assert dev.updates_per_parameter_set == host.updates_per_parameter_set
+    ll_h, v_h = host.log_likelihood(a, b, g, return_v=True)
+    ll_d, v_d = dev.log_likelihood(a, b, g, return_v=True)
+    assert np.array_equal(ll_h, ll_d) and np.array_equal(v_h, v_d)
+    with pytest.raises(RuntimeError):
+        with_rep.with_replays(1)
+
+
 def test_no_candidate_is_an_error(cuda):
     """A step whose rotated endpoints all fall outside the maze: np.max([]) raises in the reference (rl.py:184)."""
     from navigation_model_b200.batched_sessions import SessionBatch
