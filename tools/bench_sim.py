@@ -37,7 +37,6 @@ def main():
     import torch
     from navigation_model_b200.batched_sim import BatchedExperiment
     from navigation_model_b200.simulation import behavioural_components as bc
-    from navigation_model_b200.simulation.maze import Maze
     from navigation_model_b200 import workloads as W
     from oracle import np_oracle as O  # the CPU sample at the end only
 

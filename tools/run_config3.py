@@ -31,7 +31,6 @@ def main():
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
-    from navigation_model_b200.simulation.maze import Maze
     from navigation_model_b200.sweep import ConditioningSweep, parameter_grid, reduce_best, shard_bounds
     from navigation_model_b200 import workloads as W
     from oracle import np_oracle as O  # rank 0's spot check of the result only
