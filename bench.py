@@ -484,6 +484,8 @@ def run_b200(args):
                         ncu_counter(["sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"])),
                     "issue_slots_busy_ncu": (lambda v: None if v is None else v / 100.0)(
                         ncu_counter(["smsp__issue_active.avg.pct_of_peak_sustained_active"])),
+                    "executed_instr_per_update_ncu": (lambda v: None if v is None else v * 32.0 / (P * n_upd))(
+                        ncu_counter(["smsp__inst_executed.sum"])),  # warp instructions x 32 lanes / updates of a launch
                     "peak_source": "nm_fp64_peak_probe (8 independent DFMA chains/thread) timed live, burst; "
                                    "MEASURED_PEAKS.json has no FP64 figure",
                     "alg_fp64_instr_per_update": alg_instr / (P * n_upd),
