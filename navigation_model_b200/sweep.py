@@ -604,6 +604,34 @@ class _TileActionSweep:
             raise ValueError("alpha, beta and gamma must have the same length")
         return alpha, beta, gamma, P
 
+    @staticmethod
+    def regroup_order(alpha, gamma, run=32):
+        """Order that brings parameter sets with equal ``(alpha, gamma)`` together, so that every aligned run of ``run``
+        consecutive sets shares them and the sweep keeps ONE table per run (the tables do not depend on beta).
+
+        ``None`` when the arrays are already laid out that way (a grid with beta fastest), or when no such order exists
+        without padding (some ``(alpha, gamma)`` pair occurs a number of times that is not a multiple of ``run``, other
+        than the last one): the sweep then runs as given.  The sort is stable: sets of a pair keep their order."""
+        P = alpha.size
+        if P <= 1:
+            return None
+
+        def uniform_runs(a, g):
+            n_full = (P // run) * run
+            ok = True
+            if n_full:
+                A, G = a[:n_full].reshape(-1, run), g[:n_full].reshape(-1, run)
+                ok = bool((A == A[:, :1]).all() and (G == G[:, :1]).all())
+            if ok and n_full < P:
+                ok = bool((a[n_full:] == a[n_full]).all() and (g[n_full:] == g[n_full]).all())
+            return ok
+
+        if uniform_runs(alpha, gamma):
+            return None
+        order = np.lexsort((gamma, alpha))  # stable; alpha major, gamma minor
+        a, g = alpha[order], gamma[order]
+        return order if uniform_runs(a, g) else None
+
     def _timed(self, torch, launch):
         """Run ``launch()`` (one C-ABI call) between two CUDA events on the current stream."""
         with torch.cuda.device(self._base.torch_device):
@@ -682,11 +710,18 @@ class ModelBasedSweep(_TileActionSweep):
             _native.tensor_ptr(r_out), _native.cuda_stream_ptr()))  # last_kernel_ms: device time of nm_mb_kernel
         return ll_out
 
-    def log_likelihood(self, alpha, beta, gamma, v_init=None, return_tables=False):
-        """``float64[S, P]`` log-likelihoods (and, optionally, the final ``V`` and ``Rhat`` tables ``[S, P, X, Y]``)."""
+    def log_likelihood(self, alpha, beta, gamma, v_init=None, return_tables=False, regroup=True):
+        """``float64[S, P]`` log-likelihoods (and, optionally, the final ``V`` and ``Rhat`` tables ``[S, P, X, Y]``).
+        ``regroup``: bring sets with equal ``(alpha, gamma)`` together first when that yields uniform runs of 32
+        (:meth:`regroup_order`); results come back in the caller's order."""
         b = self._base
         torch = b._ensure_device()
         alpha, beta, gamma, P = self._params(alpha, beta, gamma)
+        order = self.regroup_order(alpha, gamma) if regroup else None
+        if order is not None:  # sets with equal (alpha, gamma) side by side: tables and sweeps once per run of 32
+            alpha, beta, gamma = (np.ascontiguousarray(x[order]) for x in (alpha, beta, gamma))
+            back = np.empty_like(order)
+            back[order] = np.arange(P)
         dev = b.torch_device
         X, Y = self.maze.shape
         vi = None
@@ -702,9 +737,11 @@ class ModelBasedSweep(_TileActionSweep):
             r_out = torch.empty((S, P, X * Y), dtype=torch.float64, device=dev)
         at, bt, gt = (b._to_dev(torch, x) for x in (alpha, beta, gamma))
         ll = self.log_likelihood_device(at, bt, gt, vi, v_out=v_out, r_out=r_out)
+        unsort = (lambda x: x) if order is None else (lambda x: np.ascontiguousarray(x[:, back]))
         if return_tables:
-            return (ll.cpu().numpy(), v_out.cpu().numpy().reshape(S, P, X, Y), r_out.cpu().numpy().reshape(S, P, X, Y))
-        return ll.cpu().numpy()
+            return (unsort(ll.cpu().numpy()), unsort(v_out.cpu().numpy().reshape(S, P, X, Y)),
+                    unsort(r_out.cpu().numpy().reshape(S, P, X, Y)))
+        return unsort(ll.cpu().numpy())
 
 
 class QLearningSweep(_TileActionSweep):
@@ -736,12 +773,19 @@ class QLearningSweep(_TileActionSweep):
             _native.cuda_stream_ptr()))  # last_kernel_ms: device time of nm_q_kernel
         return ll_out
 
-    def log_likelihood(self, alpha, beta, gamma, q_init=None, return_tables=False):
+    def log_likelihood(self, alpha, beta, gamma, q_init=None, return_tables=False, regroup=True):
         """``float64[S, P]`` log-likelihoods (and, optionally, the final tables ``Q[S, P, X, Y, A]``; entries of
-        non-visitable tiles and unavailable actions keep their initial value)."""
+        non-visitable tiles and unavailable actions keep their initial value).  ``regroup``: bring sets with equal
+        ``(alpha, gamma)`` together first when that yields uniform runs of 32 (:meth:`regroup_order`); results come back
+        in the caller's order."""
         b = self._base
         torch = b._ensure_device()
         alpha, beta, gamma, P = self._params(alpha, beta, gamma)
+        order = self.regroup_order(alpha, gamma) if regroup else None
+        if order is not None:
+            alpha, beta, gamma = (np.ascontiguousarray(x[order]) for x in (alpha, beta, gamma))
+            back = np.empty_like(order)
+            back[order] = np.arange(P)
         dev = b.torch_device
         X, Y = self.maze.shape
         A = self.next_table.shape[1]
@@ -755,6 +799,7 @@ class QLearningSweep(_TileActionSweep):
         q_out = torch.empty((S, P, X * Y * A), dtype=torch.float64, device=dev) if return_tables else None
         at, bt, gt = (b._to_dev(torch, x) for x in (alpha, beta, gamma))
         ll = self.log_likelihood_device(at, bt, gt, qi, q_out=q_out)
+        unsort = (lambda x: x) if order is None else (lambda x: np.ascontiguousarray(x[:, back]))
         if return_tables:
-            return ll.cpu().numpy(), q_out.cpu().numpy().reshape(S, P, X, Y, A)
-        return ll.cpu().numpy()
+            return unsort(ll.cpu().numpy()), unsort(q_out.cpu().numpy().reshape(S, P, X, Y, A))
+        return unsort(ll.cpu().numpy())

@@ -92,3 +92,30 @@ def test_model_based_sweep_configs3_grid(cuda, monkeypatch):
     for p in np.random.default_rng(5).choice(a.size, 2, replace=False):
         _, _, want = O.run_model_based(tr, nxt, a[p], b[p], g[p], n_sweeps=1)
         assert abs(ll[0, p] - want) <= 1e-9 * abs(want)
+
+
+@pytest.mark.parametrize("agent", ["qtable", "modelbased"])
+def test_regrouping_of_grids_given_in_another_order(cuda, agent):
+    """A grid with gamma fastest (``parameter_grid(alpha, beta, gamma)``): the numpy API brings sets with equal
+    (alpha, gamma) together, runs the run-sharing kernel and hands the results back in the caller's order --
+    bit-identical to the sweep over the arrays as given."""
+    from navigation_model_b200.sweep import ModelBasedSweep, QLearningSweep, parameter_grid
+    omz, maze = H.oracle_m9(), H.product_m9()
+    moves = [(dx, dy) for dx in (-1, 0, 1) for dy in (-1, 0, 1) if (dx, dy) != (0, 0)]
+    a, b, g = parameter_grid(np.linspace(0.05, 1, 6), np.logspace(-1, 1.5, 64), np.linspace(0.5, 0.99, 5))
+    sw = QLearningSweep(maze, moves) if agent == "qtable" else ModelBasedSweep(maze, moves, n_sweeps=2)
+    for sid, T in ((0, 400), (2, 150)):
+        sw.add_session(*O.synthetic_session(omz, sid, T))
+    assert sw.regroup_order(a, g) is not None
+    out = sw.log_likelihood(a, b, g, return_tables=True)
+    assert sw.last_sweep_mode() == 1
+    ref = sw.log_likelihood(a, b, g, return_tables=True, regroup=False)
+    assert sw.last_sweep_mode() == 0
+    for x, y in zip(out, ref):
+        assert np.array_equal(x, y)
+    # nothing to do for a grid that is already laid out in runs, nothing possible for 20 beta points
+    g2, a2, b2 = parameter_grid(np.linspace(0.5, 0.99, 5), np.linspace(0.05, 1, 6), np.logspace(-1, 1.5, 64))
+    assert sw.regroup_order(a2, g2) is None
+    a3, b3, g3 = parameter_grid(np.linspace(0.05, 1, 6), np.logspace(-1, 1.5, 20), np.linspace(0.5, 0.99, 5))
+    assert sw.regroup_order(a3, g3) is None
+
