@@ -204,6 +204,10 @@ int sweep_alg(bool with_ll, FitArgs a, int S, int device, cudaStream_t cs) {
   // every aligned run of 32 consecutive sets does, and exactly one of the two kernels below does the work (the other
   // returns at its first instruction) -- no host round trip, the call stays asynchronous.
   const bool try_group = group_enabled() && !a.v_init_per_unit && a.num_states * 8 * 29 + kFixedBytes <= kMaxSmem;
+  // the decision and the launches that read it reach the stream as one uninterrupted sequence, also when two host
+  // threads enqueue sweeps on the same stream
+  static std::mutex launch_mu;
+  std::lock_guard<std::mutex> launch_lock(launch_mu);
   unsigned char *scratch = nullptr;
   rc = stream_scratch((void *)cs, &scratch);
   if (rc != NM_OK) return rc;

@@ -38,6 +38,13 @@ static int runs_mode_word(void *stream, int **out) {
   return NM_OK;
 }
 
+// The decision and the launches that read it must reach the stream as one uninterrupted sequence: two host threads
+// enqueueing sweeps on the SAME stream would otherwise interleave "set / detect / kernels" and read each other's word.
+static std::mutex &runs_launch_mutex() {
+  static std::mutex mu;
+  return mu;
+}
+
 // enable = false: mode 0 (one table per parameter set); else 1 iff every aligned run of 32 sets is uniform
 static void runs_decide(bool enable, const double *d_alpha, const double *d_gamma, int64_t P, int *mode, cudaStream_t cs) {
   nm_runs_set_kernel<<<1, 1, 0, cs>>>(mode, enable ? 1 : 0);

@@ -316,6 +316,7 @@ extern "C" int nm_modelbased_sweep(const nm_maze *mz, const nm_streams *st, cons
   // Parameter sets that share (alpha, gamma) share V and Rhat: the device decides whether every aligned run of 32
   // consecutive sets does, and exactly one of the two launches does the work (NM_MB_GROUP=0: never group).
   cudaStream_t cs = (cudaStream_t)stream;
+  std::lock_guard<std::mutex> launch_lock(runs_launch_mutex());  // decision + launches: one sequence on the stream
   int *mode = nullptr;
   const int rc = runs_mode_word(stream, &mode);
   if (rc != NM_OK) return rc;

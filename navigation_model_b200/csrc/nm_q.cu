@@ -467,6 +467,7 @@ extern "C" int nm_qtable_sweep(const nm_maze *mz, const nm_streams *st, const in
   // Parameter sets that share (alpha, gamma) share their table: the device decides whether every aligned run of 32
   // consecutive sets does, and exactly one of the two kernels does the work (the other returns at its first
   // instruction) -- no host round trip.  NM_Q_GROUP=0 keeps the octet kernel (A/B runs, tests).
+  std::lock_guard<std::mutex> launch_lock(runs_launch_mutex());  // decision + launches: one sequence on the stream
   int *mode = nullptr;
   const int rc = runs_mode_word(stream, &mode);
   if (rc != NM_OK) return rc;
