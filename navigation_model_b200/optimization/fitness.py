@@ -70,16 +70,34 @@ class MultiObjectiveFitness:
 class LogLikelihoodFitness:
     """Negative log-likelihood of recorded sessions for grids of ``(alpha, beta, gamma)``.
 
+    ``algorithm``: ``"td0"`` / ``"positive"`` / ``"negative"`` (the reference's value learners, with
+    ``possible_actions`` = the mouse's relative actions), or one of the two tile-action agents (extensions) --
+    ``"qtable"`` (explicit ``Q[s, a]`` table) and ``"modelbased"`` (reward model + ``n_sweeps`` value-iteration sweeps
+    per step) -- with ``discrete_actions`` = tile displacements.
+
     >>> fit = LogLikelihoodFitness(maze, sessions, algorithm="positive", possible_actions=A8)
     >>> nll = fit(alpha, beta, gamma)                  # float64[P], summed over sessions
     >>> best_nll, best_index = fit.best(alpha, beta, gamma)   # sharded over the process group, if any
     """
 
     def __init__(self, maze, sessions, algorithm="positive", possible_actions=None, mouse_init=None,
-                 replay_n_times=0, replay_seed=None, device=None):
-        from ..sweep import ConditioningSweep
-        self._sweep = ConditioningSweep(maze, algorithm, possible_actions=possible_actions, mouse_init=mouse_init,
-                                        replay_n_times=replay_n_times, replay_seed=replay_seed, device=device)
+                 replay_n_times=0, replay_seed=None, device=None, discrete_actions=None, n_sweeps=1):
+        from ..sweep import ConditioningSweep, ModelBasedSweep, QLearningSweep
+        name = algorithm.lower() if isinstance(algorithm, str) else None
+        if name in ("qtable", "modelbased"):
+            if discrete_actions is None:
+                raise ValueError(f"algorithm {algorithm!r} needs discrete_actions (tile displacements)")
+            if name == "qtable":
+                self._sweep = QLearningSweep(maze, discrete_actions, device=device, replay_n_times=replay_n_times,
+                                             replay_seed=replay_seed)
+            else:
+                if replay_n_times:
+                    raise ValueError("the model-based agent plans instead of replaying: replay_n_times must be 0")
+                self._sweep = ModelBasedSweep(maze, discrete_actions, n_sweeps=n_sweeps, device=device)
+        else:
+            self._sweep = ConditioningSweep(maze, algorithm, possible_actions=possible_actions, mouse_init=mouse_init,
+                                            replay_n_times=replay_n_times, replay_seed=replay_seed, device=device)
+        self._tile_actions = name in ("qtable", "modelbased")
         for s in sessions:
             if isinstance(s, (tuple, list)) and len(s) == 2:
                 self._sweep.add_session(s[0], s[1])
@@ -93,7 +111,12 @@ class LogLikelihoodFitness:
         return self._sweep
 
     def per_session(self, alpha, beta, gamma, v_init=None):
-        """``float64[S, P]`` log-likelihoods."""
+        """``float64[S, P]`` log-likelihoods (``v_init``: the initial value table of the value learners / the
+        model-based agent)."""
+        if isinstance(self._sweep, _sweep_types()[2]):
+            if v_init is not None:
+                raise ValueError("the Q-table agent starts from q_init, not v_init: use fit.sweep.log_likelihood")
+            return self._sweep.log_likelihood(alpha, beta, gamma)
         return self._sweep.log_likelihood(alpha, beta, gamma, v_init=v_init)
 
     def __call__(self, alpha, beta, gamma, v_init=None):
@@ -104,4 +127,13 @@ class LogLikelihoodFitness:
         return -acc
 
     def best(self, alpha, beta, gamma, v_init=None, group=None):
+        if self._tile_actions:
+            if v_init is not None:
+                raise ValueError("best() of the tile-action agents starts from zero tables")
+            return self._sweep.best_fit(alpha, beta, gamma, group=group)
         return self._sweep.best_fit(alpha, beta, gamma, v_init=v_init, group=group)
+
+
+def _sweep_types():
+    from ..sweep import ConditioningSweep, ModelBasedSweep, QLearningSweep
+    return ConditioningSweep, ModelBasedSweep, QLearningSweep

@@ -140,3 +140,28 @@ def test_qtable_group_kernel_matches_octet_kernel_and_oracle(cuda, maze_name, ac
     ql.log_likelihood(a, b, g2)
     assert ql.last_sweep_mode() == 0
 
+
+def test_loglikelihood_fitness_drives_the_tile_action_agents(cuda):
+    """LogLikelihoodFitness (the objective the sweeps plug into, optimization/fitness.py) with the two extensions."""
+    from navigation_model_b200.optimization.fitness import LogLikelihoodFitness
+    omz, maze = H.oracle_m9(), H.product_m9()
+    sessions = [O.synthetic_session(omz, sid, 200) for sid in (0, 1)]
+    rng = np.random.default_rng(2)
+    a, b, g = H.grid_params(rng, 40)
+    nxt = O.transition_table(omz, ACTS8)
+    for name in ("qtable", "modelbased"):
+        fit = LogLikelihoodFitness(maze, sessions, algorithm=name, discrete_actions=ACTS8, n_sweeps=2)
+        nll = fit(a, b, g)
+        assert nll.shape == (40,)
+        want = np.zeros(40)
+        for traj, rew in sessions:
+            tr = O.extract_transitions(omz, traj, rew, None)
+            for p in range(40):
+                want[p] -= (O.run_q_learning(tr, nxt, a[p], b[p], g[p])[1] if name == "qtable"
+                            else O.run_model_based(tr, nxt, a[p], b[p], g[p], n_sweeps=2)[2])
+        np.testing.assert_allclose(nll, want, rtol=1e-9)
+        v, i = fit.best(a, b, g)
+        assert i == int(np.argmin(nll)) and abs(v - nll[i]) <= 1e-9 * abs(nll[i])
+    with pytest.raises(ValueError):
+        LogLikelihoodFitness(maze, sessions, algorithm="qtable")
+
