@@ -295,6 +295,13 @@ class BatchedExperiment:
             keep.append(t)
             return t
 
+        def dev_cols(*cols_):
+            """``[N, k]`` parameter block from ``k`` per-mouse columns: the columns are uploaded as they are and
+            interleaved on the device (a host ``np.stack`` of a million rows costs more than the copy)."""
+            t = torch.stack([torch.from_numpy(np.ascontiguousarray(c, dtype=np.float64)).to(dev) for c in cols_], dim=1)
+            keep.append(t)
+            return t
+
         def out(shape, dtype, zero=False):
             t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=dev)
             keep.append(t)
@@ -314,15 +321,15 @@ class BatchedExperiment:
         args.d_init_prev = dev_f64(prev).data_ptr()
         if _native.COMP_ANXIETY in self.kinds:
             p4 = cols["p4"] if "p4" in cols else np.zeros(N)
-            args.d_anxiety = dev_f64(np.stack([cols["W_anx"], cols["p1"], cols["p2"], cols["p3"], p4], 1)).data_ptr()
+            args.d_anxiety = dev_cols(cols["W_anx"], cols["p1"], cols["p2"], cols["p3"], p4).data_ptr()
         if _native.COMP_BCOST in self.kinds:
             args.d_bcost_weight = dev_f64(cols["W_bcost"]).data_ptr()
             args.d_bcost_table = dev_f64(bc.bcost_tables(self.discrete_actions, cols["k"], cols["gamma"])).data_ptr()
         if _native.COMP_EXPERIENCE in self.kinds:
-            args.d_experience = dev_f64(np.stack([cols[n] for n in ("W_exp", "xi", "kappa_home", "kappa_explo",
-                                                                    "theta_explo", "theta_home")], 1)).data_ptr()
+            args.d_experience = dev_cols(*[cols[n] for n in ("W_exp", "xi", "kappa_home", "kappa_explo",
+                                                              "theta_explo", "theta_home")]).data_ptr()
         if _native.COMP_BPERSISTENCE in self.kinds:
-            args.d_bpersistence = dev_f64(np.stack([cols[n] for n in ("W_bper", "bp", "Wm", "Wnm")], 1)).data_ptr()
+            args.d_bpersistence = dev_cols(*[cols[n] for n in ("W_bper", "bp", "Wm", "Wnm")]).data_ptr()
         if _native.COMP_VTABLE in self.kinds:
             args.d_vtable_weight = dev_f64(cols["W_values"]).data_ptr()
             v = self.v_table

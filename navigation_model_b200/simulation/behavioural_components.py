@@ -209,19 +209,39 @@ def bcost_tables(discrete_actions, k, gamma):
     k = np.atleast_1d(np.asarray(k, dtype=np.float64))
     gamma = np.atleast_1d(np.asarray(gamma, dtype=np.float64))
     angles = np.arctan2(acts[:, 1], acts[:, 0])
-    if np.all(np.isfinite(k) & (k >= 0)):
-        # scipy's own formula (vonmises_gen._pdf: exp(kappa * cosm1(x)) / (2 pi i0e(kappa))) without the generic
-        # rv_continuous.pdf machinery: same bits (tests/test_host_api.py), ~100x faster for a million mice
-        import scipy.special as sc
-        out = np.exp(k[:, None] * sc.cosm1(angles)[None, :]) / (2 * np.pi * sc.i0e(k))[:, None]
-    else:
+    null = np.all(acts == (0, 0), axis=1)
+    far = np.linalg.norm(acts, ord=np.inf, axis=1) >= 2
+    if not np.all(np.isfinite(k) & (k >= 0)):
         from scipy.stats import vonmises
         out = vonmises.pdf(angles[None, :], k[:, None])
-    out[:, np.all(acts == (0, 0), axis=1)] = 0.0
-    far = np.linalg.norm(acts, ord=np.inf, axis=1) >= 2
-    g = np.ones((len(k), len(acts)))
-    g[:, far] = gamma[:, None]
-    return out * g
+        out[:, null] = 0.0
+        out[:, far] *= gamma[:, None]  # the other columns are multiplied by 1.0 in the reference: unchanged bits
+        return out
+    # scipy's own formula (vonmises_gen._pdf: exp(kappa * cosm1(x)) / (2 pi i0e(kappa))) without the generic
+    # rv_continuous.pdf machinery: same bits (tests/test_host_api.py), ~100x faster for a million mice.  Elementwise,
+    # so large batches are cut into row blocks and spread over a few threads (numpy releases the GIL in its loops).
+    import scipy.special as sc
+    cm1 = sc.cosm1(angles)[None, :]
+    out = np.empty((len(k), len(acts)))
+
+    def block(lo, hi):
+        kk = k[lo:hi]
+        np.multiply(kk[:, None], cm1, out=out[lo:hi])
+        np.exp(out[lo:hi], out=out[lo:hi])
+        out[lo:hi] /= (2 * np.pi * sc.i0e(kk))[:, None]
+        out[lo:hi, null] = 0.0
+        out[lo:hi, far] *= gamma[lo:hi, None]
+
+    rows = 1 << 16
+    if len(k) <= 2 * rows:
+        block(0, len(k))
+    else:
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        spans = [(lo, min(lo + rows, len(k))) for lo in range(0, len(k), rows)]
+        with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+            list(pool.map(lambda sp: block(*sp), spans))
+    return out
 
 
 @weight("W_bcost")
