@@ -37,9 +37,6 @@ constexpr int kSimThreads = 128;
 #ifndef NM_SIM_MIN_CTAS
 #define NM_SIM_MIN_CTAS 3  // resident CTAs per SM the register allocation is capped for (32-bit visit counters)
 #endif
-#ifndef NM_SIM_COOP_MAX_ROUNDS
-#define NM_SIM_COOP_MAX_ROUNDS 5  // more rounds of shared ray walks than this: every mouse walks its own endpoints
-#endif
 #ifndef NM_SIM_MIN_CTAS_U16
 #define NM_SIM_MIN_CTAS_U16 6  // same, for the variant with 16-bit visit counters
 #endif
@@ -314,20 +311,7 @@ __global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 
               res_w[lane * kA + i] = (uint16_t)(cur_tile | (start_ok ? 0x8000 : 0));
         }
         const int nd = __popc(dmask);
-        if (nd * n_walk > NM_SIM_COOP_MAX_ROUNDS * 32) {
-          // (almost) every mouse moved: each walks its own endpoints
-          if (need) {
-#pragma unroll 1
-            for (int j = 0; j < n_walk; ++j) {
-              const int i = (int)((d.walk_list >> (4 * j)) & 7u);
-              double ex, ey;
-              nm_pose_endpoint(c, s, px, py, act_sm[2 * i], act_sm[2 * i + 1], &ex, &ey);
-              int tile_e;
-              const bool ok = geo.move_ok(start_ok, cur_tx, cur_ty, px, py, ex, ey, &tile_e);
-              res_w[lane * kA + i] = (uint16_t)(tile_e | (ok ? 0x8000 : 0));
-            }
-          }
-        } else if (n_walk > 0) {
+        if (n_walk > 0) {
           const int my_rank = __popc(dmask & ((1u << lane) - 1u));
           if (need) rank_w[my_rank] = (uint8_t)lane;
           __syncwarp();
