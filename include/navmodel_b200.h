@@ -220,6 +220,11 @@ int nm_vtable_sweep(int alg, const nm_maze *mz, const nm_streams *st, const doub
                     const double *d_gamma, int64_t P, const double *d_v_init, int v_init_per_unit,
                     double *d_v_out, void *stream);
 
+/* Largest number of visitable tiles (compact states) the per-parameter-set value-table kernels can hold in shared
+ * memory (867 with 227 KB: 32 table columns of 8 bytes per state next to the stream rings).  Larger mazes:
+ * ConditioningExperiment.run keeps the reference's per-transition host loop, the sweeps return NM_ERR_INVALID. */
+int nm_vtable_max_states(void);
+
 /* Same recurrence + log-likelihood of the observed choices under the softmax policy
  * p_k = softmax_k(beta * V[cand_k]) (exploration_model.py:84-93), evaluated BEFORE the update of the
  * step, accumulated in FP64 in step order over the online records whose obs != NM_OBS_NONE.
@@ -336,6 +341,10 @@ typedef struct nm_sim_args {
 
 /* StandardExperiment.run(n_steps) for n_mice independent mice on the maze's device. */
 int nm_simulate(const nm_maze *mz, const nm_sim_args *args, void *stream);
+
+/* 1 if an X x Y maze fits the simulation kernel's shared-memory visit map for runs of n_steps (the counters are 16
+ * bits wide below 65535 steps), else 0: StandardExperiment.run then keeps the reference's per-step host loop. */
+int nm_simulate_fits(int X, int Y, int n_steps);
 
 /* Vectorised Maze.is_movement_possible_cont on the device: d_segments [n,4] = (x1,y1,x2,y2),
  * d_out u8[n] (1 possible).  maze.py:563-611 */

@@ -371,6 +371,11 @@ extern "C" int nm_argmin_nll(const double *d_ll, int S, int64_t P, double *d_nll
   return NM_OK;
 }
 
+extern "C" int nm_vtable_max_states(void) {
+  // one CTA must hold at least one warp of per-parameter-set table columns next to the rings
+  return (int)((kMaxSmem - kFixedBytes) / (8 * 32));
+}
+
 extern "C" int nm_loglik_sweep_mode(void *stream, int *mode_out) {
   NM_CHECK_ARG(mode_out, "nm_loglik_sweep_mode: NULL output");
   unsigned char *scratch = nullptr;

@@ -706,6 +706,16 @@ extern "C" int nm_simulate(const nm_maze *mz, const nm_sim_args *args, void *str
   return NM_OK;
 }
 
+extern "C" int nm_simulate_fits(int X, int Y, int n_steps) {
+  // the narrowest CTA (one warp) of nm_sim_kernel: see smem_for in nm_simulate
+  if (X <= 0 || Y <= 0 || n_steps < 0) return 0;
+  const size_t nT = (size_t)X * Y, th = 32;
+  const size_t cnt_bytes = n_steps < 65535 ? sizeof(uint16_t) : sizeof(uint32_t);
+  const size_t smem = 128 + 16 * kA + th * (1 + 2 * kA) + (size_t)(5 + kA) * th * sizeof(double) + nT * th * cnt_bytes +
+                      nT * sizeof(double) + NmSimGeom::smem_bytes(X, Y);
+  return smem <= 227 * 1024 ? 1 : 0;
+}
+
 extern "C" int nm_maze_movements_possible_device(const nm_maze *mz, const double *d_segments, int64_t n,
                                                  uint8_t *d_out, void *stream) {
   NM_CHECK_ARG(mz && mz->device >= 0, "nm_maze_movements_possible_device: maze not on a device");

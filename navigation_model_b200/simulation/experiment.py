@@ -30,10 +30,13 @@ class StandardExperiment:
         self._mouse = mouse
         self._debug = debug
 
-    def _device_eligible(self):
+    def _device_eligible(self, iterations=0):
         model = self._exp_model
         if type(self._maze) is not Maze or type(self._mouse) is not Mouse:
             return False
+        X, Y = self._maze.shape
+        if not _native.lib().nm_simulate_fits(int(X), int(Y), int(iterations)):
+            return False  # the visit map does not fit the kernel's shared memory: the host loop below still works
         if type(model) is RandomModel:
             return (1 <= len(self._mouse.possible_actions) <= _native.NM_MAX_CAND
                     and type(model._rng.bit_generator).__name__ == "PCG64")
@@ -63,7 +66,7 @@ class StandardExperiment:
 
     def run(self, iterations):
         self._mouse.enable_history(True)  # experiment.py:32
-        if self._device_eligible():
+        if self._device_eligible(int(iterations)):
             self._run_device(int(iterations))
         else:
             self._run_host(int(iterations))
