@@ -174,6 +174,41 @@ def test_random_batch_vs_oracle(cuda):
     assert mismatched == 0, f"{mismatched} of {N} discrete trajectories diverged"
 
 
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_random_mazes_vs_oracle(cuda, seed):
+    """Irregular 7 x 11 mazes with scattered void tiles (ray walks past void corners, dead ends), a random subset of the
+    eight actions that keeps the null action, 48 mice x 150 steps with replayed draws: choices, poses, occupancy."""
+    from navigation_model_b200.batched_sim import BatchedExperiment
+    from navigation_model_b200.simulation.maze import Maze
+    rng = np.random.default_rng(seed)
+    X, Y, st = 7, 11, 0.1
+    rows = [[("V" if rng.random() < 0.22 else "CWM"[rng.integers(3)]) for _ in range(Y)] for _ in range(X)]
+    rows[1][1], rows[1][2] = "M", "W"
+    layout = "\n".join("".join(r) for r in rows)
+    maze, omz = Maze(layout, "", size_tile=st), O.OracleMaze(layout, st)
+    keep = np.concatenate([[0], 1 + np.sort(rng.permutation(7)[:int(rng.integers(3, 8))])])
+    units = O.A8_UNITS[keep]
+    acts = units * st
+    N, T = 48, 150
+    V = rng.random((X, Y))
+    P = _random_params(rng, N)
+    cells = np.array([omz.vis_cells[i] for i in rng.integers(0, len(omz.vis_cells), N)])
+    pos0 = np.array([maze.get_tile_centre(c) for c in cells]) + rng.uniform(-0.03, 0.03, (N, 2))
+    ori0 = rng.uniform(-np.pi, np.pi, N)
+    draws = rng.random((N, T))
+    exp = BatchedExperiment(maze, acts, units, _classes(), v_table=V)
+    res = exp.run(P, T, pos0, ori0, init_disc=cells, draws=draws, history=True, occupancy=True)
+    for m in range(N):
+        ref = O.simulate(omz, acts, units, pos0[m], ori0[m], cells[m], P["beta"][m],
+                         _oracle_components(P, m, units, V), draws[m])
+        assert ref["status"] == res.status[m] == 0
+        assert np.array_equal(ref["choice"], res.choices[m]), (seed, m)
+        np.testing.assert_allclose(res.history_position[m], ref["hist_pos"], rtol=0, atol=POSE_ATOL)
+        met = O.metrics_of_history(omz, ref["hist_pos"])
+        assert np.array_equal(met["occupancy"], res.occupancy[m])
+        assert met["it_visit"] == res.it_visit[m] and met["count_moving"] == res.count_moving[m]
+
+
 def test_component_subsets_order_and_inactive(cuda):
     """Any ordered subset of components; an inactive component contributes nothing."""
     from navigation_model_b200.batched_sim import BatchedExperiment
