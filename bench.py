@@ -472,8 +472,9 @@ def run_b200(args):
         alg_bytes = n_upd * 32 + P * 32  # stream once + (alpha, beta, gamma, ll) per parameter set
         roofline = {"bound": "fp64_issue", "achieved": achieved, "peak": peak_ginstr, "unit": "GInstr/s",
                     "frac": achieved / peak_ginstr, "traffic": ncu_dram_traffic(),
-                    "kernel": (f"nm_fit_group_kernel<{args.alg}> (one value table per warp)" if sweep_mode == 1
-                               else f"nm_fit_exact_kernel<{args.alg}, loglik>"),
+                    "kernel": {1: f"nm_fit_group_kernel<{args.alg}> (one value table per warp)",
+                               2: f"nm_fit_global_kernel<{args.alg}, loglik> (tables in device memory)"}.get(
+                                   sweep_mode, f"nm_fit_exact_kernel<{args.alg}, loglik>"),
                     "kernel_ms": float(kern_ms.mean()),
                     "kernel_ms_covers": "the whole nm_loglik_sweep call: the dominant kernel + 3 launches of a few "
                                         "microseconds (run detection, the kernel that stands down)",

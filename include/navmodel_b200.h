@@ -220,9 +220,10 @@ int nm_vtable_sweep(int alg, const nm_maze *mz, const nm_streams *st, const doub
                     const double *d_gamma, int64_t P, const double *d_v_init, int v_init_per_unit,
                     double *d_v_out, void *stream);
 
-/* Largest number of visitable tiles (compact states) the per-parameter-set value-table kernels can hold in shared
- * memory (867 with 227 KB: 32 table columns of 8 bytes per state next to the stream rings).  Larger mazes:
- * ConditioningExperiment.run keeps the reference's per-transition host loop, the sweeps return NM_ERR_INVALID. */
+/* Largest number of visitable tiles (compact states) the per-parameter-set value-table kernels can hold in SHARED
+ * memory (867 with 227 KB: 32 table columns of 8 bytes per state next to the stream rings).  Larger mazes run the same
+ * sweeps with their tables in device memory (T[state][parameter set], coalesced, L2 / HBM resident; also on request
+ * with NM_FIT_TABLES=global): same results, no size limit. */
 int nm_vtable_max_states(void);
 
 /* Same recurrence + log-likelihood of the observed choices under the softmax policy
@@ -234,11 +235,14 @@ int nm_loglik_sweep(int alg, const nm_maze *mz, const nm_streams *st, const doub
                     const double *d_beta, const double *d_gamma, int64_t P, const double *d_v_init,
                     int v_init_per_unit, double *d_ll_out, double *d_v_out, void *stream);
 
-/* Which kernel the last nm_loglik_sweep on `stream` (current device) used: 0 = one value table per parameter set,
- * 1 = one table per warp, shared by an aligned run of 32 consecutive parameter sets with equal (alpha, gamma) -- the
- * device checks the arrays itself, so a Cartesian grid whose beta axis varies fastest (a multiple of 32 points) takes
- * the shared path without any hint (results are bit-identical either way; NM_FIT_GROUP=0 forces 0).  Synchronises
- * the stream: diagnostics and tests only. */
+/* Which kernel the last nm_loglik_sweep on `stream` (current device) used:
+ *   1 = one value table per WARP in shared memory, shared by an aligned run of 32 consecutive parameter sets with equal
+ *       (alpha, gamma) -- the device checks the arrays itself, so a Cartesian grid whose beta axis varies fastest (a
+ *       multiple of 32 points) takes this path without any hint (NM_FIT_GROUP=0 disables it);
+ *   2 = one table per parameter set in DEVICE memory (T[state][set], coalesced, L2 / HBM resident): arbitrary parameter
+ *       sets, any maze size (the default for them; NM_FIT_TABLES=shared selects 0 instead);
+ *   0 = one table per parameter set in shared memory (mazes of at most nm_vtable_max_states() states).
+ * Results are bit-identical in all three.  Synchronises the stream: diagnostics and tests only. */
 int nm_loglik_sweep_mode(void *stream, int *mode_out);
 
 /* Per-shard best fit: nll[p] = -(sum_s ll[s, p]) (sessions added in index order), then the minimum and

@@ -136,9 +136,11 @@ bool memo_enabled() {
 // Cost model measured on B200 (tools/fit_group_sweep.py, profiles/r01_fit_group.md): warp i sits on scheduler i % 4
 // and a wave lasts kWave[w] (relative) for w consumer warps on the busiest scheduler -- a staircase in the warps per
 // CTA.  Pick the CTA size with the lowest waves x wave-time product; ties go to the smaller CTA.
-int group_warps(int64_t runs, int S, int device) {
+int group_warps(int64_t runs, int S, int device, int num_states) {
   static const double kWave[9] = {0.0, 1.0, 1.12, 1.29, 1.45, 1.65, 1.91, 2.19, 2.50};
-  const int max_nw = 29;
+  int max_nw = (int)(((int64_t)kMaxSmem - kFixedBytes) / ((int64_t)num_states * 8));  // one table column per warp
+  if (max_nw > 29) max_nw = 29;
+  if (max_nw < 1) max_nw = 1;
   const char *env = getenv("NM_FIT_GROUP_NW");
   if (env && atoi(env) >= 1 && atoi(env) <= max_nw) return atoi(env);
   int sms = 148;
@@ -165,7 +167,7 @@ int group_warps(int64_t runs, int S, int device) {
 template <int ALG>
 int launch_group(const FitArgs &a, int S, int device, cudaStream_t cs) {
   const int64_t runs = (a.P + 31) / 32;
-  const int nw = group_warps(runs, S, device);
+  const int nw = group_warps(runs, S, device, a.num_states);
   const size_t smem = (size_t)kFixedBytes + (size_t)a.num_states * 8 * nw;
   auto kernel = nm_fit_group_kernel<ALG>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -174,6 +176,98 @@ int launch_group(const FitArgs &a, int S, int device, cudaStream_t cs) {
   kernel<<<grid, 32 * (nw + 1), smem, cs>>>(a);
   e = cudaGetLastError();
   if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_fit_group_kernel launch: %s", cudaGetErrorString(e));
+  return NM_OK;
+}
+
+// ---- tables in device memory (any maze size) -----------------------------------------------------------
+// grow-only scratch per device: states x parameter sets (padded to 32) doubles, reused by every later sweep
+int global_tables(int device, size_t bytes, double **out) {
+  static std::mutex mu;
+  static std::map<int, std::pair<double *, size_t>> scratch;
+  std::lock_guard<std::mutex> lock(mu);
+  auto &slot = scratch[device];
+  if (slot.second < bytes) {
+    if (slot.first) {
+      cudaDeviceSynchronize();  // earlier sweeps may still use the old block
+      cudaFree(slot.first);
+      slot.first = nullptr;
+      slot.second = 0;
+    }
+    double *buf = nullptr;
+    const cudaError_t e = cudaMalloc((void **)&buf, bytes);
+    if (e != cudaSuccess) return nm_fail(NM_ERR_NOMEM, "value tables in device memory: cudaMalloc(%zu): %s", bytes,
+                                         cudaGetErrorString(e));
+    slot.first = buf;
+    slot.second = bytes;
+  }
+  *out = slot.first;
+  return NM_OK;
+}
+
+// NM_FIT_TABLES = "global" / "shared" pins the choice (tests, A/B runs); default: see sweep_alg
+int tables_choice() {
+  const char *env = getenv("NM_FIT_TABLES");
+  return !env ? 0 : env[0] == 'g' ? 1 : env[0] == 's' ? -1 : 0;
+}
+
+// which kernel family handled "mode 0" of the last likelihood sweep on a (device, stream): nm_loglik_sweep_mode
+std::map<std::pair<int, void *>, int> &last_tables_map() {
+  static std::map<std::pair<int, void *>, int> m;
+  return m;
+}
+std::mutex &last_tables_mutex() {
+  static std::mutex mu;
+  return mu;
+}
+void note_tables(void *stream, int global) {
+  int device = 0;
+  cudaGetDevice(&device);
+  std::lock_guard<std::mutex> lock(last_tables_mutex());
+  last_tables_map()[std::make_pair(device, stream)] = global;
+}
+
+template <int ALG, bool LL>
+int sweep_global(FitArgs a, int S, int device, cudaStream_t cs) {
+  // byte offsets of table rows travel as 32 bits in the decoded records: bound the parameter sets per launch
+  int64_t max_sets = (((int64_t)0xffffffffLL / 8) / (a.num_states > 0 ? a.num_states : 1)) & ~(int64_t)31;
+  if (max_sets < 32) return nm_fail(NM_ERR_INVALID, "sweep: a maze with %d states is too large", a.num_states);
+  // 64 registers (launch bounds of 960 threads): up to 28 consumer warps + producer per SM hide the L2 latency of the
+  // table accesses; few parameter sets are spread over the SMs in smaller CTAs
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const char *env_nc = getenv("NM_FIT_GLOBAL_NC");
+  int nc = (int)(((a.P + sms - 1) / sms + 31) / 32) * 32;
+  if (nc < 32) nc = 32;
+  if (nc > 896) nc = 896;
+  if (env_nc && atoi(env_nc) >= 32 && atoi(env_nc) <= 928 && atoi(env_nc) % 32 == 0) nc = atoi(env_nc);
+  if (max_sets > (int64_t)sms * 896) max_sets = (int64_t)sms * 896;  // one full wave per slice: no partial second wave
+  auto kernel = nm_fit_global_kernel<ALG, LL>;
+  const size_t smem = (size_t)kFixedBytes;
+  for (int64_t lo = 0; lo < a.P; lo += max_sets) {
+    FitArgs b = a;
+    b.P = a.P - lo < max_sets ? a.P - lo : max_sets;
+    b.alpha = a.alpha + lo;
+    b.gamma = a.gamma + lo;
+    if (a.beta) b.beta = a.beta + lo;
+    if (a.v_init && a.v_init_per_unit) b.v_init = a.v_init + lo * a.n_tiles;
+    if (b.P < a.P && !(env_nc && atoi(env_nc) > 0)) {  // CTA size of this slice
+      nc = (int)(((b.P + sms - 1) / sms + 31) / 32) * 32;
+      nc = nc < 32 ? 32 : nc > 896 ? 896 : nc;
+    }
+    const int64_t ppad = (b.P + 31) & ~(int64_t)31;
+    double *tables = nullptr;
+    const int rc = global_tables(device, sizeof(double) * (size_t)a.num_states * (size_t)ppad, &tables);
+    if (rc != NM_OK) return rc;
+    for (int sess = 0; sess < S; ++sess) {  // the scratch holds one table per parameter set: sessions in turn
+      FitArgs c = b;
+      // outputs of the whole call are [S, P_total, ...]: shift to this slice's first parameter set
+      if (a.ll_out) c.ll_out = a.ll_out + (int64_t)sess * (a.P - b.P) + lo;
+      if (a.v_out) c.v_out = a.v_out + ((int64_t)sess * (a.P - b.P) + lo) * a.n_tiles;
+      kernel<<<(unsigned)((b.P + nc - 1) / nc), nc + 32, smem, cs>>>(c, tables, ppad, sess);
+      const cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_fit_global_kernel launch: %s", cudaGetErrorString(e));
+    }
+  }
   return NM_OK;
 }
 
@@ -186,9 +280,20 @@ bool group_enabled() {
 template <int ALG>
 int sweep_alg(bool with_ll, FitArgs a, int S, int device, cudaStream_t cs) {
   LaunchPlan exact;
-  int rc = plan_launch(a.num_states * 8, a.P, S, device, "NM_FIT_NC", &exact);
-  if (rc != NM_OK) return rc;
+  const bool fits = ((int64_t)kMaxSmem - kFixedBytes) / ((int64_t)a.num_states * 8) >= 32;  // a warp of table columns
   a.mode = nullptr;
+  // Arbitrary parameter sets: tables in device memory (28 warps per SM) beat the shared-memory layout (14 warps) on the
+  // likelihood sweep; value-only sweeps and the memoised variant stay in shared memory while the maze fits.
+  const int choice = tables_choice();
+  const bool ll_global = !fits || choice > 0 || (choice == 0 && with_ll && !memo_enabled());
+  if (!fits || choice > 0) {
+    if (!with_ll) return sweep_global<ALG, false>(a, S, device, cs);
+  }
+  int rc = NM_OK;
+  if (fits) {
+    rc = plan_launch(a.num_states * 8, a.P, S, device, "NM_FIT_NC", &exact);
+    if (rc != NM_OK) return rc;
+  }
   if (!with_ll) return launch(nm_fit_exact_kernel<ALG, false, false>, a, S, exact, cs, "nm_fit_exact_kernel");
   LaunchPlan memo;
   if (memo_enabled() && plan_launch(a.num_states * 16, a.P, S, device, "NM_FIT_MEMO_NC", &memo) == NM_OK) {
@@ -203,7 +308,8 @@ int sweep_alg(bool with_ll, FitArgs a, int S, int device, cudaStream_t cs) {
   // Likelihood sweep.  Parameter sets that share (alpha, gamma) share their value table: the device decides whether
   // every aligned run of 32 consecutive sets does, and exactly one of the two kernels below does the work (the other
   // returns at its first instruction) -- no host round trip, the call stays asynchronous.
-  const bool try_group = group_enabled() && !a.v_init_per_unit && a.num_states * 8 * 29 + kFixedBytes <= kMaxSmem;
+  // (big mazes: as many warps as fit, at least one table per CTA)
+  const bool try_group = group_enabled() && !a.v_init_per_unit && a.num_states * 8 + kFixedBytes <= kMaxSmem;
   // the decision and the launches that read it reach the stream as one uninterrupted sequence, also when two host
   // threads enqueue sweeps on the same stream
   static std::mutex launch_mu;
@@ -221,6 +327,8 @@ int sweep_alg(bool with_ll, FitArgs a, int S, int device, cudaStream_t cs) {
     rc = launch_group<ALG>(a, S, device, cs);
     if (rc != NM_OK) return rc;
   }
+  note_tables((void *)cs, ll_global ? 1 : 0);
+  if (ll_global) return sweep_global<ALG, true>(a, S, device, cs);
   return launch(nm_fit_exact_kernel<ALG, true, false>, a, S, exact, cs, "nm_fit_exact_kernel");
 }
 
@@ -385,6 +493,13 @@ extern "C" int nm_loglik_sweep_mode(void *stream, int *mode_out) {
   cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
   if (e == cudaSuccess) e = cudaMemcpy(mode_out, scratch + kScratchPartials, sizeof(int), cudaMemcpyDeviceToHost);
   if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_loglik_sweep_mode: %s", cudaGetErrorString(e));
+  if (*mode_out == 0) {  // per-set tables: in shared memory (0) or in device memory (2)?
+    int device = 0;
+    cudaGetDevice(&device);
+    std::lock_guard<std::mutex> lock(last_tables_mutex());
+    const auto it = last_tables_map().find(std::make_pair(device, stream));
+    if (it != last_tables_map().end() && it->second) *mode_out = 2;
+  }
   return NM_OK;
 }
 

@@ -424,6 +424,88 @@ __global__ void __launch_bounds__(960, 1) nm_fit_group_kernel(const FitArgs a) {
   }
 }
 
+// =================================== GLOBAL body ===========================================================
+// Value tables in device memory: T[state][parameter set] (a row = all parameter sets of the launch, padded to 32), one
+// column per thread.  All threads of a warp walk the same stream, so a step's loads and its store hit one row at
+// consecutive parameter sets: coalesced 256-byte accesses, served by L2 while the working set (states x sets x 8 B)
+// fits its 126 MB, by HBM beyond.  Nothing limits the maze size, and with 64 registers 28 consumer warps per SM hide
+// the L2 latency -- twice the residency the shared-memory layout allows, which makes this the faster kernel for
+// arbitrary parameter sets (configs[1]: 4.42 ms against 4.78 ms) and the default for them; NM_FIT_TABLES=shared
+// keeps the shared-memory kernel.  One launch per session (the scratch holds one table per set).
+// Same producer warp / rings / exact_step bodies: results are bit-identical to the shared-memory kernels.
+template <int ALG, bool LL>
+__global__ void __launch_bounds__(960, 1) nm_fit_global_kernel(const FitArgs a, double *__restrict__ tables,
+                                                               const int64_t ppad, const int sess) {
+  if (a.mode && *a.mode != 0) return;  // the group kernel owns this sweep
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const Rings rg = carve_rings(smem_raw);
+  const int tid = threadIdx.x;
+  if (tid < 16) reinterpret_cast<double *>(smem_raw + kBarBytes + kRawBytes + kDecBytes)[tid] = c_exp2tab[tid];
+  const int nc = blockDim.x - 32;
+  const int64_t p = (int64_t)blockIdx.x * nc + tid;
+  const bool live = tid < nc && p < a.P;
+  const int64_t rec0 = a.offsets[sess];
+  const int64_t n = a.offsets[sess + 1] - rec0;
+  const int64_t n_on = a.online[sess];
+  const int nchunks = (int)((n + kChunk - 1) / kChunk);
+  if (tid == 0) init_rings(rg, nc >> 5);
+  __syncthreads();
+
+  if (tid >= nc) {
+    producer_loop<false>(rg, a.records + rec0, n, n_on, nchunks, (uint32_t)(ppad * 8), tid - nc);
+  } else {
+    const double alpha = live ? a.alpha[p] : 0.0;
+    const double beta = (LL && live) ? a.beta[p] : 0.0;
+    const double gamma = live ? a.gamma[p] : 0.0;
+    double *col = tables + (live ? p : (int64_t)blockIdx.x * nc);  // dead lanes shadow a live column, store nothing new
+    const int NV = a.num_states;
+    if (live) {
+      for (int s = 0; s < NV; ++s) {
+        double v0 = 0.0;  // rl.py:63-66
+        if (a.v_init) v0 = a.v_init_per_unit ? a.v_init[p * a.n_tiles + a.tile_of_state[s]] : a.v_init[a.tile_of_state[s]];
+        col[(int64_t)s * ppad] = v0;
+      }
+    }
+    char *vb = reinterpret_cast<char *>(col);
+    double ll = 0.0;
+    ExactAcc acc;
+    acc.acc_obs = 0.0;
+    acc.prod = 1.0;
+    acc.er.load(smem_u32(smem_raw + kBarBytes + kRawBytes + kDecBytes));
+    const int lane = tid & 31;
+    for (int c = 0; c < nchunks; ++c) {
+      const int dslot = c % kDecStages;
+      mbar_wait(&rg.full_dec[dslot], (uint32_t)((c / kDecStages) & 1));
+      const uint4 *recs = rg.dec + dslot * (kChunk * 4);
+      const int64_t first = (int64_t)c * kChunk;
+      const int cnt = (int)(n - first < kChunk ? n - first : kChunk);
+      if (live) {
+#pragma unroll 1
+        for (int i = 0; i < cnt; ++i) exact_step<ALG, LL>(recs + 4 * i, vb, alpha, beta, gamma, acc);
+      }
+      if (LL) {
+        ll = __dadd_rn(ll, __dsub_rn(acc.acc_obs, log(acc.prod)));
+        acc.acc_obs = 0.0;
+        acc.prod = 1.0;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&rg.empty_dec[dslot]);
+    }
+    if (LL && live && a.ll_out) a.ll_out[(int64_t)sess * a.P + p] = ll;
+    if (live && a.v_out) {
+      double *dst = a.v_out + ((int64_t)sess * a.P + p) * a.n_tiles;
+      for (int tile = 0; tile < a.n_tiles; ++tile) {
+        const int st = a.state_of_tile[tile];
+        double val;
+        if (st >= 0) val = col[(int64_t)st * ppad];
+        else if (a.v_init == nullptr) val = 0.0;
+        else val = a.v_init_per_unit ? a.v_init[p * a.n_tiles + tile] : a.v_init[tile];
+        dst[tile] = val;
+      }
+    }
+  }
+}
+
 // =================================== MEMO body =============================================================
 struct MemoState {
   double acc_obs;     // sum over observed steps of beta * V[obs]

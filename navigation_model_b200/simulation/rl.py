@@ -267,8 +267,6 @@ class ConditioningExperiment:
             return False
         if type(self._maze) is not Maze:
             return False
-        if self._maze.get_number_visitable_tiles() > _native.lib().nm_vtable_max_states():
-            return False  # the table does not fit the kernel's shared-memory layout: the host loop below still works
         if alg.device_kind != _native.ALG_TD0:
             if type(alg._mouse) is not Mouse or alg._maze is not self._maze:
                 return False

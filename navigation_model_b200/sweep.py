@@ -434,10 +434,11 @@ class ConditioningSweep:
         return ll_out
 
     def last_sweep_mode(self):
-        """Kernel the last :meth:`log_likelihood_device` on the current stream used: 0 = a value table per parameter
-        set, 1 = a table per warp shared by an aligned run of 32 consecutive parameter sets with equal
-        ``(alpha, gamma)`` (order the grid with beta fastest, ``parameter_grid(gamma, alpha, beta)``, and give the beta
-        axis a multiple of 32 points to get there).  Synchronises the stream."""
+        """Kernel the last :meth:`log_likelihood_device` on the current stream used: 1 = a table per warp shared by an
+        aligned run of 32 consecutive parameter sets with equal ``(alpha, gamma)`` (order the grid with beta fastest,
+        ``parameter_grid(gamma, alpha, beta)``, and give the beta axis a multiple of 32 points to get there); 2 = a
+        table per parameter set in device memory (arbitrary sets, any maze size); 0 = a table per parameter set in
+        shared memory (``NM_FIT_TABLES=shared``).  Synchronises the stream."""
         torch = self._ensure_device()
         mode = C.c_int(-1)
         with torch.cuda.device(self.torch_device):

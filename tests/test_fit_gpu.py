@@ -216,9 +216,13 @@ def test_group_kernels_match_exact_kernel_and_oracle(cuda, alg, n_beta, monkeypa
     assert sw.last_sweep_mode() == 1  # the shared-table kernel really ran
     monkeypatch.setenv("NM_FIT_GROUP", "0")
     ll_x, V_x = sw.log_likelihood(a, b, g, v_init=v0, return_v=True)
-    assert sw.last_sweep_mode() == 0
+    assert sw.last_sweep_mode() == 2  # a table per parameter set, in device memory
+    monkeypatch.setenv("NM_FIT_TABLES", "shared")
+    ll_s, V_s = sw.log_likelihood(a, b, g, v_init=v0, return_v=True)
+    assert sw.last_sweep_mode() == 0  # ... and in shared memory
     monkeypatch.delenv("NM_FIT_GROUP")
-    assert np.array_equal(ll, ll_x) and np.array_equal(V, V_x)
+    monkeypatch.delenv("NM_FIT_TABLES")
+    assert np.array_equal(ll, ll_x) and np.array_equal(V, V_x) and np.array_equal(ll, ll_s) and np.array_equal(V, V_s)
     for j, (traj, rew) in enumerate(sessions):
         tr = H.oracle_transitions(omz, traj, rew, H.a8())
         orders = O.replay_orders(len(tr["s"]), 1, 3)
@@ -230,9 +234,9 @@ def test_group_kernels_match_exact_kernel_and_oracle(cuda, alg, n_beta, monkeypa
     g2 = g.copy()
     g2[70] = 0.6123
     ll2 = sw.log_likelihood(a, b, g2)
-    assert sw.last_sweep_mode() == 0
-    monkeypatch.setenv("NM_FIT_GROUP", "0")
-    assert np.array_equal(ll2, sw.log_likelihood(a, b, g2))
+    assert sw.last_sweep_mode() == 2
+    monkeypatch.setenv("NM_FIT_TABLES", "shared")
+    assert np.array_equal(ll2, sw.log_likelihood(a, b, g2)) and sw.last_sweep_mode() == 0
 
 
 def test_td0_linearity_in_reward(cuda):
@@ -311,3 +315,72 @@ def test_memo_and_exact_bodies_agree_and_guard_falls_back(cuda, alg, monkeypatch
     ll0 = sw.log_likelihood(a, b, gm, v_init=v0)[0]
     _, want0 = CO.fit(ALGS[alg], tr, a, gm, 60, beta=b, v0=H.compact(omz, v0), want_v=False)
     np.testing.assert_allclose(ll0, want0, rtol=LL_RTOL, atol=0)
+
+
+@pytest.mark.parametrize("alg", ["td0", "positive", "negative"])
+def test_tables_in_device_memory_match_shared_memory_kernels(cuda, alg, monkeypatch):
+    """NM_FIT_TABLES=global: the same sweeps with T[state][parameter set] in device memory (the path mazes beyond 867
+    states take) -- bit-identical V-tables and log-likelihoods; per-set initial tables, replays, ragged sessions, a
+    parameter count that is not a multiple of the CTA size."""
+    omz = H.oracle_m9()
+    sessions = [O.synthetic_session(omz, sid, T) for sid, T in ((0, 600), (4, 97), (5, 1))]
+    if alg == "negative":
+        sessions = [(t, -r) for t, r in sessions]
+    rng = np.random.default_rng(31)
+    P = 301
+    a, b, g = H.grid_params(rng, P)
+    v0 = rng.random((P, 9, 9))
+    sw = _sweep(alg, sessions, replay_n_times=1, replay_seed=2)
+    monkeypatch.setenv("NM_FIT_TABLES", "shared")
+    want_ll, want_v = sw.log_likelihood(a, b, g, v_init=v0, return_v=True)
+    assert sw.last_sweep_mode() == 0
+    want_vt = sw.v_tables(a, g, v_init=v0[0])
+    monkeypatch.setenv("NM_FIT_TABLES", "global")
+    got_ll, got_v = sw.log_likelihood(a, b, g, v_init=v0, return_v=True)
+    assert sw.last_sweep_mode() == 2
+    got_vt = sw.v_tables(a, g, v_init=v0[0])
+    assert np.array_equal(got_ll, want_ll) and np.array_equal(got_v, want_v) and np.array_equal(got_vt, want_vt)
+
+
+def test_maze_beyond_the_shared_memory_layout(cuda):
+    """A 60 x 60 maze with a few void tiles (3 590 states > 867): sweeps and ConditioningExperiment.run keep their
+    tables in device memory; V-tables bit-exact and log-likelihoods 1e-9 against the oracle."""
+    from navigation_model_b200.simulation.maze import Maze
+    from navigation_model_b200.simulation.mouse import Mouse
+    from navigation_model_b200.simulation.rl import ConditioningExperiment, PositiveConditioning, ShuffledReplays
+    from navigation_model_b200.sweep import ConditioningSweep
+    rows = [["M"] * 60 for _ in range(60)]
+    for x, y in ((7, 7), (7, 8), (20, 33), (41, 5), (58, 58), (8, 6), (30, 30), (31, 30), (12, 50), (50, 12)):
+        rows[x][y] = "V"
+    layout = "\n".join("".join(r) for r in rows)
+    st = 0.02
+    maze, omz = Maze(layout, "", size_tile=st), O.OracleMaze(layout, st)
+    assert len(omz.vis_cells) == 3590
+    acts = H.a8(st)
+    traj, rew = O.synthetic_session(omz, 6, 500, start=(6, 6), goal=(7, 6), jitter=0.006)
+    tr = H.oracle_transitions(omz, traj, rew, acts)
+    rng = np.random.default_rng(6)
+    P = 70
+    a, b, g = H.grid_params(rng, P)
+    sw = ConditioningSweep(maze, "positive", possible_actions=acts, replay_n_times=1, replay_seed=4)
+    sw.add_session(traj, rew)
+    ll, V = sw.log_likelihood(a, b, g, return_v=True)
+    orders = O.replay_orders(len(tr["s"]), 1, 4)
+    Vw, llw = CO.fit(O.ALG_POSITIVE, tr, a, g, len(omz.vis_cells), beta=b, orders=orders)
+    np.testing.assert_allclose(ll[0], llw, rtol=LL_RTOL, atol=0)
+    for p in (0, 33, P - 1):
+        assert np.array_equal(V[0, p], O.dense_table(omz, Vw[p]))
+    # a grid with beta fastest takes the same device-memory path on this maze
+    a2, g2 = np.repeat(a[:2], 32), np.repeat(g[:2], 32)
+    b2 = np.tile(np.logspace(-1, 1.5, 32), 2)
+    ll2 = sw.log_likelihood(a2, b2, g2)
+    _, want2 = CO.fit(O.ALG_POSITIVE, tr, a2, g2, len(omz.vis_cells), beta=b2, orders=orders, want_v=False)
+    np.testing.assert_allclose(ll2[0], want2, rtol=LL_RTOL, atol=0)
+    # the reference-style single run
+    mouse = Mouse(traj[0], 0.0, acts)
+    exp = ConditioningExperiment(maze, PositiveConditioning(0.4, 0.8, mouse, maze), ShuffledReplays(0))
+    assert exp._device_eligible()
+    exp.run(list(traj), [0.0] * len(traj), list(rew))
+    want, _ = O.run_session(O.ALG_POSITIVE, tr, 0.4, 0.8, len(omz.vis_cells))
+    assert np.array_equal(exp.v_table, O.dense_table(omz, want))
+

@@ -31,8 +31,12 @@ def test_fit_sweep_configs1_grid(cuda, monkeypatch):
     assert sw.last_sweep_mode() == 1
     monkeypatch.setenv("NM_FIT_GROUP", "0")
     ll_sets = sw.log_likelihood(a, b, g)
-    assert sw.last_sweep_mode() == 0
-    assert np.array_equal(ll, ll_sets)
+    assert sw.last_sweep_mode() == 2  # a table per parameter set in device memory
+    monkeypatch.setenv("NM_FIT_TABLES", "shared")
+    ll_shared = sw.log_likelihood(a, b, g)
+    assert sw.last_sweep_mode() == 0  # ... in shared memory
+    monkeypatch.delenv("NM_FIT_TABLES")
+    assert np.array_equal(ll, ll_sets) and np.array_equal(ll, ll_shared)
     idx = np.random.default_rng(3).choice(a.size, 64, replace=False)
     tr = H.oracle_transitions(omz, traj, rew, H.a8())
     _, want = CO.fit(O.ALG_POSITIVE, tr, a[idx], g[idx], 60, beta=b[idx], want_v=False)

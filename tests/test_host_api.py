@@ -412,29 +412,20 @@ def test_multi_result_views_and_batched_leaves():
     assert len(mr) == 0
 
 
-def test_mazes_too_large_for_the_kernels_keep_the_host_loops():
-    """A 60 x 60 maze (3 600 states) fits neither the per-set value tables (867 states) nor the simulation kernel's
-    visit map: ConditioningExperiment.run and StandardExperiment.run then take the reference's per-step loops --
-    no error, no GPU needed -- and the value table is the oracle's."""
+def test_mazes_too_large_for_the_simulation_kernel_keep_the_host_loop():
+    """A 60 x 60 maze does not fit the simulation kernel's shared-memory visit map: StandardExperiment.run then takes
+    the reference's per-step loop -- no error, no GPU needed.  (Value-table sweeps have no such limit: beyond 867 states
+    their tables move to device memory, tests/test_fit_gpu.py.)"""
     from navigation_model_b200 import _native
     from navigation_model_b200.simulation.behavioural_components import AnxietyComponent
     from navigation_model_b200.simulation.experiment import StandardExperiment
     from navigation_model_b200.simulation.exploration_model import BehaviouralModel
     from navigation_model_b200.simulation.maze import Maze
     from navigation_model_b200.simulation.mouse import Mouse
-    from navigation_model_b200.simulation.rl import ConditioningExperiment, ShuffledReplays, TD0
     assert _native.lib().nm_vtable_max_states() == 867
     assert _native.lib().nm_simulate_fits(9, 9, 10000) == 1 and _native.lib().nm_simulate_fits(60, 60, 100) == 0
     layout = "\n".join(["M" * 60] * 60)
     maze = Maze(layout, "", size_tile=0.02)
-    omz = O.OracleMaze(layout, 0.02)
-    traj, rew = O.synthetic_session(omz, 4, 300, start=(5, 5), goal=(7, 6), jitter=0.005)
-    exp = ConditioningExperiment(maze, TD0(0.3, 0.9), ShuffledReplays(0))
-    assert not exp._device_eligible()
-    exp.run(list(traj), [0.0] * len(traj), list(rew))
-    tr = O.extract_transitions(omz, traj, rew, None)
-    want, _ = O.run_session(O.ALG_TD0, tr, 0.3, 0.9, len(omz.vis_cells))
-    assert np.array_equal(exp.v_table, O.dense_table(omz, want))
     acts = np.array([(0, 0), (1, 0), (0, 1), (-1, 0)]) * 0.02
     mouse = Mouse(maze.get_tile_centre(30, 30), 0.0, acts)
     model = BehaviouralModel([AnxietyComponent(W_anx=1.0, p1=0.5, p2=0.5, p3=0.5)], (30, 30), beta=1.0, seed=3)
@@ -442,4 +433,3 @@ def test_mazes_too_large_for_the_kernels_keep_the_host_loops():
     assert not sim._device_eligible(50)
     sim.run(50)
     assert len(mouse.history_position) == 51
-
