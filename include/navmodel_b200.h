@@ -390,10 +390,11 @@ int nm_qtable_sweep(const nm_maze *mz, const nm_streams *st, const int16_t *d_ne
                     const double *d_alpha, const double *d_beta, const double *d_gamma, int64_t P,
                     const double *d_q_init, double *d_ll_out, double *d_q_out, void *stream);
 
-/* Which kernel the last nm_qtable_sweep on `stream` (current device) used: 0 = one table per parameter set (eight
- * lanes each), 1 = one table per warp, shared by an aligned run of 32 consecutive parameter sets with equal
- * (alpha, gamma) -- checked on the device, bit-identical results; NM_Q_GROUP=0 forces 0.  Synchronises the stream:
- * diagnostics and tests only. */
+/* Which kernel the last nm_qtable_sweep on `stream` (current device) used: 1 = one table per warp in shared memory,
+ * shared by an aligned run of 32 consecutive parameter sets with equal (alpha, gamma) (checked on the device;
+ * NM_Q_GROUP=0 disables it); 2 = one table per parameter set in device memory (T[state * 8 + action][set], coalesced;
+ * arbitrary sets, any maze size -- the default for them); 0 = one table per parameter set in shared memory, eight lanes
+ * each (NM_Q_TABLES=shared).  Bit-identical results.  Synchronises the stream: diagnostics and tests only. */
 int nm_qtable_sweep_mode(void *stream, int *mode_out);
 
 /* ------------------------------------------------------------------------------------------------

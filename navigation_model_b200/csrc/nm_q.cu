@@ -404,6 +404,131 @@ __global__ void __launch_bounds__(960, 1) nm_qgroup_kernel(const QArgs a) {
   }
 }
 
+// =================================== one table per set, in device memory =====================================
+// Arbitrary parameter sets: tables T[state * 8 + action][parameter set] in device memory (rows padded to 32 sets, one
+// more row of -inf), one column per THREAD.  All threads of a warp walk the same stream, so the sixteen loads and the
+// store of a step hit whole rows at consecutive sets: coalesced 256-byte accesses (504 MB of tables for the
+// configs[1] grid: HBM-resident, 136 bytes per update).  Same producer warp, decoded records and step bodies as the
+// per-warp kernel (bit-identical results); 64 registers, up to 28 consumer warps per SM; one launch per session.
+// Replaces the octet kernel as the default for parameter arrays without uniform runs (NM_Q_TABLES=shared keeps it).
+__global__ void __launch_bounds__(960, 1) nm_qglobal_kernel(const QArgs a, double *__restrict__ tables, const int64_t ppad,
+                                                            const int sess) {
+  if (a.mode && *a.mode != 0) return;  // the per-warp kernel owns this sweep
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int S = a.S, A = a.A;
+  QRings rg;
+  rg.full_raw = reinterpret_cast<uint64_t *>(smem_raw);
+  rg.full_dec = rg.full_raw + kQRawStages;
+  rg.empty_dec = rg.full_dec + kQDecStages;
+  rg.raw = reinterpret_cast<uint4 *>(smem_raw + kQBarBytes);
+  rg.dec = reinterpret_cast<uint4 *>(smem_raw + kQBarBytes + kQRawBytes);
+  double *exptab = reinterpret_cast<double *>(smem_raw + kQBarBytes + kQRawBytes + kQDecBytes);
+  int16_t *nxt8 = reinterpret_cast<int16_t *>(smem_raw + kQFixedBytes);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int nc = blockDim.x - 32;
+  if (tid < 16) exptab[tid] = c_exp2tab[tid];
+  for (int i = tid; i < S * 8; i += blockDim.x) {
+    const int u = i >> 3, kk = i & 7;
+    nxt8[i] = kk < A ? a.next[u * A + kk] : (int16_t)-1;
+  }
+  const int64_t rec0 = a.offsets[sess];
+  const int64_t n = a.offsets[sess + 1] - rec0, n_on = a.online[sess];
+  const int nchunks = (int)((n + kQChunk - 1) / kQChunk);
+  if (tid == 0) {
+    for (int i = 0; i < kQRawStages; ++i) mbar_init(&rg.full_raw[i], 1);
+    for (int i = 0; i < kQDecStages; ++i) {
+      mbar_init(&rg.full_dec[i], 32);
+      mbar_init(&rg.empty_dec[i], nc >> 5);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int rows = S * 8;
+  if (tid >= nc) {
+    q_producer_loop(rg, a.records + rec0, n, n_on, nchunks, nxt8, (uint32_t)(ppad * 8), (uint32_t)((int64_t)rows * ppad * 8),
+                    lane);
+  } else {
+    const int64_t p = (int64_t)blockIdx.x * nc + tid;
+    const bool live = p < a.P;
+    const double alpha = live ? a.alpha[p] : 0.0, beta = live ? a.beta[p] : 0.0, gamma = live ? a.gamma[p] : 0.0;
+    double *col = tables + (live ? p : (int64_t)blockIdx.x * nc);
+    if (live) {
+      for (int e = 0; e < rows; ++e) {
+        const int u = e >> 3, kk = e & 7;
+        col[(int64_t)e * ppad] = (a.q_init && kk < A) ? a.q_init[(int64_t)a.tile_of_state[u] * A + kk] : 0.0;
+      }
+      col[(int64_t)rows * ppad] = -INFINITY;
+    }
+    char *qb = reinterpret_cast<char *>(col);
+    double ll = 0.0;
+    QAcc acc;
+    acc.acc_obs = 0.0;
+    acc.prod = 1.0;
+    acc.er.load(smem_u32(exptab));
+    for (int c = 0; c < nchunks; ++c) {
+      const int dslot = c % kQDecStages;
+      mbar_wait(&rg.full_dec[dslot], (uint32_t)((c / kQDecStages) & 1));
+      const uint4 *recs = rg.dec + dslot * (kQChunk * kQDecWords);
+      const int64_t first = (int64_t)c * kQChunk;
+      const int cnt = (int)(n - first < kQChunk ? n - first : kQChunk);
+      if (live) {
+#pragma unroll 1
+        for (int i = 0; i < cnt; ++i) qgroup_step(recs + kQDecWords * i, qb, alpha, beta, gamma, acc);
+      }
+      ll = __dadd_rn(ll, __dsub_rn(acc.acc_obs, log(acc.prod)));
+      acc.acc_obs = 0.0;
+      acc.prod = 1.0;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&rg.empty_dec[dslot]);
+    }
+    if (live && a.ll_out) a.ll_out[(int64_t)sess * a.P + p] = ll;
+    if (live && a.q_out) {
+      double *dst = a.q_out + ((int64_t)sess * a.P + p) * a.n_tiles * A;
+      for (int tile = 0; tile < a.n_tiles; ++tile) {
+        const int st = a.state_of_tile[tile];
+        for (int kk = 0; kk < A; ++kk)
+          dst[(int64_t)tile * A + kk] = st >= 0 ? col[(int64_t)(st * 8 + kk) * ppad]
+                                                : (a.q_init ? a.q_init[(int64_t)tile * A + kk] : 0.0);
+      }
+    }
+  }
+}
+
+// grow-only scratch per device for the tables in device memory
+int q_global_tables(int device, size_t bytes, double **out) {
+  static std::mutex mu;
+  static std::map<int, std::pair<double *, size_t>> scratch;
+  std::lock_guard<std::mutex> lock(mu);
+  auto &slot = scratch[device];
+  if (slot.second < bytes) {
+    if (slot.first) {
+      cudaDeviceSynchronize();  // earlier sweeps may still use the old block
+      cudaFree(slot.first);
+      slot.first = nullptr;
+      slot.second = 0;
+    }
+    double *buf = nullptr;
+    const cudaError_t e = cudaMalloc((void **)&buf, bytes);
+    if (e != cudaSuccess) return nm_fail(NM_ERR_NOMEM, "Q tables in device memory: cudaMalloc(%zu): %s", bytes,
+                                         cudaGetErrorString(e));
+    slot.first = buf;
+    slot.second = bytes;
+  }
+  *out = slot.first;
+  return NM_OK;
+}
+
+// 1 when "mode 0" of the last sweep on (device, stream) ran with tables in device memory: nm_qtable_sweep_mode
+std::map<std::pair<int, void *>, int> &q_last_global() {
+  static std::map<std::pair<int, void *>, int> m;
+  return m;
+}
+std::mutex &q_last_mutex() {
+  static std::mutex mu;
+  return mu;
+}
+
 }  // namespace
 
 extern "C" int nm_qtable_sweep(const nm_maze *mz, const nm_streams *st, const int16_t *d_next, int n_actions,
@@ -440,10 +565,15 @@ extern "C" int nm_qtable_sweep(const nm_maze *mz, const nm_streams *st, const in
       warps = w;
     }
   }
-  NM_CHECK_ARG(warps >= 1, "nm_qtable_sweep: the Q-tables of four parameter sets on a maze with %d states do not fit "
-               "in shared memory", S);
-  const size_t smem = fixed + per_warp * warps;
-  cudaError_t e = cudaFuncSetAttribute(nm_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // per-set tables: in device memory by default (any maze size, 3x faster), in shared memory (the octet kernel) with
+  // NM_Q_TABLES=shared
+  const char *env_tab = getenv("NM_Q_TABLES");
+  const bool octet = env_tab && env_tab[0] == 's';
+  NM_CHECK_ARG(!octet || warps >= 1, "nm_qtable_sweep: the Q-tables of four parameter sets on a maze with %d states do "
+               "not fit in shared memory", S);
+  const size_t smem = fixed + per_warp * (warps > 0 ? warps : 1);
+  cudaError_t e = cudaSuccess;
+  if (octet) e = cudaFuncSetAttribute(nm_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   QArgs a;
   a.records = st->d_records;
@@ -506,15 +636,60 @@ extern "C" int nm_qtable_sweep(const nm_maze *mz, const nm_streams *st, const in
     e = cudaGetLastError();
     if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_qgroup_kernel launch: %s", cudaGetErrorString(e));
   }
-  const int64_t per_cta = (int64_t)warps * 4;
-  const int64_t blocks = (P + per_cta - 1) / per_cta;
-  NM_CHECK_ARG(blocks <= 2147483647LL, "nm_qtable_sweep: too many parameter sets for one launch");
-  nm_q_kernel<<<dim3((unsigned)blocks, (unsigned)st->S, 1), warps * 32, smem, cs>>>(a);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_q_kernel launch: %s", cudaGetErrorString(e));
+  {
+    std::lock_guard<std::mutex> lock(q_last_mutex());
+    q_last_global()[std::make_pair(mz->device, stream)] = octet ? 0 : 1;
+  }
+  if (octet) {
+    const int64_t per_cta = (int64_t)warps * 4;
+    const int64_t blocks = (P + per_cta - 1) / per_cta;
+    NM_CHECK_ARG(blocks <= 2147483647LL, "nm_qtable_sweep: too many parameter sets for one launch");
+    nm_q_kernel<<<dim3((unsigned)blocks, (unsigned)st->S, 1), warps * 32, smem, cs>>>(a);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_q_kernel launch: %s", cudaGetErrorString(e));
+    return NM_OK;
+  }
+  // tables in device memory: slices of at most one full wave (and of 32-bit row offsets), one launch per session
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, mz->device);
+  const int64_t rows1 = (int64_t)S * 8 + 1;
+  int64_t max_sets = (((int64_t)0xffffffffLL / 8) / rows1) & ~(int64_t)31;
+  NM_CHECK_ARG(max_sets >= 32, "nm_qtable_sweep: a maze with %d states is too large", S);
+  if (max_sets > (int64_t)sms * 896) max_sets = (int64_t)sms * 896;
+  e = cudaFuncSetAttribute(nm_qglobal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_fixed);
+  if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "cudaFuncSetAttribute(nm_qglobal_kernel): %s", cudaGetErrorString(e));
+  for (int64_t lo = 0; lo < P; lo += max_sets) {
+    QArgs b = a;
+    b.P = P - lo < max_sets ? P - lo : max_sets;
+    b.alpha = d_alpha + lo;
+    b.beta = d_beta + lo;
+    b.gamma = d_gamma + lo;
+    const int64_t ppad = (b.P + 31) & ~(int64_t)31;
+    int nc = (int)(((b.P + sms - 1) / sms + 31) / 32) * 32;
+    nc = nc < 32 ? 32 : nc > 896 ? 896 : nc;
+    double *tables = nullptr;
+    const int rc2 = q_global_tables(mz->device, sizeof(double) * (size_t)rows1 * (size_t)ppad, &tables);
+    if (rc2 != NM_OK) return rc2;
+    for (int sess = 0; sess < st->S; ++sess) {
+      QArgs c = b;  // outputs of the whole call are [S, P, ...]: shift to this slice's first parameter set
+      if (d_ll_out) c.ll_out = d_ll_out + (int64_t)sess * (P - b.P) + lo;
+      if (d_q_out) c.q_out = d_q_out + ((int64_t)sess * (P - b.P) + lo) * a.n_tiles * n_actions;
+      nm_qglobal_kernel<<<(unsigned)((b.P + nc - 1) / nc), nc + 32, g_fixed, cs>>>(c, tables, ppad, sess);
+      e = cudaGetLastError();
+      if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_qglobal_kernel launch: %s", cudaGetErrorString(e));
+    }
+  }
   return NM_OK;
 }
 
 extern "C" int nm_qtable_sweep_mode(void *stream, int *mode_out) {
-  return runs_mode_read(stream, mode_out, "nm_qtable_sweep_mode");
+  const int rc = runs_mode_read(stream, mode_out, "nm_qtable_sweep_mode");
+  if (rc == NM_OK && *mode_out == 0) {  // per-set tables: shared memory (0) or device memory (2)?
+    int device = 0;
+    cudaGetDevice(&device);
+    std::lock_guard<std::mutex> lock(q_last_mutex());
+    const auto it = q_last_global().find(std::make_pair(device, stream));
+    if (it != q_last_global().end() && it->second) *mode_out = 2;
+  }
+  return rc;
 }

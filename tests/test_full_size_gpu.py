@@ -64,8 +64,12 @@ def test_qtable_sweep_configs1_grid(cuda, monkeypatch):
     assert ql.last_sweep_mode() == 1
     monkeypatch.setenv("NM_Q_GROUP", "0")
     ll_sets = ql.log_likelihood(a, b, g)
-    assert ql.last_sweep_mode() == 0
-    assert np.array_equal(ll, ll_sets)
+    assert ql.last_sweep_mode() == 2  # a table per parameter set in device memory
+    monkeypatch.setenv("NM_Q_TABLES", "shared")
+    ll_octet = ql.log_likelihood(a, b, g)
+    assert ql.last_sweep_mode() == 0  # ... in shared memory (eight lanes per set)
+    monkeypatch.delenv("NM_Q_TABLES")
+    assert np.array_equal(ll, ll_sets) and np.array_equal(ll, ll_octet)
     tr = O.extract_transitions(omz, traj, rew, None)
     nxt = O.transition_table(omz, moves)
     for p in np.random.default_rng(4).choice(a.size, 3, replace=False):
@@ -114,7 +118,7 @@ def test_regrouping_of_grids_given_in_another_order(cuda, agent):
     out = sw.log_likelihood(a, b, g, return_tables=True)
     assert sw.last_sweep_mode() == 1
     ref = sw.log_likelihood(a, b, g, return_tables=True, regroup=False)
-    assert sw.last_sweep_mode() == 0
+    assert sw.last_sweep_mode() == (2 if agent == "qtable" else 0)  # tables per parameter set
     for x, y in zip(out, ref):
         assert np.array_equal(x, y)
     # nothing to do for a grid that is already laid out in runs, nothing possible for 20 beta points

@@ -20,8 +20,9 @@ def _dense_q(omz, Q, fill=None):
     return out
 
 
+@pytest.mark.parametrize("tables", ["global", "shared"])
 @pytest.mark.parametrize("acts,n_times", [(ACTS8, 0), (ACTS8, 2), (ACTS5, 0), (ACTS5, 1)])
-def test_qtable_vs_oracle_m9(cuda, acts, n_times):
+def test_qtable_vs_oracle_m9(cuda, acts, n_times, tables, monkeypatch):
     from navigation_model_b200.sweep import QLearningSweep
     omz, maze = H.oracle_m9(), H.product_m9()
     nxt = O.transition_table(omz, acts)
@@ -33,7 +34,9 @@ def test_qtable_vs_oracle_m9(cuda, acts, n_times):
     assert np.array_equal(ql.next_table, nxt)
     for traj, rew in sessions:
         ql.add_session(traj, rew)
+    monkeypatch.setenv("NM_Q_TABLES", tables)  # per-set tables in device memory (default) / in shared memory
     ll, Q = ql.log_likelihood(a, b, g, return_tables=True)
+    assert ql.last_sweep_mode() == (2 if tables == "global" else 0)
     assert ll.shape == (3, P) and Q.shape == (3, P, omz.X, omz.Y, len(acts))
     for j, (traj, rew) in enumerate(sessions):
         tr = O.extract_transitions(omz, traj, rew, None)
@@ -123,9 +126,14 @@ def test_qtable_group_kernel_matches_octet_kernel_and_oracle(cuda, maze_name, ac
     assert ql.last_sweep_mode() == 1  # the warp-shared-table kernel really ran
     monkeypatch.setenv("NM_Q_GROUP", "0")
     ll_x, Q_x = ql.log_likelihood(a, b, g, q_init=q0, return_tables=True)
-    assert ql.last_sweep_mode() == 0
-    monkeypatch.delenv("NM_Q_GROUP")
+    assert ql.last_sweep_mode() == 2  # a table per parameter set, in device memory
     assert np.array_equal(ll, ll_x) and np.array_equal(Q, Q_x)
+    monkeypatch.setenv("NM_Q_TABLES", "shared")
+    ll_o, Q_o = ql.log_likelihood(a, b, g, q_init=q0, return_tables=True)
+    assert ql.last_sweep_mode() == 0  # ... and in shared memory (the octet kernel)
+    assert np.array_equal(ll, ll_o) and np.array_equal(Q, Q_o)
+    monkeypatch.delenv("NM_Q_GROUP")
+    monkeypatch.delenv("NM_Q_TABLES")
     q0c = np.array([q0[x, y] for x, y in omz.vis_cells])
     for j, (traj, rew) in enumerate(sessions):
         tr = O.extract_transitions(omz, traj, rew, None)
@@ -134,11 +142,11 @@ def test_qtable_group_kernel_matches_octet_kernel_and_oracle(cuda, maze_name, ac
             Qw, llw = O.run_q_learning(tr, nxt, a[p], b[p], g[p], q0=q0c, orders=orders)
             assert np.array_equal(Q[j, p], _dense_q(omz, Qw, fill=q0)), (j, p)
             assert abs(ll[j, p] - llw) <= 1e-9 * abs(llw) + 1e-300, (j, p)
-    # a run that is not uniform keeps the octet kernel
+    # a run that is not uniform: a table per parameter set
     g2 = g.copy()
     g2[40] = 0.777
-    ql.log_likelihood(a, b, g2)
-    assert ql.last_sweep_mode() == 0
+    ql.log_likelihood(a, b, g2, regroup=False)
+    assert ql.last_sweep_mode() == 2
 
 
 def test_loglikelihood_fitness_drives_the_tile_action_agents(cuda):

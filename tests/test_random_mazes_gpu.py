@@ -79,10 +79,17 @@ def test_tile_action_agents_on_random_mazes(cuda, seed, monkeypatch):
         assert sw.last_sweep_mode() == 1
         monkeypatch.setenv(env, "0")
         ref = sw.log_likelihood(a, b, g, return_tables=True, regroup=False)
-        assert sw.last_sweep_mode() == 0
-        monkeypatch.delenv(env)
+        assert sw.last_sweep_mode() == (2 if sw is ql else 0)  # tables per parameter set (Q: in device memory)
         for x, y in zip(out, ref):
             assert np.array_equal(x, y)
+        if sw is ql:  # ... and the shared-memory octet kernel
+            monkeypatch.setenv("NM_Q_TABLES", "shared")
+            ref = sw.log_likelihood(a, b, g, return_tables=True, regroup=False)
+            assert sw.last_sweep_mode() == 0
+            monkeypatch.delenv("NM_Q_TABLES")
+            for x, y in zip(out, ref):
+                assert np.array_equal(x, y)
+        monkeypatch.delenv(env)
     ll_q, Q = ql.log_likelihood(a, b, g, return_tables=True)
     ll_m, V, R = mb.log_likelihood(a, b, g, return_tables=True)
     for j, (t, r) in enumerate(sessions):
