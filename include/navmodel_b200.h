@@ -226,6 +226,11 @@ int nm_vtable_sweep(int alg, const nm_maze *mz, const nm_streams *st, const doub
  * with NM_FIT_TABLES=global): same results, no size limit. */
 int nm_vtable_max_states(void);
 
+/* The sweeps that keep per-set tables in device memory (nm_loglik_sweep / nm_vtable_sweep mode 2, nm_qtable_sweep mode
+ * 2) hold ONE grow-only scratch block per device (states x parameter sets x 8 bytes of the largest sweep so far) for
+ * the life of the process.  This call waits for the devices and gives the blocks back; later sweeps allocate again. */
+int nm_scratch_release(void);
+
 /* Same recurrence + log-likelihood of the observed choices under the softmax policy
  * p_k = softmax_k(beta * V[cand_k]) (exploration_model.py:84-93), evaluated BEFORE the update of the
  * step, accumulated in FP64 in step order over the online records whose obs != NM_OBS_NONE.

@@ -63,6 +63,7 @@ SIGNATURES = {
     "nm_vtable_sweep": (C.c_int, [C.c_int, _p, _p, _p, _p, _i64, _p, C.c_int, _p, _p]),
     "nm_loglik_sweep": (C.c_int, [C.c_int, _p, _p, _p, _p, _p, _i64, _p, C.c_int, _p, _p, _p]),
     "nm_vtable_max_states": (C.c_int, []),
+    "nm_scratch_release": (C.c_int, []),
     "nm_loglik_sweep_mode": (C.c_int, [_p, C.POINTER(C.c_int)]),
     "nm_argmin_nll": (C.c_int, [_p, C.c_int, _i64, _p, _p, _p]),
     "nm_fp64_peak_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, _p, C.POINTER(_i64), _p]),

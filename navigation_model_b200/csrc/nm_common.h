@@ -63,4 +63,7 @@ struct nm_streams {
   void *d_block = nullptr;
 };
 
+// frees the grow-only device scratch of the Q-table sweep (nm_q.cu); called by nm_scratch_release (nm_fit.cu)
+void nm_q_scratch_release();
+
 #endif  // NM_COMMON_H

@@ -181,11 +181,17 @@ int launch_group(const FitArgs &a, int S, int device, cudaStream_t cs) {
 
 // ---- tables in device memory (any maze size) -----------------------------------------------------------
 // grow-only scratch per device: states x parameter sets (padded to 32) doubles, reused by every later sweep
-int global_tables(int device, size_t bytes, double **out) {
+std::mutex &global_tables_mutex() {
   static std::mutex mu;
+  return mu;
+}
+std::map<int, std::pair<double *, size_t>> &global_tables_map() {
   static std::map<int, std::pair<double *, size_t>> scratch;
-  std::lock_guard<std::mutex> lock(mu);
-  auto &slot = scratch[device];
+  return scratch;
+}
+int global_tables(int device, size_t bytes, double **out) {
+  std::lock_guard<std::mutex> lock(global_tables_mutex());
+  auto &slot = global_tables_map()[device];
   if (slot.second < bytes) {
     if (slot.first) {
       cudaDeviceSynchronize();  // earlier sweeps may still use the old block
@@ -476,6 +482,25 @@ extern "C" int nm_argmin_nll(const double *d_ll, int S, int64_t P, double *d_nll
   nm_nll_final_kernel<<<1, 256, 0, cs>>>(partial, blocks, (Best *)d_best_out);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_argmin_nll launch: %s", cudaGetErrorString(e));
+  return NM_OK;
+}
+
+extern "C" int nm_scratch_release(void) {
+  // the tables-in-device-memory kernels keep one grow-only block per device (value-table and Q-table sweeps)
+  {
+    std::lock_guard<std::mutex> lock(global_tables_mutex());
+    int current = 0;
+    cudaGetDevice(&current);
+    for (auto &kv : global_tables_map()) {
+      if (!kv.second.first) continue;
+      cudaSetDevice(kv.first);
+      cudaDeviceSynchronize();
+      cudaFree(kv.second.first);
+      kv.second = std::make_pair((double *)nullptr, (size_t)0);
+    }
+    cudaSetDevice(current);
+  }
+  nm_q_scratch_release();
   return NM_OK;
 }
 

@@ -496,11 +496,17 @@ __global__ void __launch_bounds__(960, 1) nm_qglobal_kernel(const QArgs a, doubl
 }
 
 // grow-only scratch per device for the tables in device memory
-int q_global_tables(int device, size_t bytes, double **out) {
+std::mutex &q_tables_mutex() {
   static std::mutex mu;
+  return mu;
+}
+std::map<int, std::pair<double *, size_t>> &q_tables_map() {
   static std::map<int, std::pair<double *, size_t>> scratch;
-  std::lock_guard<std::mutex> lock(mu);
-  auto &slot = scratch[device];
+  return scratch;
+}
+int q_global_tables(int device, size_t bytes, double **out) {
+  std::lock_guard<std::mutex> lock(q_tables_mutex());
+  auto &slot = q_tables_map()[device];
   if (slot.second < bytes) {
     if (slot.first) {
       cudaDeviceSynchronize();  // earlier sweeps may still use the old block
@@ -530,6 +536,20 @@ std::mutex &q_last_mutex() {
 }
 
 }  // namespace
+
+void nm_q_scratch_release() {
+  std::lock_guard<std::mutex> lock(q_tables_mutex());
+  int current = 0;
+  cudaGetDevice(&current);
+  for (auto &kv : q_tables_map()) {
+    if (!kv.second.first) continue;
+    cudaSetDevice(kv.first);
+    cudaDeviceSynchronize();
+    cudaFree(kv.second.first);
+    kv.second = std::make_pair((double *)nullptr, (size_t)0);
+  }
+  cudaSetDevice(current);
+}
 
 extern "C" int nm_qtable_sweep(const nm_maze *mz, const nm_streams *st, const int16_t *d_next, int n_actions,
                                const double *d_alpha, const double *d_beta, const double *d_gamma, int64_t P,

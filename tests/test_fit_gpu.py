@@ -384,3 +384,17 @@ def test_maze_beyond_the_shared_memory_layout(cuda):
     want, _ = O.run_session(O.ALG_POSITIVE, tr, 0.4, 0.8, len(omz.vis_cells))
     assert np.array_equal(exp.v_table, O.dense_table(omz, want))
 
+
+def test_scratch_release_between_sweeps(cuda):
+    """nm_scratch_release gives the device-memory tables back; the next sweep allocates again and agrees."""
+    from navigation_model_b200 import _native
+    omz = H.oracle_m9()
+    traj, rew = O.synthetic_session(omz, 2, 300)
+    rng = np.random.default_rng(12)
+    a, b, g = H.grid_params(rng, 100)
+    sw = _sweep("positive", [(traj, rew)])
+    first = sw.log_likelihood(a, b, g)
+    assert sw.last_sweep_mode() == 2
+    assert _native.lib().nm_scratch_release() == 0
+    assert np.array_equal(first, sw.log_likelihood(a, b, g))
+
