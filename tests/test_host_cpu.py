@@ -178,3 +178,25 @@ def test_bench_product_arm_touches_the_oracle_only_in_its_cpu_legs():
     top = [n for n in tree.body if isinstance(n, (ast.Import, ast.ImportFrom))]
     assert not any("oracle" in ast.dump(n) for n in top)
 
+
+def test_regroup_order_of_tile_action_sweeps():
+    """The host-side re-ordering that lets grids given in any axis order share tables per run of 32 sets."""
+    from navigation_model_b200.sweep import _TileActionSweep, parameter_grid
+    a, b, g = parameter_grid(np.linspace(0.1, 1, 7), np.logspace(-1, 1, 64), np.linspace(0.5, 0.9, 3))  # gamma fastest
+    order = _TileActionSweep.regroup_order(a, g)
+    assert order is not None and sorted(order.tolist()) == list(range(a.size))
+    A, G, B = a[order].reshape(-1, 32), g[order].reshape(-1, 32), b[order].reshape(-1, 64)
+    assert (A == A[:, :1]).all() and (G == G[:, :1]).all()
+    assert (np.diff(B, axis=1) > 0).all()  # stable: the beta values of a pair keep their order
+    g2, a2, _ = parameter_grid(np.linspace(0.5, 0.9, 3), np.linspace(0.1, 1, 7), np.logspace(-1, 1, 64))
+    assert _TileActionSweep.regroup_order(a2, g2) is None  # already laid out in runs
+    a3, _, g3 = parameter_grid(np.linspace(0.1, 1, 7), np.logspace(-1, 1, 20), np.linspace(0.5, 0.9, 3))
+    assert _TileActionSweep.regroup_order(a3, g3) is None  # 20 beta points: no order gives uniform runs of 32
+    rng = np.random.default_rng(0)
+    assert _TileActionSweep.regroup_order(rng.random(500), rng.random(500)) is None
+    # a last, incomplete run is allowed when its pair sorts last
+    a4 = np.concatenate([np.full(64, 0.2), np.full(40, 0.9)])[::-1].copy()
+    g4 = np.full(104, 0.7)
+    order = _TileActionSweep.regroup_order(a4, g4)
+    assert order is not None and (a4[order][:64] == 0.2).all() and (a4[order][64:] == 0.9).all()
+
