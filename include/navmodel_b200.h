@@ -227,8 +227,8 @@ int nm_vtable_sweep(int alg, const nm_maze *mz, const nm_streams *st, const doub
 int nm_vtable_max_states(void);
 
 /* The sweeps that keep per-set tables in device memory (nm_loglik_sweep / nm_vtable_sweep mode 2, nm_qtable_sweep mode
- * 2) hold ONE grow-only scratch block per device (states x parameter sets x 8 bytes of the largest sweep so far) for
- * the life of the process.  This call waits for the devices and gives the blocks back; later sweeps allocate again. */
+ * 2) hold ONE grow-only scratch block per (device, stream) (states x parameter sets x 8 bytes of the largest sweep so
+ * far on that stream) for the life of the process.  This call waits for the devices and gives the blocks back; later sweeps allocate again. */
 int nm_scratch_release(void);
 
 /* Same recurrence + log-likelihood of the observed choices under the softmax policy

@@ -180,18 +180,19 @@ int launch_group(const FitArgs &a, int S, int device, cudaStream_t cs) {
 }
 
 // ---- tables in device memory (any maze size) -----------------------------------------------------------
-// grow-only scratch per device: states x parameter sets (padded to 32) doubles, reused by every later sweep
+// grow-only scratch per (device, stream): states x parameter sets (padded to 32) doubles, reused by every later sweep
+// on that stream (sweeps on different streams may run concurrently: each needs its own tables)
 std::mutex &global_tables_mutex() {
   static std::mutex mu;
   return mu;
 }
-std::map<int, std::pair<double *, size_t>> &global_tables_map() {
-  static std::map<int, std::pair<double *, size_t>> scratch;
+std::map<std::pair<int, void *>, std::pair<double *, size_t>> &global_tables_map() {
+  static std::map<std::pair<int, void *>, std::pair<double *, size_t>> scratch;
   return scratch;
 }
-int global_tables(int device, size_t bytes, double **out) {
+int global_tables(int device, void *stream, size_t bytes, double **out) {
   std::lock_guard<std::mutex> lock(global_tables_mutex());
-  auto &slot = global_tables_map()[device];
+  auto &slot = global_tables_map()[std::make_pair(device, stream)];
   if (slot.second < bytes) {
     if (slot.first) {
       cudaDeviceSynchronize();  // earlier sweeps may still use the old block
@@ -262,7 +263,7 @@ int sweep_global(FitArgs a, int S, int device, cudaStream_t cs) {
     }
     const int64_t ppad = (b.P + 31) & ~(int64_t)31;
     double *tables = nullptr;
-    const int rc = global_tables(device, sizeof(double) * (size_t)a.num_states * (size_t)ppad, &tables);
+    const int rc = global_tables(device, (void *)cs, sizeof(double) * (size_t)a.num_states * (size_t)ppad, &tables);
     if (rc != NM_OK) return rc;
     for (int sess = 0; sess < S; ++sess) {  // the scratch holds one table per parameter set: sessions in turn
       FitArgs c = b;
@@ -493,7 +494,7 @@ extern "C" int nm_scratch_release(void) {
     cudaGetDevice(&current);
     for (auto &kv : global_tables_map()) {
       if (!kv.second.first) continue;
-      cudaSetDevice(kv.first);
+      cudaSetDevice(kv.first.first);
       cudaDeviceSynchronize();
       cudaFree(kv.second.first);
       kv.second = std::make_pair((double *)nullptr, (size_t)0);

@@ -495,18 +495,18 @@ __global__ void __launch_bounds__(960, 1) nm_qglobal_kernel(const QArgs a, doubl
   }
 }
 
-// grow-only scratch per device for the tables in device memory
+// grow-only scratch per (device, stream) for the tables in device memory
 std::mutex &q_tables_mutex() {
   static std::mutex mu;
   return mu;
 }
-std::map<int, std::pair<double *, size_t>> &q_tables_map() {
-  static std::map<int, std::pair<double *, size_t>> scratch;
+std::map<std::pair<int, void *>, std::pair<double *, size_t>> &q_tables_map() {
+  static std::map<std::pair<int, void *>, std::pair<double *, size_t>> scratch;
   return scratch;
 }
-int q_global_tables(int device, size_t bytes, double **out) {
+int q_global_tables(int device, void *stream, size_t bytes, double **out) {
   std::lock_guard<std::mutex> lock(q_tables_mutex());
-  auto &slot = q_tables_map()[device];
+  auto &slot = q_tables_map()[std::make_pair(device, stream)];
   if (slot.second < bytes) {
     if (slot.first) {
       cudaDeviceSynchronize();  // earlier sweeps may still use the old block
@@ -543,7 +543,7 @@ void nm_q_scratch_release() {
   cudaGetDevice(&current);
   for (auto &kv : q_tables_map()) {
     if (!kv.second.first) continue;
-    cudaSetDevice(kv.first);
+    cudaSetDevice(kv.first.first);
     cudaDeviceSynchronize();
     cudaFree(kv.second.first);
     kv.second = std::make_pair((double *)nullptr, (size_t)0);
@@ -688,7 +688,7 @@ extern "C" int nm_qtable_sweep(const nm_maze *mz, const nm_streams *st, const in
     int nc = (int)(((b.P + sms - 1) / sms + 31) / 32) * 32;
     nc = nc < 32 ? 32 : nc > 896 ? 896 : nc;
     double *tables = nullptr;
-    const int rc2 = q_global_tables(mz->device, sizeof(double) * (size_t)rows1 * (size_t)ppad, &tables);
+    const int rc2 = q_global_tables(mz->device, stream, sizeof(double) * (size_t)rows1 * (size_t)ppad, &tables);
     if (rc2 != NM_OK) return rc2;
     for (int sess = 0; sess < st->S; ++sess) {
       QArgs c = b;  // outputs of the whole call are [S, P, ...]: shift to this slice's first parameter set
