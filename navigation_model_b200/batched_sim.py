@@ -229,6 +229,23 @@ class BatchedExperiment:
                                    f"[{lo}; {hi}]")
         return cols
 
+    def _fetch(self, torch, tensors):
+        """Device tensors -> fresh numpy arrays through a pinned staging buffer that is kept across runs (pageable
+        ``.cpu()`` copies run at a few GB/s and synchronise one by one).  ``{id(tensor): array}``."""
+        sizes = [(t.numel() * t.element_size() + 15) & ~15 for t in tensors]
+        total = sum(sizes)
+        pin = getattr(self, "_pinned", None)
+        if pin is None or pin.numel() < total:
+            pin = self._pinned = torch.empty(max(total, 1), dtype=torch.uint8, pin_memory=True)
+        views, off = [], 0
+        for t, nbytes in zip(tensors, sizes):
+            v = pin[off:off + t.numel() * t.element_size()].view(t.dtype).view(t.shape)
+            v.copy_(t, non_blocking=True)
+            views.append(v)
+            off += nbytes
+        torch.cuda.current_stream().synchronize()
+        return {id(t): np.array(v.numpy()) for t, v in zip(tensors, views)}  # copies: the buffer is reused
+
     def run(self, params, n_steps, init_pos, init_ori=0.0, init_disc=None, seeds=None, draws=None,
             visit_percentage=80, history=False, occupancy=False, occupancy_total=False, generators=None,
             device_seed=None, n_mice=None, shock_zone=None, corridors=None, static_intervals=False, subareas=False,
@@ -426,10 +443,18 @@ class BatchedExperiment:
             torch.cuda.current_stream().synchronize()
             self.last_kernel_ms = e0.elapsed_time(e1)  # device time of nm_sim_kernel (CUDA events)
 
-        res = SimResult(final_pose=o_pose.cpu().numpy(), status=o_st.cpu().numpy(), it_visit=o_it.cpu().numpy(),
-                        count_moving=o_mov.cpu().numpy(), tile_counts=o_tc.cpu().numpy(),
-                        pcg_state=o_pcg.cpu().numpy().view(np.uint64), model_state=o_ms.cpu().numpy(),
-                        pcg_buffered=o_p32.cpu().numpy().view(np.uint32))
+        # per-mouse results: ONE pinned staging buffer (kept across runs), asynchronous copies, one synchronisation
+        small = [t for t in (o_pose, o_st, o_it, o_mov, o_tc, o_pcg, o_ms, o_p32, o_zone, o_static, o_sub, o_oh, o_tot)
+                 if t is not None]
+        host = self._fetch(torch, small)
+
+        def on_host(t):
+            return host[id(t)] if id(t) in host else t.cpu().numpy()
+
+        res = SimResult(final_pose=on_host(o_pose), status=on_host(o_st), it_visit=on_host(o_it),
+                        count_moving=on_host(o_mov), tile_counts=on_host(o_tc),
+                        pcg_state=on_host(o_pcg).view(np.uint64), model_state=on_host(o_ms),
+                        pcg_buffered=on_host(o_p32).view(np.uint32))
         if history:
             res.history_position = np.ascontiguousarray(o_hp.cpu().numpy().transpose(1, 0, 2))
             res.history_orientation = np.ascontiguousarray(o_ho.cpu().numpy().T)
@@ -437,20 +462,20 @@ class BatchedExperiment:
         if occupancy:
             res.occupancy = o_occ.cpu().numpy().reshape(N, X, Y)
         if occupancy_total:
-            res.occupancy_total = o_tot.cpu().numpy().reshape(X, Y)
+            res.occupancy_total = on_host(o_tot).reshape(X, Y)
         res.n_positions = T + 1
         if o_zone is not None:
-            z = o_zone.cpu().numpy()
+            z = on_host(o_zone)
             if shock_zone is not None:
                 res.zone_latency, res.zone_occupancy, res.zone_entries = z[:, 0].copy(), z[:, 1].copy(), z[:, 2].copy()
             if corridors is not None:
                 res.corridor_switches = z[:, 3].copy()
         if o_static is not None:
-            res.static_intervals = o_static.cpu().numpy()
+            res.static_intervals = on_host(o_static)
         if o_sub is not None:
-            res.subarea_counts = o_sub.cpu().numpy()
+            res.subarea_counts = on_host(o_sub)
         if o_oh is not None:
-            h = o_oh.cpu().numpy()
+            h = on_host(o_oh)
             res.orientations_histogram = h if args.ori_distance else h[:, :-1].copy()
             res.orientations_histogram_bins = edges
         return res
