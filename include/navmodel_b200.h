@@ -346,10 +346,24 @@ typedef struct nm_sim_args {
   const double *h_ori_edges;               /* HOST [n_ori_bins+1] the edges numpy.histogram uses               */
   double ori_min_lim, ori_max_lim;         /* turns outside are shifted by one full turn (:331-334)            */
   int32_t *d_ori_hist;                     /* [N, n_ori_bins+1]; last entry = the distance=True extra count    */
+  /* ---- continuing an earlier run: StandardExperiment.run called again on the same model (experiment.py:33-51
+   *      keeps no per-run state: the components and the model carry on where they were); NULL = fresh objects ---- */
+  const uint32_t *d_init_visits;           /* [N,X*Y] ExperienceComponent._maze_map_exp before the run
+                                              (behavioural_components.py:437-441).  The visit map of the kernel
+                                              starts from it, so every output derived from that map (d_occupancy,
+                                              d_occupancy_total, d_tile_counts, d_it_visit, zone / subarea
+                                              occupancy) counts the seeded visits too                          */
+  const double *d_init_model_state;        /* [N,3] BehaviouralModel._moving (0/1), ExperienceComponent._familiarity,
+                                              _ment_state (0 EXPLO / 1 HOME) before the run                     */
+  uint32_t init_visits_max;                /* upper bound of d_init_visits (picks the counter width)           */
+  int32_t reserved3;
 } nm_sim_args;
 
 /* StandardExperiment.run(n_steps) for n_mice independent mice on the maze's device. */
 int nm_simulate(const nm_maze *mz, const nm_sim_args *args, void *stream);
+
+/* sizeof(nm_sim_args) of the built library: a binding checks its own mirror of the struct against it at load time. */
+int nm_sim_args_size(void);
 
 /* 1 if an X x Y maze fits the simulation kernel's shared-memory visit map for runs of n_steps (the counters are 16
  * bits wide below 65535 steps), else 0: StandardExperiment.run then keeps the reference's per-step host loop. */

@@ -74,6 +74,7 @@ SIGNATURES = {
     "nm_distance_rows": (C.c_int, [C.c_int, _p, _p, _i64, C.c_int, _p, _p]),
     "nm_simulate": (C.c_int, [_p, _p, _p]),
     "nm_simulate_fits": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "nm_sim_args_size": (C.c_int, []),
     "nm_maze_movements_possible_device": (C.c_int, [_p, _p, _i64, _p, _p]),
 }
 
@@ -111,6 +112,8 @@ class SimArgs(C.Structure):
         ("reserved2", C.c_int32),
         ("h_ori_edges", C.c_void_p), ("ori_min_lim", C.c_double), ("ori_max_lim", C.c_double),
         ("d_ori_hist", C.c_void_p),
+        ("d_init_visits", C.c_void_p), ("d_init_model_state", C.c_void_p),
+        ("init_visits_max", C.c_uint32), ("reserved3", C.c_int32),
     ]
 
 _lock = threading.Lock()
@@ -138,6 +141,9 @@ def lib():
                 fn = getattr(handle, name)  # AttributeError if the .so lacks a declared symbol
                 fn.restype = res
                 fn.argtypes = args
+            if handle.nm_sim_args_size() != C.sizeof(SimArgs):
+                raise RuntimeError(f"{path}: nm_sim_args is {handle.nm_sim_args_size()} bytes, the ctypes mirror "
+                                   f"{C.sizeof(SimArgs)}: rebuild the library (__graft_entry__.build())")
             _lib = handle
     return _lib
 

@@ -249,7 +249,7 @@ class BatchedExperiment:
     def run(self, params, n_steps, init_pos, init_ori=0.0, init_disc=None, seeds=None, draws=None,
             visit_percentage=80, history=False, occupancy=False, occupancy_total=False, generators=None,
             device_seed=None, n_mice=None, shock_zone=None, corridors=None, static_intervals=False, subareas=False,
-            orientation_histogram=None):
+            orientation_histogram=None, init_visits=None, init_model_state=None):
         """Simulate ``n_steps`` iterations for every mouse.
 
         :param params: ``{name: array[N] or scalar}`` for every name in :attr:`parameter_names`
@@ -267,6 +267,12 @@ class BatchedExperiment:
         :param orientation_histogram: ``{}`` or a dict with any of ``n_bins``, ``max_lim``, ``possible_actions``,
             ``distance``, ``tiles_filter`` (tile types: ``hist_orientations_filtered``) -- fuse ``hist_orientations``
             of the mouse's own orientation history
+        :param init_visits: ``[X, Y]`` or ``[N, X, Y]`` non-negative integers -- the ``ExperienceComponent``'s visit map
+            left by an earlier run (``StandardExperiment.run`` called again on the same objects).  The kernel's one
+            visit map starts from it: ``occupancy`` and the metrics counted from that map (``tile_counts``,
+            ``it_visit``, zone / subarea occupancy) then include the seeded visits
+        :param init_model_state: ``[3]`` or ``[N, 3]`` -- ``BehaviouralModel._moving`` (0 / 1), the component's
+            ``_familiarity`` and ``_ment_state`` (0 EXPLO / 1 HOME) left by that run
         """
         import torch
         _native.require_device()
@@ -373,6 +379,18 @@ class BatchedExperiment:
             keep.append(t32)
             args.d_pcg_u32 = t32.data_ptr()
         args.visit_percentage = float(visit_percentage)
+        if init_visits is not None:
+            iv = np.asarray(init_visits)
+            if iv.shape not in ((X, Y), (N, X, Y)) or (iv < 0).any() or (iv != np.floor(iv)).any() or iv.max() >= 2**32:
+                raise ValueError(f"init_visits must hold non-negative integers of shape {(X, Y)} or {(N, X, Y)}")
+            iv = np.array(np.broadcast_to(iv.astype(np.uint32), (N, X, Y)), order="C")  # a writable copy
+            t = torch.from_numpy(iv.view(np.int32)).to(dev)
+            keep.append(t)
+            args.d_init_visits, args.init_visits_max = t.data_ptr(), int(iv.max()) if iv.size else 0
+        if init_model_state is not None:
+            ms = np.empty((N, 3))
+            ms[:] = np.asarray(init_model_state, dtype=np.float64).reshape(-1, 3)
+            args.d_init_model_state = dev_f64(ms).data_ptr()
 
         o_pose = out((N, 3), torch.float64)
         o_pcg = out((N, 4), torch.int64)

@@ -101,7 +101,9 @@ struct Pcg64 {
 // NT = threads per CTA (compile-time: every per-mouse table is indexed [row][thread], so row strides and the
 // fixed-size tables' offsets become immediates).
 // CntT = type of a visit counter: u16 when n_steps + 1 < 65536 (half the shared memory: one more resident CTA), else u32.
-template <int NT, typename CntT>
+// SEEDED = the run continues an earlier one (d_init_visits / d_init_model_state); a separate instantiation, so that
+// the fresh-start kernel keeps its register allocation.
+template <int NT, typename CntT, bool SEEDED>
 __global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 : NM_SIM_MIN_CTAS) * kSimThreads) / NT)
     nm_sim_kernel(const SimDev d) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -125,12 +127,17 @@ __global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 
   const uint8_t *tiles = geo.tiles;
   if (d.a.d_vtable && !d.a.vtable_per_mouse)
     for (int i = tid; i < nT; i += nt) vt_sm[i] = d.a.d_vtable[i];
-  for (int i = 0; i < nT; ++i) count[i * nt + tid] = (CntT)0;
-  __syncthreads();
-
   const nm_sim_args &a = d.a;
   const int64_t N = a.n_mice;
   const int64_t n_raw = (int64_t)blockIdx.x * nt + tid;
+  if (SEEDED && a.d_init_visits) {  // continuing an earlier run: ExperienceComponent._maze_map_exp as it was left
+    const uint32_t *iv = a.d_init_visits + (n_raw < N ? n_raw : N - 1) * nT;
+    for (int i = 0; i < nT; ++i) count[i * nt + tid] = (CntT)iv[i];
+  } else {
+    for (int i = 0; i < nT; ++i) count[i * nt + tid] = (CntT)0;
+  }
+  __syncthreads();
+
   // The warp shares the ray walks of its mice (below), so all 32 lanes run the step loop together: the lanes past the
   // last mouse (final CTA only) shadow mouse N - 1 and store nothing.
   const bool live = n_raw < N;
@@ -172,6 +179,12 @@ __global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 
     if (a.d_experience) {
       const double *q = a.d_experience + 6 * n;
       ex_w = q[0]; xi = q[1]; k_home = q[2]; k_explo = q[3]; th_explo = q[4]; th_home = q[5];
+    }
+    if (SEEDED && a.d_init_model_state) {  // the model and the component carry on where an earlier run left them
+      const double *q = a.d_init_model_state + 3 * n;
+      moving = q[0] != 0.0;
+      fam = q[1];
+      home = q[2] != 0.0;
     }
     double bpw_plain = 0, bpw_m = 0, bpw_nm = 0;  // bp * W, (Wm*bp) * W, (Wnm*bp) * W   (:502-513)
     if (a.d_bpersistence) {
@@ -682,7 +695,9 @@ extern "C" int nm_simulate(const nm_maze *mz, const nm_sim_args *args, void *str
   // value table | geometry
   // a tile is visited at most n_steps + 1 times; NM_SIM_COUNTERS=32 forces the wide variant (tests)
   const char *env_cnt = getenv("NM_SIM_COUNTERS");
-  const bool small_counts = a.n_steps < 65535 && !(env_cnt && env_cnt[0] == '3');
+  const int64_t count_max = (int64_t)a.n_steps + (a.d_init_visits ? (int64_t)a.init_visits_max : 0);
+  NM_CHECK_ARG(count_max < 4294967295LL, "nm_simulate: seeded visits + n_steps overflow the 32-bit visit counters");
+  const bool small_counts = count_max < 65535 && !(env_cnt && env_cnt[0] == '3');
   const size_t cnt_bytes = small_counts ? sizeof(uint16_t) : sizeof(uint32_t);
   auto smem_for = [&](int th) {
     return 128 + 16 * kA + (size_t)th * (1 + 2 * kA) + (size_t)(5 + kA) * th * sizeof(double) + (size_t)nT * th * cnt_bytes +
@@ -694,10 +709,14 @@ extern "C" int nm_simulate(const nm_maze *mz, const nm_sim_args *args, void *str
   const int64_t blocks = (a.n_mice + threads - 1) / threads;
   NM_CHECK_ARG(blocks <= 2147483647LL, "nm_simulate: too many mice for one launch");
   void (*kern)(const SimDev);
+  const bool seeded = a.d_init_visits || a.d_init_model_state;
+#define NM_SIM_PICK(CNT, SEED) \
+  (threads == 128 ? nm_sim_kernel<128, CNT, SEED> : threads == 64 ? nm_sim_kernel<64, CNT, SEED> : nm_sim_kernel<32, CNT, SEED>)
   if (small_counts)
-    kern = threads == 128 ? nm_sim_kernel<128, uint16_t> : threads == 64 ? nm_sim_kernel<64, uint16_t> : nm_sim_kernel<32, uint16_t>;
+    kern = seeded ? NM_SIM_PICK(uint16_t, true) : NM_SIM_PICK(uint16_t, false);
   else
-    kern = threads == 128 ? nm_sim_kernel<128, uint32_t> : threads == 64 ? nm_sim_kernel<64, uint32_t> : nm_sim_kernel<32, uint32_t>;
+    kern = seeded ? NM_SIM_PICK(uint32_t, true) : NM_SIM_PICK(uint32_t, false);
+#undef NM_SIM_PICK
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   kern<<<(unsigned)blocks, threads, smem, (cudaStream_t)stream>>>(d);
@@ -705,6 +724,8 @@ extern "C" int nm_simulate(const nm_maze *mz, const nm_sim_args *args, void *str
   if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_sim_kernel launch: %s", cudaGetErrorString(e));
   return NM_OK;
 }
+
+extern "C" int nm_sim_args_size(void) { return (int)sizeof(nm_sim_args); }
 
 extern "C" int nm_simulate_fits(int X, int Y, int n_steps) {
   // the narrowest CTA (one warp) of nm_sim_kernel: see smem_for in nm_simulate

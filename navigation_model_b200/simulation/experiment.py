@@ -5,8 +5,9 @@ scope).  ``run(iterations)`` with a ``BehaviouralModel`` made of the built-in co
 loop in Python: the whole run is one launch of ``nm_simulate`` with a single mouse whose generator state
 is taken from -- and written back to -- the model's numpy ``Generator``; afterwards the mouse (pose +
 history), the model (``_prev_pos``, ``_moving``) and the ``ExperienceComponent`` (visit map, familiarity,
-mental state) hold exactly what the per-step loop would have left.  That path needs a CUDA device and
-fails loudly without one.  Models with user-defined components / exploration models are host plugins by
+mental state) hold exactly what the per-step loop would have left -- and the next ``run`` on the same objects
+starts its launch from that state (seeded visit map, familiarity, mental state, ``_moving``), as the reference's
+loop would.  That path needs a CUDA device and fails loudly without one.  Models with user-defined components / exploration models are host plugins by
 nature and run through the generic per-step loop.
 """
 import numpy as np
@@ -35,7 +36,16 @@ class StandardExperiment:
         if type(self._maze) is not Maze or type(self._mouse) is not Mouse:
             return False
         X, Y = self._maze.shape
-        if not _native.lib().nm_simulate_fits(int(X), int(Y), int(iterations)):
+        seeded = 0  # visits an ExperienceComponent already holds (a second run on the same objects)
+        if type(model) is BehaviouralModel:
+            for c in model._components:
+                if isinstance(c, bc.ExperienceComponent):
+                    m = np.asarray(c._maze_map_exp)
+                    if (m.shape != (X, Y) or not np.isfinite(m).all() or (m < 0).any() or (m != np.floor(m)).any()
+                            or m.max() + iterations >= 2 ** 32 - 1):
+                        return False  # not a visit count the kernel's integer map can carry: host loop
+                    seeded = int(m.max())
+        if not _native.lib().nm_simulate_fits(int(X), int(Y), int(iterations) + seeded):
             return False  # the visit map does not fit the kernel's shared memory: the host loop below still works
         if type(model) is RandomModel:
             return (1 <= len(self._mouse.possible_actions) <= _native.NM_MAX_CAND
@@ -52,17 +62,10 @@ class StandardExperiment:
         if not 1 <= n_act <= _native.NM_MAX_CAND:
             return False
         for c in comps:
-            if isinstance(c, bc.ExperienceComponent):
-                fresh = (c._maze_map_exp.shape == tuple(self._maze.shape) and not c._maze_map_exp.any()
-                         and c._familiarity == 0.0 and c._ment_state == c.State.EXPLO)
-                if not fresh:
-                    return False  # continuing a previous run: that state lives in the Python object
             if isinstance(c, (bc.BiomechanicalCostComponent, bc.BiomechPersistenceComponent)):
                 if len(c._discrete_actions) != n_act:
                     return False
-        if model._moving or type(model._rng.bit_generator).__name__ != "PCG64":
-            return False
-        return True
+        return type(model._rng.bit_generator).__name__ == "PCG64"
 
     def run(self, iterations):
         self._mouse.enable_history(True)  # experiment.py:32
@@ -123,8 +126,18 @@ class StandardExperiment:
         for c in comps:
             params.update(c.parameters)
         init_disc = np.asarray(model._prev_pos, dtype=np.float64).reshape(2)
+        # the model and the ExperienceComponent carry on where an earlier run() left them (the reference keeps all of
+        # that in the Python objects, exploration_model.py:101-107, behavioural_components.py:437-441)
+        seed_visits, state = None, [float(bool(model._moving)), 0.0, 0.0]
+        for c in comps:
+            if isinstance(c, bc.ExperienceComponent):
+                seed_visits = np.asarray(c._maze_map_exp, dtype=np.float64)
+                state[1:] = [float(c._familiarity), float(int(c._ment_state))]
+        if seed_visits is not None and not seed_visits.any():
+            seed_visits = None
         res = exp.run(params, iterations, mouse.position, mouse.orientation, init_disc=init_disc,
-                      generators=[model._rng], history=True, occupancy=True)
+                      generators=[model._rng], history=True, occupancy=True, init_visits=seed_visits,
+                      init_model_state=state)
         if res.status[0] != 0:  # a step without any reachable endpoint: np.max([]) in exploration_model.py:92
             raise ValueError("zero-size array to reduction operation maximum which has no identity")
         if iterations <= 0:
@@ -140,9 +153,9 @@ class StandardExperiment:
         model._moving = np.bool_(ms[2] != 0.0)
         for c in comps:
             if isinstance(c, bc.ExperienceComponent):
-                visits = res.occupancy[0].astype(np.float64)
+                visits = res.occupancy[0].astype(np.uint32).astype(np.float64)  # seeded visits + this run's positions
                 last = maze.cont2disc(hp[-1])
                 visits[last[0], last[1]] -= 1.0  # the final position has not been "experienced" yet
-                c._maze_map_exp += visits
+                c._maze_map_exp[...] = visits
                 c._familiarity = float(ms[3])
                 c._ment_state = c.State.HOME if ms[4] != 0.0 else c.State.EXPLO
