@@ -11,6 +11,8 @@ generated on the device from the host-computed state) or ``draws[N, T]`` (replay
 parity tests use).  PyTorch is used for device buffers only.  No CPU fallback.
 """
 import ctypes as C
+import functools
+import threading
 from dataclasses import dataclass
 
 import numpy as np
@@ -252,6 +254,41 @@ class BatchedExperiment:
                                    f"[{lo}; {hi}]")
         return cols
 
+    # -- host -> device: large arrays go through pinned memory kept across runs ----------------------------------------
+    def _stage_reset(self):
+        """Start of a run: the pinned arenas of the previous run are free again (every run ends synchronised)."""
+        if not hasattr(self, "_arenas"):
+            self._arenas = []  # [pinned uint8 tensor, bytes used]
+        for ar in self._arenas:
+            ar[1] = 0
+
+    def _stage_slot(self, torch, nbytes):
+        need = (nbytes + 63) & ~63
+        for ar in self._arenas:
+            if ar[0].numel() - ar[1] >= need:
+                off = ar[1]
+                ar[1] += need
+                return ar[0][off:off + nbytes]
+        self._arenas.append([torch.empty(max(need, 64 << 20), dtype=torch.uint8, pin_memory=True), need])
+        return self._arenas[-1][0][:nbytes]
+
+    def _upload_f64(self, torch, a, dev):
+        """``a`` (any dtype / strides) as a float64 device tensor.  A pageable ``.to(device)`` is a synchronous copy at
+        ~10 GB/s; above 1 MB the array is written into a pinned arena in row blocks over a few threads (conversion and
+        transposition happen in that pass) and leaves by an asynchronous copy that overlaps the next array's pass."""
+        a = np.asarray(a)
+        if a.nbytes < (1 << 20) or a.ndim == 0:
+            return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+        slot = self._stage_slot(torch, a.size * 8)
+        dst = slot.numpy().view(np.float64).reshape(a.shape)
+        rows = max(1, (4 << 20) // max(1, 8 * a.size // a.shape[0]))
+        spans = [(lo, min(lo + rows, a.shape[0])) for lo in range(0, a.shape[0], rows)]
+        if len(spans) == 1:
+            np.copyto(dst, a)
+        else:
+            list(_pool().map(lambda sp: np.copyto(dst[sp[0]:sp[1]], a[sp[0]:sp[1]]), spans))
+        return slot.view(torch.float64).view(a.shape).to(dev, non_blocking=True)
+
     def _fetch(self, torch, tensors):
         """Device tensors -> fresh numpy arrays through a pinned staging buffer that is kept across runs (pageable
         ``.cpu()`` copies run at a few GB/s and synchronise one by one).  ``{id(tensor): array}``.
@@ -284,7 +321,7 @@ class BatchedExperiment:
             out[id(t)] = a.reshape(tuple(t.shape))
         return out
 
-    def run(self, params, n_steps, init_pos, init_ori=0.0, init_disc=None, seeds=None, draws=None,
+    def _run(self, params, n_steps, init_pos, init_ori=0.0, init_disc=None, seeds=None, draws=None,
             visit_percentage=80, history=False, occupancy=False, occupancy_total=False, generators=None,
             device_seed=None, n_mice=None, shock_zone=None, corridors=None, static_intervals=False, subareas=False,
             orientation_histogram=None, init_visits=None, init_model_state=None):
@@ -351,15 +388,17 @@ class BatchedExperiment:
 
         keep = []  # device tensors must outlive the launch
 
+        self._stage_reset()
+
         def dev_f64(a):
-            t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+            t = self._upload_f64(torch, a, dev)
             keep.append(t)
             return t
 
         def dev_cols(*cols_):
             """``[N, k]`` parameter block from ``k`` per-mouse columns: the columns are uploaded as they are and
             interleaved on the device (a host ``np.stack`` of a million rows costs more than the copy)."""
-            t = torch.stack([torch.from_numpy(np.ascontiguousarray(c, dtype=np.float64)).to(dev) for c in cols_], dim=1)
+            t = torch.stack([self._upload_f64(torch, c, dev) for c in cols_], dim=1)
             keep.append(t)
             return t
 
@@ -385,7 +424,12 @@ class BatchedExperiment:
             args.d_anxiety = dev_cols(cols["W_anx"], cols["p1"], cols["p2"], cols["p3"], p4).data_ptr()
         if _native.COMP_BCOST in self.kinds:
             args.d_bcost_weight = dev_f64(cols["W_bcost"]).data_ptr()
-            args.d_bcost_table = dev_f64(bc.bcost_tables(self.discrete_actions, cols["k"], cols["gamma"])).data_ptr()
+            # the tables are computed straight into pinned memory and leave from there
+            slot = self._stage_slot(torch, N * len(self.actions) * 8)
+            bc.bcost_tables(self.discrete_actions, cols["k"], cols["gamma"],
+                            out=slot.numpy().view(np.float64).reshape(N, len(self.actions)))
+            keep.append(slot.view(torch.float64).view(N, len(self.actions)).to(dev, non_blocking=True))
+            args.d_bcost_table = keep[-1].data_ptr()
         if _native.COMP_EXPERIENCE in self.kinds:
             args.d_experience = dev_cols(*[cols[n] for n in ("W_exp", "xi", "kappa_home", "kappa_explo",
                                                               "theta_explo", "theta_home")]).data_ptr()
@@ -535,6 +579,12 @@ class BatchedExperiment:
             res.orientations_histogram = h if args.ori_distance else h[:, :-1]
             res.orientations_histogram_bins = edges
         return res
+
+    @functools.wraps(_run)
+    def run(self, *args, **kwargs):
+        # one run at a time per experiment: the pinned staging buffers on both sides of the launch belong to the object
+        with self.__dict__.setdefault("_run_lock", threading.Lock()):
+            return self._run(*args, **kwargs)
 
 
 def tile_flags(maze, shock_zone=None, corridors=None):

@@ -201,10 +201,11 @@ class AnxietyComponent(Component):
         self._val = np.array([self._maze_weights[t] for t in next_tiles])
 
 
-def bcost_tables(discrete_actions, k, gamma):
+def bcost_tables(discrete_actions, k, gamma, out=None):
     """Cached per-action values of :class:`BiomechanicalCostComponent` for arrays of ``k`` / ``gamma``
     (``:393-406``): von Mises pdf of the action's direction (0 for the null action), times ``gamma`` for
-    actions whose Chebyshev length is >= 2.  Returns ``float64[N, A]``."""
+    actions whose Chebyshev length is >= 2.  Returns ``float64[N, A]`` (written into ``out`` when given, e.g. pinned
+    memory on its way to the device)."""
     acts = np.array(discrete_actions)
     k = np.atleast_1d(np.asarray(k, dtype=np.float64))
     gamma = np.atleast_1d(np.asarray(gamma, dtype=np.float64))
@@ -213,16 +214,21 @@ def bcost_tables(discrete_actions, k, gamma):
     far = np.linalg.norm(acts, ord=np.inf, axis=1) >= 2
     if not np.all(np.isfinite(k) & (k >= 0)):
         from scipy.stats import vonmises
-        out = vonmises.pdf(angles[None, :], k[:, None])
-        out[:, null] = 0.0
-        out[:, far] *= gamma[:, None]  # the other columns are multiplied by 1.0 in the reference: unchanged bits
+        res = vonmises.pdf(angles[None, :], k[:, None])
+        res[:, null] = 0.0
+        res[:, far] *= gamma[:, None]  # the other columns are multiplied by 1.0 in the reference: unchanged bits
+        if out is None:
+            return res
+        out[...] = res
         return out
     # scipy's own formula (vonmises_gen._pdf: exp(kappa * cosm1(x)) / (2 pi i0e(kappa))) without the generic
     # rv_continuous.pdf machinery: same bits (tests/test_host_api.py), ~100x faster for a million mice.  Elementwise,
     # so large batches are cut into row blocks and spread over a few threads (numpy releases the GIL in its loops).
     import scipy.special as sc
     cm1 = sc.cosm1(angles)[None, :]
-    out = np.empty((len(k), len(acts)))
+    if out is None:
+        out = np.empty((len(k), len(acts)))
+    assert out.shape == (len(k), len(acts)) and out.dtype == np.float64
 
     def block(lo, hi):
         kk = k[lo:hi]

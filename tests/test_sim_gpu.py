@@ -339,3 +339,29 @@ def test_device_seeded_streams(cuda):
     assert freq.max() < 0.6 and (freq > 0).sum() >= 6          # a softmax policy, not a stuck generator
     with pytest.raises(ValueError):
         exp.run(P, 10, device_seed=1, seeds=[1], **kw)
+
+
+def test_results_survive_the_next_run(cuda):
+    """The per-mouse results come back through a pinned staging buffer that the next run reuses: what a run returned
+    must not change when the experiment runs again (large enough for the threaded copy-out, > 16 MB of results)."""
+    from navigation_model_b200.batched_sim import BatchedExperiment
+    from navigation_model_b200.simulation import behavioural_components as bc
+    maze = H.product_m9()
+    exp = BatchedExperiment(maze, H.a8(), O.A8_UNITS, [bc.AnxietyComponent])
+    P = {"beta": 1.5, "W_anx": 2.0, "p1": 0.9, "p2": 0.5, "p3": 0.4}
+    N = 120_000
+    kw = dict(init_pos=maze.get_tile_centre(1, 1), init_ori=0.0, init_disc=(1, 1), n_mice=N, shock_zone={"tile_lines": 5},
+              corridors=(1, 7), static_intervals=True, subareas=True, orientation_histogram={})
+    a = exp.run(P, 40, device_seed=3, **kw)
+    fields = ("final_pose", "status", "it_visit", "count_moving", "tile_counts", "pcg_state", "model_state",
+              "zone_latency", "zone_occupancy", "zone_entries", "corridor_switches", "static_intervals",
+              "subarea_counts", "orientations_histogram")
+    kept = {f: np.array(getattr(a, f), copy=True) for f in fields}
+    b = exp.run(P, 40, device_seed=4, **kw)
+    assert not np.array_equal(b.final_pose, kept["final_pose"])
+    for f in fields:
+        assert np.array_equal(getattr(a, f), kept[f]), f
+    c = exp.run(P, 40, device_seed=3, **kw)  # and the threaded copy returns the same bytes as the first time
+    for f in fields:
+        assert np.array_equal(getattr(c, f), kept[f]), f
+    assert a.tile_counts.sum(axis=1).min() == 41 and a.orientations_histogram.shape[0] == N
