@@ -205,6 +205,9 @@ class BatchedExperiment:
         self._device = device
         self._dmaze = None
         self.last_kernel_ms = None
+        self._run_lock = threading.Lock()  # one run at a time: the staging buffers below belong to the object
+        self._arenas = []                  # pinned upload arenas [uint8 tensor, bytes used], kept across runs
+        self._pinned = None                # pinned staging buffer of the per-mouse results, kept across runs
         # True: v_table already holds ValueTableComponent._v_table (normalised once at construction)
         self._normalise = (lambda t: np.asarray(t, dtype=np.float64)) if v_table_normalised else bc.normalise_v_table
 
@@ -257,8 +260,6 @@ class BatchedExperiment:
     # -- host -> device: large arrays go through pinned memory kept across runs ----------------------------------------
     def _stage_reset(self):
         """Start of a run: the pinned arenas of the previous run are free again (every run ends synchronised)."""
-        if not hasattr(self, "_arenas"):
-            self._arenas = []  # [pinned uint8 tensor, bytes used]
         for ar in self._arenas:
             ar[1] = 0
 
@@ -298,7 +299,7 @@ class BatchedExperiment:
         a million mice return, page faults of the fresh block included, took 60 ms of a 280 ms run."""
         sizes = [(t.numel() * t.element_size() + 63) & ~63 for t in tensors]
         total = sum(sizes)
-        pin = getattr(self, "_pinned", None)
+        pin = self._pinned
         if pin is None or pin.numel() < total:
             pin = self._pinned = torch.empty(max(total, 1), dtype=torch.uint8, pin_memory=True)
         offs, off = [], 0
@@ -582,8 +583,7 @@ class BatchedExperiment:
 
     @functools.wraps(_run)
     def run(self, *args, **kwargs):
-        # one run at a time per experiment: the pinned staging buffers on both sides of the launch belong to the object
-        with self.__dict__.setdefault("_run_lock", threading.Lock()):
+        with self._run_lock:
             return self._run(*args, **kwargs)
 
 
