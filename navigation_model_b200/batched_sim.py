@@ -18,23 +18,12 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _native
+from ._hostpool import pool as _pool
 from .simulation import behavioural_components as bc
 from .sweep import DeviceMaze
 
 _NP_OF_TORCH = {"torch.float64": np.float64, "torch.float32": np.float32, "torch.int64": np.int64,
                 "torch.int32": np.int32, "torch.int16": np.int16, "torch.uint8": np.uint8, "torch.int8": np.int8}
-_POOL = None
-
-
-def _pool():
-    """A few host threads for the bulk numpy work around a launch (range checks, copies out of the pinned staging
-    buffer): numpy releases the GIL inside its loops.  Created on first use, shared by all experiments."""
-    global _POOL
-    if _POOL is None:
-        import os
-        from concurrent.futures import ThreadPoolExecutor
-        _POOL = ThreadPoolExecutor(max_workers=max(1, min(8, os.cpu_count() or 1)), thread_name_prefix="nm-host")
-    return _POOL
 
 
 def pcg64_state_words(seeds):

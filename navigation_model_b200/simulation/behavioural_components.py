@@ -238,15 +238,13 @@ def bcost_tables(discrete_actions, k, gamma, out=None):
         out[lo:hi, null] = 0.0
         out[lo:hi, far] *= gamma[lo:hi, None]
 
-    rows = 1 << 16
+    rows = 1 << 15
     if len(k) <= 2 * rows:
         block(0, len(k))
     else:
-        import os
-        from concurrent.futures import ThreadPoolExecutor
+        from .._hostpool import pool
         spans = [(lo, min(lo + rows, len(k))) for lo in range(0, len(k), rows)]
-        with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
-            list(pool.map(lambda sp: block(*sp), spans))
+        list(pool().map(lambda sp: block(*sp), spans))
     return out
 
 
