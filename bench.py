@@ -259,7 +259,7 @@ def other_paths(local, world, rank, dist, dev):
         t0 = time.perf_counter()
         res = exp.run(P, T, pos0, ori0, init_disc=(1, 1), device_seed=77 + rep, n_mice=N, occupancy_total=True,
                       shock_zone={"tile_lines": 5}, corridors=(1, 7), static_intervals=True, subareas=True,
-                      orientation_histogram={})
+                      orientation_histogram={}, mouse_index_base=rank * N)  # this rank's block of world * N mice
         e2e_s.append(time.perf_counter() - t0)
         k_ms.append(exp.last_kernel_ms)
     k = max_over_ranks(min(k_ms[1:])) * 1e-3

@@ -357,6 +357,10 @@ typedef struct nm_sim_args {
                                               _ment_state (0 EXPLO / 1 HOME) before the run                     */
   uint32_t init_visits_max;                /* upper bound of d_init_visits (picks the counter width)           */
   int32_t reserved3;
+  /* ---- a shard of a larger population (mice split over the GPUs of a box in contiguous blocks) ---- */
+  int64_t mouse_index_base;                /* use_device_seed: mouse n seeds its stream from (device_seed,
+                                              mouse_index_base + n), so a population gives the same mice whatever the
+                                              number of shards                                                  */
 } nm_sim_args;
 
 /* StandardExperiment.run(n_steps) for n_mice independent mice on the maze's device. */

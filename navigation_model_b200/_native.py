@@ -114,6 +114,7 @@ class SimArgs(C.Structure):
         ("d_ori_hist", C.c_void_p),
         ("d_init_visits", C.c_void_p), ("d_init_model_state", C.c_void_p),
         ("init_visits_max", C.c_uint32), ("reserved3", C.c_int32),
+        ("mouse_index_base", C.c_int64),
     ]
 
 _lock = threading.Lock()

@@ -314,7 +314,7 @@ class BatchedExperiment:
     def _run(self, params, n_steps, init_pos, init_ori=0.0, init_disc=None, seeds=None, draws=None,
             visit_percentage=80, history=False, occupancy=False, occupancy_total=False, generators=None,
             device_seed=None, n_mice=None, shock_zone=None, corridors=None, static_intervals=False, subareas=False,
-            orientation_histogram=None, init_visits=None, init_model_state=None):
+            orientation_histogram=None, init_visits=None, init_model_state=None, mouse_index_base=0):
         """Simulate ``n_steps`` iterations for every mouse.
 
         :param params: ``{name: array[N] or scalar}`` for every name in :attr:`parameter_names`
@@ -338,6 +338,8 @@ class BatchedExperiment:
             ``it_visit``, zone / subarea occupancy) then include the seeded visits
         :param init_model_state: ``[3]`` or ``[N, 3]`` -- ``BehaviouralModel._moving`` (0 / 1), the component's
             ``_familiarity`` and ``_ment_state`` (0 EXPLO / 1 HOME) left by that run
+        :param mouse_index_base: with ``device_seed``: mouse ``n`` of this call is mouse ``mouse_index_base + n`` of a
+            larger population and draws that mouse's stream (:meth:`run_sharded`)
         """
         import torch
         _native.require_device()
@@ -439,6 +441,7 @@ class BatchedExperiment:
         if device_seed is not None:
             args.device_seed = int(device_seed) & ((1 << 64) - 1)
             args.use_device_seed = 1
+            args.mouse_index_base = int(mouse_index_base)
         elif draws is not None:
             args.d_draws = dev_f64(draws.T).data_ptr()  # time-major [T, N]: coalesced per step
         else:
@@ -574,6 +577,127 @@ class BatchedExperiment:
     def run(self, *args, **kwargs):
         with self._run_lock:
             return self._run(*args, **kwargs)
+
+    # -- a population sharded over the GPUs of a box -------------------------------------------------
+    def run_sharded(self, params, n_steps, init_pos, init_ori=0.0, init_disc=None, seeds=None, draws=None,
+                    generators=None, device_seed=None, n_mice=None, group=None, **kwargs):
+        """:meth:`run` for a population split over the ranks of an initialised ``torch.distributed`` process group (one
+        process per GPU): the flat mouse index is cut into contiguous blocks (:func:`shard_bounds_mice`), every rank
+        simulates its block -- no data-path collective; with ``device_seed`` the streams follow the GLOBAL mouse index,
+        so the population does not depend on the number of ranks -- and the population totals are summed over the
+        ranks by ONE small all-reduce (NCCL; gloo for CPU tensors): :func:`population_totals`.
+
+        Per-mouse arguments (``params`` columns, ``init_*``, ``seeds`` / ``draws`` / ``generators``, a per-mouse
+        ``v_table``, ``init_visits`` / ``init_model_state``) are given for the WHOLE population and sliced here.
+        Without a process group this is :meth:`run` plus the totals.
+
+        :return: ``(result of the local block, (lo, hi), totals)`` -- ``totals`` as :func:`population_totals` documents
+        """
+        import torch
+        import torch.distributed as dist
+        if device_seed is not None:
+            N = int(n_mice)
+        elif draws is not None:
+            N = len(draws)
+        elif generators is not None:
+            N = len(generators)
+        else:
+            seeds = list(seeds)
+            N = len(seeds)
+        rank, world = 0, 1
+        if dist.is_available() and dist.is_initialized():
+            rank, world = dist.get_rank(group), dist.get_world_size(group)
+        lo, hi = shard_bounds_mice(N, rank, world)
+
+        def cut(a, ndim=1):
+            """Rows [lo, hi) of a per-mouse array (``ndim`` axes, the first of length N); anything else -- scalars,
+            values shared by the population -- passes through."""
+            if a is None:
+                return None
+            b = np.asarray(a)
+            return b[lo:hi] if b.ndim == ndim and b.shape[0] == N else a
+
+        X, Y = self.maze.shape
+        local = {k: cut(v) for k, v in params.items()}
+        for key, ndim in (("init_visits", 3), ("init_model_state", 2)):
+            if kwargs.get(key) is not None:
+                kwargs[key] = cut(kwargs[key], ndim)
+        whole_table = self.v_table
+        if whole_table is not None and whole_table.shape == (N, X, Y):
+            self.v_table = whole_table[lo:hi]
+        try:
+            if hi > lo:
+                res = self.run(local, n_steps, cut(init_pos, 2), cut(init_ori), cut(init_disc, 2),
+                               seeds=None if seeds is None else seeds[lo:hi],
+                               draws=None if draws is None else np.asarray(draws)[lo:hi],
+                               generators=None if generators is None else list(generators)[lo:hi],
+                               device_seed=device_seed, n_mice=(hi - lo) if device_seed is not None else None,
+                               mouse_index_base=lo if device_seed is not None else 0, **kwargs)
+            else:
+                res = None  # more ranks than mice: this rank only takes part in the all-reduce
+        finally:
+            self.v_table = whole_table
+        vec = pack_population_totals(res, X * Y)
+        if world > 1:
+            on_gpu = dist.get_backend(group) == "nccl"
+            t = torch.from_numpy(vec)
+            t = t.to(torch.device("cuda", torch.cuda.current_device())) if on_gpu else t
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            vec = t.cpu().numpy()
+        n_bins = None if res is None or res.orientations_histogram is None else res.orientations_histogram.shape[1]
+        return res, (lo, hi), unpack_population_totals(vec, (X, Y), n_bins)
+
+
+def shard_bounds_mice(N, rank, world, align=128):
+    """Contiguous block ``[lo, hi)`` of the flat mouse index owned by ``rank``: blocks of ``align`` = 128 mice (one CTA
+    of the simulation kernel) dealt out evenly, the last block ragged."""
+    from .sweep import shard_bounds
+    return shard_bounds(N, rank, world, align=align)
+
+
+def pack_population_totals(res, n_tiles):
+    """Sums over the mice of one shard as ONE int64 vector (what the all-reduce carries): mice, mice without error,
+    positions, ``count_moving``, zone occupancy / entries, corridor switches, not-moving runs | ``tile_counts[8]`` |
+    ``subarea_counts[16]`` | orientation histogram ``[NM_MAX_ORI_BINS + 1]`` | ``occupancy_total[n_tiles]`` (zeros for
+    what the run did not compute; fixed layout, so that ranks without mice pack the same vector)."""
+    head = np.zeros(8, dtype=np.int64)
+    tiles, subs = np.zeros(8, dtype=np.int64), np.zeros(_native.NM_MAX_SUBAREAS, dtype=np.int64)
+    hist, occ = np.zeros(_native.NM_MAX_ORI_BINS + 1, dtype=np.int64), np.zeros(n_tiles, dtype=np.int64)
+    if res is not None:
+        def total(a):
+            return 0 if a is None else int(np.sum(a, dtype=np.int64))
+        head[:] = [len(res.status), int((res.status == 0).sum()), len(res.status) * int(res.n_positions),
+                   total(res.count_moving), total(res.zone_occupancy), total(res.zone_entries),
+                   total(res.corridor_switches), total(res.static_intervals)]
+        tiles[:] = np.sum(res.tile_counts, axis=0, dtype=np.int64)
+        if res.subarea_counts is not None:
+            subs[:] = np.sum(res.subarea_counts, axis=0, dtype=np.int64)
+        if res.orientations_histogram is not None:
+            hist[:res.orientations_histogram.shape[1]] = np.sum(res.orientations_histogram, axis=0, dtype=np.int64)
+        if res.occupancy_total is not None:
+            occ[:] = np.asarray(res.occupancy_total, dtype=np.int64).reshape(-1)
+        elif res.occupancy is not None:
+            occ[:] = np.sum(res.occupancy, axis=0, dtype=np.int64).reshape(-1)
+    return np.concatenate([head, tiles, subs, hist, occ])
+
+
+def unpack_population_totals(vec, shape, n_bins=None):
+    """``dict`` view of :func:`pack_population_totals` (after the all-reduce: totals of the whole population);
+    ``n_bins`` trims the orientation histogram to the width the run used."""
+    vec = np.asarray(vec, dtype=np.int64)
+    names = ("n_mice", "mice_ok", "n_positions", "count_moving", "zone_occupancy", "zone_entries", "corridor_switches",
+             "static_intervals")
+    out = {k: int(v) for k, v in zip(names, vec[:8])}
+    o = 8
+    out["tile_counts"] = vec[o:o + 8].copy()
+    o += 8
+    out["subarea_counts"] = vec[o:o + _native.NM_MAX_SUBAREAS].copy()
+    o += _native.NM_MAX_SUBAREAS
+    width = _native.NM_MAX_ORI_BINS + 1
+    out["orientations_histogram"] = vec[o:o + (width if n_bins is None else n_bins)].copy()
+    o += width
+    out["occupancy_total"] = vec[o:].reshape(shape).copy()
+    return out
 
 
 def tile_flags(maze, shock_zone=None, corridors=None):

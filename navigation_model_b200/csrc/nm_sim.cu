@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 
       }
     } else if (a.use_device_seed) {
       // pcg64_srandom(initstate, initseq) with both 128-bit values drawn from splitmix64(device_seed, mouse index)
-      uint64_t z = a.device_seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(4 * n + 1);
+      uint64_t z = a.device_seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(4 * (n + a.mouse_index_base) + 1);
       uint64_t w[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -637,7 +637,7 @@ extern "C" int nm_simulate(const nm_maze *mz, const nm_sim_args *args, void *str
   NM_CHECK_ARG(mz && args, "nm_simulate: NULL argument");
   NM_CHECK_ARG(mz->device >= 0, "nm_simulate: the maze has not been uploaded to a CUDA device");
   const nm_sim_args &a = *args;
-  NM_CHECK_ARG(a.n_mice >= 0 && a.n_steps >= 0, "nm_simulate: negative size");
+  NM_CHECK_ARG(a.n_mice >= 0 && a.n_steps >= 0 && a.mouse_index_base >= 0, "nm_simulate: negative size");
   NM_CHECK_ARG(a.n_actions >= 1 && a.n_actions <= NM_MAX_CAND && a.h_actions,
                "nm_simulate: need 1..%d relative actions", NM_MAX_CAND);
   NM_CHECK_ARG(a.n_components >= 0 && a.n_components <= NM_MAX_COMPONENTS, "nm_simulate: too many components");
