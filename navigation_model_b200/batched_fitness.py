@@ -63,3 +63,35 @@ class BatchedMultiObjectiveFitness:
                 out[name] = d
             torch.cuda.current_stream().synchronize()
         return {k: v.cpu().numpy() for k, v in out.items()}
+
+    def best(self, results, weights=None, offset=0, group=None):
+        """The row (mouse / simulated parameter set) with the smallest weighted sum of the objectives.
+
+        With an initialised ``torch.distributed`` process group the rows are this rank's block ``[offset, offset + N)``
+        of a sharded population (``BatchedExperiment.run_sharded``): the per-rank winners -- 16 bytes each -- are
+        all-gathered (``sweep.reduce_best``: NCCL, or gloo for CPU tensors) and every rank returns the global one,
+        lowest index on ties.  Rows whose sum is NaN never win.
+
+        :param weights: ``{objective: factor}`` (default 1 for every objective)
+        :return: ``(value, global row index)`` -- ``(nan, -1)`` when no row qualifies
+        """
+        import torch
+        import torch.distributed as dist
+        from .sweep import reduce_best
+        d = self(results)
+        total = None
+        for name, v in d.items():
+            term = v * float(1.0 if weights is None else weights.get(name, 1.0))
+            total = term if total is None else total + term
+        best = torch.empty(2, dtype=torch.float64)
+        if total is None or total.size == 0 or np.all(np.isnan(total)):
+            best[0] = float("nan")
+            best[1:].view(torch.int64)[0] = -1
+        else:
+            i = int(np.nanargmin(total))
+            best[0] = float(total[i])
+            best[1:].view(torch.int64)[0] = i
+        if dist.is_available() and dist.is_initialized() and dist.get_backend(group) == "nccl":
+            best = best.to(torch.device("cuda", torch.cuda.current_device() if self._device is None
+                                        else int(self._device)))
+        return reduce_best(best, int(offset), group=group)

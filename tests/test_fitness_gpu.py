@@ -63,6 +63,12 @@ def test_simulation_to_fitness_stays_on_device(cuda):
                                    rtol=1e-12)
         np.testing.assert_allclose(d["tiles"][n], O.js_distance(res.tile_counts[n], data["tile_counts"]), rtol=1e-10)
         assert d["moving"][n] == abs(res.count_moving[n] - 120.0)
+    # the best mouse by a weighted sum of the objectives (one rank: no exchange; `offset` = the block's first index)
+    w = {"occ": 1.0, "tiles": 2.0, "moving": 0.01}
+    total = d["occ"] + 2.0 * d["tiles"] + 0.01 * d["moving"]
+    v, i = fit.best({"occupancy": res.occupancy, "tile_counts": res.tile_counts, "count_moving": res.count_moving},
+                    weights=w, offset=1000)
+    assert i == 1000 + int(np.argmin(total)) and v == total.min()
 
 
 def test_reference_style_objectives_from_fused_metrics(cuda, golden_sim):
