@@ -124,7 +124,7 @@ def measured_hbm_peak():
         return 6650.0  # fallback stated in B200_PROFILING.md
 
 
-NCU_SUMMARY = os.path.join(ROOT, "profiles", "r01_v10_fit_kernel_ncu.txt")
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "r01_final_fit_group_deg5_kernel_ncu.txt")
 
 
 def ncu_counter(prefixes, scale_units=False):
@@ -502,7 +502,7 @@ def run_b200(args):
                     "kernel_ms_covers": "the whole nm_loglik_sweep call: the dominant kernel + 3 launches of a few "
                                         "microseconds (run detection, the kernel that stands down)",
                     "frac_note": "achieved counts the CANONICAL FP64 instructions of SURVEY 8d (exp = 20, log = 30); the "
-                                 "kernel executes fewer (table-driven exp = 12, one log per 32 steps), so the canonical "
+                                 "kernel executes fewer (table-driven exp = 10, one log per 32 steps), so the canonical "
                                  "fraction can pass 1 -- the executed fraction is fp64_pipe_busy_ncu",
                     "fp64_pipe_busy_ncu": (lambda v: None if v is None else v / 100.0)(
                         ncu_counter(["sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"])),

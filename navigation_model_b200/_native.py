@@ -122,7 +122,8 @@ _lib = None
 
 
 def library_path():
-    return _build.LIB_PATH
+    """The in-tree library; ``NM_NATIVE_LIB`` points at another build of it (A/B runs of compile-time variants)."""
+    return os.environ.get("NM_NATIVE_LIB") or _build.LIB_PATH
 
 
 def lib():

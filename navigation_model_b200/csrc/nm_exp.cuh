@@ -49,6 +49,34 @@ struct ExpRegs {
     p = __dmul_rn(p, s);
     return __hiloint2double(__double2hiint(p) + (max(k >> 4, -1021) << 20), __double2loint(p));
   }
+  // The same reduction with the polynomial cut to degree NM_LL_EXP_DEGREE (default 5: 10 FP64 instructions) for the
+  // softmax DENOMINATOR of a log-likelihood step, whose bar is 1e-9 relative on the session's log-likelihood
+  // (BASELINE.json north_star), not the last bit: |r| <= ln2/32 bounds the truncation by r^6/720 = 1.5e-13 relative
+  // per exponential (measured over [-40, 0]: max 1.46e-13, mean -2.0e-14), i.e. <= 1.5e-13 on a step's log-probability
+  // and ~1e-14 relative on a session.  Value tables never see an exponential; the simulation kernel, whose discrete
+  // choices must reproduce the reference's, keeps exp_nonpos.  -DNM_LL_EXP_DEGREE=7 restores the full polynomial.
+#ifndef NM_LL_EXP_DEGREE
+#define NM_LL_EXP_DEGREE 5
+#endif
+  __device__ __forceinline__ double exp_nonpos_ll(double x) const {
+    static_assert(NM_LL_EXP_DEGREE >= 4 && NM_LL_EXP_DEGREE <= 7, "NM_LL_EXP_DEGREE: 4..7");
+    if (NM_LL_EXP_DEGREE == 7) return exp_nonpos(x);
+    const double t = fma(x, c[0], c[1]);
+    const int k = __double2loint(t);
+    const double n = __dsub_rn(t, c[1]);
+    double r = fma(n, c[2], x);
+    r = fma(n, c[3], r);
+    double s;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(s) : "r"(tab + ((uint32_t)(k & 15) << 3)));
+    constexpr int first = 4 + (7 - NM_LL_EXP_DEGREE);  // c[4] = 1/7!, c[5] = 1/6!, c[6] = 1/5!, ...
+    double p = fma(c[first], r, c[first + 1]);
+#pragma unroll
+    for (int i = first + 2; i < 10; ++i) p = fma(p, r, c[i]);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    p = __dmul_rn(p, s);
+    return __hiloint2double(__double2hiint(p) + (max(k >> 4, -1021) << 20), __double2loint(p));
+  }
 };
 
 #endif  // NM_EXP_CUH

@@ -209,7 +209,7 @@ __device__ __forceinline__ void exact_step_k(const uint4 q0, const uint4 q1, con
     }
     double e[NM_MAX_CAND];
 #pragma unroll
-    for (int k = 0; k < K; ++k) e[k] = acc.er.exp_nonpos(__dsub_rn(z[k], m));  // :92-93
+    for (int k = 0; k < K; ++k) e[k] = acc.er.exp_nonpos_ll(__dsub_rn(z[k], m));  // :92-93
     const double sum = np_sum_fixed<K>(e);
     const double zobs = __dmul_rn(beta, lds_f64(vb, q0.w));
     acc.acc_obs = __dadd_rn(acc.acc_obs, __dsub_rn(zobs, m));
