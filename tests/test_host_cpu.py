@@ -200,3 +200,36 @@ def test_regroup_order_of_tile_action_sweeps():
     order = _TileActionSweep.regroup_order(a4, g4)
     assert order is not None and (a4[order][:64] == 0.2).all() and (a4[order][64:] == 0.9).all()
 
+
+
+def test_upload_staging_converts_and_transposes():
+    """The pinned-arena upload path of the batched simulation (host logic only: pinned allocation and the device copy
+    are stubbed): any dtype / strides in, float64 in the caller's shape out; arenas are reused by the next run."""
+    import torch
+    from navigation_model_b200.batched_sim import BatchedExperiment
+    from navigation_model_b200.simulation import behavioural_components as bc
+
+    class Shim:  # torch without pinned memory
+        float64, uint8 = torch.float64, torch.uint8
+        from_numpy = staticmethod(torch.from_numpy)
+
+        @staticmethod
+        def empty(n, dtype=None, pin_memory=False):
+            return torch.empty(n, dtype=dtype)
+
+    exp = BatchedExperiment(H.product_m9(), H.a8(), O.A8_UNITS, [bc.AnxietyComponent])
+    rng = np.random.default_rng(0)
+    arrays = [rng.random((300000, 8)), rng.integers(0, 9, 2_000_000), rng.random((50, 400000)).T, rng.random(7),
+              np.float32(rng.random((200000, 3)))]
+    exp._stage_reset()
+    for x in arrays:
+        t = exp._upload_f64(Shim, x, "cpu")
+        assert t.dtype == torch.float64 and tuple(t.shape) == x.shape
+        assert np.array_equal(t.numpy(), x.astype(np.float64))
+    used = [ar[1] for ar in exp._arenas]
+    assert sum(used) >= sum(a.size * 8 for a in arrays if a.nbytes >= (1 << 20))
+    exp._stage_reset()
+    assert all(ar[1] == 0 for ar in exp._arenas)
+    n_arenas = len(exp._arenas)
+    exp._upload_f64(Shim, arrays[0], "cpu")
+    assert len(exp._arenas) == n_arenas  # no new pinned allocation for the next run
