@@ -194,7 +194,7 @@ class BatchedExperiment:
         self._device = device
         self._dmaze = None
         self.last_kernel_ms = None
-        self._run_lock = threading.Lock()  # one run at a time: the staging buffers below belong to the object
+        self._run_lock = threading.RLock()  # one run at a time: the staging buffers below belong to the object
         self._arenas = []                  # pinned upload arenas [uint8 tensor, bytes used], kept across runs
         self._pinned = None                # pinned staging buffer of the per-mouse results, kept across runs
         # True: v_table already holds ValueTableComponent._v_table (normalised once at construction)
@@ -622,21 +622,22 @@ class BatchedExperiment:
         for key, ndim in (("init_visits", 3), ("init_model_state", 2)):
             if kwargs.get(key) is not None:
                 kwargs[key] = cut(kwargs[key], ndim)
-        whole_table = self.v_table
-        if whole_table is not None and whole_table.shape == (N, X, Y):
-            self.v_table = whole_table[lo:hi]
-        try:
-            if hi > lo:
-                res = self.run(local, n_steps, cut(init_pos, 2), cut(init_ori), cut(init_disc, 2),
-                               seeds=None if seeds is None else seeds[lo:hi],
-                               draws=None if draws is None else np.asarray(draws)[lo:hi],
-                               generators=None if generators is None else list(generators)[lo:hi],
-                               device_seed=device_seed, n_mice=(hi - lo) if device_seed is not None else None,
-                               mouse_index_base=lo if device_seed is not None else 0, **kwargs)
-            else:
-                res = None  # more ranks than mice: this rank only takes part in the all-reduce
-        finally:
-            self.v_table = whole_table
+        with self._run_lock:  # the per-mouse value tables are swapped for this rank's rows while the block runs
+            whole_table = self.v_table
+            if whole_table is not None and whole_table.shape == (N, X, Y):
+                self.v_table = whole_table[lo:hi]
+            try:
+                if hi > lo:
+                    res = self.run(local, n_steps, cut(init_pos, 2), cut(init_ori), cut(init_disc, 2),
+                                   seeds=None if seeds is None else seeds[lo:hi],
+                                   draws=None if draws is None else np.asarray(draws)[lo:hi],
+                                   generators=None if generators is None else list(generators)[lo:hi],
+                                   device_seed=device_seed, n_mice=(hi - lo) if device_seed is not None else None,
+                                   mouse_index_base=lo if device_seed is not None else 0, **kwargs)
+                else:
+                    res = None  # more ranks than mice: this rank only takes part in the all-reduce
+            finally:
+                self.v_table = whole_table
         vec = pack_population_totals(res, X * Y)
         if world > 1:
             on_gpu = dist.get_backend(group) == "nccl"

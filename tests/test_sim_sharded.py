@@ -56,6 +56,10 @@ def _sharded_worker(rank, world, port, q):
     c = calls[0]
     ok = (np.array_equal(c["beta"], P["beta"][lo:hi]) and c["W_anx"] == 2.0 and np.array_equal(c["pos"], pos[lo:hi])
           and c["ori"] == 0.25 and c["base"] == lo and c["n"] == hi - lo and c["seed"] == 5)
+    # more ranks than mice: the rank without a block still takes part in the all-reduce
+    one, (lo1, hi1), tot1 = exp.run_sharded({**P, "beta": 1.5}, T, pos[0], 0.25, (1, 1), device_seed=5, n_mice=1)
+    ok = ok and (one is None) == (rank == 1) and (lo1, hi1) == ((0, 1) if rank == 0 else (1, 1)) and tot1["n_mice"] == 1 \
+        and tot1["n_positions"] == T + 1
     q.put((rank, lo, hi, ok, {k: (v.tolist() if isinstance(v, np.ndarray) else v) for k, v in tot.items()}))
     dist.destroy_process_group()
 
