@@ -270,6 +270,86 @@ def _as_param(x, P=None):
     return a
 
 
+def _params3(alpha, beta, gamma):
+    """Broadcast scalars against the longest of the three arrays; ``ValueError`` on any other length mismatch."""
+    alpha, beta, gamma = _as_param(alpha), _as_param(beta), _as_param(gamma)
+    P = max(alpha.size, beta.size, gamma.size)
+    alpha, beta, gamma = _as_param(alpha, P), _as_param(beta, P), _as_param(gamma, P)
+    if not (alpha.size == beta.size == gamma.size == P):
+        raise ValueError("alpha, beta and gamma must have the same length")
+    return alpha, beta, gamma, P
+
+
+def regroup_order(alpha, gamma, run=32):
+    """Order that brings parameter sets with equal ``(alpha, gamma)`` together, so that every aligned run of ``run``
+    consecutive sets shares them and the sweep keeps ONE table per run (the tables do not depend on beta).
+
+    ``None`` when the arrays are already laid out that way (a grid with beta fastest), or when no such order exists
+    without padding (some ``(alpha, gamma)`` pair occurs a number of times that is not a multiple of ``run``, other
+    than the last one): the sweep then runs as given.  The sort is stable: sets of a pair keep their order."""
+    P = alpha.size
+    if P <= 1:
+        return None
+
+    def uniform_runs(a, g):
+        n_full = (P // run) * run
+        ok = True
+        if n_full:
+            A, G = a[:n_full].reshape(-1, run), g[:n_full].reshape(-1, run)
+            ok = bool((A == A[:, :1]).all() and (G == G[:, :1]).all())
+        if ok and n_full < P:
+            ok = bool((a[n_full:] == a[n_full]).all() and (g[n_full:] == g[n_full]).all())
+        return ok
+
+    if uniform_runs(alpha, gamma):
+        return None
+    order = np.lexsort((gamma, alpha))  # stable; alpha major, gamma minor
+    a, g = alpha[order], gamma[order]
+    return order if uniform_runs(a, g) else None
+
+
+def sharded_best_fit(base, ll_device, alpha, beta, gamma, group=None, v_init=None, regroup=True):
+    """Grid search shared by the three sweeps: minimise the negative log-likelihood summed over sessions.
+
+    The parameter sets are first brought into runs of 32 sharing ``(alpha, gamma)`` when a re-ordering achieves that
+    (:func:`regroup_order`; the per-run-table kernels then apply whatever axis order the caller's grid has), the flat
+    index of that order is sharded in contiguous blocks over the ranks of an initialised process group, and the
+    per-shard ``(nll, index in the CALLER's order)`` pairs -- 16 bytes per rank -- are all-gathered.  Ties go to the
+    lowest caller index, like ``numpy.argmin``.
+
+    ``ll_device(alpha_t, beta_t, gamma_t, v_init_slice_or_None) -> ll[S, n]`` runs one shard on the device."""
+    import torch
+    import torch.distributed as dist
+    alpha, beta, gamma, P = _params3(alpha, beta, gamma)
+    per_unit = v_init is not None and np.asarray(v_init).ndim == 3
+    order = regroup_order(alpha, gamma) if (regroup and not per_unit) else None
+    if order is not None:
+        alpha, beta, gamma = (np.ascontiguousarray(x[order]) for x in (alpha, beta, gamma))
+    rank, world = 0, 1
+    if dist.is_available() and dist.is_initialized():
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+    lo, hi = shard_bounds(P, rank, world)
+    dev = base.torch_device
+    if hi > lo:
+        vi = None if v_init is None else (np.asarray(v_init)[lo:hi] if per_unit else v_init)
+        ll = ll_device(base._to_dev(torch, alpha[lo:hi]), base._to_dev(torch, beta[lo:hi]),
+                       base._to_dev(torch, gamma[lo:hi]), vi)
+        if order is None:
+            return reduce_best(base.argmin_device(ll), lo, group=group)
+        nll = torch.empty(hi - lo, dtype=torch.float64, device=dev)
+        best = base.argmin_device(ll, nll_out=nll)
+        caller_idx = torch.from_numpy(order[lo:hi]).to(dev)
+        tied = nll == best[0]
+        local = best[1:].view(torch.int64)
+        pick = torch.where(tied.any(), torch.where(tied, caller_idx, torch.iinfo(torch.int64).max).min(),
+                           caller_idx[local.clamp(min=0)][0])
+        local.copy_(torch.where(local >= 0, pick, local).reshape(1))
+        return reduce_best(best, 0, group=group)
+    best = torch.tensor([float("nan"), 0.0], dtype=torch.float64, device=dev)
+    best[1:].view(torch.int64).fill_(-1)
+    return reduce_best(best, lo, group=group)
+
+
 def parameter_grid(*axes):
     """Cartesian product of 1-D axes -> tuple of flat ``float64[P]`` arrays (first axis slowest)."""
     mesh = np.meshgrid(*[np.asarray(a, dtype=np.float64) for a in axes], indexing="ij")
@@ -474,59 +554,54 @@ class ConditioningSweep:
         X, Y = self.maze.shape
         return out.cpu().numpy().reshape(self.n_sessions, P, X, Y)
 
-    def log_likelihood(self, alpha, beta, gamma, v_init=None, return_v=False):
-        """Per-session log-likelihood of the observed choices: ``float64[S, P]``."""
+    def log_likelihood(self, alpha, beta, gamma, v_init=None, return_v=False, regroup=True):
+        """Per-session log-likelihood of the observed choices: ``float64[S, P]``.
+
+        ``regroup``: a value table depends on ``(alpha, gamma)`` only, so sets sharing them are brought side by side
+        first when that yields uniform runs of 32 (:func:`regroup_order` -- any Cartesian grid whose beta axis has a
+        multiple of 32 points, whatever its axis order); the kernel with one table per warp then applies, and the
+        results come back in the caller's order (bit-identical either way)."""
         torch = self._ensure_device()
-        alpha, beta, gamma = _as_param(alpha), _as_param(beta), _as_param(gamma)
-        P = max(alpha.size, beta.size, gamma.size)
-        alpha, beta, gamma = _as_param(alpha, P), _as_param(beta, P), _as_param(gamma, P)
-        if not (alpha.size == beta.size == gamma.size == P):
-            raise ValueError("alpha, beta and gamma must have the same length")
+        alpha, beta, gamma, P = _params3(alpha, beta, gamma)
         if (self._external and not self._dstreams.has_candidates) or \
                 any(r["ncand"].min(initial=1) == 0 for r in self._records if len(r)):
             raise ValueError("the log-likelihood needs candidate next states: pass possible_actions")
         vi, per = self._v_init_tensor(torch, v_init, P)
+        order = regroup_order(alpha, gamma) if (regroup and not per) else None
+        if order is not None:
+            alpha, beta, gamma = (np.ascontiguousarray(x[order]) for x in (alpha, beta, gamma))
+            back = np.empty_like(order)
+            back[order] = np.arange(P)
+        unsort = (lambda x: x) if order is None else (lambda x: np.ascontiguousarray(x[:, back]))
         v_out = None
         if return_v:
             v_out = torch.empty((self.n_sessions, P, self._dmaze.n_tiles), dtype=torch.float64,
                                 device=self.torch_device)
         ll = self.log_likelihood_device(self._to_dev(torch, alpha), self._to_dev(torch, beta),
                                         self._to_dev(torch, gamma), vi, per, v_out=v_out)
-        ll = ll.cpu().numpy()
+        ll = unsort(ll.cpu().numpy())
         if return_v:
             X, Y = self.maze.shape
-            return ll, v_out.cpu().numpy().reshape(self.n_sessions, P, X, Y)
+            return ll, unsort(v_out.cpu().numpy().reshape(self.n_sessions, P, X, Y))
         return ll
 
-    def best_fit(self, alpha, beta, gamma, v_init=None, group=None):
-        """Grid search: minimise the negative log-likelihood summed over sessions.
+    def best_fit(self, alpha, beta, gamma, v_init=None, group=None, regroup=True):
+        """Grid search: minimise the negative log-likelihood summed over sessions (:func:`sharded_best_fit`).
 
-        With an initialised ``torch.distributed`` process group the flat parameter index is sharded in
-        contiguous blocks over the ranks (every rank holds all sessions) and the per-shard best fits
-        ``(nll, global index)`` -- 16 bytes per rank -- are all-gathered; every rank returns the global
-        arg-min (lowest index on ties, like ``numpy.argmin``).
+        Scalars broadcast against the longest array as in :meth:`log_likelihood`.  With an initialised
+        ``torch.distributed`` process group the flat parameter index is sharded in contiguous blocks over the ranks
+        (every rank holds all sessions) and the per-shard best fits ``(nll, index)`` -- 16 bytes per rank -- are
+        all-gathered; every rank returns the global arg-min (lowest index on ties, like ``numpy.argmin``).
 
         :return: ``(best_nll, best_index)``
         """
         torch = self._ensure_device()
-        import torch.distributed as dist
-        alpha, beta, gamma = _as_param(alpha), _as_param(beta), _as_param(gamma)
-        P = alpha.size
-        rank, world = 0, 1
-        if dist.is_available() and dist.is_initialized():
-            rank, world = dist.get_rank(group), dist.get_world_size(group)
-        lo, hi = shard_bounds(P, rank, world)
-        if hi > lo:
-            vi, per = self._v_init_tensor(torch, None if v_init is None else
-                                          (v_init if np.asarray(v_init).ndim == 2 else np.asarray(v_init)[lo:hi]),
-                                          hi - lo)
-            ll = self.log_likelihood_device(self._to_dev(torch, alpha[lo:hi]), self._to_dev(torch, beta[lo:hi]),
-                                            self._to_dev(torch, gamma[lo:hi]), vi, per)
-            best = self.argmin_device(ll)
-        else:
-            best = torch.tensor([float("nan"), 0.0], dtype=torch.float64, device=self.torch_device)
-            best[1:].view(torch.int64).fill_(-1)
-        return reduce_best(best, lo, group=group)
+
+        def ll_device(at, bt, gt, vi_np):
+            vi, per = self._v_init_tensor(torch, vi_np, int(at.numel()))
+            return self.log_likelihood_device(at, bt, gt, vi, per)
+
+        return sharded_best_fit(self, ll_device, alpha, beta, gamma, group=group, v_init=v_init, regroup=regroup)
 
 
 def reduce_best(best, offset, group=None):
@@ -596,42 +671,8 @@ class _TileActionSweep:
     def updates_per_parameter_set(self):
         return self._base.updates_per_parameter_set
 
-    @staticmethod
-    def _params(alpha, beta, gamma):
-        alpha, beta, gamma = _as_param(alpha), _as_param(beta), _as_param(gamma)
-        P = max(alpha.size, beta.size, gamma.size)
-        alpha, beta, gamma = _as_param(alpha, P), _as_param(beta, P), _as_param(gamma, P)
-        if not (alpha.size == beta.size == gamma.size == P):
-            raise ValueError("alpha, beta and gamma must have the same length")
-        return alpha, beta, gamma, P
-
-    @staticmethod
-    def regroup_order(alpha, gamma, run=32):
-        """Order that brings parameter sets with equal ``(alpha, gamma)`` together, so that every aligned run of ``run``
-        consecutive sets shares them and the sweep keeps ONE table per run (the tables do not depend on beta).
-
-        ``None`` when the arrays are already laid out that way (a grid with beta fastest), or when no such order exists
-        without padding (some ``(alpha, gamma)`` pair occurs a number of times that is not a multiple of ``run``, other
-        than the last one): the sweep then runs as given.  The sort is stable: sets of a pair keep their order."""
-        P = alpha.size
-        if P <= 1:
-            return None
-
-        def uniform_runs(a, g):
-            n_full = (P // run) * run
-            ok = True
-            if n_full:
-                A, G = a[:n_full].reshape(-1, run), g[:n_full].reshape(-1, run)
-                ok = bool((A == A[:, :1]).all() and (G == G[:, :1]).all())
-            if ok and n_full < P:
-                ok = bool((a[n_full:] == a[n_full]).all() and (g[n_full:] == g[n_full]).all())
-            return ok
-
-        if uniform_runs(alpha, gamma):
-            return None
-        order = np.lexsort((gamma, alpha))  # stable; alpha major, gamma minor
-        a, g = alpha[order], gamma[order]
-        return order if uniform_runs(a, g) else None
+    _params = staticmethod(_params3)
+    regroup_order = staticmethod(regroup_order)
 
     def _timed(self, torch, launch):
         """Run ``launch()`` (one C-ABI call) between two CUDA events on the current stream."""
@@ -660,24 +701,13 @@ class _TileActionSweep:
             _native.check(getattr(b._dmaze._lib, self._mode_symbol)(_native.cuda_stream_ptr(), C.byref(mode)))
         return mode.value
 
-    def best_fit(self, alpha, beta, gamma, group=None):
-        """Grid search like :meth:`ConditioningSweep.best_fit`: the flat parameter index is sharded over the ranks of
-        an initialised process group, 16 bytes per rank are all-gathered.  ``(best_nll, best_index)``."""
-        b = self._base
-        torch = b._ensure_device()
-        import torch.distributed as dist
-        alpha, beta, gamma, P = self._params(alpha, beta, gamma)
-        rank, world = 0, 1
-        if dist.is_available() and dist.is_initialized():
-            rank, world = dist.get_rank(group), dist.get_world_size(group)
-        lo, hi = shard_bounds(P, rank, world)
-        if hi > lo:
-            ll = self.log_likelihood_device(*(b._to_dev(torch, x[lo:hi]) for x in (alpha, beta, gamma)))
-            best = b.argmin_device(ll)
-        else:
-            best = torch.tensor([float("nan"), 0.0], dtype=torch.float64, device=b.torch_device)
-            best[1:].view(torch.int64).fill_(-1)
-        return reduce_best(best, lo, group=group)
+    def best_fit(self, alpha, beta, gamma, group=None, regroup=True):
+        """Grid search like :meth:`ConditioningSweep.best_fit` (:func:`sharded_best_fit`): sets re-ordered into runs
+        of 32 sharing ``(alpha, gamma)`` when possible, the flat index sharded over the ranks of an initialised
+        process group, 16 bytes per rank all-gathered.  ``(best_nll, best_index)`` in the caller's order."""
+        self._base._ensure_device()
+        return sharded_best_fit(self._base, lambda at, bt, gt, _vi: self.log_likelihood_device(at, bt, gt),
+                                alpha, beta, gamma, group=group, regroup=regroup)
 
 
 class ModelBasedSweep(_TileActionSweep):

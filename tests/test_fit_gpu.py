@@ -398,3 +398,31 @@ def test_scratch_release_between_sweeps(cuda):
     assert _native.lib().nm_scratch_release() == 0
     assert np.array_equal(first, sw.log_likelihood(a, b, g))
 
+
+
+@pytest.mark.parametrize("alg", ["td0", "positive"])
+def test_value_table_sweep_regroups_grids_given_in_any_axis_order(cuda, alg):
+    """A grid with gamma fastest (``parameter_grid(alpha, beta, gamma)``): ConditioningSweep brings sets sharing
+    (alpha, gamma) side by side, the table-per-warp kernel runs, results come back in the caller's order -- bit-identical
+    to the sweep over the arrays as given; best_fit answers in the caller's order and broadcasts scalars."""
+    from navigation_model_b200.sweep import parameter_grid
+    omz = H.oracle_m9()
+    sessions = [O.synthetic_session(omz, sid, T) for sid, T in ((0, 500), (3, 120))]
+    a, b, g = parameter_grid(np.linspace(0.05, 1, 6), np.logspace(-1, 1.5, 64), np.linspace(0.5, 0.99, 5))
+    sw = _sweep(alg, sessions)
+    ll, V = sw.log_likelihood(a, b, g, return_v=True)
+    assert sw.last_sweep_mode() == 1
+    ll_x, V_x = sw.log_likelihood(a, b, g, return_v=True, regroup=False)
+    assert sw.last_sweep_mode() == 2
+    assert np.array_equal(ll, ll_x) and np.array_equal(V, V_x)
+    nll = -(ll[0] + ll[1])
+    v, i = sw.best_fit(a, b, g)
+    assert i == int(np.argmin(nll)) and v == nll[i]
+    assert sw.best_fit(a, b, g, regroup=False) == (v, i)
+    # scalar alpha and gamma against a beta axis (ADVICE r1: only one set was evaluated)
+    betas = np.logspace(-1, 1.5, 40)
+    ll1 = sw.log_likelihood(0.3, betas, 0.9)
+    v1, i1 = sw.best_fit(0.3, betas, 0.9)
+    assert i1 == int(np.argmin(-(ll1[0] + ll1[1]))) and i1 != 0
+    with pytest.raises(ValueError):
+        sw.best_fit([0.1, 0.2], betas, 0.9)

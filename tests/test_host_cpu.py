@@ -257,3 +257,98 @@ def test_ll_exponential_truncation_bound():
     got = p * tab[k & 15] * np.exp2((k >> 4).astype(np.float64))
     rel = np.abs(got - np.exp(x)) / np.exp(x)
     assert rel.max() < 1.5e-13 and got[0] == 1.0  # exp(0) is exact: the largest softmax term carries no error
+
+
+class _FakeBase:
+    """CPU stand-in for the device side of a sweep: the likelihood is a fixed function of the parameters, the arg-min is
+    torch on the CPU.  Lets sharded_best_fit's host logic (broadcast, re-ordering, sharding, tie-break) run anywhere."""
+
+    def __init__(self):
+        import torch
+        self.torch_device = torch.device("cpu")
+
+    @staticmethod
+    def _to_dev(torch, a):
+        return torch.from_numpy(np.ascontiguousarray(a))
+
+    @staticmethod
+    def ll(at, bt, gt, _vi=None):
+        import torch
+        nll = (at - 0.3) ** 2 + (torch.log(bt) - 1.0) ** 2 + (gt - 0.8) ** 2
+        return torch.stack([-0.25 * nll, -0.75 * nll])  # two "sessions"
+
+    @staticmethod
+    def argmin_device(ll, nll_out=None):
+        import torch
+        nll = -(ll[0] + ll[1])
+        if nll_out is not None:
+            nll_out.copy_(nll)
+        best = torch.empty(2, dtype=torch.float64)
+        i = int(torch.argmin(nll))
+        best[0] = nll[i]
+        best[1:].view(torch.int64)[0] = i
+        return best
+
+
+def test_best_fit_broadcasts_scalars_and_validates_lengths():
+    """best_fit with a scalar alpha evaluated one parameter set only.  Scalars broadcast now, like
+    log_likelihood; other length mismatches raise."""
+    from navigation_model_b200.sweep import sharded_best_fit
+    base = _FakeBase()
+    betas = np.logspace(-1, 1.5, 50)
+    v, i = sharded_best_fit(base, base.ll, 0.3, betas, 0.8)
+    assert i == int(np.argmin((np.log(betas) - 1.0) ** 2)) and i != 0
+    with pytest.raises(ValueError):
+        sharded_best_fit(base, base.ll, [0.1, 0.2], betas, 0.8)
+
+
+def test_best_fit_regroups_and_answers_in_the_callers_order():
+    from navigation_model_b200.sweep import parameter_grid, regroup_order, sharded_best_fit
+    base = _FakeBase()
+    a, b, g = parameter_grid(np.linspace(0.1, 1, 7), np.logspace(-1, 1, 64), np.linspace(0.5, 0.9, 3))  # gamma fastest
+    assert regroup_order(a, g) is not None
+    seen = []
+
+    def ll(at, bt, gt, vi=None):
+        seen.append((at.numpy().copy(), gt.numpy().copy()))
+        return base.ll(at, bt, gt)
+
+    v, i = sharded_best_fit(base, ll, a, b, g)
+    A, G = seen[0][0].reshape(-1, 32), seen[0][1].reshape(-1, 32)
+    assert (A == A[:, :1]).all() and (G == G[:, :1]).all()  # the device saw runs of 32 sharing (alpha, gamma)
+    nll = (a - 0.3) ** 2 + (np.log(b) - 1.0) ** 2 + (g - 0.8) ** 2
+    assert i == int(np.argmin(nll))
+    assert sharded_best_fit(base, base.ll, a, b, g, regroup=False)[1] == i
+    # ties go to the lowest index of the CALLER's order, whatever order the device saw
+    a2, b2, g2 = np.tile(a, 2), np.tile(b, 2), np.tile(g, 2)
+    assert sharded_best_fit(base, base.ll, a2, b2, g2)[1] == i
+
+
+def _gloo_best_fit_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from navigation_model_b200.sweep import parameter_grid, sharded_best_fit
+    base = _FakeBase()
+    a, b, g = parameter_grid(np.linspace(0.1, 1, 9), np.logspace(-1, 1, 32), np.linspace(0.5, 0.9, 5))
+    q.put((rank,) + tuple(sharded_best_fit(base, base.ll, a, b, g)))
+    dist.destroy_process_group()
+
+
+def test_sharded_best_fit_world2_gloo():
+    import torch.multiprocessing as mp
+    from navigation_model_b200.sweep import parameter_grid
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_best_fit_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    a, b, g = parameter_grid(np.linspace(0.1, 1, 9), np.logspace(-1, 1, 32), np.linspace(0.5, 0.9, 5))
+    want = int(np.argmin((a - 0.3) ** 2 + (np.log(b) - 1.0) ** 2 + (g - 0.8) ** 2))
+    assert [r[2] for r in res] == [want, want]
