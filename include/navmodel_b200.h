@@ -82,6 +82,10 @@ int nm_mouse_num_actions(const nm_mouse *m);
 int nm_mouse_endpoints(const nm_mouse *m, double *out);
 /* returns 1 if the mouse moved, 0 if new_pos isApprox(pos)  (mouse.cpp:75-87) */
 int nm_mouse_move_to(nm_mouse *m, double x, double y);
+/* n move_to calls in a row, points: [n, 2]; returns what the last one returned.  The replay passes of
+ * PositiveConditioning / NegativeConditioning move the learner's mouse to every replayed arrival point
+ * (rl.py:189, 232): the device launch computes the tables, this call leaves the mouse where the reference does. */
+int nm_mouse_move_through(nm_mouse *m, const double *points, int64_t n);
 int nm_mouse_enable_history(nm_mouse *m, int enable);
 int nm_mouse_reset_history(nm_mouse *m);
 /* init_pos / init_ori may be NULL (= keep)  (mouse.cpp:43-53) */

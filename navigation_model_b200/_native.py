@@ -42,6 +42,7 @@ SIGNATURES = {
     "nm_mouse_history_len": (_i64, [_p]),
     "nm_mouse_history": (C.c_int, [_p, _p, _p]),
     "nm_mouse_adopt_trajectory": (C.c_int, [_p, _p, _p, _i64]),
+    "nm_mouse_move_through": (C.c_int, [_p, _p, _i64]),
     "nm_maze_upload": (_p, [_p, _p, C.c_int, C.c_int, C.c_double, C.c_int, _p]),
     "nm_maze_free": (None, [_p]),
     "nm_maze_num_states": (C.c_int, [_p]),

@@ -211,6 +211,12 @@ int global_tables(int device, void *stream, size_t bytes, double **out) {
   return NM_OK;
 }
 
+size_t global_tables_capacity(int device, void *stream) {
+  std::lock_guard<std::mutex> lock(global_tables_mutex());
+  const auto it = global_tables_map().find(std::make_pair(device, stream));
+  return it == global_tables_map().end() ? 0 : it->second.second;
+}
+
 // NM_FIT_TABLES = "global" / "shared" pins the choice (tests, A/B runs); default: see sweep_alg
 int tables_choice() {
   const char *env = getenv("NM_FIT_TABLES");
@@ -250,6 +256,21 @@ int sweep_global(FitArgs a, int S, int device, cudaStream_t cs) {
   if (max_sets > (int64_t)sms * 896) max_sets = (int64_t)sms * 896;  // one full wave per slice: no partial second wave
   auto kernel = nm_fit_global_kernel<ALG, LL>;
   const size_t smem = (size_t)kFixedBytes;
+  if (a.mode) {
+    // The device is deciding whether the table-per-warp kernel does the work (then every launch below returns at its
+    // first instruction).  Do not GROW the table scratch for launches that may turn out to be no-ops: when the block
+    // kept for this (device, stream) is too small, wait for the decision once and skip this path if the runs are
+    // uniform -- a process that only ever sweeps grids never allocates per-set tables.
+    const int64_t first = a.P < max_sets ? a.P : max_sets;
+    const size_t need = sizeof(double) * (size_t)a.num_states * (size_t)((first + 31) & ~(int64_t)31);
+    if (global_tables_capacity(device, (void *)cs) < need) {
+      int decided = 0;
+      cudaError_t e = cudaStreamSynchronize(cs);
+      if (e == cudaSuccess) e = cudaMemcpy(&decided, a.mode, sizeof(int), cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "sweep: reading the sweep mode: %s", cudaGetErrorString(e));
+      if (decided == 1) return NM_OK;
+    }
+  }
   for (int64_t lo = 0; lo < a.P; lo += max_sets) {
     FitArgs b = a;
     b.P = a.P - lo < max_sets ? a.P - lo : max_sets;
@@ -282,6 +303,13 @@ int sweep_global(FitArgs a, int S, int device, cudaStream_t cs) {
 bool group_enabled() {
   const char *env = getenv("NM_FIT_GROUP");
   return !(env && atoi(env) == 0);
+}
+
+// ONE mutex for every algorithm instantiation of sweep_alg: the mode word is shared per (device, stream), so the
+// "decide / kernels that read the decision" sequences of two host threads must not interleave whatever they sweep.
+std::mutex &fit_launch_mutex() {
+  static std::mutex mu;
+  return mu;
 }
 
 template <int ALG>
@@ -319,8 +347,7 @@ int sweep_alg(bool with_ll, FitArgs a, int S, int device, cudaStream_t cs) {
   const bool try_group = group_enabled() && !a.v_init_per_unit && a.num_states * 8 + kFixedBytes <= kMaxSmem;
   // the decision and the launches that read it reach the stream as one uninterrupted sequence, also when two host
   // threads enqueue sweeps on the same stream
-  static std::mutex launch_mu;
-  std::lock_guard<std::mutex> launch_lock(launch_mu);
+  std::lock_guard<std::mutex> launch_lock(fit_launch_mutex());
   unsigned char *scratch = nullptr;
   rc = stream_scratch((void *)cs, &scratch);
   if (rc != NM_OK) return rc;

@@ -92,6 +92,13 @@ extern "C" int nm_mouse_move_to(nm_mouse *m, double x, double y) {
   return nm_mouse_move_impl(m, x, y);
 }
 
+extern "C" int nm_mouse_move_through(nm_mouse *m, const double *points, int64_t n) {
+  NM_CHECK_ARG(m && n >= 0 && (n == 0 || points), "nm_mouse_move_through: bad argument");
+  int moved = 0;
+  for (int64_t i = 0; i < n; ++i) moved = nm_mouse_move_impl(m, points[2 * i], points[2 * i + 1]);
+  return moved;
+}
+
 extern "C" int nm_mouse_enable_history(nm_mouse *m, int enable) {
   NM_CHECK_ARG(m, "nm_mouse_enable_history: NULL handle");
   m->save_history = enable != 0;

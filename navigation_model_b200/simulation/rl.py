@@ -339,10 +339,18 @@ class ConditioningExperiment:
         all_recs = np.zeros(len(rs._buffer), dtype=_native.STEP_REC_DTYPE)
         for i, u in enumerate(rs._buffer):
             all_recs[i] = sweep.record_from_transition(self._maze, u.transition)
+        arrivals = [u.transition.cs1 for u in rs._buffer]
         orders = rs.next_orders()
         if orders.size == 0:
             return np.zeros(0, dtype=_native.STEP_REC_DTYPE)
-        return all_recs[orders.reshape(-1)]
+        flat = orders.reshape(-1)
+        if self._alg.device_kind != _native.ALG_TD0:
+            # every replayed update of the look-ahead learners ends with mouse.move_to(t.cs1) (rl.py:189, 232): the
+            # tables come from the launch, the learner's mouse (pose, heading, history) is walked through the same
+            # arrival points here, so that a later run() on this experiment starts from the reference's pose
+            pts = np.ascontiguousarray(np.asarray(arrivals, dtype=np.float64).reshape(-1, 2)[flat])
+            _native.check(_native.lib().nm_mouse_move_through(self._alg._mouse._h, _native.np_ptr(pts), len(pts)))
+        return all_recs[flat]
 
     def _replays_device(self):
         recs = self._replay_records()
