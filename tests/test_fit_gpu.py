@@ -407,7 +407,7 @@ def test_value_table_sweep_regroups_grids_given_in_any_axis_order(cuda, alg):
     to the sweep over the arrays as given; best_fit answers in the caller's order and broadcasts scalars."""
     from navigation_model_b200.sweep import parameter_grid
     omz = H.oracle_m9()
-    sessions = [O.synthetic_session(omz, sid, T) for sid, T in ((0, 500), (3, 120))]
+    sessions = [O.synthetic_session(omz, sid, T) for sid, T in ((1, 900), (2, 400))]  # both reach the goal
     a, b, g = parameter_grid(np.linspace(0.05, 1, 6), np.logspace(-1, 1.5, 64), np.linspace(0.5, 0.99, 5))
     sw = _sweep(alg, sessions)
     ll, V = sw.log_likelihood(a, b, g, return_v=True)
@@ -420,7 +420,7 @@ def test_value_table_sweep_regroups_grids_given_in_any_axis_order(cuda, alg):
     assert i == int(np.argmin(nll)) and v == nll[i]
     assert sw.best_fit(a, b, g, regroup=False) == (v, i)
     # scalar alpha and gamma against a beta axis (only one set was evaluated)
-    betas = np.logspace(-1, 1.5, 40)
+    betas = np.logspace(1.5, -1, 40)  # random-walk sessions: the flattest policy fits best -> the LAST set
     ll1 = sw.log_likelihood(0.3, betas, 0.9)
     v1, i1 = sw.best_fit(0.3, betas, 0.9)
     assert i1 == int(np.argmin(-(ll1[0] + ll1[1]))) and i1 != 0
