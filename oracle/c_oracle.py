@@ -69,3 +69,64 @@ def fit(alg, tr, alpha, gamma, n_states, beta=None, v0=None, orders=(), want_v=T
     if rc != 0:
         raise RuntimeError(f"orc_fit failed ({rc})")
     return V, ll
+
+
+def simulate(maze, actions, discrete_actions, kinds, P, init_pose, init_disc, draws, vtable_norm=None, bcost_tables=None,
+             threads=0, history=True):
+    """N mice x T steps with replayed draws through ``orc_simulate`` (the compiled twin of ``np_oracle.simulate``).
+
+    :param maze: ``np_oracle.OracleMaze``
+    :param kinds: component kinds in model order (``np_oracle.COMP_*``)
+    :param P: dict of per-mouse parameter arrays (``beta`` + the reference's parameter names; ``p4`` optional)
+    :param bcost_tables: ``[N, A]`` cached von-Mises values (``np_oracle.bcost_table`` per mouse); computed here if None
+    :return: dict(hist_pos [N,T+1,2], hist_ori [N,T+1], choice [N,T], occupancy [N,X,Y], status [N], final_pose [N,3])
+    """
+    from . import np_oracle as O
+    h = lib()
+    if not hasattr(h, "_sim_ready"):
+        h.orc_simulate.restype = C.c_int
+        h.orc_simulate.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_int64,
+                                   C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 17 + [C.c_int]
+        h._sim_ready = True
+    f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)  # noqa: E731
+    actions = f64(actions).reshape(-1, 2)
+    units = np.asarray(discrete_actions)
+    A = len(actions)
+    zero_act = np.ascontiguousarray(np.all(units == 0, axis=1), dtype=np.uint8)
+    draws = f64(draws)
+    N, T = draws.shape
+    col = lambda *names: f64(np.stack([np.broadcast_to(np.asarray(P[k], dtype=np.float64), (N,)) for k in names], 1))  # noqa: E731
+    anx = bcw = bct = exq = bpq = vtw = vt = None
+    if O.COMP_ANXIETY in kinds:
+        P = dict(P)
+        P.setdefault("p4", np.zeros(N))
+        anx = col("W_anx", "p1", "p2", "p3", "p4")
+    if O.COMP_BCOST in kinds:
+        bcw = f64(np.broadcast_to(P["W_bcost"], (N,)))
+        if bcost_tables is None:
+            k, gm = np.broadcast_to(P["k"], (N,)), np.broadcast_to(P["gamma"], (N,))
+            bcost_tables = np.stack([O.bcost_table(units, k[m], gm[m]) for m in range(N)])
+        bct = f64(bcost_tables)
+    if O.COMP_EXPERIENCE in kinds:
+        exq = col("W_exp", "xi", "kappa_home", "kappa_explo", "theta_explo", "theta_home")
+    if O.COMP_BPERSISTENCE in kinds:
+        bpq = col("W_bper", "bp", "Wm", "Wnm")
+    if O.COMP_VTABLE in kinds:
+        vtw = f64(np.broadcast_to(P["W_values"], (N,)))
+        vt = f64(vtable_norm).reshape(-1)
+    kinds_a = np.ascontiguousarray(kinds, dtype=np.int32)
+    tiles = np.ascontiguousarray(maze.tiles, dtype=np.uint8)
+    pose = f64(init_pose).reshape(N, 3)
+    disc = f64(np.broadcast_to(np.asarray(init_disc, dtype=np.float64), (N, 2)))
+    beta = f64(np.broadcast_to(P["beta"], (N,)))
+    out = {"hist_pos": np.empty((N, T + 1, 2)) if history else None, "hist_ori": np.empty((N, T + 1)) if history else None,
+           "choice": np.empty((N, T), dtype=np.uint8), "occupancy": np.empty((N, maze.X, maze.Y), dtype=np.int32),
+           "status": np.empty(N, dtype=np.int32), "final_pose": np.empty((N, 3))}
+    rc = h.orc_simulate(_ptr(tiles), maze.X, maze.Y, float(maze.st), _ptr(actions), _ptr(zero_act), A, N, T,
+                        _ptr(kinds_a), len(kinds_a), _ptr(beta), _ptr(anx), _ptr(bcw), _ptr(bct), _ptr(exq), _ptr(bpq),
+                        _ptr(vtw), _ptr(vt), _ptr(pose), _ptr(disc), _ptr(draws), _ptr(out["hist_pos"]),
+                        _ptr(out["hist_ori"]), _ptr(out["choice"]), _ptr(out["occupancy"]), _ptr(out["status"]),
+                        _ptr(out["final_pose"]), int(threads))
+    if rc != 0:
+        raise RuntimeError(f"orc_simulate failed ({rc})")
+    return out
