@@ -3,18 +3,24 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--alg positive|td0|negative]
 
-One *step* = one pass of the hot path over one batch: the softmax log-likelihood + value-update sweep of
-this rank's shard of the parameter grid over the session stream, the per-shard arg-min epilogue and the
-all-gather of the per-shard best fits.  Workload at N=1 (``config.workload``): BASELINE.json configs[1]
--- the 64 x 64 x 32 (alpha, beta, gamma) grid = 131 072 parameter sets over one synthetic 5 000-step
-session on the 9x9 test maze with the 8-action set, max-backup learner (PositiveConditioning, i.e.
-Q-learning on deterministic after-states).  Weak scaling: every rank owns a 131 072-set shard (the gamma
-axis grows with N), no data-path collective besides the 16-byte-per-rank gather.
+One *step* = one pass of the hot path over one batch = ``config.sweeps_per_step`` (16) back-to-back fitness sweeps of
+this rank's shard of the parameter grid over the session stream -- each the softmax log-likelihood + value-update
+kernel and the per-shard arg-min epilogue -- followed by ONE all-gather of the per-shard best fits (16 bytes per rank).
+Workload of every sweep at N=1 (``config.workload``): BASELINE.json configs[1] -- the 64 x 64 x 32 (alpha, beta, gamma)
+grid = 131 072 parameter sets over one synthetic 5 000-step session on the 9x9 test maze with the 8-action set,
+max-backup learner (PositiveConditioning, i.e. Q-learning on deterministic after-states).  Sixteen sweeps per step make
+the timed region of the driver's ``--steps 20`` run longer than a second and the exchange (one per step) and the launch
+skew between ranks negligible against the arithmetic.  Weak scaling: every rank owns a 131 072-set shard (the gamma axis
+grows with N), no data-path collective besides the 16-byte-per-rank gather.
 
-Printed JSON (rank 0, one line): the base contract keys + ``roofline`` (FP64-issue bound; the peak is a
-DFMA probe kernel timed live because MEASURED_PEAKS.json has no FP64 figure) + ``cpu_baseline`` (the C
-oracle port on the box's host cores, bounded sample) + ``e2e`` (host buffers, H2D/D2H inside the timed
-region) + ``clocks``.  ``--impl reference`` times the CPU port alone, same metric/config.
+Printed JSON (rank 0, one line): the base contract keys + ``roofline`` (FP64-issue bound: EXECUTED FP64 instructions
+per launch -- ncu's ``sm__inst_executed_pipe_fp64.sum`` x 32 lanes, taken from profiles/ncu_counts.json and only when the
+kernel sources and the workload still hash to what was profiled -- over the live kernel time, against a DFMA probe kernel
+timed live because MEASURED_PEAKS.json has no FP64 figure; the canonical SURVEY 8(d) accounting rides along) +
+``cpu_baseline`` (the C oracle port on the box's host cores, bounded sample) + ``e2e`` (host buffers, H2D/D2H of every
+sweep inside the timed region) + ``clocks`` + ``config0`` (BASELINE configs[0]: one parameter set, the log-likelihood
+value on the GPU and on one host core) + ``also_measured`` (per-GPU shards of configs[2], [3], [4] and the Q-table
+agent, each with its own ``roofline`` block).  ``--impl reference`` times the CPU port alone, same metric/config.
 """
 import argparse
 import json
@@ -31,6 +37,7 @@ if ROOT not in sys.path:
 
 T_STEPS = 5000
 GRID = (64, 64, 32)
+SWEEPS_PER_STEP = int(os.environ.get("NM_BENCH_SWEEPS_PER_STEP", 16))
 CANON_EXP, CANON_LOG = 20, 30  # canonical FP64-instruction accounting of exp / log
 
 
@@ -124,28 +131,61 @@ def measured_hbm_peak():
         return 6650.0  # fallback stated in B200_PROFILING.md
 
 
-NCU_SUMMARY = os.path.join(ROOT, "profiles", "r01_final_fit_group_deg5_kernel_ncu.txt")
+NCU_COUNTS = os.path.join(ROOT, "profiles", "ncu_counts.json")
+CSRC = os.path.join(ROOT, "navigation_model_b200", "csrc")
+#: the sources whose content decides a kernel's instruction stream (hashed into profiles/ncu_counts.json by
+#: tools/ncu_counts.py when it profiles; a mismatch here means the committed counters are STALE and are not used)
+KERNEL_SOURCES = {
+    "fit": ["nm_fit_kernels.cuh", "nm_fit.cu", "nm_exp.cuh", "nm_step_math.cuh", "nm_ring.cuh"],
+    "sim": ["nm_sim.cu", "nm_simgeom.cuh", "nm_exp.cuh", "nm_pose.h", "nm_geometry.h", "nm_libm.cuh"],
+    "mb": ["nm_mb.cu", "nm_group.cuh", "nm_exp.cuh", "nm_step_math.cuh"],
+    "q": ["nm_q.cu", "nm_group.cuh", "nm_exp.cuh", "nm_step_math.cuh", "nm_ring.cuh"],
+}
 
 
-def ncu_counter(prefixes, scale_units=False):
-    """Sum of the counters whose line starts with one of `prefixes` in the committed `ncu --set full` summary of the
-    dominant kernel (same command, profiles/); None if the summary is missing."""
+def source_sha(kind):
+    import hashlib
+    h = hashlib.sha256()
+    for name in KERNEL_SOURCES[kind]:
+        path = os.path.join(CSRC, name)
+        if os.path.exists(path):
+            h.update(name.encode())
+            h.update(open(path, "rb").read())
+    return h.hexdigest()[:16]
+
+
+def ncu_counts(key, kind):
+    """Per-launch hardware counters of one kernel on one bench workload, captured by `ncu` (tools/ncu_counts.py, the
+    raw csv next to it under profiles/).  Instruction and byte COUNTS of a deterministic kernel on a seeded workload do
+    not depend on the run, so they may be combined with a live time -- but only while the kernel is the one that was
+    profiled: the entry carries the hash of the kernel's sources and is ignored (None) when that no longer matches."""
     try:
-        total, seen = 0.0, False
-        for line in open(NCU_SUMMARY):
-            if any(line.startswith(p + " [") for p in prefixes):
-                unit = line.split("[")[1].split("]")[0]
-                val = float(line.split("=")[1])
-                total += val * ({"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit] if scale_units else 1.0)
-                seen = True
-        return total if seen else None
+        entry = json.load(open(NCU_COUNTS))[key]
     except Exception:
         return None
+    if entry.get("source_sha") != source_sha(kind):
+        return None
+    return entry
 
 
-def ncu_dram_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the fit kernel, per launch."""
-    return ncu_counter(["dram__bytes_read.sum", "dram__bytes_write.sum"], scale_units=True)
+def executed_roofline(entry, units, seconds, peak_ginstr):
+    """FP64-issue block from ncu counts scaled to `units` of work done in `seconds` (live)."""
+    if entry is None:
+        return {"executed_frac": None, "ncu": "profiles/ncu_counts.json has no entry for this kernel build (stale or "
+                                              "missing): re-run tools/ncu_counts.py"}
+    per_unit = 1.0 / entry["units_per_launch"]
+    fp64 = entry["sm__inst_executed_pipe_fp64.sum"] * 32.0 * per_unit  # thread-level FP64 instructions per unit
+    out = {"executed_frac": fp64 * units / seconds / 1e9 / peak_ginstr,
+           "executed_fp64_instr_per_unit_ncu": fp64,
+           "executed_instr_per_unit_ncu": entry["smsp__inst_executed.sum"] * 32.0 * per_unit,
+           "dram_bytes_per_unit_ncu": (entry["dram__bytes_read.sum"] + entry["dram__bytes_write.sum"]) * per_unit,
+           "l2_bytes_per_unit_ncu": entry.get("lts__t_bytes.sum", 0.0) * per_unit,
+           "lsu_wavefronts_per_unit_ncu": entry.get("l1tex__data_pipe_lsu_wavefronts.sum", 0.0) * per_unit,
+           "fp64_pipe_busy_when_profiled": entry.get("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+           "issue_slots_busy_when_profiled": entry.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+           "ncu": f"profiles/ncu_counts.json[{entry.get('key', '?')}] ({entry.get('captured', '?')}), sources "
+                  f"{entry.get('source_sha')}"}
+    return out
 
 
 def oracle_transitions(traj, rew):
@@ -174,6 +214,36 @@ def cpu_port_rate(records_tr, alg_code, a, b, g, seconds, threads=0):
     return P * n / dt, f"{P} of {len(a)} parameter sets (evenly spaced over the grid) x {n} steps, {dt:.1f} s", cores
 
 
+def cpu_port_sim_rate(seconds=3.0):
+    """The compiled CPU port of the forward simulation (oracle/nm_oracle.c:orc_simulate, OpenMP over mice, all host
+    threads) on a bounded sample of the configs[4] population: agent-steps/s.  cpu_baseline leg of also_measured."""
+    from oracle import c_oracle as CO
+    from oracle import np_oracle as O
+    from scipy.stats import vonmises
+    omz = O.OracleMaze(O.M9_LAYOUT, O.M9_SIZE_TILE)
+    rng = np.random.default_rng(5)
+    N, T = 2048, 1000
+    P = sim_population(rng, N)
+    angles = np.arctan2(O.A8_UNITS[:, 1], O.A8_UNITS[:, 0])
+    tabs = vonmises.pdf(angles[None, :], P["k"][:, None])
+    tabs[:, 0] = 0.0
+    tabs[:, 2] = tabs[:, 2] * P["gamma"]
+    pose = np.concatenate([np.array(omz.centre((1, 1)))[None, :] + rng.uniform(-0.03, 0.03, (N, 2)),
+                           rng.uniform(-3, 3, (N, 1))], axis=1)
+    draws = rng.random((N, T))
+    cores = host_threads()
+    kinds = [O.COMP_ANXIETY, O.COMP_BCOST, O.COMP_EXPERIENCE, O.COMP_BPERSISTENCE, O.COMP_VTABLE]
+    V = O.normalise_vtable(rng.random((9, 9)))
+    done, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        CO.simulate(omz, O.A8_UNITS * O.M9_SIZE_TILE, O.A8_UNITS, kinds, P, pose, (1, 1), draws, vtable_norm=V,
+                    bcost_tables=tabs, threads=cores, history=False)
+        done += N * T
+    dt = time.perf_counter() - t0
+    return {"value": done / dt, "unit": "agent-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{done // (N * T)} x ({N} mice x {T} steps, replayed draws, five components), {dt:.1f} s"}
+
+
 def run_reference(args):
     """--impl reference: the CPU port of the path (oracle/nm_oracle.c, OpenMP over parameter sets) on the
     box's host cores; each step is a bounded sample of the workload."""
@@ -196,13 +266,16 @@ def run_reference(args):
         CO.fit(alg_code, tr, a[idx], g[idx], 60, beta=b[idx], want_v=False, threads=cores)
     dt = time.perf_counter() - t0
     value = P_s * n * args.steps / dt
+    sample = (f"each step = ONE sweep of {P_s} of the job's {len(a)} parameter sets (evenly spaced over the grid) x {n} "
+              f"steps on {cores} host threads; the GPU arm's step is {SWEEPS_PER_STEP} sweeps of all its sets -- rates "
+              "are per update, hence comparable")
+    config = workload_config(args, world, len(a) // world)  # the product arm's config, word for word ...
+    config["reference_arm_sample"] = sample  # ... plus what this arm's step is
     line = {"impl": "reference", "metric": "agent-trial updates/s (fitness grid sweep)", "value": value,
             "unit": "updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, world, len(a) // world),  # the product arm's config, word for word
-            "cpu_baseline": {"value": value, "unit": "updates/s", "cores": cores, "kind": "port",
-                             "sample": f"{P_s} of {len(a)} parameter sets (evenly spaced) x {n} steps per step"},
+            "dtype": "f64", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": value, "unit": "updates/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -213,22 +286,58 @@ def workload_config(args, n_gpus, p_per_rank):
                         "64x64x32 (alpha,beta,gamma) over one synthetic 5000-step session, 9x9 maze, 8 actions"
                         if args.alg == "positive" else f"configs[1] grid sweep with {args.alg}",
             "algorithm": args.alg, "parameter_sets_per_gpu": int(p_per_rank), "sessions": 1, "steps_per_session": T_STEPS,
-            "sharding": f"parameter grid, {n_gpus} contiguous shard(s); all-gather of 16 B/rank best fits",
+            "sweeps_per_step": SWEEPS_PER_STEP,
+            "step": f"{SWEEPS_PER_STEP} back-to-back sweeps of the workload (kernel + arg-min each), then one exchange",
+            "sharding": f"parameter grid, {n_gpus} contiguous shard(s); all-gather of 16 B/rank best fits, once per step",
             "l2": "flushed between timed steps (256 MiB memset, untimed)"}
 
 
-def other_paths(local, world, rank, dist, dev):
-    """The other kernels of the hot path, measured the same way (per-rank shard of fixed size, device time as the
-    max over ranks): forward simulation (BASELINE configs[4] shape, scaled to 909 312 mice x 1 000 steps per GPU, all
-    five components, device-seeded PCG64 streams, fused metrics) and the model-based agent (configs[3] shape: 400-state
-    maze, 8 actions, 20 000 parameter sets x 1 000 steps per GPU, one value-iteration sweep per step) and the Q-table agent
-    (the configs[1] grid and session).  Reported under
-    ``also_measured``; the headline metric stays the fitness grid sweep."""
+def fp64_peak(torch, dev, stream):
+    """FP64 issue peak in G thread-instructions/s: a DFMA probe kernel (8 independent chains per thread) timed live."""
+    import ctypes as C
+    from navigation_model_b200 import _native
+    sink = torch.zeros(1, dtype=torch.float64, device=dev)
+    n_instr = C.c_int64(0)
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    probe_ms = []
+    for it in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        _native.check(_native.lib().nm_fp64_peak_probe(sms * 4, 512, 20000, _native.tensor_ptr(sink), C.byref(n_instr),
+                                                       _native.cuda_stream_ptr()))
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if it:
+            probe_ms.append(e0.elapsed_time(e1))
+    return n_instr.value / (min(probe_ms) * 1e-3) / 1e9
+
+
+def sim_population(rng, N):
+    u = rng.uniform
+    return {"beta": u(0.5, 6, N), "W_anx": u(0, 10, N), "p1": u(0, 1, N), "p2": u(0, 1, N), "p3": u(0, 1, N),
+            "W_bcost": u(0, 10, N), "k": u(0.05, 4, N), "gamma": u(0.2, 2, N), "W_exp": u(0, 10, N),
+            "xi": u(0.006, 0.6, N), "kappa_home": u(0.01, 5, N), "kappa_explo": u(0.01, 5, N),
+            "theta_explo": u(80, 120, N), "theta_home": u(30, 70, N), "W_bper": u(0, 10, N), "bp": u(0, 1, N),
+            "Wm": u(0, 2, N), "Wnm": u(0, 2, N), "W_values": u(0, 10, N)}
+
+
+def other_paths(args, local, world, rank, dist, dev, peak_ginstr, sw1):
+    """Per-GPU shards of the other BASELINE configs, measured the same way (fixed work per rank, device time as the max
+    over ranks), each with its own roofline block: configs[2] (64^3 parameter sets x 100 sessions of 5 000 steps per
+    GPU = the 8-GPU shard of the 128^3 grid), configs[3] (model-based agent, 400-state maze, 10^5 parameter sets x 5 000
+    steps, arbitrary sets and a beta-fastest grid), configs[4] (forward simulation, 10^6 mice x 10^4 steps, five
+    components, device-seeded PCG64, fused metrics), the explicit Q-table agent and the headline grid in a random
+    order.  ``NM_BENCH_SMALL=1`` shrinks every workload (smoke runs)."""
     import torch
     from navigation_model_b200.batched_sim import BatchedExperiment
     from navigation_model_b200.simulation import behavioural_components as bc
     from navigation_model_b200 import workloads as W
-    from navigation_model_b200.sweep import ModelBasedSweep, QLearningSweep, parameter_grid
+    from navigation_model_b200.sweep import ConditioningSweep, ModelBasedSweep, QLearningSweep, parameter_grid
+
+    small = os.environ.get("NM_BENCH_SMALL") == "1"
+    stream = torch.cuda.current_stream()
+    sm_clk_hz = 1.965e9
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
 
     def max_over_ranks(x):
         t = torch.tensor([x], dtype=torch.float64, device=dev)
@@ -236,17 +345,104 @@ def other_paths(local, world, rank, dist, dev):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def timed(fn, reps=2):
+        """min over `reps` of (device ms between two events around fn, host seconds around fn + synchronize)."""
+        k_ms, e2e_s = [], []
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            e2e_s.append(time.perf_counter() - t0)
+            k_ms.append(e0.elapsed_time(e1))
+        return max_over_ranks(min(k_ms)) * 1e-3, max_over_ranks(min(e2e_s))
+
     out = {}
-    # ---- forward simulation -----------------------------------------------------------------------------
     maze = W.maze_m9()
+    # ---- configs[2] shard: 64^3 parameter sets x 100 sessions -------------------------------------------------------
+    G, S2 = (16, 4) if small else (64, 100)
+    sw = ConditioningSweep(maze, args.alg, possible_actions=W.a8(), device=local)
+    for sid in range(S2):
+        sw.add_session(*W.synthetic_session(maze, sid, T_STEPS))
+    sw.upload()
+    g2, a2, b2 = parameter_grid(np.linspace(0.5, 0.99, G), np.linspace(0.01, 1.0, G), np.logspace(-1.0, 1.5, max(G, 32)))
+    a_t, b_t, g_t = (torch.from_numpy(x).to(dev) for x in (a2, b2, g2))
+    ll2 = torch.empty((S2, a2.size), dtype=torch.float64, device=dev)
+
+    def config2():
+        sw.log_likelihood_device(a_t, b_t, g_t, ll_out=ll2)
+        sw.argmin_device(ll2)
+
+    config2()  # warm-up
+    k, _ = timed(config2)
+    upd = float(world) * a2.size * sw.updates_per_parameter_set
+    canon = sum(algorithmic_fp64(r, n_on, args.alg) for r, n_on in zip(sw._records, sw._online)) * float(a2.size)
+    entry = ncu_counts(f"fit_group_{args.alg}_configs1", "fit")
+    rf = {"bound": "fp64_issue", "unit": "GInstr/s", "peak": peak_ginstr, "canonical_achieved": canon * world / k / 1e9,
+          "canonical_frac": canon / k / 1e9 / peak_ginstr}
+    rf.update(executed_roofline(entry, upd / world, k, peak_ginstr))
+    rf["frac"] = rf["executed_frac"] if rf["executed_frac"] is not None else rf["canonical_frac"]
+    rf["achieved"] = rf["frac"] * peak_ginstr
+    rf["note"] = ("executed instructions per update as profiled on the configs[1] session (the 100 sessions differ in "
+                  "their candidate counts by a few per cent)")
+    out["config2_shard"] = {
+        "metric": "agent-trial updates/s", "value": upd / k, "seconds": k, "sweep_mode": sw.last_sweep_mode(),
+        "workload": f"per GPU: {G}^2 x {max(G, 32)} = {a2.size} parameter sets x {S2} synthetic sessions x {T_STEPS} steps in ONE "
+                    "launch + arg-min over the session sums (BASELINE configs[2] = 128^3 sets x 100 sessions on 8 GPUs "
+                    "is eight of these shards)",
+        "roofline": rf}
+    del sw, ll2
+    # ---- configs[3]: model-based agent --------------------------------------------------------------------------------
+    acts = W.MOVES8
+    maze20 = W.maze_m20()
     rng = np.random.default_rng(1000 + rank)
-    N, T = 148 * 6 * 128 * 8, 1000  # eight full waves of the kernel's residency (6 CTAs of 128 mice per SM)
-    u = rng.uniform
-    P = {"beta": u(0.5, 6, N), "W_anx": u(0, 10, N), "p1": u(0, 1, N), "p2": u(0, 1, N), "p3": u(0, 1, N),
-         "W_bcost": u(0, 10, N), "k": u(0.05, 4, N), "gamma": u(0.2, 2, N), "W_exp": u(0, 10, N),
-         "xi": u(0.006, 0.6, N), "kappa_home": u(0.01, 5, N), "kappa_explo": u(0.01, 5, N),
-         "theta_explo": u(80, 120, N), "theta_home": u(30, 70, N), "W_bper": u(0, 10, N), "bp": u(0, 1, N),
-         "Wm": u(0, 2, N), "Wnm": u(0, 2, N), "W_values": u(0, 10, N)}
+    Tm, Pm, Gm = (500, 4096, 8) if small else (T_STEPS, 100000, 56)
+    traj, rew = W.synthetic_session(maze20, 0, Tm, start=(3, 3), goal=(15, 12), jitter=0.02)
+    a, b, g = rng.uniform(0.01, 1, Pm), np.exp(rng.uniform(np.log(0.1), np.log(30), Pm)), rng.uniform(0.5, 0.99, Pm)
+    mb = ModelBasedSweep(maze20, acts, n_sweeps=1, device=local)
+    mb.add_session(traj, rew)
+    peak_wavefronts = sms * sm_clk_hz  # one LSU wavefront per SM and clock
+
+    def mb_block(name, aa, bb, gg, key, what):
+        mb.log_likelihood(aa, bb, gg)
+        k_ms, e2e_s = [], []
+        for _ in range(2):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            mb.log_likelihood(aa, bb, gg)
+            e2e_s.append(time.perf_counter() - t0)
+            k_ms.append(mb.last_kernel_ms)
+        k, e = max_over_ranks(min(k_ms)) * 1e-3, max_over_ranks(min(e2e_s))
+        upd = float(world) * aa.size * mb.updates_per_parameter_set
+        entry = ncu_counts(key, "mb")
+        rf = {"bound": "shared-memory bandwidth (LSU wavefronts)", "unit": "Gwavefronts/s", "peak": peak_wavefronts / 1e9}
+        ex = executed_roofline(entry, upd / world, k, peak_ginstr)
+        if entry is not None:
+            rf["achieved"] = ex["lsu_wavefronts_per_unit_ncu"] * (upd / world) / k / 1e9
+            rf["frac"] = rf["achieved"] / rf["peak"]
+            rf["fp64_issue_frac"] = ex["executed_frac"]
+        else:
+            rf["achieved"] = rf["frac"] = None
+        rf.update({kk: vv for kk, vv in ex.items() if kk != "executed_frac"})
+        out[name] = {"metric": "agent-trial updates/s", "value": upd / k, "e2e_value": upd / e, "seconds": k,
+                     "sweep_mode": mb.last_sweep_mode(), "state_action_backups_per_s": upd * 400 * 8 / k,
+                     "workload": what, "roofline": rf}
+
+    mb_block("config3_model_based", a, b, g, "mb_arbitrary_config3",
+             f"per GPU: {Pm} ARBITRARY parameter sets x {mb.updates_per_parameter_set} steps, 400-state maze, 8 actions, 1 "
+             "value-iteration sweep per step, a warp per parameter set (BASELINE configs[3]; extension: parity against "
+             "this repo's numpy oracle only)")
+    ag, gg, bg = parameter_grid(np.linspace(0.01, 1, Gm), np.linspace(0.5, 0.99, Gm), np.logspace(-1, 1.5, 32))
+    mb_block("config3_model_based_grid", ag, bg, gg, "mb_grid_config3",
+             f"per GPU: {ag.size} parameter sets = {Gm} x {Gm} (alpha, gamma) x 32 beta, beta fastest, x "
+             f"{mb.updates_per_parameter_set} steps, same maze: tables and planning sweeps once per run of 32 sets")
+    del mb
+    # ---- configs[4]: forward simulation -------------------------------------------------------------------------------
+    N, T = (148 * 6 * 128, 500) if small else (1000000, 10000)
+    P = sim_population(rng, N)
     exp = BatchedExperiment(maze, W.a8(), W.A8_UNITS,
                             [bc.AnxietyComponent, bc.BiomechanicalCostComponent, bc.ExperienceComponent,
                              bc.BiomechPersistenceComponent, bc.ValueTableComponent], v_table=rng.random((9, 9)),
@@ -254,85 +450,120 @@ def other_paths(local, world, rank, dist, dev):
     pos0 = np.array(maze.get_tile_centre(1, 1)) + rng.uniform(-0.03, 0.03, (N, 2))
     ori0 = rng.uniform(-3, 3, N)
     k_ms, e2e_s = [], []
-    for rep in range(3):
+    for rep, steps in enumerate((max(T // 100, 10), T, T)):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        res = exp.run(P, T, pos0, ori0, init_disc=(1, 1), device_seed=77 + rep, n_mice=N, occupancy_total=True,
+        res = exp.run(P, steps, pos0, ori0, init_disc=(1, 1), device_seed=77 + rep, n_mice=N, occupancy_total=True,
                       shock_zone={"tile_lines": 5}, corridors=(1, 7), static_intervals=True, subareas=True,
                       orientation_histogram={}, mouse_index_base=rank * N)  # this rank's block of world * N mice
-        e2e_s.append(time.perf_counter() - t0)
-        k_ms.append(exp.last_kernel_ms)
-    k = max_over_ranks(min(k_ms[1:])) * 1e-3
-    e = max_over_ranks(min(e2e_s[1:]))
-    out["forward_simulation"] = {
-        "metric": "agent-steps/s", "value": world * N * T / k, "e2e_value": world * N * T / e, "kernel_ms": k * 1e3,
-        "workload": f"{N} mice x {T} steps per GPU, 9x9 maze, 8 actions, 5 components, device-seeded PCG64, fused "
-                    "occupancy / exploration / orientation / shock-zone metrics; e2e includes host parameter "
-                    "preparation, H2D and D2H of every per-mouse result",
-        "mice_ok": int((res.status == 0).sum())}
-    # ---- model-based agent ------------------------------------------------------------------------------
-    acts = W.MOVES8
-    maze20 = W.maze_m20()
-    traj, rew = W.synthetic_session(maze20, 0, 1000, start=(3, 3), goal=(15, 12), jitter=0.02)
-    Pm = 20000
-    a, b, g = rng.uniform(0.01, 1, Pm), np.exp(rng.uniform(np.log(0.1), np.log(30), Pm)), rng.uniform(0.5, 0.99, Pm)
-    mb = ModelBasedSweep(maze20, acts, n_sweeps=1, device=local)
-    mb.add_session(traj, rew)
-    k_ms, e2e_s = [], []
-    for rep in range(3):
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        mb.log_likelihood(a, b, g)
-        e2e_s.append(time.perf_counter() - t0)
-        k_ms.append(mb.last_kernel_ms)
-    k = max_over_ranks(min(k_ms[1:])) * 1e-3
-    e = max_over_ranks(min(e2e_s[1:]))
-    upd = world * Pm * mb.updates_per_parameter_set
-    out["model_based"] = {
-        "metric": "agent-trial updates/s", "value": upd / k, "e2e_value": upd / e, "kernel_ms": k * 1e3,
-        "state_action_backups_per_s": upd * 400 * 8 / k,
-        "workload": f"{Pm} ARBITRARY parameter sets x {mb.updates_per_parameter_set} steps per GPU, 400-state maze, 8 "
-                    "actions, 1 value-iteration sweep per step, a warp per parameter set (extension: parity against "
-                    "this repo's numpy oracle only)"}
-    # the same agent on a Cartesian grid with beta fastest: runs of 32 sets share (alpha, gamma), hence V, Rhat and the
-    # planning sweeps -- a warp per run
-    ag, gg, bg = parameter_grid(np.linspace(0.01, 1, 25), np.linspace(0.5, 0.99, 25), np.logspace(-1, 1.5, 32))
-    k_ms, e2e_s = [], []
-    for rep in range(3):
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        mb.log_likelihood(ag, bg, gg)
-        e2e_s.append(time.perf_counter() - t0)
-        k_ms.append(mb.last_kernel_ms)
-    k = max_over_ranks(min(k_ms[1:])) * 1e-3
-    e = max_over_ranks(min(e2e_s[1:]))
-    upd = world * ag.size * mb.updates_per_parameter_set
-    out["model_based_grid"] = {
-        "metric": "agent-trial updates/s", "value": upd / k, "e2e_value": upd / e, "kernel_ms": k * 1e3,
-        "sweep_mode": mb.last_sweep_mode(),
-        "workload": f"{ag.size} parameter sets = 25 x 25 (alpha, gamma) x 32 beta, beta fastest, x "
-                    f"{mb.updates_per_parameter_set} steps per GPU, same maze: tables and sweeps once per run of 32 sets"}
-    # ---- Q-table agent ------------------------------------------------------------------------------------
+        if rep:
+            e2e_s.append(time.perf_counter() - t0)
+            k_ms.append(exp.last_kernel_ms)
+    k, e = max_over_ranks(min(k_ms)) * 1e-3, max_over_ranks(min(e2e_s))
+    steps_done = float(world) * N * T
+    entry = ncu_counts("sim_config4", "sim")
+    canon = 1.0e3  # ~1e3 FP64 instructions per agent-step (canonical)
+    rf = {"bound": "fp64_issue", "unit": "GInstr/s", "peak": peak_ginstr, "canonical_instr_per_agent_step": canon,
+          "canonical_frac": canon * N * T / k / 1e9 / peak_ginstr}
+    rf.update(executed_roofline(entry, float(N) * T, k, peak_ginstr))
+    rf["frac"] = rf["executed_frac"] if rf["executed_frac"] is not None else rf["canonical_frac"]
+    rf["achieved"] = rf["frac"] * peak_ginstr
+    out["config4_forward_simulation"] = {
+        "metric": "agent-steps/s", "value": steps_done / k, "e2e_value": steps_done / e, "seconds": k, "e2e_seconds": e,
+        "workload": f"per GPU: {N} mice x {T} steps (BASELINE configs[4]), 9x9 maze, 8 actions, 5 components, device-seeded "
+                    "PCG64, fused occupancy / exploration / orientation / shock-zone metrics; e2e includes host "
+                    "parameter preparation, H2D and D2H of every per-mouse result",
+        "mice_ok": int((res.status == 0).sum()), "roofline": rf}
+    del exp, res
+    # ---- Q-table agent (extension) --------------------------------------------------------------------------------------
     traj9, rew9 = W.synthetic_session(maze, 0, T_STEPS)
-    gq, aq, bq = parameter_grid(np.linspace(0.5, 0.99, 32), np.linspace(0.01, 1, 64), np.logspace(-1, 1.5, 64))
+    Gq = 16 if small else 64
+    gq, aq, bq = parameter_grid(np.linspace(0.5, 0.99, Gq // 2), np.linspace(0.01, 1, Gq), np.logspace(-1, 1.5, 64))
     ql = QLearningSweep(maze, acts, device=local)
     ql.add_session(traj9, rew9)
+    ql.log_likelihood(aq, bq, gq)
     k_ms, e2e_s = [], []
-    for rep in range(3):
+    for _ in range(2):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         ql.log_likelihood(aq, bq, gq)
         e2e_s.append(time.perf_counter() - t0)
         k_ms.append(ql.last_kernel_ms)
-    k = max_over_ranks(min(k_ms[1:])) * 1e-3
-    e = max_over_ranks(min(e2e_s[1:]))
-    upd = world * aq.size * ql.updates_per_parameter_set
+    k, e = max_over_ranks(min(k_ms)) * 1e-3, max_over_ranks(min(e2e_s))
+    upd = float(world) * aq.size * ql.updates_per_parameter_set
+    entry = ncu_counts("q_group_configs1", "q")
+    rf = {"bound": "fp64_issue", "unit": "GInstr/s", "peak": peak_ginstr}
+    rf.update(executed_roofline(entry, upd / world, k, peak_ginstr))
+    rf["frac"] = rf["executed_frac"]
+    rf["achieved"] = None if rf["frac"] is None else rf["frac"] * peak_ginstr
     out["q_table"] = {
-        "metric": "agent-trial updates/s", "value": upd / k, "e2e_value": upd / e, "kernel_ms": k * 1e3,
-        "workload": f"{aq.size} parameter sets (the configs[1] grid) x {ql.updates_per_parameter_set} steps per GPU, "
-                    "9x9 maze, 8 tile actions, explicit Q[s,a] table in shared memory (extension: parity against this "
-                    "repo's numpy oracle only)"}
+        "metric": "agent-trial updates/s", "value": upd / k, "e2e_value": upd / e, "seconds": k,
+        "workload": f"per GPU: {aq.size} parameter sets (the configs[1] grid) x {ql.updates_per_parameter_set} steps, 9x9 "
+                    "maze, 8 tile actions, explicit Q[s,a] table, one table per warp (extension: parity against this "
+                    "repo's numpy oracle only)", "roofline": rf}
+    del ql
+    # ---- the headline grid in a random order: a table per parameter set, in device memory ------------------------------
+    P1 = sw1["P"]
+    flush = sw1["flush"]
+    perm = torch.from_numpy(np.random.default_rng(7 + rank).permutation(P1)).to(dev)
+    a_p, b_p, g_p = sw1["a_t"][perm], sw1["b_t"][perm], sw1["g_t"][perm]
+    k_ms = []
+    for rep in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        flush.zero_()
+        e0.record(stream)
+        sw1["sw"].log_likelihood_device(a_p, b_p, g_p, ll_out=sw1["ll_t"])
+        e1.record(stream)
+        torch.cuda.synchronize()
+        k_ms.append(e0.elapsed_time(e1))
+    mode_p = sw1["sw"].last_sweep_mode()
+    k = max_over_ranks(min(k_ms[1:])) * 1e-3
+    upd = float(world) * P1 * sw1["n_upd"]
+    entry = ncu_counts(f"fit_global_{args.alg}_configs1", "fit")
+    rf = {"bound": "fp64_issue", "unit": "GInstr/s", "peak": peak_ginstr}
+    rf.update(executed_roofline(entry, upd / world, k, peak_ginstr))
+    rf["frac"] = rf["executed_frac"]
+    rf["achieved"] = None if rf["frac"] is None else rf["frac"] * peak_ginstr
+    out["fit_arbitrary_parameter_sets"] = {
+        "metric": "agent-trial updates/s", "value": upd / k, "seconds": k, "sweep_mode": mode_p,
+        "workload": "the headline grid in a random order (no run of 32 sets shares alpha and gamma): one value table per "
+                    "parameter set, in device memory", "roofline": rf}
     return out
+
+
+def cpu_baseline_config0(args, local, dev, traj, rew, tr):
+    """BASELINE configs[0]: ONE parameter set (alpha 0.1, beta 2.0, gamma 0.9) over the benchmark session -- the
+    log-likelihood value from the GPU, from the C port and from the pure-Python port on one host core, with their
+    rates.  (The Python REFERENCE itself cannot run on the GPU box: /root/reference exists in the build container only;
+    its own per-step cost there is in BASELINE.md.)"""
+    import torch
+    from navigation_model_b200 import workloads as W
+    from navigation_model_b200.sweep import ConditioningSweep
+    from oracle import c_oracle as CO
+    from oracle import np_oracle as O
+    alg_code = {"td0": 0, "positive": 1, "negative": 2}[args.alg]
+    a, b, g = np.array([0.1]), np.array([2.0]), np.array([0.9])
+    sw = ConditioningSweep(W.maze_m9(), args.alg, possible_actions=W.a8(), device=local)
+    sw.add_session(traj, rew)
+    sw.log_likelihood(a, b, g)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ll_gpu = float(sw.log_likelihood(a, b, g)[0, 0])
+    t_gpu = time.perf_counter() - t0
+    n = len(tr["s"])
+    t0 = time.perf_counter()
+    reps = 20
+    for _ in range(reps):
+        _, ll_c = CO.fit(alg_code, tr, a, g, 60, beta=b, want_v=False, threads=1)
+    t_c = (time.perf_counter() - t0) / reps
+    t0 = time.perf_counter()
+    _, ll_py = O.run_session(alg_code, tr, 0.1, 0.9, 60, beta=2.0)
+    t_py = time.perf_counter() - t0
+    return {"workload": "BASELINE configs[0]: one parameter set (alpha 0.1, beta 2.0, gamma 0.9), one 5000-step session",
+            "log_likelihood_gpu": ll_gpu, "log_likelihood_c_port": float(ll_c[0]), "log_likelihood_python_port": float(ll_py),
+            "rel_diff_gpu_vs_c_port": abs(ll_gpu - float(ll_c[0])) / abs(float(ll_c[0])),
+            "updates_per_s": {"gpu_single_set_call_incl_copies": n / t_gpu, "c_port_1_core": n / t_c,
+                              "python_port_1_core": n / t_py}}
 
 
 def run_b200(args):
@@ -358,77 +589,108 @@ def run_b200(args):
     records = sw._records[0]
     n_upd = sw.updates_per_parameter_set
     h2d_stream_bytes = sw.upload()
+    R = SWEEPS_PER_STEP
 
     # resident device inputs / outputs
     a_t, b_t, g_t = (torch.from_numpy(x).to(dev) for x in (a, b, g))
     ll_t = torch.empty((1, P), dtype=torch.float64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
+    gathered = torch.empty(world * 2, dtype=torch.float64, device=dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident():
-        sw.log_likelihood_device(a_t, b_t, g_t, ll_out=ll_t)
-        best = sw.argmin_device(ll_t)
-        return reduce_best_device(best, lo, world, dist)
-
-    def reduce_best_device(best, offset, world, dist):
+    def exchange(best):
         if world > 1:
-            gathered = torch.empty(world * 2, dtype=torch.float64, device=dev)
             dist.all_gather_into_tensor(gathered, best)
             return gathered
         return best
 
+    def step_resident(ev=None):
+        """One step with inputs resident in HBM: R sweeps (kernel + arg-min each), then one exchange."""
+        for r in range(R):
+            if ev is not None:
+                ev["k0"][r].record(stream)
+            sw.log_likelihood_device(a_t, b_t, g_t, ll_out=ll_t)
+            if ev is not None:
+                ev["k1"][r].record(stream)  # end of the dominant kernel
+            best = sw.argmin_device(ll_t)
+        if ev is not None:
+            ev["x0"].record(stream)  # before the cross-GPU exchange
+        exchange(best)
+
+    def new_events():
+        mk = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+        return {"t0": mk(), "t1": mk(), "x0": mk(), "k0": [mk() for _ in range(R)], "k1": [mk() for _ in range(R)]}
+
     # ---- value: inputs resident in HBM, per-step CUDA events on the launching stream ---------------------
+    # (both timed loops below synchronise the stream at the end of every step -- the same discipline -- so that no
+    #  rank runs ahead of the others by more than one step)
     for _ in range(args.warmup):
         flush.zero_()
         step_resident()
+        stream.synchronize()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    ev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(4)) for _ in range(args.steps)]
+    evs = [new_events() for _ in range(args.steps)]
     t_wall0 = time.perf_counter()
     for i in range(args.steps):
         flush.zero_()
-        ev[i][0].record(stream)
-        sw.log_likelihood_device(a_t, b_t, g_t, ll_out=ll_t)
-        ev[i][1].record(stream)  # end of the dominant kernel
-        best = sw.argmin_device(ll_t)
-        ev[i][3].record(stream)  # before the cross-GPU exchange
-        reduce_best_device(best, lo, world, dist)
-        ev[i][2].record(stream)
+        evs[i]["t0"].record(stream)
+        step_resident(evs[i])
+        evs[i]["t1"].record(stream)
+        stream.synchronize()
     barrier()
     wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
     sweep_mode = sw.last_sweep_mode()  # which fit kernel the device picked (reads one word; after the timed region)
-    step_ms = np.array([e[0].elapsed_time(e[2]) for e in ev])
-    kern_ms = np.array([e[0].elapsed_time(e[1]) for e in ev])
-    gather_ms = np.array([e[3].elapsed_time(e[2]) for e in ev])  # all-gather incl. the wait for the slowest rank
-    total_ms = torch.tensor([step_ms.sum()], dtype=torch.float64, device=dev)
+    step_ms = np.array([e["t0"].elapsed_time(e["t1"]) for e in evs])
+    kern_ms = np.array([[k0.elapsed_time(k1) for k0, k1 in zip(e["k0"], e["k1"])] for e in evs])  # [steps, R]
+    gather_ms = np.array([e["x0"].elapsed_time(e["t1"]) for e in evs])  # all-gather incl. the wait for the slowest rank
+    stat = torch.tensor([step_ms.sum(), gather_ms.mean(), kern_ms.mean()], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_s = float(total_ms.item()) * 1e-3
-    units = float(world) * P * n_upd * args.steps
+        dist.all_reduce(stat, op=dist.ReduceOp.MAX)
+    total_s = float(stat[0].item()) * 1e-3
+    exchange_ms_max = float(stat[1].item()) if world > 1 else 0.0
+    kern_ms_max = float(stat[2].item())
+    units = float(world) * P * n_upd * R * args.steps
     value = units / total_s
 
-    # ---- e2e: host buffers, H2D / D2H inside the timed region, through the public API ---------------------
+    # ---- e2e: host buffers, H2D / D2H of EVERY sweep inside the timed region, through the public API ---------
     pin = [torch.from_numpy(x).pin_memory() for x in (a, b, g)]
-    ll_host = torch.empty((1, P), dtype=torch.float64).pin_memory()
+    ll_host = [torch.empty((1, P), dtype=torch.float64).pin_memory() for _ in range(2)]
+    ll_dev = [ll_t, torch.empty_like(ll_t)]
     best_host = torch.empty(2 * world, dtype=torch.float64).pin_memory()
+    copy_stream = torch.cuda.Stream(device=dev)
+    done = [torch.cuda.Event() for _ in range(2)]
+    copied = [torch.cuda.Event() for _ in range(2)]
 
     def step_e2e():
-        nbytes = sw.upload()  # session stream: pinned host -> HBM (nm_streams_upload)
-        for dst, src in zip((a_t, b_t, g_t), pin):
-            dst.copy_(src, non_blocking=True)
-        sw.log_likelihood_device(a_t, b_t, g_t, ll_out=ll_t)
-        best = sw.argmin_device(ll_t)
-        out = reduce_best_device(best, lo, world, dist)
-        ll_host.copy_(ll_t, non_blocking=True)
+        """R public-API sweeps with host inputs and host outputs: per sweep the session stream and the three parameter
+        arrays go pinned host -> HBM and ll[P] comes back; the read-back of sweep r overlaps sweep r + 1 (two ll
+        buffers, a copy stream); one exchange and one synchronisation per step."""
+        nbytes = 0
+        for r in range(R):
+            j = r & 1
+            nbytes += sw.upload()  # session stream: pinned host -> HBM (nm_streams_upload)
+            for dst, src in zip((a_t, b_t, g_t), pin):
+                dst.copy_(src, non_blocking=True)
+            stream.wait_event(copied[j])  # ll_dev[j] has been read back (sweep r - 2)
+            sw.log_likelihood_device(a_t, b_t, g_t, ll_out=ll_dev[j])
+            best = sw.argmin_device(ll_dev[j])
+            done[j].record(stream)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done[j])
+                ll_host[j].copy_(ll_dev[j], non_blocking=True)
+                copied[j].record(copy_stream)
+        out = exchange(best)
         best_host[: out.numel()].copy_(out, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        stream.synchronize()
+        copy_stream.synchronize()
         return nbytes
 
     for _ in range(max(1, args.warmup)):
@@ -437,90 +699,65 @@ def run_b200(args):
     t0 = time.perf_counter()
     e2e_step_ms = []
     for _ in range(args.steps):
+        flush.zero_()
+        stream.synchronize()
         ts = time.perf_counter()
         h2d_stream_bytes = step_e2e()
         e2e_step_ms.append(1e3 * (time.perf_counter() - ts))
     barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    e2e_s = torch.tensor([sum(e2e_step_ms) * 1e-3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = units / float(e2e_s.item())
-    h2d = int(h2d_stream_bytes + 3 * P * 8)
-    d2h = int(P * 8 + 16 * world)
+    h2d = int(h2d_stream_bytes + R * 3 * P * 8)
+    d2h = int(R * P * 8 + 16 * world)
 
-    extras = None if args.no_extras else other_paths(local, world, rank, dist, dev)
-    if extras is not None:
-        # the same parameter sets in a random order: no run shares (alpha, gamma), every set owns a table -- the general
-        # case (stochastic optimisers); tables in device memory (nm_fit_global_kernel)
-        perm = torch.from_numpy(np.random.default_rng(7 + rank).permutation(P)).to(dev)
-        a_p, b_p, g_p = a_t[perm], b_t[perm], g_t[perm]
-        k_ms = []
-        for rep in range(4):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            flush.zero_()
-            e0.record(stream)
-            sw.log_likelihood_device(a_p, b_p, g_p, ll_out=ll_t)
-            e1.record(stream)
-            torch.cuda.synchronize()
-            k_ms.append(e0.elapsed_time(e1))
-        mode_p = sw.last_sweep_mode()
-        t_p = torch.tensor([min(k_ms[1:])], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t_p, op=dist.ReduceOp.MAX)
-        extras["fit_arbitrary_parameter_sets"] = {
-            "metric": "agent-trial updates/s", "value": float(world) * P * n_upd / (float(t_p.item()) * 1e-3),
-            "kernel_ms": float(t_p.item()), "sweep_mode": mode_p,
-            "workload": "the headline grid in a random order (no run of 32 sets shares alpha and gamma): one value table "
-                        "per parameter set, in device memory"}
+    peak_ginstr = fp64_peak(torch, dev, stream)
+    extras = None
+    if not args.no_extras:
+        extras = other_paths(args, local, world, rank, dist, dev, peak_ginstr,
+                             {"sw": sw, "P": P, "n_upd": n_upd, "a_t": a_t, "b_t": b_t, "g_t": g_t, "ll_t": ll_t,
+                              "flush": flush})
     if rank == 0:
         # ---- roofline: FP64 issue; peak measured live with the DFMA probe (burst, kernel timed alone) -------
-        sink = torch.zeros(1, dtype=torch.float64, device=dev)
-        lib = _native.lib()
-        import ctypes as C
-        n_instr = C.c_int64(0)
-        sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        probe_ms = []
-        for it in range(4):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            _native.check(lib.nm_fp64_peak_probe(sms * 4, 512, 20000, _native.tensor_ptr(sink), C.byref(n_instr),
-                                                 _native.cuda_stream_ptr()))
-            e1.record(stream)
-            torch.cuda.synchronize()
-            if it:
-                probe_ms.append(e0.elapsed_time(e1))
-        peak_ginstr = n_instr.value / (min(probe_ms) * 1e-3) / 1e9
+        kname = {1: "fit_group", 2: "fit_global"}.get(sweep_mode, "fit_exact")
+        entry = ncu_counts(f"{kname}_{args.alg}_configs1", "fit")
+        kern_s = kern_ms.mean() * 1e-3
         alg_instr = algorithmic_fp64(records, sw._online[0], args.alg) * P
-        achieved = alg_instr / (kern_ms.mean() * 1e-3) / 1e9
+        canonical = alg_instr / kern_s / 1e9
         alg_bytes = n_upd * 32 + P * 32  # stream once + (alpha, beta, gamma, ll) per parameter set
-        roofline = {"bound": "fp64_issue", "achieved": achieved, "peak": peak_ginstr, "unit": "GInstr/s",
-                    "frac": achieved / peak_ginstr, "traffic": ncu_dram_traffic(),
+        ex = executed_roofline(entry, float(P) * n_upd, kern_s, peak_ginstr)
+        frac = ex["executed_frac"] if ex["executed_frac"] is not None else canonical / peak_ginstr
+        roofline = {"bound": "fp64_issue", "achieved": frac * peak_ginstr, "peak": peak_ginstr, "unit": "GInstr/s",
+                    "frac": frac,
+                    "frac_kind": "EXECUTED FP64 thread-instructions (ncu sm__inst_executed_pipe_fp64.sum x 32 per launch, "
+                                 "profiles/ncu_counts.json) / live kernel time / live DFMA-probe peak"
+                                 if ex["executed_frac"] is not None else
+                                 "CANONICAL (SURVEY 8d) -- the committed ncu counts do not match this kernel build",
+                    "traffic": None if entry is None else entry["dram__bytes_read.sum"] + entry["dram__bytes_write.sum"],
                     "kernel": {1: f"nm_fit_group_kernel<{args.alg}> (one value table per warp)",
                                2: f"nm_fit_global_kernel<{args.alg}, loglik> (tables in device memory)"}.get(
                                    sweep_mode, f"nm_fit_exact_kernel<{args.alg}, loglik>"),
-                    "kernel_ms": float(kern_ms.mean()),
-                    "kernel_ms_covers": "the whole nm_loglik_sweep call: the dominant kernel + 3 launches of a few "
+                    "kernel_ms": float(kern_ms.mean()), "kernel_ms_min_max": [float(kern_ms.min()), float(kern_ms.max())],
+                    "kernel_share_of_step": float(kern_ms.sum(axis=1).mean() / step_ms.mean()),
+                    "kernel_ms_covers": "one nm_loglik_sweep call: the dominant kernel + 3 launches of a few "
                                         "microseconds (run detection, the kernel that stands down)",
-                    "frac_note": "achieved counts the CANONICAL FP64 instructions of SURVEY 8d (exp = 20, log = 30); the "
-                                 "kernel executes fewer (table-driven exp = 10, one log per 32 steps), so the canonical "
-                                 "fraction can pass 1 -- the executed fraction is fp64_pipe_busy_ncu",
-                    "fp64_pipe_busy_ncu": (lambda v: None if v is None else v / 100.0)(
-                        ncu_counter(["sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"])),
-                    "issue_slots_busy_ncu": (lambda v: None if v is None else v / 100.0)(
-                        ncu_counter(["smsp__issue_active.avg.pct_of_peak_sustained_active"])),
-                    "executed_instr_per_update_ncu": (lambda v: None if v is None else v * 32.0 / (P * n_upd))(
-                        ncu_counter(["smsp__inst_executed.sum"])),  # warp instructions x 32 lanes / updates of a launch
+                    "canonical_achieved": canonical, "canonical_frac": canonical / peak_ginstr,
+                    "canonical_note": "SURVEY 8d accounting (exp = 20, log = 30 FP64 instructions): the kernel executes "
+                                      "fewer (table-driven exp = 10, one log per 32 steps), so this can pass 1",
+                    "alg_fp64_instr_per_update": alg_instr / (P * n_upd),
                     "peak_source": "nm_fp64_peak_probe (8 independent DFMA chains/thread) timed live, burst; "
                                    "MEASURED_PEAKS.json has no FP64 figure",
-                    "alg_fp64_instr_per_update": alg_instr / (P * n_upd),
                     "why_not_hbm": "the stream (160 KB) and V-tables live in L2 / shared memory: algorithmic HBM bytes "
                                    "per launch = %d (%.2f GB/s achieved of %s GB/s measured copy peak)"
-                                   % (alg_bytes, alg_bytes / (kern_ms.mean() * 1e-3) / 1e9, measured_hbm_peak()),
-                    "hbm_gbs_achieved": alg_bytes / (kern_ms.mean() * 1e-3) / 1e9}
+                                   % (alg_bytes, alg_bytes / kern_s / 1e9, measured_hbm_peak()),
+                    "hbm_gbs_achieved": alg_bytes / kern_s / 1e9}
+        roofline.update({k: v for k, v in ex.items() if k != "executed_frac"})
         # ---- cpu_baseline: the C oracle port on this box's host cores ---------------------------------------
         tr = oracle_transitions(traj, rew)  # the one place the product arm touches oracle/: the cpu_baseline leg
         alg_code = {"td0": 0, "positive": 1, "negative": 2}[args.alg]
         cpu_val, cpu_sample, cores = cpu_port_rate(tr, alg_code, a, b, g, seconds=args.cpu_seconds)
+        launches_per_sweep = 4 if os.environ.get("NM_FIT_GROUP") == "0" else 6
         line = {"metric": "agent-trial updates/s (fitness grid sweep)", "value": value, "unit": "updates/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -532,13 +769,14 @@ def run_b200(args):
                         "step_ms_min_median_max": [float(np.min(e2e_step_ms)), float(np.median(e2e_step_ms)),
                                                    float(np.max(e2e_step_ms))],
                         "slowest_step_index": int(np.argmax(e2e_step_ms))},
-                "gpu_launches": (4 if os.environ.get("NM_FIT_GROUP") == "0" else 6) * args.steps, "clocks": clocks, "wall_s": wall,
-                "exchange_ms_per_step_rank0": float(gather_ms.mean()) if world > 1 else 0.0,
-                "target_updates_per_s_8gpu": 1e10}
+                "gpu_launches": launches_per_sweep * R * args.steps, "clocks": clocks, "wall_s": wall,
+                "exchange_ms_per_step_max_over_ranks": exchange_ms_max,
+                "kernel_ms_per_sweep_max_over_ranks": kern_ms_max,
+                "target_updates_per_s_8gpu": 1e10,
+                "config0": cpu_baseline_config0(args, local, dev, traj, rew, tr)}
         if extras is not None:
+            extras["config4_forward_simulation"]["cpu_baseline"] = cpu_port_sim_rate()
             line["also_measured"] = extras
-            # simulation, model-based (two workloads), Q-table, value tables per parameter set
-            line["gpu_launches_also_measured"] = 3 + 12 + 12 + 12 + 16
         emit(line)
     if world > 1:
         dist.barrier()
