@@ -137,7 +137,7 @@ CSRC = os.path.join(ROOT, "navigation_model_b200", "csrc")
 #: tools/ncu_counts.py when it profiles; a mismatch here means the committed counters are STALE and are not used)
 KERNEL_SOURCES = {
     "fit": ["nm_fit_kernels.cuh", "nm_fit.cu", "nm_exp.cuh", "nm_step_math.cuh", "nm_ring.cuh"],
-    "sim": ["nm_sim.cu", "nm_simgeom.cuh", "nm_exp.cuh", "nm_pose.h", "nm_geometry.h", "nm_libm.cuh"],
+    "sim": ["nm_sim.cu", "nm_simgeom.cuh", "nm_exp.cuh", "nm_pose.h", "nm_geometry.h", "nm_libm.h", "nm_libm_tables.h"],
     "mb": ["nm_mb.cu", "nm_group.cuh", "nm_exp.cuh", "nm_step_math.cuh"],
     "q": ["nm_q.cu", "nm_group.cuh", "nm_exp.cuh", "nm_step_math.cuh", "nm_ring.cuh"],
 }

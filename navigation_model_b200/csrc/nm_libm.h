@@ -1,0 +1,353 @@
+// sin / cos / atan2 that reproduce, BIT FOR BIT, the results of the host C library the reference ran on.
+//
+// Why.  The reference's C++ Mouse calls std::cos / std::sin / std::atan2 (src/_navigation_model/mouse.cpp:66, 78); a pose
+// is a chain of such calls, so a device libm that differs from the host's in the last place of ONE result makes every
+// later position of that mouse differ in its last bits.  north_star asks for bit-exact simulated trajectories under
+// replayed draws, so the simulation kernel evaluates these three functions with the algorithm of the host library --
+// GNU libc 2.39 (the image's libm.so.6; x86-64 FMA variants, which is what every host with FMA3 + AVX2 dispatches to):
+//     sysdeps/ieee754/dbl-64/s_sin.c   (__sin, __cos: table-driven, 440-entry sin/cos table on a 1/128 grid,
+//                                       Cody-Waite reduction by pi/2 in four pieces for 2.43 < |x| < 1.05e8)
+//     sysdeps/ieee754/dbl-64/e_atan2.c (__ieee754_atan2: quotient in double-double, 241-row table of
+//                                       atan expansions for |u| >= 1/16, odd polynomial below)
+// restated here operation by operation, INCLUDING which multiply-adds the FMA build fuses (taken from the machine code of
+// the library: tools/libm_tables.py documents the addresses; tests/test_libm_port.py holds this file to the library on
+// 10^8+ arguments on the host).  Every operation below is an IEEE-754 basic operation or a fused multiply-add, which
+// round identically on the host and on the device -- so agreement with the library on the host is agreement on the GPU.
+//
+// Scope: finite arguments with |x| < 105414350 for sin / cos (beyond that the library switches to a multi-precision
+// reduction: the caller falls back to the platform function there); atan2 for finite arguments, signed zeros included,
+// whose exponents differ by less than 2^57 either way and that are not subnormal-scaled (|x|, |y| in [2^-500, 2^500]) --
+// poses of a maze are of order 1.  Outside that scope the platform function is used (NML_FALLBACK_*).
+//
+// The tables (nm_libm_tables.h) are the library's own read-only data, extracted by tools/libm_tables.py.
+#ifndef NM_LIBM_H
+#define NM_LIBM_H
+
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define NML_HD __host__ __device__ __forceinline__
+#else
+#define NML_HD static inline
+#endif
+#if defined(__CUDA_ARCH__)
+#define NML_FMA(a, b, c) __fma_rn((a), (b), (c))
+#define NML_MUL(a, b) __dmul_rn((a), (b))
+#define NML_ADD(a, b) __dadd_rn((a), (b))
+#define NML_SUB(a, b) __dsub_rn((a), (b))
+#define NML_DIV(a, b) __ddiv_rn((a), (b))
+#define NML_TAB(t) t##_dev
+#define NML_BITS(x) __double_as_longlong(x)
+#define NML_FROM_BITS(i) __longlong_as_double(i)
+#else
+// host: compile with -ffp-contract=off so that nothing but NML_FMA fuses
+#define NML_FMA(a, b, c) fma((a), (b), (c))
+#define NML_MUL(a, b) ((a) * (b))
+#define NML_ADD(a, b) ((a) + (b))
+#define NML_SUB(a, b) ((a) - (b))
+#define NML_DIV(a, b) ((a) / (b))
+#define NML_TAB(t) t##_host
+static inline int64_t nml_bits_(double x) {
+  int64_t i;
+  memcpy(&i, &x, 8);
+  return i;
+}
+static inline double nml_from_bits_(int64_t i) {
+  double x;
+  memcpy(&x, &i, 8);
+  return x;
+}
+#define NML_BITS(x) nml_bits_(x)
+#define NML_FROM_BITS(i) nml_from_bits_(i)
+#endif
+
+#include "nm_libm_tables.h"
+
+// ---- constants of s_sin.c / usncs.h (read from the library's .rodata, hexadecimal so that no decimal conversion rounds) ----
+#define NML_S1 (-0x1.5555555555555p-3)
+#define NML_S2 (0x1.1111111110ecep-7)
+#define NML_S3 (-0x1.a01a019db08b8p-13)
+#define NML_S4 (0x1.71de27b9a7ed9p-19)
+#define NML_S5 (-0x1.addffc2fcdf59p-26)
+#define NML_SN3 (-0x1.5555555555515p-3)
+#define NML_SN5 (0x1.11110e829872fp-7)
+#define NML_CS2 (0x1.0000000000000p-1)
+#define NML_CS4 (-0x1.5555555555535p-5)
+#define NML_CS6 (0x1.6c16bedd9e239p-10)
+#define NML_BIG (0x1.8000000000000p+45)
+#define NML_TOINT (0x1.8000000000000p+52)
+#define NML_HPINV (0x1.45f306dc9c883p-1)
+#define NML_MP1 (0x1.921fb58000000p+0)
+#define NML_MP2 (-0x1.dde973c000000p-27)
+#define NML_PP3 (-0x1.cb3b398000000p-55)
+#define NML_PP4 (-0x1.d747f23e32ed7p-83)
+#define NML_HP0 (0x1.921fb54442d18p+0)
+#define NML_HP1 (0x1.1a62633145c07p-54)
+#define NML_TAYLOR_LIMIT (0x1.020c49ba5e354p-3) /* 0.126 */
+
+NML_HD double nml_copysign(double mag, double sgn) {
+  return NML_FROM_BITS((NML_BITS(mag) & 0x7fffffffffffffffLL) | (NML_BITS(sgn) & (int64_t)0x8000000000000000ULL));
+}
+NML_HD double nml_fabs(double x) { return NML_FROM_BITS(NML_BITS(x) & 0x7fffffffffffffffLL); }
+
+// TAYLOR_SIN(xx, x, dx): x + ((POLY(xx) * x - 0.5 * dx) * xx + dx), every "* .. +" fused
+NML_HD double nml_taylor_sin(double xx, double x, double dx) {
+  double p = NML_FMA(NML_S5, xx, NML_S4);
+  p = NML_FMA(p, xx, NML_S3);
+  p = NML_FMA(p, xx, NML_S2);
+  p = NML_FMA(p, xx, NML_S1);
+  const double t1 = NML_FMA(p, x, -NML_MUL(0.5, dx));  // vfmsub: p * x - 0.5 * dx
+  const double t = NML_FMA(xx, t1, dx);
+  return NML_ADD(x, t);
+}
+
+// do_sin(x, dx) for |x| >= 0.126 after the caller's sign handling: ax = |x|, dx already negated when x <= 0.
+// Returns the magnitude (the caller copies the sign of x onto it).
+NML_HD double nml_do_sin_body(double ax, double dx) {
+  const double u = NML_ADD(NML_BIG, ax);
+  const double x = NML_SUB(ax, NML_SUB(u, NML_BIG));
+  const int k = ((int)(uint32_t)NML_BITS(u)) << 2;
+  const double xx = NML_MUL(x, x);
+  const double s = NML_ADD(x, NML_FMA(NML_MUL(x, xx), NML_FMA(NML_SN5, xx, NML_SN3), dx));
+  const double c = NML_FMA(x, dx, NML_MUL(xx, NML_FMA(NML_FMA(NML_CS6, xx, NML_CS4), xx, NML_CS2)));
+  const double *T = NML_TAB(nml_sincostab) + k;
+  const double sn = T[0], ssn = T[1], cs = T[2], ccs = T[3];
+  const double cor = NML_FMA(s, cs, NML_FMA(-c, sn, NML_FMA(s, ccs, ssn)));
+  return NML_ADD(sn, cor);
+}
+
+// do_cos(x, dx): ax = |x|, dx already negated when x < 0
+NML_HD double nml_do_cos_body(double ax, double dx) {
+  const double u = NML_ADD(NML_BIG, ax);
+  const double x = NML_ADD(NML_SUB(ax, NML_SUB(u, NML_BIG)), dx);
+  const int k = ((int)(uint32_t)NML_BITS(u)) << 2;
+  const double xx = NML_MUL(x, x);
+  const double s = NML_FMA(NML_MUL(x, xx), NML_FMA(NML_SN5, xx, NML_SN3), x);
+  const double c = NML_MUL(xx, NML_FMA(NML_FMA(NML_CS6, xx, NML_CS4), xx, NML_CS2));
+  const double *T = NML_TAB(nml_sincostab) + k;
+  const double sn = T[0], ssn = T[1], cs = T[2], ccs = T[3];
+  const double cor = NML_FMA(-s, sn, NML_FMA(-c, cs, NML_FMA(-s, ssn, ccs)));
+  return NML_ADD(cs, cor);
+}
+
+// do_sin(a, da) as the library's inline: Taylor branch below 0.126, sign of a copied onto the table branch
+NML_HD double nml_do_sin(double a, double da) {
+  const double aa = nml_fabs(a);
+  if (aa < NML_TAYLOR_LIMIT) return nml_taylor_sin(NML_MUL(a, a), a, da);
+  if (a <= 0.0) da = -da;
+  return nml_copysign(nml_do_sin_body(aa, da), a);
+}
+NML_HD double nml_do_cos(double a, double da) {
+  if (a < 0.0) da = -da;
+  return nml_do_cos_body(nml_fabs(a), da);
+}
+
+// reduce_sincos: x = n * pi/2 + (a + da), n mod 4 returned
+NML_HD int nml_reduce_sincos(double x, double *a, double *da) {
+  const double t = NML_FMA(x, NML_HPINV, NML_TOINT);
+  const double xn = NML_SUB(t, NML_TOINT);
+  const double y = NML_FMA(-xn, NML_MP2, NML_FMA(-xn, NML_MP1, x));
+  const int n = (int)((uint32_t)NML_BITS(t) & 3u);
+  const double t2 = NML_FMA(-xn, NML_PP3, y);
+  double db = NML_FMA(-xn, NML_PP3, NML_SUB(y, t2));
+  const double b = NML_FMA(-xn, NML_PP4, t2);
+  db = NML_ADD(db, NML_FMA(-xn, NML_PP4, NML_SUB(t2, b)));
+  *a = b;
+  *da = db;
+  return n;
+}
+
+NML_HD double nml_do_sincos(double a, double da, int n) {
+  const double r = (n & 1) ? nml_do_cos(a, da) : nml_do_sin(a, da);
+  return (n & 2) ? -r : r;
+}
+
+// 1 when nml_sin / nml_cos cover x (finite, below the multi-precision range of the library)
+NML_HD int nml_sincos_in_scope(double x) { return ((uint32_t)(NML_BITS(x) >> 32) & 0x7fffffffu) < 0x419921FBu; }
+
+NML_HD double nml_sin(double x) {
+  const uint32_t k = (uint32_t)(NML_BITS(x) >> 32) & 0x7fffffffu;
+  if (k < 0x3e500000u) return x;  // |x| < 2^-26
+  if (k < 0x3feb6000u) {          // |x| < 0.855469
+    const double ax = nml_fabs(x);
+    if (ax < NML_TAYLOR_LIMIT) return nml_taylor_sin(NML_MUL(x, x), x, 0.0);
+    return nml_copysign(nml_do_sin_body(ax, x > 0.0 ? 0.0 : -0.0), x);
+  }
+  if (k < 0x400368fdu) {  // 0.855469 <= |x| < 2.426265: cos(pi/2 - |x|), sign of x
+    const double t = NML_SUB(NML_HP0, nml_fabs(x));
+    return nml_copysign(nml_do_cos_body(nml_fabs(t), t >= 0.0 ? NML_HP1 : -NML_HP1), x);
+  }
+  double a, da;
+  const int n = nml_reduce_sincos(x, &a, &da);
+  return nml_do_sincos(a, da, n);
+}
+
+NML_HD double nml_cos(double x) {
+  const uint32_t k = (uint32_t)(NML_BITS(x) >> 32) & 0x7fffffffu;
+  if (k < 0x3e400000u) return 1.0;  // |x| < 2^-27
+  if (k < 0x3feb6000u) return nml_do_cos_body(nml_fabs(x), x >= 0.0 ? 0.0 : -0.0);
+  if (k < 0x400368fdu) {  // sin(pi/2 - |x|) with the 106-bit pi/2
+    const double y = NML_SUB(NML_HP0, nml_fabs(x));
+    const double a = NML_ADD(y, NML_HP1);
+    const double da = NML_ADD(NML_SUB(y, a), NML_HP1);
+    return nml_do_sin(a, da);
+  }
+  double a, da;
+  const int n = nml_reduce_sincos(x, &a, &da);
+  return nml_do_sincos(a, da, n + 1);
+}
+
+// ---- atan2 (e_atan2.c) ---------------------------------------------------------------------------------------------
+#define NML_D3 (-0x1.5555555555555p-2)
+#define NML_D5 (0x1.99999999997fdp-3)
+#define NML_D7 (-0x1.24924923f7603p-3)
+#define NML_D9 (0x1.c71c6e5129a3bp-4)
+#define NML_D11 (-0x1.7458022b13c25p-4)
+#define NML_D13 (0x1.375f08b31cbcep-4)
+#define NML_HPI (0x1.921fb54442d18p+0)
+#define NML_HPI1 (0x1.1a62633145c07p-54)
+#define NML_OPI (0x1.921fb54442d18p+1)
+#define NML_OPI1 (0x1.1a62633145c07p-53)
+#define NML_TWO52 (0x1.0p+52)
+#define NML_TWO8 (0x1.0p+8)
+#define NML_TWO500 (0x1.0p+500)
+#define NML_TWOM500 (0x1.0p-500)
+
+// d3 + v * (d5 + v * (d7 + v * (d9 + v * (d11 + v * d13)))), every step fused
+NML_HD double nml_atan_poly(double v) {
+  double p = NML_FMA(NML_D13, v, NML_D11);
+  p = NML_FMA(p, v, NML_D9);
+  p = NML_FMA(p, v, NML_D7);
+  p = NML_FMA(p, v, NML_D5);
+  return NML_FMA(p, v, NML_D3);
+}
+
+// row of cij for u in [1/16, 1]: i = (int)((TWO52 + TWO8 * u) - TWO52) - 16
+NML_HD const double *nml_atan_row(double u) {
+  const double t = NML_SUB(NML_FMA(u, NML_TWO8, NML_TWO52), NML_TWO52);
+  return NML_TAB(nml_cij) + 7 * ((int)t - 16);
+}
+
+// c[2] + v * (c[3] + v * (c[4] + v * (c[5] + v * c[6])))
+NML_HD double nml_atan_row_poly(const double *c, double v) {
+  double q = NML_FMA(c[6], v, c[5]);
+  q = NML_FMA(q, v, c[4]);
+  q = NML_FMA(q, v, c[3]);
+  return NML_FMA(q, v, c[2]);
+}
+
+// finite arguments only (NaN / infinity: the caller uses the platform function)
+NML_HD int nml_atan2_in_scope(double y, double x) {
+  const uint32_t ex = (uint32_t)(NML_BITS(x) >> 32) & 0x7ff00000u, ey = (uint32_t)(NML_BITS(y) >> 32) & 0x7ff00000u;
+  return ex != 0x7ff00000u && ey != 0x7ff00000u;
+}
+
+NML_HD double nml_atan2(double y, double x) {
+  const int64_t bx = NML_BITS(x), by = NML_BITS(y);
+  const int ux = (int)(bx >> 32), uy = (int)(by >> 32);
+  if ((by & 0x7fffffffffffffffLL) == 0) return bx < 0 ? nml_copysign(NML_OPI, y) : y;  // y = +-0
+  if ((bx & 0x7fffffffffffffffLL) == 0) return nml_copysign(NML_HPI, y);                 // x = +-0
+  double ax = nml_fabs(x), ay = nml_fabs(y);
+  const int de = (uy & 0x7ff00000) - (ux & 0x7ff00000);
+  if (de >= 59768832) return nml_copysign(NML_HPI, y);  // |y / x| >= 2^57
+  if (de <= -59768832) return x > 0.0 ? nml_copysign(NML_DIV(ay, ax), y) : nml_copysign(NML_OPI, y);
+  if (ax < NML_TWOM500 || ay < NML_TWOM500) {
+    ax = NML_MUL(ax, NML_TWO500);
+    ay = NML_MUL(ay, NML_TWO500);
+  }
+  if (ax > NML_TWO500 || ay > NML_TWO500) {
+    ax = NML_MUL(ax, NML_TWOM500);
+    ay = NML_MUL(ay, NML_TWOM500);
+  }
+  // the quotient of the smaller by the larger magnitude in double-double: u + du
+  double u, du;
+  const int y_smaller = ay < ax;
+  {
+    const double num = y_smaller ? ay : ax, den = y_smaller ? ax : ay;
+    u = NML_DIV(num, den);
+    const double v = NML_MUL(u, den);
+    const double vv = NML_FMA(u, den, -v);
+    du = NML_DIV(NML_SUB(NML_SUB(num, v), vv), den);
+  }
+  double z;
+  if (x > 0.0) {
+    if (y_smaller) {  // (i) atan(ay / ax)
+      if (u < 0x1.0p-4) {
+        const double v = NML_MUL(u, u);
+        z = NML_ADD(u, NML_FMA(NML_MUL(u, v), nml_atan_poly(v), du));
+      } else {
+        const double *c = nml_atan_row(u);
+        const double t3 = NML_SUB(u, c[0]);
+        const double v = NML_ADD(t3, du);
+        const double dv = nml_fabs(t3) > nml_fabs(du) ? NML_ADD(NML_SUB(t3, v), du) : NML_ADD(NML_SUB(du, v), t3);
+        double p = NML_FMA(c[6], v, c[5]);
+        p = NML_FMA(p, v, c[4]);
+        p = NML_FMA(p, v, c[3]);
+        const double zz = NML_FMA(v, c[2], NML_FMA(dv, c[2], NML_MUL(NML_MUL(v, v), p)));
+        z = NML_ADD(zz, c[1]);
+      }
+    } else {  // (ii) pi/2 - atan(ax / ay)
+      if (u < 0x1.0p-4) {
+        const double v = NML_MUL(u, u);
+        const double zz = NML_MUL(NML_MUL(u, v), nml_atan_poly(v));
+        const double t2 = NML_SUB(NML_HPI, u);
+        const double cor = NML_SUB(NML_SUB(NML_HPI, t2), u);  // |hpi| > |u| always here
+        z = NML_ADD(NML_SUB(NML_SUB(NML_ADD(cor, NML_HPI1), du), zz), t2);
+      } else {
+        const double *c = nml_atan_row(u);
+        const double v = NML_ADD(NML_SUB(u, c[0]), du);
+        const double zz = NML_FMA(-v, nml_atan_row_poly(c, v), NML_HPI1);
+        z = NML_ADD(NML_SUB(NML_HPI, c[1]), zz);
+      }
+    }
+  } else {
+    if (!y_smaller) {  // (iii) pi/2 + atan(ax / ay)
+      if (u < 0x1.0p-4) {
+        const double v = NML_MUL(u, u);
+        const double zz = NML_MUL(NML_MUL(u, v), nml_atan_poly(v));
+        const double t2 = NML_ADD(u, NML_HPI);
+        const double cor = NML_ADD(NML_SUB(NML_HPI, t2), u);
+        z = NML_ADD(NML_ADD(NML_ADD(NML_ADD(cor, NML_HPI1), du), zz), t2);
+      } else {
+        const double *c = nml_atan_row(u);
+        const double v = NML_ADD(NML_SUB(u, c[0]), du);
+        const double zz = NML_FMA(v, nml_atan_row_poly(c, v), NML_HPI1);
+        z = NML_ADD(NML_ADD(NML_HPI, c[1]), zz);
+      }
+    } else {  // (iv) pi - atan(ay / ax)
+      if (u < 0x1.0p-4) {
+        const double v = NML_MUL(u, u);
+        const double zz = NML_MUL(NML_MUL(u, v), nml_atan_poly(v));
+        const double t2 = NML_SUB(NML_OPI, u);
+        const double cor = NML_SUB(NML_SUB(NML_OPI, t2), u);
+        z = NML_ADD(NML_SUB(NML_SUB(NML_ADD(cor, NML_OPI1), du), zz), t2);
+      } else {
+        const double *c = nml_atan_row(u);
+        const double v = NML_ADD(NML_SUB(u, c[0]), du);
+        const double zz = NML_FMA(-v, nml_atan_row_poly(c, v), NML_OPI1);
+        z = NML_ADD(NML_SUB(NML_OPI, c[1]), zz);
+      }
+    }
+  }
+  return nml_copysign(z, y);
+}
+
+#if defined(__CUDACC__)
+// Device entry points (out of line: three call sites in a kernel share one copy of the code).  Out-of-scope arguments
+// (|heading| >= 1.05e8, non-finite values) fall back to the CUDA functions.
+static __device__ __noinline__ void nm_host_sincos(double x, double *s, double *c) {
+  if (nml_sincos_in_scope(x)) {
+    *s = nml_sin(x);
+    *c = nml_cos(x);
+  } else {
+    sincos(x, s, c);
+  }
+}
+static __device__ __noinline__ double nm_host_atan2(double y, double x) {
+  return nml_atan2_in_scope(y, x) ? nml_atan2(y, x) : atan2(y, x);
+}
+#endif
+
+#endif  // NM_LIBM_H

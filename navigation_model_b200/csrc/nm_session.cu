@@ -16,15 +16,16 @@
 //     chain, walked by one thread per session (nm_pose_chain_kernel, 3 doubles per step); everything else -- nearest
 //     visitable tile of both end points, eight rotated endpoints, tile lookups, the index of the observed candidate --
 //     is independent per step and runs one THREAD PER RECORD (nm_records_kernel) over all sessions.
-// Device cos / sin / atan2 are within 1-2 ulp of the host's libm: a candidate list can differ from the host builder's
-// only when an endpoint lies within an ulp of a tile boundary (tests/test_session_device_gpu.py compares whole
-// streams).
+// cos / sin / atan2 are the host C library's (nm_libm.h: its algorithms restated with their fused operations), so
+// headings, rotated endpoints and therefore candidate lists equal the host builder's bit for bit
+// (tests/test_session_device_gpu.py compares whole streams).
 #include <cuda_runtime.h>
 
 #include <new>
 #include <vector>
 
 #include "nm_common.h"
+#include "nm_libm.h"
 #include "nm_pose.h"
 
 namespace {
@@ -103,7 +104,7 @@ __global__ void nm_pose_chain_kernel(const BuildArgs a) {
   }
   auto move_to = [&](double x, double y) {  // mouse.cpp:75-87
     if (!nm_pos_is_approx(x, y, px, py)) {
-      ori = atan2(y - py, x - px);
+      ori = nm_host_atan2(y - py, x - px);
       px = x;
       py = y;
     }
@@ -153,7 +154,8 @@ __global__ void nm_records_kernel(const BuildArgs a, int64_t total) {
     for (int k = 0; k < NM_MAX_CAND; ++k) rec.cand[k] = 0;
     if (a.A > 0) {
       const double px = a.pose[3 * g], py = a.pose[3 * g + 1], ori = a.pose[3 * g + 2];
-      const double c = cos(ori), sn = sin(ori);
+      double c, sn;
+      nm_host_sincos(ori, &sn, &c);
       for (int k = 0; k < a.A; ++k) {
         double ex, ey;
         nm_pose_endpoint(c, sn, px, py, a.act[k][0], a.act[k][1], &ex, &ey);
@@ -206,7 +208,8 @@ __global__ void nm_orientations_kernel(const OriArgs a) {
     bool moved = !(nm_np_isclose(x1, x2) && nm_np_isclose(y1, y2));
     if (moved && a.A > 0) {  // the tile reached must be the tile under one of the rotated endpoints (:668-671)
       const int tx = nm_tile_index_inv(x2, a.st, inv), ty = nm_tile_index_inv(y2, a.st, inv);
-      const double c = cos(prev), sn = sin(prev);
+      double c, sn;
+      nm_host_sincos(prev, &sn, &c);
       bool hit = false;
       for (int k = 0; k < a.A; ++k) {
         double ex, ey;
@@ -216,7 +219,7 @@ __global__ void nm_orientations_kernel(const OriArgs a) {
       moved = hit;
     }
     if (moved) {
-      last = atan2(y2 - y1, x2 - x1);  // always inside [-pi, pi]: the corrections of :676-679 never fire
+      last = nm_host_atan2(y2 - y1, x2 - x1);  // always inside [-pi, pi]: the corrections of :676-679 never fire
       prev = last;
       if (first < 0) {
         first = i;

@@ -24,6 +24,7 @@
 #include <cstdlib>
 
 #include "nm_common.h"
+#include "nm_libm.h"
 #include "nm_pose.h"
 #include "nm_simgeom.cuh"
 
@@ -56,6 +57,8 @@ struct SimDev {
   double ori_edges[NM_MAX_ORI_BINS + 1];   // numpy.histogram edges of the turn histogram
 };
 
+// cos / sin / atan2 of the pose chain: nm_host_sincos / nm_host_atan2 (nm_libm.h) give the HOST library's results, so
+// that a simulated trajectory equals the reference's to the last bit (mouse.cpp:66, 78 call std::cos / sin / atan2).
 __device__ __forceinline__ uint64_t rotr64(uint64_t v, unsigned r) { return (v >> r) | (v << ((64 - r) & 63)); }
 
 // numpy PCG64: 128-bit LCG step, then XSL-RR output of the NEW state; random() = (u64 >> 11) * 2^-53
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 
         const bool start_ok = cur_inside && tiles[cur_tx * d.Y + cur_ty] != 0;  // tile under the mouse (maze.py:578)
         const int cur_tile = cur_inside ? cur_tx * d.Y + cur_ty : 0;
         if (need) {
-          sincos(ori, &s, &c);
+          nm_host_sincos(ori, &s, &c);
 #pragma unroll
           for (int i = 0; i < kA; ++i)
             if (i < A && d.null_act[i])
@@ -499,7 +502,7 @@ __global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 
       // -- Mouse.move_to                                                      mouse.cpp:75-87
       const double ori_before = ori;
       if (!nm_pos_is_approx(nx, ny, px, py)) {
-        ori = atan2(ny - py, nx - px);
+        ori = nm_host_atan2(ny - py, nx - px);
         px = nx;
         py = ny;
         dirty = true;  // new pose: the cached reachability is stale

@@ -101,7 +101,8 @@ def test_batched_kernel_matches_reference(cuda, g):
     assert not res.status.any()
     for m in range(len(g["pose"])):
         assert np.array_equal(np.floor_divide(res.history_position[m], st), np.floor_divide(g["hist_pos"][m], st))
-        np.testing.assert_allclose(res.history_position[m], g["hist_pos"][m], rtol=0, atol=1e-12)
+        assert np.array_equal(res.history_position[m], g["hist_pos"][m])
+        assert np.array_equal(res.history_orientation[m], g["hist_ori"][m])
     assert np.array_equal(res.occupancy, g["occupancy"].astype(np.int64))
     assert np.array_equal(res.tile_counts[:, :5], g["tile_counts"])  # VOID, WALL, CORNER, CENTRE, DECISION_POINT
 
@@ -124,4 +125,5 @@ def test_standard_experiment_device_path(cuda, g):
         exp.run(300)
         hp = np.array(mouse.history[0])
         assert np.array_equal(np.floor_divide(hp, st), np.floor_divide(g["hist_pos"][m], st))
-        np.testing.assert_allclose(hp, g["hist_pos"][m], rtol=0, atol=1e-12)
+        assert np.array_equal(hp, g["hist_pos"][m])
+        assert np.array_equal(np.array(mouse.history[1]), g["hist_ori"][m])

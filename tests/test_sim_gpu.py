@@ -2,8 +2,9 @@
 with the oracle, under replayed uniform draws.
 
 Bar (BASELINE.json north_star / SURVEY section 7 "hard parts"): the DISCRETE trajectory -- chosen action
-at every step, tile sequence, occupancy / exploration metrics -- is bit-exact; continuous poses agree to
-1e-12 absolute (device cos/sin/atan2/exp differ from glibc / numpy by <= 1-2 ulp)."""
+at every step, tile sequence, occupancy / exploration metrics -- is bit-exact, AND SO ARE THE CONTINUOUS POSES (positions
+and headings): since round 2 the kernel evaluates cos / sin / atan2 with the host C library's algorithm
+(csrc/nm_libm.h), so every comparison below is an equality (POSE_ATOL = 0)."""
 import numpy as np
 import pytest
 
@@ -13,7 +14,7 @@ import helpers as H
 
 pytestmark = pytest.mark.gpu
 
-POSE_ATOL = 1e-12
+POSE_ATOL = 0.0
 
 
 def _classes():
@@ -62,9 +63,7 @@ def test_golden_histories(cuda, golden_sim, counters, monkeypatch):
             got_disc = [omz.cont2disc(x, y) for x, y in res.history_position[m]]
             assert got_disc == want_disc, f"mouse {m}: tile sequence differs"
             np.testing.assert_allclose(res.history_position[m], g["hist_pos"][m], rtol=0, atol=POSE_ATOL)
-            # headings agree modulo 2*pi: a 1-ulp difference in dy flips atan2(+-0, -dx) between +pi and -pi
-            dori = np.angle(np.exp(1j * (res.history_orientation[m] - g["hist_ori"][m])))
-            np.testing.assert_allclose(dori, 0.0, rtol=0, atol=1e-9)
+            assert np.array_equal(res.history_orientation[m], g["hist_ori"][m])  # headings: the reference's bits
         assert np.array_equal(res.occupancy, g["occupancy"].astype(np.int64))
         assert np.array_equal(res.it_visit, g[key])
         assert np.array_equal(res.count_moving, g["count_moving"])

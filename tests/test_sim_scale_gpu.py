@@ -3,8 +3,10 @@ replayed draws through the CUDA kernel against the compiled oracle (oracle/nm_or
 on every history the unmodified reference produced for tests/golden/).
 
 Bar: the DISCRETE trajectory (action chosen at every one of the 4.1e6 steps, visit maps, first-visit iterations, motion
-counts) is identical for every mouse.  The continuous poses are compared in units in the last place; the statistics go
-to gpurun_out/sim_scale_parity.json (copied to profiles/ by hand when the kernel changes)."""
+counts) AND the continuous poses (positions, headings) are bit-identical for every mouse (north_star: "simulated
+trajectories are bit-exact when fed the reference's own replayed uniform draws").  Statistics in units in the last place
+go to gpurun_out/sim_scale_parity.json (copied to profiles/; round 1's CUDA-libm kernel: 23 % of the positions identical,
+max 1.8e-14 absolute; round 2: 100 %)."""
 import json
 import os
 
@@ -94,5 +96,7 @@ def test_four_million_agent_steps_against_the_oracle(cuda):
     with open(os.path.join("gpurun_out", "sim_scale_parity.json"), "w") as fh:
         json.dump(stats, fh, indent=1)
     print(json.dumps(stats))
-    assert stats["position_abs_max"] <= 1e-12
-    assert float(np.abs(dori).max()) <= 1e-9
+    # round 2: the kernel's cos / sin / atan2 are the host library's (csrc/nm_libm.h) -> every pose bit-identical
+    assert np.array_equal(res.history_position, ref["hist_pos"])
+    assert np.array_equal(res.history_orientation, ref["hist_ori"])
+    assert np.array_equal(res.final_pose, ref["final_pose"])
