@@ -79,4 +79,52 @@ struct ExpRegs {
   }
 };
 
+// ---- exponentials of a LIKELIHOOD step (softmax denominator) ---------------------------------------------------------
+// Bar: 1e-9 relative on a session's log-likelihood (BASELINE.json north_star), not the last bit -- value tables never see
+// an exponential, and the simulation kernel (whose discrete choices must reproduce the reference's) keeps exp_nonpos.
+// exp(x), x <= ~0:  x = (32 e + j) * ln2/32 + r, |r| <= ln2/64:  exp(x) = 2^e * 2^(j/32) * P4(r)
+//   * ONE fused step of range reduction against the double nearest to ln2/32 (error |x| * 1.1e-16 relative -- a term of
+//     weight exp(x) <= 1 in a sum >= 1 moves it by < 5e-17);
+//   * a 32-entry table (two 128-byte shared-memory rows) and a degree-4 Taylor polynomial: truncation r^5/120 <= 1.25e-12
+//     relative per exponential, of either sign;
+//   * the caller forms x = fma(beta, v, -m) in one instruction.
+// 8 FP64 instructions + the caller's fma instead of 10 + 2 (round 1's degree-5 / 16-entry form), 4 integer instructions
+// instead of 6.  The binary exponent is clamped (k >= -1021 * 32) so that a hugely negative x gives ~2^-1021, not garbage.
+__constant__ double c_exp2tab32[32] = {
+    1.00000000000000000e+00, 1.02189714865411663e+00, 1.04427378242741375e+00, 1.06714040067682370e+00,
+    1.09050773266525769e+00, 1.11438674259589243e+00, 1.13878863475669156e+00, 1.16372485877757748e+00,
+    1.18920711500272103e+00, 1.21524735998046896e+00, 1.24185781207348400e+00, 1.26905095719173322e+00,
+    1.29683955465100964e+00, 1.32523664315974132e+00, 1.35425554693689265e+00, 1.38390988196383202e+00,
+    1.41421356237309515e+00, 1.44518080697704665e+00, 1.47682614593949935e+00, 1.50916442759342284e+00,
+    1.54221082540794074e+00, 1.57598084510788650e+00, 1.61049033194925428e+00, 1.64575547815396495e+00,
+    1.68179283050742900e+00, 1.71861929812247793e+00, 1.75625216037329945e+00, 1.79470907500310717e+00,
+    1.83400808640934243e+00, 1.87416763411029996e+00, 1.91520656139714740e+00, 1.95714412417540018e+00};
+__constant__ double c_expll_k[5] = {4.61662413084468283841e+01,   // 32 * log2(e)
+                                    6755399441055744.0,           // 1.5 * 2^52
+                                    -2.16608493924982901946e-02,  // -ln2/32 (nearest double)
+                                    1.0 / 24.0, 1.0 / 6.0};
+
+struct ExpLL {
+  double c[5];
+  uint32_t tab;  // shared-window address of 32 doubles holding c_exp2tab32 (the kernel fills them)
+  __device__ __forceinline__ void load(uint32_t table_addr) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) asm volatile("mov.f64 %0, %1;" : "=d"(c[i]) : "d"(c_expll_k[i]));
+    tab = table_addr;
+  }
+  __device__ __forceinline__ double operator()(double x) const {
+    const double t = fma(x, c[0], c[1]);
+    const int k = max(__double2loint(t), -1021 * 32);  // round(32 x / ln2), clamped
+    const double r = fma(__dsub_rn(t, c[1]), c[2], x);
+    double s;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(s) : "r"(tab + (((uint32_t)k << 3) & 0xf8u)));
+    double p = fma(c[3], r, c[4]);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    p = __dmul_rn(p, s);
+    return __hiloint2double(__double2hiint(p) + (k & ~31) * 32768, __double2loint(p));  // += (k >> 5) << 20
+  }
+};
+
 #endif  // NM_EXP_CUH

@@ -34,7 +34,7 @@ constexpr int kDecStages = 4;   // decoded ring
 constexpr int kRawBytes = kRawStages * kChunk * 32;
 constexpr int kDecBytes = kDecStages * kChunk * 64;
 constexpr int kBarBytes = 128;  // full_raw[2], full_dec[4], empty_dec[4]
-constexpr int kTabBytes = 128;  // 2^(j/16), j = 0..15: one shared-memory row, conflict-free for any lane pattern
+constexpr int kTabBytes = 256;  // 2^(j/32), j = 0..31: two shared-memory rows (ExpLL, nm_exp.cuh)
 constexpr int kFixedBytes = kBarBytes + kRawBytes + kDecBytes + kTabBytes;
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 
@@ -127,6 +127,17 @@ __device__ __forceinline__ void producer_loop(const Rings &rg, const nm_step_rec
     } else {
 #pragma unroll
       for (int k = 0; k < NM_MAX_CAND; ++k) oc[k] = cs[k] * row_bytes;
+      // likelihood steps: the OBSERVED candidate goes first (swapped with candidate 0), so that the consumer's
+      // exponential argument of candidate 0 is the observed log-odds.  The value update takes the extremum of the
+      // same multiset of table entries: bit-identical tables whatever the order.
+      if (oobs != kNone) {
+#pragma unroll
+        for (int k = 1; k < NM_MAX_CAND; ++k)
+          if ((uint32_t)k == obs) {
+            oc[k] = oc[0];
+            oc[0] = oobs;
+          }
+      }
     }
     if (lane < cnt) {
       const double nhz = (double)(K - Kw);
@@ -178,7 +189,7 @@ __device__ __forceinline__ double exp_nonpos(double x) { return (x < -708.0) ? 0
 // =================================== EXACT body ===========================================================
 struct ExactAcc {
   double acc_obs, prod;
-  ExpRegs er;
+  ExpLL er;
 };
 
 template <int ALG, bool LL, int K>
@@ -197,23 +208,27 @@ __device__ __forceinline__ void exact_step_k(const uint4 q0, const uint4 q1, con
   }
   if constexpr (ALG == NM_ALG_TD0) boot = lds_f64(vb, q1.y);
   else boot = extremum<ALG, K>(v);
-  if (LL && q0.w != kNone) {  // observed step (warp-uniform)
-    double z[NM_MAX_CAND];
-#pragma unroll
-    for (int k = 0; k < K; ++k) z[k] = __dmul_rn(beta, v[k]);  // exploration_model.py:87
+  if (LL && q0.w != kNone) {  // observed step (warp-uniform); the producer put the OBSERVED candidate first
+    // val_k = beta * V[cand_k] - max (exploration_model.py:87, 92) in one fused instruction per candidate; the maximum
+    // itself is fl(beta * max V) for a non-negative beta (rounding is monotonic), else the largest rounded product
     double m;
     if ((ALG == NM_ALG_POSITIVE && beta >= 0.0) || (ALG == NM_ALG_NEGATIVE && beta <= 0.0)) {
-      m = __dmul_rn(beta, boot);  // == max_k fl(beta * v_k): rounding is monotonic
+      m = __dmul_rn(beta, boot);
     } else {
+      double z[NM_MAX_CAND];
+#pragma unroll
+      for (int k = 0; k < K; ++k) z[k] = __dmul_rn(beta, v[k]);
       m = extremum<NM_ALG_POSITIVE, K>(z);
     }
-    double e[NM_MAX_CAND];
+    const double neg_m = -m;
+    double x[NM_MAX_CAND], e[NM_MAX_CAND];
 #pragma unroll
-    for (int k = 0; k < K; ++k) e[k] = acc.er.exp_nonpos_ll(__dsub_rn(z[k], m));  // :92-93
+    for (int k = 0; k < K; ++k) x[k] = fma(beta, v[k], neg_m);
+#pragma unroll
+    for (int k = 0; k < K; ++k) e[k] = acc.er(x[k]);  // :93
     const double sum = np_sum_fixed<K>(e);
-    const double zobs = __dmul_rn(beta, lds_f64(vb, q0.w));
-    acc.acc_obs = __dadd_rn(acc.acc_obs, __dsub_rn(zobs, m));
-    acc.prod = __dmul_rn(acc.prod, sum);  // sum in [1, 8]; 32 steps per chunk -> prod <= 2^96
+    acc.acc_obs = __dadd_rn(acc.acc_obs, x[0]);  // log p = val_obs - log(sum): val_obs is candidate 0's argument
+    acc.prod = __dmul_rn(acc.prod, sum);         // sum in [1, 8]; 32 steps per chunk -> prod <= 2^96
   }
   const double rpe = __dsub_rn(__dadd_rn(r, __dmul_rn(gamma, boot)), vs);  // rl.py:185, 228, 257
   *ps = __dadd_rn(vs, __dmul_rn(alpha, rpe));                               // rl.py:186-187, 258-259
@@ -278,7 +293,7 @@ __global__ void __launch_bounds__(512, 1) nm_fit_exact_kernel(const FitArgs a) {
   const Rings rg = carve_rings(smem_raw);
   double *V = reinterpret_cast<double *>(smem_raw + kFixedBytes);
   const int tid = threadIdx.x;
-  if (tid < 16) reinterpret_cast<double *>(smem_raw + kBarBytes + kRawBytes + kDecBytes)[tid] = c_exp2tab[tid];
+  if (tid < 32) reinterpret_cast<double *>(smem_raw + kBarBytes + kRawBytes + kDecBytes)[tid] = c_exp2tab32[tid];
   const int nc = blockDim.x - 32;
   const int sess = blockIdx.y;
   const int64_t p = (int64_t)blockIdx.x * nc + tid;
@@ -365,7 +380,7 @@ __global__ void __launch_bounds__(960, 1) nm_fit_group_kernel(const FitArgs a) {
   const Rings rg = carve_rings(smem_raw);
   double *V = reinterpret_cast<double *>(smem_raw + kFixedBytes);
   const int tid = threadIdx.x;
-  if (tid < 16) reinterpret_cast<double *>(smem_raw + kBarBytes + kRawBytes + kDecBytes)[tid] = c_exp2tab[tid];
+  if (tid < 32) reinterpret_cast<double *>(smem_raw + kBarBytes + kRawBytes + kDecBytes)[tid] = c_exp2tab32[tid];
   const int nw = (blockDim.x >> 5) - 1;
   const int sess = blockIdx.y;
   const int64_t rec0 = a.offsets[sess];
@@ -440,7 +455,7 @@ __global__ void __launch_bounds__(960, 1) nm_fit_global_kernel(const FitArgs a, 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const Rings rg = carve_rings(smem_raw);
   const int tid = threadIdx.x;
-  if (tid < 16) reinterpret_cast<double *>(smem_raw + kBarBytes + kRawBytes + kDecBytes)[tid] = c_exp2tab[tid];
+  if (tid < 32) reinterpret_cast<double *>(smem_raw + kBarBytes + kRawBytes + kDecBytes)[tid] = c_exp2tab32[tid];
   const int nc = blockDim.x - 32;
   const int64_t p = (int64_t)blockIdx.x * nc + tid;
   const bool live = tid < nc && p < a.P;

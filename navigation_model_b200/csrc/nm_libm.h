@@ -103,100 +103,94 @@ NML_HD double nml_taylor_sin(double xx, double x, double dx) {
   return NML_ADD(x, t);
 }
 
-// do_sin(x, dx) for |x| >= 0.126 after the caller's sign handling: ax = |x|, dx already negated when x <= 0.
-// Returns the magnitude (the caller copies the sign of x onto it).
-NML_HD double nml_do_sin_body(double ax, double dx) {
-  const double u = NML_ADD(NML_BIG, ax);
-  const double x = NML_SUB(ax, NML_SUB(u, NML_BIG));
-  const int k = ((int)(uint32_t)NML_BITS(u)) << 2;
-  const double xx = NML_MUL(x, x);
-  const double s = NML_ADD(x, NML_FMA(NML_MUL(x, xx), NML_FMA(NML_SN5, xx, NML_SN3), dx));
-  const double c = NML_FMA(x, dx, NML_MUL(xx, NML_FMA(NML_FMA(NML_CS6, xx, NML_CS4), xx, NML_CS2)));
-  const double *T = NML_TAB(nml_sincostab) + k;
-  const double sn = T[0], ssn = T[1], cs = T[2], ccs = T[3];
-  const double cor = NML_FMA(s, cs, NML_FMA(-c, sn, NML_FMA(s, ccs, ssn)));
-  return NML_ADD(sn, cor);
-}
-
-// do_cos(x, dx): ax = |x|, dx already negated when x < 0
-NML_HD double nml_do_cos_body(double ax, double dx) {
-  const double u = NML_ADD(NML_BIG, ax);
-  const double x = NML_ADD(NML_SUB(ax, NML_SUB(u, NML_BIG)), dx);
-  const int k = ((int)(uint32_t)NML_BITS(u)) << 2;
-  const double xx = NML_MUL(x, x);
-  const double s = NML_FMA(NML_MUL(x, xx), NML_FMA(NML_SN5, xx, NML_SN3), x);
-  const double c = NML_MUL(xx, NML_FMA(NML_FMA(NML_CS6, xx, NML_CS4), xx, NML_CS2));
-  const double *T = NML_TAB(nml_sincostab) + k;
-  const double sn = T[0], ssn = T[1], cs = T[2], ccs = T[3];
-  const double cor = NML_FMA(-s, sn, NML_FMA(-c, cs, NML_FMA(-s, ssn, ccs)));
-  return NML_ADD(cs, cor);
-}
-
-// do_sin(a, da) as the library's inline: Taylor branch below 0.126, sign of a copied onto the table branch
-NML_HD double nml_do_sin(double a, double da) {
+// do_sin(a, da) (is_cos = 0) or do_cos(a, da) (is_cos = 1) of s_sin.c in ONE straight line: the two table-driven bodies
+// differ in four places, each a select here, so a warp whose lanes need different functions does not diverge (the
+// library's own code branches; the operations executed per lane are exactly the library's):
+//   do_sin: if (a <= 0) da = -da;  x = |a| - (u - big);       s = x + (x*xx * P1 + da);  c = x * da + xx * P2;
+//           cor = s * cs + (-(c * sn) + (s * ccs + ssn));  result = copysign(sn + cor, a)   [|a| >= 0.126, else Taylor]
+//   do_cos: if (a <  0) da = -da;  x = |a| - (u - big) + da;  s = x*xx * P1 + x;         c = xx * P2;
+//           cor = -(s * sn) + (-(c * cs) + (-(s * ssn) + ccs));  result = cs + cor
+NML_HD double nml_do_sin_or_cos(double a, double da, int is_cos) {
   const double aa = nml_fabs(a);
-  if (aa < NML_TAYLOR_LIMIT) return nml_taylor_sin(NML_MUL(a, a), a, da);
-  if (a <= 0.0) da = -da;
-  return nml_copysign(nml_do_sin_body(aa, da), a);
-}
-NML_HD double nml_do_cos(double a, double da) {
-  if (a < 0.0) da = -da;
-  return nml_do_cos_body(nml_fabs(a), da);
-}
-
-// reduce_sincos: x = n * pi/2 + (a + da), n mod 4 returned
-NML_HD int nml_reduce_sincos(double x, double *a, double *da) {
-  const double t = NML_FMA(x, NML_HPINV, NML_TOINT);
-  const double xn = NML_SUB(t, NML_TOINT);
-  const double y = NML_FMA(-xn, NML_MP2, NML_FMA(-xn, NML_MP1, x));
-  const int n = (int)((uint32_t)NML_BITS(t) & 3u);
-  const double t2 = NML_FMA(-xn, NML_PP3, y);
-  double db = NML_FMA(-xn, NML_PP3, NML_SUB(y, t2));
-  const double b = NML_FMA(-xn, NML_PP4, t2);
-  db = NML_ADD(db, NML_FMA(-xn, NML_PP4, NML_SUB(t2, b)));
-  *a = b;
-  *da = db;
-  return n;
-}
-
-NML_HD double nml_do_sincos(double a, double da, int n) {
-  const double r = (n & 1) ? nml_do_cos(a, da) : nml_do_sin(a, da);
-  return (n & 2) ? -r : r;
+  if (!is_cos && aa < NML_TAYLOR_LIMIT) return nml_taylor_sin(NML_MUL(a, a), a, da);
+  if (is_cos ? (a < 0.0) : (a <= 0.0)) da = -da;
+  const double u = NML_ADD(NML_BIG, aa);
+  const double x0 = NML_SUB(aa, NML_SUB(u, NML_BIG));
+  const double x = is_cos ? NML_ADD(x0, da) : x0;
+  const int k = ((int)(uint32_t)NML_BITS(u)) << 2;
+  const double xx = NML_MUL(x, x);
+  const double m = NML_MUL(x, xx);
+  const double p1 = NML_FMA(NML_SN5, xx, NML_SN3);
+  const double p2 = NML_MUL(xx, NML_FMA(NML_FMA(NML_CS6, xx, NML_CS4), xx, NML_CS2));
+  const double s = is_cos ? NML_FMA(m, p1, x) : NML_ADD(x, NML_FMA(m, p1, da));
+  const double c = is_cos ? p2 : NML_FMA(x, da, p2);
+  const double *T = NML_TAB(nml_sincostab) + k;
+  const double sn = T[0], ssn = T[1], cs = T[2], ccs = T[3];
+  const double A = is_cos ? cs : sn, dA = is_cos ? ccs : ssn, B = is_cos ? sn : cs, dB = is_cos ? ssn : ccs;
+  const double ss = is_cos ? -s : s;
+  const double res = NML_ADD(A, NML_FMA(ss, B, NML_FMA(-c, A, NML_FMA(ss, dB, dA))));
+  return is_cos ? res : nml_copysign(res, a);
 }
 
 // 1 when nml_sin / nml_cos cover x (finite, below the multi-precision range of the library)
 NML_HD int nml_sincos_in_scope(double x) { return ((uint32_t)(NML_BITS(x) >> 32) & 0x7fffffffu) < 0x419921FBu; }
 
-NML_HD double nml_sin(double x) {
+// __sin and __cos in one pass.  Each is +-do_sin(a, da) or +-do_cos(a, da) for an (a, da) that depends on the range of |x|
+// (s_sin.c): the ranges only SELECT the arguments here; the evaluation is the straight line above, once per function.
+//   |x| < 0.855469:            sin = do_sin(x, 0)                       cos = do_cos(x, 0)
+//   0.855469 <= |x| < 2.426265: sin = copysign(do_cos(hp0 - |x|, hp1), x)  cos = do_sin(y + hp1, (y - (y + hp1)) + hp1), y = hp0 - |x|
+//   2.426265 <= |x| < 1.05e8:  (a, da, n) = reduce_sincos(x);  sin = do_sincos(a, da, n), cos = do_sincos(a, da, n + 1)
+NML_HD void nml_sincos(double x, double *sin_out, double *cos_out) {
   const uint32_t k = (uint32_t)(NML_BITS(x) >> 32) & 0x7fffffffu;
-  if (k < 0x3e500000u) return x;  // |x| < 2^-26
-  if (k < 0x3feb6000u) {          // |x| < 0.855469
-    const double ax = nml_fabs(x);
-    if (ax < NML_TAYLOR_LIMIT) return nml_taylor_sin(NML_MUL(x, x), x, 0.0);
-    return nml_copysign(nml_do_sin_body(ax, x > 0.0 ? 0.0 : -0.0), x);
+  const double ax = nml_fabs(x);
+  double sa, sda, ca, cda;
+  int n_s, n_c, s_copysign_x = 0;
+  if (k < 0x3feb6000u) {
+    sa = ca = x;
+    sda = cda = 0.0;
+    n_s = 0;
+    n_c = 1;
+  } else if (k < 0x400368fdu) {
+    const double y = NML_SUB(NML_HP0, ax);
+    sa = y;
+    sda = NML_HP1;
+    n_s = 1;
+    s_copysign_x = 1;
+    ca = NML_ADD(y, NML_HP1);
+    cda = NML_ADD(NML_SUB(y, ca), NML_HP1);
+    n_c = 0;
+  } else {  // reduce_sincos: x = n * pi/2 + (a + da)
+    const double t = NML_FMA(x, NML_HPINV, NML_TOINT);
+    const double xn = NML_SUB(t, NML_TOINT);
+    const double y = NML_FMA(-xn, NML_MP2, NML_FMA(-xn, NML_MP1, x));
+    const int n = (int)((uint32_t)NML_BITS(t) & 3u);
+    const double t2 = NML_FMA(-xn, NML_PP3, y);
+    double db = NML_FMA(-xn, NML_PP3, NML_SUB(y, t2));
+    const double b = NML_FMA(-xn, NML_PP4, t2);
+    db = NML_ADD(db, NML_FMA(-xn, NML_PP4, NML_SUB(t2, b)));
+    sa = ca = b;
+    sda = cda = db;
+    n_s = n;
+    n_c = n + 1;
   }
-  if (k < 0x400368fdu) {  // 0.855469 <= |x| < 2.426265: cos(pi/2 - |x|), sign of x
-    const double t = NML_SUB(NML_HP0, nml_fabs(x));
-    return nml_copysign(nml_do_cos_body(nml_fabs(t), t >= 0.0 ? NML_HP1 : -NML_HP1), x);
-  }
-  double a, da;
-  const int n = nml_reduce_sincos(x, &a, &da);
-  return nml_do_sincos(a, da, n);
+  double rs = nml_do_sin_or_cos(sa, sda, n_s & 1);
+  double rc = nml_do_sin_or_cos(ca, cda, n_c & 1);
+  if (s_copysign_x) rs = nml_copysign(rs, x);
+  else if (n_s & 2) rs = -rs;
+  if (n_c & 2) rc = -rc;
+  *sin_out = k < 0x3e500000u ? x : rs;    // |x| < 2^-26
+  *cos_out = k < 0x3e400000u ? 1.0 : rc;  // |x| < 2^-27
 }
 
+NML_HD double nml_sin(double x) {
+  double s, c;
+  nml_sincos(x, &s, &c);
+  return s;
+}
 NML_HD double nml_cos(double x) {
-  const uint32_t k = (uint32_t)(NML_BITS(x) >> 32) & 0x7fffffffu;
-  if (k < 0x3e400000u) return 1.0;  // |x| < 2^-27
-  if (k < 0x3feb6000u) return nml_do_cos_body(nml_fabs(x), x >= 0.0 ? 0.0 : -0.0);
-  if (k < 0x400368fdu) {  // sin(pi/2 - |x|) with the 106-bit pi/2
-    const double y = NML_SUB(NML_HP0, nml_fabs(x));
-    const double a = NML_ADD(y, NML_HP1);
-    const double da = NML_ADD(NML_SUB(y, a), NML_HP1);
-    return nml_do_sin(a, da);
-  }
-  double a, da;
-  const int n = nml_reduce_sincos(x, &a, &da);
-  return nml_do_sincos(a, da, n + 1);
+  double s, c;
+  nml_sincos(x, &s, &c);
+  return c;
 }
 
 // ---- atan2 (e_atan2.c) ---------------------------------------------------------------------------------------------
@@ -271,81 +265,62 @@ NML_HD double nml_atan2(double y, double x) {
     const double vv = NML_FMA(u, den, -v);
     du = NML_DIV(NML_SUB(NML_SUB(num, v), vv), den);
   }
+  // Four cases in the library: (i) x > 0, |y| < |x|: atan(u);  (ii) x > 0, |x| <= |y|: pi/2 - atan(u);
+  // (iii) x < 0, |x| < |y|: pi/2 + atan(u);  (iv) x < 0, |y| <= |x|: pi - atan(u).  (ii)-(iv) are one formula with
+  // K = pi/2 or pi (in two pieces K0 + K1) and a sign on u / du / the correction, so they are evaluated as ONE straight
+  // line with selects (x - y == x + (-y) and fma(-a, b, c) == fma(a, -b, c) exactly); (i) keeps its own, more careful
+  // form.  Below 1/16 an odd polynomial, above it the 241-row table of expansions around x_i.
   double z;
-  if (x > 0.0) {
-    if (y_smaller) {  // (i) atan(ay / ax)
-      if (u < 0x1.0p-4) {
-        const double v = NML_MUL(u, u);
-        z = NML_ADD(u, NML_FMA(NML_MUL(u, v), nml_atan_poly(v), du));
-      } else {
-        const double *c = nml_atan_row(u);
-        const double t3 = NML_SUB(u, c[0]);
-        const double v = NML_ADD(t3, du);
-        const double dv = nml_fabs(t3) > nml_fabs(du) ? NML_ADD(NML_SUB(t3, v), du) : NML_ADD(NML_SUB(du, v), t3);
-        double p = NML_FMA(c[6], v, c[5]);
-        p = NML_FMA(p, v, c[4]);
-        p = NML_FMA(p, v, c[3]);
-        const double zz = NML_FMA(v, c[2], NML_FMA(dv, c[2], NML_MUL(NML_MUL(v, v), p)));
-        z = NML_ADD(zz, c[1]);
-      }
-    } else {  // (ii) pi/2 - atan(ax / ay)
-      if (u < 0x1.0p-4) {
-        const double v = NML_MUL(u, u);
-        const double zz = NML_MUL(NML_MUL(u, v), nml_atan_poly(v));
-        const double t2 = NML_SUB(NML_HPI, u);
-        const double cor = NML_SUB(NML_SUB(NML_HPI, t2), u);  // |hpi| > |u| always here
-        z = NML_ADD(NML_SUB(NML_SUB(NML_ADD(cor, NML_HPI1), du), zz), t2);
-      } else {
-        const double *c = nml_atan_row(u);
-        const double v = NML_ADD(NML_SUB(u, c[0]), du);
-        const double zz = NML_FMA(-v, nml_atan_row_poly(c, v), NML_HPI1);
-        z = NML_ADD(NML_SUB(NML_HPI, c[1]), zz);
-      }
+  const int small = u < 0x1.0p-4;
+  if (x > 0.0 && y_smaller) {  // (i)
+    if (small) {
+      const double v = NML_MUL(u, u);
+      z = NML_ADD(u, NML_FMA(NML_MUL(u, v), nml_atan_poly(v), du));
+    } else {
+      const double *c = nml_atan_row(u);
+      const double t3 = NML_SUB(u, c[0]);
+      const double v = NML_ADD(t3, du);
+      const double dv = nml_fabs(t3) > nml_fabs(du) ? NML_ADD(NML_SUB(t3, v), du) : NML_ADD(NML_SUB(du, v), t3);
+      double p = NML_FMA(c[6], v, c[5]);
+      p = NML_FMA(p, v, c[4]);
+      p = NML_FMA(p, v, c[3]);
+      const double zz = NML_FMA(v, c[2], NML_FMA(dv, c[2], NML_MUL(NML_MUL(v, v), p)));
+      z = NML_ADD(zz, c[1]);
     }
   } else {
-    if (!y_smaller) {  // (iii) pi/2 + atan(ax / ay)
-      if (u < 0x1.0p-4) {
-        const double v = NML_MUL(u, u);
-        const double zz = NML_MUL(NML_MUL(u, v), nml_atan_poly(v));
-        const double t2 = NML_ADD(u, NML_HPI);
-        const double cor = NML_ADD(NML_SUB(NML_HPI, t2), u);
-        z = NML_ADD(NML_ADD(NML_ADD(NML_ADD(cor, NML_HPI1), du), zz), t2);
-      } else {
-        const double *c = nml_atan_row(u);
-        const double v = NML_ADD(NML_SUB(u, c[0]), du);
-        const double zz = NML_FMA(v, nml_atan_row_poly(c, v), NML_HPI1);
-        z = NML_ADD(NML_ADD(NML_HPI, c[1]), zz);
-      }
-    } else {  // (iv) pi - atan(ay / ax)
-      if (u < 0x1.0p-4) {
-        const double v = NML_MUL(u, u);
-        const double zz = NML_MUL(NML_MUL(u, v), nml_atan_poly(v));
-        const double t2 = NML_SUB(NML_OPI, u);
-        const double cor = NML_SUB(NML_SUB(NML_OPI, t2), u);
-        z = NML_ADD(NML_SUB(NML_SUB(NML_ADD(cor, NML_OPI1), du), zz), t2);
-      } else {
-        const double *c = nml_atan_row(u);
-        const double v = NML_ADD(NML_SUB(u, c[0]), du);
-        const double zz = NML_FMA(-v, nml_atan_row_poly(c, v), NML_OPI1);
-        z = NML_ADD(NML_SUB(NML_OPI, c[1]), zz);
-      }
+    const int plus = !(x > 0.0) && !y_smaller;             // (iii): + atan(u); (ii), (iv): - atan(u)
+    const int full = !(x > 0.0) && y_smaller;              // (iv): K = pi; (ii), (iii): K = pi/2
+    const double K0 = full ? NML_OPI : NML_HPI, K1 = full ? NML_OPI1 : NML_HPI1;
+    if (small) {
+      const double v = NML_MUL(u, u);
+      const double zz = NML_MUL(NML_MUL(u, v), nml_atan_poly(v));
+      const double su = plus ? u : -u, sdu = plus ? du : -du, szz = plus ? zz : -zz;
+      const double t2 = NML_ADD(K0, su);
+      const double cor = NML_ADD(NML_SUB(K0, t2), su);
+      z = NML_ADD(NML_ADD(NML_ADD(NML_ADD(cor, K1), sdu), szz), t2);
+    } else {
+      const double *c = nml_atan_row(u);
+      const double v = NML_ADD(NML_SUB(u, c[0]), du);
+      const double zz = NML_FMA(plus ? v : -v, nml_atan_row_poly(c, v), K1);
+      z = NML_ADD(NML_ADD(K0, plus ? c[1] : -c[1]), zz);
     }
   }
   return nml_copysign(z, y);
 }
 
 #if defined(__CUDACC__)
-// Device entry points (out of line: three call sites in a kernel share one copy of the code).  Out-of-scope arguments
-// (|heading| >= 1.05e8, non-finite values) fall back to the CUDA functions.
-static __device__ __noinline__ void nm_host_sincos(double x, double *s, double *c) {
+// Device entry points.  Out-of-scope arguments (|heading| >= 1.05e8, non-finite values) fall back to the CUDA functions.
+#ifndef NM_LIBM_CALL
+#define NM_LIBM_CALL __forceinline__  // measured on the simulation kernel: 171 ms inline against 187 ms out of line
+#endif
+static __device__ NM_LIBM_CALL void nm_host_sincos(double x, double *s, double *c) {
   if (nml_sincos_in_scope(x)) {
-    *s = nml_sin(x);
-    *c = nml_cos(x);
+    nml_sincos(x, s, c);
   } else {
     sincos(x, s, c);
   }
 }
-static __device__ __noinline__ double nm_host_atan2(double y, double x) {
+static __device__ NM_LIBM_CALL double nm_host_atan2(double y, double x) {
   return nml_atan2_in_scope(y, x) ? nml_atan2(y, x) : atan2(y, x);
 }
 #endif
