@@ -82,49 +82,95 @@ struct ExpRegs {
 // ---- exponentials of a LIKELIHOOD step (softmax denominator) ---------------------------------------------------------
 // Bar: 1e-9 relative on a session's log-likelihood (BASELINE.json north_star), not the last bit -- value tables never see
 // an exponential, and the simulation kernel (whose discrete choices must reproduce the reference's) keeps exp_nonpos.
-// exp(x), x <= ~0:  x = (32 e + j) * ln2/32 + r, |r| <= ln2/64:  exp(x) = 2^e * 2^(j/32) * P4(r)
-//   * ONE fused step of range reduction against the double nearest to ln2/32 (error |x| * 1.1e-16 relative -- a term of
+// exp(x), x <= ~0:  x = (64 e + j) * ln2/64 + r, |r| <= ln2/128:  exp(x) = 2^e * 2^(j/64) * P3(r)
+//   * ONE fused step of range reduction against the double nearest to ln2/64 (error |x| * 1.1e-16 relative -- a term of
 //     weight exp(x) <= 1 in a sum >= 1 moves it by < 5e-17);
-//   * a 32-entry table (two 128-byte shared-memory rows) and a degree-4 Taylor polynomial: truncation r^5/120 <= 1.25e-12
-//     relative per exponential, of either sign;
+//   * a 64-entry table (four 128-byte shared-memory rows) and a degree-3 Taylor polynomial: truncation r^4/24 <= 3.6e-11
+//     relative per exponential (mean 7e-12), always low: a session's log-likelihood moves by < 1e-11 relative;
 //   * the caller forms x = fma(beta, v, -m) in one instruction.
-// 8 FP64 instructions + the caller's fma instead of 10 + 2 (round 1's degree-5 / 16-entry form), 4 integer instructions
-// instead of 6.  The binary exponent is clamped (k >= -1021 * 32) so that a hugely negative x gives ~2^-1021, not garbage.
-__constant__ double c_exp2tab32[32] = {
-    1.00000000000000000e+00, 1.02189714865411663e+00, 1.04427378242741375e+00, 1.06714040067682370e+00,
-    1.09050773266525769e+00, 1.11438674259589243e+00, 1.13878863475669156e+00, 1.16372485877757748e+00,
-    1.18920711500272103e+00, 1.21524735998046896e+00, 1.24185781207348400e+00, 1.26905095719173322e+00,
-    1.29683955465100964e+00, 1.32523664315974132e+00, 1.35425554693689265e+00, 1.38390988196383202e+00,
-    1.41421356237309515e+00, 1.44518080697704665e+00, 1.47682614593949935e+00, 1.50916442759342284e+00,
-    1.54221082540794074e+00, 1.57598084510788650e+00, 1.61049033194925428e+00, 1.64575547815396495e+00,
-    1.68179283050742900e+00, 1.71861929812247793e+00, 1.75625216037329945e+00, 1.79470907500310717e+00,
-    1.83400808640934243e+00, 1.87416763411029996e+00, 1.91520656139714740e+00, 1.95714412417540018e+00};
-__constant__ double c_expll_k[5] = {4.61662413084468283841e+01,   // 32 * log2(e)
+// 7 FP64 instructions + the caller's fma instead of 10 + 2 (round 1's degree-5 / 16-entry form), 5 integer instructions
+// instead of 6.  An FP64 warp instruction holds a scheduler's issue port for two cycles on this part (64 lanes / clk / SM),
+// so each one saved is worth two of the others.  The binary exponent is clamped (k >= -1021 * 64) so that a hugely
+// negative x gives ~2^-1021, not garbage.
+__constant__ double c_exp2tab64[64] = {
+    1.00000000000000000e+00, 1.01088928605170048e+00, 1.02189714865411663e+00, 1.03302487902122841e+00,
+    1.04427378242741375e+00, 1.05564517836055716e+00, 1.06714040067682370e+00, 1.07876079775711986e+00,
+    1.09050773266525769e+00, 1.10238258330784089e+00, 1.11438674259589243e+00, 1.12652161860824185e+00,
+    1.13878863475669156e+00, 1.15118922995298267e+00, 1.16372485877757748e+00, 1.17639699165028122e+00,
+    1.18920711500272103e+00, 1.20215673145270308e+00, 1.21524735998046896e+00, 1.22848053610687002e+00,
+    1.24185781207348400e+00, 1.25538075702469110e+00, 1.26905095719173322e+00, 1.28287001607877826e+00,
+    1.29683955465100964e+00, 1.31096121152476441e+00, 1.32523664315974132e+00, 1.33966752405330292e+00,
+    1.35425554693689265e+00, 1.36900242297459052e+00, 1.38390988196383202e+00, 1.39897967253831124e+00,
+    1.41421356237309515e+00, 1.42961333839197002e+00, 1.44518080697704665e+00, 1.46091779418064704e+00,
+    1.47682614593949935e+00, 1.49290772829126484e+00, 1.50916442759342284e+00, 1.52559815074453842e+00,
+    1.54221082540794074e+00, 1.55900440023783693e+00, 1.57598084510788650e+00, 1.59314215134226700e+00,
+    1.61049033194925428e+00, 1.62802742185734783e+00, 1.64575547815396495e+00, 1.66367658032673638e+00,
+    1.68179283050742900e+00, 1.70010635371852348e+00, 1.71861929812247793e+00, 1.73733383527370622e+00,
+    1.75625216037329945e+00, 1.77537649252652119e+00, 1.79470907500310717e+00, 1.81425217550039886e+00,
+    1.83400808640934243e+00, 1.85397912508338547e+00, 1.87416763411029996e+00, 1.89457598158696561e+00,
+    1.91520656139714740e+00, 1.93606179349229435e+00, 1.95714412417540018e+00, 1.97845602638795093e+00};
+__constant__ double c_expll_k[4] = {9.23324826168936567683e+01,   // 64 * log2(e)
                                     6755399441055744.0,           // 1.5 * 2^52
-                                    -2.16608493924982901946e-02,  // -ln2/32 (nearest double)
-                                    1.0 / 24.0, 1.0 / 6.0};
+                                    -1.08304246962491450973e-02,  // -ln2/64 (nearest double)
+                                    1.0 / 6.0};
 
 struct ExpLL {
-  double c[5];
-  uint32_t tab;  // shared-window address of 32 doubles holding c_exp2tab32 (the kernel fills them)
-  __device__ __forceinline__ void load(uint32_t table_addr) {
+  double c[4];
+  uint32_t tab;  // shared-window address of 64 doubles holding c_exp2tab64, 512-BYTE ALIGNED (the entry index is OR-ed in)
+  // `region`: 1024 bytes of shared memory; the table sits at the first 512-byte boundary inside it.
+  // fill(): threads 0..63 of the CTA write the table -- call it BEFORE the __syncthreads() that precedes the first use.
+  static __device__ __forceinline__ void fill(unsigned char *region, int tid) {
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(region);
+    if (tid < 64) reinterpret_cast<double *>(region + (((base + 511u) & ~511u) - base))[tid] = c_exp2tab64[tid];
+  }
+  __device__ __forceinline__ void load(unsigned char *region) {
 #pragma unroll
-    for (int i = 0; i < 5; ++i) asm volatile("mov.f64 %0, %1;" : "=d"(c[i]) : "d"(c_expll_k[i]));
-    tab = table_addr;
+    for (int i = 0; i < 4; ++i) asm volatile("mov.f64 %0, %1;" : "=d"(c[i]) : "d"(c_expll_k[i]));
+    tab = ((uint32_t)__cvta_generic_to_shared(region) + 511u) & ~511u;
   }
   __device__ __forceinline__ double operator()(double x) const {
     const double t = fma(x, c[0], c[1]);
-    const int k = max(__double2loint(t), -1021 * 32);  // round(32 x / ln2), clamped
+    const uint32_t k8 = (uint32_t)max(__double2loint(t), -1021 * 64) << 3;  // 8 * round(64 x / ln2), clamped
     const double r = fma(__dsub_rn(t, c[1]), c[2], x);
     double s;
-    asm("ld.shared.f64 %0, [%1];" : "=d"(s) : "r"(tab + (((uint32_t)k << 3) & 0xf8u)));
-    double p = fma(c[3], r, c[4]);
-    p = fma(p, r, 0.5);
+    asm("ld.shared.f64 %0, [%1];" : "=d"(s) : "r"(tab | (k8 & 0x1f8u)));
+    double p = fma(c[3], r, 0.5);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
     p = __dmul_rn(p, s);
-    return __hiloint2double(__double2hiint(p) + (k & ~31) * 32768, __double2loint(p));  // += (k >> 5) << 20
+    // binary exponent: hi += (k >> 6) << 20 = (k8 & ~0x1ff) * 2048
+    return __hiloint2double(__double2hiint(p) + (int)(k8 & 0xfffffe00u) * 2048, __double2loint(p));
   }
 };
+
+// log(x) for the per-chunk fold of the likelihood kernels: x = product of 32 softmax denominators, in [1, 2^96] (normal,
+// positive -- no special cases).  x = 2^e * m, m in [sqrt(1/2), sqrt(2)):  log x = e * ln2 + 2 atanh(s), s = (m-1)/(m+1),
+// |s| <= 0.1716: odd series to s^19 (next term 2 s^21 / 21 < 8e-18).  ~30 instructions against ~200 of the library log
+// (whose denormal / special-value paths this range never takes); relative error < 3e-16 -- far inside the 1e-9 bar.
+__device__ __forceinline__ double log_chunk_product(double x) {
+  int hi = __double2hiint(x);
+  int e = (hi >> 20) - 1023;
+  hi = (hi & 0x000fffff) | 0x3ff00000;  // m in [1, 2)
+  if (hi >= 0x3ff6a09f) {               // m >= sqrt(2): halve it
+    hi -= 0x00100000;
+    e += 1;
+  }
+  const double m = __hiloint2double(hi, __double2loint(x));
+  const double s = __ddiv_rn(__dsub_rn(m, 1.0), __dadd_rn(m, 1.0));
+  const double s2 = __dmul_rn(s, s);
+  double p = 2.0 / 19.0;
+  p = fma(p, s2, 2.0 / 17.0);
+  p = fma(p, s2, 2.0 / 15.0);
+  p = fma(p, s2, 2.0 / 13.0);
+  p = fma(p, s2, 2.0 / 11.0);
+  p = fma(p, s2, 2.0 / 9.0);
+  p = fma(p, s2, 2.0 / 7.0);
+  p = fma(p, s2, 2.0 / 5.0);
+  p = fma(p, s2, 2.0 / 3.0);
+  p = fma(p, s2, 2.0);
+  // e * ln2 in two pieces (hi part exact for |e| < 2^20), then the series
+  const double de = (double)e;
+  return fma(de, 6.93147180369123816490e-01, fma(de, 1.90821492927058770002e-10, __dmul_rn(p, s)));
+}
 
 #endif  // NM_EXP_CUH

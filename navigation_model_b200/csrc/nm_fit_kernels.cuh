@@ -30,11 +30,15 @@
 
 constexpr int kChunk = 32;      // records per chunk = one per producer lane
 constexpr int kRawStages = 2;   // raw (TMA landing) ring
-constexpr int kDecStages = 4;   // decoded ring
+#ifndef NM_FIT_DEC_STAGES
+#define NM_FIT_DEC_STAGES 4
+#endif
+constexpr int kDecStages = NM_FIT_DEC_STAGES;   // decoded ring
 constexpr int kRawBytes = kRawStages * kChunk * 32;
 constexpr int kDecBytes = kDecStages * kChunk * 64;
-constexpr int kBarBytes = 128;  // full_raw[2], full_dec[4], empty_dec[4]
-constexpr int kTabBytes = 256;  // 2^(j/32), j = 0..31: two shared-memory rows (ExpLL, nm_exp.cuh)
+constexpr int kBarBytes = 256;  // full_raw[2], full_dec[kDecStages], empty_dec[kDecStages]
+static_assert((kRawStages + 2 * kDecStages) * 8 <= kBarBytes, "mbarrier block too small");
+constexpr int kTabBytes = 1024;  // room for the 512-byte-aligned 2^(j/64) table of ExpLL (nm_exp.cuh)
 constexpr int kFixedBytes = kBarBytes + kRawBytes + kDecBytes + kTabBytes;
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 
@@ -293,7 +297,6 @@ __global__ void __launch_bounds__(512, 1) nm_fit_exact_kernel(const FitArgs a) {
   const Rings rg = carve_rings(smem_raw);
   double *V = reinterpret_cast<double *>(smem_raw + kFixedBytes);
   const int tid = threadIdx.x;
-  if (tid < 32) reinterpret_cast<double *>(smem_raw + kBarBytes + kRawBytes + kDecBytes)[tid] = c_exp2tab32[tid];
   const int nc = blockDim.x - 32;
   const int sess = blockIdx.y;
   const int64_t p = (int64_t)blockIdx.x * nc + tid;
@@ -308,6 +311,7 @@ __global__ void __launch_bounds__(512, 1) nm_fit_exact_kernel(const FitArgs a) {
   const int64_t n_on = a.online[sess];
   const int nchunks = (int)((n + kChunk - 1) / kChunk);
   if (tid == 0) init_rings(rg, nc >> 5);
+  ExpLL::fill(smem_raw + kBarBytes + kRawBytes + kDecBytes, tid);
   __syncthreads();
 
   if (tid >= nc) {
@@ -323,7 +327,7 @@ __global__ void __launch_bounds__(512, 1) nm_fit_exact_kernel(const FitArgs a) {
     ExactAcc acc;
     acc.acc_obs = 0.0;
     acc.prod = 1.0;
-    acc.er.load(smem_u32(smem_raw + kBarBytes + kRawBytes + kDecBytes));
+    acc.er.load(smem_raw + kBarBytes + kRawBytes + kDecBytes);
     const int lane = tid & 31;
     for (int c = 0; c < nchunks; ++c) {
       const int dslot = c % kDecStages;
@@ -334,7 +338,7 @@ __global__ void __launch_bounds__(512, 1) nm_fit_exact_kernel(const FitArgs a) {
 #pragma unroll 1
       for (int i = 0; i < cnt; ++i) exact_step<ALG, LL>(recs + 4 * i, vb, alpha, beta, gamma, acc);
       if (LL) {  // fold the chunk:  ll += sum(zobs - m) - log(prod of the softmax denominators)
-        ll = __dadd_rn(ll, __dsub_rn(acc.acc_obs, log(acc.prod)));
+        ll = __dadd_rn(ll, __dsub_rn(acc.acc_obs, log_chunk_product(acc.prod)));
         acc.acc_obs = 0.0;
         acc.prod = 1.0;
       }
@@ -380,7 +384,6 @@ __global__ void __launch_bounds__(960, 1) nm_fit_group_kernel(const FitArgs a) {
   const Rings rg = carve_rings(smem_raw);
   double *V = reinterpret_cast<double *>(smem_raw + kFixedBytes);
   const int tid = threadIdx.x;
-  if (tid < 32) reinterpret_cast<double *>(smem_raw + kBarBytes + kRawBytes + kDecBytes)[tid] = c_exp2tab32[tid];
   const int nw = (blockDim.x >> 5) - 1;
   const int sess = blockIdx.y;
   const int64_t rec0 = a.offsets[sess];
@@ -388,6 +391,7 @@ __global__ void __launch_bounds__(960, 1) nm_fit_group_kernel(const FitArgs a) {
   const int64_t n_on = a.online[sess];
   const int nchunks = (int)((n + kChunk - 1) / kChunk);
   if (tid == 0) init_rings(rg, nw);
+  ExpLL::fill(smem_raw + kBarBytes + kRawBytes + kDecBytes, tid);
   __syncthreads();
 
   const int warp = tid >> 5, lane = tid & 31;
@@ -408,7 +412,7 @@ __global__ void __launch_bounds__(960, 1) nm_fit_group_kernel(const FitArgs a) {
     ExactAcc acc;
     acc.acc_obs = 0.0;
     acc.prod = 1.0;
-    acc.er.load(smem_u32(smem_raw + kBarBytes + kRawBytes + kDecBytes));
+    acc.er.load(smem_raw + kBarBytes + kRawBytes + kDecBytes);
     for (int c = 0; c < nchunks; ++c) {
       const int dslot = c % kDecStages;
       mbar_wait(&rg.full_dec[dslot], (uint32_t)((c / kDecStages) & 1));
@@ -417,7 +421,7 @@ __global__ void __launch_bounds__(960, 1) nm_fit_group_kernel(const FitArgs a) {
       const int cnt = (int)(n - first < kChunk ? n - first : kChunk);
 #pragma unroll 1
       for (int i = 0; i < cnt; ++i) exact_step<ALG, true>(recs + 4 * i, vb, alpha, beta, gamma, acc);
-      ll = __dadd_rn(ll, __dsub_rn(acc.acc_obs, log(acc.prod)));  // fold the chunk exactly like the exact kernel
+      ll = __dadd_rn(ll, __dsub_rn(acc.acc_obs, log_chunk_product(acc.prod)));  // fold the chunk exactly like the exact kernel
       acc.acc_obs = 0.0;
       acc.prod = 1.0;
       __syncwarp();
@@ -455,7 +459,6 @@ __global__ void __launch_bounds__(960, 1) nm_fit_global_kernel(const FitArgs a, 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const Rings rg = carve_rings(smem_raw);
   const int tid = threadIdx.x;
-  if (tid < 32) reinterpret_cast<double *>(smem_raw + kBarBytes + kRawBytes + kDecBytes)[tid] = c_exp2tab32[tid];
   const int nc = blockDim.x - 32;
   const int64_t p = (int64_t)blockIdx.x * nc + tid;
   const bool live = tid < nc && p < a.P;
@@ -464,6 +467,7 @@ __global__ void __launch_bounds__(960, 1) nm_fit_global_kernel(const FitArgs a, 
   const int64_t n_on = a.online[sess];
   const int nchunks = (int)((n + kChunk - 1) / kChunk);
   if (tid == 0) init_rings(rg, nc >> 5);
+  ExpLL::fill(smem_raw + kBarBytes + kRawBytes + kDecBytes, tid);
   __syncthreads();
 
   if (tid >= nc) {
@@ -486,7 +490,7 @@ __global__ void __launch_bounds__(960, 1) nm_fit_global_kernel(const FitArgs a, 
     ExactAcc acc;
     acc.acc_obs = 0.0;
     acc.prod = 1.0;
-    acc.er.load(smem_u32(smem_raw + kBarBytes + kRawBytes + kDecBytes));
+    acc.er.load(smem_raw + kBarBytes + kRawBytes + kDecBytes);
     const int lane = tid & 31;
     for (int c = 0; c < nchunks; ++c) {
       const int dslot = c % kDecStages;
@@ -499,7 +503,7 @@ __global__ void __launch_bounds__(960, 1) nm_fit_global_kernel(const FitArgs a, 
         for (int i = 0; i < cnt; ++i) exact_step<ALG, LL>(recs + 4 * i, vb, alpha, beta, gamma, acc);
       }
       if (LL) {
-        ll = __dadd_rn(ll, __dsub_rn(acc.acc_obs, log(acc.prod)));
+        ll = __dadd_rn(ll, __dsub_rn(acc.acc_obs, log_chunk_product(acc.prod)));
         acc.acc_obs = 0.0;
         acc.prod = 1.0;
       }
@@ -608,6 +612,7 @@ __global__ void __launch_bounds__(512, 1) nm_fit_memo_kernel(const FitArgs a) {
   const int64_t n_on = a.online[sess];
   const int nchunks = (int)((n + kChunk - 1) / kChunk);
   if (tid == 0) init_rings(rg, nc >> 5);
+  ExpLL::fill(smem_raw + kBarBytes + kRawBytes + kDecBytes, tid);
   __syncthreads();
 
   if (tid >= nc) {
