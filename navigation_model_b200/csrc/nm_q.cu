@@ -78,11 +78,11 @@ __global__ void __launch_bounds__(512) nm_q_kernel(const QArgs a) {
   const int S = a.S, A = a.A;
   const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int oct = lane >> 3, k = lane & 7;
-  double *exptab = reinterpret_cast<double *>(smem_raw);                 // 128 B
-  int16_t *nxt8 = reinterpret_cast<int16_t *>(smem_raw + 128);           // [S][8], -1 = unavailable
+  unsigned char *exptab = smem_raw;                                       // 1024 B (ExpLL table region)
+  int16_t *nxt8 = reinterpret_cast<int16_t *>(smem_raw + 1024);          // [S][8], -1 = unavailable
   const size_t nxt_bytes = ((size_t)S * 16 + 127) & ~(size_t)127;
-  double *Q = reinterpret_cast<double *>(smem_raw + 128 + nxt_bytes + (size_t)(warp * 4 + oct) * a.stride);
-  if (threadIdx.x < 16) exptab[threadIdx.x] = c_exp2tab[threadIdx.x];
+  double *Q = reinterpret_cast<double *>(smem_raw + 1024 + nxt_bytes + (size_t)(warp * 4 + oct) * a.stride);
+  ExpLL::fill(exptab, (int)threadIdx.x);
   for (int i = threadIdx.x; i < S * 8; i += blockDim.x) {
     const int u = i >> 3, kk = i & 7;
     nxt8[i] = kk < A ? a.next[u * A + kk] : (int16_t)-1;
@@ -94,8 +94,8 @@ __global__ void __launch_bounds__(512) nm_q_kernel(const QArgs a) {
   for (int u = 0; u < S; ++u)
     Q[u * 8 + k] = (a.q_init && k < A) ? a.q_init[(int64_t)a.tile_of_state[u] * A + k] : 0.0;
   __syncthreads();
-  ExpRegs er;
-  er.load((uint32_t)__cvta_generic_to_shared(exptab));
+  ExpLL er;
+  er.load(exptab);
 
   const int64_t rec0 = a.offsets[sess];
   const int64_t n = a.offsets[sess + 1] - rec0, n_on = a.online[sess];
@@ -140,8 +140,8 @@ __global__ void __launch_bounds__(512) nm_q_kernel(const QArgs a) {
       octet_max2(boot, m);
       if (!st.avail1) boot = 0.0;
       if (i < n_on32) {
-        const double zc = __dsub_rn(z, m);  // :92
-        const double e = st.ok ? er.exp_nonpos(dmax2(zc, -800.0)) : 0.0;  // :93
+        const double zc = fma(beta, q, -m);  // :92, fused like the per-warp-table kernel (bit-identical results)
+        const double e = st.ok ? er(zc) : 0.0;  // :93
         // every lane gathers the octet's eight terms (sixteen independent shuffles), then adds them in numpy's order:
         // pairwise for n == 8, else sequentially from 0.0 over the available actions -- an unavailable action's term
         // is +0.0, and x + 0.0 == x bit for bit for the non-negative partial sums, so nothing needs to be skipped
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(512) nm_q_kernel(const QArgs a) {
       }
     }
     if ((i & 31) == 31 || i + 1 == n32) {  // fold: at most 32 sums, each in [1, 8] -> prod <= 2^96
-      ll = __dadd_rn(ll, __dsub_rn(acc_obs, log(prod)));
+      ll = __dadd_rn(ll, __dsub_rn(acc_obs, log_chunk_product(prod)));
       acc_obs = 0.0;
       prod = 1.0;
     }
@@ -190,7 +190,7 @@ constexpr int kQDecWords = 5;   // uint4 per decoded record (80 bytes)
 constexpr int kQBarBytes = 128;
 constexpr int kQRawBytes = kQRawStages * kQChunk * 32;
 constexpr int kQDecBytes = kQDecStages * kQChunk * kQDecWords * 16;
-constexpr int kQTabBytes = 128;  // 2^(j/16)
+constexpr int kQTabBytes = 1024;  // room for the 512-byte-aligned 2^(j/64) table of ExpLL (nm_exp.cuh)
 constexpr int kQFixedBytes = kQBarBytes + kQRawBytes + kQDecBytes + kQTabBytes;
 constexpr uint32_t kQOnline = 1u << 8, kQHit = 1u << 9, kQBoot = 1u << 10;
 
@@ -264,7 +264,7 @@ __device__ __forceinline__ void q_producer_loop(const QRings &rg, const nm_step_
 
 struct QAcc {
   double acc_obs, prod;
-  ExpRegs er;
+  ExpLL er;  // likelihood exponentials: nm_exp.cuh (1e-9 bar on the session's log-likelihood, tables never see them)
 };
 
 template <int K1>
@@ -282,16 +282,23 @@ __device__ __forceinline__ void qgroup_step_k(const uint4 q0, const uint4 q1, co
   if (!(q0.z & kQBoot)) boot = 0.0;
   if (q0.z & kQOnline) {
     const uint32_t o1[8] = {q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
-    double v[NM_MAX_CAND], z[NM_MAX_CAND], e[NM_MAX_CAND];
+    double v[NM_MAX_CAND], e[NM_MAX_CAND];
 #pragma unroll
     for (int k = 0; k < K1; ++k) v[k] = lds_f64(qb, o1[k]);
+    // beta >= 0: max_k fl(beta * v_k) == fl(beta * max_k v_k), rounding is monotonic   (exploration_model.py:87, 92)
+    double m;
+    if (beta >= 0.0) {
+      m = __dmul_rn(beta, extremum<NM_ALG_POSITIVE, K1>(v));
+    } else {
+      double z[NM_MAX_CAND];
 #pragma unroll
-    for (int k = 0; k < K1; ++k) z[k] = __dmul_rn(beta, v[k]);  // exploration_model.py:87
-    // beta >= 0: max_k fl(beta * v_k) == fl(beta * max_k v_k), rounding is monotonic
-    const double m = (beta >= 0.0) ? __dmul_rn(beta, extremum<NM_ALG_POSITIVE, K1>(v)) : extremum<NM_ALG_POSITIVE, K1>(z);
+      for (int k = 0; k < K1; ++k) z[k] = __dmul_rn(beta, v[k]);
+      m = extremum<NM_ALG_POSITIVE, K1>(z);
+    }
+    const double neg_m = -m;
 #pragma unroll
-    for (int k = 0; k < K1; ++k) e[k] = acc.er.exp_nonpos(dmax(__dsub_rn(z[k], m), -800.0));  // :92-93
-    acc.acc_obs = __dadd_rn(acc.acc_obs, __dsub_rn(__dmul_rn(beta, q), m));
+    for (int k = 0; k < K1; ++k) e[k] = acc.er(fma(beta, v[k], neg_m));  // :92-93, one fused argument per action
+    acc.acc_obs = __dadd_rn(acc.acc_obs, fma(beta, q, neg_m));
     acc.prod = __dmul_rn(acc.prod, np_sum_fixed<K1>(e));
   }
   const double rpe = __dsub_rn(__dadd_rn(r, __dmul_rn(gamma, boot)), q);  // update form of rl.py:185
@@ -324,13 +331,13 @@ __global__ void __launch_bounds__(960, 1) nm_qgroup_kernel(const QArgs a) {
   rg.empty_dec = rg.full_dec + kQDecStages;
   rg.raw = reinterpret_cast<uint4 *>(smem_raw + kQBarBytes);
   rg.dec = reinterpret_cast<uint4 *>(smem_raw + kQBarBytes + kQRawBytes);
-  double *exptab = reinterpret_cast<double *>(smem_raw + kQBarBytes + kQRawBytes + kQDecBytes);
+  unsigned char *exptab = smem_raw + kQBarBytes + kQRawBytes + kQDecBytes;
   int16_t *nxt8 = reinterpret_cast<int16_t *>(smem_raw + kQFixedBytes);
   const size_t nxt_bytes = ((size_t)S * 16 + 127) & ~(size_t)127;
   double *Q = reinterpret_cast<double *>(smem_raw + kQFixedBytes + nxt_bytes);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nw = (blockDim.x >> 5) - 1;
-  if (tid < 16) exptab[tid] = c_exp2tab[tid];
+  ExpLL::fill(exptab, tid);
   for (int i = tid; i < S * 8; i += blockDim.x) {
     const int u = i >> 3, kk = i & 7;
     nxt8[i] = kk < A ? a.next[u * A + kk] : (int16_t)-1;
@@ -371,7 +378,7 @@ __global__ void __launch_bounds__(960, 1) nm_qgroup_kernel(const QArgs a) {
     QAcc acc;
     acc.acc_obs = 0.0;
     acc.prod = 1.0;
-    acc.er.load(smem_u32(exptab));
+    acc.er.load(exptab);
     for (int c = 0; c < nchunks; ++c) {
       const int dslot = c % kQDecStages;
       mbar_wait(&rg.full_dec[dslot], (uint32_t)((c / kQDecStages) & 1));
@@ -380,7 +387,7 @@ __global__ void __launch_bounds__(960, 1) nm_qgroup_kernel(const QArgs a) {
       const int cnt = (int)(n - first < kQChunk ? n - first : kQChunk);
 #pragma unroll 1
       for (int i = 0; i < cnt; ++i) qgroup_step(recs + kQDecWords * i, qb, alpha, beta, gamma, acc);
-      ll = __dadd_rn(ll, __dsub_rn(acc.acc_obs, log(acc.prod)));  // the octet kernel folds every 32 records too
+      ll = __dadd_rn(ll, __dsub_rn(acc.acc_obs, log_chunk_product(acc.prod)));  // the octet kernel folds every 32 records too
       acc.acc_obs = 0.0;
       acc.prod = 1.0;
       __syncwarp();
@@ -422,11 +429,11 @@ __global__ void __launch_bounds__(960, 1) nm_qglobal_kernel(const QArgs a, doubl
   rg.empty_dec = rg.full_dec + kQDecStages;
   rg.raw = reinterpret_cast<uint4 *>(smem_raw + kQBarBytes);
   rg.dec = reinterpret_cast<uint4 *>(smem_raw + kQBarBytes + kQRawBytes);
-  double *exptab = reinterpret_cast<double *>(smem_raw + kQBarBytes + kQRawBytes + kQDecBytes);
+  unsigned char *exptab = smem_raw + kQBarBytes + kQRawBytes + kQDecBytes;
   int16_t *nxt8 = reinterpret_cast<int16_t *>(smem_raw + kQFixedBytes);
   const int tid = threadIdx.x, lane = tid & 31;
   const int nc = blockDim.x - 32;
-  if (tid < 16) exptab[tid] = c_exp2tab[tid];
+  ExpLL::fill(exptab, tid);
   for (int i = tid; i < S * 8; i += blockDim.x) {
     const int u = i >> 3, kk = i & 7;
     nxt8[i] = kk < A ? a.next[u * A + kk] : (int16_t)-1;
@@ -465,7 +472,7 @@ __global__ void __launch_bounds__(960, 1) nm_qglobal_kernel(const QArgs a, doubl
     QAcc acc;
     acc.acc_obs = 0.0;
     acc.prod = 1.0;
-    acc.er.load(smem_u32(exptab));
+    acc.er.load(exptab);
     for (int c = 0; c < nchunks; ++c) {
       const int dslot = c % kQDecStages;
       mbar_wait(&rg.full_dec[dslot], (uint32_t)((c / kQDecStages) & 1));
@@ -476,7 +483,7 @@ __global__ void __launch_bounds__(960, 1) nm_qglobal_kernel(const QArgs a, doubl
 #pragma unroll 1
         for (int i = 0; i < cnt; ++i) qgroup_step(recs + kQDecWords * i, qb, alpha, beta, gamma, acc);
       }
-      ll = __dadd_rn(ll, __dsub_rn(acc.acc_obs, log(acc.prod)));
+      ll = __dadd_rn(ll, __dsub_rn(acc.acc_obs, log_chunk_product(acc.prod)));
       acc.acc_obs = 0.0;
       acc.prod = 1.0;
       __syncwarp();
@@ -569,7 +576,7 @@ extern "C" int nm_qtable_sweep(const nm_maze *mz, const nm_streams *st, const in
   NM_CHECK_ARG(S <= 32767, "nm_qtable_sweep: at most 32767 states (16-bit successor ids)");
   size_t stride = (size_t)S * 64;
   if ((stride & 127) == 0) stride += 64;  // 64 (mod 128): the two octets of a half-warp use different bank halves
-  const size_t fixed = 128 + (((size_t)S * 16 + 127) & ~(size_t)127);
+  const size_t fixed = 1024 + (((size_t)S * 16 + 127) & ~(size_t)127);  // ExpLL table region + packed next[S][8]
   const size_t per_warp = 4 * stride;
   // CTAs per SM x warps per CTA: as many resident warps as 227 KB of shared memory (1 KB reserved per CTA) allow
   int warps = 0, best_total = 0;
