@@ -225,7 +225,7 @@ int nm_vtable_sweep(int alg, const nm_maze *mz, const nm_streams *st, const doub
                     double *d_v_out, void *stream);
 
 /* Largest number of visitable tiles (compact states) the per-parameter-set value-table kernels can hold in SHARED
- * memory (867 with 227 KB: 32 table columns of 8 bytes per state next to the stream rings).  Larger mazes run the same
+ * memory (863 with 227 KB: 32 table columns of 8 bytes per state next to the stream rings).  Larger mazes run the same
  * sweeps with their tables in device memory (T[state][parameter set], coalesced, L2 / HBM resident; also on request
  * with NM_FIT_TABLES=global): same results, no size limit. */
 int nm_vtable_max_states(void);
@@ -365,6 +365,11 @@ typedef struct nm_sim_args {
   int64_t mouse_index_base;                /* use_device_seed: mouse n seeds its stream from (device_seed,
                                               mouse_index_base + n), so a population gives the same mice whatever the
                                               number of shards                                                  */
+  /* ---- mazes whose visit map does not fit shared memory (nm_simulate_fits == 2) ---- */
+  uint32_t *d_visit_scratch;               /* [X*Y, visit_scratch_columns] 32-bit words of device memory for the visit
+                                              maps (count[tile][launched thread]); contents on entry are ignored.
+                                              NULL when the shared-memory map is used                             */
+  int64_t visit_scratch_columns;           /* >= nm_simulate_scratch_columns(n_mice)                             */
 } nm_sim_args;
 
 /* StandardExperiment.run(n_steps) for n_mice independent mice on the maze's device. */
@@ -373,9 +378,13 @@ int nm_simulate(const nm_maze *mz, const nm_sim_args *args, void *stream);
 /* sizeof(nm_sim_args) of the built library: a binding checks its own mirror of the struct against it at load time. */
 int nm_sim_args_size(void);
 
-/* 1 if an X x Y maze fits the simulation kernel's shared-memory visit map for runs of n_steps (the counters are 16
- * bits wide below 65535 steps), else 0: StandardExperiment.run then keeps the reference's per-step host loop. */
+/* Where the visit maps of an X x Y maze live for runs of n_steps: 1 = shared memory (the counters are 16 bits wide
+ * below 65535 steps; mazes up to about 50 x 50 tiles); 2 = device memory (the caller passes nm_sim_args.d_visit_scratch;
+ * same step body and results; up to about 66 000 tiles, whose tile / grid-line tables must still fit shared memory);
+ * 0 = the maze is too large for nm_simulate. */
 int nm_simulate_fits(int X, int Y, int n_steps);
+/* columns of nm_sim_args.d_visit_scratch nm_simulate needs for n_mice (the launched threads: whole CTAs) */
+int64_t nm_simulate_scratch_columns(int64_t n_mice);
 
 /* Vectorised Maze.is_movement_possible_cont on the device: d_segments [n,4] = (x1,y1,x2,y2),
  * d_out u8[n] (1 possible).  maze.py:563-611 */

@@ -75,6 +75,7 @@ SIGNATURES = {
     "nm_distance_rows": (C.c_int, [C.c_int, _p, _p, _i64, C.c_int, _p, _p]),
     "nm_simulate": (C.c_int, [_p, _p, _p]),
     "nm_simulate_fits": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "nm_simulate_scratch_columns": (C.c_int64, [C.c_int64]),
     "nm_sim_args_size": (C.c_int, []),
     "nm_maze_movements_possible_device": (C.c_int, [_p, _p, _i64, _p, _p]),
 }
@@ -116,6 +117,7 @@ class SimArgs(C.Structure):
         ("d_init_visits", C.c_void_p), ("d_init_model_state", C.c_void_p),
         ("init_visits_max", C.c_uint32), ("reserved3", C.c_int32),
         ("mouse_index_base", C.c_int64),
+        ("d_visit_scratch", C.c_void_p), ("visit_scratch_columns", C.c_int64),
     ]
 
 _lock = threading.Lock()

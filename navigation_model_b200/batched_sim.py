@@ -12,6 +12,7 @@ parity tests use).  PyTorch is used for device buffers only.  No CPU fallback.
 """
 import ctypes as C
 import functools
+import os
 import threading
 from dataclasses import dataclass
 
@@ -466,6 +467,18 @@ class BatchedExperiment:
             ms = np.empty((N, 3))
             ms[:] = np.asarray(init_model_state, dtype=np.float64).reshape(-1, 3)
             args.d_init_model_state = dev_f64(ms).data_ptr()
+
+        # visit maps: shared memory while the maze fits (about 50 x 50 tiles), else a device-memory scratch the kernel
+        # indexes [tile][launched thread] (same step body, same results); NM_SIM_MAP=global forces the latter (tests)
+        where = self._dmaze._lib.nm_simulate_fits(int(X), int(Y), int(n_steps) + int(args.init_visits_max))
+        if where == 0:
+            raise ValueError(f"a maze of {X} x {Y} tiles is too large for the simulation kernel (its tile and "
+                             "grid-line tables must fit shared memory: about 66 000 tiles)")
+        if where == 2 or os.environ.get("NM_SIM_MAP", "").startswith("g"):
+            cols = int(self._dmaze._lib.nm_simulate_scratch_columns(int(N)))
+            scratch = torch.empty((X * Y, cols), dtype=torch.int32, device=dev)
+            keep.append(scratch)
+            args.d_visit_scratch, args.visit_scratch_columns = scratch.data_ptr(), cols
 
         o_pose = out((N, 3), torch.float64)
         o_pcg = out((N, 4), torch.int64)

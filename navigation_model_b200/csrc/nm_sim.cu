@@ -55,6 +55,7 @@ struct SimDev {
   int n_walk;            // number of those
   const uint8_t *subareas;                 // [X*Y] or NULL
   double ori_edges[NM_MAX_ORI_BINS + 1];   // numpy.histogram edges of the turn histogram
+  int64_t scratch_columns;                 // GMAP: columns (= launched threads) of the device-memory visit map
 };
 
 // cos / sin / atan2 of the pose chain: nm_host_sincos / nm_host_atan2 (nm_libm.h) give the HOST library's results, so
@@ -106,7 +107,11 @@ struct Pcg64 {
 // CntT = type of a visit counter: u16 when n_steps + 1 < 65536 (half the shared memory: one more resident CTA), else u32.
 // SEEDED = the run continues an earlier one (d_init_visits / d_init_model_state); a separate instantiation, so that
 // the fresh-start kernel keeps its register allocation.
-template <int NT, typename CntT, bool SEEDED>
+// GMAP = the visit map lives in DEVICE memory (a.d_visit_scratch, count[tile][launched thread] u32: the 32 mice of a warp
+// touch 32 consecutive words of a row) and the shared normalised value table is read from device memory too: mazes whose
+// map does not fit shared memory (beyond ~50 x 50 tiles) run the same step body -- same operations, same results -- with
+// only the tile / grid-line tables in shared memory (up to ~66 000 tiles).
+template <int NT, typename CntT, bool SEEDED, bool GMAP>
 __global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 : NM_SIM_MIN_CTAS) * kSimThreads) / NT)
     nm_sim_kernel(const SimDev d) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -121,23 +126,26 @@ __global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 
   uint16_t *res_sm = reinterpret_cast<uint16_t *>(rank_sm + nt);        // [thread][kA] walk results: tile | ok << 15
   double *anx_sm = exp_tab + 16 + 2 * kA + (nt / 32) * 4 + 2 * nt;
   double *bcw_sm = anx_sm + 5 * nt;
-  CntT *count = reinterpret_cast<CntT *>(bcw_sm + kA * nt);
-  double *vt_sm = reinterpret_cast<double *>(count + (size_t)nT * nt);
+  // visit map: count[tile * cs + column]; shared memory (cs = nt, column = tid) or device memory (GMAP)
+  CntT *count = GMAP ? reinterpret_cast<CntT *>(d.a.d_visit_scratch) : reinterpret_cast<CntT *>(bcw_sm + kA * nt);
+  const size_t cs = GMAP ? (size_t)d.scratch_columns : (size_t)nt;
+  double *vt_sm = GMAP ? bcw_sm + kA * nt : reinterpret_cast<double *>(count + (size_t)nT * nt);
   if (tid < 16) exp_tab[tid] = c_exp2tab[tid];
   if (tid < 2 * kA) act_sm[tid] = d.act[tid >> 1][tid & 1];
   NmSimGeom geo;  // tile table, grid-line tables (nm_simgeom.cuh)
-  geo.build(reinterpret_cast<unsigned char *>(vt_sm + nT), d.tiles, d.X, d.Y, d.st);
+  geo.build(reinterpret_cast<unsigned char *>(GMAP ? vt_sm : vt_sm + nT), d.tiles, d.X, d.Y, d.st);
   const uint8_t *tiles = geo.tiles;
-  if (d.a.d_vtable && !d.a.vtable_per_mouse)
+  if (!GMAP && d.a.d_vtable && !d.a.vtable_per_mouse)
     for (int i = tid; i < nT; i += nt) vt_sm[i] = d.a.d_vtable[i];
   const nm_sim_args &a = d.a;
   const int64_t N = a.n_mice;
   const int64_t n_raw = (int64_t)blockIdx.x * nt + tid;
+  CntT *cnt = count + (GMAP ? (size_t)n_raw : (size_t)tid);  // this thread's column
   if (SEEDED && a.d_init_visits) {  // continuing an earlier run: ExperienceComponent._maze_map_exp as it was left
     const uint32_t *iv = a.d_init_visits + (n_raw < N ? n_raw : N - 1) * nT;
-    for (int i = 0; i < nT; ++i) count[i * nt + tid] = (CntT)iv[i];
+    for (int i = 0; i < nT; ++i) cnt[(size_t)i * cs] = (CntT)iv[i];
   } else {
-    for (int i = 0; i < nT; ++i) count[i * nt + tid] = (CntT)0;
+    for (int i = 0; i < nT; ++i) cnt[(size_t)i * cs] = (CntT)0;
   }
   __syncthreads();
 
@@ -147,7 +155,6 @@ __global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 
   const int64_t n = live ? n_raw : N - 1;
   const int A = a.n_actions;
   const int T = a.n_steps;
-  CntT *cnt = count + tid;
 
   int status = 0;
   ExpRegs er;
@@ -200,7 +207,7 @@ __global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 
     const double *vt = nullptr;
     if (a.d_vtable) {
       vt_w = a.d_vtable_weight[n];
-      vt = a.vtable_per_mouse ? a.d_vtable + n * nT : vt_sm;
+      vt = a.vtable_per_mouse ? a.d_vtable + n * nT : (GMAP ? a.d_vtable : vt_sm);
     }
     Pcg64 rng;
     rng.state = 0;
@@ -268,8 +275,8 @@ __global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 
           corridor_side = side;
         }
       }
-      const uint32_t c = cnt[tile * nt];
-      cnt[tile * nt] = (CntT)(c + 1u);
+      const uint32_t c = cnt[(size_t)tile * cs];
+      cnt[(size_t)tile * cs] = (CntT)(c + 1u);
       if (c == 0u) {
         n_visited += 1;
         // perc = n_visited * 100 / number_visitable_tiles >= percentage      metrics.py:711-721
@@ -373,7 +380,7 @@ __global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 
       if (a.model_kind == 0) {  // ---------------- BehaviouralModel -----------------------------------------
       // -- component updates                                                 exploration_model.py:79-81
       if (a.d_experience) {  // :456-466 (count of the current tile was just incremented above)
-        const double nvis = cur_inside ? (double)cnt[(cur_tx * d.Y + cur_ty) * nt] : 0.0;
+        const double nvis = cur_inside ? (double)cnt[(size_t)(cur_tx * d.Y + cur_ty) * cs] : 0.0;
         fam = (1.0 - xi) * fam + xi * nvis;
         if (home && fam >= th_explo) home = false;
         else if (!home && fam < th_home) home = true;
@@ -411,7 +418,7 @@ __global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 
             for (int i = 0; i < kA; ++i)
               if (i < A) {
                 // (double)count by the 2^52 trick: exact for a u32, and no I2F on the quarter-rate pipe
-                const double cn = __hiloint2double(0x43300000, (int)cnt[etile[i] * nt]) - 4503599627370496.0;
+                const double cn = __hiloint2double(0x43300000, (int)cnt[(size_t)etile[i] * cs]) - 4503599627370496.0;
                 const double ee = er.exp_nonpos(kk * cn);
                 val[i] = val[i] + (home ? 1.0 - ee : ee) * ex_w;
               }
@@ -562,7 +569,7 @@ __global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 
       for (int code = 0; code < 8; ++code) {
         int acc = 0;
         for (int tile = 0; tile < nT; ++tile)
-          if ((tiles[tile] & 7) == code) acc += (int)cnt[tile * nt];
+          if ((tiles[tile] & 7) == code) acc += (int)cnt[(size_t)tile * cs];
         a.d_tile_counts[8 * n + code] = acc;
       }
     }
@@ -571,7 +578,7 @@ __global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 
       int zone_occ = 0;  // positions inside the zone = the visit map summed over the zone's tiles
       if (a.d_tile_flags)
         for (int tile = 0; tile < nT; ++tile)
-          if (a.d_tile_flags[tile] & NM_TILE_ZONE_IN) zone_occ += (int)cnt[tile * nt];
+          if (a.d_tile_flags[tile] & NM_TILE_ZONE_IN) zone_occ += (int)cnt[(size_t)tile * cs];
       int *q = a.d_zone_metrics + 4 * n;
       q[0] = zone_latency; q[1] = zone_occ; q[2] = zone_entries; q[3] = corridor_switches;
     }
@@ -581,7 +588,7 @@ __global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 
       for (int sub = 0; sub < NM_MAX_SUBAREAS; ++sub) {
         int acc = 0;
         for (int tile = 0; tile < nT; ++tile)
-          if (d.subareas[tile] == sub) acc += (int)cnt[tile * nt];
+          if (d.subareas[tile] == sub) acc += (int)cnt[(size_t)tile * cs];
         a.d_subarea_counts[(int64_t)NM_MAX_SUBAREAS * n + sub] = acc;
       }
     }
@@ -603,13 +610,13 @@ __global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 
       uint32_t *dst = a.d_occupancy + n0 * nT;
       for (int64_t i = tid; i < np * nT; i += nt) {
         const int u = (int)(i / nT), tile = (int)(i - (int64_t)u * nT);
-        dst[i] = count[tile * nt + u];
+        dst[i] = count[(size_t)tile * cs + (GMAP ? (size_t)n0 : (size_t)0) + u];
       }
     }
     if (a.d_occupancy_total) {
       for (int tile = tid; tile < nT; tile += nt) {
         unsigned long long acc = 0ull;
-        for (int u = 0; u < (int)np; ++u) acc += count[tile * nt + u];
+        for (int u = 0; u < (int)np; ++u) acc += count[(size_t)tile * cs + (GMAP ? (size_t)n0 : (size_t)0) + u];
         if (acc) atomicAdd(a.d_occupancy_total + tile, acc);
       }
     }
@@ -700,22 +707,42 @@ extern "C" int nm_simulate(const nm_maze *mz, const nm_sim_args *args, void *str
   const char *env_cnt = getenv("NM_SIM_COUNTERS");
   const int64_t count_max = (int64_t)a.n_steps + (a.d_init_visits ? (int64_t)a.init_visits_max : 0);
   NM_CHECK_ARG(count_max < 4294967295LL, "nm_simulate: seeded visits + n_steps overflow the 32-bit visit counters");
-  const bool small_counts = count_max < 65535 && !(env_cnt && env_cnt[0] == '3');
-  const size_t cnt_bytes = small_counts ? sizeof(uint16_t) : sizeof(uint32_t);
+  bool small_counts = count_max < 65535 && !(env_cnt && env_cnt[0] == '3');
+  size_t cnt_bytes = small_counts ? sizeof(uint16_t) : sizeof(uint32_t);
+  const size_t per_thread = (size_t)(1 + 2 * kA) + (size_t)(5 + kA) * sizeof(double);
   auto smem_for = [&](int th) {
-    return 128 + 16 * kA + (size_t)th * (1 + 2 * kA) + (size_t)(5 + kA) * th * sizeof(double) + (size_t)nT * th * cnt_bytes +
-           (size_t)nT * sizeof(double) + geo_bytes;
+    return 128 + 16 * kA + per_thread * th + (size_t)nT * th * cnt_bytes + (size_t)nT * sizeof(double) + geo_bytes;
   };
-  while (threads > 32 && smem_for(threads) > 200 * 1024) threads /= 2;
-  const size_t smem = smem_for(threads);
-  NM_CHECK_ARG(smem <= 227 * 1024, "nm_simulate: maze of %d tiles does not fit the shared-memory visit map", nT);
+  // the visit map in device memory: mazes whose map does not fit shared memory even for one warp, or NM_SIM_MAP=global
+  const char *env_map = getenv("NM_SIM_MAP");
+  const bool gmap = smem_for(32) > 227 * 1024 || (env_map && env_map[0] == 'g');
+  size_t smem;
+  if (gmap) {
+    small_counts = false;
+    cnt_bytes = sizeof(uint32_t);
+    smem = 128 + 16 * kA + per_thread * threads + geo_bytes;
+    NM_CHECK_ARG(smem <= 227 * 1024, "nm_simulate: the tile and grid-line tables of a maze of %d tiles do not fit shared "
+                 "memory (about 66 000 tiles at most)", nT);
+    const int64_t columns = ((a.n_mice + threads - 1) / threads) * threads;
+    NM_CHECK_ARG(a.d_visit_scratch && a.visit_scratch_columns >= columns,
+                 "nm_simulate: a maze of %d tiles keeps its visit map in device memory: pass d_visit_scratch with "
+                 "X*Y x nm_simulate_scratch_columns(n_mice) = %lld 32-bit words", nT, (long long)columns);
+    d.scratch_columns = a.visit_scratch_columns;
+  } else {
+    while (threads > 32 && smem_for(threads) > 200 * 1024) threads /= 2;
+    smem = smem_for(threads);
+    d.scratch_columns = 0;
+  }
   const int64_t blocks = (a.n_mice + threads - 1) / threads;
   NM_CHECK_ARG(blocks <= 2147483647LL, "nm_simulate: too many mice for one launch");
   void (*kern)(const SimDev);
   const bool seeded = a.d_init_visits || a.d_init_model_state;
 #define NM_SIM_PICK(CNT, SEED) \
-  (threads == 128 ? nm_sim_kernel<128, CNT, SEED> : threads == 64 ? nm_sim_kernel<64, CNT, SEED> : nm_sim_kernel<32, CNT, SEED>)
-  if (small_counts)
+  (threads == 128 ? nm_sim_kernel<128, CNT, SEED, false> : threads == 64 ? nm_sim_kernel<64, CNT, SEED, false> \
+                                                                            : nm_sim_kernel<32, CNT, SEED, false>)
+  if (gmap)
+    kern = seeded ? nm_sim_kernel<128, uint32_t, true, true> : nm_sim_kernel<128, uint32_t, false, true>;
+  else if (small_counts)
     kern = seeded ? NM_SIM_PICK(uint16_t, true) : NM_SIM_PICK(uint16_t, false);
   else
     kern = seeded ? NM_SIM_PICK(uint32_t, true) : NM_SIM_PICK(uint32_t, false);
@@ -735,9 +762,14 @@ extern "C" int nm_simulate_fits(int X, int Y, int n_steps) {
   if (X <= 0 || Y <= 0 || n_steps < 0) return 0;
   const size_t nT = (size_t)X * Y, th = 32;
   const size_t cnt_bytes = n_steps < 65535 ? sizeof(uint16_t) : sizeof(uint32_t);
-  const size_t smem = 128 + 16 * kA + th * (1 + 2 * kA) + (size_t)(5 + kA) * th * sizeof(double) + nT * th * cnt_bytes +
-                      nT * sizeof(double) + NmSimGeom::smem_bytes(X, Y);
-  return smem <= 227 * 1024 ? 1 : 0;
+  const size_t per_thread = (size_t)(1 + 2 * kA) + (size_t)(5 + kA) * sizeof(double);
+  const size_t geo = NmSimGeom::smem_bytes(X, Y);
+  if (128 + 16 * kA + th * per_thread + nT * th * cnt_bytes + nT * sizeof(double) + geo <= 227 * 1024) return 1;
+  return 128 + 16 * kA + (size_t)kSimThreads * per_thread + geo <= 227 * 1024 ? 2 : 0;
+}
+
+extern "C" int64_t nm_simulate_scratch_columns(int64_t n_mice) {
+  return n_mice <= 0 ? 0 : ((n_mice + kSimThreads - 1) / kSimThreads) * kSimThreads;
 }
 
 extern "C" int nm_maze_movements_possible_device(const nm_maze *mz, const double *d_segments, int64_t n,

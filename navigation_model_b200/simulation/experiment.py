@@ -45,8 +45,13 @@ class StandardExperiment:
                             or m.max() + iterations >= 2 ** 32 - 1):
                         return False  # not a visit count the kernel's integer map can carry: host loop
                     seeded = int(m.max())
-        if not _native.lib().nm_simulate_fits(int(X), int(Y), int(iterations) + seeded):
-            return False  # the visit map does not fit the kernel's shared memory: the host loop below still works
+        if type(model) in (BehaviouralModel, RandomModel) and \
+                not _native.lib().nm_simulate_fits(int(X), int(Y), int(iterations) + seeded):
+            # beyond ~66 000 tiles not even the tile tables fit shared memory; smaller mazes whose VISIT MAP does not fit
+            # it (beyond ~50 x 50 tiles) run on the device with the map in device memory
+            raise RuntimeError(f"a maze of {X} x {Y} tiles is too large for the simulation kernel; there is no CPU "
+                               "fallback for the built-in models (a user-defined exploration model takes the per-step "
+                               "plugin loop)")
         if type(model) is RandomModel:
             return (1 <= len(self._mouse.possible_actions) <= _native.NM_MAX_CAND
                     and type(model._rng.bit_generator).__name__ == "PCG64")

@@ -319,7 +319,7 @@ def test_memo_and_exact_bodies_agree_and_guard_falls_back(cuda, alg, monkeypatch
 
 @pytest.mark.parametrize("alg", ["td0", "positive", "negative"])
 def test_tables_in_device_memory_match_shared_memory_kernels(cuda, alg, monkeypatch):
-    """NM_FIT_TABLES=global: the same sweeps with T[state][parameter set] in device memory (the path mazes beyond 867
+    """NM_FIT_TABLES=global: the same sweeps with T[state][parameter set] in device memory (the path mazes beyond 863
     states take) -- bit-identical V-tables and log-likelihoods; per-set initial tables, replays, ragged sessions, a
     parameter count that is not a multiple of the CTA size."""
     omz = H.oracle_m9()
@@ -343,7 +343,7 @@ def test_tables_in_device_memory_match_shared_memory_kernels(cuda, alg, monkeypa
 
 
 def test_maze_beyond_the_shared_memory_layout(cuda):
-    """A 60 x 60 maze with a few void tiles (3 590 states > 867): sweeps and ConditioningExperiment.run keep their
+    """A 60 x 60 maze with a few void tiles (3 590 states > 863): sweeps and ConditioningExperiment.run keep their
     tables in device memory; V-tables bit-exact and log-likelihoods 1e-9 against the oracle."""
     from navigation_model_b200.simulation.maze import Maze
     from navigation_model_b200.simulation.mouse import Mouse

@@ -412,24 +412,33 @@ def test_multi_result_views_and_batched_leaves():
     assert len(mr) == 0
 
 
-def test_mazes_too_large_for_the_simulation_kernel_keep_the_host_loop():
-    """A 60 x 60 maze does not fit the simulation kernel's shared-memory visit map: StandardExperiment.run then takes
-    the reference's per-step loop -- no error, no GPU needed.  (Value-table sweeps have no such limit: beyond 867 states
-    their tables move to device memory, tests/test_fit_gpu.py.)"""
+def test_where_the_visit_map_of_a_maze_lives():
+    """A 60 x 60 maze does not fit the simulation kernel's shared-memory visit map: the map moves to device memory
+    (nm_simulate_fits == 2; the GPU test is tests/test_sim_gpu.py::test_large_maze_visit_map_in_device_memory) -- no
+    silent CPU fallback for the built-in models; a user-defined model still takes the per-step plugin loop.  (Value-table
+    sweeps: beyond 863 states their tables move to device memory too, tests/test_fit_gpu.py.)"""
     from navigation_model_b200 import _native
     from navigation_model_b200.simulation.behavioural_components import AnxietyComponent
     from navigation_model_b200.simulation.experiment import StandardExperiment
     from navigation_model_b200.simulation.exploration_model import BehaviouralModel
     from navigation_model_b200.simulation.maze import Maze
     from navigation_model_b200.simulation.mouse import Mouse
-    assert _native.lib().nm_vtable_max_states() == 867
-    assert _native.lib().nm_simulate_fits(9, 9, 10000) == 1 and _native.lib().nm_simulate_fits(60, 60, 100) == 0
+    assert _native.lib().nm_vtable_max_states() == 863
+    fits = _native.lib().nm_simulate_fits
+    assert fits(9, 9, 10000) == 1 and fits(60, 60, 100) == 2 and fits(250, 250, 100) == 2 and fits(400, 400, 10) == 0
+    assert _native.lib().nm_simulate_scratch_columns(1) == 128 and _native.lib().nm_simulate_scratch_columns(129) == 256
     layout = "\n".join(["M" * 60] * 60)
     maze = Maze(layout, "", size_tile=0.02)
     acts = np.array([(0, 0), (1, 0), (0, 1), (-1, 0)]) * 0.02
     mouse = Mouse(maze.get_tile_centre(30, 30), 0.0, acts)
-    model = BehaviouralModel([AnxietyComponent(W_anx=1.0, p1=0.5, p2=0.5, p3=0.5)], (30, 30), beta=1.0, seed=3)
+    user_model = type("UserModel", (BehaviouralModel,), {})  # a plugin: per-step host loop, any maze size
+    model = user_model([AnxietyComponent(W_anx=1.0, p1=0.5, p2=0.5, p3=0.5)], (30, 30), beta=1.0, seed=3)
     sim = StandardExperiment(model, maze, mouse)
     assert not sim._device_eligible(50)
     sim.run(50)
     assert len(mouse.history_position) == 51
+    builtin = BehaviouralModel([AnxietyComponent(W_anx=1.0, p1=0.5, p2=0.5, p3=0.5)], (30, 30), beta=1.0, seed=3)
+    assert StandardExperiment(builtin, maze, Mouse(maze.get_tile_centre(30, 30), 0.0, acts))._device_eligible(50)
+    huge = Maze("\n".join(["M" * 400] * 400), "", size_tile=0.01)
+    with pytest.raises(RuntimeError, match="too large for the simulation kernel"):
+        StandardExperiment(builtin, huge, Mouse(huge.get_tile_centre(30, 30), 0.0, acts)).run(5)

@@ -364,3 +364,83 @@ def test_results_survive_the_next_run(cuda):
     for f in fields:
         assert np.array_equal(getattr(c, f), kept[f]), f
     assert a.tile_counts.sum(axis=1).min() == 41 and a.orientations_histogram.shape[0] == N
+
+
+@pytest.mark.parametrize("forced", [False, True])
+def test_large_maze_visit_map_in_device_memory(cuda, forced, monkeypatch):
+    """beyond ~50 x 50 tiles the simulation used to fall back to a Python per-step loop.  The visit maps now
+    move to device memory (nm_sim_kernel<..., GMAP>): a 70 x 64 maze with void blocks, 96 mice x 200 steps against the
+    compiled oracle -- choices, poses, visit maps bit for bit; and the 9 x 9 maze forced onto the same variant
+    (NM_SIM_MAP=global) reproduces the shared-memory run exactly, metrics included."""
+    from navigation_model_b200 import _native
+    from navigation_model_b200.batched_sim import BatchedExperiment
+    from navigation_model_b200.simulation.maze import Maze
+    from oracle import c_oracle as CO
+    rng = np.random.default_rng(8)
+    if forced:
+        maze, omz = H.product_m9(), H.oracle_m9()
+        X, Y, st = 9, 9, O.M9_SIZE_TILE
+    else:
+        X, Y, st = 70, 64, 0.02
+        rows = [["M"] * Y for _ in range(X)]
+        for bx in range(5, X - 5, 9):
+            for by in range(4, Y - 4, 7):
+                for dx in range(3):
+                    for dy in range(2):
+                        rows[bx + dx][by + dy] = "V"
+        layout = "\n".join("".join(r) for r in rows)
+        maze, omz = Maze(layout, "", size_tile=st), O.OracleMaze(layout, st)
+        assert _native.lib().nm_simulate_fits(X, Y, 200) == 2
+    N, T = 96, 200
+    acts = O.A8_UNITS * st
+    P = _random_params(rng, N)
+    P["beta"] = rng.uniform(0.02, 0.6, N)
+    V = rng.random((X, Y))
+    cells = np.array([omz.vis_cells[i] for i in rng.integers(0, len(omz.vis_cells), N)])
+    pos0 = np.array([maze.get_tile_centre(c) for c in cells]) + rng.uniform(-0.3, 0.3, (N, 2)) * st
+    ori0 = rng.uniform(-np.pi, np.pi, N)
+    draws = rng.random((N, T))
+    exp = BatchedExperiment(maze, acts, O.A8_UNITS, _classes(), v_table=V)
+    kw = dict(init_disc=cells, draws=draws, history=True, occupancy=True, occupancy_total=True)
+    if forced:
+        base = exp.run(P, T, pos0, ori0, **kw)
+        monkeypatch.setenv("NM_SIM_MAP", "global")
+    res = exp.run(P, T, pos0, ori0, **kw)
+    if forced:
+        for f in ("choices", "history_position", "history_orientation", "occupancy", "occupancy_total", "it_visit",
+                  "count_moving", "tile_counts", "final_pose", "model_state"):
+            assert np.array_equal(getattr(res, f), getattr(base, f)), f
+    ref = CO.simulate(omz, acts, O.A8_UNITS, [O.COMP_ANXIETY, O.COMP_BCOST, O.COMP_EXPERIENCE, O.COMP_BPERSISTENCE,
+                                              O.COMP_VTABLE], P, np.concatenate([pos0, ori0[:, None]], axis=1), cells,
+                      draws, vtable_norm=O.normalise_vtable(V))
+    assert not ref["status"].any() and not res.status.any()
+    assert np.array_equal(ref["choice"], res.choices)
+    assert np.array_equal(ref["hist_pos"], res.history_position) and np.array_equal(ref["hist_ori"], res.history_orientation)
+    assert np.array_equal(ref["occupancy"], res.occupancy.astype(np.int32))
+    assert np.array_equal(res.occupancy_total, ref["occupancy"].sum(0))
+
+
+def test_standard_experiment_on_a_large_maze_runs_on_the_device(cuda):
+    from navigation_model_b200.simulation.behavioural_components import AnxietyComponent, ExperienceComponent
+    from navigation_model_b200.simulation.experiment import StandardExperiment
+    from navigation_model_b200.simulation.exploration_model import BehaviouralModel
+    from navigation_model_b200.simulation.maze import Maze
+    from navigation_model_b200.simulation.mouse import Mouse
+    maze = Maze("\n".join(["M" * 60] * 60), "", size_tile=0.02)
+    acts = np.array([(0, 0), (1, 0), (0, 1), (-1, 0), (1, 1)]) * 0.02
+
+    def run(model_cls):
+        comps = [AnxietyComponent(W_anx=1.0, p1=0.5, p2=0.5, p3=0.5),
+                 ExperienceComponent(maze.shape, W_exp=2.0, xi=0.1, kappa_home=1.0, kappa_explo=1.0, theta_explo=100.0,
+                                     theta_home=50.0)]
+        mouse = Mouse(maze.get_tile_centre(30, 30), 0.3, acts)
+        sim = StandardExperiment(model_cls(comps, (30, 30), beta=0.7, seed=3), maze, mouse)
+        eligible = sim._device_eligible(150)
+        sim.run(150)
+        return eligible, np.array(mouse.history[0]), np.array(mouse.history[1]), comps[1]._maze_map_exp.copy()
+
+    on_device = run(BehaviouralModel)
+    plugin = run(type("UserModel", (BehaviouralModel,), {}))  # the reference's per-step loop on the host
+    assert on_device[0] and not plugin[0]
+    for a, b in zip(on_device[1:], plugin[1:]):
+        assert np.array_equal(a, b)
