@@ -373,6 +373,10 @@ class BatchedExperiment:
         pose = np.empty((N, 3))
         pose[:, :2] = np.asarray(init_pos, dtype=np.float64).reshape(-1, 2)
         pose[:, 2] = np.asarray(init_ori, dtype=np.float64).reshape(-1)
+        # the kernel evaluates cos / sin / atan2 with the host C library's algorithm (csrc/nm_libm.h), whose table-driven
+        # range covers |heading| < 105414350 and finite coordinates; anything else is refused here, not approximated
+        if not np.isfinite(pose).all() or (np.abs(pose[:, 2]) >= 105414350.0).any():
+            raise ValueError("initial poses must be finite, with |orientation| < 105414350 rad")
         if init_disc is None:
             prev = self.maze.cont2disc_array(pose[:, :2]).astype(np.float64)
         else:

@@ -127,6 +127,7 @@ struct ExpLL {
 #pragma unroll
     for (int i = 0; i < 4; ++i) asm volatile("mov.f64 %0, %1;" : "=d"(c[i]) : "d"(c_expll_k[i]));
     tab = ((uint32_t)__cvta_generic_to_shared(region) + 511u) & ~511u;
+    asm volatile("mov.u32 %0, %0;" : "+r"(tab));  // pinned: not recomputed per step under register pressure
   }
   __device__ __forceinline__ double operator()(double x) const {
     const double t = fma(x, c[0], c[1]);

@@ -190,27 +190,51 @@ __device__ __forceinline__ double exp_nonpos(double x) { return (x < -708.0) ? 0
 
 #include "nm_step_math.cuh"
 
+// Where a value table lives.  GenericCol: any pointer (device-memory tables; shared-memory columns whose address the
+// compiler may recompute).  SharedCol: a 32-bit shared-window address pinned in a register through an opaque move --
+// under the 64-register cap of the per-warp-table kernel the compiler otherwise REMATERIALISES the column base and
+// the exponential table's address in every step (S2R / S2UR / ULEA / shifts: ~10 instructions per step).
+struct GenericCol {
+  char *vb;
+  __device__ __forceinline__ double ld(uint32_t off) const { return *reinterpret_cast<const double *>(vb + off); }
+  __device__ __forceinline__ void st(uint32_t off, double v) const { *reinterpret_cast<double *>(vb + off) = v; }
+};
+struct SharedCol {
+  uint32_t base;
+  __device__ __forceinline__ explicit SharedCol(const void *col) {
+    base = (uint32_t)__cvta_generic_to_shared(col);
+    asm volatile("mov.u32 %0, %0;" : "+r"(base));
+  }
+  __device__ __forceinline__ double ld(uint32_t off) const {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(base + off) : "memory");
+    return v;
+  }
+  __device__ __forceinline__ void st(uint32_t off, double v) const {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(base + off), "d"(v) : "memory");
+  }
+};
+
 // =================================== EXACT body ===========================================================
 struct ExactAcc {
   double acc_obs, prod;
   ExpLL er;
 };
 
-template <int ALG, bool LL, int K>
-__device__ __forceinline__ void exact_step_k(const uint4 q0, const uint4 q1, const uint4 q2, const uint4 q3, char *vb,
+template <int ALG, bool LL, int K, class Col>
+__device__ __forceinline__ void exact_step_k(const uint4 q0, const uint4 q1, const uint4 q2, const uint4 q3, const Col vb,
                                              const double alpha, const double beta, const double gamma,
                                              ExactAcc &acc) {
   const double r = __hiloint2double((int)q0.y, (int)q0.x);
   const uint32_t offs[NM_MAX_CAND] = {q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y};
-  double *ps = reinterpret_cast<double *>(vb + q0.z);
-  const double vs = *ps;
+  const double vs = vb.ld(q0.z);
   double v[NM_MAX_CAND];
   double boot = 0.0;
   if constexpr (LL || ALG != NM_ALG_TD0) {
 #pragma unroll
-    for (int k = 0; k < K; ++k) v[k] = lds_f64(vb, offs[k]);
+    for (int k = 0; k < K; ++k) v[k] = vb.ld(offs[k]);
   }
-  if constexpr (ALG == NM_ALG_TD0) boot = lds_f64(vb, q1.y);
+  if constexpr (ALG == NM_ALG_TD0) boot = vb.ld(q1.y);
   else boot = extremum<ALG, K>(v);
   if (LL && q0.w != kNone) {  // observed step (warp-uniform); the producer put the OBSERVED candidate first
     // val_k = beta * V[cand_k] - max (exploration_model.py:87, 92) in one fused instruction per candidate; the maximum
@@ -235,23 +259,23 @@ __device__ __forceinline__ void exact_step_k(const uint4 q0, const uint4 q1, con
     acc.prod = __dmul_rn(acc.prod, sum);         // sum in [1, 8]; 32 steps per chunk -> prod <= 2^96
   }
   const double rpe = __dsub_rn(__dadd_rn(r, __dmul_rn(gamma, boot)), vs);  // rl.py:185, 228, 257
-  *ps = __dadd_rn(vs, __dmul_rn(alpha, rpe));                               // rl.py:186-187, 258-259
+  vb.st(q0.z, __dadd_rn(vs, __dmul_rn(alpha, rpe)));                        // rl.py:186-187, 258-259
 }
 
-template <int ALG, bool LL>
-__device__ __forceinline__ void exact_step(const uint4 *__restrict__ rec, char *vb, const double alpha,
+template <int ALG, bool LL, class Col>
+__device__ __forceinline__ void exact_step(const uint4 *__restrict__ rec, const Col vb, const double alpha,
                                            const double beta, const double gamma, ExactAcc &acc) {
   const uint4 q0 = rec[0], q1 = rec[1], q2 = rec[2], q3 = rec[3];
   if constexpr (!LL && ALG == NM_ALG_TD0) {  // no candidates needed
-    exact_step_k<NM_ALG_TD0, false, 0>(q0, q1, q2, q3, vb, alpha, beta, gamma, acc);
+    exact_step_k<NM_ALG_TD0, false, 0, Col>(q0, q1, q2, q3, vb, alpha, beta, gamma, acc);
   } else {
 #define NM_CASE(KK) \
-  case KK: exact_step_k<ALG, LL, KK>(q0, q1, q2, q3, vb, alpha, beta, gamma, acc); break;
+  case KK: exact_step_k<ALG, LL, KK, Col>(q0, q1, q2, q3, vb, alpha, beta, gamma, acc); break;
     switch (q1.x & 0xffu) {  // K, warp-uniform
       NM_CASE(1) NM_CASE(2) NM_CASE(3) NM_CASE(4) NM_CASE(5) NM_CASE(6) NM_CASE(7) NM_CASE(8)
       default:  // K == 0 only occurs in TD0 streams built without candidates (validated on the host)
         if constexpr (ALG == NM_ALG_TD0)
-          exact_step_k<NM_ALG_TD0, false, 0>(q0, q1, q2, q3, vb, alpha, beta, gamma, acc);
+          exact_step_k<NM_ALG_TD0, false, 0, Col>(q0, q1, q2, q3, vb, alpha, beta, gamma, acc);
         break;
     }
 #undef NM_CASE
@@ -322,7 +346,7 @@ __global__ void __launch_bounds__(512, 1) nm_fit_exact_kernel(const FitArgs a) {
     const double gamma = live ? a.gamma[p] : 0.0;
     double *Vcol = V + tid;
     init_v_column(a, Vcol, nc, p, live);
-    char *vb = reinterpret_cast<char *>(Vcol);
+    const GenericCol vb{reinterpret_cast<char *>(Vcol)};
     double ll = 0.0;
     ExactAcc acc;
     acc.acc_obs = 0.0;
@@ -407,7 +431,7 @@ __global__ void __launch_bounds__(960, 1) nm_fit_group_kernel(const FitArgs a) {
     for (int s = lane; s < a.num_states; s += 32)
       Vcol[s * nw] = a.v_init ? a.v_init[a.tile_of_state[s]] : 0.0;  // rl.py:63-66 (shared initial table)
     __syncwarp();
-    char *vb = reinterpret_cast<char *>(Vcol);
+    const SharedCol vb(Vcol);
     double ll = 0.0;
     ExactAcc acc;
     acc.acc_obs = 0.0;
@@ -485,7 +509,7 @@ __global__ void __launch_bounds__(960, 1) nm_fit_global_kernel(const FitArgs a, 
         col[(int64_t)s * ppad] = v0;
       }
     }
-    char *vb = reinterpret_cast<char *>(col);
+    const GenericCol vb{reinterpret_cast<char *>(col)};
     double ll = 0.0;
     ExactAcc acc;
     acc.acc_obs = 0.0;

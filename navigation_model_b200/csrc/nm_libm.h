@@ -15,9 +15,9 @@
 // round identically on the host and on the device -- so agreement with the library on the host is agreement on the GPU.
 //
 // Scope: finite arguments with |x| < 105414350 for sin / cos (beyond that the library switches to a multi-precision
-// reduction: the caller falls back to the platform function there); atan2 for finite arguments, signed zeros included,
-// whose exponents differ by less than 2^57 either way and that are not subnormal-scaled (|x|, |y| in [2^-500, 2^500]) --
-// poses of a maze are of order 1.  Outside that scope the platform function is used (NML_FALLBACK_*).
+// reduction, not restated: nml_sincos_in_scope); atan2 for finite arguments, signed
+// zeros, subnormal and huge magnitudes included (the library's own scaling and exponent-gap shortcuts are restated).
+// NaN / infinite arguments are out of scope (nml_atan2_in_scope).
 //
 // The tables (nm_libm_tables.h) are the library's own read-only data, extracted by tools/libm_tables.py.
 #ifndef NM_LIBM_H
@@ -309,20 +309,15 @@ NML_HD double nml_atan2(double y, double x) {
 }
 
 #if defined(__CUDACC__)
-// Device entry points.  Out-of-scope arguments (|heading| >= 1.05e8, non-finite values) fall back to the CUDA functions.
+// Device entry points.  Arguments must be in scope: finite, |heading| < 105414350 (checked where poses enter the
+// library -- a mouse's heading is its initial one or an atan2 result, its positions are maze coordinates).  There is no
+// fallback to the CUDA functions: their argument-reduction slow paths would triple the code a simulation step drags
+// through the instruction cache for a case that does not occur.
 #ifndef NM_LIBM_CALL
 #define NM_LIBM_CALL __forceinline__  // measured on the simulation kernel: 171 ms inline against 187 ms out of line
 #endif
-static __device__ NM_LIBM_CALL void nm_host_sincos(double x, double *s, double *c) {
-  if (nml_sincos_in_scope(x)) {
-    nml_sincos(x, s, c);
-  } else {
-    sincos(x, s, c);
-  }
-}
-static __device__ NM_LIBM_CALL double nm_host_atan2(double y, double x) {
-  return nml_atan2_in_scope(y, x) ? nml_atan2(y, x) : atan2(y, x);
-}
+static __device__ NM_LIBM_CALL void nm_host_sincos(double x, double *s, double *c) { nml_sincos(x, s, c); }
+static __device__ NM_LIBM_CALL double nm_host_atan2(double y, double x) { return nml_atan2(y, x); }
 #endif
 
 #endif  // NM_LIBM_H
