@@ -139,8 +139,11 @@ struct ExpLL {
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
     p = __dmul_rn(p, s);
-    // binary exponent: hi += (k >> 6) << 20 = (k8 & ~0x1ff) * 2048
-    return __hiloint2double(__double2hiint(p) + (int)(k8 & 0xfffffe00u) * 2048, __double2loint(p));
+    // binary exponent: hi += (k >> 6) << 20 = (k8 & ~0x1ff) * 2048 -- one logic op + one integer multiply-add (spelled in
+    // PTX: the compiler otherwise turns the product back into shift + mask + add)
+    int hi;
+    asm("{\n.reg .b32 t;\nand.b32 t, %1, 0xfffffe00;\nmad.lo.s32 %0, t, 2048, %2;\n}" : "=r"(hi) : "r"(k8), "r"(__double2hiint(p)));
+    return __hiloint2double(hi, __double2loint(p));
   }
 };
 

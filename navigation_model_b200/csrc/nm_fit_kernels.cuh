@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(512, 1) nm_fit_exact_kernel(const FitArgs a) {
     const double gamma = live ? a.gamma[p] : 0.0;
     double *Vcol = V + tid;
     init_v_column(a, Vcol, nc, p, live);
-    const GenericCol vb{reinterpret_cast<char *>(Vcol)};
+    const SharedCol vb(Vcol);
     double ll = 0.0;
     ExactAcc acc;
     acc.acc_obs = 0.0;

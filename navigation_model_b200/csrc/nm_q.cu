@@ -262,29 +262,50 @@ __device__ __forceinline__ void q_producer_loop(const QRings &rg, const nm_step_
   }
 }
 
+// Where a table lives (see nm_fit_kernels.cuh): any pointer, or a shared-window address pinned in a register.
+struct QGenericCol {
+  char *qb;
+  __device__ __forceinline__ double ld(uint32_t off) const { return *reinterpret_cast<const double *>(qb + off); }
+  __device__ __forceinline__ void st(uint32_t off, double v) const { *reinterpret_cast<double *>(qb + off) = v; }
+};
+struct QSharedCol {
+  uint32_t base;
+  __device__ __forceinline__ explicit QSharedCol(const void *col) {
+    base = (uint32_t)__cvta_generic_to_shared(col);
+    asm volatile("mov.u32 %0, %0;" : "+r"(base));
+  }
+  __device__ __forceinline__ double ld(uint32_t off) const {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(base + off) : "memory");
+    return v;
+  }
+  __device__ __forceinline__ void st(uint32_t off, double v) const {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(base + off), "d"(v) : "memory");
+  }
+};
+
 struct QAcc {
   double acc_obs, prod;
   ExpLL er;  // likelihood exponentials: nm_exp.cuh (1e-9 bar on the session's log-likelihood, tables never see them)
 };
 
-template <int K1>
+template <int K1, class Col>
 __device__ __forceinline__ void qgroup_step_k(const uint4 q0, const uint4 q1, const uint4 q2, const uint4 q3,
-                                              const uint4 q4, char *qb, const double alpha, const double beta,
+                                              const uint4 q4, const Col qb, const double alpha, const double beta,
                                               const double gamma, QAcc &acc) {
   const double r = __hiloint2double((int)q0.y, (int)q0.x);
-  double *pu = reinterpret_cast<double *>(qb + q0.w);
-  const double q = *pu;  // Q[s, observed action]
+  const double q = qb.ld(q0.w);  // Q[s, observed action]
   const uint32_t o2[8] = {q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, q4.z, q4.w};
   double w[NM_MAX_CAND];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) w[k] = lds_f64(qb, o2[k]);
+  for (int k = 0; k < 8; ++k) w[k] = qb.ld(o2[k]);
   double boot = extremum<NM_ALG_POSITIVE, 8>(w);  // unavailable actions read -inf
   if (!(q0.z & kQBoot)) boot = 0.0;
   if (q0.z & kQOnline) {
     const uint32_t o1[8] = {q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
     double v[NM_MAX_CAND], e[NM_MAX_CAND];
 #pragma unroll
-    for (int k = 0; k < K1; ++k) v[k] = lds_f64(qb, o1[k]);
+    for (int k = 0; k < K1; ++k) v[k] = qb.ld(o1[k]);
     // beta >= 0: max_k fl(beta * v_k) == fl(beta * max_k v_k), rounding is monotonic   (exploration_model.py:87, 92)
     double m;
     if (beta >= 0.0) {
@@ -302,16 +323,17 @@ __device__ __forceinline__ void qgroup_step_k(const uint4 q0, const uint4 q1, co
     acc.prod = __dmul_rn(acc.prod, np_sum_fixed<K1>(e));
   }
   const double rpe = __dsub_rn(__dadd_rn(r, __dmul_rn(gamma, boot)), q);  // update form of rl.py:185
-  *pu = __dadd_rn(q, __dmul_rn(alpha, rpe));                               // rl.py:186-187
+  qb.st(q0.w, __dadd_rn(q, __dmul_rn(alpha, rpe)));                        // rl.py:186-187
 }
 
-__device__ __forceinline__ void qgroup_step(const uint4 *__restrict__ rec, char *qb, const double alpha, const double beta,
+template <class Col>
+__device__ __forceinline__ void qgroup_step(const uint4 *__restrict__ rec, const Col qb, const double alpha, const double beta,
                                             const double gamma, QAcc &acc) {
   const uint4 q0 = rec[0];
   if (!(q0.z & kQHit)) return;  // no observed action: the step is skipped entirely (warp-uniform)
   const uint4 q1 = rec[1], q2 = rec[2], q3 = rec[3], q4 = rec[4];
 #define NM_CASE(KK) \
-  case KK: qgroup_step_k<KK>(q0, q1, q2, q3, q4, qb, alpha, beta, gamma, acc); break;
+  case KK: qgroup_step_k<KK, Col>(q0, q1, q2, q3, q4, qb, alpha, beta, gamma, acc); break;
   switch (q0.z & 0xffu) {  // K1, warp-uniform (>= 1 on a hit)
     NM_CASE(1) NM_CASE(2) NM_CASE(3) NM_CASE(4) NM_CASE(5) NM_CASE(6) NM_CASE(7) NM_CASE(8)
     default: break;
@@ -373,7 +395,7 @@ __global__ void __launch_bounds__(960, 1) nm_qgroup_kernel(const QArgs a) {
     }
     if (lane == 0) Qcol[rows * nw] = -INFINITY;
     __syncwarp();
-    char *qb = reinterpret_cast<char *>(Qcol);
+    const QSharedCol qb(Qcol);
     double ll = 0.0;
     QAcc acc;
     acc.acc_obs = 0.0;
@@ -467,7 +489,7 @@ __global__ void __launch_bounds__(960, 1) nm_qglobal_kernel(const QArgs a, doubl
       }
       col[(int64_t)rows * ppad] = -INFINITY;
     }
-    char *qb = reinterpret_cast<char *>(col);
+    const QGenericCol qb{reinterpret_cast<char *>(col)};
     double ll = 0.0;
     QAcc acc;
     acc.acc_obs = 0.0;
