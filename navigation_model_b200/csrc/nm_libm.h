@@ -65,27 +65,102 @@ static inline double nml_from_bits_(int64_t i) {
 
 #include "nm_libm_tables.h"
 
-// ---- constants of s_sin.c / usncs.h (read from the library's .rodata, hexadecimal so that no decimal conversion rounds) ----
-#define NML_S1 (-0x1.5555555555555p-3)
-#define NML_S2 (0x1.1111111110ecep-7)
-#define NML_S3 (-0x1.a01a019db08b8p-13)
-#define NML_S4 (0x1.71de27b9a7ed9p-19)
-#define NML_S5 (-0x1.addffc2fcdf59p-26)
-#define NML_SN3 (-0x1.5555555555515p-3)
-#define NML_SN5 (0x1.11110e829872fp-7)
-#define NML_CS2 (0x1.0000000000000p-1)
-#define NML_CS4 (-0x1.5555555555535p-5)
-#define NML_CS6 (0x1.6c16bedd9e239p-10)
-#define NML_BIG (0x1.8000000000000p+45)
-#define NML_TOINT (0x1.8000000000000p+52)
-#define NML_HPINV (0x1.45f306dc9c883p-1)
-#define NML_MP1 (0x1.921fb58000000p+0)
-#define NML_MP2 (-0x1.dde973c000000p-27)
-#define NML_PP3 (-0x1.cb3b398000000p-55)
-#define NML_PP4 (-0x1.d747f23e32ed7p-83)
-#define NML_HP0 (0x1.921fb54442d18p+0)
-#define NML_HP1 (0x1.1a62633145c07p-54)
-#define NML_TAYLOR_LIMIT (0x1.020c49ba5e354p-3) /* 0.126 */
+// ---- the libraries' constants (read from its .rodata; hexadecimal so that no decimal conversion rounds).  On the device
+// they live in ONE __constant__ array, so that an FP64 instruction takes its constant straight from the constant bank: as
+// literals every use costs two extra instructions that build the 64-bit immediate.
+#define NML_CONSTANTS(X) \
+  X(NML_S1, -0x1.5555555555555p-3) \
+  X(NML_S2, 0x1.1111111110ecep-7) \
+  X(NML_S3, -0x1.a01a019db08b8p-13) \
+  X(NML_S4, 0x1.71de27b9a7ed9p-19) \
+  X(NML_S5, -0x1.addffc2fcdf59p-26) \
+  X(NML_SN3, -0x1.5555555555515p-3) \
+  X(NML_SN5, 0x1.11110e829872fp-7) \
+  X(NML_CS2, 0x1.0000000000000p-1) \
+  X(NML_CS4, -0x1.5555555555535p-5) \
+  X(NML_CS6, 0x1.6c16bedd9e239p-10) \
+  X(NML_BIG, 0x1.8000000000000p+45) \
+  X(NML_TOINT, 0x1.8000000000000p+52) \
+  X(NML_HPINV, 0x1.45f306dc9c883p-1) \
+  X(NML_MP1, 0x1.921fb58000000p+0) \
+  X(NML_MP2, -0x1.dde973c000000p-27) \
+  X(NML_PP3, -0x1.cb3b398000000p-55) \
+  X(NML_PP4, -0x1.d747f23e32ed7p-83) \
+  X(NML_HP0, 0x1.921fb54442d18p+0) \
+  X(NML_HP1, 0x1.1a62633145c07p-54) \
+  X(NML_TAYLOR_LIMIT, 0x1.020c49ba5e354p-3) \
+  X(NML_D3, -0x1.5555555555555p-2) \
+  X(NML_D5, 0x1.99999999997fdp-3) \
+  X(NML_D7, -0x1.24924923f7603p-3) \
+  X(NML_D9, 0x1.c71c6e5129a3bp-4) \
+  X(NML_D11, -0x1.7458022b13c25p-4) \
+  X(NML_D13, 0x1.375f08b31cbcep-4) \
+  X(NML_HPI, 0x1.921fb54442d18p+0) \
+  X(NML_HPI1, 0x1.1a62633145c07p-54) \
+  X(NML_OPI, 0x1.921fb54442d18p+1) \
+  X(NML_OPI1, 0x1.1a62633145c07p-53) \
+  X(NML_TWO52, 0x1.0p+52) \
+  X(NML_TWO8, 0x1.0p+8) \
+  X(NML_TWO500, 0x1.0p+500) \
+  X(NML_TWOM500, 0x1.0p-500)
+enum {
+#define NML_X(name, value) name##_IDX,
+  NML_CONSTANTS(NML_X)
+#undef NML_X
+  NML_N_CONSTANTS
+};
+#if defined(__CUDACC__)
+static __constant__ double nml_k_dev[NML_N_CONSTANTS] = {
+#define NML_X(name, value) value,
+    NML_CONSTANTS(NML_X)
+#undef NML_X
+};
+#endif
+static const double nml_k_host[NML_N_CONSTANTS] = {
+#define NML_X(name, value) value,
+    NML_CONSTANTS(NML_X)
+#undef NML_X
+};
+#if defined(__CUDA_ARCH__)
+#define NML_K(name) nml_k_dev[name##_IDX]
+#else
+#define NML_K(name) nml_k_host[name##_IDX]
+#endif
+#define NML_S1 NML_K(NML_S1)
+#define NML_S2 NML_K(NML_S2)
+#define NML_S3 NML_K(NML_S3)
+#define NML_S4 NML_K(NML_S4)
+#define NML_S5 NML_K(NML_S5)
+#define NML_SN3 NML_K(NML_SN3)
+#define NML_SN5 NML_K(NML_SN5)
+#define NML_CS2 NML_K(NML_CS2)
+#define NML_CS4 NML_K(NML_CS4)
+#define NML_CS6 NML_K(NML_CS6)
+#define NML_BIG NML_K(NML_BIG)
+#define NML_TOINT NML_K(NML_TOINT)
+#define NML_HPINV NML_K(NML_HPINV)
+#define NML_MP1 NML_K(NML_MP1)
+#define NML_MP2 NML_K(NML_MP2)
+#define NML_PP3 NML_K(NML_PP3)
+#define NML_PP4 NML_K(NML_PP4)
+#define NML_HP0 NML_K(NML_HP0)
+#define NML_HP1 NML_K(NML_HP1)
+#define NML_TAYLOR_LIMIT NML_K(NML_TAYLOR_LIMIT)
+#define NML_D3 NML_K(NML_D3)
+#define NML_D5 NML_K(NML_D5)
+#define NML_D7 NML_K(NML_D7)
+#define NML_D9 NML_K(NML_D9)
+#define NML_D11 NML_K(NML_D11)
+#define NML_D13 NML_K(NML_D13)
+#define NML_HPI NML_K(NML_HPI)
+#define NML_HPI1 NML_K(NML_HPI1)
+#define NML_OPI NML_K(NML_OPI)
+#define NML_OPI1 NML_K(NML_OPI1)
+#define NML_TWO52 NML_K(NML_TWO52)
+#define NML_TWO8 NML_K(NML_TWO8)
+#define NML_TWO500 NML_K(NML_TWO500)
+#define NML_TWOM500 NML_K(NML_TWOM500)
+
 
 NML_HD double nml_copysign(double mag, double sgn) {
   return NML_FROM_BITS((NML_BITS(mag) & 0x7fffffffffffffffLL) | (NML_BITS(sgn) & (int64_t)0x8000000000000000ULL));
@@ -194,20 +269,6 @@ NML_HD double nml_cos(double x) {
 }
 
 // ---- atan2 (e_atan2.c) ---------------------------------------------------------------------------------------------
-#define NML_D3 (-0x1.5555555555555p-2)
-#define NML_D5 (0x1.99999999997fdp-3)
-#define NML_D7 (-0x1.24924923f7603p-3)
-#define NML_D9 (0x1.c71c6e5129a3bp-4)
-#define NML_D11 (-0x1.7458022b13c25p-4)
-#define NML_D13 (0x1.375f08b31cbcep-4)
-#define NML_HPI (0x1.921fb54442d18p+0)
-#define NML_HPI1 (0x1.1a62633145c07p-54)
-#define NML_OPI (0x1.921fb54442d18p+1)
-#define NML_OPI1 (0x1.1a62633145c07p-53)
-#define NML_TWO52 (0x1.0p+52)
-#define NML_TWO8 (0x1.0p+8)
-#define NML_TWO500 (0x1.0p+500)
-#define NML_TWOM500 (0x1.0p-500)
 
 // d3 + v * (d5 + v * (d7 + v * (d9 + v * (d11 + v * d13)))), every step fused
 NML_HD double nml_atan_poly(double v) {
