@@ -168,8 +168,13 @@ def ncu_counts(key, kind):
     return entry
 
 
-def executed_roofline(entry, units, seconds, peak_ginstr):
-    """FP64-issue block from ncu counts scaled to `units` of work done in `seconds` (live)."""
+def executed_roofline(entry, units, seconds, peak_ginstr, sm_hz=1.965e9, schedulers=148 * 4):
+    """FP64-issue block from ncu counts scaled to `units` of work done in `seconds` (live).
+
+    Besides the executed FP64 fraction it evaluates the ISSUE MODEL this part obeys (measured on the fit kernels, see
+    DESIGN.md section 6): an FP64 warp instruction holds its scheduler's issue port for two cycles (64 FP64 lanes per
+    clock and SM = 16 per scheduler), any other instruction for one, so a launch needs at least
+    2 * N_fp64 + N_other issue cycles per scheduler; `issue_model_frac` = that minimum / the cycles the launch took."""
     if entry is None:
         return {"executed_frac": None, "ncu": "profiles/ncu_counts.json has no entry for this kernel build (stale or "
                                               "missing): re-run tools/ncu_counts.py"}
@@ -178,6 +183,9 @@ def executed_roofline(entry, units, seconds, peak_ginstr):
     out = {"executed_frac": fp64 * units / seconds / 1e9 / peak_ginstr,
            "executed_fp64_instr_per_unit_ncu": fp64,
            "executed_instr_per_unit_ncu": entry["smsp__inst_executed.sum"] * 32.0 * per_unit,
+           "issue_model_frac": (2.0 * entry["sm__inst_executed_pipe_fp64.sum"] + (entry["smsp__inst_executed.sum"]
+                                - entry["sm__inst_executed_pipe_fp64.sum"])) * per_unit * units
+           / (seconds * sm_hz * schedulers),
            "dram_bytes_per_unit_ncu": (entry["dram__bytes_read.sum"] + entry["dram__bytes_write.sum"]) * per_unit,
            "l2_bytes_per_unit_ncu": entry.get("lts__t_bytes.sum", 0.0) * per_unit,
            "lsu_wavefronts_per_unit_ncu": entry.get("l1tex__data_pipe_lsu_wavefronts.sum", 0.0) * per_unit,

@@ -44,8 +44,10 @@ METRICS = ["sm__inst_executed_pipe_fp64.sum", "smsp__inst_executed.sum", "smsp__
 KEYS = {
     "fit_group_positive_configs1": ("nm_fit_group_kernel", 1, "fit"),
     "fit_global_positive_configs1": ("nm_fit_global_kernel", 1, "fit"),
-    "mb_arbitrary_config3": ("nm_mb_kernel", 1, "mb"),
-    "mb_grid_config3": ("nm_mb_kernel", 1, "mb"),
+    # both instantiations are launched by every sweep (the one that does not apply returns at once): select by the
+    # DEMANGLED name, which carries the template argument
+    "mb_arbitrary_config3": ("nm_mb_kernel<.bool.0>", 1, "mb"),
+    "mb_grid_config3": ("nm_mb_kernel<.bool.1>", 1, "mb"),
     "sim_config4": ("nm_sim_kernel", 1, "sim"),
     "q_group_configs1": ("nm_qgroup_kernel", 1, "q"),
 }
@@ -136,6 +138,9 @@ def parse():
         if not (os.path.exists(path) and os.path.exists(upath)):
             continue
         rows = [r for r in csv.reader(open(path)) if len(r) > 10]
+        if not any("Metric Name" in r for r in rows):
+            print(key, "-- no kernel was profiled (see", path + ")")
+            continue
         hdr = next(r for r in rows if "Metric Name" in r)
         iname, ival, iunit, ik = hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit"), hdr.index("Kernel Name")
         entry = {"key": key, "source_sha": bench.source_sha(kind),
@@ -168,7 +173,8 @@ if __name__ == "__main__":
         print(",".join(METRICS))
     elif cmd == "select":
         regex, skip, _ = KEYS[sys.argv[2]]
-        print(f"-k regex:{regex} -s {skip} -c 1")
+        base = "--kernel-name-base demangled " if "<" in regex else ""
+        print(f"{base}-k regex:{regex} -s {skip} -c 1")  # substituted unquoted: the shell does not re-parse < > there
     elif cmd == "target":
         target(sys.argv[2])
     elif cmd == "parse":
