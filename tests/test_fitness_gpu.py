@@ -1,5 +1,6 @@
-"""Batched distances / multi-objective fitness on the device vs the restated reference formulas
-(analysis/statistics.py).  Reduction order differs from numpy's: 1e-12 relative."""
+"""Batched distances / multi-objective fitness on the device vs distances the UNMODIFIED reference computed
+(tests/golden/distances_golden.npz, analysis/statistics.py:10-54, 67-103) and vs the oracle's restated formulas (pinned to
+the same fixture on the CPU, tests/test_metrics_golden.py).  Reduction order differs from numpy's: 1e-12 relative."""
 import numpy as np
 import pytest
 
@@ -34,6 +35,15 @@ def test_distance_rows_vs_reference_formulas(cuda):
         np.testing.assert_allclose(d["js"][n], O.js_distance(x[n], data), rtol=1e-10, atol=1e-12)
         np.testing.assert_allclose(d["nd_zero_data"][n], O.normalized_distance(x[n], np.zeros(L)), rtol=1e-12)
     assert d["nd"][1] == 0.0 and abs(d["js"][0] - np.sqrt(np.log(2.0) / 2.0)) < 1e-12  # identical; empty vs data
+    # ... and against the reference's own outputs on the same seeded inputs
+    import os
+    from conftest import GOLDEN
+    g = dict(np.load(os.path.join(GOLDEN, "distances_golden.npz"), allow_pickle=False))
+    assert np.array_equal(g["x"], x) and np.array_equal(g["data"], data)
+    np.testing.assert_allclose(d["nd"], g["nd"], rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(d["l1"], g["l1"], rtol=1e-12)
+    np.testing.assert_allclose(d["js"], g["js"], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(d["nd_zero_data"], g["nd_zero_data"], rtol=1e-12)
 
 
 def test_simulation_to_fitness_stays_on_device(cuda):

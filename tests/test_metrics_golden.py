@@ -83,3 +83,21 @@ def test_metric_error_behaviour():
     assert M.latency_enter_shock_zone([(7, 0), (7, 1)], maze) == 1   # no zone described: len - 1, like the reference
     with pytest.raises(UnboundLocalError):
         M.shock_zone_entries([(7, 0)], maze)
+
+
+def test_oracle_distance_formulas_match_reference():
+    """The oracle's restated distances (np_oracle.normalized_distance / manhattan_distance / js_distance) and the product's
+    host mirror (analysis/statistics.py) against the reference's own outputs (tests/golden/distances_golden.npz)."""
+    import os
+    from conftest import GOLDEN
+    from navigation_model_b200.analysis import statistics as S
+    from oracle import np_oracle as O
+    g = dict(np.load(os.path.join(GOLDEN, "distances_golden.npz"), allow_pickle=False))
+    zero = np.zeros(len(g["data"]))
+    for n in range(len(g["x"])):
+        x = g["x"][n]
+        assert O.normalized_distance(x, g["data"]) == g["nd"][n] and S.normalized_distance(x, g["data"]) == g["nd"][n]
+        assert O.manhattan_distance(x, g["data"]) == g["l1"][n] and S.manhattan_distance(x, g["data"]) == g["l1"][n]
+        assert abs(O.js_distance(x, g["data"]) - g["js"][n]) <= 1e-15
+        assert abs(S.js_distance((x,), (g["data"],)) - g["js"][n]) <= 1e-15
+        assert O.normalized_distance(x, zero) == g["nd_zero_data"][n]
