@@ -389,8 +389,9 @@ __global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 
       // (candidates stay in action order: the reference's list is the action list filtered by
       //  reachability, so "k-th candidate" == "k-th reachable action" and nothing needs compacting)
       // Components outermost (one uniform dispatch per component and step), the eight endpoints innermost and
-      // unrolled; every endpoint is evaluated (an unreachable one reads the tile it would land on, or tile 0) and the
-      // reachable ones are selected afterwards, so the warp stays converged.  Per endpoint the sum still runs over the
+      // unrolled; every endpoint is evaluated (an unreachable one reads the tile it would land on, or tile 0; slots
+      // beyond the A actions read tile 0 and zero tables -- no per-slot `i < A` test) and the reachable ones are
+      // selected afterwards, so the warp stays converged.  Per endpoint the sum still runs over the
       // components in model order starting from 0.0 (:84-86).
       double val[kA];
 #pragma unroll
@@ -401,39 +402,36 @@ __global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 
         switch (a.component_kind[ci]) {
           case NM_COMP_ANXIETY:
 #pragma unroll
-            for (int i = 0; i < kA; ++i)
-              if (i < A) {
-                const int code = tiles[etile[i]];
-                val[i] = val[i] + anx_t[(code > 4 ? 0 : code) * nt];
-              }
+            for (int i = 0; i < kA; ++i) {
+              const int code = tiles[etile[i]];
+              val[i] = val[i] + anx_t[(code > 4 ? 0 : code) * nt];
+            }
             break;
           case NM_COMP_BCOST:  // cached[is_visitable] if moving else zeros   :410-413
 #pragma unroll
             for (int i = 0; i < kA; ++i)
-              if (i < A) val[i] = val[i] + (moving ? bcw_t[i * nt] : bc_zero);
+              val[i] = val[i] + (moving ? bcw_t[i * nt] : bc_zero);
             break;
           case NM_COMP_EXPERIENCE: {  // :473-479
             const double kk = home ? -k_home : -k_explo;
 #pragma unroll
-            for (int i = 0; i < kA; ++i)
-              if (i < A) {
-                // (double)count by the 2^52 trick: exact for a u32, and no I2F on the quarter-rate pipe
-                const double cn = __hiloint2double(0x43300000, (int)cnt[(size_t)etile[i] * cs]) - 4503599627370496.0;
-                const double ee = er.exp_nonpos(kk * cn);
-                val[i] = val[i] + (home ? 1.0 - ee : ee) * ex_w;
-              }
+            for (int i = 0; i < kA; ++i) {
+              // (double)count by the 2^52 trick: exact for a u32, and no I2F on the quarter-rate pipe
+              const double cn = __hiloint2double(0x43300000, (int)cnt[(size_t)etile[i] * cs]) - 4503599627370496.0;
+              const double ee = er.exp_nonpos(kk * cn);
+              val[i] = val[i] + (home ? 1.0 - ee : ee) * ex_w;
+            }
             break;
           }
           case NM_COMP_BPERSISTENCE:  // :508-513
 #pragma unroll
             for (int i = 0; i < kA; ++i)
-              if (i < A)
-                val[i] = val[i] + (moving ? (d.zero_act[i] ? bpw_m : bpw_plain) : (d.zero_act[i] ? bpw_plain : bpw_nm));
+              val[i] = val[i] + (moving ? (d.zero_act[i] ? bpw_m : bpw_plain) : (d.zero_act[i] ? bpw_plain : bpw_nm));
             break;
           case NM_COMP_VTABLE:  // :537-541
 #pragma unroll
             for (int i = 0; i < kA; ++i)
-              if (i < A) val[i] = val[i] + vt[etile[i]] * vt_w;
+              val[i] = val[i] + vt[etile[i]] * vt_w;
             break;
           default:
             break;
