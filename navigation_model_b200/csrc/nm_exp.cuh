@@ -30,6 +30,7 @@ struct ExpRegs {
 #pragma unroll
     for (int i = 0; i < 10; ++i) asm volatile("mov.f64 %0, %1;" : "=d"(c[i]) : "d"(c_exptab_k[i]));
     tab = table_addr;
+    asm volatile("mov.u32 %0, %0;" : "+r"(tab));  // pinned: not recomputed at every use under register pressure
   }
   __device__ __forceinline__ double exp_nonpos(double x) const {
     const double t = fma(x, c[0], c[1]);

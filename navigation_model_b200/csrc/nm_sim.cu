@@ -134,18 +134,41 @@ __global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 
   if (tid < 2 * kA) act_sm[tid] = d.act[tid >> 1][tid & 1];
   NmSimGeom geo;  // tile table, grid-line tables (nm_simgeom.cuh)
   geo.build(reinterpret_cast<unsigned char *>(GMAP ? vt_sm : vt_sm + nT), d.tiles, d.X, d.Y, d.st);
-  const uint8_t *tiles = geo.tiles;
   if (!GMAP && d.a.d_vtable && !d.a.vtable_per_mouse)
     for (int i = tid; i < nT; i += nt) vt_sm[i] = d.a.d_vtable[i];
   const nm_sim_args &a = d.a;
   const int64_t N = a.n_mice;
   const int64_t n_raw = (int64_t)blockIdx.x * nt + tid;
   CntT *cnt = count + (GMAP ? (size_t)n_raw : (size_t)tid);  // this thread's column
+  // shared-memory map: one pinned shared-window address, rows nt * sizeof(CntT) bytes apart (compile-time stride)
+  const uint32_t a_cnt = GMAP ? 0u : nm_pin_u32((uint32_t)__cvta_generic_to_shared(cnt));
+  auto cnt_ld = [&](int tile) -> uint32_t {
+    if constexpr (GMAP) {
+      return (uint32_t)cnt[(size_t)tile * cs];
+    } else {
+      uint32_t v;
+      if constexpr (sizeof(CntT) == 2)
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a_cnt + (uint32_t)tile * (uint32_t)(nt * sizeof(CntT))));
+      else
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a_cnt + (uint32_t)tile * (uint32_t)(nt * sizeof(CntT))));
+      return v;
+    }
+  };
+  auto cnt_st = [&](int tile, uint32_t v) {
+    if constexpr (GMAP) {
+      cnt[(size_t)tile * cs] = (CntT)v;
+    } else {
+      if constexpr (sizeof(CntT) == 2)
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(a_cnt + (uint32_t)tile * (uint32_t)(nt * sizeof(CntT))), "r"(v));
+      else
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(a_cnt + (uint32_t)tile * (uint32_t)(nt * sizeof(CntT))), "r"(v));
+    }
+  };
   if (SEEDED && a.d_init_visits) {  // continuing an earlier run: ExperienceComponent._maze_map_exp as it was left
     const uint32_t *iv = a.d_init_visits + (n_raw < N ? n_raw : N - 1) * nT;
-    for (int i = 0; i < nT; ++i) cnt[(size_t)i * cs] = (CntT)iv[i];
+    for (int i = 0; i < nT; ++i) cnt_st(i, iv[i]);
   } else {
-    for (int i = 0; i < nT; ++i) cnt[(size_t)i * cs] = (CntT)0;
+    for (int i = 0; i < nT; ++i) cnt_st(i, 0u);
   }
   __syncthreads();
 
@@ -167,22 +190,25 @@ __global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 
     const double beta = a.d_beta[n];
     // value * weight is the same product at every step (Component.weighted_values, behavioural_components.py:277-285):
     // it is formed once here and looked up afterwards.
-    double *anx_t = anx_sm + tid, *bcw_t = bcw_sm + tid;
+    // this thread's value * weight tables: anxiety by tile code at a_thr + code * nt * 8, biomechanical cost by action
+    // after them -- one pinned shared-window address, every offset a compile-time constant
+    uint32_t a_thr = nm_pin_u32((uint32_t)__cvta_generic_to_shared(anx_sm + tid));
+    constexpr uint32_t kRow = (uint32_t)nt * 8u;
     if (a.d_anxiety) {
       const double *q = a.d_anxiety + 5 * n;
       const double w = q[0];
-      anx_t[0 * nt] = -1.0 * w;                  // VOID
-      anx_t[2 * nt] = q[1] * w;                  // CORNER: p1                    behavioural_components.py:364
-      anx_t[1 * nt] = (q[2] * q[1]) * w;         // WALL:   p2 * p1
-      anx_t[3 * nt] = (q[3] * q[2] * q[1]) * w;  // CENTRE: p3 * p2 * p1
-      anx_t[4 * nt] = q[4] * w;                  // DECISION_POINT: p4            :332-333
+      nm_sts_f64(a_thr + 0u * kRow, -1.0 * w);                  // VOID
+      nm_sts_f64(a_thr + 2u * kRow, q[1] * w);                  // CORNER: p1                    behavioural_components.py:364
+      nm_sts_f64(a_thr + 1u * kRow, (q[2] * q[1]) * w);         // WALL:   p2 * p1
+      nm_sts_f64(a_thr + 3u * kRow, (q[3] * q[2] * q[1]) * w);  // CENTRE: p3 * p2 * p1
+      nm_sts_f64(a_thr + 4u * kRow, q[4] * w);                  // DECISION_POINT: p4            :332-333
     }
     double bc_zero = 0.0;  // 0.0 * W_bcost: the component's contribution when the mouse has just moved (:410-413)
     if (a.d_bcost_table) {
       const double w = a.d_bcost_weight[n];
       bc_zero = 0.0 * w;
 #pragma unroll
-      for (int i = 0; i < kA; ++i) bcw_t[i * nt] = i < A ? a.d_bcost_table[n * A + i] * w : 0.0;
+      for (int i = 0; i < kA; ++i) nm_sts_f64(a_thr + (5u + (uint32_t)i) * kRow, i < A ? a.d_bcost_table[n * A + i] * w : 0.0);
     }
     double ex_w = 0, xi = 0, k_home = 0, k_explo = 0, th_explo = 0, th_home = 0, fam = 0.0;
     bool home = false;  // ExperienceComponent.State.EXPLO at start (:440)
@@ -196,6 +222,7 @@ __global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 
       fam = q[1];
       home = q[2] != 0.0;
     }
+    a_thr = nm_pin_u32(a_thr);  // re-pinned after the stores above: the step loop's (plain) loads cannot move above them
     double bpw_plain = 0, bpw_m = 0, bpw_nm = 0;  // bp * W, (Wm*bp) * W, (Wnm*bp) * W   (:502-513)
     if (a.d_bpersistence) {
       const double *q = a.d_bpersistence + 4 * n;
@@ -275,8 +302,8 @@ __global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 
           corridor_side = side;
         }
       }
-      const uint32_t c = cnt[(size_t)tile * cs];
-      cnt[(size_t)tile * cs] = (CntT)(c + 1u);
+      const uint32_t c = cnt_ld(tile);
+      cnt_st(tile, c + 1u);
       if (c == 0u) {
         n_visited += 1;
         // perc = n_visited * 100 / number_visitable_tiles >= percentage      metrics.py:711-721
@@ -322,7 +349,7 @@ __global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 
       const bool need = active && dirty;
       const unsigned dmask = __ballot_sync(kFull, need);
       if (dmask != 0u) {
-        const bool start_ok = cur_inside && tiles[cur_tx * d.Y + cur_ty] != 0;  // tile under the mouse (maze.py:578)
+        const bool start_ok = cur_inside && geo.tile_code(cur_tx * d.Y + cur_ty) != 0;  // tile under the mouse (maze.py:578)
         const int cur_tile = cur_inside ? cur_tx * d.Y + cur_ty : 0;
         if (need) {
           nm_host_sincos(ori, &s, &c);
@@ -380,7 +407,7 @@ __global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 
       if (a.model_kind == 0) {  // ---------------- BehaviouralModel -----------------------------------------
       // -- component updates                                                 exploration_model.py:79-81
       if (a.d_experience) {  // :456-466 (count of the current tile was just incremented above)
-        const double nvis = cur_inside ? (double)cnt[(size_t)(cur_tx * d.Y + cur_ty) * cs] : 0.0;
+        const double nvis = cur_inside ? (double)cnt_ld(cur_tx * d.Y + cur_ty) : 0.0;
         fam = (1.0 - xi) * fam + xi * nvis;
         if (home && fam >= th_explo) home = false;
         else if (!home && fam < th_home) home = true;
@@ -403,21 +430,21 @@ __global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 
           case NM_COMP_ANXIETY:
 #pragma unroll
             for (int i = 0; i < kA; ++i) {
-              const int code = tiles[etile[i]];
-              val[i] = val[i] + anx_t[(code > 4 ? 0 : code) * nt];
+              const int code = (int)geo.tile_code(etile[i]);
+              val[i] = val[i] + nm_lds_f64(a_thr + (uint32_t)(code > 4 ? 0 : code) * kRow);
             }
             break;
           case NM_COMP_BCOST:  // cached[is_visitable] if moving else zeros   :410-413
 #pragma unroll
             for (int i = 0; i < kA; ++i)
-              val[i] = val[i] + (moving ? bcw_t[i * nt] : bc_zero);
+              val[i] = val[i] + (moving ? nm_lds_f64(a_thr + (5u + (uint32_t)i) * kRow) : bc_zero);
             break;
           case NM_COMP_EXPERIENCE: {  // :473-479
             const double kk = home ? -k_home : -k_explo;
 #pragma unroll
             for (int i = 0; i < kA; ++i) {
               // (double)count by the 2^52 trick: exact for a u32, and no I2F on the quarter-rate pipe
-              const double cn = __hiloint2double(0x43300000, (int)cnt[(size_t)etile[i] * cs]) - 4503599627370496.0;
+              const double cn = __hiloint2double(0x43300000, (int)cnt_ld(etile[i])) - 4503599627370496.0;
               const double ee = er.exp_nonpos(kk * cn);
               val[i] = val[i] + (home ? 1.0 - ee : ee) * ex_w;
             }
@@ -518,7 +545,7 @@ __global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 
       if (prev_moved && !tile_changed) static_runs += 1;
       prev_moved = tile_changed;
       if (a.n_ori_bins > 0 && tile_changed &&
-          (a.ori_tile_filter == 0u || (cur_inside && ((a.ori_tile_filter >> tiles[cur_tx * d.Y + cur_ty]) & 1u)))) {
+          (a.ori_tile_filter == 0u || (cur_inside && ((a.ori_tile_filter >> geo.tile_code(cur_tx * d.Y + cur_ty)) & 1u)))) {
         // hist_orientations (:329-356): the turn of this step, brought back by one full turn when it leaves
         // [min_lim, max_lim]; numpy.histogram's bins (left-closed, the last one closed on both sides)
         double rel = ori - ori_before;
@@ -567,7 +594,7 @@ __global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 
       for (int code = 0; code < 8; ++code) {
         int acc = 0;
         for (int tile = 0; tile < nT; ++tile)
-          if ((tiles[tile] & 7) == code) acc += (int)cnt[(size_t)tile * cs];
+          if ((int)(geo.tile_code(tile) & 7u) == code) acc += (int)cnt_ld(tile);
         a.d_tile_counts[8 * n + code] = acc;
       }
     }
@@ -576,7 +603,7 @@ __global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 
       int zone_occ = 0;  // positions inside the zone = the visit map summed over the zone's tiles
       if (a.d_tile_flags)
         for (int tile = 0; tile < nT; ++tile)
-          if (a.d_tile_flags[tile] & NM_TILE_ZONE_IN) zone_occ += (int)cnt[(size_t)tile * cs];
+          if (a.d_tile_flags[tile] & NM_TILE_ZONE_IN) zone_occ += (int)cnt_ld(tile);
       int *q = a.d_zone_metrics + 4 * n;
       q[0] = zone_latency; q[1] = zone_occ; q[2] = zone_entries; q[3] = corridor_switches;
     }
@@ -586,7 +613,7 @@ __global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 
       for (int sub = 0; sub < NM_MAX_SUBAREAS; ++sub) {
         int acc = 0;
         for (int tile = 0; tile < nT; ++tile)
-          if (d.subareas[tile] == sub) acc += (int)cnt[(size_t)tile * cs];
+          if (d.subareas[tile] == sub) acc += (int)cnt_ld(tile);
         a.d_subarea_counts[(int64_t)NM_MAX_SUBAREAS * n + sub] = acc;
       }
     }
@@ -633,7 +660,7 @@ __global__ void __launch_bounds__(256) nm_segments_kernel(const uint8_t *__restr
     const double x1 = seg[4 * i], y1 = seg[4 * i + 1], x2 = seg[4 * i + 2], y2 = seg[4 * i + 3];
     const int tx = geo.tile(x1), ty = geo.tile(y1);
     const bool s_in = (unsigned)tx < (unsigned)X && (unsigned)ty < (unsigned)Y;
-    const bool start_ok = s_in && geo.tiles[s_in ? tx * Y + ty : 0] != 0;
+    const bool start_ok = s_in && geo.tile_code(s_in ? tx * Y + ty : 0) != 0;
     int et;
     out[i] = geo.move_ok(start_ok, tx, ty, x1, y1, x2, y2, &et) ? 1 : 0;
   }

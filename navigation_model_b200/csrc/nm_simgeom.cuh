@@ -23,13 +23,39 @@
 
 #include "nm_geometry.h"
 
+// Shared-memory reads by 32-bit shared-window address.  The tables below are addressed through four such addresses,
+// PINNED in registers by an opaque move: under the simulation kernel's 80-register cap the compiler otherwise
+// rematerialises every table pointer at every use (S2R / S2UR / UMOV / ULEA / IMAD chains from the launch parameters --
+// 14 % of the kernel's executed instructions in round 1's profile).
+// Loads of tables that no longer change: plain asm (the compiler may schedule and merge them freely).  Their addresses
+// derive from a pin executed AFTER the table was written, so no load can move above its table's initialisation.
+__device__ __forceinline__ uint32_t nm_lds_u8(uint32_t addr) {
+  uint32_t v;
+  asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ double nm_lds_f64(uint32_t addr) {
+  double v;
+  asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void nm_sts_f64(uint32_t addr, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t nm_pin_u32(uint32_t v) {
+  asm volatile("mov.u32 %0, %0;" : "+r"(v));
+  return v;
+}
+
 struct NmSimGeom {
-  const uint8_t *tiles;   // [X*Y] shared memory
-  const uint8_t *crossx;  // [X][Y]
-  const uint8_t *crossy;  // [Y][X]
-  const double *gl;       // [max(X,Y)]  fl((i+1)*st)
+  uint32_t a_tiles;   // [X*Y] shared-window address of the tile table
+  uint32_t a_crossx;  // [X][Y]
+  uint32_t a_crossy;  // [Y][X]
+  uint32_t a_gl;      // [max(X,Y)] doubles  fl((i+1)*st)
   int X, Y;
   double st, inv;
+
+  __device__ __forceinline__ uint32_t tile_code(int idx) const { return nm_lds_u8(a_tiles + (uint32_t)idx); }
 
   static __host__ __device__ size_t smem_bytes(int X, int Y) {
     const int m = X > Y ? X : Y;
@@ -40,11 +66,12 @@ struct NmSimGeom {
   __device__ __forceinline__ void attach(unsigned char *base, int X_, int Y_, double st_) {
     X = X_; Y = Y_; st = st_; inv = 1.0 / st_;
     const int m = X > Y ? X : Y;
-    const size_t slab = ((size_t)X * Y + 15) & ~(size_t)15;
-    gl = reinterpret_cast<const double *>(base);
-    tiles = base + (size_t)m * sizeof(double);
-    crossx = tiles + slab;
-    crossy = crossx + slab;
+    const uint32_t slab = ((uint32_t)(X * Y) + 15u) & ~15u;
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(base);
+    a_gl = nm_pin_u32(b);
+    a_tiles = nm_pin_u32(b + (uint32_t)m * (uint32_t)sizeof(double));
+    a_crossx = nm_pin_u32(a_tiles + slab);
+    a_crossy = nm_pin_u32(a_crossx + slab);
   }
 
   static __device__ __noinline__ void fill(unsigned char *base, const uint8_t *g_tiles, int X, int Y, double st) {
@@ -75,9 +102,11 @@ struct NmSimGeom {
     }
   }
 
+  // every thread of the CTA: fill the tables, synchronise, THEN take the (pinned) addresses the reads go through
   __device__ __forceinline__ void build(unsigned char *base, const uint8_t *g_tiles, int X_, int Y_, double st_) {
-    attach(base, X_, Y_, st_);
     fill(base, g_tiles, X_, Y_, st_);
+    __syncthreads();
+    attach(base, X_, Y_, st_);
   }
 
   __device__ __forceinline__ int tile(double x) const {
@@ -91,7 +120,7 @@ struct NmSimGeom {
   // one pass of the walk: lines crossed between the start tile index s_t and the end tile index e_t along the axis
   // whose coordinates are (pa, ea); (pb, eb) are the coordinates along the other axis.
   __device__ __forceinline__ bool pass(bool ok, double pa, double pb, double ea, double eb, int s_t, int e_t,
-                                       const uint8_t *cross, int n_other) const {
+                                       const uint32_t cross, int n_other) const {
     const bool sw = pa > ea;                       // order the end points along this axis
     const double a1 = sw ? ea : pa, b1 = sw ? eb : pb;
     const int lo = sw ? e_t : s_t, hi = sw ? s_t : e_t;
@@ -103,19 +132,20 @@ struct NmSimGeom {
     for (int c = 0; c < 2; ++c) {                  // the first two crossings, predicated
       const bool on = n > c;
       const int d = on ? lo + c : 0;
-      const double g = gl[d];
+      const double g = nm_lds_f64(a_gl + 8u * (uint32_t)d);
       const double o = __dadd_rn(__dmul_rn(m, __dsub_rn(g, a1)), b1);
       const int t = tile(o);
       const bool in = (unsigned)t < (unsigned)n_other;
-      const uint8_t f = cross[d * n_other + (in ? t : 0)];
+      const uint32_t f = nm_lds_u8(cross + (uint32_t)(d * n_other + (in ? t : 0)));
       good = good && (!on || (in && f != 0));
     }
 #pragma unroll 1
     for (int c = 2; c < n; ++c) {                  // longer moves (actions of more than two tiles)
       const int d = lo + c;
-      const double o = __dadd_rn(__dmul_rn(m, __dsub_rn(gl[d], a1)), b1);
+      const double o = __dadd_rn(__dmul_rn(m, __dsub_rn(nm_lds_f64(a_gl + 8u * (uint32_t)d), a1)), b1);
       const int t = tile(o);
-      good = good && (unsigned)t < (unsigned)n_other && cross[d * n_other + t] != 0;
+      const bool in = (unsigned)t < (unsigned)n_other;
+      good = good && in && nm_lds_u8(cross + (uint32_t)(d * n_other + (in ? t : 0))) != 0;
     }
     return good;
   }
@@ -128,9 +158,9 @@ struct NmSimGeom {
     const bool e_in = (unsigned)etx < (unsigned)X && (unsigned)ety < (unsigned)Y;
     const int et = e_in ? etx * Y + ety : 0;
     *etile = et;
-    const bool ok = start_ok && e_in && tiles[et] != 0;      // maze.py:578-579
-    const bool gx = pass(ok, px, py, ex, ey, stx, etx, crossx, Y);  // vertical lines   :581-595
-    const bool gy = pass(ok, py, px, ey, ex, sty, ety, crossy, X);  // horizontal lines :597-610
+    const bool ok = start_ok && e_in && tile_code(et) != 0;  // maze.py:578-579
+    const bool gx = pass(ok, px, py, ex, ey, stx, etx, a_crossx, Y);  // vertical lines   :581-595
+    const bool gy = pass(ok, py, px, ey, ex, sty, ety, a_crossy, X);  // horizontal lines :597-610
     return ok && gx && gy;
   }
 };
