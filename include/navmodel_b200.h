@@ -224,6 +224,17 @@ int nm_vtable_sweep(int alg, const nm_maze *mz, const nm_streams *st, const doub
                     const double *d_gamma, int64_t P, const double *d_v_init, int v_init_per_unit,
                     double *d_v_out, void *stream);
 
+/* ONE parameter set over ONE session of the streams, with what RLAlgorithm.update RETURNS per step: the reference puts
+ * Update(transition, dv, |rpe|) of every online step into the replay buffer (rl.py:97-98, 190-194, 233-237, 260-262).
+ * Same recurrence and operations as nm_vtable_sweep (bit-identical table).  This is the launch behind
+ * ConditioningExperiment.run / do_replays for the built-in learners.
+ *   d_v_init: NULL (zeros) | [X*Y];  d_v_out: [X*Y] dense;  d_dv_out, d_rpe_out: [records of the session] or NULL
+ *   (records past the session's online count are replay passes: their entries are filled too). */
+int nm_vtable_trace(int alg, const nm_maze *mz, const nm_streams *st, int session, double alpha, double gamma,
+                    const double *d_v_init, double *d_v_out, double *d_dv_out, double *d_rpe_out, void *stream);
+/* largest number of visitable tiles nm_vtable_trace holds (its table lives in shared memory) */
+int nm_vtable_trace_max_states(void);
+
 /* Largest number of visitable tiles (compact states) the per-parameter-set value-table kernels can hold in SHARED
  * memory (863 with 227 KB: 32 table columns of 8 bytes per state next to the stream rings).  Larger mazes run the same
  * sweeps with their tables in device memory (T[state][parameter set], coalesced, L2 / HBM resident; also on request

@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_NAME = "libnavmodel_b200.so"
 LIB_PATH = os.path.join(HERE, LIB_NAME)
 
-SOURCES = ["nm_error.cpp", "nm_mouse.cpp", "nm_stream.cpp", "nm_maze.cu", "nm_fit.cu", "nm_sim.cu", "nm_mb.cu", "nm_q.cu", "nm_dist.cu", "nm_session.cu"]
+SOURCES = ["nm_error.cpp", "nm_mouse.cpp", "nm_stream.cpp", "nm_maze.cu", "nm_fit.cu", "nm_sim.cu", "nm_mb.cu", "nm_q.cu", "nm_dist.cu", "nm_session.cu", "nm_trace.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

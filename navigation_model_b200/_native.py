@@ -74,6 +74,8 @@ SIGNATURES = {
     "nm_qtable_sweep_mode": (C.c_int, [_p, C.POINTER(C.c_int)]),
     "nm_distance_rows": (C.c_int, [C.c_int, _p, _p, _i64, C.c_int, _p, _p]),
     "nm_simulate": (C.c_int, [_p, _p, _p]),
+    "nm_vtable_trace": (C.c_int, [C.c_int, _p, _p, C.c_int, C.c_double, C.c_double, _p, _p, _p, _p, _p]),
+    "nm_vtable_trace_max_states": (C.c_int, []),
     "nm_simulate_fits": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "nm_simulate_scratch_columns": (C.c_int64, [C.c_int64]),
     "nm_sim_args_size": (C.c_int, []),

@@ -554,6 +554,12 @@ int q_global_tables(int device, void *stream, size_t bytes, double **out) {
   return NM_OK;
 }
 
+size_t q_global_capacity(int device, void *stream) {
+  std::lock_guard<std::mutex> lock(q_tables_mutex());
+  const auto it = q_tables_map().find(std::make_pair(device, stream));
+  return it == q_tables_map().end() ? 0 : it->second.second;
+}
+
 // 1 when "mode 0" of the last sweep on (device, stream) ran with tables in device memory: nm_qtable_sweep_mode
 std::map<std::pair<int, void *>, int> &q_last_global() {
   static std::map<std::pair<int, void *>, int> m;
@@ -707,6 +713,20 @@ extern "C" int nm_qtable_sweep(const nm_maze *mz, const nm_streams *st, const in
   if (max_sets > (int64_t)sms * 896) max_sets = (int64_t)sms * 896;
   e = cudaFuncSetAttribute(nm_qglobal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_fixed);
   if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "cudaFuncSetAttribute(nm_qglobal_kernel): %s", cudaGetErrorString(e));
+  if (a.mode) {
+    // the device is deciding whether the table-per-warp kernel owns this sweep (then every launch below is a no-op):
+    // do not GROW the per-set table scratch (504 MB for the configs[1] grid) for launches that may not need it -- when
+    // the block kept for this (device, stream) is too small, wait for the decision once
+    const int64_t first = P < max_sets ? P : max_sets;
+    const size_t need = sizeof(double) * (size_t)rows1 * (size_t)((first + 31) & ~(int64_t)31);
+    if (q_global_capacity(mz->device, stream) < need) {
+      int decided = 0;
+      e = cudaStreamSynchronize(cs);
+      if (e == cudaSuccess) e = cudaMemcpy(&decided, a.mode, sizeof(int), cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_qtable_sweep: reading the sweep mode: %s", cudaGetErrorString(e));
+      if (decided == 1) return NM_OK;
+    }
+  }
   for (int64_t lo = 0; lo < P; lo += max_sets) {
     QArgs b = a;
     b.P = P - lo < max_sets ? P - lo : max_sets;

@@ -11,9 +11,9 @@ Same names, signatures and error behaviour as the reference (``rl.py:12-424``):
 
 ``ConditioningExperiment.run`` / ``do_replays`` with the three built-in algorithms and ``ShuffledReplays``
 do **not** loop in Python: the trajectory is flattened to a step stream by the native builder
-(``nm_stream_build``) and the whole recurrence -- online pass and replay passes -- runs in one launch of
-the sweep kernel (``nm_vtable_sweep`` with a single parameter set; many parameter sets:
-:mod:`navigation_model_b200.sweep`).  Replay passes are parameter-independent step records too: shuffled
+(``nm_stream_build``) and the whole recurrence -- online pass and replay passes -- runs in one launch
+(``nm_vtable_trace``: one parameter set, the table plus the ``dv`` / ``|rpe|`` every ``update`` returns, which fill the
+replay buffer's ``Update`` entries like the reference's; many parameter sets: :mod:`navigation_model_b200.sweep`).  Replay passes are parameter-independent step records too: shuffled
 passes are permutations of the online records; ``imaginary=True`` passes (``rl.py:388-418``) are transitions
 sampled from the maze with the stdlib ``random`` module exactly as the reference samples them (seed it with
 ``random.seed`` for a replayable run), flattened by ``nm_stream_build_pairs``.  That path needs a CUDA device
@@ -319,12 +319,17 @@ class ConditioningExperiment:
         mouse = alg._mouse if with_cand else None
         recs, trans = sweep.build_session_records(self._maze, traj, rew, mouse=mouse,
                                                   orientations=orientations, make_transitions=True)
-        for t in trans:
-            rs.append(Update(transition=t))
+        fresh = [Update(transition=t) for t in trans]
+        for u in fresh:
+            rs.append(u)
         n_online = len(recs)
         if do_replays:
             recs = np.concatenate([recs, self._replay_records()])
-        self._launch(recs, n_online)
+        trace = self._launch(recs, n_online)
+        if trace is not None:  # what the learner's update returned for every online step (rl.py:190-194, 260-262)
+            dv, rpe = trace
+            for i, u in enumerate(fresh):
+                u.dv, u.rpe = dv[i], rpe[i]
 
     def _replay_records(self):
         from .. import sweep
@@ -361,7 +366,11 @@ class ConditioningExperiment:
         from .. import sweep
         alg = self._alg
         v = alg._v_table
-        out = sweep.vtable_single(self._maze, alg.device_kind, recs, n_online,
-                                  float(np.asarray(alg._alpha).reshape(-1)[0]),
-                                  float(np.asarray(alg._discount_rate).reshape(-1)[0]), v)
-        v[...] = out  # the reference mutates the table in place
+        alpha = float(np.asarray(alg._alpha).reshape(-1)[0])
+        gamma = float(np.asarray(alg._discount_rate).reshape(-1)[0])
+        traced = sweep.vtable_trace_single(self._maze, alg.device_kind, recs, n_online, alpha, gamma, v)
+        if traced is None:  # more states than the trace kernel's table holds: tables only (Update.dv / rpe stay None)
+            v[...] = sweep.vtable_single(self._maze, alg.device_kind, recs, n_online, alpha, gamma, v)
+            return None
+        v[...] = traced[0]  # the reference mutates the table in place
+        return traced[1], traced[2]

@@ -640,6 +640,32 @@ def vtable_single(maze, alg, records, n_online, alpha, gamma, v_init):
     return sw.v_tables([alpha], [gamma], v_init=v_init)[0, 0]
 
 
+def vtable_trace_single(maze, alg, records, n_online, alpha, gamma, v_init):
+    """One parameter set, one stream through ``nm_vtable_trace``: the dense ``float64[X, Y]`` table AND what the
+    learner's ``update`` returns per record -- ``dv`` and ``|rpe|`` (``rl.py:190-194, 260-262``).  ``None`` when the maze
+    has more states than the trace kernel's shared-memory table holds (the caller falls back to :func:`vtable_single`)."""
+    import torch
+    lib = _native.lib()
+    hm = host_maze(maze)
+    if hm.num_states > lib.nm_vtable_trace_max_states():
+        return None
+    sw = ConditioningSweep(maze, alg)
+    sw.add_records(records, n_online)
+    sw._ensure_device()
+    dev = sw.torch_device
+    X, Y = maze.shape
+    n = len(records)
+    vi = None if v_init is None else torch.from_numpy(np.ascontiguousarray(v_init, dtype=np.float64).reshape(-1)).to(dev)
+    out = torch.empty(X * Y + 2 * n, dtype=torch.float64, device=dev)
+    v_t, dv_t, rpe_t = out[: X * Y], out[X * Y: X * Y + n], out[X * Y + n:]
+    with torch.cuda.device(dev):
+        _native.check(lib.nm_vtable_trace(sw.alg, sw._dmaze.handle, sw._dstreams.handle, 0, float(alpha), float(gamma),
+                                          _native.tensor_ptr(vi), _native.tensor_ptr(v_t), _native.tensor_ptr(dv_t),
+                                          _native.tensor_ptr(rpe_t), _native.cuda_stream_ptr()))
+    host = out.cpu().numpy()
+    return host[: X * Y].reshape(X, Y), host[X * Y: X * Y + n], host[X * Y + n:]
+
+
 class _TileActionSweep:
     """Shared host side of the two tile-action agents (model-based, Q-table): actions are tile displacements, the
     transition model ``next[s, a]`` is the maze's own geometry (``Maze.is_movement_possible``, ``maze.py:512-527``),
