@@ -49,6 +49,8 @@ struct SimDev {
   double st;
   double act[kA][2];
   uint8_t zero_act[kA];
+  uint32_t zero_mask;    // bit i = zero_act[i]
+  uint32_t comp_word;    // 4 bits per ACTIVE component, in model order: its NM_COMP_* kind (0 terminates the list)
   uint8_t null_act[kA];  // exactly (0, 0): the endpoint is the position itself
   uint8_t walk_ord[kA];  // ordinal of action i among the actions that need a ray walk
   uint32_t walk_list;    // 4 bits per entry: walk_list >> 4j & 7 = j-th action that needs a ray walk
@@ -178,6 +180,7 @@ __global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 
   const int64_t n = live ? n_raw : N - 1;
   const int A = a.n_actions;
   const int T = a.n_steps;
+  const uint32_t zero_mask = nm_pin_u32(d.zero_mask), comp_word = nm_pin_u32(d.comp_word);
 
   int status = 0;
   ExpRegs er;
@@ -424,9 +427,10 @@ __global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 
 #pragma unroll
       for (int i = 0; i < kA; ++i) val[i] = 0.0;
 #pragma unroll 1
-      for (int ci = 0; ci < a.n_components; ++ci) {
-        if (!a.component_active[ci]) continue;  // inactive: contributes integer 0 (:283-285)
-        switch (a.component_kind[ci]) {
+      // the active components' kinds travel in ONE register word (an inactive component contributes integer 0,
+      // :283-285, and is left out on the host): no per-step loads from the launch-parameter arrays
+      for (uint32_t cw = comp_word; cw != 0u; cw >>= 4) {
+        switch (cw & 15u) {
           case NM_COMP_ANXIETY:
 #pragma unroll
             for (int i = 0; i < kA; ++i) {
@@ -453,7 +457,7 @@ __global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 
           case NM_COMP_BPERSISTENCE:  // :508-513
 #pragma unroll
             for (int i = 0; i < kA; ++i)
-              val[i] = val[i] + (moving ? (d.zero_act[i] ? bpw_m : bpw_plain) : (d.zero_act[i] ? bpw_plain : bpw_nm));
+              val[i] = val[i] + (moving ? ((zero_mask >> i) & 1u ? bpw_m : bpw_plain) : ((zero_mask >> i) & 1u ? bpw_plain : bpw_nm));
             break;
           case NM_COMP_VTABLE:  // :537-541
 #pragma unroll
@@ -708,10 +712,18 @@ extern "C" int nm_simulate(const nm_maze *mz, const nm_sim_args *args, void *str
   d.Y = mz->Y;
   d.n_visitable = mz->num_states;
   d.st = mz->size_tile;
+  d.zero_mask = 0u;
+  d.comp_word = 0u;
+  {
+    int slot = 0;
+    for (int i = 0; i < a.n_components; ++i)
+      if (a.component_active[i]) d.comp_word |= (uint32_t)(a.component_kind[i] & 15) << (4 * slot++);
+  }
   for (int i = 0; i < kA; ++i) {
     d.act[i][0] = i < a.n_actions ? a.h_actions[2 * i] : 0.0;
     d.act[i][1] = i < a.n_actions ? a.h_actions[2 * i + 1] : 0.0;
     d.zero_act[i] = (i < a.n_actions && a.h_zero_action) ? a.h_zero_action[i] : 0;
+    if (d.zero_act[i]) d.zero_mask |= 1u << i;
   }
   d.n_walk = 0;
   d.walk_list = 0u;
