@@ -35,11 +35,16 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 
 constexpr int kA = NM_MAX_CAND;
 constexpr int kSimThreads = 128;
+#ifndef NM_SIM_BCW_GLOBAL
+#define NM_SIM_BCW_GLOBAL 1  // the biomechanical-cost tables stay in device memory: 64 B of shared memory less per mouse
+                             // buy a 7th resident CTA per SM (measured: 144.7 ms against 154.3 ms per 1M x 1000 steps)
+#endif
+constexpr int kBcwRows = NM_SIM_BCW_GLOBAL ? 0 : kA;
 #ifndef NM_SIM_MIN_CTAS
-#define NM_SIM_MIN_CTAS 3  // resident CTAs per SM the register allocation is capped for (32-bit visit counters)
+#define NM_SIM_MIN_CTAS 4  // resident CTAs per SM the register allocation is capped for (32-bit visit counters)
 #endif
 #ifndef NM_SIM_MIN_CTAS_U16
-#define NM_SIM_MIN_CTAS_U16 6  // same, for the variant with 16-bit visit counters
+#define NM_SIM_MIN_CTAS_U16 7  // same, for the variant with 16-bit visit counters (72 registers; more warps beat fewer spills)
 #endif
 
 struct SimDev {
@@ -129,9 +134,9 @@ __global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 
   double *anx_sm = exp_tab + 16 + 2 * kA + (nt / 32) * 4 + 2 * nt;
   double *bcw_sm = anx_sm + 5 * nt;
   // visit map: count[tile * cs + column]; shared memory (cs = nt, column = tid) or device memory (GMAP)
-  CntT *count = GMAP ? reinterpret_cast<CntT *>(d.a.d_visit_scratch) : reinterpret_cast<CntT *>(bcw_sm + kA * nt);
+  CntT *count = GMAP ? reinterpret_cast<CntT *>(d.a.d_visit_scratch) : reinterpret_cast<CntT *>(bcw_sm + kBcwRows * nt);
   const size_t cs = GMAP ? (size_t)d.scratch_columns : (size_t)nt;
-  double *vt_sm = GMAP ? bcw_sm + kA * nt : reinterpret_cast<double *>(count + (size_t)nT * nt);
+  double *vt_sm = GMAP ? bcw_sm + kBcwRows * nt : reinterpret_cast<double *>(count + (size_t)nT * nt);
   if (tid < 16) exp_tab[tid] = c_exp2tab[tid];
   if (tid < 2 * kA) act_sm[tid] = d.act[tid >> 1][tid & 1];
   NmSimGeom geo;  // tile table, grid-line tables (nm_simgeom.cuh)
@@ -207,11 +212,16 @@ __global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 
       nm_sts_f64(a_thr + 4u * kRow, q[4] * w);                  // DECISION_POINT: p4            :332-333
     }
     double bc_zero = 0.0;  // 0.0 * W_bcost: the component's contribution when the mouse has just moved (:410-413)
+    double bc_w = 0.0;
+    const double *bc_row = a.d_bcost_table ? a.d_bcost_table + n * A : nullptr;
     if (a.d_bcost_table) {
       const double w = a.d_bcost_weight[n];
       bc_zero = 0.0 * w;
+      bc_w = w;
+#if !NM_SIM_BCW_GLOBAL
 #pragma unroll
       for (int i = 0; i < kA; ++i) nm_sts_f64(a_thr + (5u + (uint32_t)i) * kRow, i < A ? a.d_bcost_table[n * A + i] * w : 0.0);
+#endif
     }
     double ex_w = 0, xi = 0, k_home = 0, k_explo = 0, th_explo = 0, th_home = 0, fam = 0.0;
     bool home = false;  // ExperienceComponent.State.EXPLO at start (:440)
@@ -441,7 +451,11 @@ __global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 
           case NM_COMP_BCOST:  // cached[is_visitable] if moving else zeros   :410-413
 #pragma unroll
             for (int i = 0; i < kA; ++i)
+#if NM_SIM_BCW_GLOBAL
+              val[i] = val[i] + (moving ? __ldg(bc_row + (i < A ? i : A - 1)) * bc_w : bc_zero);
+#else
               val[i] = val[i] + (moving ? nm_lds_f64(a_thr + (5u + (uint32_t)i) * kRow) : bc_zero);
+#endif
             break;
           case NM_COMP_EXPERIENCE: {  // :473-479
             const double kk = home ? -k_home : -k_explo;
@@ -746,7 +760,7 @@ extern "C" int nm_simulate(const nm_maze *mz, const nm_sim_args *args, void *str
   NM_CHECK_ARG(count_max < 4294967295LL, "nm_simulate: seeded visits + n_steps overflow the 32-bit visit counters");
   bool small_counts = count_max < 65535 && !(env_cnt && env_cnt[0] == '3');
   size_t cnt_bytes = small_counts ? sizeof(uint16_t) : sizeof(uint32_t);
-  const size_t per_thread = (size_t)(1 + 2 * kA) + (size_t)(5 + kA) * sizeof(double);
+  const size_t per_thread = (size_t)(1 + 2 * kA) + (size_t)(5 + kBcwRows) * sizeof(double);
   auto smem_for = [&](int th) {
     return 128 + 16 * kA + per_thread * th + (size_t)nT * th * cnt_bytes + (size_t)nT * sizeof(double) + geo_bytes;
   };
@@ -799,7 +813,7 @@ extern "C" int nm_simulate_fits(int X, int Y, int n_steps) {
   if (X <= 0 || Y <= 0 || n_steps < 0) return 0;
   const size_t nT = (size_t)X * Y, th = 32;
   const size_t cnt_bytes = n_steps < 65535 ? sizeof(uint16_t) : sizeof(uint32_t);
-  const size_t per_thread = (size_t)(1 + 2 * kA) + (size_t)(5 + kA) * sizeof(double);
+  const size_t per_thread = (size_t)(1 + 2 * kA) + (size_t)(5 + kBcwRows) * sizeof(double);
   const size_t geo = NmSimGeom::smem_bytes(X, Y);
   if (128 + 16 * kA + th * per_thread + nT * th * cnt_bytes + nT * sizeof(double) + geo <= 227 * 1024) return 1;
   return 128 + 16 * kA + (size_t)kSimThreads * per_thread + geo <= 227 * 1024 ? 2 : 0;
