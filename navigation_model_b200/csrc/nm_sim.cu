@@ -119,7 +119,7 @@ struct Pcg64 {
 // map does not fit shared memory (beyond ~50 x 50 tiles) run the same step body -- same operations, same results -- with
 // only the tile / grid-line tables in shared memory (up to ~66 000 tiles).
 template <int NT, typename CntT, bool SEEDED, bool GMAP>
-__global__ void __launch_bounds__(NT, ((sizeof(CntT) == 2 ? NM_SIM_MIN_CTAS_U16 : NM_SIM_MIN_CTAS) * kSimThreads) / NT)
+__global__ void __launch_bounds__(NT, (((sizeof(CntT) == 2 || GMAP) ? NM_SIM_MIN_CTAS_U16 : NM_SIM_MIN_CTAS) * kSimThreads) / NT)
     nm_sim_kernel(const SimDev d) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nT = d.X * d.Y;
