@@ -28,6 +28,8 @@
 // numpy scalars: V-tables are bit-identical (rl.py:184-187, 227-230, 257-259).  (max / min are
 // compare-selects: like np.max they keep the first of equal values; NaN tables are out of contract.)
 
+#include <type_traits>
+
 constexpr int kChunk = 32;      // records per chunk = one per producer lane
 constexpr int kRawStages = 2;   // raw (TMA landing) ring
 #ifndef NM_FIT_DEC_STAGES
@@ -221,7 +223,10 @@ struct ExactAcc {
   ExpLL er;
 };
 
-template <int ALG, bool LL, int K, class Col>
+// SIGN: the caller has established (once, outside the step loop, for the whole warp) that beta has the sign for which
+// max_k fl(beta * V_k) == fl(beta * extremum_k V_k) -- non-negative for the max-backup learner, non-positive for the
+// min-backup one -- so the per-step test and its predicated twin disappear from the step body.
+template <int ALG, bool LL, int K, class Col, bool SIGN = false>
 __device__ __forceinline__ void exact_step_k(const uint4 q0, const uint4 q1, const uint4 q2, const uint4 q3, const Col vb,
                                              const double alpha, const double beta, const double gamma,
                                              ExactAcc &acc) {
@@ -240,7 +245,7 @@ __device__ __forceinline__ void exact_step_k(const uint4 q0, const uint4 q1, con
     // val_k = beta * V[cand_k] - max (exploration_model.py:87, 92) in one fused instruction per candidate; the maximum
     // itself is fl(beta * max V) for a non-negative beta (rounding is monotonic), else the largest rounded product
     double m;
-    if ((ALG == NM_ALG_POSITIVE && beta >= 0.0) || (ALG == NM_ALG_NEGATIVE && beta <= 0.0)) {
+    if (SIGN || (ALG == NM_ALG_POSITIVE && beta >= 0.0) || (ALG == NM_ALG_NEGATIVE && beta <= 0.0)) {
       m = __dmul_rn(beta, boot);
     } else {
       double z[NM_MAX_CAND];
@@ -262,7 +267,7 @@ __device__ __forceinline__ void exact_step_k(const uint4 q0, const uint4 q1, con
   vb.st(q0.z, __dadd_rn(vs, __dmul_rn(alpha, rpe)));                        // rl.py:186-187, 258-259
 }
 
-template <int ALG, bool LL, class Col>
+template <int ALG, bool LL, class Col, bool SIGN = false>
 __device__ __forceinline__ void exact_step(const uint4 *__restrict__ rec, const Col vb, const double alpha,
                                            const double beta, const double gamma, ExactAcc &acc) {
   const uint4 q0 = rec[0], q1 = rec[1], q2 = rec[2], q3 = rec[3];
@@ -270,7 +275,7 @@ __device__ __forceinline__ void exact_step(const uint4 *__restrict__ rec, const 
     exact_step_k<NM_ALG_TD0, false, 0, Col>(q0, q1, q2, q3, vb, alpha, beta, gamma, acc);
   } else {
 #define NM_CASE(KK) \
-  case KK: exact_step_k<ALG, LL, KK, Col>(q0, q1, q2, q3, vb, alpha, beta, gamma, acc); break;
+  case KK: exact_step_k<ALG, LL, KK, Col, SIGN>(q0, q1, q2, q3, vb, alpha, beta, gamma, acc); break;
     switch (q1.x & 0xffu) {  // K, warp-uniform
       NM_CASE(1) NM_CASE(2) NM_CASE(3) NM_CASE(4) NM_CASE(5) NM_CASE(6) NM_CASE(7) NM_CASE(8)
       default:  // K == 0 only occurs in TD0 streams built without candidates (validated on the host)
@@ -437,20 +442,29 @@ __global__ void __launch_bounds__(960, 1) nm_fit_group_kernel(const FitArgs a) {
     acc.acc_obs = 0.0;
     acc.prod = 1.0;
     acc.er.load(smem_raw + kBarBytes + kRawBytes + kDecBytes);
-    for (int c = 0; c < nchunks; ++c) {
-      const int dslot = c % kDecStages;
-      mbar_wait(&rg.full_dec[dslot], (uint32_t)((c / kDecStages) & 1));
-      const uint4 *recs = rg.dec + dslot * (kChunk * 4);
-      const int64_t first = (int64_t)c * kChunk;
-      const int cnt = (int)(n - first < kChunk ? n - first : kChunk);
+    // does every lane's beta have the sign that lets the softmax maximum be fl(beta * extremum V)?  (warp-uniform answer,
+    // taken once: the step body is compiled twice)
+    const bool sign_ok = ALG != NM_ALG_TD0 &&
+                         __all_sync(0xffffffffu, ALG == NM_ALG_POSITIVE ? beta >= 0.0 : beta <= 0.0);
+    auto sweep_chunks = [&](auto sign_tag) {
+      constexpr bool SIGN = decltype(sign_tag)::value;
+      for (int c = 0; c < nchunks; ++c) {
+        const int dslot = c % kDecStages;
+        mbar_wait(&rg.full_dec[dslot], (uint32_t)((c / kDecStages) & 1));
+        const uint4 *recs = rg.dec + dslot * (kChunk * 4);
+        const int64_t first = (int64_t)c * kChunk;
+        const int cnt = (int)(n - first < kChunk ? n - first : kChunk);
 #pragma unroll 1
-      for (int i = 0; i < cnt; ++i) exact_step<ALG, true>(recs + 4 * i, vb, alpha, beta, gamma, acc);
-      ll = __dadd_rn(ll, __dsub_rn(acc.acc_obs, log_chunk_product(acc.prod)));  // fold the chunk exactly like the exact kernel
-      acc.acc_obs = 0.0;
-      acc.prod = 1.0;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&rg.empty_dec[dslot]);
-    }
+        for (int i = 0; i < cnt; ++i) exact_step<ALG, true, SharedCol, SIGN>(recs + 4 * i, vb, alpha, beta, gamma, acc);
+        ll = __dadd_rn(ll, __dsub_rn(acc.acc_obs, log_chunk_product(acc.prod)));  // fold the chunk exactly like the exact kernel
+        acc.acc_obs = 0.0;
+        acc.prod = 1.0;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&rg.empty_dec[dslot]);
+      }
+    };
+    if (sign_ok) sweep_chunks(std::true_type{});
+    else sweep_chunks(std::false_type{});
     if (p < a.P && a.ll_out) a.ll_out[(int64_t)sess * a.P + p] = ll;
   }
   if (a.v_out) {  // every parameter set of a run receives the run's table
