@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdlib>
+#include <type_traits>
 
 #include "nm_common.h"
 #include "nm_libm.h"
@@ -57,13 +58,18 @@ struct SimDev {
   uint32_t zero_mask;    // bit i = zero_act[i]
   uint32_t comp_word;    // 4 bits per ACTIVE component, in model order: its NM_COMP_* kind (0 terminates the list)
   uint8_t null_act[kA];  // exactly (0, 0): the endpoint is the position itself
+  uint32_t null_mask;    // bit i = null_act[i]
   uint8_t walk_ord[kA];  // ordinal of action i among the actions that need a ray walk
   uint32_t walk_list;    // 4 bits per entry: walk_list >> 4j & 7 = j-th action that needs a ray walk
   int n_walk;            // number of those
   const uint8_t *subareas;                 // [X*Y] or NULL
   double ori_edges[NM_MAX_ORI_BINS + 1];   // numpy.histogram edges of the turn histogram
   int64_t scratch_columns;                 // GMAP: columns (= launched threads) of the device-memory visit map
+  int n_visit_thr;                         // smallest number of visited tiles that reaches a.visit_percentage (metrics.py:711-721)
 };
+
+constexpr uint32_t kStdWord = NM_COMP_ANXIETY | (NM_COMP_BCOST << 4) | (NM_COMP_EXPERIENCE << 8) |
+                              (NM_COMP_BPERSISTENCE << 12) | (NM_COMP_VTABLE << 16);
 
 // cos / sin / atan2 of the pose chain: nm_host_sincos / nm_host_atan2 (nm_libm.h) give the HOST library's results, so
 // that a simulated trajectory equals the reference's to the last bit (mouse.cpp:66, 78 call std::cos / sin / atan2).
@@ -118,7 +124,10 @@ struct Pcg64 {
 // touch 32 consecutive words of a row) and the shared normalised value table is read from device memory too: mazes whose
 // map does not fit shared memory (beyond ~50 x 50 tiles) run the same step body -- same operations, same results -- with
 // only the tile / grid-line tables in shared memory (up to ~66 000 tiles).
-template <int NT, typename CntT, bool SEEDED, bool GMAP>
+// CW = the model's component word when it is known at compile time (kStdWord: the reference's standard model --
+// anxiety, biomechanical cost, experience, biomechanical persistence, value table, in that order): the five component
+// bodies follow one another in a straight line, no per-component dispatch.  0 = any component list (run-time loop).
+template <int NT, typename CntT, bool SEEDED, bool GMAP, uint32_t CW = 0u>
 __global__ void __launch_bounds__(NT, (((sizeof(CntT) == 2 || GMAP) ? NM_SIM_MIN_CTAS_U16 : NM_SIM_MIN_CTAS) * kSimThreads) / NT)
     nm_sim_kernel(const SimDev d) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -186,6 +195,7 @@ __global__ void __launch_bounds__(NT, (((sizeof(CntT) == 2 || GMAP) ? NM_SIM_MIN
   const int A = a.n_actions;
   const int T = a.n_steps;
   const uint32_t zero_mask = nm_pin_u32(d.zero_mask), comp_word = nm_pin_u32(d.comp_word);
+  const uint32_t null_mask = d.null_mask;  // bit i = action i is exactly (0, 0)
 
   int status = 0;
   ExpRegs er;
@@ -249,6 +259,7 @@ __global__ void __launch_bounds__(NT, (((sizeof(CntT) == 2 || GMAP) ? NM_SIM_MIN
       vt_w = a.d_vtable_weight[n];
       vt = a.vtable_per_mouse ? a.d_vtable + n * nT : (GMAP ? a.d_vtable : vt_sm);
     }
+    const uint32_t a_vt = nm_pin_u32((uint32_t)__cvta_generic_to_shared(vt_sm));  // the shared normalised value table
     Pcg64 rng;
     rng.state = 0;
     rng.inc = 0;
@@ -320,8 +331,9 @@ __global__ void __launch_bounds__(NT, (((sizeof(CntT) == 2 || GMAP) ? NM_SIM_MIN
       if (c == 0u) {
         n_visited += 1;
         // perc = n_visited * 100 / number_visitable_tiles >= percentage      metrics.py:711-721
-        if (it_visit == T + 1 && (double)(n_visited * 100) / (double)d.n_visitable >= a.visit_percentage)
-          it_visit = t_idx;
+        // (the quotient is monotone in n_visited: the host evaluates it once per count and passes the first count that
+        //  reaches the percentage, nm_simulate)
+        if (it_visit == T + 1 && n_visited >= d.n_visit_thr) it_visit = t_idx;
       }
     };
     bool cur_inside = cur_tx >= 0 && cur_tx < d.X && cur_ty >= 0 && cur_ty < d.Y;
@@ -366,12 +378,11 @@ __global__ void __launch_bounds__(NT, (((sizeof(CntT) == 2 || GMAP) ? NM_SIM_MIN
         const int cur_tile = cur_inside ? cur_tx * d.Y + cur_ty : 0;
         if (need) {
           nm_host_sincos(ori, &s, &c);
-#pragma unroll
-          for (int i = 0; i < kA; ++i)
-            if (i < A && d.null_act[i])
-              // null displacement: the endpoint IS the position, R(ori)*0 + p == p bit for bit, and no grid line is
-              // crossed -- reachable iff the tile under the mouse is visitable
-              res_w[lane * kA + i] = (uint16_t)(cur_tile | (start_ok ? 0x8000 : 0));
+          // null displacement: the endpoint IS the position, R(ori)*0 + p == p bit for bit, and no grid line is
+          // crossed -- reachable iff the tile under the mouse is visitable
+#pragma unroll 1
+          for (uint32_t m = null_mask; m != 0u; m &= m - 1u)
+            res_w[lane * kA + (__ffs((int)m) - 1)] = (uint16_t)(cur_tile | (start_ok ? 0x8000 : 0));
         }
         const int nd = __popc(dmask);
         if (n_walk > 0) {
@@ -417,7 +428,7 @@ __global__ void __launch_bounds__(NT, (((sizeof(CntT) == 2 || GMAP) ? NM_SIM_MIN
         continue;
       }
       int act_idx = -1;
-      if (a.model_kind == 0) {  // ---------------- BehaviouralModel -----------------------------------------
+      if (CW != 0u || a.model_kind == 0) {  // ---------------- BehaviouralModel -----------------------------------------
       // -- component updates                                                 exploration_model.py:79-81
       if (a.d_experience) {  // :456-466 (count of the current tile was just incremented above)
         const double nvis = cur_inside ? (double)cnt_ld(cur_tx * d.Y + cur_ty) : 0.0;
@@ -436,96 +447,120 @@ __global__ void __launch_bounds__(NT, (((sizeof(CntT) == 2 || GMAP) ? NM_SIM_MIN
       double val[kA];
 #pragma unroll
       for (int i = 0; i < kA; ++i) val[i] = 0.0;
-#pragma unroll 1
-      // the active components' kinds travel in ONE register word (an inactive component contributes integer 0,
-      // :283-285, and is left out on the host): no per-step loads from the launch-parameter arrays
-      for (uint32_t cw = comp_word; cw != 0u; cw >>= 4) {
-        switch (cw & 15u) {
-          case NM_COMP_ANXIETY:
+      // one component's weighted values added to the running sums; KIND is a compile-time constant
+      auto component = [&](auto kind_tag) {
+        constexpr int KIND = decltype(kind_tag)::value;
+        if constexpr (KIND == NM_COMP_ANXIETY) {
 #pragma unroll
-            for (int i = 0; i < kA; ++i) {
-              const int code = (int)geo.tile_code(etile[i]);
-              val[i] = val[i] + nm_lds_f64(a_thr + (uint32_t)(code > 4 ? 0 : code) * kRow);
-            }
-            break;
-          case NM_COMP_BCOST:  // cached[is_visitable] if moving else zeros   :410-413
-#pragma unroll
-            for (int i = 0; i < kA; ++i)
-#if NM_SIM_BCW_GLOBAL
-              val[i] = val[i] + (moving ? __ldg(bc_row + (i < A ? i : A - 1)) * bc_w : bc_zero);
-#else
-              val[i] = val[i] + (moving ? nm_lds_f64(a_thr + (5u + (uint32_t)i) * kRow) : bc_zero);
-#endif
-            break;
-          case NM_COMP_EXPERIENCE: {  // :473-479
-            const double kk = home ? -k_home : -k_explo;
-#pragma unroll
-            for (int i = 0; i < kA; ++i) {
-              // (double)count by the 2^52 trick: exact for a u32, and no I2F on the quarter-rate pipe
-              const double cn = __hiloint2double(0x43300000, (int)cnt_ld(etile[i])) - 4503599627370496.0;
-              const double ee = er.exp_nonpos(kk * cn);
-              val[i] = val[i] + (home ? 1.0 - ee : ee) * ex_w;
-            }
-            break;
+          for (int i = 0; i < kA; ++i) {
+            const int code = (int)geo.tile_code(etile[i]);
+            val[i] = val[i] + nm_lds_f64(a_thr + (uint32_t)(code > 4 ? 0 : code) * kRow);
           }
-          case NM_COMP_BPERSISTENCE:  // :508-513
+        } else if constexpr (KIND == NM_COMP_BCOST) {  // cached[is_visitable] if moving else zeros   :410-413
 #pragma unroll
-            for (int i = 0; i < kA; ++i)
-              val[i] = val[i] + (moving ? ((zero_mask >> i) & 1u ? bpw_m : bpw_plain) : ((zero_mask >> i) & 1u ? bpw_plain : bpw_nm));
-            break;
-          case NM_COMP_VTABLE:  // :537-541
+          for (int i = 0; i < kA; ++i)
+#if NM_SIM_BCW_GLOBAL
+            val[i] = val[i] + (moving ? __ldg(bc_row + (i < A ? i : A - 1)) * bc_w : bc_zero);
+#else
+            val[i] = val[i] + (moving ? nm_lds_f64(a_thr + (5u + (uint32_t)i) * kRow) : bc_zero);
+#endif
+        } else if constexpr (KIND == NM_COMP_EXPERIENCE) {  // :473-479
+          // home: (1 - e) * W, else e * W -- fma(sg, e, one) is fl(1 - e) resp. e itself (0 + e), one instruction
+          const double kk = home ? -k_home : -k_explo, sg = home ? -1.0 : 1.0, one = home ? 1.0 : 0.0;
 #pragma unroll
-            for (int i = 0; i < kA; ++i)
-              val[i] = val[i] + vt[etile[i]] * vt_w;
-            break;
-          default:
-            break;
+          for (int i = 0; i < kA; ++i) {
+            // (double)count by the 2^52 trick: exact for a u32, and no I2F on the quarter-rate pipe
+            const double cn = __hiloint2double(0x43300000, (int)cnt_ld(etile[i])) - 4503599627370496.0;
+            const double ee = er.exp_nonpos(kk * cn);
+            val[i] = val[i] + fma(sg, ee, one) * ex_w;
+          }
+        } else if constexpr (KIND == NM_COMP_BPERSISTENCE) {  // :508-513
+          const double vz = moving ? bpw_m : bpw_plain, vn = moving ? bpw_plain : bpw_nm;
+#pragma unroll
+          for (int i = 0; i < kA; ++i) val[i] = val[i] + ((zero_mask >> i) & 1u ? vz : vn);
+        } else if constexpr (KIND == NM_COMP_VTABLE) {  // :537-541
+          if (!GMAP && !a.vtable_per_mouse) {  // the shared table: pinned shared-window address
+#pragma unroll
+            for (int i = 0; i < kA; ++i) val[i] = val[i] + nm_lds_f64(a_vt + 8u * (uint32_t)etile[i]) * vt_w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < kA; ++i) val[i] = val[i] + vt[etile[i]] * vt_w;
+          }
+        }
+      };
+      if constexpr (CW != 0u) {  // the component list is known: straight line
+        if constexpr (((CW >> 0) & 15u) != 0u) component(std::integral_constant<int, (int)((CW >> 0) & 15u)>{});
+        if constexpr (((CW >> 4) & 15u) != 0u) component(std::integral_constant<int, (int)((CW >> 4) & 15u)>{});
+        if constexpr (((CW >> 8) & 15u) != 0u) component(std::integral_constant<int, (int)((CW >> 8) & 15u)>{});
+        if constexpr (((CW >> 12) & 15u) != 0u) component(std::integral_constant<int, (int)((CW >> 12) & 15u)>{});
+        if constexpr (((CW >> 16) & 15u) != 0u) component(std::integral_constant<int, (int)((CW >> 16) & 15u)>{});
+      } else {
+#pragma unroll 1
+        // the active components' kinds travel in ONE register word (an inactive component contributes integer 0,
+        // :283-285, and is left out on the host): no per-step loads from the launch-parameter arrays
+        for (uint32_t cw = comp_word; cw != 0u; cw >>= 4) {
+          switch (cw & 15u) {
+            case NM_COMP_ANXIETY: component(std::integral_constant<int, NM_COMP_ANXIETY>{}); break;
+            case NM_COMP_BCOST: component(std::integral_constant<int, NM_COMP_BCOST>{}); break;
+            case NM_COMP_EXPERIENCE: component(std::integral_constant<int, NM_COMP_EXPERIENCE>{}); break;
+            case NM_COMP_BPERSISTENCE: component(std::integral_constant<int, NM_COMP_BPERSISTENCE>{}); break;
+            case NM_COMP_VTABLE: component(std::integral_constant<int, NM_COMP_VTABLE>{}); break;
+            default: break;
+          }
         }
       }
-      double vmax = -INFINITY;
+      // -- val_fin = beta * val; the unreachable slots are parked at -inf, so that the maximum over the candidates is a
+      // plain tree of compare-selects over all eight (NaN is out of contract; which of two equal values wins changes
+      // nothing below)
+      double vmax;
+      {
 #pragma unroll
-      for (int i = 0; i < kA; ++i) {
-        val[i] = beta * val[i];
-        if (vis & (1u << i)) vmax = fmax(vmax, val[i]);
+        for (int i = 0; i < kA; ++i) {
+          const double b = beta * val[i];
+          val[i] = (vis & (1u << i)) != 0u ? b : -INFINITY;
+        }
+        const double m01 = val[0] > val[1] ? val[0] : val[1], m23 = val[2] > val[3] ? val[2] : val[3];
+        const double m45 = val[4] > val[5] ? val[4] : val[5], m67 = val[6] > val[7] ? val[6] : val[7];
+        const double m03 = m01 > m23 ? m01 : m23, m47 = m45 > m67 ? m45 : m67;
+        vmax = m03 > m47 ? m03 : m47;
       }
       // -- softmax + numpy Generator.choice                                   :92-98
+      // every slot is evaluated (an unreachable one on -inf: whatever comes out is discarded) and the unreachable ones
+      // are set to 0 afterwards: adding +0.0 changes no partial sum, so the sums below run over all eight slots without
+      // a test and give the bits of the sums over the candidates
       double e[kA];
 #pragma unroll
-      for (int i = 0; i < kA; ++i) e[i] = (vis & (1u << i)) ? er.exp_nonpos(val[i] - vmax) : 0.0;
-      double sum;
-      if (K == kA) {
-        sum = ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));  // numpy pairwise, n == 8
-      } else {
-        sum = 0.0;  // n < 8: sequential from 0.0 over the candidates
-#pragma unroll
-        for (int i = 0; i < kA; ++i)
-          if (vis & (1u << i)) sum = sum + e[i];
+      for (int i = 0; i < kA; ++i) {
+        const double ex = er.exp_nonpos(val[i] - vmax);
+        e[i] = (vis & (1u << i)) != 0u ? ex : 0.0;
       }
+      // numpy's sum: pairwise for n == 8, sequential from the first candidate for n < 8
+      const double sum_pw = ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+      double sum_sq = e[0];
+#pragma unroll
+      for (int i = 1; i < kA; ++i) sum_sq = sum_sq + e[i];
+      const double sum = K == kA ? sum_pw : sum_sq;
       // p = e / sum, cdf = cumsum(p), choice = first k with cdf_k / cdf_last > u.  The 2 K divisions are replaced by
       // one reciprocal and K + 1 multiplications (p = e * (1/sum); cdf_k > u * cdf_last): like the device exp, this
       // moves p by <= 1 ulp against numpy, which can only change a choice when u falls within ~1e-16 of a cdf step.
-      double cdf[kA];
-      double run = 0.0;
-      bool first = true;
-      int last_vis = 0;
+      // The cdf is non-decreasing and flat across unreachable slots, so the first candidate whose cdf exceeds the
+      // threshold is the NUMBER of slots at or below it (searchsorted, side='right').
       const double inv_sum = 1.0 / sum;
+      double cdf[kA];
+      double run = e[0] * inv_sum;
+      cdf[0] = run;
 #pragma unroll
-      for (int i = 0; i < kA; ++i) {
-        if (vis & (1u << i)) {
-          const double p = e[i] * inv_sum;
-          run = first ? p : run + p;  // cumsum
-          first = false;
-          last_vis = i;
-        }
+      for (int i = 1; i < kA; ++i) {
+        run = run + e[i] * inv_sum;  // cumsum
         cdf[i] = run;
       }
       const double u = a.d_draws ? a.d_draws[(int64_t)t * N + n] : rng.next_double();
       const double thr = u * run;  // u * cdf[-1]
-      // searchsorted(cdf / cdf[-1], u, side='right'): the first candidate whose normalised cdf exceeds u
+      int below = 0;
 #pragma unroll
-      for (int i = 0; i < kA; ++i)
-        if (act_idx < 0 && (vis & (1u << i)) && !(cdf[i] <= thr)) act_idx = i;
-      if (act_idx < 0) act_idx = last_vis;  // cannot happen for u < 1 and finite probabilities
+      for (int i = 0; i < kA; ++i) below += (cdf[i] <= thr) ? 1 : 0;
+      const int last_vis = 31 - __clz((int)vis);
+      act_idx = below < last_vis ? below : last_vis;  // beyond the last candidate: cannot happen for u < 1
       } else {  // ---------------- RandomModel: rng.choice(next_positions_cont)   exploration_model.py:141 ----
         uint32_t pick;
         if (a.d_draws) {  // replayed uniforms: floor(u * K) (convenience mode, not numpy's draw)
@@ -739,10 +774,20 @@ extern "C" int nm_simulate(const nm_maze *mz, const nm_sim_args *args, void *str
     d.zero_act[i] = (i < a.n_actions && a.h_zero_action) ? a.h_zero_action[i] : 0;
     if (d.zero_act[i]) d.zero_mask |= 1u << i;
   }
+  // it_perc_visited_maze (metrics.py:711-721): first count of visited tiles whose percentage reaches the bar -- the
+  // same two conversions and division the kernel would do at every first visit, once per possible count here
+  d.n_visit_thr = 2147483647;
+  for (int nv = 1; nv <= mz->X * mz->Y + 1; ++nv)
+    if ((double)(nv * 100) / (double)d.n_visitable >= a.visit_percentage) {
+      d.n_visit_thr = nv;
+      break;
+    }
   d.n_walk = 0;
   d.walk_list = 0u;
+  d.null_mask = 0u;
   for (int i = 0; i < kA; ++i) {
     d.null_act[i] = (i < a.n_actions && d.act[i][0] == 0.0 && d.act[i][1] == 0.0) ? 1 : 0;
+    if (d.null_act[i]) d.null_mask |= 1u << i;
     d.walk_ord[i] = (uint8_t)d.n_walk;
     if (i < a.n_actions && !d.null_act[i]) {
       d.walk_list |= (uint32_t)i << (4 * d.n_walk);
@@ -798,6 +843,10 @@ extern "C" int nm_simulate(const nm_maze *mz, const nm_sim_args *args, void *str
   else
     kern = seeded ? NM_SIM_PICK(uint32_t, true) : NM_SIM_PICK(uint32_t, false);
 #undef NM_SIM_PICK
+  // the reference's standard five-component model on the common launch shape: the specialised step body
+  if (d.comp_word == kStdWord && a.model_kind == 0 && !gmap && !seeded && threads == 128)
+    kern = small_counts ? nm_sim_kernel<128, uint16_t, false, false, kStdWord>
+                        : nm_sim_kernel<128, uint32_t, false, false, kStdWord>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   kern<<<(unsigned)blocks, threads, smem, (cudaStream_t)stream>>>(d);
