@@ -148,6 +148,56 @@ struct ExpLL {
   }
 };
 
+// ---- exponentials of the SIMULATION kernel (component values and the softmax of a decision) ------------------------------
+// exp(x), x <= 0, to ~1 ulp: x = (64 e + j) * ln2/64 + r, |r| <= ln2/128, two-step Cody-Waite reduction (exact products:
+// the high part of ln2/64 has 32 trailing zero bits), the 64-entry table of ExpLL, and
+//     exp(r) - 1 = q = r + r^2 * (1/2 + r/6 + r^2/24 + r^3/120)      (truncation r^6/720 <= 3.5e-17)
+//     result     = fma(s, q, s),  s = 2^(j/64)                        (ONE rounding after the table value's own)
+// 10 FP64 instructions (round 1's 16-entry / degree-7 form: 12) and a shorter dependent chain (r^2 beside the Horner steps).
+// Measured on the host against the long-double exponential over [-700, 0] (2e7 arguments): max 1.27 ulp, 99.86 % within
+// 1 ulp, 81 % correctly rounded -- the 16-entry form: max 1.96 ulp, 96 % within 1 ulp, 75 % correctly rounded.  Seven
+// constants pinned in registers (0.5 is an immediate); the binary exponent is clamped like ExpLL's.
+__constant__ double c_expsim_k[7] = {9.23324826168936567683e+01,           // 64 * log2(e)
+                                     6755399441055744.0,                  // 1.5 * 2^52
+                                     -6.93147180369123816490e-01 / 64.0,  // -ln2/64 (high part, exact scaling)
+                                     -1.90821492927058770002e-10 / 64.0,  // -ln2/64 (low part)
+                                     1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0};
+
+struct ExpSim {
+  double c[7];
+  uint32_t tab;  // shared-window address of 64 doubles holding c_exp2tab64, 512-BYTE ALIGNED (the entry index is OR-ed in)
+  static constexpr int kRegionBytes = 1024;  // the table sits at the first 512-byte boundary inside the region
+  // every thread of the CTA calls fill() BEFORE the __syncthreads() that precedes the first use (any CTA size)
+  static __device__ __forceinline__ void fill(unsigned char *region, int tid) {
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(region);
+    double *t = reinterpret_cast<double *>(region + (((base + 511u) & ~511u) - base));
+    for (int i = tid; i < 64; i += (int)blockDim.x) t[i] = c_exp2tab64[i];
+  }
+  __device__ __forceinline__ void load(unsigned char *region) {
+#pragma unroll
+    for (int i = 0; i < 7; ++i) asm volatile("mov.f64 %0, %1;" : "=d"(c[i]) : "d"(c_expsim_k[i]));
+    tab = ((uint32_t)__cvta_generic_to_shared(region) + 511u) & ~511u;
+    asm volatile("mov.u32 %0, %0;" : "+r"(tab));  // pinned: not recomputed per use under register pressure
+  }
+  __device__ __forceinline__ double exp_nonpos(double x) const {
+    const double t = fma(x, c[0], c[1]);
+    const uint32_t k8 = (uint32_t)max(__double2loint(t), -1021 * 64) << 3;  // 8 * round(64 x / ln2), clamped
+    const double n = __dsub_rn(t, c[1]);
+    double r = fma(n, c[2], x);
+    r = fma(n, c[3], r);
+    double s;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(s) : "r"(tab | (k8 & 0x1f8u)));
+    double p = fma(c[4], r, c[5]);
+    p = fma(p, r, c[6]);
+    p = fma(p, r, 0.5);
+    const double q = fma(p, __dmul_rn(r, r), r);
+    const double v = fma(s, q, s);
+    int hi;  // hi += (k >> 6) << 20 = (k8 & ~0x1ff) * 2048
+    asm("{\n.reg .b32 t;\nand.b32 t, %1, 0xfffffe00;\nmad.lo.s32 %0, t, 2048, %2;\n}" : "=r"(hi) : "r"(k8), "r"(__double2hiint(v)));
+    return __hiloint2double(hi, __double2loint(v));
+  }
+};
+
 // log(x) for the per-chunk fold of the likelihood kernels: x = product of 32 softmax denominators, in [1, 2^96] (normal,
 // positive -- no special cases).  x = 2^e * m, m in [sqrt(1/2), sqrt(2)):  log x = e * ln2 + 2 atanh(s), s = (m-1)/(m+1),
 // |s| <= 0.1716: odd series to s^19 (next term 2 s^21 / 21 < 8e-18).  ~30 instructions against ~200 of the library log

@@ -41,6 +41,7 @@ constexpr int kSimThreads = 128;
                              // buy a 7th resident CTA per SM (measured: 144.7 ms against 154.3 ms per 1M x 1000 steps)
 #endif
 constexpr int kBcwRows = NM_SIM_BCW_GLOBAL ? 0 : kA;
+constexpr size_t kSimFixedBytes = ExpSim::kRegionBytes + 16 * kA;  // exponential table region + relative actions
 #ifndef NM_SIM_MIN_CTAS
 #define NM_SIM_MIN_CTAS 4  // resident CTAs per SM the register allocation is capped for (32-bit visit counters)
 #endif
@@ -115,6 +116,20 @@ struct Pcg64 {
   }
 };
 
+// the per-mouse booleans of the step loop, one bit each of one register word
+struct Bits {
+  uint32_t w;
+  template <int B>
+  __device__ __forceinline__ bool get() const {
+    return (w & (1u << B)) != 0u;
+  }
+  template <int B>
+  __device__ __forceinline__ void set(bool v) {
+    w = v ? (w | (1u << B)) : (w & ~(1u << B));
+  }
+};
+enum { F_ACTIVE, F_DIRTY, F_MOVING, F_HOME, F_INSIDE, F_INZONE, F_PREVMOVED, F_LIVE };
+
 // NT = threads per CTA (compile-time: every per-mouse table is indexed [row][thread], so row strides and the
 // fixed-size tables' offsets become immediates).
 // CntT = type of a visit counter: u16 when n_steps + 1 < 65536 (half the shared memory: one more resident CTA), else u32.
@@ -134,19 +149,18 @@ __global__ void __launch_bounds__(NT, (((sizeof(CntT) == 2 || GMAP) ? NM_SIM_MIN
   const int nT = d.X * d.Y;
   constexpr int nt = NT;
   const int tid = threadIdx.x;
-  // 2^(j/16) | anxiety value*weight by tile code [5][nt] | biomechanical cost*weight by action [kA][nt] |
+  // 2^(j/64) (1 KB region) | actions | rank / mailbox scratch | anxiety value*weight by tile code [5][nt] | biomechanical cost*weight by action [kA][nt] |
   // visit map [nT][nt] u32 | shared normalised value table [nT] | geometry tables
-  double *exp_tab = reinterpret_cast<double *>(smem_raw);
-  double *act_sm = exp_tab + 16;                                        // [kA][2] relative actions
+  double *act_sm = reinterpret_cast<double *>(smem_raw + ExpSim::kRegionBytes);  // [kA][2] relative actions
   uint8_t *rank_sm = reinterpret_cast<uint8_t *>(act_sm + 2 * kA);      // [warps][32] rank -> lane of the dirty mice
   uint16_t *res_sm = reinterpret_cast<uint16_t *>(rank_sm + nt);        // [thread][kA] walk results: tile | ok << 15
-  double *anx_sm = exp_tab + 16 + 2 * kA + (nt / 32) * 4 + 2 * nt;
+  double *anx_sm = act_sm + 2 * kA + (nt / 32) * 4 + 2 * nt;
   double *bcw_sm = anx_sm + 5 * nt;
   // visit map: count[tile * cs + column]; shared memory (cs = nt, column = tid) or device memory (GMAP)
   CntT *count = GMAP ? reinterpret_cast<CntT *>(d.a.d_visit_scratch) : reinterpret_cast<CntT *>(bcw_sm + kBcwRows * nt);
   const size_t cs = GMAP ? (size_t)d.scratch_columns : (size_t)nt;
   double *vt_sm = GMAP ? bcw_sm + kBcwRows * nt : reinterpret_cast<double *>(count + (size_t)nT * nt);
-  if (tid < 16) exp_tab[tid] = c_exp2tab[tid];
+  ExpSim::fill(smem_raw, tid);
   if (tid < 2 * kA) act_sm[tid] = d.act[tid >> 1][tid & 1];
   NmSimGeom geo;  // tile table, grid-line tables (nm_simgeom.cuh)
   geo.build(reinterpret_cast<unsigned char *>(GMAP ? vt_sm : vt_sm + nT), d.tiles, d.X, d.Y, d.st);
@@ -198,13 +212,18 @@ __global__ void __launch_bounds__(NT, (((sizeof(CntT) == 2 || GMAP) ? NM_SIM_MIN
   const uint32_t null_mask = d.null_mask;  // bit i = action i is exactly (0, 0)
 
   int status = 0;
-  ExpRegs er;
-  er.load(smem_u32(exp_tab));
+  ExpSim er;
+  er.load(smem_raw);
   {
     // ---- per-mouse state -------------------------------------------------------------------------
     double px = a.d_init_pose[3 * n], py = a.d_init_pose[3 * n + 1], ori = a.d_init_pose[3 * n + 2];
     double prevx = a.d_init_prev[2 * n], prevy = a.d_init_prev[2 * n + 1];
-    bool moving = false;  // BehaviouralModel._moving (True when the last choice was to STAY)
+    // the per-mouse booleans travel in ONE register word (as separate bools they were spilled to local memory byte by
+    // byte and every test waited for a reload)
+    Bits fl;
+    fl.w = 0u;
+    fl.set<F_LIVE>(live);
+    fl.set<F_MOVING>(false);  // BehaviouralModel._moving (True when the last choice was to STAY)
     const double beta = a.d_beta[n];
     // value * weight is the same product at every step (Component.weighted_values, behavioural_components.py:277-285):
     // it is formed once here and looked up afterwards.
@@ -234,16 +253,16 @@ __global__ void __launch_bounds__(NT, (((sizeof(CntT) == 2 || GMAP) ? NM_SIM_MIN
 #endif
     }
     double ex_w = 0, xi = 0, k_home = 0, k_explo = 0, th_explo = 0, th_home = 0, fam = 0.0;
-    bool home = false;  // ExperienceComponent.State.EXPLO at start (:440)
+    // F_HOME clear: ExperienceComponent.State.EXPLO at start (:440)
     if (a.d_experience) {
       const double *q = a.d_experience + 6 * n;
       ex_w = q[0]; xi = q[1]; k_home = q[2]; k_explo = q[3]; th_explo = q[4]; th_home = q[5];
     }
     if (SEEDED && a.d_init_model_state) {  // the model and the component carry on where an earlier run left them
       const double *q = a.d_init_model_state + 3 * n;
-      moving = q[0] != 0.0;
+      fl.set<F_MOVING>(q[0] != 0.0);
       fam = q[1];
-      home = q[2] != 0.0;
+      fl.set<F_HOME>(q[2] != 0.0);
     }
     a_thr = nm_pin_u32(a_thr);  // re-pinned after the stores above: the step loop's (plain) loads cannot move above them
     double bpw_plain = 0, bpw_m = 0, bpw_nm = 0;  // bp * W, (Wm*bp) * W, (Wnm*bp) * W   (:502-513)
@@ -300,7 +319,7 @@ __global__ void __launch_bounds__(NT, (((sizeof(CntT) == 2 || GMAP) ? NM_SIM_MIN
     // not-moving runs (hist_time_moving -> compute_static_intervals, :445-467, 621-635): moving_bool_list[0] is False,
     // so the history opens with a not-moving run
     int zone_latency = T, zone_entries = 0, corridor_switches = 0, corridor_side = 0, static_runs = 1;
-    bool in_zone = false, prev_moved = false;
+
     int ohist[NM_MAX_ORI_BINS + 1];
 #pragma unroll
     for (int i = 0; i <= NM_MAX_ORI_BINS; ++i) ohist[i] = 0;
@@ -313,12 +332,12 @@ __global__ void __launch_bounds__(NT, (((sizeof(CntT) == 2 || GMAP) ? NM_SIM_MIN
         const unsigned f = a.d_tile_flags[tile];
         if (f & NM_TILE_ZONE_IN) {
           if (zone_latency == T && t_idx < T) zone_latency = t_idx;  // "never" and "at the last position" are both T
-          if (!in_zone) {
+          if (!fl.get<F_INZONE>()) {
             zone_entries += 1;
-            in_zone = true;
+            fl.set<F_INZONE>(true);
           }
-        } else if ((f & NM_TILE_ZONE_OUT) && in_zone) {
-          in_zone = false;
+        } else if ((f & NM_TILE_ZONE_OUT) && fl.get<F_INZONE>()) {
+          fl.set<F_INZONE>(false);
         }
         const int side = (int)((f >> 2) & 3u);
         if (side) {
@@ -336,7 +355,7 @@ __global__ void __launch_bounds__(NT, (((sizeof(CntT) == 2 || GMAP) ? NM_SIM_MIN
         if (it_visit == T + 1 && n_visited >= d.n_visit_thr) it_visit = t_idx;
       }
     };
-    bool cur_inside = cur_tx >= 0 && cur_tx < d.X && cur_ty >= 0 && cur_ty < d.Y;
+    fl.set<F_INSIDE>(cur_tx >= 0 && cur_tx < d.X && cur_ty >= 0 && cur_ty < d.Y);
     // NOTE: the ExperienceComponent increments count[x, y] of the CURRENT tile at every decision
     // (:456) -- that is exactly "occupancy over history[0..t]", so history entry t is recorded at the
     // top of step t and the final entry after the loop.
@@ -356,7 +375,8 @@ __global__ void __launch_bounds__(NT, (((sizeof(CntT) == 2 || GMAP) ? NM_SIM_MIN
     uint16_t *res_w = res_sm + (tid >> 5) * (32 * kA);  // the warp's mailbox: [lane][action]
     const int n_walk = d.n_walk;
     const unsigned div_walk = n_walk > 0 ? (65536u + (unsigned)n_walk - 1u) / (unsigned)n_walk : 0u;  // item / n_walk
-    bool active = true, dirty = true;
+    fl.set<F_ACTIVE>(true);
+    fl.set<F_DIRTY>(true);
     unsigned vis = 0u;
     uint4 et = make_uint4(0u, 0u, 0u, 0u);  // eight 16-bit entries: tile under endpoint i | reachable << 15
     double c = 1.0, s = 0.0;
@@ -369,9 +389,11 @@ __global__ void __launch_bounds__(NT, (((sizeof(CntT) == 2 || GMAP) ? NM_SIM_MIN
 
     for (int t = 0; t < T; ++t) {
       __syncwarp();
+      const bool active = fl.get<F_ACTIVE>();
       if (__ballot_sync(kFull, active) == 0u) break;
+      const bool cur_inside = fl.get<F_INSIDE>();
       if (active) record_position(t, cur_tx, cur_ty, cur_inside);
-      const bool need = active && dirty;
+      const bool need = active && fl.get<F_DIRTY>();
       const unsigned dmask = __ballot_sync(kFull, need);
       if (dmask != 0u) {
         const bool start_ok = cur_inside && geo.tile_code(cur_tx * d.Y + cur_ty) != 0;  // tile under the mouse (maze.py:578)
@@ -415,7 +437,7 @@ __global__ void __launch_bounds__(NT, (((sizeof(CntT) == 2 || GMAP) ? NM_SIM_MIN
           vis = ((et.x >> 15) & 1u) | ((et.x >> 30) & 2u) | ((et.y >> 13) & 4u) | ((et.y >> 28) & 8u) |
                 ((et.z >> 11) & 16u) | ((et.z >> 26) & 32u) | ((et.w >> 9) & 64u) | ((et.w >> 24) & 128u);
         }
-        dirty = false;
+        fl.set<F_DIRTY>(false);
       }
       if (!active) continue;
       int etile[kA];
@@ -424,7 +446,7 @@ __global__ void __launch_bounds__(NT, (((sizeof(CntT) == 2 || GMAP) ? NM_SIM_MIN
       const int K = __popc(vis);
       if (K == 0) {  // np.max([]) raises in the reference (exploration_model.py:92)
         status = t + 1;
-        active = false;
+        fl.set<F_ACTIVE>(false);
         continue;
       }
       int act_idx = -1;
@@ -433,8 +455,8 @@ __global__ void __launch_bounds__(NT, (((sizeof(CntT) == 2 || GMAP) ? NM_SIM_MIN
       if (a.d_experience) {  // :456-466 (count of the current tile was just incremented above)
         const double nvis = cur_inside ? (double)cnt_ld(cur_tx * d.Y + cur_ty) : 0.0;
         fam = (1.0 - xi) * fam + xi * nvis;
-        if (home && fam >= th_explo) home = false;
-        else if (!home && fam < th_home) home = true;
+        if (fl.get<F_HOME>() && fam >= th_explo) fl.set<F_HOME>(false);
+        else if (!fl.get<F_HOME>() && fam < th_home) fl.set<F_HOME>(true);
       }
       // -- val_fin = beta * sum_c weighted_values_c                           :84-87
       // (candidates stay in action order: the reference's list is the action list filtered by
@@ -444,6 +466,7 @@ __global__ void __launch_bounds__(NT, (((sizeof(CntT) == 2 || GMAP) ? NM_SIM_MIN
       // beyond the A actions read tile 0 and zero tables -- no per-slot `i < A` test) and the reachable ones are
       // selected afterwards, so the warp stays converged.  Per endpoint the sum still runs over the
       // components in model order starting from 0.0 (:84-86).
+      const bool moving = fl.get<F_MOVING>(), home = fl.get<F_HOME>();
       double val[kA];
 #pragma unroll
       for (int i = 0; i < kA; ++i) val[i] = 0.0;
@@ -581,7 +604,7 @@ __global__ void __launch_bounds__(NT, (((sizeof(CntT) == 2 || GMAP) ? NM_SIM_MIN
       double nx, ny;  // the chosen endpoint, recomputed (same operations, same bits)
       nm_pose_endpoint(c, s, px, py, d.act[act_idx][0], d.act[act_idx][1], &nx, &ny);
       // -- moving flag                                                        :101-107
-      moving = (prevx == nx) && (prevy == ny);
+      fl.set<F_MOVING>((prevx == nx) && (prevy == ny));
       prevx = nx;
       prevy = ny;
       // -- Mouse.move_to                                                      mouse.cpp:75-87
@@ -590,13 +613,13 @@ __global__ void __launch_bounds__(NT, (((sizeof(CntT) == 2 || GMAP) ? NM_SIM_MIN
         ori = nm_host_atan2(ny - py, nx - px);
         px = nx;
         py = ny;
-        dirty = true;  // new pose: the cached reachability is stale
+        fl.set<F_DIRTY>(true);  // new pose: the cached reachability is stale
       }
       const int ntx = geo.tile(px), nty = geo.tile(py);
       const bool tile_changed = ntx != cur_tx || nty != cur_ty;
       if (tile_changed) count_moving += 1;  // motion_analysis, metrics.py:437-440
-      if (prev_moved && !tile_changed) static_runs += 1;
-      prev_moved = tile_changed;
+      if (fl.get<F_PREVMOVED>() && !tile_changed) static_runs += 1;
+      fl.set<F_PREVMOVED>(tile_changed);
       if (a.n_ori_bins > 0 && tile_changed &&
           (a.ori_tile_filter == 0u || (cur_inside && ((a.ori_tile_filter >> geo.tile_code(cur_tx * d.Y + cur_ty)) & 1u)))) {
         // hist_orientations (:329-356): the turn of this step, brought back by one full turn when it leaves
@@ -615,15 +638,15 @@ __global__ void __launch_bounds__(NT, (((sizeof(CntT) == 2 || GMAP) ? NM_SIM_MIN
       }
       cur_tx = ntx;
       cur_ty = nty;
-      cur_inside = cur_tx >= 0 && cur_tx < d.X && cur_ty >= 0 && cur_ty < d.Y;
-      if (live && a.d_hist_pos) {
+      fl.set<F_INSIDE>(cur_tx >= 0 && cur_tx < d.X && cur_ty >= 0 && cur_ty < d.Y);
+      if (fl.get<F_LIVE>() && a.d_hist_pos) {
         a.d_hist_pos[((int64_t)(t + 1) * N + n) * 2] = px;
         a.d_hist_pos[((int64_t)(t + 1) * N + n) * 2 + 1] = py;
       }
-      if (live && a.d_hist_ori) a.d_hist_ori[(int64_t)(t + 1) * N + n] = ori;
-      if (live && a.d_hist_choice) a.d_hist_choice[(int64_t)t * N + n] = (uint8_t)act_idx;
+      if (fl.get<F_LIVE>() && a.d_hist_ori) a.d_hist_ori[(int64_t)(t + 1) * N + n] = ori;
+      if (fl.get<F_LIVE>() && a.d_hist_choice) a.d_hist_choice[(int64_t)t * N + n] = (uint8_t)act_idx;
     }
-    if (status == 0) record_position(T, cur_tx, cur_ty, cur_inside);
+    if (status == 0) record_position(T, cur_tx, cur_ty, fl.get<F_INSIDE>());
 
     if (live) {
     if (a.d_final_pose) {
@@ -674,7 +697,7 @@ __global__ void __launch_bounds__(NT, (((sizeof(CntT) == 2 || GMAP) ? NM_SIM_MIN
       for (int b = 0; b <= a.n_ori_bins; ++b) a.d_ori_hist[(int64_t)(a.n_ori_bins + 1) * n + b] = ohist[b];
     if (a.d_model_state) {
       double *q = a.d_model_state + 5 * n;
-      q[0] = prevx; q[1] = prevy; q[2] = moving ? 1.0 : 0.0; q[3] = fam; q[4] = home ? 1.0 : 0.0;
+      q[0] = prevx; q[1] = prevy; q[2] = fl.get<F_MOVING>() ? 1.0 : 0.0; q[3] = fam; q[4] = fl.get<F_HOME>() ? 1.0 : 0.0;
     }
     }  // live
   }
@@ -797,7 +820,7 @@ extern "C" int nm_simulate(const nm_maze *mz, const nm_sim_args *args, void *str
   const int nT = mz->X * mz->Y;
   int threads = kSimThreads;
   const size_t geo_bytes = NmSimGeom::smem_bytes(mz->X, mz->Y);
-  // 2^(j/16) | actions | rank -> lane scratch | per-mouse anxiety and biomechanical-cost tables | visit map | shared
+  // 2^(j/64) region | actions | rank -> lane scratch | per-mouse anxiety and biomechanical-cost tables | visit map | shared
   // value table | geometry
   // a tile is visited at most n_steps + 1 times; NM_SIM_COUNTERS=32 forces the wide variant (tests)
   const char *env_cnt = getenv("NM_SIM_COUNTERS");
@@ -807,7 +830,7 @@ extern "C" int nm_simulate(const nm_maze *mz, const nm_sim_args *args, void *str
   size_t cnt_bytes = small_counts ? sizeof(uint16_t) : sizeof(uint32_t);
   const size_t per_thread = (size_t)(1 + 2 * kA) + (size_t)(5 + kBcwRows) * sizeof(double);
   auto smem_for = [&](int th) {
-    return 128 + 16 * kA + per_thread * th + (size_t)nT * th * cnt_bytes + (size_t)nT * sizeof(double) + geo_bytes;
+    return kSimFixedBytes + per_thread * th + (size_t)nT * th * cnt_bytes + (size_t)nT * sizeof(double) + geo_bytes;
   };
   // the visit map in device memory: mazes whose map does not fit shared memory even for one warp, or NM_SIM_MAP=global
   const char *env_map = getenv("NM_SIM_MAP");
@@ -816,7 +839,7 @@ extern "C" int nm_simulate(const nm_maze *mz, const nm_sim_args *args, void *str
   if (gmap) {
     small_counts = false;
     cnt_bytes = sizeof(uint32_t);
-    smem = 128 + 16 * kA + per_thread * threads + geo_bytes;
+    smem = kSimFixedBytes + per_thread * threads + geo_bytes;
     NM_CHECK_ARG(smem <= 227 * 1024, "nm_simulate: the tile and grid-line tables of a maze of %d tiles do not fit shared "
                  "memory (about 66 000 tiles at most)", nT);
     const int64_t columns = ((a.n_mice + threads - 1) / threads) * threads;
@@ -829,8 +852,6 @@ extern "C" int nm_simulate(const nm_maze *mz, const nm_sim_args *args, void *str
     smem = smem_for(threads);
     d.scratch_columns = 0;
   }
-  const int64_t blocks = (a.n_mice + threads - 1) / threads;
-  NM_CHECK_ARG(blocks <= 2147483647LL, "nm_simulate: too many mice for one launch");
   void (*kern)(const SimDev);
   const bool seeded = a.d_init_visits || a.d_init_model_state;
 #define NM_SIM_PICK(CNT, SEED) \
@@ -847,6 +868,8 @@ extern "C" int nm_simulate(const nm_maze *mz, const nm_sim_args *args, void *str
   if (d.comp_word == kStdWord && a.model_kind == 0 && !gmap && !seeded && threads == 128)
     kern = small_counts ? nm_sim_kernel<128, uint16_t, false, false, kStdWord>
                         : nm_sim_kernel<128, uint32_t, false, false, kStdWord>;
+  const int64_t blocks = (a.n_mice + threads - 1) / threads;
+  NM_CHECK_ARG(blocks <= 2147483647LL, "nm_simulate: too many mice for one launch");
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return nm_fail(NM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   kern<<<(unsigned)blocks, threads, smem, (cudaStream_t)stream>>>(d);
@@ -864,8 +887,8 @@ extern "C" int nm_simulate_fits(int X, int Y, int n_steps) {
   const size_t cnt_bytes = n_steps < 65535 ? sizeof(uint16_t) : sizeof(uint32_t);
   const size_t per_thread = (size_t)(1 + 2 * kA) + (size_t)(5 + kBcwRows) * sizeof(double);
   const size_t geo = NmSimGeom::smem_bytes(X, Y);
-  if (128 + 16 * kA + th * per_thread + nT * th * cnt_bytes + nT * sizeof(double) + geo <= 227 * 1024) return 1;
-  return 128 + 16 * kA + (size_t)kSimThreads * per_thread + geo <= 227 * 1024 ? 2 : 0;
+  if (kSimFixedBytes + th * per_thread + nT * th * cnt_bytes + nT * sizeof(double) + geo <= 227 * 1024) return 1;
+  return kSimFixedBytes + (size_t)kSimThreads * per_thread + geo <= 227 * 1024 ? 2 : 0;
 }
 
 extern "C" int64_t nm_simulate_scratch_columns(int64_t n_mice) {
