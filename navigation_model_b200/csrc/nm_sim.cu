@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(NT, (((sizeof(CntT) == 2 || GMAP) ? NM_SIM_MIN
   ExpSim::fill(smem_raw, tid);
   if (tid < 2 * kA) act_sm[tid] = d.act[tid >> 1][tid & 1];
   NmSimGeom geo;  // tile table, grid-line tables (nm_simgeom.cuh)
-  geo.build(reinterpret_cast<unsigned char *>(GMAP ? vt_sm : vt_sm + nT), d.tiles, d.X, d.Y, d.st);
+  geo.build(reinterpret_cast<unsigned char *>(GMAP ? vt_sm : vt_sm + nT), d.tiles, d.a.d_tile_flags, d.X, d.Y, d.st);
   if (!GMAP && d.a.d_vtable && !d.a.vtable_per_mouse)
     for (int i = tid; i < nT; i += nt) vt_sm[i] = d.a.d_vtable[i];
   const nm_sim_args &a = d.a;
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(NT, (((sizeof(CntT) == 2 || GMAP) ? NM_SIM_MIN
       if (!inside) return;
       const int tile = tx * d.Y + ty;
       if (a.d_tile_flags) {
-        const unsigned f = a.d_tile_flags[tile];
+        const unsigned f = geo.tile_flags(tile);  // staged in shared memory with the tile table
         if (f & NM_TILE_ZONE_IN) {
           if (zone_latency == T && t_idx < T) zone_latency = t_idx;  // "never" and "at the last position" are both T
           if (!fl.get<F_INZONE>()) {
@@ -730,7 +730,7 @@ __global__ void __launch_bounds__(256) nm_segments_kernel(const uint8_t *__restr
   // the simulation kernel's geometry (tabulated grid lines, branch-free walk) on caller-supplied segments
   extern __shared__ __align__(16) unsigned char sm_geo[];
   NmSimGeom geo;
-  geo.build(sm_geo, g_tiles, X, Y, st);
+  geo.build(sm_geo, g_tiles, nullptr, X, Y, st);
   __syncthreads();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const double x1 = seg[4 * i], y1 = seg[4 * i + 1], x2 = seg[4 * i + 2], y2 = seg[4 * i + 3];

@@ -12,6 +12,7 @@
 //   * what remains per crossing is y = m*(x - x1) + y1 (the reference's operations, no FMA) and ONE tile index;
 //   * m = (y2-y1)/(x2-x1) does not depend on the swap that orders the end points (maze.py:583-586, 598-601):
 //     IEEE subtraction and division are sign-symmetric, (-a)/(-b) == a/b bit for bit;
+//   * the caller's per-tile flag bytes (zone / corridor marks of the fused metrics) ride along as a fourth table;
 //   * both end points are inside the maze whenever the walk runs, so dx in [0, X-2] and the tables never overflow;
 //     lanes whose move is already refused run the same instructions on index 0 and discard the result.
 //
@@ -51,15 +52,17 @@ struct NmSimGeom {
   uint32_t a_tiles;   // [X*Y] shared-window address of the tile table
   uint32_t a_crossx;  // [X][Y]
   uint32_t a_crossy;  // [Y][X]
+  uint32_t a_flags;   // [X*Y] the caller's per-tile flag bytes (zone / corridor marks of the fused metrics), 0 without
   uint32_t a_gl;      // [max(X,Y)] doubles  fl((i+1)*st)
   int X, Y;
   double st, inv;
 
   __device__ __forceinline__ uint32_t tile_code(int idx) const { return nm_lds_u8(a_tiles + (uint32_t)idx); }
+  __device__ __forceinline__ uint32_t tile_flags(int idx) const { return nm_lds_u8(a_flags + (uint32_t)idx); }
 
   static __host__ __device__ size_t smem_bytes(int X, int Y) {
     const int m = X > Y ? X : Y;
-    return (size_t)m * sizeof(double) + 3 * (((size_t)X * Y + 15) & ~(size_t)15);
+    return (size_t)m * sizeof(double) + 4 * (((size_t)X * Y + 15) & ~(size_t)15);
   }
 
   // `base` 8-byte aligned, smem_bytes(X, Y) long; every thread of the CTA calls build(), then __syncthreads().
@@ -72,14 +75,16 @@ struct NmSimGeom {
     a_tiles = nm_pin_u32(b + (uint32_t)m * (uint32_t)sizeof(double));
     a_crossx = nm_pin_u32(a_tiles + slab);
     a_crossy = nm_pin_u32(a_crossx + slab);
+    a_flags = nm_pin_u32(a_crossy + slab);
   }
 
-  static __device__ __noinline__ void fill(unsigned char *base, const uint8_t *g_tiles, int X, int Y, double st) {
+  static __device__ __noinline__ void fill(unsigned char *base, const uint8_t *g_tiles, const uint8_t *g_flags, int X, int Y,
+                                           double st) {
     const double inv = 1.0 / st;
     const int nT = X * Y, m = X > Y ? X : Y;
     const size_t slab = ((size_t)nT + 15) & ~(size_t)15;
     double *gl_w = reinterpret_cast<double *>(base);
-    uint8_t *t_w = base + (size_t)m * sizeof(double), *cx_w = t_w + slab, *cy_w = cx_w + slab;
+    uint8_t *t_w = base + (size_t)m * sizeof(double), *cx_w = t_w + slab, *cy_w = cx_w + slab, *f_w = cy_w + slab;
     NmMazeView mv;
     mv.tiles = g_tiles; mv.X = X; mv.Y = Y; mv.st = st; mv.inv = inv;
 #pragma unroll 1
@@ -87,6 +92,7 @@ struct NmSimGeom {
 #pragma unroll 1
     for (int i = threadIdx.x; i < nT; i += blockDim.x) {
       t_w[i] = g_tiles[i];
+      f_w[i] = g_flags ? g_flags[i] : 0;
       {  // crossx[dx][ty]
         const int dx = i / Y, ty = i - dx * Y;
         const double gx = (double)(dx + 1) * st;
@@ -103,8 +109,9 @@ struct NmSimGeom {
   }
 
   // every thread of the CTA: fill the tables, synchronise, THEN take the (pinned) addresses the reads go through
-  __device__ __forceinline__ void build(unsigned char *base, const uint8_t *g_tiles, int X_, int Y_, double st_) {
-    fill(base, g_tiles, X_, Y_, st_);
+  __device__ __forceinline__ void build(unsigned char *base, const uint8_t *g_tiles, const uint8_t *g_flags, int X_, int Y_,
+                                        double st_) {
+    fill(base, g_tiles, g_flags, X_, Y_, st_);
     __syncthreads();
     attach(base, X_, Y_, st_);
   }
