@@ -329,7 +329,8 @@ __global__ void __launch_bounds__(NT, (((sizeof(CntT) == 2 || GMAP) ? NM_SIM_MIN
       if (!inside) return;
       const int tile = tx * d.Y + ty;
       if (a.d_tile_flags) {
-        const unsigned f = geo.tile_flags(tile);  // staged in shared memory with the tile table
+        // staged in shared memory with the tile table (mazes of up to 4096 tiles), else read from device memory
+        const unsigned f = NmSimGeom::flags_staged(d.X, d.Y) ? geo.tile_flags(tile) : a.d_tile_flags[tile];
         if (f & NM_TILE_ZONE_IN) {
           if (zone_latency == T && t_idx < T) zone_latency = t_idx;  // "never" and "at the last position" are both T
           if (!fl.get<F_INZONE>()) {

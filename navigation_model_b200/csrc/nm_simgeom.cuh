@@ -60,9 +60,12 @@ struct NmSimGeom {
   __device__ __forceinline__ uint32_t tile_code(int idx) const { return nm_lds_u8(a_tiles + (uint32_t)idx); }
   __device__ __forceinline__ uint32_t tile_flags(int idx) const { return nm_lds_u8(a_flags + (uint32_t)idx); }
 
+  // the flag bytes are staged for mazes of up to 4096 tiles (where shared memory is plentiful); larger mazes read them
+  // from device memory, so that the tile / grid-line tables alone decide how large a maze fits (~66 000 tiles)
+  static __host__ __device__ bool flags_staged(int X, int Y) { return (size_t)X * Y <= 4096; }
   static __host__ __device__ size_t smem_bytes(int X, int Y) {
     const int m = X > Y ? X : Y;
-    return (size_t)m * sizeof(double) + 4 * (((size_t)X * Y + 15) & ~(size_t)15);
+    return (size_t)m * sizeof(double) + (flags_staged(X, Y) ? 4 : 3) * (((size_t)X * Y + 15) & ~(size_t)15);
   }
 
   // `base` 8-byte aligned, smem_bytes(X, Y) long; every thread of the CTA calls build(), then __syncthreads().
@@ -92,7 +95,7 @@ struct NmSimGeom {
 #pragma unroll 1
     for (int i = threadIdx.x; i < nT; i += blockDim.x) {
       t_w[i] = g_tiles[i];
-      f_w[i] = g_flags ? g_flags[i] : 0;
+      if (flags_staged(X, Y)) f_w[i] = g_flags ? g_flags[i] : 0;
       {  // crossx[dx][ty]
         const int dx = i / Y, ty = i - dx * Y;
         const double gx = (double)(dx + 1) * st;
