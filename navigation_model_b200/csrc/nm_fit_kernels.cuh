@@ -358,21 +358,33 @@ __global__ void __launch_bounds__(512, 1) nm_fit_exact_kernel(const FitArgs a) {
     acc.prod = 1.0;
     acc.er.load(smem_raw + kBarBytes + kRawBytes + kDecBytes);
     const int lane = tid & 31;
-    for (int c = 0; c < nchunks; ++c) {
-      const int dslot = c % kDecStages;
-      mbar_wait(&rg.full_dec[dslot], (uint32_t)((c / kDecStages) & 1));
-      const uint4 *recs = rg.dec + dslot * (kChunk * 4);
-      const int64_t first = (int64_t)c * kChunk;
-      const int cnt = (int)(n - first < kChunk ? n - first : kChunk);
+    // the sign test of beta, once per warp (see the group kernel); lanes without a parameter set carry beta = 0
+    const bool sign_ok = LL && ALG != NM_ALG_TD0 &&
+                         __all_sync(0xffffffffu, ALG == NM_ALG_POSITIVE ? beta >= 0.0 : beta <= 0.0);
+    auto sweep_chunks = [&](auto sign_tag) {
+      constexpr bool SIGN = decltype(sign_tag)::value;
+      for (int c = 0; c < nchunks; ++c) {
+        const int dslot = c % kDecStages;
+        mbar_wait(&rg.full_dec[dslot], (uint32_t)((c / kDecStages) & 1));
+        const uint4 *recs = rg.dec + dslot * (kChunk * 4);
+        const int64_t first = (int64_t)c * kChunk;
+        const int cnt = (int)(n - first < kChunk ? n - first : kChunk);
 #pragma unroll 1
-      for (int i = 0; i < cnt; ++i) exact_step<ALG, LL>(recs + 4 * i, vb, alpha, beta, gamma, acc);
-      if (LL) {  // fold the chunk:  ll += sum(zobs - m) - log(prod of the softmax denominators)
-        ll = __dadd_rn(ll, __dsub_rn(acc.acc_obs, log_chunk_product(acc.prod)));
-        acc.acc_obs = 0.0;
-        acc.prod = 1.0;
+        for (int i = 0; i < cnt; ++i) exact_step<ALG, LL, SharedCol, SIGN>(recs + 4 * i, vb, alpha, beta, gamma, acc);
+        if (LL) {  // fold the chunk:  ll += sum(zobs - m) - log(prod of the softmax denominators)
+          ll = __dadd_rn(ll, __dsub_rn(acc.acc_obs, log_chunk_product(acc.prod)));
+          acc.acc_obs = 0.0;
+          acc.prod = 1.0;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&rg.empty_dec[dslot]);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&rg.empty_dec[dslot]);
+    };
+    if constexpr (LL && ALG != NM_ALG_TD0) {
+      if (sign_ok) sweep_chunks(std::true_type{});
+      else sweep_chunks(std::false_type{});
+    } else {
+      sweep_chunks(std::false_type{});
     }
     if (LL && wanted && a.ll_out) a.ll_out[(int64_t)sess * a.P + p] = ll;
   }
@@ -530,23 +542,35 @@ __global__ void __launch_bounds__(960, 1) nm_fit_global_kernel(const FitArgs a, 
     acc.prod = 1.0;
     acc.er.load(smem_raw + kBarBytes + kRawBytes + kDecBytes);
     const int lane = tid & 31;
-    for (int c = 0; c < nchunks; ++c) {
-      const int dslot = c % kDecStages;
-      mbar_wait(&rg.full_dec[dslot], (uint32_t)((c / kDecStages) & 1));
-      const uint4 *recs = rg.dec + dslot * (kChunk * 4);
-      const int64_t first = (int64_t)c * kChunk;
-      const int cnt = (int)(n - first < kChunk ? n - first : kChunk);
-      if (live) {
+    // the sign test of beta, once per warp (see the group kernel); lanes without a parameter set carry beta = 0
+    const bool sign_ok = LL && ALG != NM_ALG_TD0 &&
+                         __all_sync(0xffffffffu, ALG == NM_ALG_POSITIVE ? beta >= 0.0 : beta <= 0.0);
+    auto sweep_chunks = [&](auto sign_tag) {
+      constexpr bool SIGN = decltype(sign_tag)::value;
+      for (int c = 0; c < nchunks; ++c) {
+        const int dslot = c % kDecStages;
+        mbar_wait(&rg.full_dec[dslot], (uint32_t)((c / kDecStages) & 1));
+        const uint4 *recs = rg.dec + dslot * (kChunk * 4);
+        const int64_t first = (int64_t)c * kChunk;
+        const int cnt = (int)(n - first < kChunk ? n - first : kChunk);
+        if (live) {
 #pragma unroll 1
-        for (int i = 0; i < cnt; ++i) exact_step<ALG, LL>(recs + 4 * i, vb, alpha, beta, gamma, acc);
+          for (int i = 0; i < cnt; ++i) exact_step<ALG, LL, GenericCol, SIGN>(recs + 4 * i, vb, alpha, beta, gamma, acc);
+        }
+        if (LL) {
+          ll = __dadd_rn(ll, __dsub_rn(acc.acc_obs, log_chunk_product(acc.prod)));
+          acc.acc_obs = 0.0;
+          acc.prod = 1.0;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&rg.empty_dec[dslot]);
       }
-      if (LL) {
-        ll = __dadd_rn(ll, __dsub_rn(acc.acc_obs, log_chunk_product(acc.prod)));
-        acc.acc_obs = 0.0;
-        acc.prod = 1.0;
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&rg.empty_dec[dslot]);
+    };
+    if constexpr (LL && ALG != NM_ALG_TD0) {
+      if (sign_ok) sweep_chunks(std::true_type{});
+      else sweep_chunks(std::false_type{});
+    } else {
+      sweep_chunks(std::false_type{});
     }
     if (LL && live && a.ll_out) a.ll_out[(int64_t)sess * a.P + p] = ll;
     if (live && a.v_out) {

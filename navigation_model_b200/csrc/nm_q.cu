@@ -27,6 +27,8 @@
 // parameter set the operations are those of the octet kernel, in the same order: results are bit-identical.
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include <stdlib.h>
 
 #include <map>
@@ -289,7 +291,9 @@ struct QAcc {
   ExpLL er;  // likelihood exponentials: nm_exp.cuh (1e-9 bar on the session's log-likelihood, tables never see them)
 };
 
-template <int K1, class Col>
+// SIGN: the caller has established once, for the whole warp, that beta >= 0 (the per-step test and its predicated twin
+// disappear from the step body; same results).
+template <int K1, class Col, bool SIGN = false>
 __device__ __forceinline__ void qgroup_step_k(const uint4 q0, const uint4 q1, const uint4 q2, const uint4 q3,
                                               const uint4 q4, const Col qb, const double alpha, const double beta,
                                               const double gamma, QAcc &acc) {
@@ -308,7 +312,7 @@ __device__ __forceinline__ void qgroup_step_k(const uint4 q0, const uint4 q1, co
     for (int k = 0; k < K1; ++k) v[k] = qb.ld(o1[k]);
     // beta >= 0: max_k fl(beta * v_k) == fl(beta * max_k v_k), rounding is monotonic   (exploration_model.py:87, 92)
     double m;
-    if (beta >= 0.0) {
+    if (SIGN || beta >= 0.0) {
       m = __dmul_rn(beta, extremum<NM_ALG_POSITIVE, K1>(v));
     } else {
       double z[NM_MAX_CAND];
@@ -326,14 +330,14 @@ __device__ __forceinline__ void qgroup_step_k(const uint4 q0, const uint4 q1, co
   qb.st(q0.w, __dadd_rn(q, __dmul_rn(alpha, rpe)));                        // rl.py:186-187
 }
 
-template <class Col>
+template <class Col, bool SIGN = false>
 __device__ __forceinline__ void qgroup_step(const uint4 *__restrict__ rec, const Col qb, const double alpha, const double beta,
                                             const double gamma, QAcc &acc) {
   const uint4 q0 = rec[0];
   if (!(q0.z & kQHit)) return;  // no observed action: the step is skipped entirely (warp-uniform)
   const uint4 q1 = rec[1], q2 = rec[2], q3 = rec[3], q4 = rec[4];
 #define NM_CASE(KK) \
-  case KK: qgroup_step_k<KK, Col>(q0, q1, q2, q3, q4, qb, alpha, beta, gamma, acc); break;
+  case KK: qgroup_step_k<KK, Col, SIGN>(q0, q1, q2, q3, q4, qb, alpha, beta, gamma, acc); break;
   switch (q0.z & 0xffu) {  // K1, warp-uniform (>= 1 on a hit)
     NM_CASE(1) NM_CASE(2) NM_CASE(3) NM_CASE(4) NM_CASE(5) NM_CASE(6) NM_CASE(7) NM_CASE(8)
     default: break;
@@ -401,20 +405,27 @@ __global__ void __launch_bounds__(960, 1) nm_qgroup_kernel(const QArgs a) {
     acc.acc_obs = 0.0;
     acc.prod = 1.0;
     acc.er.load(exptab);
-    for (int c = 0; c < nchunks; ++c) {
-      const int dslot = c % kQDecStages;
-      mbar_wait(&rg.full_dec[dslot], (uint32_t)((c / kQDecStages) & 1));
-      const uint4 *recs = rg.dec + dslot * (kQChunk * kQDecWords);
-      const int64_t first = (int64_t)c * kQChunk;
-      const int cnt = (int)(n - first < kQChunk ? n - first : kQChunk);
+    // is every lane's beta non-negative?  (warp-uniform answer, taken once: the step body is compiled twice)
+    const bool sign_ok = __all_sync(0xffffffffu, beta >= 0.0);
+    auto sweep_chunks = [&](auto sign_tag) {
+      constexpr bool SIGN = decltype(sign_tag)::value;
+      for (int c = 0; c < nchunks; ++c) {
+        const int dslot = c % kQDecStages;
+        mbar_wait(&rg.full_dec[dslot], (uint32_t)((c / kQDecStages) & 1));
+        const uint4 *recs = rg.dec + dslot * (kQChunk * kQDecWords);
+        const int64_t first = (int64_t)c * kQChunk;
+        const int cnt = (int)(n - first < kQChunk ? n - first : kQChunk);
 #pragma unroll 1
-      for (int i = 0; i < cnt; ++i) qgroup_step(recs + kQDecWords * i, qb, alpha, beta, gamma, acc);
-      ll = __dadd_rn(ll, __dsub_rn(acc.acc_obs, log_chunk_product(acc.prod)));  // the octet kernel folds every 32 records too
-      acc.acc_obs = 0.0;
-      acc.prod = 1.0;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&rg.empty_dec[dslot]);
-    }
+        for (int i = 0; i < cnt; ++i) qgroup_step<QSharedCol, SIGN>(recs + kQDecWords * i, qb, alpha, beta, gamma, acc);
+        ll = __dadd_rn(ll, __dsub_rn(acc.acc_obs, log_chunk_product(acc.prod)));  // the octet kernel folds every 32 records too
+        acc.acc_obs = 0.0;
+        acc.prod = 1.0;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&rg.empty_dec[dslot]);
+      }
+    };
+    if (sign_ok) sweep_chunks(std::true_type{});
+    else sweep_chunks(std::false_type{});
     if (p < a.P && a.ll_out) a.ll_out[(int64_t)sess * a.P + p] = ll;
   }
   if (a.q_out) {  // every parameter set of a run receives the run's table

@@ -192,6 +192,44 @@ def test_full_grid_properties(cuda):
     assert best_i == int(np.argmin(-ll)) and best_v == float((-ll).min())
 
 
+@pytest.mark.parametrize("alg,sign", [("positive", 1.0), ("positive", -1.0), ("negative", 1.0), ("negative", -1.0)])
+def test_sign_of_beta_taken_once_per_warp(cuda, alg, sign, monkeypatch):
+    """The likelihood kernels test the sign of beta once per warp and run a step body compiled for the answer (for the
+    max-backup learner and beta >= 0 -- the min-backup learner and beta <= 0 -- the softmax maximum is fl(beta * extremum
+    V)).  Warps whose 32 betas all have the favourable sign, warps whose betas all have the other sign and a warp with
+    both: the three kernels stay bit-identical to one another and agree with the oracle."""
+    omz = H.oracle_m9()
+    sessions = [O.synthetic_session(omz, sid, T) for sid, T in ((0, 500), (4, 97))]
+    if alg == "negative":
+        sessions = [(t, -r) for t, r in sessions]
+    rng = np.random.default_rng(17)
+    pairs, n_beta = 4, 32
+    a = np.repeat(rng.uniform(0.01, 1, pairs), n_beta)
+    g = np.repeat(rng.uniform(0.5, 0.99, pairs), n_beta)
+    b = sign * np.tile(np.logspace(-1, 1.3, n_beta), pairs)
+    b[32:64] = -b[32:64]      # one warp with the other sign throughout
+    b[70] = -b[70]            # one warp with both signs
+    b[100] = 0.0              # beta = 0 has both signs
+    sw = _sweep(alg, sessions)
+    ll, V = sw.log_likelihood(a, b, g, return_v=True)
+    assert sw.last_sweep_mode() == 1
+    monkeypatch.setenv("NM_FIT_GROUP", "0")
+    ll_x, V_x = sw.log_likelihood(a, b, g, return_v=True)
+    assert sw.last_sweep_mode() == 2
+    monkeypatch.setenv("NM_FIT_TABLES", "shared")
+    ll_s, V_s = sw.log_likelihood(a, b, g, return_v=True)
+    assert sw.last_sweep_mode() == 0
+    monkeypatch.delenv("NM_FIT_GROUP")
+    monkeypatch.delenv("NM_FIT_TABLES")
+    assert np.array_equal(ll, ll_x) and np.array_equal(V, V_x) and np.array_equal(ll, ll_s) and np.array_equal(V, V_s)
+    for j, (traj, rew) in enumerate(sessions):
+        tr = H.oracle_transitions(omz, traj, rew, H.a8())
+        Vw, llw = CO.fit(ALGS[alg], tr, a, g, 60, beta=b)
+        np.testing.assert_allclose(ll[j], llw, rtol=LL_RTOL, atol=1e-300)
+        for p in (0, 40, 70, 100, 127):
+            assert np.array_equal(V[j, p], O.dense_table(omz, Vw[p]))
+
+
 @pytest.mark.parametrize("alg", ["td0", "positive", "negative"])
 @pytest.mark.parametrize("n_beta", [64, 128, 32, 160])
 def test_group_kernels_match_exact_kernel_and_oracle(cuda, alg, n_beta, monkeypatch):
