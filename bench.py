@@ -674,23 +674,32 @@ def run_b200(args):
     pin = [torch.from_numpy(x).pin_memory() for x in (a, b, g)]
     ll_host = [torch.empty((1, P), dtype=torch.float64).pin_memory() for _ in range(2)]
     ll_dev = [ll_t, torch.empty_like(ll_t)]
+    abg_dev = [(a_t, b_t, g_t), tuple(torch.empty_like(x) for x in (a_t, b_t, g_t))]
     best_host = torch.empty(2 * world, dtype=torch.float64).pin_memory()
-    copy_stream = torch.cuda.Stream(device=dev)
+    copy_stream = torch.cuda.Stream(device=dev)   # device -> host
+    h2d_stream = torch.cuda.Stream(device=dev)    # host -> device
     done = [torch.cuda.Event() for _ in range(2)]
     copied = [torch.cuda.Event() for _ in range(2)]
+    uploaded = [torch.cuda.Event() for _ in range(2)]
 
     def step_e2e():
         """R public-API sweeps with host inputs and host outputs: per sweep the session stream and the three parameter
-        arrays go pinned host -> HBM and ll[P] comes back; the read-back of sweep r overlaps sweep r + 1 (two ll
-        buffers, a copy stream); one exchange and one synchronisation per step."""
+        arrays go pinned host -> HBM and ll[P] comes back.  Two sets of device buffers: the parameter upload of sweep
+        r + 1 (its own stream) and the read-back of sweep r - 1 (copy stream) overlap the kernel of sweep r; the session
+        stream (160 KB) is uploaded on the compute stream, in order with the kernels that read it; one exchange and one
+        synchronisation per step."""
         nbytes = 0
         for r in range(R):
             j = r & 1
+            with torch.cuda.stream(h2d_stream):
+                h2d_stream.wait_event(done[j])  # the sweep that last read this buffer set (r - 2) has finished
+                for dst, src in zip(abg_dev[j], pin):
+                    dst.copy_(src, non_blocking=True)
+                uploaded[j].record(h2d_stream)
             nbytes += sw.upload()  # session stream: pinned host -> HBM (nm_streams_upload)
-            for dst, src in zip((a_t, b_t, g_t), pin):
-                dst.copy_(src, non_blocking=True)
+            stream.wait_event(uploaded[j])
             stream.wait_event(copied[j])  # ll_dev[j] has been read back (sweep r - 2)
-            sw.log_likelihood_device(a_t, b_t, g_t, ll_out=ll_dev[j])
+            sw.log_likelihood_device(*abg_dev[j], ll_out=ll_dev[j])
             best = sw.argmin_device(ll_dev[j])
             done[j].record(stream)
             with torch.cuda.stream(copy_stream):
@@ -701,6 +710,7 @@ def run_b200(args):
         best_host[: out.numel()].copy_(out, non_blocking=True)
         stream.synchronize()
         copy_stream.synchronize()
+        h2d_stream.synchronize()
         return nbytes
 
     for _ in range(max(1, args.warmup)):
