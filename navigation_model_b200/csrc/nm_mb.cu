@@ -41,7 +41,11 @@ namespace {
 
 #include "nm_group.cuh"
 
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+#include "nm_exp.cuh"
+
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kExpRegionBytes = 1024;  // room for the 512-byte-aligned 2^(j/64) table of the likelihood exponential
 constexpr int kSent = 16;  // sentinel slots in front of W (one per bank pair of a half-warp's 64-bit access)
 
 struct MbArgs {
@@ -125,6 +129,7 @@ __global__ void __launch_bounds__(512) nm_mb_kernel(const MbArgs a) {
     R[u] = 0.0;
   }
   if (lane < kSent) W[lane] = -INFINITY;
+  ExpSim::fill(smem_raw + rows_bytes + (size_t)warps * tab_doubles * sizeof(double), (int)threadIdx.x);
   __syncthreads();
   const uint32_t w_base = (uint32_t)__cvta_generic_to_shared(W);
   const uint4 *rows4 = reinterpret_cast<const uint4 *>(rows);
@@ -133,6 +138,11 @@ __global__ void __launch_bounds__(512) nm_mb_kernel(const MbArgs a) {
   const int64_t n = a.offsets[sess + 1] - rec0, n_on = a.online[sess];
   const uint4 *recs = reinterpret_cast<const uint4 *>(a.records + rec0);
   double ll = 0.0;
+  // the likelihood exponentials and the per-chunk logarithm of the fit kernels (nm_exp.cuh: ExpLL, one log per 32
+  // steps of the product of the softmax denominators -- each in [1, 8], so the product stays below 2^96)
+  ExpLL er;
+  double acc_obs = 0.0, prod = 1.0;
+  er.load(smem_raw + rows_bytes + (size_t)warps * tab_doubles * sizeof(double));
   for (int64_t i = 0; i < n; ++i) {
     const uint4 w0 = __ldg(recs + 2 * i);  // warp-uniform address: one broadcast transaction
     const double r = __hiloint2double((int)w0.y, (int)w0.x);
@@ -152,7 +162,7 @@ __global__ void __launch_bounds__(512) nm_mb_kernel(const MbArgs a) {
       for (int off = 4; off > 0; off >>= 1) m = dmax2(m, __shfl_xor_sync(kFull, m, off));  // lanes 0..7 hold the max
       m = __shfl_sync(kFull, m, 0);
       const double zc = __dsub_rn(z, m);  // :92
-      const double e = ok ? exp(zc) : 0.0;
+      const double e = ok ? er(zc) : 0.0;
       const int K = __popc(avail);
       double sum;
       if (K == NM_MAX_CAND) {  // numpy pairwise sum, n == 8: lanes 0..7 are all available
@@ -167,7 +177,8 @@ __global__ void __launch_bounds__(512) nm_mb_kernel(const MbArgs a) {
         }
       }
       const double zobs = __shfl_sync(kFull, zc, a_obs);
-      ll = __dadd_rn(ll, __dsub_rn(zobs, log(sum)));
+      acc_obs = __dadd_rn(acc_obs, zobs);
+      prod = __dmul_rn(prod, sum);
     }
     } else {
     // every lane loads the (at most eight) action values as broadcasts and evaluates its own beta; the action set
@@ -199,7 +210,7 @@ __global__ void __launch_bounds__(512) nm_mb_kernel(const MbArgs a) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const double zc = __dsub_rn(z[k], m);  // :92
-        e[k] = ((avail >> k) & 1u) ? exp(zc) : 0.0;
+        e[k] = ((avail >> k) & 1u) ? er(zc) : 0.0;
         if (k == a_obs) zobs = zc;
       }
       double sum;
@@ -211,8 +222,14 @@ __global__ void __launch_bounds__(512) nm_mb_kernel(const MbArgs a) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) sum = __dadd_rn(sum, e[k]);
       }
-      ll = __dadd_rn(ll, __dsub_rn(zobs, log(sum)));
+      acc_obs = __dadd_rn(acc_obs, zobs);
+      prod = __dmul_rn(prod, sum);
     }
+    }
+    if ((i & 31) == 31 || i == n - 1) {  // fold the chunk:  ll += sum(zobs) - log(prod of the softmax denominators)
+      ll = __dadd_rn(ll, __dsub_rn(acc_obs, log_chunk_product(prod)));
+      acc_obs = 0.0;
+      prod = 1.0;
     }
     // ---- world model: Rhat[s1] += alpha * (r - Rhat[s1]) ---------------------------------------------------
     if (lane == 0) {
@@ -277,7 +294,7 @@ extern "C" int nm_modelbased_sweep(const nm_maze *mz, const nm_streams *st, cons
   // CTAs per SM x warps per CTA: as many resident warps as 227 KB of shared memory (1 KB reserved per CTA) allow
   int warps = 0, best_total = 0;
   for (int ctas = 1; ctas <= 8; ++ctas) {
-    const long avail = (long)(227 * 1024) / ctas - 1024 - (long)rows_bytes;
+    const long avail = (long)(227 * 1024) / ctas - 1024 - (long)rows_bytes - (long)kExpRegionBytes;
     if (avail < (long)per_warp) break;
     int w = (int)(avail / (long)per_warp);
     if (w > 16) w = 16;
@@ -289,7 +306,7 @@ extern "C" int nm_modelbased_sweep(const nm_maze *mz, const nm_streams *st, cons
     }
   }
   NM_CHECK_ARG(warps >= 1, "nm_modelbased_sweep: a maze with %d states does not fit in shared memory", S);
-  const size_t smem = rows_bytes + per_warp * warps;
+  const size_t smem = rows_bytes + per_warp * warps + kExpRegionBytes;
   cudaError_t e = cudaFuncSetAttribute(nm_mb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(nm_mb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -334,8 +351,8 @@ extern "C" int nm_modelbased_sweep(const nm_maze *mz, const nm_streams *st, cons
     int64_t per_cta = (runs * st->S + sms - 1) / sms;
     per_cta = (per_cta + st->S - 1) / st->S;
     const int gw = (int)(per_cta < 1 ? 1 : per_cta > warps ? warps : per_cta);
-    nm_mb_kernel<true><<<dim3((unsigned)((runs + gw - 1) / gw), (unsigned)st->S, 1), gw * 32, rows_bytes + per_warp * gw,
-                         cs>>>(a);
+    nm_mb_kernel<true><<<dim3((unsigned)((runs + gw - 1) / gw), (unsigned)st->S, 1), gw * 32,
+                         rows_bytes + per_warp * gw + kExpRegionBytes, cs>>>(a);
   }
   nm_mb_kernel<false><<<dim3((unsigned)blocks, (unsigned)st->S, 1), warps * 32, smem, cs>>>(a);
   e = cudaGetLastError();
