@@ -1,88 +1,12 @@
-// Table-driven FP64 exp for non-positive arguments, shared by the fit and simulation kernels.
+// Table-driven FP64 exponentials for non-positive arguments: ExpLL (likelihood kernels: fit, Q-table, model-based) and ExpSim
+// (simulation kernel), and the per-chunk logarithm of the likelihood kernels.
 // Included inside each translation unit's anonymous namespace (every TU gets its own constant tables).
 #ifndef NM_EXP_CUH
 #define NM_EXP_CUH
 
-// exp(x), x <= 0, for the hot loop: table-driven.  x = (16 e + j) * ln2/16 + r with |r| <= ln2/32, so
-// exp(x) = 2^e * 2^(j/16) * exp(r): a degree-7 polynomial (truncation 1.2e-18) instead of degree 13, one
-// conflict-free LDS for 2^(j/16) and one DMUL -- 12 FP64 instructions instead of 17, and a 6-deep instead of a
-// 13-deep dependent chain.  The 10 constants are pinned in registers (loaded once per thread through an opaque
-// move: as immediates / constant-bank operands they cost an LDCU or two UMOVs per use -- 11 % of the issued
-// instructions before).  Very negative x: the binary exponent is clamped instead of selecting 0 -- the result
-// (<= 2^-1021) is as good as 0 next to a softmax denominator >= 1.  Valid for -1e8 < x <= 0.
-__constant__ double c_exp2tab[16] = {1.00000000000000000e+00, 1.04427378242741375e+00, 1.09050773266525769e+00,
-                                     1.13878863475669156e+00, 1.18920711500272103e+00, 1.24185781207348400e+00,
-                                     1.29683955465100964e+00, 1.35425554693689265e+00, 1.41421356237309515e+00,
-                                     1.47682614593949935e+00, 1.54221082540794074e+00, 1.61049033194925428e+00,
-                                     1.68179283050742900e+00, 1.75625216037329945e+00, 1.83400808640934243e+00,
-                                     1.91520656139714740e+00};
-__constant__ double c_exptab_k[10] = {2.30831206542234141921e+01,           // 16 * log2(e)
-                                      6755399441055744.0,                  // 1.5 * 2^52
-                                      -6.93147180369123816490e-01 / 16.0,  // -ln2/16 (high part, exact scaling)
-                                      -1.90821492927058770002e-10 / 16.0,  // -ln2/16 (low part)
-                                      1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5};
-
-struct ExpRegs {
-  double c[10];
-  uint32_t tab;  // shared-window address of the 2^(j/16) table
-  // `table_addr`: shared-window address of 16 doubles holding c_exp2tab (8-byte aligned; the kernel fills it)
-  __device__ __forceinline__ void load(uint32_t table_addr) {
-#pragma unroll
-    for (int i = 0; i < 10; ++i) asm volatile("mov.f64 %0, %1;" : "=d"(c[i]) : "d"(c_exptab_k[i]));
-    tab = table_addr;
-    asm volatile("mov.u32 %0, %0;" : "+r"(tab));  // pinned: not recomputed at every use under register pressure
-  }
-  __device__ __forceinline__ double exp_nonpos(double x) const {
-    const double t = fma(x, c[0], c[1]);
-    const int k = __double2loint(t);  // round(16 x / ln2)
-    const double n = __dsub_rn(t, c[1]);
-    double r = fma(n, c[2], x);
-    r = fma(n, c[3], r);
-    double s;
-    asm("ld.shared.f64 %0, [%1];" : "=d"(s) : "r"(tab + ((uint32_t)(k & 15) << 3)));
-    double p = fma(c[4], r, c[5]);
-    p = fma(p, r, c[6]);
-    p = fma(p, r, c[7]);
-    p = fma(p, r, c[8]);
-    p = fma(p, r, c[9]);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
-    p = __dmul_rn(p, s);
-    return __hiloint2double(__double2hiint(p) + (max(k >> 4, -1021) << 20), __double2loint(p));
-  }
-  // The same reduction with the polynomial cut to degree NM_LL_EXP_DEGREE (default 5: 10 FP64 instructions) for the
-  // softmax DENOMINATOR of a log-likelihood step, whose bar is 1e-9 relative on the session's log-likelihood
-  // (BASELINE.json north_star), not the last bit: |r| <= ln2/32 bounds the truncation by r^6/720 = 1.5e-13 relative
-  // per exponential (measured over [-40, 0]: max 1.46e-13, mean -2.0e-14), i.e. <= 1.5e-13 on a step's log-probability
-  // and ~1e-14 relative on a session.  Value tables never see an exponential; the simulation kernel, whose discrete
-  // choices must reproduce the reference's, keeps exp_nonpos.  -DNM_LL_EXP_DEGREE=7 restores the full polynomial.
-#ifndef NM_LL_EXP_DEGREE
-#define NM_LL_EXP_DEGREE 5
-#endif
-  __device__ __forceinline__ double exp_nonpos_ll(double x) const {
-    static_assert(NM_LL_EXP_DEGREE >= 4 && NM_LL_EXP_DEGREE <= 7, "NM_LL_EXP_DEGREE: 4..7");
-    if (NM_LL_EXP_DEGREE == 7) return exp_nonpos(x);
-    const double t = fma(x, c[0], c[1]);
-    const int k = __double2loint(t);
-    const double n = __dsub_rn(t, c[1]);
-    double r = fma(n, c[2], x);
-    r = fma(n, c[3], r);
-    double s;
-    asm("ld.shared.f64 %0, [%1];" : "=d"(s) : "r"(tab + ((uint32_t)(k & 15) << 3)));
-    constexpr int first = 4 + (7 - NM_LL_EXP_DEGREE);  // c[4] = 1/7!, c[5] = 1/6!, c[6] = 1/5!, ...
-    double p = fma(c[first], r, c[first + 1]);
-#pragma unroll
-    for (int i = first + 2; i < 10; ++i) p = fma(p, r, c[i]);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
-    p = __dmul_rn(p, s);
-    return __hiloint2double(__double2hiint(p) + (max(k >> 4, -1021) << 20), __double2loint(p));
-  }
-};
-
 // ---- exponentials of a LIKELIHOOD step (softmax denominator) ---------------------------------------------------------
 // Bar: 1e-9 relative on a session's log-likelihood (BASELINE.json north_star), not the last bit -- value tables never see
-// an exponential, and the simulation kernel (whose discrete choices must reproduce the reference's) keeps exp_nonpos.
+// an exponential, and the simulation kernel (whose discrete choices must reproduce the reference's) has its own ~1-ulp form, ExpSim below.
 // exp(x), x <= ~0:  x = (64 e + j) * ln2/64 + r, |r| <= ln2/128:  exp(x) = 2^e * 2^(j/64) * P3(r)
 //   * ONE fused step of range reduction against the double nearest to ln2/64 (error |x| * 1.1e-16 relative -- a term of
 //     weight exp(x) <= 1 in a sum >= 1 moves it by < 5e-17);
