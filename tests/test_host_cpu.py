@@ -236,33 +236,6 @@ def test_upload_staging_converts_and_transposes():
     assert len(exp._arenas) == n_arenas  # no new pinned allocation for the next run
 
 
-def test_ll_exponential_truncation_bound():
-    """The likelihood kernels evaluate the softmax denominator's exponentials with ExpLL (csrc/nm_exp.cuh): one fused
-    reduction step against the double nearest to ln2/32, a 32-entry table of 2^(j/32) and a degree-4 polynomial.
-    Restated in numpy with the same constants and the same operation order (numpy has no fused multiply-add: the extra
-    roundings are ~1e-16): the relative error stays below 1.3e-12 -- three orders of magnitude under the 1e-9 bar on a
-    session's log-likelihood -- and the largest softmax term, exp(0), is exact."""
-    c0, c1, cL = 46.16624130844683, 6755399441055744.0, -0.02166084939249829
-    tab = np.array([2.0 ** (j / 32) for j in range(32)])
-    x = -np.random.default_rng(0).uniform(0, 40, 1_000_000)
-    x[:4] = [0.0, -1e-300, -40.0, 3e-13]  # the last: fma(beta, Vmax, -fl(beta * Vmax)) can be a rounding error above 0
-    t = x * c0 + c1
-    k = (t.view(np.int64) & 0xffffffff).astype(np.int64)
-    k = np.where(k >= 2 ** 31, k - 2 ** 32, k)
-    r = (t - c1) * cL + x
-    assert np.abs(r).max() <= np.log(2) / 64 * (1 + 1e-9)
-    p = (1 / 24) * r + 1 / 6
-    for c in (0.5, 1.0, 1.0):
-        p = p * r + c
-    got = p * tab[k & 31] * np.exp2((k >> 5).astype(np.float64))
-    rel = np.abs(got - np.exp(x)) / np.exp(x)
-    assert rel.max() < 1.3e-12 and got[0] == 1.0
-    # hugely negative arguments: the clamp of the binary exponent gives ~2^-1021, never garbage
-    xs = np.array([-800.0, -5000.0, -1e6])
-    ks = np.maximum(np.rint(xs * c0).astype(np.int64), -1021 * 32)
-    assert ((ks >> 5) >= -1021).all()
-
-
 class _FakeBase:
     """CPU stand-in for the device side of a sweep: the likelihood is a fixed function of the parameters, the arg-min is
     torch on the CPU.  Lets sharded_best_fit's host logic (broadcast, re-ordering, sharding, tie-break) run anywhere."""
