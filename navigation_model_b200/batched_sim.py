@@ -198,6 +198,7 @@ class BatchedExperiment:
         self._run_lock = threading.RLock()  # one run at a time: the staging buffers below belong to the object
         self._arenas = []                  # pinned upload arenas [uint8 tensor, bytes used], kept across runs
         self._pinned = None                # pinned staging buffer of the per-mouse results, kept across runs
+        self._workers = None               # run_pipelined: two shallow copies with their own staging buffers + streams
         # True: v_table already holds ValueTableComponent._v_table (normalised once at construction)
         self._normalise = (lambda t: np.asarray(t, dtype=np.float64)) if v_table_normalised else bc.normalise_v_table
 
@@ -299,6 +300,14 @@ class BatchedExperiment:
             off += nbytes
         torch.cuda.current_stream().synchronize()
         src = pin.numpy()
+        if getattr(self, "_fetch_views", False):
+            # a run_pipelined worker: the caller copies the rows straight from the staging buffer into the population's
+            # arrays before this worker runs again (one host copy instead of two)
+            out = {}
+            for t, o in zip(tensors, offs):
+                a = src[o:o + t.numel() * t.element_size()].view(_NP_OF_TORCH[str(t.dtype)])
+                out[id(t)] = a.reshape(tuple(t.shape))
+            return out
         block = np.empty(total, dtype=np.uint8)
         chunk = 8 << 20
         if total <= 2 * chunk:
@@ -595,6 +604,127 @@ class BatchedExperiment:
         with self._run_lock:
             return self._run(*args, **kwargs)
 
+    # -- one large population through two host threads / CUDA streams ----------------------------------------------------
+    def _worker(self):
+        """A shallow copy for one pipeline thread: same maze / model / device tables, its own staging buffers and lock."""
+        import copy
+        w = copy.copy(self)
+        w._run_lock = threading.RLock()
+        w._arenas, w._pinned, w.last_kernel_ms = [], None, None
+        w._workers = None
+        w._fetch_views = True
+        return w
+
+    def run_pipelined(self, params, n_steps, init_pos, init_ori=0.0, init_disc=None, seeds=None, draws=None,
+                      generators=None, device_seed=None, n_mice=None, chunks=6, workers=3, **kwargs):
+        """:meth:`run` for a large population cut into ``chunks`` contiguous blocks of whole CTAs (the first one split
+        1 : 3, so that the device starts early) that travel through ``workers`` host threads, each with its own CUDA
+        stream and pinned staging buffers: the parameter preparation and upload of one block and the read-back of
+        another overlap the kernel of a third (one :meth:`run` does them one after the other: for a million mice x
+        1 000 steps a third of its wall time is host work; measured 158 -> 116 ms with the defaults).  Same results as
+        :meth:`run`: the mice are independent, and device-seeded streams follow the global mouse index
+        (``mouse_index_base``).
+
+        Per-mouse arguments are given for the whole population, as for :meth:`run_sharded`.  ``history=True`` is not
+        supported here (the histories of a large population do not belong on the host)."""
+        import torch
+        from concurrent.futures import ThreadPoolExecutor
+        if kwargs.get("history"):
+            raise ValueError("run_pipelined does not return histories; use run()")
+        base = int(kwargs.pop("mouse_index_base", 0))
+        if device_seed is not None:
+            N = int(n_mice)
+        elif draws is not None:
+            N = len(draws)
+        elif generators is not None:
+            N = len(generators)
+        else:
+            seeds = list(seeds)
+            N = len(seeds)
+        bounds = pipeline_bounds(N, chunks)
+        if len(bounds) <= 1:
+            return self.run(params, n_steps, init_pos, init_ori, init_disc, seeds=seeds, draws=draws,
+                            generators=generators, device_seed=device_seed, n_mice=n_mice, mouse_index_base=base, **kwargs)
+        _native.require_device()
+        if self._dmaze is None:
+            self._dmaze = DeviceMaze(self.maze, self._device)
+        dev = self._dmaze.torch_device
+        X, Y = self.maze.shape
+        n_workers = max(1, min(int(workers), 4))
+        with self._run_lock:
+            if getattr(self, "_workers", None) is None:
+                self._workers = []
+            while len(self._workers) < n_workers:
+                self._workers.append((self._worker(), torch.cuda.Stream(device=dev)))
+            workers = self._workers[:n_workers]
+            for w, _ in workers:  # whatever may have changed on the parent since the copies were made
+                w.v_table, w._dmaze = self.v_table, self._dmaze
+            merged, lock = {}, threading.Lock()
+            kernel_ms = [0.0]
+
+            def cut(a, lo, hi, ndim=1):
+                if a is None:
+                    return None
+                b = np.asarray(a)
+                return b[lo:hi] if b.ndim == ndim and b.shape[0] == N else a
+
+            def place(name, arr, lo, hi):
+                """Rows [lo, hi) of the population-wide array `name` (allocated by whichever block arrives first)."""
+                with lock:
+                    if name not in merged:
+                        merged[name] = np.empty((N,) + arr.shape[1:], dtype=arr.dtype)
+                    dst = merged[name]
+                rows = max(1, (4 << 20) // max(1, arr[0].nbytes if len(arr) else 1))
+                if len(arr) <= 2 * rows:
+                    np.copyto(dst[lo:hi], arr)
+                else:  # large blocks: slices over a few threads (the page faults of the fresh array included)
+                    list(_pool().map(lambda r0: np.copyto(dst[lo + r0:min(lo + r0 + rows, hi)], arr[r0:r0 + rows]),
+                                     range(0, len(arr), rows)))
+
+            def one(idx):
+                lo, hi = bounds[idx]
+                w, stream = workers[idx % n_workers]
+                kw = dict(kwargs)
+                for key, ndim in (("init_visits", 3), ("init_model_state", 2)):
+                    if kw.get(key) is not None:
+                        kw[key] = cut(kw[key], lo, hi, ndim)
+                with w._run_lock, torch.cuda.device(dev), torch.cuda.stream(stream):
+                    whole = w.v_table
+                    if whole is not None and whole.shape == (N, X, Y):
+                        w.v_table = whole[lo:hi]
+                    try:
+                        res = w._run({k: cut(v, lo, hi) for k, v in params.items()}, n_steps, cut(init_pos, lo, hi, 2),
+                                     cut(init_ori, lo, hi), cut(init_disc, lo, hi, 2),
+                                     seeds=None if seeds is None else seeds[lo:hi],
+                                     draws=None if draws is None else np.asarray(draws)[lo:hi],
+                                     generators=None if generators is None else list(generators)[lo:hi],
+                                     device_seed=device_seed, n_mice=(hi - lo) if device_seed is not None else None,
+                                     mouse_index_base=base + lo if device_seed is not None else 0, **kw)
+                    finally:
+                        w.v_table = whole
+                shared = {}
+                for name, val in vars(res).items():
+                    if isinstance(val, np.ndarray) and val.ndim >= 1 and val.shape[0] == hi - lo and \
+                            name not in ("occupancy_total", "orientations_histogram_bins"):
+                        place(name, val, lo, hi)
+                    else:  # population-wide values: copied out of the worker's staging buffer
+                        shared[name] = val.copy() if isinstance(val, np.ndarray) else val
+                with lock:
+                    kernel_ms[0] += w.last_kernel_ms or 0.0
+                return shared
+
+            with ThreadPoolExecutor(max_workers=n_workers) as pool:
+                # block i goes to worker i % n_workers: each worker handles its blocks in order, on its own stream
+                futures = [pool.submit(lambda ids: [one(i) for i in ids], list(range(k, len(bounds), n_workers)))
+                           for k in range(n_workers)]
+                shared = [sh for f in futures for sh in f.result()]
+        out = dict(shared[0])
+        if shared[0].get("occupancy_total") is not None:
+            out["occupancy_total"] = np.sum([sh["occupancy_total"] for sh in shared], axis=0)
+        out.update(merged)
+        self.last_kernel_ms = kernel_ms[0]  # sum of the blocks' kernel times (blocks of the two streams overlap)
+        return SimResult(**out)
+
     # -- a population sharded over the GPUs of a box (SURVEY section 8e) -------------------------------------------------
     def run_sharded(self, params, n_steps, init_pos, init_ori=0.0, init_disc=None, seeds=None, draws=None,
                     generators=None, device_seed=None, n_mice=None, group=None, **kwargs):
@@ -664,6 +794,20 @@ class BatchedExperiment:
             vec = t.cpu().numpy()
         n_bins = None if res is None or res.orientations_histogram is None else res.orientations_histogram.shape[1]
         return res, (lo, hi), unpack_population_totals(vec, (X, Y), n_bins)
+
+
+def pipeline_bounds(N, chunks, align=128):
+    """Blocks ``[(lo, hi), ...]`` of :meth:`BatchedExperiment.run_pipelined`: ``chunks`` contiguous blocks of whole CTAs
+    (:func:`shard_bounds_mice`), the first one split 1 : 3 -- the device starts working after a quarter of a block's
+    preparation, and from then on the host threads prepare blocks while another block runs."""
+    chunks = max(1, min(int(chunks), (N + align - 1) // align))
+    bounds = [shard_bounds_mice(N, c, chunks, align) for c in range(chunks)]
+    bounds = [(lo, hi) for lo, hi in bounds if hi > lo]
+    if len(bounds) > 1 and bounds[0][1] - bounds[0][0] >= 4 * align:
+        lo, hi = bounds[0]
+        mid = lo + (((hi - lo) // 4 + align - 1) // align) * align
+        bounds[0:1] = [(lo, mid), (mid, hi)]
+    return bounds
 
 
 def shard_bounds_mice(N, rank, world, align=128):

@@ -86,6 +86,18 @@ def test_run_sharded_world2_gloo():
     assert whole["n_mice"] == 1000 and whole["n_positions"] == 21000 and whole["occupancy_total"].sum() == 1000
 
 
+def test_pipeline_bounds_cover_the_population_in_whole_ctas():
+    from navigation_model_b200.batched_sim import pipeline_bounds
+    for N, chunks in ((1 << 20, 6), (5000, 4), (5000, 64), (700, 3), (100, 4), (128, 2), (1, 6), (1000000, 6)):
+        b = pipeline_bounds(N, chunks)
+        assert b[0][0] == 0 and b[-1][1] == N and all(hi > lo for lo, hi in b)
+        assert all(b[i][1] == b[i + 1][0] for i in range(len(b) - 1))
+        assert all(lo % 128 == 0 for lo, _ in b)          # every block starts on a CTA boundary
+        if len(b) > 2 and b[1][1] - b[0][0] >= 4 * 128:
+            assert b[0][1] - b[0][0] <= (b[1][1] - b[0][0]) // 4 + 128   # the short first block
+    assert pipeline_bounds(100, 4) == [(0, 100)]
+
+
 def test_shard_bounds_mice_cover_the_population():
     from navigation_model_b200.batched_sim import shard_bounds_mice
     for N in (0, 1, 127, 128, 129, 1000, 909312, 10 ** 6):

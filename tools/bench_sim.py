@@ -33,6 +33,8 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--cpu-mice", type=int, default=4)
+    ap.add_argument("--pipelined", type=int, default=0, metavar="CHUNKS", help="run_pipelined with this many blocks")
+    ap.add_argument("--workers", type=int, default=2)
     args = ap.parse_args()
     import torch
     from navigation_model_b200.batched_sim import BatchedExperiment
@@ -55,7 +57,8 @@ def main():
     res = None
     for rep in range(args.reps + 1):
         t0 = time.perf_counter()
-        res = exp.run(P, T, pos0, ori0, init_disc=(1, 1), device_seed=1234 + rep, n_mice=N, occupancy_total=True)
+        run = (lambda *a, **k: exp.run_pipelined(*a, chunks=args.pipelined, workers=args.workers, **k)) if args.pipelined else exp.run
+        res = run(P, T, pos0, ori0, init_disc=(1, 1), device_seed=1234 + rep, n_mice=N, occupancy_total=True)
         torch.cuda.synchronize()
         times.append(time.perf_counter() - t0)
         kernel_ms.append(exp.last_kernel_ms)
