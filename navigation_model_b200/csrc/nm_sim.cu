@@ -34,6 +34,20 @@ namespace {
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 #include "nm_exp.cuh"
 
+// A mouse's biomechanical-cost row comes from L2 every step (64 bytes per mouse: far more per SM than the 28 KB of L1 left
+// beside the shared memory), and read right before its use, behind the `moving` test, that latency was exposed.  The row
+// is therefore read through a plain (non-volatile, side-effect-free) asm load: the compiler may -- and does -- issue the
+// eight loads early in the step, above the branches and the shared-memory asm statements that an ordinary load does not
+// cross (measured: 96.1 -> 94.2 ms per 1M x 1000; an unconditional __ldg in C++ is NOT moved and costs 97.4 ms).  Because
+// the load can run for every mouse of every model, the pointer must always be valid: nm_zero_row stands in when the model
+// has no biomechanical-cost component.
+__device__ const double nm_zero_row[NM_MAX_CAND] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+__device__ __forceinline__ double nm_ldg_early(const double *p) {
+  double v;
+  asm("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+
 constexpr int kA = NM_MAX_CAND;
 constexpr int kSimThreads = 128;
 #ifndef NM_SIM_BCW_GLOBAL
@@ -242,7 +256,7 @@ __global__ void __launch_bounds__(NT, (((sizeof(CntT) == 2 || GMAP) ? NM_SIM_MIN
     }
     double bc_zero = 0.0;  // 0.0 * W_bcost: the component's contribution when the mouse has just moved (:410-413)
     double bc_w = 0.0;
-    const double *bc_row = a.d_bcost_table ? a.d_bcost_table + n * A : nullptr;
+    const double *bc_row = a.d_bcost_table ? a.d_bcost_table + n * A : nm_zero_row;
     if (a.d_bcost_table) {
       const double w = a.d_bcost_weight[n];
       bc_zero = 0.0 * w;
@@ -484,7 +498,7 @@ __global__ void __launch_bounds__(NT, (((sizeof(CntT) == 2 || GMAP) ? NM_SIM_MIN
 #pragma unroll
           for (int i = 0; i < kA; ++i)
 #if NM_SIM_BCW_GLOBAL
-            val[i] = val[i] + (moving ? __ldg(bc_row + (i < A ? i : A - 1)) * bc_w : bc_zero);
+            val[i] = val[i] + (moving ? nm_ldg_early(bc_row + (i < A ? i : A - 1)) * bc_w : bc_zero);
 #else
             val[i] = val[i] + (moving ? nm_lds_f64(a_thr + (5u + (uint32_t)i) * kRow) : bc_zero);
 #endif
