@@ -4,9 +4,12 @@
 //   * one THREAD owns one mouse: pose, softmax policy state, experience map and generator live in
 //     registers / shared memory for the whole run; nothing is written to HBM per step unless a
 //     history is requested;
-//   * the visit-count map is kept in shared memory as count[tile][thread] (u32): one map serves both the
-//     ExperienceComponent (visits so far, behavioural_components.py:456-479) and the fused occupancy
-//     metric (analysis/metrics.py:204-216);
+//   * the visit-count map is kept in shared memory as count[tile][thread] (u16 while n_steps < 65535, else u32; in device
+//     memory for mazes beyond ~50 x 50 tiles): one map serves both the ExperienceComponent (visits so far,
+//     behavioural_components.py:456-479) and the fused occupancy metric (analysis/metrics.py:204-216);
+//   * the per-mouse booleans travel in one register word, the reachability of the eight endpoints is cached per mouse and
+//     the ray walks of the mice that moved are shared by the 32 lanes of the warp; the reference's standard
+//     five-component model has its own instantiation with straight-line component bodies (kStdWord);
 //   * the maze tile table is staged once per CTA into shared memory; the ray / AABB walk reads it there;
 //   * random draws are either replayed (`draws[T, N]`, coalesced) or generated on the device with a
 //     numpy-identical PCG64 (XSL-RR 128/64) from host-computed (state, inc).
